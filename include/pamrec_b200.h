@@ -1,0 +1,148 @@
+/*
+ * pamrec_b200 — C ABI of the B200-native PAMRec train / score step.
+ *
+ * This is the drop-in boundary for the reference's device work.  The reference has no
+ * FFI: its "device" is a TensorFlow session, and the calls this library replaces are the
+ * three `sess.run` sites plus the graph construction they depend on (all paths relative
+ * to the reference root, reco_utils/recommender/deeprec/...):
+ *
+ *   pamrec_train_step   <->  PAMRECModel.train            models/sequential/pamrec.py:426-453
+ *                            (update + BN moving stats + 5 loss scalars in one run)
+ *   pamrec_forward      <->  SequentialBaseModel.eval_with_user / eval / infer
+ *                            models/sequential/sequential_base_model.py:502-516, 415-418, 557-560
+ *   pamrec_create/bind  <->  BaseModel.__init__ graph + session bootstrap, models/base_model.py:20-75
+ *   PamrecBatch         <->  SequentialIterator.gen_feed_dict, io/sequential_iterator.py:1143-1181
+ *   parameter inventory <->  tf.get_variable sites
+ *
+ * Conventions: plain C, no exceptions, int return (0 = ok, <0 = error, text through
+ * pamrec_last_error).  The CALLER owns every device buffer (the Python host allocates
+ * them with torch); the library owns nothing on the device, never frees caller memory
+ * and keeps no hidden global state (one handle per stream / thread).  Every launch goes
+ * to the `stream` argument (a cudaStream_t passed as void*).  All tensors are row-major,
+ * contiguous; ids are int32, values fp32.
+ */
+#ifndef PAMREC_B200_H_
+#define PAMREC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAMREC_ITEM_DIM 16
+#define PAMREC_CATE_DIM 4
+#define PAMREC_USER_DIM 20
+#define PAMREC_EMB_DIM 20   /* item + cate */
+#define PAMREC_D 40         /* model width = 2 * (item + cate), pamrec.py:144,523 */
+#define PAMREC_NBUCKET 10   /* rows of the time-aware Q/K/V tables, pamrec.py:699-713 */
+#define PAMREC_GROUP 5      /* listwise group, pamrec.py:73-75 */
+#define PAMREC_MAX_T 256
+
+typedef struct PamrecHandle_* PamrecHandle;
+
+/* sparse (embedding-table) Adam flavours, SURVEY.md section 7 H2 */
+enum { PAMREC_ADAM_DENSE_EXACT = 0, /* tf.train.AdamOptimizer: decay + update EVERY row     */
+       PAMREC_ADAM_LAZY = 1 };      /* touched rows only (tf.contrib.opt.LazyAdamOptimizer) */
+
+typedef struct PamrecConfig {
+  int32_t n_users, n_items, n_cates; /* vocabulary sizes = table rows (sequential_base_model.py:565-567) */
+  int32_t max_seq_len;               /* T, hparams.max_seq_length                                       */
+  int32_t max_batch;                 /* capacity B; training batches must be multiples of PAMREC_GROUP   */
+  float learning_rate, beta1, beta2, epsilon; /* tf.train.AdamOptimizer(lr), base_model.py:270-271      */
+  float embed_l2, layer_l2;          /* base_model.py:122-134                                           */
+  float max_grad_norm;               /* per-tensor tf.clip_by_norm, base_model.py:297-303               */
+  int32_t is_clip_norm;
+  float fuzhu_weight;                /* pamrec.py:106                                                   */
+  float order_weight;                /* hparams.discrepancy_loss_weight, pamrec.py:79                   */
+  int32_t sparse_adam_mode;          /* PAMREC_ADAM_*                                                   */
+  /* data parallel (one process per GPU): this rank's share of one global batch.  With
+   * world_size > 1 the host all-reduces the buffers named by pamrec_sync_info between
+   * phases; single GPU uses pamrec_train_step.                                          */
+  int32_t world_size, rank;
+} PamrecConfig;
+
+/* One batch, device pointers (layouts of io/sequential_iterator.py:1111-1135). */
+typedef struct PamrecBatch {
+  int32_t batch;                      /* B rows in this batch (<= max_batch)                   */
+  const int32_t* item_history;        /* [B,T]                                                 */
+  const int32_t* item_cate_history;   /* [B,T]                                                 */
+  const float* item_loop_times_history; /* [B,T] play-ratio bucket as float; cast like pamrec.py:716 */
+  const int32_t* mask;                /* [B,T] 1 = real position                               */
+  const int32_t* users;               /* [B]                                                   */
+  const int32_t* items;               /* [B]                                                   */
+  const int32_t* cates;               /* [B]                                                   */
+  const float* labels_satisfied;      /* [B]  (train only)                                     */
+  const float* labels_play;           /* [B]  (train only)                                     */
+  const float* plays;                 /* [B]  bucket index as float (train only)               */
+} PamrecBatch;
+
+/* Caller-owned device memory handed to the library once. */
+typedef struct PamrecBuffers {
+  float* dense_param; float* dense_grad; float* dense_m; float* dense_v; /* [dense_numel] each      */
+  float* bn_moving;                                                      /* [bn_numel] mean|var sets */
+  float* item_w; float* item_m; float* item_v;                           /* [n_items,16]            */
+  float* cate_w; float* cate_m; float* cate_v;                           /* [n_cates,4]             */
+  float* ulong_w; float* ulong_m; float* ulong_v;                        /* [n_users,20]            */
+  float* ushort_w; float* ushort_m; float* ushort_v;                     /* [n_users,20]            */
+  void* workspace; size_t workspace_bytes;                               /* >= pamrec_workspace_bytes */
+} PamrecBuffers;
+
+/* Named slice of one of the caller's pools. */
+enum { PAMREC_POOL_DENSE = 0, PAMREC_POOL_BN = 1, PAMREC_POOL_WORKSPACE = 2 };
+enum { PAMREC_F32 = 0, PAMREC_I32 = 1, PAMREC_F64 = 2, PAMREC_U8 = 3 };
+enum { PAMREC_SEG_L2 = 1,        /* in layer_params: gets layer_l2 (sequential_base_model.py:714-721) */
+       PAMREC_SEG_POS = 2,       /* position table: sparse-style clip norm, no L2                     */
+       PAMREC_SEG_DEAD = 4 };    /* never reaches the logits: gradient is the L2 term only            */
+typedef struct PamrecTensorInfo {
+  char name[160];     /* TF variable name (dense / bn pools) or workspace tensor name */
+  int32_t pool, dtype, flags;
+  int64_t offset;     /* element offset inside the pool (bytes for the workspace pool) */
+  int64_t numel;
+  int32_t ndim; int64_t shape[4];
+} PamrecTensorInfo;
+
+const char* pamrec_version(void);
+
+/* Host-only: allowed without a GPU. */
+int pamrec_create(const PamrecConfig* cfg, PamrecHandle* out);
+int pamrec_destroy(PamrecHandle h);
+const char* pamrec_last_error(PamrecHandle h);
+int64_t pamrec_dense_numel(PamrecHandle h);
+int64_t pamrec_bn_numel(PamrecHandle h);
+size_t pamrec_workspace_bytes(PamrecHandle h);
+int pamrec_tensor_count(PamrecHandle h, int pool);
+int pamrec_tensor_info(PamrecHandle h, int pool, int index, PamrecTensorInfo* out);
+
+/* Device entry points. */
+int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream);
+/* gather only: x0[B,T,40] = item|cate|target + position (sequential_base_model.py:603-616,666-668; pamrec.py:155-159,251-257) */
+int pamrec_gather_fwd(PamrecHandle h, const PamrecBatch* b, float* x0_out, void* stream);
+/* forward; training=0 -> BN moving stats (eval_with_user), writes sigmoid(logit) to pred_out[B] if non-null */
+int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pred_out, void* stream);
+/* losses + backward into dense_grad / workspace (requires pamrec_forward(training=1) on the same batch) */
+int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream);
+/* per-tensor clip + Adam on dense and sparse variables; `step` is 1-based (beta powers) */
+int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, void* stream);
+/* forward + backward + apply; losses_out (device, 5 floats): loss, data, regular, auxiliary, order (pamrec.py:444-448) */
+int pamrec_train_step(PamrecHandle h, const PamrecBatch* b, int64_t step, float* losses_out, void* stream);
+
+/* Data-parallel phases (world_size > 1): the host runs an NCCL all-reduce(sum) on the
+ * workspace tensor named by `sync_name` after each phase returns 1, then calls the next
+ * phase; returns 0 when the step is complete.  Phase ids are opaque and sequential. */
+int pamrec_train_phase(PamrecHandle h, const PamrecBatch* b, int64_t step, int phase, float* losses_out,
+                       char sync_name[160], void* stream);
+
+/* Stand-alone HBM kernels for roofline measurement (same kernels the step uses). */
+int pamrec_bench_gather(PamrecHandle h, const int32_t* item_ids, const int32_t* cate_ids, const int32_t* tgt_items,
+                        const int32_t* tgt_cates, int64_t n_rows, int32_t T, float* out, void* stream);
+int pamrec_bench_table_adam(PamrecHandle h, int64_t step, void* stream);
+
+/* number of kernel launches issued by the last device call on this handle */
+int64_t pamrec_last_launch_count(PamrecHandle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAMREC_B200_H_ */

@@ -1,0 +1,560 @@
+// C ABI of libpamrec_b200.so (see include/pamrec_b200.h): handle, inventory queries and the
+// orchestration of one train / score step as a sequence of kernel launches on the caller's stream.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "layout.h"
+
+namespace pamrec {
+void launch_slot_reset(const SparseTable& t, int64_t n_keys, cudaStream_t st);
+}
+using namespace pamrec;
+
+struct PamrecHandle_ {
+  PamrecConfig cfg;
+  Layout L;
+  PamrecBuffers buf;
+  bool bound = false;
+  std::string err;
+  int64_t launches = 0;
+  BnSet bn[BN_COUNT];
+  std::vector<int> h_seg_id, h_seg_tab;
+
+  float* P(int64_t off) const { return buf.dense_param + off; }
+  float* G(int64_t off) const { return buf.dense_grad + off; }
+  template <typename T>
+  T* ws(const std::string& name) const { return reinterpret_cast<T*>(static_cast<char*>(buf.workspace) + L.ws_off(name)); }
+  float* wf(const std::string& name) const { return ws<float>(name); }
+  int* wi(const std::string& name) const { return ws<int>(name); }
+  double* wd(const std::string& name) const { return ws<double>(name); }
+};
+
+static int fail(PamrecHandle h, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return -1;
+}
+static int check_cuda(PamrecHandle h, const char* where) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, "%s: %s", where, cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" {
+
+const char* pamrec_version(void) { return "pamrec_b200 0.1 (sm_100a)"; }
+
+int pamrec_create(const PamrecConfig* cfg, PamrecHandle* out) {
+  if (!cfg || !out) return -1;
+  *out = nullptr;
+  if (cfg->n_users < 1 || cfg->n_items < 1 || cfg->n_cates < 1) return -2;
+  if (cfg->max_seq_len < 1 || cfg->max_seq_len > PAMREC_MAX_T) return -3;
+  if (cfg->max_batch < 1) return -4;
+  PamrecHandle h = new PamrecHandle_();
+  h->cfg = *cfg;
+  if (h->cfg.world_size < 1) h->cfg.world_size = 1;
+  h->L.build(h->cfg);
+  const int n_seg = (int)h->L.dense.size();
+  h->h_seg_id.assign((size_t)h->L.dense_numel, 0);
+  h->h_seg_tab.assign((size_t)n_seg * 4, 0);
+  for (int s = 0; s < n_seg; ++s) {
+    const TensorDesc& t = h->L.dense[s];
+    h->h_seg_tab[4 * s] = (int)t.offset;
+    h->h_seg_tab[4 * s + 1] = (int)t.numel;
+    h->h_seg_tab[4 * s + 2] = t.flags;
+    for (int64_t i = 0; i < t.numel; ++i) h->h_seg_id[(size_t)(t.offset + i)] = s;
+  }
+  *out = h;
+  return 0;
+}
+
+int pamrec_destroy(PamrecHandle h) {
+  delete h;
+  return 0;
+}
+const char* pamrec_last_error(PamrecHandle h) { return h ? h->err.c_str() : "null handle"; }
+int64_t pamrec_dense_numel(PamrecHandle h) { return h ? h->L.dense_numel : -1; }
+int64_t pamrec_bn_numel(PamrecHandle h) { return h ? h->L.bn_numel : -1; }
+size_t pamrec_workspace_bytes(PamrecHandle h) { return h ? h->L.ws_bytes : 0; }
+int64_t pamrec_last_launch_count(PamrecHandle h) { return h ? h->launches : -1; }
+
+static const std::vector<TensorDesc>* pool_of(PamrecHandle h, int pool) {
+  if (!h) return nullptr;
+  if (pool == PAMREC_POOL_DENSE) return &h->L.dense;
+  if (pool == PAMREC_POOL_BN) return &h->L.bn;
+  if (pool == PAMREC_POOL_WORKSPACE) return &h->L.ws;
+  return nullptr;
+}
+int pamrec_tensor_count(PamrecHandle h, int pool) {
+  auto* v = pool_of(h, pool);
+  return v ? (int)v->size() : -1;
+}
+int pamrec_tensor_info(PamrecHandle h, int pool, int index, PamrecTensorInfo* out) {
+  auto* v = pool_of(h, pool);
+  if (!v || !out || index < 0 || index >= (int)v->size()) return -1;
+  const TensorDesc& t = (*v)[index];
+  memset(out, 0, sizeof *out);
+  snprintf(out->name, sizeof out->name, "%s", t.name.c_str());
+  out->pool = t.pool; out->dtype = t.dtype; out->flags = t.flags;
+  out->offset = t.offset; out->numel = t.numel; out->ndim = t.ndim;
+  for (int i = 0; i < 4; ++i) out->shape[i] = t.shape[i];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+static BnSet make_bn(PamrecHandle h, int id, const char* name) {
+  const BnOff& o = h->L.bnoff[id];
+  BnSet s;
+  s.C = o.C;
+  s.gamma = h->P(o.gamma); s.beta = h->P(o.beta);
+  s.dgamma = h->G(o.gamma); s.dbeta = h->G(o.beta);
+  s.mmean = h->buf.bn_moving + o.mm; s.mvar = h->buf.bn_moving + o.mv;
+  std::string p = std::string("bn.") + name;
+  s.sums = h->wd(p + ".sums"); s.stat = h->wf(p + ".stat"); s.bsums = h->wd(p + ".bsums");
+  return s;
+}
+
+int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
+  if (!h || !bufs) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bufs->workspace_bytes < h->L.ws_bytes) return fail(h, "workspace too small: %zu < %zu", bufs->workspace_bytes, h->L.ws_bytes);
+  if (!bufs->dense_param || !bufs->dense_grad || !bufs->dense_m || !bufs->dense_v || !bufs->bn_moving || !bufs->item_w ||
+      !bufs->cate_w || !bufs->ulong_w || !bufs->ushort_w || !bufs->workspace)
+    return fail(h, "null buffer");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(h, "no CUDA device: the CUDA path is the only path"); }
+  h->buf = *bufs;
+  static const char* names[BN_COUNT] = {"s0", "s1", "e0", "g0", "e1", "g1", "t0", "t1"};
+  for (int i = 0; i < BN_COUNT; ++i) h->bn[i] = make_bn(h, i, names[i]);
+  const int64_t NK = (int64_t)h->cfg.max_batch * h->cfg.max_seq_len + h->cfg.max_batch;
+  size_t need = sparse_temp_bytes(NK);
+  size_t have = (size_t)h->L.ws[h->L.ws_index["cub_temp"]].numel;
+  if (need > have) return fail(h, "cub temp storage: need %zu have %zu", need, have);
+  cudaMemsetAsync(h->buf.workspace, 0, h->L.ws_bytes, st);
+  cudaMemsetAsync(h->wi("sp.item.slot"), 0xFF, (size_t)h->cfg.n_items * 4, st);
+  cudaMemsetAsync(h->wi("sp.cate.slot"), 0xFF, (size_t)h->cfg.n_cates * 4, st);
+  cudaMemsetAsync(h->wi("sp.user.slot"), 0xFF, (size_t)h->cfg.n_users * 4, st);
+  cudaMemcpyAsync(h->wi("seg_id"), h->h_seg_id.data(), h->h_seg_id.size() * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(h->wi("seg_tab"), h->h_seg_tab.data(), h->h_seg_tab.size() * 4, cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);
+  h->bound = true;
+  return check_cuda(h, "bind");
+}
+
+static int check_batch(PamrecHandle h, const PamrecBatch* b, bool training) {
+  if (!h) return -1;
+  if (!h->bound) return fail(h, "pamrec_bind has not been called");
+  if (!b) return fail(h, "null batch");
+  if (b->batch < 1 || b->batch > h->cfg.max_batch) return fail(h, "batch %d outside [1, %d]", b->batch, h->cfg.max_batch);
+  if (training && b->batch % PAMREC_GROUP != 0)
+    return fail(h, "training batch %d is not a multiple of %d (pamrec.py:73-75)", b->batch, PAMREC_GROUP);
+  if (!b->item_history || !b->item_cate_history || !b->item_loop_times_history || !b->mask || !b->items || !b->cates)
+    return fail(h, "null batch field");
+  if (training && (!b->users || !b->labels_satisfied || !b->labels_play || !b->plays)) return fail(h, "null label field");
+  return 0;
+}
+
+int pamrec_gather_fwd(PamrecHandle h, const PamrecBatch* b, float* x0_out, void* stream) {
+  if (int rc = check_batch(h, b, false)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  h->launches = 1;
+  launch_embed_fwd(b->item_history, b->item_cate_history, b->items, b->cates, h->buf.item_w, h->buf.cate_w, h->P(h->L.pos),
+                   x0_out ? x0_out : h->wf("x0"), h->wf("tgt"), b->batch, h->cfg.max_seq_len, st);
+  return check_cuda(h, "gather_fwd");
+}
+
+static DenseP dense_p(const float* X, int ldx, int M, int groups, int K, int N, const float* W, int ws, const float* bias,
+                      int bs, float* Z, int ldz) {
+  DenseP p;
+  memset(&p, 0, sizeof p);
+  p.X = X; p.ldx = ldx; p.M = M; p.n_groups = groups; p.K = K; p.N = N;
+  p.W = W; p.w_stride = ws; p.bias = bias; p.b_stride = bs; p.Z = Z; p.ldz = ldz;
+  return p;
+}
+static void set_in_bn(DenseP& p, const BnSet& s) { p.in_stat = s.stat; p.in_gamma = s.gamma; p.in_beta = s.beta; }
+static void set_in_bn_dw(DenseDwP& p, const BnSet& s) { p.in_stat = s.stat; p.in_gamma = s.gamma; p.in_beta = s.beta; }
+
+int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pred_out, void* stream) {
+  if (int rc = check_batch(h, b, training != 0)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const Layout& L = h->L;
+  const int B = b->batch, T = h->cfg.max_seq_len, N = B * T;
+  const int W = h->cfg.world_size;
+  const double cntN = (double)N * W, cntB = (double)B * W;
+  int64_t nl = 0;
+  float* x0 = h->wf("x0");
+  launch_embed_fwd(b->item_history, b->item_cate_history, b->items, b->cates, h->buf.item_w, h->buf.cate_w, h->P(L.pos), x0,
+                   h->wf("tgt"), B, T, st); nl += 1;
+  int* ctl = h->wi("bucket_ctl");
+  launch_bucket_plan(b->item_loop_times_history, N, h->wi("bucket"), h->wi("perm"), ctl, h->wi("tile_bucket"),
+                     h->wi("tile_begin"), h->wi("tile_count"), st); nl += 3;
+  const int max_tiles = N / kTokTile + kNB + 1;
+  const float* xin = x0;
+  for (int k = 0; k < 2; ++k) {
+    const BlockOff& o = L.blk[k];
+    std::string p = "blk" + std::to_string(k) + ".";
+    launch_proj_fwd(xin, h->wi("perm"), ctl, h->wi("tile_bucket"), h->wi("tile_begin"), h->wi("tile_count"), max_tiles,
+                    h->P(o.wq), h->P(o.wk), h->P(o.wv), h->P(o.ln_a_beta), h->P(o.ln_a_gamma), h->wf(p + "qin"), h->wf(p + "Q"),
+                    h->wf(p + "K"), h->wf(p + "V"), st);
+    launch_attn_fwd(h->wf(p + "Q"), h->wf(p + "K"), h->wf(p + "V"), h->wf(p + "qin"), b->mask, h->wf(p + "y"), B, T, st);
+    launch_ffn_fwd(h->wf(p + "y"), h->P(o.w1), h->P(o.b1), h->P(o.w2), h->P(o.b2), h->P(o.ln_b_beta), h->P(o.ln_b_gamma),
+                   h->wf(p + "out"), N, st);
+    nl += 3;
+    xin = h->wf(p + "out");
+  }
+  const float* H = xin;
+  BnSet* bn = h->bn;
+  if (!training) {
+    for (int i = 0; i < BN_COUNT; ++i) launch_bn_eval_stat(bn[i], st);
+    nl += BN_COUNT;
+  }
+  auto fin = [&](int id, double cnt) {
+    if (training) { launch_bn_finalize(bn[id], cnt, st); nl += 1; }
+  };
+  // attention pooling score MLP (pamrec.py:273)
+  {
+    DenseP p = dense_p(H, kD, N, 1, kD, 20, h->P(L.score.w0), 0, h->P(L.score.b0), 0, h->wf("z1"), 20);
+    p.out_sums = training ? bn[BN_S0].sums : nullptr;
+    launch_dense_fwd(p, st); nl += 1;
+    fin(BN_S0, cntN);
+    DenseP q = dense_p(h->wf("z1"), 20, N, 1, 20, 1, h->P(L.score.w1), 0, h->P(L.score.b1), 0, h->wf("z2"), 1);
+    set_in_bn(q, bn[BN_S0]);
+    q.out_sums = training ? bn[BN_S1].sums : nullptr;
+    launch_dense_fwd(q, st); nl += 1;
+    fin(BN_S1, cntN);
+  }
+  launch_pool_fwd(H, h->wf("z2"), bn[BN_S1], b->mask, h->wf("new_long"), B, T, st); nl += 1;
+  // MMoE (pamrec.py:26-50)
+  {
+    DenseP e0 = dense_p(h->wf("new_long"), kD, B, 5, kD, 100, h->P(L.expert.w0), 4000, h->P(L.expert.b0), 100, h->wf("ze0"), 500);
+    for (int g = 0; g < 5; ++g) { e0.x_off[g] = 0; e0.z_off[g] = g * 100; }
+    e0.out_sums = training ? bn[BN_E0].sums : nullptr;
+    launch_dense_fwd(e0, st);
+    DenseP g0 = dense_p(h->wf("new_long"), kD, B, 2, kD, 64, h->P(L.gate.w0), 2560, h->P(L.gate.b0), 64, h->wf("zg0"), 128);
+    for (int g = 0; g < 2; ++g) { g0.x_off[g] = 0; g0.z_off[g] = g * 64; }
+    g0.out_sums = training ? bn[BN_G0].sums : nullptr;
+    launch_dense_fwd(g0, st);
+    nl += 2;
+    fin(BN_E0, cntB); fin(BN_G0, cntB);
+    DenseP e1 = dense_p(h->wf("ze0"), 500, B, 5, 100, 64, h->P(L.expert.w1), 6400, h->P(L.expert.b1), 64, h->wf("ze1"), 320);
+    for (int g = 0; g < 5; ++g) { e1.x_off[g] = g * 100; e1.z_off[g] = g * 64; }
+    set_in_bn(e1, bn[BN_E0]);
+    e1.out_sums = training ? bn[BN_E1].sums : nullptr;
+    launch_dense_fwd(e1, st);
+    DenseP g1 = dense_p(h->wf("zg0"), 128, B, 2, 64, 5, h->P(L.gate.w1), 320, h->P(L.gate.b1), 5, h->wf("zg1"), 10);
+    for (int g = 0; g < 2; ++g) { g1.x_off[g] = g * 64; g1.z_off[g] = g * 5; }
+    set_in_bn(g1, bn[BN_G0]);
+    g1.out_sums = training ? bn[BN_G1].sums : nullptr;
+    launch_dense_fwd(g1, st);
+    nl += 2;
+    fin(BN_E1, cntB); fin(BN_G1, cntB);
+  }
+  launch_combine_fwd(h->wf("ze1"), h->wf("zg1"), bn[BN_E1], bn[BN_G1], h->wf("tgt"), h->wf("u"), B, st); nl += 1;
+  // towers: logit_fcn(main|tgt), valid_logit_fcn(sub|tgt), xilidu_logit_fcn(main|tgt)   pamrec.py:212-215, 71
+  {
+    DenseP t0 = dense_p(h->wf("u"), 168, B, 3, 84, 100, h->P(L.tower.w0), 8400, h->P(L.tower.b0), 100, h->wf("zt0"), 300);
+    t0.x_off[0] = 0; t0.x_off[1] = 84; t0.x_off[2] = 0;
+    for (int g = 0; g < 3; ++g) t0.z_off[g] = g * 100;
+    t0.out_sums = training ? bn[BN_T0].sums : nullptr;
+    launch_dense_fwd(t0, st); nl += 1;
+    fin(BN_T0, cntB);
+    DenseP t1 = dense_p(h->wf("zt0"), 300, B, 3, 100, 64, h->P(L.tower.w1), 6400, h->P(L.tower.b1), 64, h->wf("zt1"), 192);
+    for (int g = 0; g < 3; ++g) { t1.x_off[g] = g * 100; t1.z_off[g] = g * 64; }
+    set_in_bn(t1, bn[BN_T0]);
+    t1.out_sums = training ? bn[BN_T1].sums : nullptr;
+    launch_dense_fwd(t1, st); nl += 1;
+    fin(BN_T1, cntB);
+    DenseP to = dense_p(h->wf("zt1"), 192, B, 3, 64, 1, h->P(L.tower.wout), 64, h->P(L.tower.bout), 1, h->wf("logits"), 3);
+    for (int g = 0; g < 3; ++g) { to.x_off[g] = g * 64; to.z_off[g] = g; }
+    set_in_bn(to, bn[BN_T1]);
+    launch_dense_fwd(to, st); nl += 1;
+  }
+  if (pred_out) { launch_sigmoid_col0(h->wf("logits"), pred_out, B, st); nl += 1; }
+  h->launches = nl;
+  return check_cuda(h, "forward");
+}
+
+// ------------------------------------------------------------------------------------------
+static DenseDwP dw_p(const float* X, int ldx, int M, int groups, int K, int N, const float* dZ, int lddz, float* dW, int ws,
+                     float* db, int bs) {
+  DenseDwP p;
+  memset(&p, 0, sizeof p);
+  p.X = X; p.ldx = ldx; p.M = M; p.n_groups = groups; p.K = K; p.N = N; p.dZ = dZ; p.lddz = lddz;
+  p.dW = dW; p.w_stride = ws; p.db = db; p.b_stride = bs;
+  return p;
+}
+static DenseDxP dx_p(const float* dZ, int lddz, int M, int K, const float* Wbase, float* dX, int lddx, int accumulate) {
+  DenseDxP p;
+  memset(&p, 0, sizeof p);
+  p.dZ = dZ; p.lddz = lddz; p.M = M; p.K = K; p.Wbase = Wbase; p.dX = dX; p.lddx = lddx; p.accumulate = accumulate;
+  return p;
+}
+static void dx_add(DenseDxP& p, int slice, int out_off, int dz_off, int64_t w_off, int N) {
+  if (slice >= p.n_slices) { p.n_slices = slice + 1; p.out_off[slice] = out_off; p.n_contrib[slice] = 0; }
+  int c = p.n_contrib[slice]++;
+  p.dz_off[slice][c] = dz_off; p.w_off[slice][c] = w_off; p.Ncon[slice][c] = N;
+}
+
+int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
+  if (int rc = check_batch(h, b, true)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const Layout& L = h->L;
+  const int B = b->batch, T = h->cfg.max_seq_len, N = B * T;
+  const int W = h->cfg.world_size;
+  const double cntN = (double)N * W, cntB = (double)B * W;
+  const float gs = 1.0f / (float)W;
+  BnSet* bn = h->bn;
+  int64_t nl = 0;
+  const float* Pb = h->buf.dense_param;
+  cudaMemsetAsync(h->buf.dense_grad, 0, (size_t)L.dense_numel * 4, st);
+  cudaMemsetAsync(h->wd("loss_acc"), 0, 8 * sizeof(double), st);
+  cudaMemsetAsync(h->wd("sp_normsq"), 0, 8 * sizeof(double), st);
+  launch_loss(h->wf("logits"), b->labels_satisfied, b->labels_play, b->plays, h->wf("d_logits"), h->wd("loss_acc"), B, B * W,
+              W > 1 ? -2 : -1, h->cfg.fuzhu_weight, h->cfg.order_weight, st); nl += 1;
+  auto bn_bwd = [&](int id, float* dA, const float* Z, int M, double cnt) {
+    launch_bn_bwd_stats(bn[id], dA, Z, M, st);
+    launch_bn_bwd_apply(bn[id], dA, Z, M, cnt, gs, st);
+    nl += 3;
+  };
+  // ---- towers
+  {
+    DenseDwP w = dw_p(h->wf("zt1"), 192, B, 3, 64, 1, h->wf("d_logits"), 3, h->G(L.tower.wout), 64, h->G(L.tower.bout), 1);
+    for (int g = 0; g < 3; ++g) { w.x_off[g] = g * 64; w.z_off[g] = g; }
+    set_in_bn_dw(w, bn[BN_T1]);
+    launch_dense_dw(w, st);
+    DenseDxP x = dx_p(h->wf("d_logits"), 3, B, 64, Pb, h->wf("d_t1"), 192, 0);
+    for (int g = 0; g < 3; ++g) dx_add(x, g, g * 64, g, L.tower.wout + g * 64, 1);
+    launch_dense_dx(x, st);
+    nl += 2;
+    bn_bwd(BN_T1, h->wf("d_t1"), h->wf("zt1"), B, cntB);
+    DenseDwP w1 = dw_p(h->wf("zt0"), 300, B, 3, 100, 64, h->wf("d_t1"), 192, h->G(L.tower.w1), 6400, h->G(L.tower.b1), 64);
+    for (int g = 0; g < 3; ++g) { w1.x_off[g] = g * 100; w1.z_off[g] = g * 64; }
+    set_in_bn_dw(w1, bn[BN_T0]);
+    launch_dense_dw(w1, st);
+    DenseDxP x1 = dx_p(h->wf("d_t1"), 192, B, 100, Pb, h->wf("d_t0"), 300, 0);
+    for (int g = 0; g < 3; ++g) dx_add(x1, g, g * 100, g * 64, L.tower.w1 + (int64_t)g * 6400, 64);
+    launch_dense_dx(x1, st);
+    nl += 2;
+    bn_bwd(BN_T0, h->wf("d_t0"), h->wf("zt0"), B, cntB);
+    DenseDwP w0 = dw_p(h->wf("u"), 168, B, 3, 84, 100, h->wf("d_t0"), 300, h->G(L.tower.w0), 8400, h->G(L.tower.b0), 100);
+    w0.x_off[0] = 0; w0.x_off[1] = 84; w0.x_off[2] = 0;
+    for (int g = 0; g < 3; ++g) w0.z_off[g] = g * 100;
+    launch_dense_dw(w0, st);
+    DenseDxP x0 = dx_p(h->wf("d_t0"), 300, B, 84, Pb, h->wf("d_u"), 168, 0);
+    dx_add(x0, 0, 0, 0, L.tower.w0, 100);
+    dx_add(x0, 0, 0, 200, L.tower.w0 + 2 * 8400, 100);
+    dx_add(x0, 1, 84, 100, L.tower.w0 + 8400, 100);
+    launch_dense_dx(x0, st);
+    nl += 2;
+  }
+  launch_combine_bwd(h->wf("ze1"), h->wf("zg1"), bn[BN_E1], bn[BN_G1], h->wf("d_u"), h->wf("d_e1"), h->wf("d_g1"),
+                     h->wf("d_tgt"), B, st); nl += 1;
+  // ---- MMoE
+  {
+    bn_bwd(BN_E1, h->wf("d_e1"), h->wf("ze1"), B, cntB);
+    bn_bwd(BN_G1, h->wf("d_g1"), h->wf("zg1"), B, cntB);
+    DenseDwP we = dw_p(h->wf("ze0"), 500, B, 5, 100, 64, h->wf("d_e1"), 320, h->G(L.expert.w1), 6400, h->G(L.expert.b1), 64);
+    for (int g = 0; g < 5; ++g) { we.x_off[g] = g * 100; we.z_off[g] = g * 64; }
+    set_in_bn_dw(we, bn[BN_E0]);
+    launch_dense_dw(we, st);
+    DenseDxP xe = dx_p(h->wf("d_e1"), 320, B, 100, Pb, h->wf("d_e0"), 500, 0);
+    for (int g = 0; g < 5; ++g) dx_add(xe, g, g * 100, g * 64, L.expert.w1 + (int64_t)g * 6400, 64);
+    launch_dense_dx(xe, st);
+    DenseDwP wg = dw_p(h->wf("zg0"), 128, B, 2, 64, 5, h->wf("d_g1"), 10, h->G(L.gate.w1), 320, h->G(L.gate.b1), 5);
+    for (int g = 0; g < 2; ++g) { wg.x_off[g] = g * 64; wg.z_off[g] = g * 5; }
+    set_in_bn_dw(wg, bn[BN_G0]);
+    launch_dense_dw(wg, st);
+    DenseDxP xg = dx_p(h->wf("d_g1"), 10, B, 64, Pb, h->wf("d_g0"), 128, 0);
+    for (int g = 0; g < 2; ++g) dx_add(xg, g, g * 64, g * 5, L.gate.w1 + (int64_t)g * 320, 5);
+    launch_dense_dx(xg, st);
+    nl += 4;
+    bn_bwd(BN_E0, h->wf("d_e0"), h->wf("ze0"), B, cntB);
+    bn_bwd(BN_G0, h->wf("d_g0"), h->wf("zg0"), B, cntB);
+    DenseDwP we0 = dw_p(h->wf("new_long"), kD, B, 5, kD, 100, h->wf("d_e0"), 500, h->G(L.expert.w0), 4000, h->G(L.expert.b0), 100);
+    for (int g = 0; g < 5; ++g) { we0.x_off[g] = 0; we0.z_off[g] = g * 100; }
+    launch_dense_dw(we0, st);
+    DenseDwP wg0 = dw_p(h->wf("new_long"), kD, B, 2, kD, 64, h->wf("d_g0"), 128, h->G(L.gate.w0), 2560, h->G(L.gate.b0), 64);
+    for (int g = 0; g < 2; ++g) { wg0.x_off[g] = 0; wg0.z_off[g] = g * 64; }
+    launch_dense_dw(wg0, st);
+    DenseDxP xe0 = dx_p(h->wf("d_e0"), 500, B, kD, Pb, h->wf("d_new_long"), kD, 0);
+    for (int g = 0; g < 5; ++g) dx_add(xe0, 0, 0, g * 100, L.expert.w0 + (int64_t)g * 4000, 100);
+    launch_dense_dx(xe0, st);
+    DenseDxP xg0 = dx_p(h->wf("d_g0"), 128, B, kD, Pb, h->wf("d_new_long"), kD, 1);
+    for (int g = 0; g < 2; ++g) dx_add(xg0, 0, 0, g * 64, L.gate.w0 + (int64_t)g * 2560, 64);
+    launch_dense_dx(xg0, st);
+    nl += 4;
+  }
+  // ---- attention pooling
+  const float* H = h->wf("blk1.out");
+  float* g_a = h->wf("g_a");
+  float* g_b = h->wf("g_b");
+  {
+    launch_pool_bwd(H, h->wf("z2"), bn[BN_S1], b->mask, h->wf("d_new_long"), h->wf("d_z2"), g_a, B, T, st); nl += 1;
+    bn_bwd(BN_S1, h->wf("d_z2"), h->wf("z2"), N, cntN);
+    DenseDwP w1 = dw_p(h->wf("z1"), 20, N, 1, 20, 1, h->wf("d_z2"), 1, h->G(L.score.w1), 0, h->G(L.score.b1), 0);
+    set_in_bn_dw(w1, bn[BN_S0]);
+    launch_dense_dw(w1, st);
+    DenseDxP x1 = dx_p(h->wf("d_z2"), 1, N, 20, Pb, h->wf("d_a1"), 20, 0);
+    dx_add(x1, 0, 0, 0, L.score.w1, 1);
+    launch_dense_dx(x1, st);
+    nl += 2;
+    bn_bwd(BN_S0, h->wf("d_a1"), h->wf("z1"), N, cntN);
+    DenseDwP w0 = dw_p(H, kD, N, 1, kD, 20, h->wf("d_a1"), 20, h->G(L.score.w0), 0, h->G(L.score.b0), 0);
+    launch_dense_dw(w0, st);
+    DenseDxP x0 = dx_p(h->wf("d_a1"), 20, N, kD, Pb, g_a, kD, 1);
+    dx_add(x0, 0, 0, 0, L.score.w0, 20);
+    launch_dense_dx(x0, st);
+    nl += 2;
+  }
+  // ---- encoder blocks (grad of blk1.out is in g_a)
+  const int max_tiles = N / kTokTile + kNB + 1;
+  int* ctl = h->wi("bucket_ctl");
+  for (int k = 1; k >= 0; --k) {
+    const BlockOff& o = L.blk[k];
+    std::string p = "blk" + std::to_string(k) + ".";
+    const float* xin = k == 0 ? h->wf("x0") : h->wf("blk0.out");
+    float* gout = k == 1 ? g_a : g_b;
+    float* gin = k == 1 ? g_b : g_a;
+    launch_ffn_bwd(h->wf(p + "y"), gout, h->P(o.w1), h->P(o.b1), h->P(o.w2), h->P(o.ln_b_beta), h->P(o.ln_b_gamma), h->wf("d_y"),
+                   h->G(o.w1), h->G(o.b1), h->G(o.w2), h->G(o.b2), h->G(o.ln_b_beta), h->G(o.ln_b_gamma), N, st);
+    launch_attn_bwd(h->wf(p + "Q"), h->wf(p + "K"), h->wf(p + "V"), h->wf("d_y"), b->mask, h->wf("d_Q"), h->wf("d_K"),
+                    h->wf("d_V"), B, T, st);
+    launch_proj_bwd(xin, h->wf("d_y"), h->wf("d_Q"), h->wf("d_K"), h->wf("d_V"), h->wi("perm"), ctl, h->wi("tile_bucket"),
+                    h->wi("tile_begin"), h->wi("tile_count"), max_tiles, h->P(o.wq), h->P(o.wk), h->P(o.wv), h->P(o.ln_a_beta),
+                    h->P(o.ln_a_gamma), gin, h->G(o.wq), h->G(o.wk), h->G(o.wv), h->G(o.ln_a_beta), h->G(o.ln_a_gamma), st);
+    nl += 3;
+  }
+  // dX0 is in g_a
+  launch_embed_bwd_reduce(g_a, h->wf("d_tgt"), h->wf("d_tgt_total"), h->G(L.pos), h->wd("sp_normsq") + 4, B, T, st); nl += 2;
+  h->launches = nl;
+  return check_cuda(h, "backward");
+}
+
+// ------------------------------------------------------------------------------------------
+static SparseTable table_of(PamrecHandle h, const char* which) {
+  SparseTable t;
+  memset(&t, 0, sizeof t);
+  std::string w = which;
+  std::string p = (w == "item" || w == "cate") ? "sp." + w + "." : "sp.user.";
+  t.keys = h->wi(p + "keys"); t.idx = h->wi(p + "idx"); t.skeys = h->wi(p + "skeys"); t.sidx = h->wi(p + "sidx");
+  t.uidx = h->wi(p + "uidx"); t.ukeys = h->wi(p + "ukeys"); t.slot = h->wi(p + "slot");
+  int* nu = h->wi("sp.nuniq");
+  double* ns = h->wd("sp_normsq");
+  if (w == "item") { t.width = kI; t.n_rows = h->cfg.n_items; t.w = h->buf.item_w; t.m = h->buf.item_m; t.v = h->buf.item_v;
+                     t.accum = h->wf("sp.item.accum"); t.nuniq = nu; t.normsq = ns; }
+  else if (w == "cate") { t.width = kC; t.n_rows = h->cfg.n_cates; t.w = h->buf.cate_w; t.m = h->buf.cate_m; t.v = h->buf.cate_v;
+                          t.accum = h->wf("sp.cate.accum"); t.nuniq = nu + 1; t.normsq = ns + 1; }
+  else if (w == "ulong") { t.width = PAMREC_USER_DIM; t.n_rows = h->cfg.n_users; t.w = h->buf.ulong_w; t.m = h->buf.ulong_m;
+                           t.v = h->buf.ulong_v; t.accum = nullptr; t.nuniq = nu + 2; t.normsq = ns + 2; }
+  else { t.width = PAMREC_USER_DIM; t.n_rows = h->cfg.n_users; t.w = h->buf.ushort_w; t.m = h->buf.ushort_m;
+         t.v = h->buf.ushort_v; t.accum = nullptr; t.nuniq = nu + 2; t.normsq = ns + 3; }
+  return t;
+}
+
+int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, void* stream) {
+  if (int rc = check_batch(h, b, true)) return rc;
+  if (step < 1) return fail(h, "step must be >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Layout& L = h->L;
+  const PamrecConfig& c = h->cfg;
+  const int B = b->batch, T = c.max_seq_len;
+  const int64_t N = (int64_t)B * T;
+  const double b1 = c.beta1, b2 = c.beta2;
+  const float lr_t = (float)((double)c.learning_rate * std::sqrt(1.0 - std::pow(b2, (double)step)) / (1.0 - std::pow(b1, (double)step)));
+  double* reg = h->wd("loss_acc") + 3;
+  void* tmp = h->ws<char>("cub_temp");
+  size_t tmp_bytes = (size_t)L.ws[L.ws_index.at("cub_temp")].numel;
+  int64_t nl = 0;
+  const float* dX0 = h->wf("g_a");
+  const float* dT = h->wf("d_tgt_total");
+  {
+    SparseTable t = table_of(h, "item");
+    if (launch_sparse_reduce(t, b->item_history, b->items, N, B, dX0, kD, 0, dT, kE, 0, tmp, tmp_bytes, st)) return fail(h, "cub sort failed");
+    launch_sparse_l2norm(t, N + B, c.embed_l2, reg, st);
+    launch_sparse_adam(t, N + B, c.sparse_adam_mode, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm, c.is_clip_norm, st);
+    launch_slot_reset(t, N + B, st);
+    nl += 7;
+  }
+  {
+    SparseTable t = table_of(h, "cate");
+    if (launch_sparse_reduce(t, b->item_cate_history, b->cates, N, B, dX0, kD, kI, dT, kE, kI, tmp, tmp_bytes, st)) return fail(h, "cub sort failed");
+    launch_sparse_l2norm(t, N + B, c.embed_l2, reg, st);
+    launch_sparse_adam(t, N + B, c.sparse_adam_mode, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm, c.is_clip_norm, st);
+    launch_slot_reset(t, N + B, st);
+    nl += 7;
+  }
+  {
+    SparseTable tl = table_of(h, "ulong"), ts = table_of(h, "ushort");
+    if (launch_sparse_reduce(tl, b->users, nullptr, B, 0, nullptr, 0, 0, nullptr, 0, 0, tmp, tmp_bytes, st)) return fail(h, "cub sort failed");
+    launch_sparse_l2norm(tl, B, c.embed_l2, reg, st);
+    launch_sparse_l2norm(ts, B, c.embed_l2, reg, st);
+    launch_sparse_adam(tl, B, c.sparse_adam_mode, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm, c.is_clip_norm, st);
+    launch_sparse_adam(ts, B, c.sparse_adam_mode, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm, c.is_clip_norm, st);
+    launch_slot_reset(tl, B, st);
+    nl += 8;
+  }
+  const int n_seg = (int)L.dense.size();
+  launch_dense_norm(h->buf.dense_param, h->buf.dense_grad, h->wi("seg_tab"), n_seg, c.layer_l2, h->wd("seg_normsq"),
+                    h->wd("sp_normsq") + 4, reg, st);
+  launch_dense_adam(h->buf.dense_param, h->buf.dense_grad, h->buf.dense_m, h->buf.dense_v, h->wi("seg_id"), h->wi("seg_tab"),
+                    h->wd("seg_normsq"), L.dense_numel, c.layer_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm,
+                    c.is_clip_norm, st);
+  launch_finish_losses(h->wd("loss_acc"), h->wf("losses"), st);
+  nl += 3;
+  h->launches = nl;
+  return check_cuda(h, "apply_gradients");
+}
+
+int pamrec_train_step(PamrecHandle h, const PamrecBatch* b, int64_t step, float* losses_out, void* stream) {
+  if (!h) return -1;
+  if (h->cfg.world_size > 1) return fail(h, "world_size > 1: drive the step with pamrec_train_phase");
+  int64_t nl = 0;
+  if (int rc = pamrec_forward(h, b, 1, nullptr, stream)) return rc;
+  nl += h->launches;
+  if (int rc = pamrec_backward(h, b, stream)) return rc;
+  nl += h->launches;
+  if (int rc = pamrec_apply_gradients(h, b, step, stream)) return rc;
+  nl += h->launches;
+  if (losses_out)
+    cudaMemcpyAsync(losses_out, h->wf("losses"), 5 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  h->launches = nl;
+  return check_cuda(h, "train_step");
+}
+
+int pamrec_train_phase(PamrecHandle h, const PamrecBatch* b, int64_t step, int phase, float* losses_out, char sync_name[160],
+                       void* stream) {
+  (void)b; (void)step; (void)phase; (void)losses_out; (void)sync_name; (void)stream;
+  return fail(h, "pamrec_train_phase: not built yet");
+}
+
+int pamrec_bench_gather(PamrecHandle h, const int32_t* item_ids, const int32_t* cate_ids, const int32_t* tgt_items,
+                        const int32_t* tgt_cates, int64_t n_rows, int32_t T, float* out, void* stream) {
+  if (!h || !h->bound) return fail(h, "not bound");
+  if (T < 1 || T > h->cfg.max_seq_len) return fail(h, "T outside the position table");
+  launch_embed_fwd(item_ids, cate_ids, tgt_items, tgt_cates, h->buf.item_w, h->buf.cate_w, h->P(h->L.pos), out, nullptr, n_rows,
+                   T, (cudaStream_t)stream);
+  h->launches = 1;
+  return check_cuda(h, "bench_gather");
+}
+
+int pamrec_bench_table_adam(PamrecHandle h, int64_t step, void* stream) {
+  if (!h || !h->bound) return fail(h, "not bound");
+  const PamrecConfig& c = h->cfg;
+  const double b1 = c.beta1, b2 = c.beta2;
+  const float lr_t = (float)((double)c.learning_rate * std::sqrt(1.0 - std::pow(b2, (double)step)) / (1.0 - std::pow(b1, (double)step)));
+  SparseTable t = table_of(h, "item");
+  launch_sparse_adam(t, 0, PAMREC_ADAM_DENSE_EXACT, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm, c.is_clip_norm,
+                     (cudaStream_t)stream);
+  h->launches = 1;
+  return check_cuda(h, "bench_table_adam");
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+// Launcher declarations shared by the translation units of libpamrec_b200.so.
+#pragma once
+#include "common.cuh"
+
+namespace pamrec {
+
+// ---- kernels_encoder.cu
+void launch_embed_fwd(const int* ih, const int* ch, const int* items, const int* cates, const float* item_w,
+                      const float* cate_w, const float* pos, float* x0, float* tgt, int64_t n_rows, int T, cudaStream_t st);
+void launch_bucket_plan(const float* lt, int n, int* bucket, int* perm, int* ctl, int* tile_bucket, int* tile_begin,
+                        int* tile_count, cudaStream_t st);
+void launch_proj_fwd(const float* X, const int* perm, const int* ctl, const int* tile_bucket, const int* tile_begin,
+                     const int* tile_count, int max_tiles, const float* Wq, const float* Wk, const float* Wv,
+                     const float* ln_beta, const float* ln_gamma, float* QIN, float* Q, float* K, float* V, cudaStream_t st);
+void launch_attn_fwd(const float* Q, const float* K, const float* V, const float* QIN, const int* mask, float* Y, int B,
+                     int T, cudaStream_t st);
+void launch_ffn_fwd(const float* Y, const float* W1, const float* b1, const float* W2, const float* b2,
+                    const float* ln_beta, const float* ln_gamma, float* OUT, int n_tok, cudaStream_t st);
+void launch_ffn_bwd(const float* Y, const float* dOUT, const float* W1, const float* b1, const float* W2,
+                    const float* ln_beta, const float* ln_gamma, float* dY, float* dW1, float* db1, float* dW2,
+                    float* db2, float* dbeta, float* dgamma, int n_tok, cudaStream_t st);
+void launch_attn_bwd(const float* Q, const float* K, const float* V, const float* dY, const int* mask, float* dQ,
+                     float* dK, float* dV, int B, int T, cudaStream_t st);
+void launch_proj_bwd(const float* X, const float* dY, const float* dQ, const float* dK, const float* dV, const int* perm,
+                     const int* ctl, const int* tile_bucket, const int* tile_begin, const int* tile_count, int max_tiles,
+                     const float* Wq, const float* Wk, const float* Wv, const float* ln_beta, const float* ln_gamma,
+                     float* dX, float* dWq, float* dWk, float* dWv, float* dbeta, float* dgamma, cudaStream_t st);
+
+// ---- kernels_head.cu
+void launch_dense_fwd(const DenseP& p, cudaStream_t st);
+void launch_dense_dx(const DenseDxP& p, cudaStream_t st);
+void launch_dense_dw(const DenseDwP& p, cudaStream_t st);
+void launch_bn_finalize(const BnSet& s, double count, cudaStream_t st);   // training: sums -> stat, moving update, sums := 0
+void launch_bn_eval_stat(const BnSet& s, cudaStream_t st);                // inference: stat from moving stats
+void launch_bn_bwd_stats(const BnSet& s, const float* dA, const float* Z, int M, cudaStream_t st);
+void launch_bn_bwd_apply(const BnSet& s, float* dA_inout, const float* Z, int M, double count, float grad_scale,
+                         cudaStream_t st);
+void launch_pool_fwd(const float* H, const float* Z2, const BnSet& s1, const int* mask, float* new_long, int B, int T,
+                     cudaStream_t st);
+void launch_pool_bwd(const float* H, const float* Z2, const BnSet& s1, const int* mask, const float* d_new_long, float* dA2,
+                     float* dH, int B, int T, cudaStream_t st);
+void launch_combine_fwd(const float* ZE1, const float* ZG1, const BnSet& e1, const BnSet& g1, const float* tgt, float* U,
+                        int B, cudaStream_t st);
+void launch_combine_bwd(const float* ZE1, const float* ZG1, const BnSet& e1, const BnSet& g1, const float* dU, float* dE1,
+                        float* dG1, float* dTgt, int B, cudaStream_t st);
+// loss_acc (double[8]): [0] data [1] aux [2] order (all already weighted / averaged)
+void launch_loss(const float* logits, const float* y_sat, const float* y_play, const float* plays, float* d_logits,
+                 double* loss_acc, int B, int B_global, int n_valid_global_or_neg, float fuzhu_w, float order_w,
+                 cudaStream_t st);
+void launch_sigmoid_col0(const float* logits, float* pred, int B, cudaStream_t st);
+
+// ---- kernels_optim.cu
+struct SparseTable {
+  int width;                  // floats per row (16 / 4 / 20)
+  int64_t n_rows;
+  float* w; float* m; float* v;
+  int* keys; int* idx; int* skeys; int* sidx; int* uidx; int* ukeys; int* slot;
+  float* accum;               // [n_keys, width]
+  int* nuniq;                 // device scalar
+  double* normsq;             // device scalar: sum of squares of every un-deduplicated gradient row
+};
+void launch_embed_bwd_reduce(const float* dX0, const float* dTgtHead, float* dTgtTotal, float* dPos, double* pos_normsq,
+                             int B, int T, cudaStream_t st);
+size_t sparse_temp_bytes(int64_t n_keys);
+// builds keys (history ids then target ids), sorts, finds unique rows, reduces duplicate rows into accum
+int launch_sparse_reduce(const SparseTable& t, const int* hist_ids, const int* tgt_ids, int64_t n_hist, int64_t n_tgt,
+                         const float* hist_grad, int hist_ld, int hist_col, const float* tgt_grad, int tgt_ld, int tgt_col,
+                         void* cub_temp, size_t cub_bytes, cudaStream_t st);
+// L2 rows of the unique ids: adds their squared norm to normsq and 0.5*l2*|w|^2 to reg_acc
+void launch_sparse_l2norm(const SparseTable& t, int64_t n_keys, float l2, double* reg_acc, cudaStream_t st);
+void launch_sparse_adam(const SparseTable& t, int64_t n_keys, int mode, float l2, float lr_t, float b1, float b2, float eps,
+                        float clip, int is_clip, cudaStream_t st);
+void launch_dense_norm(const float* P, const float* G, const int* seg_tab, int n_seg, float layer_l2, double* seg_normsq,
+                       const double* pos_normsq, double* reg_acc, cudaStream_t st);
+void launch_dense_adam(float* P, const float* G, float* M, float* V, const int* seg_id, const int* seg_tab,
+                       const double* seg_normsq, int64_t n, float layer_l2, float lr_t, float b1, float b2, float eps,
+                       float clip, int is_clip, cudaStream_t st);
+void launch_finish_losses(const double* loss_acc, float* losses, cudaStream_t st);
+
+}  // namespace pamrec

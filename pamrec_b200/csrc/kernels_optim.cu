@@ -1,0 +1,363 @@
+// Sparse embedding backward (sorted ids -> warp-level segmented reduction -> row-wise Adam)
+// and the dense-parameter optimiser.
+//
+// TF semantics reproduced:
+//  * the gradient of an embedding table is the CONCATENATION of every lookup's rows
+//    (history, target, and the L2 rows of tf.unique(ids)); tf.clip_by_norm (base_model.py:297-303)
+//    takes its norm over those un-deduplicated rows;
+//  * tf.train.AdamOptimizer then sums duplicate rows and, for sparse variables, decays m and v
+//    and moves the weights of EVERY row of the table (mode DENSE_EXACT).  Mode LAZY touches
+//    only the looked-up rows.
+#include <cub/cub.cuh>
+
+#include "kernels.h"
+
+namespace pamrec {
+
+// ------------------------------------------------------------------------------------------
+// d_tgt_total[b,:] = d_tgt_head[b,:] + sum_t dX0[b,t,20:40];  pos_normsq += |dX0|^2;
+// dPos[t,:] += sum_b dX0[b,t,:]
+__global__ void __launch_bounds__(128) k_dtgt_total(const float* __restrict__ dX0, const float* __restrict__ dTgtHead,
+                                                    float* __restrict__ dTgtTotal, double* __restrict__ pos_normsq, int T) {
+  __shared__ double sh[4];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* base = dX0 + (int64_t)b * T * kD;
+  double sq = 0.0;
+  for (int i = tid; i < T * kD; i += 128) { float v = base[i]; sq += (double)v * (double)v; }
+  sq = warp_sum_d(sq);
+  if ((tid & 31) == 0) sh[tid >> 5] = sq;
+  __syncthreads();
+  if (tid == 0) atomicAdd(pos_normsq, sh[0] + sh[1] + sh[2] + sh[3]);
+  if (tid < kE) {
+    float s = dTgtHead[(int64_t)b * kE + tid];
+    for (int t = 0; t < T; ++t) s += base[t * kD + kE + tid];
+    dTgtTotal[(int64_t)b * kE + tid] = s;
+  }
+}
+constexpr int kPosRows = 64;
+__global__ void k_pos_grad(const float* __restrict__ dX0, float* __restrict__ dPos, int B, int T) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= T * kD) return;
+  int b0 = blockIdx.y * kPosRows, b1 = min(B, b0 + kPosRows);
+  float s = 0.f;
+  for (int b = b0; b < b1; ++b) s += dX0[(int64_t)b * T * kD + e];
+  atomicAdd(dPos + e, s);
+}
+void launch_embed_bwd_reduce(const float* dX0, const float* dTgtHead, float* dTgtTotal, float* dPos, double* pos_normsq,
+                             int B, int T, cudaStream_t st) {
+  k_dtgt_total<<<B, 128, 0, st>>>(dX0, dTgtHead, dTgtTotal, pos_normsq, T);
+  dim3 grid((T * kD + 127) / 128, (B + kPosRows - 1) / kPosRows);
+  k_pos_grad<<<grid, 128, 0, st>>>(dX0, dPos, B, T);
+}
+
+// ------------------------------------------------------------------------------------------
+size_t sparse_temp_bytes(int64_t n_keys) {
+  size_t a = 0, b = 0;
+  int* p = nullptr;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, p, p, p, p, (int)n_keys, 0, 32, (cudaStream_t)0);
+  cub::DeviceScan::InclusiveSum(nullptr, b, p, p, (int)n_keys, (cudaStream_t)0);
+  return a > b ? a : b;
+}
+
+__global__ void k_build_keys(const int* __restrict__ hist_ids, const int* __restrict__ tgt_ids, int64_t n_hist,
+                             int64_t n_tgt, int* __restrict__ keys, int* __restrict__ idx) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_hist + n_tgt) return;
+  keys[p] = p < n_hist ? hist_ids[p] : tgt_ids[p - n_hist];
+  idx[p] = (int)p;
+}
+__global__ void k_head_flags(const int* __restrict__ skeys, int64_t n, int* __restrict__ flags) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  flags[p] = (p == 0 || skeys[p] != skeys[p - 1]) ? 1 : 0;
+}
+__global__ void k_unique_fill(const int* __restrict__ skeys, const int* __restrict__ uidx, int64_t n,
+                              int* __restrict__ ukeys, int* __restrict__ slot, int* __restrict__ nuniq) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  if (p == 0 || skeys[p] != skeys[p - 1]) {
+    int u = uidx[p] - 1;
+    ukeys[u] = skeys[p];
+    slot[skeys[p]] = u;
+  }
+  if (p == n - 1) *nuniq = uidx[p];
+}
+
+__device__ __forceinline__ void atomic_add4(float* p, const float4& v) {
+#if __CUDA_ARCH__ >= 900
+  atomicAdd(reinterpret_cast<float4*>(p), v);
+#else
+  atomicAdd(p, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); atomicAdd(p + 3, v.w);
+#endif
+}
+
+// warp-level segmented reduction over 32 consecutive sorted positions
+template <int W>
+__global__ void __launch_bounds__(256)
+k_seg_reduce(const int* __restrict__ skeys, const int* __restrict__ sidx, const int* __restrict__ uidx, int64_t n,
+             int64_t n_hist, const float* __restrict__ hist_grad, int hist_ld, int hist_col,
+             const float* __restrict__ tgt_grad, int tgt_ld, int tgt_col, float* __restrict__ accum,
+             double* __restrict__ normsq) {
+  const int lane = threadIdx.x & 31;
+  const int64_t p = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
+  const bool valid = p < n;
+  int key = -1 - lane;
+  const float* row = nullptr;
+  int u = 0;
+  if (valid) {
+    key = skeys[p];
+    int src = sidx[p];
+    row = src < n_hist ? hist_grad + (int64_t)src * hist_ld + hist_col
+                       : tgt_grad + (int64_t)(src - n_hist) * tgt_ld + tgt_col;
+    u = uidx[p] - 1;
+  }
+  const int key_next = __shfl_down_sync(0xffffffffu, key, 1);
+  const bool tail = valid && (lane == 31 || key_next != key);
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < W / 4; ++c) {
+    float4 g = valid ? ld4(row + 4 * c) : f4_zero();
+    sq += f4_dot(g, g);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      float4 o;
+      o.x = __shfl_up_sync(0xffffffffu, g.x, d); o.y = __shfl_up_sync(0xffffffffu, g.y, d);
+      o.z = __shfl_up_sync(0xffffffffu, g.z, d); o.w = __shfl_up_sync(0xffffffffu, g.w, d);
+      int ko = __shfl_up_sync(0xffffffffu, key, d);
+      if (lane >= d && ko == key) { g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w; }
+    }
+    if (tail) atomic_add4(accum + (int64_t)u * W + 4 * c, g);
+  }
+  double s = warp_sum_d((double)sq);
+  if (lane == 0 && s != 0.0) atomicAdd(normsq, s);
+}
+
+int launch_sparse_reduce(const SparseTable& t, const int* hist_ids, const int* tgt_ids, int64_t n_hist, int64_t n_tgt,
+                         const float* hist_grad, int hist_ld, int hist_col, const float* tgt_grad, int tgt_ld, int tgt_col,
+                         void* cub_temp, size_t cub_bytes, cudaStream_t st) {
+  const int64_t n = n_hist + n_tgt;
+  if (n == 0) return 0;
+  const unsigned g256 = (unsigned)((n + 255) / 256);
+  k_build_keys<<<g256, 256, 0, st>>>(hist_ids, tgt_ids, n_hist, n_tgt, t.keys, t.idx);
+  int bits = 1;
+  while (bits < 31 && ((int64_t)1 << bits) < t.n_rows) ++bits;
+  size_t bytes = cub_bytes;
+  if (cub::DeviceRadixSort::SortPairs(cub_temp, bytes, t.keys, t.skeys, t.idx, t.sidx, (int)n, 0, bits, st) != cudaSuccess)
+    return -1;
+  k_head_flags<<<g256, 256, 0, st>>>(t.skeys, n, t.keys);          // keys buffer reused as head flags
+  bytes = cub_bytes;
+  if (cub::DeviceScan::InclusiveSum(cub_temp, bytes, t.keys, t.uidx, (int)n, st) != cudaSuccess) return -1;
+  k_unique_fill<<<g256, 256, 0, st>>>(t.skeys, t.uidx, n, t.ukeys, t.slot, t.nuniq);
+  if (t.accum != nullptr && hist_grad != nullptr) {
+    cudaMemsetAsync(t.accum, 0, (size_t)n * t.width * sizeof(float), st);
+    const unsigned gw = (unsigned)((n + 255) / 256);               // 8 warps x 32 positions per CTA
+    if (t.width == 16)
+      k_seg_reduce<16><<<gw, 256, 0, st>>>(t.skeys, t.sidx, t.uidx, n, n_hist, hist_grad, hist_ld, hist_col, tgt_grad, tgt_ld,
+                                           tgt_col, t.accum, t.normsq);
+    else
+      k_seg_reduce<4><<<gw, 256, 0, st>>>(t.skeys, t.sidx, t.uidx, n, n_hist, hist_grad, hist_ld, hist_col, tgt_grad, tgt_ld,
+                                          tgt_col, t.accum, t.normsq);
+  }
+  return 0;
+}
+
+// L2 rows of the unique ids (sequential_base_model.py:647-664, pamrec.py:173-182)
+template <int W>
+__global__ void __launch_bounds__(256)
+k_sparse_l2norm(const int* __restrict__ ukeys, const int* __restrict__ nuniq, const float* __restrict__ w, float l2,
+                double* __restrict__ normsq, double* __restrict__ reg_acc) {
+  __shared__ double sh[8];
+  constexpr int CH = W / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)(*nuniq) * CH;
+  double s = 0.0;
+  if (i < total) {
+    int u = (int)(i / CH), c = (int)(i % CH);
+    float4 v = ld4(w + (int64_t)ukeys[u] * W + 4 * c);
+    s = (double)f4_dot(v, v);
+  }
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int k = 0; k < 8; ++k) tot += sh[k];
+    if (tot != 0.0) {
+      atomicAdd(normsq, (double)l2 * (double)l2 * tot);
+      atomicAdd(reg_acc, 0.5 * (double)l2 * tot);
+    }
+  }
+}
+void launch_sparse_l2norm(const SparseTable& t, int64_t n_keys, float l2, double* reg_acc, cudaStream_t st) {
+  int64_t total = n_keys * (t.width / 4);
+  unsigned g = (unsigned)((total + 255) / 256);
+  if (t.width == 16) k_sparse_l2norm<16><<<g, 256, 0, st>>>(t.ukeys, t.nuniq, t.w, l2, t.normsq, reg_acc);
+  else if (t.width == 4) k_sparse_l2norm<4><<<g, 256, 0, st>>>(t.ukeys, t.nuniq, t.w, l2, t.normsq, reg_acc);
+  else k_sparse_l2norm<20><<<g, 256, 0, st>>>(t.ukeys, t.nuniq, t.w, l2, t.normsq, reg_acc);
+}
+
+__device__ __forceinline__ void adam_row4(float4& w, float4& m, float4& v, const float4& g, float lr, float b1, float b2,
+                                          float eps) {
+  // TF _apply_sparse_shared: m = m*b1 + g*(1-b1); v = v*b2 + g*g*(1-b2); w -= lr*m/(sqrt(v)+eps)
+  m.x = m.x * b1 + g.x * (1.f - b1); m.y = m.y * b1 + g.y * (1.f - b1);
+  m.z = m.z * b1 + g.z * (1.f - b1); m.w = m.w * b1 + g.w * (1.f - b1);
+  v.x = v.x * b2 + (g.x * g.x) * (1.f - b2); v.y = v.y * b2 + (g.y * g.y) * (1.f - b2);
+  v.z = v.z * b2 + (g.z * g.z) * (1.f - b2); v.w = v.w * b2 + (g.w * g.w) * (1.f - b2);
+  w.x -= lr * m.x / (sqrtf(v.x) + eps); w.y -= lr * m.y / (sqrtf(v.y) + eps);
+  w.z -= lr * m.z / (sqrtf(v.z) + eps); w.w -= lr * m.w / (sqrtf(v.w) + eps);
+}
+__device__ __forceinline__ float clip_scale(const double* normsq, float clip, int is_clip) {
+  if (!is_clip) return 1.0f;
+  float norm = (float)sqrt(*normsq);
+  return clip / fmaxf(norm, clip);            // tf.clip_by_norm: t * clip / max(norm, clip)
+}
+
+// full-table sweep: the HBM-bound kernel (6 x row bytes per row + 4 B slot)
+template <int W>
+__global__ void __launch_bounds__(256)
+k_table_adam_dense(float* __restrict__ tw, float* __restrict__ tm, float* __restrict__ tv, const int* __restrict__ slot,
+                   const float* __restrict__ accum, const double* __restrict__ normsq, int64_t n_rows, float l2, float lr,
+                   float b1, float b2, float eps, float clip, int is_clip) {
+  constexpr int CH = W / 4;
+  const int64_t total = n_rows * CH;
+  const float scale = clip_scale(normsq, clip, is_clip);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / CH;
+    const int c = (int)(i % CH);
+    float4 w = ld4(tw + 4 * i), m = ld4(tm + 4 * i), v = ld4(tv + 4 * i);
+    float4 g = f4_zero();
+    const int u = __ldg(slot + r);
+    if (u >= 0) {
+      float4 a = accum ? ld4(accum + (int64_t)u * W + 4 * c) : f4_zero();
+      g.x = scale * (a.x + l2 * w.x); g.y = scale * (a.y + l2 * w.y);
+      g.z = scale * (a.z + l2 * w.z); g.w = scale * (a.w + l2 * w.w);
+    }
+    adam_row4(w, m, v, g, lr, b1, b2, eps);
+    st4(tw + 4 * i, w); st4(tm + 4 * i, m); st4(tv + 4 * i, v);
+  }
+}
+template <int W>
+__global__ void __launch_bounds__(256)
+k_table_adam_lazy(float* __restrict__ tw, float* __restrict__ tm, float* __restrict__ tv, const int* __restrict__ ukeys,
+                  const int* __restrict__ nuniq, const float* __restrict__ accum, const double* __restrict__ normsq, float l2,
+                  float lr, float b1, float b2, float eps, float clip, int is_clip) {
+  constexpr int CH = W / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)(*nuniq) * CH) return;
+  const int u = (int)(i / CH), c = (int)(i % CH);
+  const int64_t o = (int64_t)ukeys[u] * W + 4 * c;
+  const float scale = clip_scale(normsq, clip, is_clip);
+  float4 w = ld4(tw + o), m = ld4(tm + o), v = ld4(tv + o);
+  float4 a = accum ? ld4(accum + (int64_t)u * W + 4 * c) : f4_zero();
+  float4 g;
+  g.x = scale * (a.x + l2 * w.x); g.y = scale * (a.y + l2 * w.y);
+  g.z = scale * (a.z + l2 * w.z); g.w = scale * (a.w + l2 * w.w);
+  adam_row4(w, m, v, g, lr, b1, b2, eps);
+  st4(tw + o, w); st4(tm + o, m); st4(tv + o, v);
+}
+__global__ void k_slot_reset(const int* __restrict__ ukeys, const int* __restrict__ nuniq, int* __restrict__ slot) {
+  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < *nuniq) slot[ukeys[u]] = -1;
+}
+
+template <int W>
+static void sparse_adam_w(const SparseTable& t, int64_t n_keys, int mode, float l2, float lr, float b1, float b2, float eps,
+                          float clip, int is_clip, cudaStream_t st) {
+  if (mode == PAMREC_ADAM_DENSE_EXACT) {
+    int64_t total = t.n_rows * (W / 4);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = 148 * 32;                                 // grid-stride above 32 CTAs per SM
+    unsigned g = (unsigned)(blocks < cap ? blocks : cap);
+    k_table_adam_dense<W><<<g, 256, 0, st>>>(t.w, t.m, t.v, t.slot, t.accum, t.normsq, t.n_rows, l2, lr, b1, b2, eps, clip, is_clip);
+  } else {
+    int64_t total = n_keys * (W / 4);
+    k_table_adam_lazy<W><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t.w, t.m, t.v, t.ukeys, t.nuniq, t.accum, t.normsq, l2,
+                                                                        lr, b1, b2, eps, clip, is_clip);
+  }
+}
+void launch_sparse_adam(const SparseTable& t, int64_t n_keys, int mode, float l2, float lr_t, float b1, float b2, float eps,
+                        float clip, int is_clip, cudaStream_t st) {
+  if (t.width == 16) sparse_adam_w<16>(t, n_keys, mode, l2, lr_t, b1, b2, eps, clip, is_clip, st);
+  else if (t.width == 4) sparse_adam_w<4>(t, n_keys, mode, l2, lr_t, b1, b2, eps, clip, is_clip, st);
+  else sparse_adam_w<20>(t, n_keys, mode, l2, lr_t, b1, b2, eps, clip, is_clip, st);
+}
+void launch_slot_reset(const SparseTable& t, int64_t n_keys, cudaStream_t st) {
+  k_slot_reset<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(t.ukeys, t.nuniq, t.slot);
+}
+
+// ------------------------------------------------------------------------------------------
+// dense variables: one CTA per TF variable computes |g + l2 p|^2 and the L2 loss term
+__global__ void __launch_bounds__(256)
+k_dense_norm(const float* __restrict__ P, const float* __restrict__ G, const int* __restrict__ seg_tab, float layer_l2,
+             double* __restrict__ seg_normsq, const double* __restrict__ pos_normsq, double* __restrict__ reg_acc) {
+  __shared__ double sh[2][8];
+  const int s = blockIdx.x;
+  const int64_t off = seg_tab[4 * s];
+  const int n = seg_tab[4 * s + 1], flags = seg_tab[4 * s + 2];
+  const float l2 = (flags & PAMREC_SEG_L2) ? layer_l2 : 0.f;
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    float p = P[off + i];
+    float g = G[off + i] + l2 * p;
+    a += (double)g * (double)g;
+    b += (double)p * (double)p;
+  }
+  a = warp_sum_d(a); b = warp_sum_d(b);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+    for (int k = 0; k < 8; ++k) { ta += sh[0][k]; tb += sh[1][k]; }
+    seg_normsq[s] = (flags & PAMREC_SEG_POS) ? *pos_normsq : ta;
+    if (l2 != 0.f) atomicAdd(reg_acc, 0.5 * (double)l2 * tb);
+  }
+}
+void launch_dense_norm(const float* P, const float* G, const int* seg_tab, int n_seg, float layer_l2, double* seg_normsq,
+                       const double* pos_normsq, double* reg_acc, cudaStream_t st) {
+  k_dense_norm<<<n_seg, 256, 0, st>>>(P, G, seg_tab, layer_l2, seg_normsq, pos_normsq, reg_acc);
+}
+
+__global__ void __launch_bounds__(256)
+k_dense_adam(float* __restrict__ P, const float* __restrict__ G, float* __restrict__ M, float* __restrict__ V,
+             const int* __restrict__ seg_id, const int* __restrict__ seg_tab, const double* __restrict__ seg_normsq, int64_t n,
+             float layer_l2, float lr, float b1, float b2, float eps, float clip, int is_clip) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = seg_id[i];
+  const int flags = seg_tab[4 * s + 2];
+  const float l2 = (flags & PAMREC_SEG_L2) ? layer_l2 : 0.f;
+  float p = P[i];
+  float g = G[i] + l2 * p;
+  if (is_clip) {
+    float norm = (float)sqrt(seg_normsq[s]);
+    g = g * clip / fmaxf(norm, clip);
+  }
+  float m = M[i], v = V[i];
+  if (flags & PAMREC_SEG_POS) {           // IndexedSlices variable: sparse apply form
+    m = m * b1 + g * (1.f - b1);
+    v = v * b2 + (g * g) * (1.f - b2);
+  } else {                                // ApplyAdam kernel form
+    m += (g - m) * (1.f - b1);
+    v += (g * g - v) * (1.f - b2);
+  }
+  p -= lr * m / (sqrtf(v) + eps);
+  P[i] = p; M[i] = m; V[i] = v;
+}
+void launch_dense_adam(float* P, const float* G, float* M, float* V, const int* seg_id, const int* seg_tab,
+                       const double* seg_normsq, int64_t n, float layer_l2, float lr_t, float b1, float b2, float eps,
+                       float clip, int is_clip, cudaStream_t st) {
+  k_dense_adam<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, G, M, V, seg_id, seg_tab, seg_normsq, n, layer_l2, lr_t, b1, b2,
+                                                           eps, clip, is_clip);
+}
+
+__global__ void k_finish_losses(const double* __restrict__ acc, float* __restrict__ losses) {
+  // pamrec.py:444-448 order: loss, data_loss, regular_loss, auxiliary_data_loss, order_loss
+  losses[0] = (float)(acc[0] + acc[3] + acc[1] + acc[2]);
+  losses[1] = (float)acc[0];
+  losses[2] = (float)acc[3];
+  losses[3] = (float)acc[1];
+  losses[4] = (float)acc[2];
+}
+void launch_finish_losses(const double* loss_acc, float* losses, cudaStream_t st) { k_finish_losses<<<1, 1, 0, st>>>(loss_acc, losses); }
+
+}  // namespace pamrec

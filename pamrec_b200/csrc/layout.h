@@ -1,0 +1,234 @@
+// Host-side description of the model: where every TF variable lives in
+// the caller's flat pools, and how the workspace is carved.  No CUDA calls in here, so the
+// inventory can be queried on a machine without a GPU.
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pamrec {
+
+struct TensorDesc {
+  std::string name;
+  int pool = 0, dtype = PAMREC_F32, flags = 0;
+  int64_t offset = 0, numel = 0;
+  int ndim = 0;
+  int64_t shape[4] = {0, 0, 0, 0};
+};
+
+struct BlockOff { int64_t ln_a_beta, ln_a_gamma, wq, wk, wv, w1, b1, w2, b2, ln_b_beta, ln_b_gamma; };
+// 2-layer BN MLP, group-strided: offset of group 0; group g lives at off + g * (numel of one member)
+struct MlpOff { int64_t w0, b0, g0, be0, w1, b1, g1, be1, wout, bout; };
+struct BnOff { int C; int64_t gamma, beta, mm, mv; };
+
+enum BnId { BN_S0 = 0, BN_S1, BN_E0, BN_G0, BN_E1, BN_G1, BN_T0, BN_T1, BN_COUNT };
+
+struct Layout {
+  int n_users = 0, n_items = 0, n_cates = 0, T = 0, Bcap = 0;
+  std::vector<TensorDesc> dense, bn, ws;
+  int64_t dense_numel = 0, bn_numel = 0;
+  size_t ws_bytes = 0;
+  int64_t pos = 0;
+  BlockOff blk[2];
+  MlpOff score, expert, gate, tower;
+  BnOff bnoff[BN_COUNT];
+  std::map<std::string, size_t> ws_index;
+
+  int64_t add_dense(const std::string& name, std::initializer_list<int64_t> shape, int flags) {
+    TensorDesc t;
+    t.name = name; t.pool = PAMREC_POOL_DENSE; t.flags = flags; t.offset = dense_numel;
+    t.numel = 1; t.ndim = 0;
+    for (int64_t s : shape) { t.shape[t.ndim++] = s; t.numel *= s; }
+    dense_numel += t.numel;
+    dense.push_back(t);
+    return t.offset;
+  }
+  int64_t add_bn(const std::string& name, int64_t n) {
+    TensorDesc t;
+    t.name = name; t.pool = PAMREC_POOL_BN; t.offset = bn_numel; t.numel = n; t.ndim = 1; t.shape[0] = n;
+    bn_numel += n;
+    bn.push_back(t);
+    return t.offset;
+  }
+  void add_ws(const std::string& name, int dtype, std::initializer_list<int64_t> shape) {
+    TensorDesc t;
+    t.name = name; t.pool = PAMREC_POOL_WORKSPACE; t.dtype = dtype; t.offset = (int64_t)ws_bytes;
+    t.numel = 1; t.ndim = 0;
+    for (int64_t s : shape) { t.shape[t.ndim++] = s; t.numel *= s; }
+    size_t esz = (dtype == PAMREC_F64) ? 8 : (dtype == PAMREC_U8 ? 1 : 4);
+    size_t bytes = (size_t)t.numel * esz;
+    ws_bytes += (bytes + 255) / 256 * 256;
+    ws_index[name] = ws.size();
+    ws.push_back(t);
+  }
+  size_t ws_off(const std::string& name) const {
+    auto it = ws_index.find(name);
+    if (it == ws_index.end()) { fprintf(stderr, "pamrec: unknown workspace tensor %s\n", name.c_str()); abort(); }
+    return (size_t)ws[it->second].offset;
+  }
+
+  // members: TF scope of each group member; sizes in->h0->h1(->1)
+  MlpOff add_mlp(const std::vector<std::string>& scopes, const std::vector<int>& flags, int in, int h0, int h1, bool out,
+                 BnOff* bn0, BnOff* bn1, bool live = true) {
+    MlpOff o{};
+    auto role = [&](const char* leaf, std::initializer_list<int64_t> shape) {
+      int64_t first = -1;
+      for (size_t g = 0; g < scopes.size(); ++g) {
+        int64_t off = add_dense(scopes[g] + "/nn_part/" + leaf, shape, flags[g]);
+        if (g == 0) first = off;
+      }
+      return first;
+    };
+    o.w0 = role("w_nn_layer0", {in, h0});
+    o.b0 = role("b_nn_layer0", {h0});
+    o.g0 = role("batch_normalization/gamma", {h0});
+    o.be0 = role("batch_normalization/beta", {h0});
+    o.w1 = role("w_nn_layer1", {h0, h1});
+    o.b1 = role("b_nn_layer1", {h1});
+    o.g1 = role("batch_normalization_1/gamma", {h1});
+    o.be1 = role("batch_normalization_1/beta", {h1});
+    o.wout = o.bout = -1;
+    if (out) {
+      o.wout = role("w_nn_output", {h1, 1});
+      o.bout = role("b_nn_output", {1});
+    }
+    int G = (int)scopes.size();
+    int64_t mm0 = -1, mv0 = -1, mm1 = -1, mv1 = -1;
+    for (int g = 0; g < G; ++g) { int64_t x = add_bn(scopes[g] + "/nn_part/batch_normalization/moving_mean", h0); if (!g) mm0 = x; }
+    for (int g = 0; g < G; ++g) { int64_t x = add_bn(scopes[g] + "/nn_part/batch_normalization/moving_variance", h0); if (!g) mv0 = x; }
+    for (int g = 0; g < G; ++g) { int64_t x = add_bn(scopes[g] + "/nn_part/batch_normalization_1/moving_mean", h1); if (!g) mm1 = x; }
+    for (int g = 0; g < G; ++g) { int64_t x = add_bn(scopes[g] + "/nn_part/batch_normalization_1/moving_variance", h1); if (!g) mv1 = x; }
+    if (bn0) *bn0 = BnOff{G * h0, o.g0, o.be0, mm0, mv0};
+    if (bn1) *bn1 = BnOff{G * h1, o.g1, o.be1, mm1, mv1};
+    (void)live;
+    return o;
+  }
+
+  void build(const PamrecConfig& c) {
+    n_users = c.n_users; n_items = c.n_items; n_cates = c.n_cates; T = c.max_seq_len; Bcap = c.max_batch;
+    const int L2 = PAMREC_SEG_L2;
+    // ---- dense pool: encoder first so that every float4-loaded matrix starts on a 16-byte boundary
+    pos = add_dense("sequential/embedding/position_embedding", {T, kD}, PAMREC_SEG_POS);
+    for (int b = 0; b < 2; ++b) {
+      std::string p = "sequential/pamrec/num_blocks_" + std::to_string(b) + "/";
+      BlockOff& o = blk[b];
+      o.ln_a_beta = add_dense(p + "ln/Variable", {kD}, L2);
+      o.ln_a_gamma = add_dense(p + "ln/Variable_1", {kD}, L2);
+      o.wq = add_dense(p + "self_attention/Q_timeaware_embedding", {kNB, kDD}, L2);
+      o.wk = add_dense(p + "self_attention/K_timeaware_embedding", {kNB, kDD}, L2);
+      o.wv = add_dense(p + "self_attention/V_timeaware_embedding", {kNB, kDD}, L2);
+      o.w1 = add_dense(p + "multihead_attention/conv1d/kernel", {1, kD, kD}, L2);
+      o.b1 = add_dense(p + "multihead_attention/conv1d/bias", {kD}, L2);
+      o.w2 = add_dense(p + "multihead_attention/conv1d_1/kernel", {1, kD, kD}, L2);
+      o.b2 = add_dense(p + "multihead_attention/conv1d_1/bias", {kD}, L2);
+      o.ln_b_beta = add_dense(p + "ln_1/Variable", {kD}, L2);
+      o.ln_b_gamma = add_dense(p + "ln_1/Variable_1", {kD}, L2);
+    }
+    score = add_mlp({"sequential/pamrec/new_long/score_1"}, {L2}, kD, 20, 1, false, &bnoff[BN_S0], &bnoff[BN_S1]);
+    std::vector<std::string> ex;
+    for (int j = 0; j < 5; ++j) ex.push_back("sequential/pamrec/expert_" + std::to_string(j));
+    expert = add_mlp(ex, {L2, L2, L2, L2, L2}, kD, 100, 64, false, &bnoff[BN_E0], &bnoff[BN_E1]);
+    gate = add_mlp({"sequential/pamrec/gate_main", "sequential/pamrec/gate_sub"}, {L2, L2}, kD, 64, 5, false,
+                   &bnoff[BN_G0], &bnoff[BN_G1]);
+    tower = add_mlp({"sequential/logit_fcn", "sequential/valid_logit_fcn", "xilidu_logit_fcn"}, {L2, L2, 0}, 64 + kE, 100, 64,
+                    true, &bnoff[BN_T0], &bnoff[BN_T1]);
+    // dead-for-logits branches (pamrec.py:293-311): variables exist, receive only the L2 gradient
+    const char* dead[3] = {"new_distill", "long_term", "short_term"};
+    const int dq[3] = {40, 20, 20};
+    for (int i = 0; i < 3; ++i) {
+      std::string p = std::string("sequential/pamrec/") + dead[i] + "/attention_fcn";
+      add_dense(p + "/attention_mat", {kD, dq[i]}, L2 | PAMREC_SEG_DEAD);
+      add_mlp({p + "/att_fcn"}, {L2 | PAMREC_SEG_DEAD}, 4 * dq[i], 80, 40, true, nullptr, nullptr, false);
+    }
+
+    // ---- workspace
+    const int64_t B = Bcap, N = (int64_t)Bcap * T;
+    const int64_t NT = N / kTokTile + kNB + 2;   // bucket-sorted tiles
+    add_ws("bucket", PAMREC_I32, {N});
+    add_ws("perm", PAMREC_I32, {N});
+    add_ws("bucket_ctl", PAMREC_I32, {64});       // [0..15] counts, [16..31] cursors, [32] n_tiles
+    add_ws("tile_bucket", PAMREC_I32, {NT});
+    add_ws("tile_begin", PAMREC_I32, {NT});
+    add_ws("tile_count", PAMREC_I32, {NT});
+    add_ws("x0", PAMREC_F32, {B, T, kD});
+    add_ws("tgt", PAMREC_F32, {B, kE});
+    for (int b = 0; b < 2; ++b) {
+      std::string p = "blk" + std::to_string(b) + ".";
+      for (const char* n : {"qin", "Q", "K", "V", "y", "out"}) add_ws(p + n, PAMREC_F32, {B, T, kD});
+    }
+    add_ws("z1", PAMREC_F32, {B, T, 20});
+    add_ws("z2", PAMREC_F32, {B, T});
+    add_ws("new_long", PAMREC_F32, {B, kD});
+    add_ws("ze0", PAMREC_F32, {B, 500});
+    add_ws("zg0", PAMREC_F32, {B, 128});
+    add_ws("ze1", PAMREC_F32, {B, 320});
+    add_ws("zg1", PAMREC_F32, {B, 10});
+    add_ws("u", PAMREC_F32, {B, 168});
+    add_ws("zt0", PAMREC_F32, {B, 300});
+    add_ws("zt1", PAMREC_F32, {B, 192});
+    add_ws("logits", PAMREC_F32, {B, 3});
+    add_ws("losses", PAMREC_F32, {8});
+    add_ws("loss_acc", PAMREC_F64, {8});          // [0] data [1] aux [2] order [3] regular
+    // gradients
+    add_ws("d_logits", PAMREC_F32, {B, 3});
+    add_ws("d_t1", PAMREC_F32, {B, 192});
+    add_ws("d_t0", PAMREC_F32, {B, 300});
+    add_ws("d_u", PAMREC_F32, {B, 168});
+    add_ws("d_e1", PAMREC_F32, {B, 320});
+    add_ws("d_g1", PAMREC_F32, {B, 10});
+    add_ws("d_e0", PAMREC_F32, {B, 500});
+    add_ws("d_g0", PAMREC_F32, {B, 128});
+    add_ws("d_new_long", PAMREC_F32, {B, kD});
+    add_ws("d_tgt", PAMREC_F32, {B, kE});
+    add_ws("d_tgt_total", PAMREC_F32, {B, kE});
+    add_ws("d_z2", PAMREC_F32, {B, T});
+    add_ws("d_a1", PAMREC_F32, {B, T, 20});
+    add_ws("g_a", PAMREC_F32, {B, T, kD});        // ping-pong grads of block outputs / inputs
+    add_ws("g_b", PAMREC_F32, {B, T, kD});
+    add_ws("d_y", PAMREC_F32, {B, T, kD});
+    add_ws("d_Q", PAMREC_F32, {B, T, kD});
+    add_ws("d_K", PAMREC_F32, {B, T, kD});
+    add_ws("d_V", PAMREC_F32, {B, T, kD});
+    // batch-norm statistics
+    const char* bn_names[BN_COUNT] = {"s0", "s1", "e0", "g0", "e1", "g1", "t0", "t1"};
+    for (int i = 0; i < BN_COUNT; ++i) {
+      std::string p = std::string("bn.") + bn_names[i];
+      add_ws(p + ".sums", PAMREC_F64, {bnoff[i].C, 2});
+      add_ws(p + ".stat", PAMREC_F32, {bnoff[i].C, 2});
+      add_ws(p + ".bsums", PAMREC_F64, {bnoff[i].C, 2});
+    }
+    // optimiser scratch
+    add_ws("seg_id", PAMREC_I32, {dense_numel});
+    add_ws("seg_tab", PAMREC_I32, {(int64_t)dense.size(), 4});   // off, numel, flags, -
+    add_ws("seg_normsq", PAMREC_F64, {(int64_t)dense.size()});
+    add_ws("sp_normsq", PAMREC_F64, {8});          // 0 item 1 cate 2 ulong 3 ushort 4 pos
+    // sparse path: keys = history ids then target ids
+    const int64_t NK = N + B;
+    for (const char* t : {"item", "cate"}) {
+      std::string p = std::string("sp.") + t + ".";
+      add_ws(p + "keys", PAMREC_I32, {NK});
+      add_ws(p + "idx", PAMREC_I32, {NK});
+      add_ws(p + "skeys", PAMREC_I32, {NK});
+      add_ws(p + "sidx", PAMREC_I32, {NK});
+      add_ws(p + "uidx", PAMREC_I32, {NK});
+      add_ws(p + "ukeys", PAMREC_I32, {NK});
+      add_ws(p + "accum", PAMREC_F32, {NK, t[0] == 'i' ? kI : kC});
+      add_ws(p + "slot", PAMREC_I32, {t[0] == 'i' ? (int64_t)n_items : (int64_t)n_cates});
+    }
+    add_ws("sp.user.keys", PAMREC_I32, {B});
+    add_ws("sp.user.idx", PAMREC_I32, {B});
+    add_ws("sp.user.skeys", PAMREC_I32, {B});
+    add_ws("sp.user.sidx", PAMREC_I32, {B});
+    add_ws("sp.user.uidx", PAMREC_I32, {B});
+    add_ws("sp.user.ukeys", PAMREC_I32, {B});
+    add_ws("sp.user.slot", PAMREC_I32, {(int64_t)n_users});
+    add_ws("sp.nuniq", PAMREC_I32, {8});           // 0 item 1 cate 2 user
+    add_ws("cub_temp", PAMREC_U8, {(int64_t)(16u << 20) + 16 * NK});
+  }
+};
+
+}  // namespace pamrec

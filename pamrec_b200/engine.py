@@ -1,0 +1,247 @@
+"""Device engine: owns the torch-allocated pools, binds them to libpamrec_b200.so and drives one
+train / score step through the C ABI.  PyTorch is used for device memory and streams only."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+EMB = "sequential/embedding/"
+TABLES = {
+    EMB + "item_embedding": ("item", 16),
+    EMB + "cate_embedding": ("cate", 4),
+    EMB + "user_long_embedding": ("ulong", 20),
+    EMB + "user_short_embedding": ("ushort", 20),
+}
+# variables that exist in the reference graph but never receive a gradient: kept on the
+# host so that checkpoints carry the complete variable list of base_model.py:62.
+FROZEN = {
+    EMB + "user_embedding": lambda nu: (nu, 20),
+    EMB + "looptimes_embedding": lambda nu: (10, 4),
+    EMB + "play_lookup": lambda nu: (10, 40),
+}
+_TORCH_DTYPE = {L.F32: torch.float32, L.I32: torch.int32, L.F64: torch.float64, L.U8: torch.uint8}
+_ESIZE = {L.F32: 4, L.I32: 4, L.F64: 8, L.U8: 1}
+
+DEFAULT_HP = dict(learning_rate=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8, embed_l2=1e-6, layer_l2=1e-6,
+                  max_grad_norm=2.0, is_clip_norm=1, fuzhu_weight=0.5, discrepancy_loss_weight=0.1)
+
+BATCH_FIELDS = (  # name, dtype, per-row shape suffix, needed for scoring
+    ("item_history", np.int32, True), ("item_cate_history", np.int32, True), ("item_loop_times_history", np.float32, True),
+    ("mask", np.int32, True), ("users", np.int32, False), ("items", np.int32, False), ("cates", np.int32, False),
+    ("labels_satisfied", np.float32, False), ("labels_play", np.float32, False), ("plays", np.float32, False),
+)
+
+
+class PamrecError(RuntimeError):
+    pass
+
+
+class DeviceBatch:
+    """Device copies of one feed dict plus the PamrecBatch struct pointing at them."""
+
+    def __init__(self, tensors, batch):
+        self.tensors = tensors
+        self.batch = batch
+        self.struct = L.PamrecBatch(batch=batch, **{k: C.c_void_p(v.data_ptr()) for k, v in tensors.items()})
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.tensors.values())
+
+
+class Engine:
+    def __init__(self, n_users, n_items, n_cates, max_seq_len, max_batch, hp=None, sparse_adam="dense_exact",
+                 world_size=1, rank=0):
+        self.lib = L.load()
+        h = dict(DEFAULT_HP)
+        if hp:
+            h.update(hp)
+        self.hp = h
+        self.dims = (int(n_users), int(n_items), int(n_cates), int(max_seq_len), int(max_batch))
+        mode = {"dense_exact": L.ADAM_DENSE_EXACT, "lazy": L.ADAM_LAZY}[sparse_adam]
+        self.cfg = L.PamrecConfig(
+            n_users=n_users, n_items=n_items, n_cates=n_cates, max_seq_len=max_seq_len, max_batch=max_batch,
+            learning_rate=h["learning_rate"], beta1=h["beta1"], beta2=h["beta2"], epsilon=h["epsilon"],
+            embed_l2=h["embed_l2"], layer_l2=h["layer_l2"], max_grad_norm=h["max_grad_norm"],
+            is_clip_norm=int(h["is_clip_norm"]), fuzhu_weight=h["fuzhu_weight"],
+            order_weight=h["discrepancy_loss_weight"], sparse_adam_mode=mode, world_size=world_size, rank=rank)
+        self.handle = C.c_void_p()
+        rc = self.lib.pamrec_create(C.byref(self.cfg), C.byref(self.handle))
+        if rc != 0:
+            raise PamrecError(f"pamrec_create failed ({rc}): check vocabulary sizes, max_seq_len <= 256, max_batch")
+        self.dense_numel = self.lib.pamrec_dense_numel(self.handle)
+        self.bn_numel = self.lib.pamrec_bn_numel(self.handle)
+        self.workspace_bytes = self.lib.pamrec_workspace_bytes(self.handle)
+        self.info = {p: self._query(p) for p in (L.POOL_DENSE, L.POOL_BN, L.POOL_WORKSPACE)}
+        self.step = 0
+        self.device = None
+        self.frozen = {n: np.zeros(f(n_users), np.float32) for n, f in FROZEN.items()}
+
+    # ------------------------------------------------------------------ inventory (host only)
+    def _query(self, pool):
+        out = {}
+        info = L.PamrecTensorInfo()
+        for i in range(self.lib.pamrec_tensor_count(self.handle, pool)):
+            self._check(self.lib.pamrec_tensor_info(self.handle, pool, i, C.byref(info)))
+            out[info.name.decode()] = dict(offset=info.offset, numel=info.numel, dtype=info.dtype, flags=info.flags,
+                                           shape=tuple(info.shape[k] for k in range(info.ndim)))
+        return out
+
+    def variable_shapes(self):
+        """TF variable name -> shape for every variable of the reference graph."""
+        nu, ni, nc, T, _ = self.dims
+        shapes = {n: d["shape"] for n, d in self.info[L.POOL_DENSE].items()}
+        shapes.update({EMB + "item_embedding": (ni, 16), EMB + "cate_embedding": (nc, 4),
+                       EMB + "user_long_embedding": (nu, 20), EMB + "user_short_embedding": (nu, 20)})
+        shapes.update({n: a.shape for n, a in self.frozen.items()})
+        shapes.update({n: d["shape"] for n, d in self.info[L.POOL_BN].items()})
+        return shapes
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PamrecError(self.lib.pamrec_last_error(self.handle).decode() or f"error {rc}")
+
+    # ------------------------------------------------------------------ device memory
+    def allocate(self, device="cuda:0"):
+        if not torch.cuda.is_available():
+            raise PamrecError("pamrec_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        nu, ni, nc, T, B = self.dims
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)
+        self.pool = {k: z(self.dense_numel) for k in ("dense_param", "dense_grad", "dense_m", "dense_v")}
+        self.pool["bn_moving"] = z(self.bn_numel)
+        for pre, rows, w in (("item", ni, 16), ("cate", nc, 4), ("ulong", nu, 20), ("ushort", nu, 20)):
+            for s in ("w", "m", "v"):
+                self.pool[f"{pre}_{s}"] = z(rows, w)
+        self.pool["workspace"] = torch.zeros(self.workspace_bytes, dtype=torch.uint8, device=self.device)
+        bufs = L.PamrecBuffers(workspace_bytes=self.workspace_bytes,
+                               **{k: C.c_void_p(v.data_ptr()) for k, v in self.pool.items()})
+        self._check(self.lib.pamrec_bind(self.handle, C.byref(bufs), self._stream()))
+        return self
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def dense(self, name, which="dense_param"):
+        d = self.info[L.POOL_DENSE][name]
+        return self.pool[which][d["offset"]:d["offset"] + d["numel"]].view(d["shape"])
+
+    def bn(self, name):
+        d = self.info[L.POOL_BN][name]
+        return self.pool["bn_moving"][d["offset"]:d["offset"] + d["numel"]]
+
+    def ws(self, name, rows=None):
+        """View of a workspace tensor (first dimension optionally cut to `rows`)."""
+        d = self.info[L.POOL_WORKSPACE][name]
+        raw = self.pool["workspace"][d["offset"]:d["offset"] + d["numel"] * _ESIZE[d["dtype"]]]
+        t = raw.view(_TORCH_DTYPE[d["dtype"]])
+        shape = d["shape"]
+        if rows is not None:
+            inner = int(np.prod(shape[1:])) if len(shape) > 1 else 1
+            return t[:rows * inner].view((rows,) + tuple(shape[1:]))
+        return t.view(shape)
+
+    # ------------------------------------------------------------------ variables by TF name
+    def set_variables(self, variables):
+        """variables: TF name -> array.  Unknown names raise; missing names keep their current value."""
+        for name, val in variables.items():
+            t = torch.as_tensor(np.asarray(val, dtype=np.float32))
+            if name in TABLES:
+                self.pool[TABLES[name][0] + "_w"].copy_(t.to(self.device))
+            elif name in self.info[L.POOL_DENSE]:
+                self.dense(name).copy_(t.to(self.device).view(self.dense(name).shape))
+            elif name in self.info[L.POOL_BN]:
+                self.bn(name).copy_(t.to(self.device))
+            elif name in self.frozen:
+                self.frozen[name] = np.asarray(val, dtype=np.float32).copy()
+            else:
+                raise KeyError(f"unknown variable {name}")
+
+    def get_variables(self, pools=("var", "bn")):
+        out = {}
+        if "var" in pools:
+            for name in self.info[L.POOL_DENSE]:
+                out[name] = self.dense(name).detach().cpu().numpy().copy()
+            for name, (pre, _) in TABLES.items():
+                out[name] = self.pool[pre + "_w"].detach().cpu().numpy().copy()
+            out.update({n: a.copy() for n, a in self.frozen.items()})
+        if "bn" in pools:
+            for name in self.info[L.POOL_BN]:
+                out[name] = self.bn(name).detach().cpu().numpy().copy()
+        return out
+
+    def get_optimizer_state(self):
+        st = {"step": self.step}
+        for name in self.info[L.POOL_DENSE]:
+            st[name + "/Adam"] = self.dense(name, "dense_m").detach().cpu().numpy().copy()
+            st[name + "/Adam_1"] = self.dense(name, "dense_v").detach().cpu().numpy().copy()
+        for name, (pre, _) in TABLES.items():
+            st[name + "/Adam"] = self.pool[pre + "_m"].detach().cpu().numpy().copy()
+            st[name + "/Adam_1"] = self.pool[pre + "_v"].detach().cpu().numpy().copy()
+        return st
+
+    # ------------------------------------------------------------------ batches
+    def upload(self, feed, training=True):
+        """feed: the reference's feed dict with string keys (io/sequential_iterator.py:1155-1175)."""
+        B = int(np.asarray(feed["items"]).shape[0])
+        T = self.dims[3]
+        tensors = {}
+        for name, dt, is_seq in BATCH_FIELDS:
+            if name not in feed:
+                if training or name in ("item_history", "item_cate_history", "item_loop_times_history", "mask", "items", "cates"):
+                    raise KeyError(f"feed is missing {name}")
+                continue
+            a = np.ascontiguousarray(np.asarray(feed[name]).reshape((B, T) if is_seq else (B,)).astype(dt, copy=False))
+            tensors[name] = torch.from_numpy(a).to(self.device, non_blocking=True)
+        for name, _, _ in BATCH_FIELDS:          # scoring: unused pointers stay null
+            if name not in tensors:
+                tensors[name] = torch.empty(0, device=self.device)
+        db = DeviceBatch(tensors, B)
+        for name, _, _ in BATCH_FIELDS:
+            if tensors[name].numel() == 0:
+                setattr(db.struct, name, None)
+        return db
+
+    # ------------------------------------------------------------------ steps
+    def gather(self, db):
+        self._check(self.lib.pamrec_gather_fwd(self.handle, C.byref(db.struct), None, self._stream()))
+        return self.ws("x0", db.batch)
+
+    def forward(self, db, training=False, want_pred=True):
+        pred = torch.empty(db.batch, dtype=torch.float32, device=self.device) if want_pred else None
+        self._check(self.lib.pamrec_forward(self.handle, C.byref(db.struct), int(training),
+                                            C.c_void_p(pred.data_ptr()) if want_pred else None, self._stream()))
+        return pred
+
+    def backward(self, db):
+        self._check(self.lib.pamrec_backward(self.handle, C.byref(db.struct), self._stream()))
+
+    def apply_gradients(self, db):
+        self.step += 1
+        self._check(self.lib.pamrec_apply_gradients(self.handle, C.byref(db.struct), self.step, self._stream()))
+        return self.ws("losses")[:5]
+
+    def train_step(self, db, losses_out=None):
+        """One optimisation step; returns a device tensor [loss, data, regular, auxiliary, order] (pamrec.py:444-448)."""
+        self.step += 1
+        if losses_out is None:
+            losses_out = torch.empty(5, dtype=torch.float32, device=self.device)
+        self._check(self.lib.pamrec_train_step(self.handle, C.byref(db.struct), self.step,
+                                               C.c_void_p(losses_out.data_ptr()), self._stream()))
+        return losses_out
+
+    def launches(self):
+        return int(self.lib.pamrec_last_launch_count(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.lib.pamrec_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
