@@ -495,8 +495,10 @@ class OracleModel:
         # Adam (tf.train.AdamOptimizer, TF 2.4 adam.py): beta powers start at beta -> t = step+1
         self.step += 1
         t = self.step
-        b1, b2, eps = hp["beta1"], hp["beta2"], hp["epsilon"]
-        lr_t = hp["learning_rate"] * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+        # TF holds lr / beta1 / beta2 / epsilon and the beta powers as float32 tensors: round them the same way
+        f32 = lambda x: float(np.float32(x))
+        b1, b2, eps = f32(hp["beta1"]), f32(hp["beta2"]), f32(hp["epsilon"])
+        lr_t = f32(hp["learning_rate"]) * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
         for n, g in grads.items():
             g = g * scales[n]
             grp = self.group_of[n]

@@ -23,7 +23,7 @@ __device__ __forceinline__ float bn_relu(float z, const float* stat, const float
 __global__ void __launch_bounds__(kRows) k_dense_fwd(const DenseP p) {
   extern __shared__ __align__(16) float sm[];
   float* Xs = sm;                       // [K][129]
-  float* Wc = Xs + p.K * kXs;           // [K][16]
+  float* Wc = Xs + ((p.K * kXs + 3) & ~3);   // [K][16], 16-byte aligned
   const int tid = threadIdx.x, lane = tid & 31;
   const int nchunk = (p.N + kNc - 1) / kNc;
   const int g = blockIdx.y / nchunk, c0 = (blockIdx.y % nchunk) * kNc;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kRows) k_dense_fwd(const DenseP p) {
 
 void launch_dense_fwd(const DenseP& p, cudaStream_t st) {
   static int smem_set = 0;
-  int smem = p.K * (kXs + kNc) * 4;
+  int smem = (p.K * (kXs + kNc) + 4) * 4;
   if (smem > smem_set) { cudaFuncSetAttribute(k_dense_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set = smem; }
   int nchunk = (p.N + kNc - 1) / kNc;
   dim3 grid((p.M + kRows - 1) / kRows, p.n_groups * nchunk);
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kRows) k_dense_dx(const DenseDxP p) {
     const int N = p.Ncon[s][ci], dzo = p.dz_off[s][ci];
     const float* W = p.Wbase + p.w_off[s][ci];
     float* Gs = sm;                 // [N][129]
-    float* Wt = Gs + N * kXs;       // [N][16]  Wt[n][kk] = W[k0+kk][n]
+    float* Wt = Gs + ((N * kXs + 3) & ~3);   // [N][16]  Wt[n][kk] = W[k0+kk][n]  (16-byte aligned)
     __syncthreads();
     for (int i = tid; i < kRows * N; i += kRows) {
       int r = i / N, n = i % N;
@@ -143,7 +143,7 @@ void launch_dense_dx(const DenseDxP& p, cudaStream_t st) {
   int maxN = 1;
   for (int s = 0; s < p.n_slices; ++s)
     for (int c = 0; c < p.n_contrib[s]; ++c) maxN = max(maxN, p.Ncon[s][c]);
-  int smem = maxN * (kXs + kNc) * 4;
+  int smem = (maxN * (kXs + kNc) + 4) * 4;
   if (smem > smem_set) { cudaFuncSetAttribute(k_dense_dx, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set = smem; }
   int kchunk = (p.K + kNc - 1) / kNc;
   dim3 grid((p.M + kRows - 1) / kRows, p.n_slices * kchunk);

@@ -1,0 +1,239 @@
+"""Host-side mirror of the reference's ``reco_utils/recommender/deeprec/deeprec_utils.py`` for the PAMRec
+path: the two-level hparams YAML -> flat ``HParams`` object, and the ranking metrics used by
+``run_eval`` / ``run_weighted_eval``.  Same function names, arguments and error behaviour as the
+reference (citations: DU = deeprec_utils.py in the reference tree); no TensorFlow.
+"""
+import pickle
+
+import numpy as np
+import yaml
+from sklearn.metrics import accuracy_score, f1_score, log_loss, mean_squared_error, roc_auc_score
+
+__all__ = ["prepare_hparams", "create_hparams", "HParams", "load_yaml", "flat_config", "check_type", "check_nn_config",
+           "cal_metric", "cal_weighted_metric", "mrr_score", "ndcg_score", "dcg_score", "hit_score", "load_dict",
+           "filter_single_class_users"]
+
+
+# ----------------------------------------------------------------------------- configuration
+def flat_config(config):
+    """DU:27-41: {section: {key: value}} -> {key: value} (later sections win)."""
+    flat = {}
+    for section in config.values():
+        flat.update(section)
+    return flat
+
+
+_INT_KEYS = ("epochs", "batch_size", "show_step", "save_epoch", "item_embedding_dim", "cate_embedding_dim",
+             "user_embedding_dim", "max_seq_length", "hidden_size", "min_seq_length", "attention_size", "train_num_ngs")
+_FLOAT_KEYS = ("init_value", "learning_rate", "embed_l2", "embed_l1", "layer_l2", "layer_l1")
+_STR_KEYS = ("method", "loss", "optimizer", "init_method", "user_vocab", "item_vocab", "cate_vocab")
+_LIST_KEYS = ("layer_sizes", "activation", "dropout", "att_fcn_layer_sizes")
+
+
+def check_type(config):
+    """DU:44-137: TypeError with the reference's message when a known key has the wrong type."""
+    for keys, typ, word in ((_INT_KEYS, int, "int"), (_FLOAT_KEYS, float, "float"), (_STR_KEYS, str, "str"),
+                            (_LIST_KEYS, list, "list")):
+        for k in keys:
+            if k in config and not isinstance(config[k], typ):
+                raise TypeError("Parameters {0} must be {1}".format(k, word))
+
+
+def check_nn_config(f_config):
+    """DU:140-297.  ``model_type: mmoe`` (what PAMRec loads, config/mmoe.yaml:11) has no required-key list
+    in the reference, so only the type check applies; a missing model_type is a KeyError as there."""
+    f_config["model_type"]
+    check_type(f_config)
+
+
+def load_yaml(filename):
+    """DU:310-326."""
+    try:
+        with open(filename, "r") as f:
+            return yaml.load(f, yaml.SafeLoader)
+    except FileNotFoundError:
+        raise
+    except Exception:
+        raise IOError("load {0} error!".format(filename))
+
+
+class HParams:
+    """DU:329-363: attribute access over a dict whose values must be int / float / str / list."""
+
+    def __init__(self, hparams_dict):
+        for val in hparams_dict.values():
+            if not isinstance(val, (int, float, str, list)):
+                raise ValueError("Hyperparameter value {} should be integer, float, string or list.".format(val))
+        self._values = hparams_dict
+        for k, v in hparams_dict.items():
+            setattr(self, k, v)
+
+    def __repr__(self):
+        return "HParams object with values {}".format(self._values.__repr__())
+
+    def values(self):
+        return self._values
+
+
+# defaults that the PAMRec path can observe (DU:375-445); keys of other model families are not carried.
+_DEFAULTS = {
+    "user_dropout": False, "dropout": [0.0], "load_saved_model": False,
+    "init_method": "tnormal", "init_value": 0.01,
+    "embed_l2": 0.0, "embed_l1": 0.0, "layer_l2": 0.0, "layer_l1": 0.0, "cross_l2": 0.0, "cross_l1": 0.0,
+    "attn_loss_weight": 0.0, "contrastive_loss": "bpr", "triplet_margin": 1.0, "discrepancy_loss_weight": 0.0,
+    "contrastive_loss_weight": 0.0, "contrastive_length_threshold": 1, "contrastive_recent_k": 3,
+    "learning_rate": 0.001, "max_grad_norm": 2, "is_clip_norm": 0, "manual_alpha": False, "manual_alpha_value": 0.5,
+    "interest_evolve": True, "predict_long_short": True, "dtype": 32, "optimizer": "adam", "epochs": 10, "batch_size": 1,
+    "enable_BN": False, "show_step": 1, "save_model": True, "save_epoch": 5, "write_tfevents": False,
+    "train_num_ngs": 4, "need_sample": True, "embedding_dropout": 0.3, "EARLY_STOP": 100, "min_seq_length": 1,
+    "sequential_model": "time4lstm", "time_unit": "s",
+}
+
+
+def create_hparams(flags):
+    """DU:366-446."""
+    d = dict(_DEFAULTS)
+    d.update(flags)
+    return HParams(d)
+
+
+def prepare_hparams(yaml_file=None, **kwargs):
+    """DU:625-645: YAML (optional) overridden by keyword arguments, type-checked, defaults merged."""
+    config = flat_config(load_yaml(yaml_file)) if yaml_file is not None else {}
+    config.update(kwargs)
+    check_nn_config(config)
+    return create_hparams(config)
+
+
+def load_dict(filename):
+    """DU:985-997: vocabulary pickle."""
+    with open(filename, "rb") as f:
+        return pickle.load(f)
+
+
+# ----------------------------------------------------------------------------- metrics
+def mrr_score(y_true, y_score):
+    """DU:665-678."""
+    order = np.argsort(y_score)[::-1]
+    y_true = np.take(y_true, order)
+    return np.sum(y_true / (np.arange(len(y_true)) + 1)) / np.sum(y_true)
+
+
+def dcg_score(y_true, y_score, k=10):
+    """DU:732-747: gain 2^y - 1, log2 discount."""
+    k = min(np.shape(y_true)[-1], k)
+    order = np.argsort(y_score)[::-1]
+    y_true = np.take(y_true, order[:k])
+    return np.sum((2 ** y_true - 1) / np.log2(np.arange(len(y_true)) + 2))
+
+
+def ndcg_score(y_true, y_score, k=10):
+    """DU:681-694."""
+    return dcg_score(y_true, y_score, k) / dcg_score(y_true, y_true, k)
+
+
+def hit_score(y_true, y_score, k=10):
+    """DU:713-729: fraction of the top-k that are positives (hits / len(top-k), not 0/1)."""
+    positives = set(np.where(np.asarray(y_true) == 1)[0].tolist())
+    top = np.argsort(y_score)[::-1][:k]
+    return sum(1 for i in top if i in positives) / len(top)
+
+
+def _ks(metric, default):
+    parts = metric.split("@")
+    return [int(t) for t in parts[1].split(";")] if len(parts) > 1 else default
+
+
+def cal_metric(labels, preds, metrics):
+    """DU:750-828.  Point metrics take flat lists; mean_mrr / ndcg@ / hit@ / group_auc take lists of groups."""
+    res = {}
+    if not metrics:
+        return res
+    for metric in metrics:
+        if metric == "auc":
+            res["auc"] = round(roc_auc_score(np.asarray(labels), np.asarray(preds)), 4)
+        elif metric == "rmse":
+            res["rmse"] = np.sqrt(round(mean_squared_error(np.asarray(labels), np.asarray(preds)), 4))
+        elif metric == "logloss":
+            preds = [max(min(p, 1.0 - 10e-12), 10e-12) for p in preds]
+            res["logloss"] = round(log_loss(np.asarray(labels), np.asarray(preds)), 4)
+        elif metric == "acc":
+            res["acc"] = round(accuracy_score(np.asarray(labels), (np.asarray(preds) >= 0.5).astype(np.float64)), 4)
+        elif metric == "f1":
+            res["f1"] = round(f1_score(np.asarray(labels), (np.asarray(preds) >= 0.5).astype(np.float64)), 4)
+        elif metric == "mean_mrr":
+            res["mean_mrr"] = round(np.mean([mrr_score(l, p) for l, p in zip(labels, preds)]), 4)
+        elif metric.startswith("ndcg"):
+            for k in _ks(metric, [1, 2]):
+                res["ndcg@{0}".format(k)] = round(np.mean([ndcg_score(l, p, k) for l, p in zip(labels, preds)]), 4)
+        elif metric.startswith("hit"):
+            for k in _ks(metric, [1, 2]):
+                res["hit@{0}".format(k)] = round(np.mean([hit_score(l, p, k) for l, p in zip(labels, preds)]), 4)
+        elif metric == "group_auc":
+            res["group_auc"] = round(np.mean([roc_auc_score(l, p) for l, p in zip(labels, preds)]), 4)
+        else:
+            raise ValueError("not define this metric {0}".format(metric))
+    return res
+
+
+def _user_groups(users, preds, labels):
+    """Rows of each user in first-to-last order, users sorted ascending (pandas groupby order)."""
+    users = np.asarray(users)
+    preds = np.asarray(preds, dtype=np.float64)
+    labels = np.asarray(labels, dtype=np.float64)
+    order = np.argsort(users, kind="stable")
+    su = users[order]
+    cuts = np.flatnonzero(su[1:] != su[:-1]) + 1
+    return [(labels[idx], preds[idx]) for idx in np.split(order, cuts)] if len(users) else []
+
+
+def cal_weighted_metric(users, preds, labels, metrics):
+    """DU:831-971: per-user metric weighted by the user's share of rows (wauc, wmrr, wmrr@k, whit@k, wndcg@k)."""
+    res = {}
+    if not metrics:
+        return res
+    groups = _user_groups(users, preds, labels)
+    total = float(sum(len(l) for l, _ in groups))
+    weights = [len(l) / total for l, _ in groups]
+
+    def wsum(fn):
+        return sum(w * fn(l, p) for w, (l, p) in zip(weights, groups))
+
+    def sub_mrr(y_true, y_score, k):                      # DU:925-931
+        order = np.argsort(y_score)[::-1][:k]
+        y = np.take(y_true, order)
+        return np.sum(y / (np.arange(len(y)) + 1))
+
+    for metric in metrics:
+        if metric == "wauc":
+            res["wauc"] = round(wsum(lambda l, p: roc_auc_score(l, p)), 4)
+        elif metric == "wmrr":
+            res["wmrr"] = round(wsum(mrr_score), 4)
+        elif metric.startswith("wmrr"):
+            for k in _ks(metric, [10]):
+                res["wmrr@{0}".format(k)] = round(wsum(lambda l, p, k=k: sub_mrr(l, p, k)), 4)
+        elif metric.startswith("whit"):
+            for k in _ks(metric, [1, 2]):
+                res["whit@{0}".format(k)] = round(wsum(lambda l, p, k=k: hit_score(l, p, k)), 4)
+        elif metric.startswith("wndcg"):
+            for k in _ks(metric, [1, 2]):
+                res["wndcg@{0}".format(k)] = round(wsum(lambda l, p, k=k: ndcg_score(l, p, k)), 4)
+        else:
+            raise ValueError("not define this metric {0}".format(metric))
+    return res
+
+
+def filter_single_class_users(users, preds, labels):
+    """sequential_base_model.py:466-486: drop every user whose labels are all 0 or all 1.  The reference does it with a
+    groupby.apply + inner merge on the left frame, which keeps the surviving rows in their original order."""
+    users = np.asarray(users)
+    preds = np.asarray(preds)
+    labels = np.asarray(labels)
+    if len(users) == 0:
+        return [], [], []
+    uniq, inv = np.unique(users, return_inverse=True)
+    n_rows = np.bincount(inv, minlength=len(uniq))
+    n_zero = np.bincount(inv, weights=(labels == 0).astype(np.float64), minlength=len(uniq))
+    mixed = (n_zero != 0) & (n_zero != n_rows)
+    keep = mixed[inv]
+    return users[keep].tolist(), preds[keep].tolist(), labels[keep].tolist()

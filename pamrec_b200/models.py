@@ -1,0 +1,391 @@
+"""Host-side mirror of the reference's model classes for the PAMRec path.
+
+``PAMRECModel(hparams, iterator_creator, graph=None, seed=None)`` keeps the public surface that
+``example/00_quick_start/sequential.py`` drives (reference files: PAM = models/sequential/pamrec.py,
+SBM = models/sequential/sequential_base_model.py, BM = models/base_model.py):
+
+    fit_step, fit, run_weighted_eval, run_eval, predict, load_model,
+    train(sess, feed), eval(sess, feed), eval_with_user(sess, feed), infer(sess, feed)
+
+``sess`` arguments are accepted and ignored: the "session" is a ``pamrec_b200.engine.Engine`` that runs the
+whole step as hand-written CUDA kernels behind the C ABI.  There is no CPU path.
+"""
+import math
+import os
+import random
+import time
+
+import numpy as np
+import torch
+
+from .deeprec_utils import cal_metric, cal_weighted_metric, filter_single_class_users, load_dict
+from .engine import Engine, EMB, TABLES
+
+__all__ = ["PAMRECModel", "SequentialBaseModel", "BaseModel", "latest_checkpoint", "initial_variables"]
+
+
+# ----------------------------------------------------------------------------- initial values
+def initial_variables(shapes, hparams, seed):
+    """Initial value of every variable by TF name.
+
+    Same initializer families as the reference: ``hparams.init_method`` for variables created under a scope
+    that carries ``self.initializer`` (BM:165-193), TF's default glorot_uniform for the time-aware tables and
+    conv1d kernels, zeros for biases / LN beta / BN beta, ones for LN gamma / BN gamma / moving variance.
+    TF's Philox streams are not reproducible, so the draws come from a seeded torch generator.
+    """
+    g = torch.Generator().manual_seed(0 if seed is None else int(seed))
+    sigma = float(hparams.init_value)
+    method = hparams.init_method
+    out = {}
+    for name, shape in shapes.items():
+        leaf = name.rsplit("/", 1)[-1]
+        shape = tuple(int(s) for s in shape)
+        if leaf in ("moving_mean", "beta", "bias") or leaf.startswith("b_nn_") or name.endswith("ln/Variable") \
+                or name.endswith("ln_1/Variable"):
+            t = torch.zeros(shape)
+        elif leaf in ("moving_variance", "gamma", "Variable_1"):
+            t = torch.ones(shape)
+        elif leaf.endswith("timeaware_embedding") or leaf == "kernel":
+            fan_in, fan_out = (shape[0] * shape[1], shape[0] * shape[2]) if len(shape) == 3 else shape
+            lim = math.sqrt(6.0 / (fan_in + fan_out))
+            t = (torch.rand(shape, generator=g) * 2 - 1) * lim
+        elif method == "uniform":
+            t = (torch.rand(shape, generator=g) * 2 - 1) * sigma
+        elif method == "normal":
+            t = torch.randn(shape, generator=g) * sigma
+        elif method in ("tnormal",) or method not in ("xavier_normal", "xavier_uniform", "he_normal", "he_uniform"):
+            t = torch.empty(shape)
+            torch.nn.init.trunc_normal_(t, mean=0.0, std=sigma, a=-2 * sigma, b=2 * sigma, generator=g)
+        else:
+            fan_in, fan_out = (shape[0], shape[-1]) if len(shape) > 1 else (shape[0], shape[0])
+            if method.startswith("xavier"):
+                std = math.sqrt(2.0 / (fan_in + fan_out))
+            else:
+                std = math.sqrt(2.0 / fan_in)
+            if method.endswith("uniform"):
+                t = (torch.rand(shape, generator=g) * 2 - 1) * (std * math.sqrt(3.0))
+            else:
+                t = torch.randn(shape, generator=g) * std
+        out[name] = t.numpy().astype(np.float32)
+    return out
+
+
+# ----------------------------------------------------------------------------- checkpoints
+def latest_checkpoint(model_dir):
+    """tf.train.latest_checkpoint: reads ``<dir>/checkpoint`` written by Saver.save."""
+    idx = os.path.join(model_dir, "checkpoint")
+    if not os.path.exists(idx):
+        return None
+    with open(idx) as f:
+        for line in f:
+            if line.startswith("model_checkpoint_path:"):
+                name = line.split(":", 1)[1].strip().strip('"')
+                return name if os.path.isabs(name) else os.path.join(model_dir, name)
+    return None
+
+
+class Saver:
+    """Counterpart of ``tf.train.Saver(max_to_keep=epochs)`` (BM:62).  One ``<path>.npz`` per checkpoint keyed by TF
+    variable name: model variables + BN moving statistics — exactly the Saver's var-list in the reference, which is
+    built before the optimizer exists, so Adam slots are NOT part of a checkpoint."""
+
+    def __init__(self, model, max_to_keep=5):
+        self.model = model
+        self.max_to_keep = max(int(max_to_keep), 1)
+        self.kept = []
+
+    def save(self, sess=None, save_path=None):
+        d = os.path.dirname(save_path)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        variables = self.model.engine.get_variables()
+        np.savez(save_path + ".npz", **{k.replace("/", "|"): v for k, v in variables.items()})
+        self.kept.append(save_path)
+        while len(self.kept) > self.max_to_keep:
+            old = self.kept.pop(0)
+            if os.path.exists(old + ".npz"):
+                os.remove(old + ".npz")
+        with open(os.path.join(d, "checkpoint"), "w") as f:
+            f.write('model_checkpoint_path: "{}"\n'.format(os.path.basename(save_path)))
+            for p in self.kept:
+                f.write('all_model_checkpoint_paths: "{}"\n'.format(os.path.basename(p)))
+        return save_path
+
+    def restore(self, sess, path):
+        with np.load(path + ".npz") as z:
+            self.model.engine.set_variables({k.replace("|", "/"): z[k] for k in z.files})
+
+
+class _Session:
+    """Placeholder for ``tf.Session``: kept so that ``model.sess`` exists."""
+    graph = None
+
+
+# ----------------------------------------------------------------------------- models
+class BaseModel:
+    def __init__(self, hparams, iterator_creator, graph=None, seed=None):
+        """BM:20-75: seed python/numpy RNGs, build iterator, variables and the device session."""
+        self.seed = seed
+        np.random.seed(seed)
+        random.seed(seed)
+        self.graph = graph
+        self.iterator = iterator_creator(hparams, self.graph)
+        self.train_num_ngs = hparams.train_num_ngs
+        self.hparams = hparams
+        self.keep_prob_train = 1 - np.array(hparams.dropout)
+        self.keep_prob_test = np.ones_like(hparams.dropout)
+        self._check_supported(hparams)
+        self._build_graph()
+        self.saver = Saver(self, max_to_keep=hparams.epochs)
+        self.sess = _Session()
+
+    def _check_supported(self, hp):
+        """The kernels implement the graph that config/mmoe.yaml + the quick-start flags build; anything that would
+        change the arithmetic is refused rather than silently approximated."""
+        def need(cond, what):
+            if not cond:
+                raise ValueError("pamrec_b200: unsupported configuration: " + what)
+        need(hp.method == "classification", "method must be classification (BM:93-113)")
+        need(hp.loss == "cross_entropy_loss", "loss must be cross_entropy_loss")
+        need(hp.optimizer == "adam", "optimizer must be adam (BM:270-271)")
+        need(hp.item_embedding_dim == 16 and hp.cate_embedding_dim == 4 and hp.user_embedding_dim == 20,
+             "embedding dims must be 16 / 4 / 20 (config/mmoe.yaml:22-24)")
+        need(list(hp.layer_sizes) == [100, 64] and list(hp.expert_layer_sizes) == [100, 64] and
+             list(hp.gate_layer_sizes) == [64, 5] and hp.expert_num == 5, "tower / expert / gate sizes of config/mmoe.yaml")
+        need(list(hp.activation)[:2] == ["relu", "relu"], "activation must be [relu, relu]")
+        need(bool(hp.enable_BN), "enable_BN must be True")
+        need(all(float(d) == 0.0 for d in hp.dropout) and float(hp.embedding_dropout) == 0.0 and not hp.user_dropout,
+             "dropout must be 0 (SURVEY.md Appendix A)")
+        need(not getattr(hp, "add_feature", False), "add_feature must be False")
+        need(not getattr(hp, "fine_tune", False), "fine_tune must be False")
+        need(float(hp.embed_l1) == 0.0 and float(hp.layer_l1) == 0.0 and float(hp.cross_l1) == 0.0 and
+             float(hp.cross_l2) == 0.0, "L1 / cross regularisation must be 0")
+        need(1 <= hp.max_seq_length <= 256, "max_seq_length must be in [1, 256]")
+        need(hp.batch_size % 5 == 0, "batch_size must be a multiple of 5 (IT:684-685, PAM:73-75)")
+
+    def _build_graph(self):
+        raise NotImplementedError
+
+    # ---- BM:350-399
+    def train(self, sess, feed_dict):
+        raise NotImplementedError
+
+    def load_model(self, model_path=None):
+        """BM:401-417."""
+        act_path = self.hparams.load_saved_model
+        if model_path is not None:
+            act_path = model_path
+        try:
+            self.saver.restore(self.sess, act_path)
+        except Exception:
+            raise IOError("Failed to find any matching files for {0}".format(act_path))
+
+
+class SequentialBaseModel(BaseModel):
+    def __init__(self, hparams, iterator_creator, graph=None, seed=None):
+        """SBM:22-54."""
+        self.hparams = hparams
+        self.need_sample = hparams.need_sample
+        self.train_num_ngs = hparams.train_num_ngs
+        if self.train_num_ngs is None:
+            raise ValueError("Please confirm the number of negative samples for each positive instance.")
+        self.min_seq_length = hparams.min_seq_length
+        self.hidden_size = hparams.hidden_size
+        self.embedding_keep_prob_train = 1.0 - hparams.embedding_dropout
+        self.embedding_keep_prob_test = 1.0
+        super().__init__(hparams, iterator_creator, graph=graph, seed=seed)
+
+    # ------------------------------------------------------------------ device steps
+    def _score(self, feed_dict):
+        db = self.engine.upload(feed_dict, training=False)
+        return self.engine.forward(db, training=False).cpu().numpy().reshape(-1, 1)
+
+    def eval(self, sess, feed_dict):
+        """SBM:415-418 / BM:373-386 -> (pred [B,1], labels [B,1])."""
+        return self._score(feed_dict), np.asarray(feed_dict["labels_satisfied"], np.float32).reshape(-1, 1)
+
+    def eval_with_user(self, sess, feed_dict):
+        """SBM:502-516 -> (users [B], pred [B,1], labels [B,1])."""
+        users = np.asarray(feed_dict["users"]).astype(np.int32)
+        return users, self._score(feed_dict), np.asarray(feed_dict["labels_satisfied"], np.float32).reshape(-1, 1)
+
+    def infer(self, sess, feed_dict):
+        """SBM:557-560 / BM:388-399 -> [pred]."""
+        return [self._score(feed_dict)]
+
+    # ------------------------------------------------------------------ loops
+    def _maybe_save(self, progress, tag):
+        if self.hparams.save_model and self.hparams.MODEL_DIR:
+            if not os.path.exists(self.hparams.MODEL_DIR):
+                os.makedirs(self.hparams.MODEL_DIR)
+            if progress:
+                self.saver.save(sess=self.sess, save_path=self.hparams.MODEL_DIR + tag)
+
+    def fit(self, train_file, valid_file, valid_num_ngs, eval_metric="group_auc"):
+        """SBM:133-224: epoch loop, evaluation after every epoch, early stop on epochs."""
+        if not self.need_sample and self.train_num_ngs < 1:
+            raise ValueError("Please specify a positive integer of negative numbers for training without sampling needed.")
+        if valid_num_ngs < 1:
+            raise ValueError("Please specify a positive integer of negative numbers for validation.")
+        if self.need_sample and self.train_num_ngs < 1:
+            self.train_num_ngs = 1
+        eval_info = []
+        best_metric, self.best_epoch = 0, 0
+        for epoch in range(1, self.hparams.epochs + 1):
+            self.hparams.current_epoch = epoch
+            file_iterator = self.iterator.load_data_from_file(train_file, min_seq_length=self.min_seq_length,
+                                                              batch_num_ngs=self.train_num_ngs)
+            self.batch_train(file_iterator, self.sess)
+            valid_res = self.run_weighted_eval(valid_file, valid_num_ngs)
+            print("eval valid at epoch {0}: {1}".format(epoch, ",".join(str(k) + ":" + str(v) for k, v in valid_res.items())))
+            eval_info.append((epoch, valid_res))
+            progress = False
+            early_stop = self.hparams.EARLY_STOP
+            if valid_res[eval_metric] > best_metric:
+                best_metric = valid_res[eval_metric]
+                self.best_epoch = epoch
+                progress = True
+            elif early_stop > 0 and epoch - self.best_epoch >= early_stop:
+                print("early stop at epoch {0}!".format(epoch))
+                break
+            self._maybe_save(progress, "epoch_" + str(epoch))
+        print(eval_info)
+        print("best step: {0}".format(self.best_epoch))
+        return self
+
+    def fit_step(self, train_file, valid_file, valid_num_ngs, eval_metric="group_auc"):
+        """SBM:239-377: step loop, evaluation every ``eval_step`` steps, early stop on steps, checkpoint on improvement."""
+        if self.need_sample and self.train_num_ngs < 1:
+            self.train_num_ngs = 1
+        eval_info = []
+        best_metric, self.best_step = 0, 0
+        step = 0
+        break_flag = False
+        for epoch in range(1, self.hparams.epochs + 1):
+            print("epoch:{}".format(epoch))
+            if break_flag:
+                break
+            self.hparams.current_epoch = epoch
+            file_iterator = self.iterator.load_data_from_file(train_file, min_seq_length=self.min_seq_length,
+                                                              batch_num_ngs=self.train_num_ngs)
+            for batch_data_input in file_iterator:
+                if not batch_data_input:
+                    continue
+                step_result = self.train(self.sess, batch_data_input)
+                self.step_train(step, step_result)
+                step += 1
+                if step % self.hparams.eval_step == 0:
+                    valid_res = self.run_weighted_eval(valid_file, valid_num_ngs)
+                    print("eval valid at epoch {0} step {1}: {2}".format(
+                        epoch, step, ",".join(str(k) + ":" + str(v) for k, v in valid_res.items())))
+                    eval_info.append((step, valid_res))
+                    progress = False
+                    early_stop = self.hparams.EARLY_STOP
+                    if valid_res[eval_metric] > best_metric:
+                        best_metric = valid_res[eval_metric]
+                        self.best_step = step
+                        progress = True
+                    elif early_stop > 0 and step - self.best_step >= early_stop * self.hparams.eval_step:
+                        print("early stop at epoch {0}, step {1}!".format(epoch, step))
+                        break_flag = True
+                        break
+                    self._maybe_save(progress, "step_" + str(step))
+        print(eval_info)
+        print("best step: {0}".format(self.best_step))
+        return self
+
+    def run_eval(self, filename, num_ngs):
+        """SBM:380-413."""
+        preds, labels, group_preds, group_labels = [], [], [], []
+        group = num_ngs + 1
+        for feed in self.iterator.load_data_from_file(filename, min_seq_length=self.min_seq_length, batch_num_ngs=0):
+            if feed:
+                step_pred, step_labels = self.eval(self.sess, feed)
+                preds.extend(np.reshape(step_pred, -1))
+                labels.extend(np.reshape(step_labels, -1))
+                group_preds.extend(np.reshape(step_pred, (-1, group)))
+                group_labels.extend(np.reshape(step_labels, (-1, group)))
+        res = cal_metric(labels, preds, self.hparams.metrics)
+        res.update(cal_metric(group_labels, group_preds, self.hparams.pairwise_metrics))
+        return res
+
+    def run_weighted_eval(self, filename, num_ngs, calc_mean_alpha=False, manual_alpha=False):
+        """SBM:420-500: score every impression, drop groups without a positive (pairwise metrics) and users whose labels
+        are all 0 or all 1 (point + user-weighted metrics)."""
+        if calc_mean_alpha:
+            raise NotImplementedError("alpha outputs belong to the CLSR models, not to PAMRec (SBM:518-532)")
+        users, preds, labels, group_preds, group_labels = [], [], [], [], []
+        group = num_ngs + 1
+        for feed in self.iterator.load_data_from_file(filename, min_seq_length=self.min_seq_length, batch_num_ngs=0):
+            if not feed:
+                continue
+            step_user, step_pred, step_labels = self.eval_with_user(self.sess, feed)
+            users.extend(np.reshape(step_user, -1))
+            preds.extend(np.reshape(step_pred, -1))
+            labels.extend(np.reshape(step_labels, -1))
+            gp = np.reshape(step_pred, (-1, group))
+            for i, ag in enumerate(np.reshape(step_labels, (-1, group))):
+                if sum(ag) != 0:
+                    group_preds.append(gp[i])
+                    group_labels.append(ag)
+        users, preds, labels = filter_single_class_users(users, preds, labels)
+        res = cal_metric(labels, preds, self.hparams.metrics)
+        res.update(cal_metric(group_labels, group_preds, self.hparams.pairwise_metrics))
+        res.update(cal_weighted_metric(users, preds, labels, self.hparams.weighted_metrics))
+        return res
+
+    def predict(self, infile_name, outfile_name):
+        """SBM:534-555: one score per line."""
+        with open(outfile_name, "w") as wt:
+            for feed in self.iterator.load_data_from_file(infile_name, batch_num_ngs=0):
+                if feed:
+                    step_pred = np.reshape(self.infer(self.sess, feed), -1)
+                    wt.write("\n".join(map(str, step_pred)))
+                    wt.write("\n")
+        return self
+
+
+class PAMRECModel(SequentialBaseModel):
+    """PAM:25: the playback-duration-augmented model.  The graph (embeddings, time-aware 2-block encoder, attention
+    pooling, MMoE, three towers, four-term loss, per-tensor clip + Adam) is libpamrec_b200.so."""
+
+    def _build_graph(self):
+        hp = self.hparams
+        n_users = len(load_dict(hp.user_vocab))        # SBM:565-567
+        n_items = len(load_dict(hp.item_vocab))
+        n_cates = len(load_dict(hp.cate_vocab))
+        engine_hp = dict(
+            learning_rate=float(hp.learning_rate), embed_l2=float(hp.embed_l2), layer_l2=float(hp.layer_l2),
+            max_grad_norm=float(hp.max_grad_norm), is_clip_norm=int(bool(hp.is_clip_norm)),
+            fuzhu_weight=float(hp.fuzhu_weight), discrepancy_loss_weight=float(hp.discrepancy_loss_weight))
+        mode = getattr(hp, "sparse_adam", "dense_exact")
+        self.engine = Engine(n_users, n_items, n_cates, hp.max_seq_length, hp.batch_size, hp=engine_hp, sparse_adam=mode)
+        self.engine.allocate(getattr(hp, "device", "cuda:0"))
+        self.engine.set_variables(initial_variables(self.engine.variable_shapes(), hp, self.seed))
+
+    def train(self, sess, feed_dict):
+        """PAM:426-453: one optimisation step.  Returns the reference's 8-tuple
+        (update, extra_update_ops, loss, data_loss, regular_loss, auxiliary_data_loss, order_loss, summary)."""
+        db = self.engine.upload(feed_dict, training=True)
+        losses = self.engine.train_step(db).cpu().numpy()
+        return [None, None, float(losses[0]), float(losses[1]), float(losses[2]), float(losses[3]), float(losses[4]), None]
+
+    def step_train(self, step, step_result):
+        """PAM:455-465."""
+        (_, _, step_loss, step_data_loss, _, step_aux, order_loss, _) = step_result
+        if step % self.hparams.show_step == 0:
+            print("step {0:d} , total_loss: {1:.4f}, data_loss: {2:.4f}, auxiliary_data_loss: {3:.4f}, order_loss: {4:.4f}".format(
+                step, step_loss, step_data_loss, step_aux, order_loss))
+
+    def batch_train(self, file_iterator, train_sess):
+        """PAM:467-503 (the reference unpacks a 7-tuple from an 8-tuple there and would raise; this version works)."""
+        step, epoch_loss = 0, 0.0
+        for feed in file_iterator:
+            if feed:
+                r = self.train(train_sess, feed)
+                epoch_loss += r[2]
+                step += 1
+                if step % self.hparams.show_step == 0:
+                    print("step {0:d} , total_loss: {1:.4f}, data_loss: {2:.4f}, auxiliary_data_loss: {3:.4f}".format(
+                        step, r[2], r[3], r[5]))
+        return epoch_loss

@@ -1,0 +1,318 @@
+"""Host-side mirror of the reference's ``SequentialIterator`` (IT = reco_utils/recommender/deeprec/io/
+sequential_iterator.py in the reference tree): same text formats, same batching algorithm, same Python
+``random`` call order, so batches are bit-identical to the reference's feed dicts — but the yielded
+mapping is keyed by strings (the placeholder names of IT:120-163) and there is no TensorFlow.
+
+Differences in HOW, not WHAT: a file is tokenised once into per-line numpy columns, the play-ratio
+bucket of every history element is computed once when the line is parsed (vectorised ``lisan``), and a
+training group writes its shared history window straight into the five rows of the batch arrays instead
+of deep-copying six Python lists five times (IT:677-682).
+"""
+import os
+import random
+
+import numpy as np
+
+from .deeprec_utils import load_dict
+
+__all__ = ["SequentialIterator", "lisan", "bar_border_list", "takatak_bar_border_list_dict"]
+
+# decile borders of play_time / duration (IT:24-42)
+bar_border_list = [0.00000000e+00, 4.09545455e-02, 1.28786778e-01, 3.27894289e-01,
+                   7.66666667e-01, 1.05850847e+00, 1.18596610e+00, 1.53888889e+00,
+                   2.13000000e+00, 3.18951300e+03]
+takatak_bar_border_list_dict = {
+    10: [0.00000000e+00, 9.42727958e-02, 1.83767085e-01, 3.43377108e-01,
+         5.84957075e-01, 8.40688722e-01, 1.01619134e+00, 1.06384801e+00,
+         1.12731802e+00, 1.53233455e+00, 1.42410704e+02],
+    8: [0., 0.11222045, 0.25718205, 0.5326864, 0.85086416,
+        1.03270076, 1.08606422, 1.32310015, 34.54434426],
+    6: [0., 0.14884331, 0.42646411, 0.85086416, 1.0506716,
+        1.17514919, 34.54434426],
+}
+
+FEED_KEYS = (
+    "labels_satisfied", "labels_play", "plays", "users", "items", "cates", "durations", "item_history",
+    "item_cate_history", "item_duration_history", "mask", "item_satisfied_value_history", "item_play_value_history",
+    "item_loop_times_history", "satisfied_item_history", "satisfied_cate_history", "satisfied_duration_history",
+    "satisfied_play_history", "satisfied_mask")
+
+
+def _borders(dataset, num):
+    if dataset == "takatak":
+        return takatak_bar_border_list_dict[num]
+    if dataset == "wechat":
+        return bar_border_list
+    raise Exception("the dataset is wrong")
+
+
+def lisan(x, dataset, num=10):
+    """IT:43-53: max(bisect_right(borders, x) - 1, 0)."""
+    return int(lisan_array(np.asarray([x]), dataset, num)[0])
+
+
+def lisan_array(x, dataset, num=10):
+    """Vectorised lisan; NaN sorts last exactly like bisect's `x < a[mid]` walk."""
+    idx = np.searchsorted(np.asarray(_borders(dataset, num)), x, side="right") - 1
+    return np.maximum(idx, 0)
+
+
+def _ratio64(play, dur):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.asarray(play, np.float64) / np.asarray(dur, np.float64)
+
+
+class SequentialIterator:
+    """``SequentialIterator(hparams, graph)`` — ``graph`` is accepted and ignored (IT:56)."""
+
+    VALID_THRESHOLD = 8          # seconds, IT:96
+    BEGIN_HISTORY_LEN_MAX = 5    # IT:98
+    MAX_SEQUENCE = 100           # IT:476
+
+    def __init__(self, hparams, graph=None, col_spliter="\t"):
+        self.noise_train_hist = hparams.noise_train_hist
+        self.noise_train_listwise = hparams.noise_train_listwise
+        self.noise_only_predict = hparams.noise_only_predict
+        self.dataset = hparams.dataset
+        self.bucket_num = hparams.bucket_num
+        _borders(self.dataset, self.bucket_num) if self.dataset in ("wechat", "takatak") else None
+        dirs, _ = os.path.split(hparams.item_vocab)
+        if self.dataset == "wechat":
+            meta_path = os.path.join(dirs, "wechat_business_recommenders.csv")
+        elif self.dataset == "takatak":
+            meta_path = os.path.join(dirs, "takatak_business_recommenders.csv")
+        else:
+            raise Exception("there is no the dataset")
+        self.meta_dict = {}                      # IT:79-86: loaded, unused by the live path
+        with open(meta_path, "r") as f:
+            for line in f:
+                parts = line.strip().split("\t")
+                iid = int(parts[0])
+                if iid not in self.meta_dict:
+                    self.meta_dict[iid] = [int(parts[1]), float(parts[2])]
+        self.train = False
+        self.col_spliter = col_spliter
+        self.userdict = load_dict(hparams.user_vocab)
+        self.itemdict = load_dict(hparams.item_vocab)
+        self.catedict = load_dict(hparams.cate_vocab)
+        self.max_seq_length = hparams.max_seq_length
+        self.batch_size = hparams.batch_size
+        self.iter_data = dict()
+        self.time_unit = hparams.time_unit
+        self.graph = graph
+
+    # ------------------------------------------------------------------ parsing (IT:175-322)
+    def _history_columns(self, words, first):
+        items = [self.itemdict.get(w, 0) for w in words[first].strip().split(",")]
+        cates = [self.catedict.get(w, 0) for w in words[first + 1].strip().split(",")]
+        durs = [float(w) for w in words[first + 2].strip().split(",")]
+        sats = [float(w) for w in words[first + 3].strip().split(",")]
+        plays_ms = words[first + 4].strip().split(",")
+        if self.noise_only_predict != 0:         # IT:317-318 (zip with durations bounds the length)
+            plays = np.array([max(float(w) / 1000 + np.random.normal(0, self.noise_only_predict), 0)
+                              for w, _ in zip(plays_ms, durs)])
+        else:
+            plays = np.array([float(w) / 1000 for w in plays_ms])
+        durs = durs[:len(plays_ms)]              # IT:313 zips plays with durations
+        return items, cates, sats, plays, durs
+
+    def parser_one_line(self, line):
+        """Train line (6 columns, one per user) or eval line (11 columns, one per impression)."""
+        words = line.strip().split(self.col_spliter)
+        if self.train:
+            user_id = self.userdict.get(words[0], 0)
+            items, cates, sats, plays, durs = self._history_columns(words, 1)
+            return (user_id, items, cates, durs, sats, plays)
+        label_satisfied = int(words[0])
+        label_play = float(words[1]) / 1000
+        user_id = self.userdict.get(words[2], 0)
+        item_id = self.itemdict.get(words[3], 0)
+        item_cate = self.catedict.get(words[4], 0)
+        duration = float(words[5])
+        items, cates, sats, plays, durs = self._history_columns(words, 6)
+        return (label_satisfied, label_play, user_id, item_id, item_cate, duration, items, cates, durs, sats, plays)
+
+    def parse_file(self, input_file):
+        with open(input_file, "r") as f:
+            lines = f.readlines()
+        return [self.parser_one_line(line) for line in lines if line]
+
+    # ------------------------------------------------------------------ batches
+    def load_data_from_file(self, infile, batch_num_ngs=0, min_seq_length=1):
+        """Generator of feed mappings (IT:334-763).  The mode switch is on the file's basename (IT:361-364)."""
+        self.train = os.path.basename(infile) == "train_data"
+        if infile not in self.iter_data:
+            self.iter_data[infile] = self.parse_file(infile)
+        lines = self.iter_data[infile]
+        if batch_num_ngs > 0:
+            # the reference's in-batch negative sampler is a commented-out block ending in exit(-1) (IT:801-1008)
+            raise NotImplementedError("batch_num_ngs > 0 is not executable in the reference (IT:1008)")
+        if self.train:
+            yield from self._train_batches(lines)
+        else:
+            yield from self._eval_batches(lines, min_seq_length)
+
+    def _new_acc(self):
+        return {"sat": [], "lplay": [], "plays": [], "users": [], "items": [], "cates": [], "durs": [], "hist": []}
+
+    def _eval_batches(self, lines, min_seq_length):
+        acc = self._new_acc()
+        for line in lines:
+            if not line:
+                continue
+            (label_satisfied, label_play, user_id, item_id, item_cate, duration, items, cates, durs, sats, plays) = line
+            if len(items) < min_seq_length:
+                continue
+            acc["sat"].append(label_satisfied)
+            acc["lplay"].append(1.0 if label_play >= 10 else 0.0)       # IT:410 (10 s at eval, 8 s at train)
+            acc["plays"].append(label_play)                             # IT:411 seconds, not a bucket
+            acc["users"].append(user_id)
+            acc["items"].append(item_id)
+            acc["cates"].append(item_cate)
+            acc["durs"].append(duration)
+            n = min(len(plays), len(durs))
+            loops = lisan_array(_ratio64(plays[:n], durs[:n]), self.dataset, self.bucket_num)   # IT:421
+            acc["hist"].append((items, cates, durs, sats, plays, loops, 1))
+            if len(acc["sat"]) == self.batch_size:
+                yield self._convert_data(acc)
+                acc = self._new_acc()
+        if acc["sat"]:
+            yield self._convert_data(acc)
+
+    def _push(self, st, item, cate, dur, sat, play):
+        """add_a_item_to_hist (IT:479-522).  st = [items, cates, durs, sats, plays, not_satisfied_index]."""
+        if play < self.VALID_THRESHOLD and sat != 1:
+            return
+        items, cates, durs, sats, plays, nsi = st
+        items.append(item); cates.append(cate); durs.append(dur); sats.append(sat)
+        plays.append(play if self.noise_train_hist == 0 else max(play + np.random.normal(0, self.noise_train_hist), 0))
+        if sat == 0:
+            nsi.append(len(items) - 1)
+        if len(items) > self.MAX_SEQUENCE:
+            if not nsi:
+                for col in (items, cates, durs, sats, plays):
+                    del col[:-self.MAX_SEQUENCE]
+            else:
+                k = len(items) - self.MAX_SEQUENCE
+                for j, idx in enumerate(nsi[:k]):      # evict the oldest unsatisfied first
+                    for col in (items, cates, durs, sats, plays):
+                        col.pop(idx - j)
+                st[5] = [i - k for i in nsi[k:]]
+
+    def _train_batches(self, lines):
+        G = self.BEGIN_HISTORY_LEN_MAX
+        data_source = []
+        for line in lines:
+            if not line:
+                continue
+            user_id, items, cates, durs, sats, plays = line
+            satisfied_num = sum(sats)
+            if satisfied_num < 2:
+                continue
+            begin_loc = 1 if satisfied_num <= G else random.randint(1, G)       # IT:542-545
+            st = [[], [], [], [], [], []]
+            i = 0
+            while sats[i] != 1:                                                 # IT:556-570
+                self._push(st, items[i], cates[i], durs[i], sats[i], plays[i])
+                i += 1
+            for _ in range(begin_loc):                                          # IT:573-588
+                self._push(st, items[i], cates[i], durs[i], sats[i], plays[i])
+                i += 1
+            data_source.append([st, user_id, i, line])
+        random.shuffle(data_source)                                             # IT:622
+        acc = self._new_acc()
+        alive = list(range(len(data_source)))
+        while alive:
+            nxt = []
+            for ind in alive:
+                st, user_id, i, line = data_source[ind]
+                _, items, cates, durs, sats, plays = line
+                future = len(items) - i
+                if future < G:
+                    continue
+                fplays = plays[i:i + G]
+                fdurs = durs[i:i + G]
+                acc["sat"].extend(sats[i:i + G])
+                acc["lplay"].extend(1.0 if x >= self.VALID_THRESHOLD else 0.0 for x in fplays)     # IT:646
+                if self.noise_train_listwise == 0:
+                    ratio = _ratio64(fplays, fdurs)
+                else:                                                                               # IT:656
+                    ratio = _ratio64([max(x + np.random.normal(0, self.noise_train_listwise), 0) for x in fplays], fdurs)
+                acc["plays"].extend(lisan_array(ratio, self.dataset, self.bucket_num).tolist())
+                acc["users"].extend([user_id] * G)
+                acc["items"].extend(items[i:i + G])
+                acc["cates"].extend(cates[i:i + G])
+                acc["durs"].extend(fdurs)
+                h_items, h_cates, h_durs, h_sats, h_plays, _ = st
+                loops = lisan_array(_ratio64(h_plays, h_durs), self.dataset, self.bucket_num)       # IT:682
+                acc["hist"].append((list(h_items), list(h_cates), list(h_durs), list(h_sats), list(h_plays), loops, G))
+                if len(acc["sat"]) == self.batch_size:                                              # IT:684-685
+                    yield self._convert_data(acc)
+                    acc = self._new_acc()
+                if future > G:                                                                      # IT:719-741
+                    for k in range(i, i + G):
+                        self._push(st, items[k], cates[k], durs[k], sats[k], plays[k])
+                    data_source[ind][2] = i + G
+                    nxt.append(ind)
+            alive = nxt
+        if acc["sat"]:                                                                              # IT:745-763
+            yield self._convert_data(acc)
+
+    # ------------------------------------------------------------------ arrays (IT:1009-1141, no-negatives branch)
+    def _convert_data(self, acc):
+        T = self.max_seq_length
+        n = len(acc["sat"])
+        item_h = np.zeros((n, T), np.int32)
+        cate_h = np.zeros((n, T), np.int32)
+        dur_h = np.zeros((n, T), np.float32)
+        sat_h = np.zeros((n, T), np.float32)
+        play_h = np.zeros((n, T), np.float32)
+        loop_h = np.zeros((n, T), np.float32)
+        mask = np.zeros((n, T), np.float32)
+        r = 0
+        for items, cates, durs, sats, plays, loops, rep in acc["hist"]:
+            L = min(len(items), T)
+            if L:
+                rows = slice(r, r + rep)
+                item_h[rows, :L] = items[-L:]
+                cate_h[rows, :L] = cates[-L:]
+                dur_h[rows, :L] = durs[-L:]
+                sat_h[rows, :L] = sats[-L:]
+                play_h[rows, :L] = plays[-L:]
+                loop_h[rows, :L] = loops[-L:]
+                mask[rows, :L] = 1.0
+            r += rep
+        # satisfied-only compaction (IT:1069-1103); the bucket here comes from the float32 arrays
+        is_sat = (sat_h == 1.0) & (mask == 1.0)
+        order = np.argsort(~is_sat, axis=1, kind="stable")
+        cnt = is_sat.sum(1)
+        keep = np.arange(T)[None, :] < cnt[:, None]
+        take = lambda a: np.where(keep, np.take_along_axis(a, order, 1), 0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            sat_loops = lisan_array(play_h / dur_h, self.dataset, self.bucket_num).astype(np.float32)
+        res = {
+            "labels_satisfied": np.asarray(acc["sat"], dtype=np.float32).reshape(-1, 1),
+            "labels_play": np.asarray(acc["lplay"], dtype=np.float32).reshape(-1, 1),
+            "plays": np.asarray(acc["plays"], dtype=np.float32).reshape(-1, 1),
+            "users": np.asarray(acc["users"], dtype=np.float32),          # IT:1115 builds users as float32
+            "items": np.asarray(acc["items"], dtype=np.int32),
+            "cates": np.asarray(acc["cates"], dtype=np.int32),
+            "durations": np.asarray(acc["durs"], dtype=np.float32),
+            "item_history": item_h,
+            "item_cate_history": cate_h,
+            "item_duration_history": dur_h,
+            "mask": mask,
+            "item_satisfied_value_history": sat_h,
+            "item_play_value_history": play_h,
+            "item_loop_times_history": loop_h,
+            "satisfied_item_history": take(item_h).astype(np.int32),
+            "satisfied_cate_history": take(cate_h).astype(np.int32),
+            "satisfied_duration_history": take(dur_h).astype(np.float32),
+            "satisfied_play_history": take(sat_loops).astype(np.float32),
+            "satisfied_mask": keep.astype(np.float32),
+        }
+        return res
+
+    def gen_feed_dict(self, data_dict):
+        """IT:1143-1181: identity here — the feed mapping is keyed by placeholder name."""
+        return {k: data_dict[k] for k in FEED_KEYS}

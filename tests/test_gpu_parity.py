@@ -91,13 +91,22 @@ def test_train_step_stagewise(nu, ni, nc, T, B):
     _close("d_x0", eng.ws("g_a", B).cpu().numpy(), t["x0"].grad.numpy(), rtol=1e-4, report=rep)
     from pamrec_b200 import _lib as L
     l2 = om.hp["layer_l2"]
+    # Parameter gradients are sums over B*T tokens that can cancel almost completely (e.g. a bias in front of a
+    # mean-removing BN): the fp32 rounding noise of such a sum scales with the summands, not with the result, so
+    # the absolute floor is tied to the largest gradient entry of the whole model.
+    gmax = max(float(ref["grads"][n].abs().max()) for n in eng.info[L.POOL_DENSE])
+    bad = []
     for name, d in eng.info[L.POOL_DENSE].items():
         g = eng.dense(name, "dense_grad").cpu().numpy().astype(np.float64)
         if d["flags"] & L.SEG_L2:
             g = g + l2 * eng.dense(name).cpu().numpy().astype(np.float64)
-        gr = ref["grads"][name].numpy()
-        tol = 1e-4
-        _close("grad " + name, g, gr, rtol=tol, report=rep)
+        gr = ref["grads"][name].numpy().reshape(g.shape)
+        err = np.abs(g - gr).max()
+        lim = 1e-4 * np.abs(gr).max() + 2e-6 * gmax
+        rep.append(("grad " + name, err / max(np.abs(gr).max(), 1e-30)))
+        if not (np.isfinite(g).all() and err <= lim):
+            bad.append((name, err, np.abs(gr).max()))
+    assert not bad, f"gmax={gmax:.3e} " + "; ".join(f"{n}: err {e:.3e} max|ref| {m:.3e}" for n, e, m in bad)
     # ---- apply: sparse gradients, clip norms, losses
     tables0 = {k: eng.pool[k].clone() for k in ("item_w", "cate_w", "ulong_w", "ushort_w")}
     M0, V0 = eng.pool["dense_m"].clone(), eng.pool["dense_v"].clone()
@@ -128,11 +137,12 @@ def test_train_step_stagewise(nu, ni, nc, T, B):
     segn = eng.ws("seg_normsq").cpu().numpy()
     for s, (name, d) in enumerate(eng.info[L.POOL_DENSE].items()):
         want = ref["sqnorms"][name]
-        assert abs(segn[s] - want) <= 2e-4 * want + 1e-30, (name, segn[s], want)
+        assert abs(segn[s] - want) <= 2e-4 * want + d["numel"] * (2e-6 * gmax) ** 2, (name, segn[s], want)
     # ---- optimiser kernels against the TF formulas applied to the engine's own gradients
     hp = om.hp
     b1, b2, eps = hp["beta1"], hp["beta2"], hp["epsilon"]
-    lr_t = np.float32(hp["learning_rate"] * math.sqrt(1 - b2) / (1 - b1))
+    f32 = lambda x: float(np.float32(x))
+    lr_t = np.float32(f32(hp["learning_rate"]) * math.sqrt(1 - f32(b2)) / (1 - f32(b1)))
     for s, (name, d) in enumerate(eng.info[L.POOL_DENSE].items()):
         o, n = d["offset"], d["numel"]
         p0 = P0[o:o + n].cpu().numpy(); g = G0[o:o + n].cpu().numpy()
@@ -140,8 +150,8 @@ def test_train_step_stagewise(nu, ni, nc, T, B):
             g = g + np.float32(l2) * p0
         norm = np.float32(math.sqrt(segn[s]))
         g = g * np.float32(2.0) / max(norm, np.float32(2.0))
-        m = (M0[o:o + n].cpu().numpy() + (g - M0[o:o + n].cpu().numpy()) * np.float32(1 - b1)).astype(np.float32)
-        v = (V0[o:o + n].cpu().numpy() + (g * g - V0[o:o + n].cpu().numpy()) * np.float32(1 - b2)).astype(np.float32)
+        m = (M0[o:o + n].cpu().numpy() + (g - M0[o:o + n].cpu().numpy()) * (np.float32(1) - np.float32(b1))).astype(np.float32)
+        v = (V0[o:o + n].cpu().numpy() + (g * g - V0[o:o + n].cpu().numpy()) * (np.float32(1) - np.float32(b2))).astype(np.float32)
         p = p0 - lr_t * m / (np.sqrt(v) + np.float32(eps))
         got = eng.dense(name).cpu().numpy().reshape(-1)
         assert np.allclose(got, p, rtol=1e-6, atol=1e-9), name
@@ -150,7 +160,8 @@ def test_train_step_stagewise(nu, ni, nc, T, B):
         w0 = tables0[tab + "_w"].cpu().numpy(); w1 = eng.pool[tab + "_w"].cpu().numpy()
         assert np.isfinite(w1).all()
         assert (w0 != w1).any()
-    print("\n".join(f"{n:60s} {e:.2e}" for n, e in sorted(rep, key=lambda x: -x[1])[:12]))
+    print(f"\n[{nu},{ni},{nc},T={T},B={B}] worst relative errors:")
+    print("\n".join(f"  {n:70s} {e:.2e}" for n, e in sorted(rep, key=lambda x: -x[1])[:10]))
     eng.close()
 
 
@@ -172,9 +183,12 @@ def test_multi_step_losses_and_eval():
     pred = eng.forward(eng.upload(ev, training=False), training=False).cpu().numpy()
     want = om.eval_forward(ev).t["pred"].numpy().reshape(-1)
     assert np.abs(pred - want).max() <= 1e-4
+    # A bias in front of a BN layer has a mathematically zero data gradient, so Adam moves it along fp32 rounding
+    # noise; moving_mean tracks that bias (and cancels it again at inference), hence the looser absolute floor.
     for name in eng.info[1]:
         got = eng.bn(name).cpu().numpy()
-        assert np.allclose(got, om.bn_state[name].numpy(), rtol=1e-4, atol=1e-6), name
+        atol = 2e-4 if name.endswith("moving_mean") else 1e-6
+        assert np.allclose(got, om.bn_state[name].numpy(), rtol=1e-4, atol=atol), name
     eng.close()
 
 

@@ -1,0 +1,152 @@
+"""Host logic pinned against the reference: batches of pamrec_b200.SequentialIterator are BIT-EXACT with the
+reference's SequentialIterator (golden fixtures made by oracle/gen_golden.py from the unmodified reference run
+under a stub tensorflow; re-checked live whenever /root/reference is mounted), bucket ids and metrics likewise."""
+import json
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import gen_golden as G
+from pamrec_b200 import deeprec_utils as DU
+from pamrec_b200 import sequential_iterator as IT
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+HAVE_REF = os.path.isdir(os.path.join(G.REF, "reco_utils"))
+
+
+def _ours(case, data_dir):
+    hp = G.hparams_for(case, data_dir)
+    return G.run_iterator(lambda: IT.SequentialIterator(hp, None), data_dir)
+
+
+@pytest.mark.parametrize("case", list(G.CASES))
+def test_iterator_matches_golden(case):
+    z = np.load(os.path.join(GOLDEN, f"iterator_{case}.npz"))
+    with tempfile.TemporaryDirectory() as tmp:
+        data_dir = G.synth_case(case, tmp)
+        res = _ours(case, data_dir)
+    for split in ("train", "valid"):
+        want = z[f"{split}_digests"].tolist()
+        got = [G.batch_digest(b) for b in res[split]]
+        assert len(got) == len(want), (split, len(got), len(want))
+        bad = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
+        assert not bad, f"{split}: first differing batch {bad[0]} of {len(want)}"
+    for tag, b in (("train_first", res["train"][0]), ("train_last", res["train"][-1]), ("valid_first", res["valid"][0]),
+                   ("valid_last", res["valid"][-1])):
+        for name in G.FEED_NAMES:
+            ref = z[f"{tag}.{name}"]
+            assert b[name].dtype == ref.dtype and b[name].shape == ref.shape, (tag, name)
+            assert np.array_equal(b[name], ref, equal_nan=True), (tag, name)
+    # structure the kernels rely on: train batches are groups of 5 rows sharing one history
+    tb = res["train"][0]
+    assert tb["items"].shape[0] % 5 == 0
+    for k in ("item_history", "item_cate_history", "mask", "item_loop_times_history", "users"):
+        a = tb[k].reshape(-1, 5, *tb[k].shape[1:])
+        assert (a == a[:, :1]).all(), k
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree not mounted")
+@pytest.mark.parametrize("case", list(G.CASES))
+def test_iterator_matches_reference_live(case):
+    _, RIT = G.reference_modules()
+    with tempfile.TemporaryDirectory() as tmp:
+        data_dir = G.synth_case(case, tmp)
+        hp = G.hparams_for(case, data_dir)
+        ref = G.run_iterator(lambda: RIT.SequentialIterator(hp, G._Graph()), data_dir, epochs=1)
+        got = G.run_iterator(lambda: IT.SequentialIterator(hp, None), data_dir, epochs=1)
+    for split in ("train", "valid"):
+        assert len(ref[split]) == len(got[split])
+        for i, (a, b) in enumerate(zip(ref[split], got[split])):
+            for name in G.FEED_NAMES:
+                assert a[name].dtype == b[name].dtype, (split, i, name)
+                assert np.array_equal(a[name], b[name], equal_nan=True), (split, i, name)
+
+
+def test_lisan_known_answers():
+    kat = json.load(open(os.path.join(GOLDEN, "lisan.json")))
+    xs = np.asarray(kat["x"], dtype=np.float64)
+    for key, (ds, num) in {"wechat": ("wechat", 10), "takatak10": ("takatak", 10), "takatak8": ("takatak", 8),
+                           "takatak6": ("takatak", 6)}.items():
+        assert IT.lisan_array(xs, ds, num).tolist() == kat[key], key
+        assert [IT.lisan(float(x), ds, num) for x in xs[:5]] == kat[key][:5]
+    assert IT.lisan(float("nan"), "wechat") == 9            # bisect walks right on NaN
+    with pytest.raises(Exception):
+        IT.lisan(1.0, "taobao")
+
+
+def test_metrics_match_reference():
+    want = json.load(open(os.path.join(GOLDEN, "metrics.json")))
+    users, preds, labels, g_labels, g_preds = G.metric_inputs()
+    u, p, l = DU.filter_single_class_users(users, preds, labels)
+    assert 3 not in u and 4 not in u
+    point = DU.cal_metric(l, p, G.POINT_METRICS)
+    group = DU.cal_metric(g_labels, g_preds, G.GROUP_METRICS)
+    weighted = DU.cal_weighted_metric(u, p, l, G.WEIGHTED_METRICS)
+    for got, ref in ((point, want["point"]), (group, want["group"]), (weighted, want["weighted"])):
+        assert set(got) == set(ref)
+        for k in ref:
+            assert abs(float(got[k]) - ref[k]) < 1e-12, (k, got[k], ref[k])
+    with pytest.raises(ValueError):
+        DU.cal_metric([1, 0], [0.2, 0.3], ["nope"])
+    with pytest.raises(ValueError):
+        DU.cal_weighted_metric([1, 1], [0.2, 0.3], [1, 0], ["nope"])
+    assert DU.cal_metric([1], [0.5], []) == {}
+
+
+def test_hparams_yaml_and_errors(tmp_path):
+    yml = os.path.join(os.path.dirname(GOLDEN), "..", "pamrec_b200", "config", "mmoe.yaml")
+    hp = DU.prepare_hparams(yml, dataset="wechat", batch_size=500, max_seq_length=100, embed_l2=1e-6)
+    assert hp.expert_num == 5 and hp.gate_layer_sizes == [64, 5] and hp.max_seq_length == 100 and hp.batch_size == 500
+    assert hp.time_unit == "s" and hp.max_grad_norm == 2 and hp.embed_l2 == 1e-6 and hp.enable_BN is True
+    with pytest.raises(TypeError):
+        DU.prepare_hparams(yml, batch_size="500")
+    with pytest.raises(TypeError):
+        DU.prepare_hparams(yml, learning_rate=1)
+    with pytest.raises(ValueError):
+        DU.prepare_hparams(yml, weird={"a": 1})
+    with pytest.raises(FileNotFoundError):
+        DU.prepare_hparams(str(tmp_path / "missing.yaml"))
+    bad = tmp_path / "bad.yaml"
+    bad.write_text("a: [1, 2\n")
+    with pytest.raises(IOError):
+        DU.load_yaml(str(bad))
+
+
+def test_iterator_edge_cases(tmp_path):
+    """empty / ragged inputs: users with < 2 satisfied items are skipped, unknown tokens map to id 0, histories
+    longer than T keep the most recent T, the tail batch is smaller, negatives in-batch are refused."""
+    d = tmp_path / "wechat"
+    d.mkdir()
+    import pickle
+    for name, voc in (("user_vocab.pkl", {"default_uid": 0, "u1": 1, "u2": 2}), ("item_vocab.pkl", {"default_mid": 0, **{str(i): i for i in range(1, 50)}}),
+                      ("category_vocab.pkl", {"default_cat": 0, "c1": 1})):
+        pickle.dump(voc, open(d / name, "wb"))
+    (d / "wechat_business_recommenders.csv").write_text("1\t1\t10.0\n")
+    n = 30
+    items = ",".join(str(1 + i % 49) for i in range(n))
+    line = lambda u, sats: "\t".join([u, items, ",".join(["c1"] * n), ",".join(["10.0"] * n), ",".join(sats), ",".join(["12000"] * n)])
+    (d / "train_data").write_text(line("u1", ["1"] * n) + "\n" + line("u2", ["0"] * (n - 1) + ["1"]) + "\n" + line("zzz", ["1", "0"] * (n // 2)) + "\n")
+    ev = "\t".join(["1", "12000", "u1", "999", "c1", "10.0", items, ",".join(["c1"] * n), ",".join(["10.0"] * n), ",".join(["1"] * n), ",".join(["12000"] * n)])
+    (d / "valid_data").write_text((ev + "\n") * 7)
+    hp = DU.prepare_hparams(None, model_type="mmoe", dataset="wechat", bucket_num=10, batch_size=10, max_seq_length=8,
+                            noise_train_hist=0, noise_train_listwise=0, noise_only_predict=0, user_vocab=str(d / "user_vocab.pkl"),
+                            item_vocab=str(d / "item_vocab.pkl"), cate_vocab=str(d / "category_vocab.pkl"))
+    import random
+    random.seed(8)
+    it = IT.SequentialIterator(hp, None)
+    tr = list(it.load_data_from_file(str(d / "train_data")))
+    assert all(b["items"].shape[0] % 5 == 0 for b in tr)
+    users = np.concatenate([b["users"] for b in tr])
+    assert set(users.tolist()) <= {0.0, 1.0}          # u2 has a single satisfied item -> skipped; zzz -> id 0
+    assert tr[0]["item_history"].shape == (10, 8)
+    va = list(it.load_data_from_file(str(d / "valid_data")))
+    assert [b["items"].shape[0] for b in va] == [7]
+    assert va[0]["items"][0] == 0                     # unknown item token
+    assert (va[0]["mask"].sum(1) == 8).all()          # truncated to the last T
+    assert va[0]["item_history"][0].tolist() == [1 + i % 49 for i in range(n - 8, n)]
+    assert va[0]["labels_play"][0, 0] == 1.0 and va[0]["plays"][0, 0] == 12.0
+    with pytest.raises(NotImplementedError):
+        next(it.load_data_from_file(str(d / "valid_data"), batch_num_ngs=4))
+    assert list(it.load_data_from_file(str(d / "valid_data"), min_seq_length=1000)) == []
