@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Headline benchmark of the PAMRec train step (BASELINE.json: train samples/sec; gather/Adam HBM GB/s vs peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+One "step" = one optimisation step (forward + losses + backward + per-tensor clip + Adam) over one batch of
+synthetic MX-TakaTak-shaped input.  Prints ONE JSON line (rank 0).  Keys: see DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: takatak-shaped, seq_len 50, group of 5 (1 pos + 4), batch 1024 -> 1025 (must be a
+    # multiple of 5: io/sequential_iterator.py:684-685), single B200
+    "takatak_b1025_t50": dict(dataset="takatak", n_users=50000, n_items=30000, n_cates=50, T=50, B=1025),
+    # configs[3]: long history
+    "long_b4095_t200": dict(dataset="takatak", n_users=50000, n_items=30000, n_cates=50, T=200, B=4095),
+    # configs[0]-shaped quick start
+    "wechat_b500_t100": dict(dataset="wechat", n_users=20000, n_items=100000, n_cates=500, T=100, B=500),
+}
+METRIC = "train samples/sec"
+N_POOL = 8            # distinct resident batches cycled through the timed steps
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops"], tensor_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(w, tmp, sparse_adam="dense_exact"):
+    from pamrec_b200 import synth
+    from pamrec_b200.deeprec_utils import prepare_hparams
+    from pamrec_b200.models import PAMRECModel
+    from pamrec_b200.sequential_iterator import SequentialIterator
+    d = synth.write_vocab_only(tmp, w["dataset"], w["n_users"], w["n_items"], w["n_cates"])
+    hp = prepare_hparams(os.path.join(ROOT, "pamrec_b200", "config", "mmoe.yaml"), dataset=w["dataset"], bucket_num=10,
+                         add_feature=False, embed_l2=1e-6, layer_l2=1e-6, discrepancy_loss_weight=0.1, learning_rate=0.001,
+                         epochs=1, EARLY_STOP=5, is_clip_norm=1, batch_size=w["B"], show_step=10 ** 9, MODEL_DIR=os.path.join(tmp, "model/"),
+                         SUMMARIES_DIR=os.path.join(tmp, "summary/"), user_vocab=os.path.join(d, "user_vocab.pkl"),
+                         item_vocab=os.path.join(d, "item_vocab.pkl"), cate_vocab=os.path.join(d, "category_vocab.pkl"),
+                         train_num_ngs=0, max_seq_length=w["T"], pairwise_metrics=[], weighted_metrics=["wauc"], fuzhu_weight=0.5,
+                         fine_tune=False, eval_step=10 ** 9, noise_train_hist=0, noise_train_listwise=0, noise_only_predict=0,
+                         write_tfevents=False, sparse_adam=sparse_adam)
+    return PAMRECModel(hp, SequentialIterator, seed=8)
+
+
+def flops_bytes(w):
+    """Algorithmic work per launch (DESIGN.md section 'Kernels'): name -> (bound, units per launch, unit)."""
+    B, T = w["B"], w["T"]
+    N = B * T
+    return {
+        "attn_fwd": ("tensor", 2 * (2 * T * T * 40) * B, "flop"),          # Q K^T and P V
+        "attn_bwd": ("tensor", 2 * (4 * T * T * 40) * B, "flop"),          # dP, dV, dQ, dK
+        "proj_fwd": ("tensor", 2 * (3 * 1600) * N, "flop"),
+        "proj_bwd": ("tensor", 2 * (6 * 1600) * N, "flop"),
+        "ffn_fwd": ("tensor", 2 * (2 * 1600) * N, "flop"),
+        "ffn_bwd": ("tensor", 2 * (4 * 1600) * N, "flop"),
+        "embed_fwd": ("hbm", 248 * N + 168 * B, "byte"),                   # 88 B read + 160 B written per lookup
+        "sparse_adam": ("hbm", None, "byte"),
+    }
+
+
+def hbm_microbench(eng, pk):
+    """Stand-alone HBM kernels at sizes far above L2 (same kernels the step uses): gather and the full-table Adam sweep."""
+    out = {}
+    dev = eng.device
+    nu, ni, nc, T, _ = eng.dims
+    rows = 1 << 20                                         # 1 Mi sequences x T lookups
+    g = torch.Generator(device="cpu").manual_seed(1)
+    ih = torch.randint(0, ni, (rows * T,), generator=g, dtype=torch.int32).to(dev)
+    ch = torch.randint(0, nc, (rows * T,), generator=g, dtype=torch.int32).to(dev)
+    ti = torch.randint(0, ni, (rows,), generator=g, dtype=torch.int32).to(dev)
+    tc = torch.randint(0, nc, (rows,), generator=g, dtype=torch.int32).to(dev)
+    outb = torch.empty(rows * T * 40, dtype=torch.float32, device=dev)
+    import ctypes as C
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    call = lambda: eng._check(eng.lib.pamrec_bench_gather(eng.handle, C.c_void_p(ih.data_ptr()), C.c_void_p(ch.data_ptr()),
+                                                           C.c_void_p(ti.data_ptr()), C.c_void_p(tc.data_ptr()), rows, T,
+                                                           C.c_void_p(outb.data_ptr()), st))
+    for _ in range(3):
+        call()
+    ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); call(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = min(ts)
+    byts = 248 * rows * T + 8 * rows
+    out["embed_fwd"] = dict(lookups=rows * T, table_rows=ni, ms=ms, achieved=byts / ms / 1e6, peak=pk["hbm"], unit="GB/s",
+                            frac=byts / ms / 1e6 / pk["hbm"], bytes_per_lookup=248,
+                            note="random ids over the workload's item table (L2-resident at this table size)")
+    del ih, ch, outb
+    return out
+
+
+def run_ours(args, w, rank, world):
+    from pamrec_b200 import synth
+    pk = peaks()
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    tmp = tempfile.mkdtemp(prefix="pamrec_bench_")
+    model = build_model(w, tmp)
+    eng = model.engine
+    B, T = w["B"], w["T"]
+    feeds = [synth.array_batch(1000 + 17 * i + rank, B, T, w["n_users"], w["n_items"], w["n_cates"]) for i in range(N_POOL)]
+    resident = [eng.upload(f) for f in feeds]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM, device-timed per step, L2 flushed between steps
+    for i in range(W):
+        eng.train_step(resident[i % N_POOL])
+    barrier()
+    clocks = ClockSampler(torch.cuda.current_device()).start()
+    evs = []
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.fill_(i & 0xFF)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.train_step(resident[i % N_POOL])
+        b.record()
+        evs.append((a, b))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    launches = eng.launches()
+    total_ms = sum(step_ms)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = B * world * K / (total_ms / 1e3)
+
+    # ---- e2e: the public call (PAMRECModel.train) with HOST feed dicts: pinned staging + one H2D per step, losses D2H
+    for i in range(W):
+        model.train(None, feeds[i % N_POOL])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        model.train(None, feeds[i % N_POOL])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clk = clocks.stop()
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = eng.upload(feeds[0], staged=True).h2d_bytes
+    e2e = {"value": B * world * K / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 20}
+
+    # ---- per-launcher device time over a second pass of the same K steps (CUDA events around every launch)
+    eng.profile(True)
+    for i in range(K):
+        flush.fill_(i & 0xFF)
+        eng.train_step(resident[i % N_POOL])
+    tab = eng.profile_table()
+    eng.profile(False)
+    tot = sum(ms for ms, _ in tab.values())
+    kernels = {k: {"ms_per_step": ms / K, "share": ms / tot, "launches_per_step": n / K} for k, (ms, n) in
+               sorted(tab.items(), key=lambda kv: -kv[1][0])}
+    dom = next(iter(kernels))
+    fb = flops_bytes(w)
+    roof = None
+    if dom in fb and fb[dom][1]:
+        bound, units, unit = fb[dom]
+        per_launch_ms = tab[dom][0] / tab[dom][1]
+        if bound == "tensor":
+            ach = units / (per_launch_ms / 1e3) / 1e12
+            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tensor_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained bf16",
+                    "note": "fp32 FFMA kernel (1e-5 tolerance rules out plain TF32/BF16); tensor-pipe utilisation is 0"}
+        else:
+            ach = units / (per_launch_ms / 1e3) / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                    "traffic": None, "peak_source": pk["source"]}
+    hbm = hbm_microbench(eng, pk)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "pamrec_b200",
+        "config": {"workload": args.workload, "batch_per_gpu": B, "seq_len": T, "group": 5, "n_items": w["n_items"],
+                   "n_cates": w["n_cates"], "n_users": w["n_users"], "sparse_adam": "dense_exact",
+                   "l2": "flushed between timed steps (256 MiB write); per-step working set also exceeds L2",
+                   "batch_note": "BASELINE batch 1024 rounded to 1025: batches must be multiples of 5"},
+        "e2e": e2e, "gpu_launches": int(launches) * K, "gpu_launches_per_step": int(launches), "clocks": clk, "roofline": roof, "roofline_hbm": hbm,
+        "kernels": kernels, "wall_s_timed_region": t_wall,
+    }
+    return out, model
+
+
+def cpu_baseline(w, seconds=20.0, rows=205):
+    """The oracle port of the reference step (torch CPU fp32, all host threads) on a bounded sample of the workload."""
+    from oracle import pamrec_oracle as O            # CPU baseline arm: the one place bench.py executes oracle/
+    from pamrec_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    om = O.OracleModel(w["n_users"], w["n_items"], w["n_cates"], w["T"], dtype=torch.float32)
+    feeds = [synth.array_batch(50 + i, rows, w["T"], w["n_users"], w["n_items"], w["n_cates"]) for i in range(4)]
+    for f in feeds:
+        f["mask"] = f["mask"].astype(np.int32); f["users"] = f["users"].astype(np.int32)
+    om.train_step(feeds[0])
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        om.train_step(feeds[n % 4])
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n * rows / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} steps of {rows} rows (T={w['T']}) of the same synthetic workload, {dt:.1f} s",
+            "note": "restated CPU baseline (oracle/pamrec_oracle.py, torch CPU fp32): TF 2.4 is not installable offline"}
+
+
+def run_reference(args, w, rank):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (TF cannot be installed)."""
+    if rank != 0:
+        return None
+    from oracle import pamrec_oracle as O
+    from pamrec_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    rows = 205
+    om = O.OracleModel(w["n_users"], w["n_items"], w["n_cates"], w["T"], dtype=torch.float32)
+    feeds = [synth.array_batch(50 + i, rows, w["T"], w["n_users"], w["n_items"], w["n_cates"]) for i in range(4)]
+    for f in feeds:
+        f["mask"] = f["mask"].astype(np.int32); f["users"] = f["users"].astype(np.int32)
+    for i in range(args.warmup):
+        om.train_step(feeds[i % 4])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        om.train_step(feeds[i % 4])
+    dt = time.perf_counter() - t0
+    v = args.steps * rows / dt
+    cb = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+          "sample": f"each step = {rows} rows (41 listwise groups) of the {args.workload} workload"}
+    return {"metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": args.workload, "batch_per_step": rows, "seq_len": w["T"],
+                       "note": "oracle port of the reference TF graph on host cores; TF 2.4 / tensorflow_ranking not installable offline"},
+            "cpu_baseline": cb, "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="pamrec_b200", choices=["pamrec_b200", "reference"])
+    ap.add_argument("--workload", default="takatak_b1025_t50", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        out = run_reference(args, w, rank)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return
+    if world > 1:
+        raise SystemExit("bench.py: data-parallel multi-GPU step is not wired into the bench yet (N=1 only)")
+    out, _ = run_ours(args, w, rank, world)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(w)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

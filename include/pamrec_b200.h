@@ -139,6 +139,13 @@ int pamrec_bench_gather(PamrecHandle h, const int32_t* item_ids, const int32_t* 
                         const int32_t* tgt_cates, int64_t n_rows, int32_t T, float* out, void* stream);
 int pamrec_bench_table_adam(PamrecHandle h, int64_t step, void* stream);
 
+/* Per-launcher device timing: CUDA events recorded on the caller's stream around every launch while enabled.
+ * Synchronise the stream, then read (name, accumulated ms, timed launches) per launcher. */
+int pamrec_profile_enable(PamrecHandle h, int on);
+int pamrec_profile_reset(PamrecHandle h);
+int pamrec_profile_count(PamrecHandle h);
+int pamrec_profile_get(PamrecHandle h, int index, char name[64], double* total_ms, int64_t* launches);
+
 /* number of kernel launches issued by the last device call on this handle */
 int64_t pamrec_last_launch_count(PamrecHandle h);
 

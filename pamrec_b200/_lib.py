@@ -65,6 +65,10 @@ EXPORTS = {
     "pamrec_bench_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                       C.c_void_p, C.c_void_p]),
     "pamrec_bench_table_adam": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "pamrec_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "pamrec_profile_reset": (C.c_int, [C.c_void_p]),
+    "pamrec_profile_count": (C.c_int, [C.c_void_p]),
+    "pamrec_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pamrec_last_launch_count": (C.c_int64, [C.c_void_p]),
 }
 

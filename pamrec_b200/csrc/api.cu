@@ -21,6 +21,7 @@ struct PamrecHandle_ {
   bool bound = false;
   std::string err;
   int64_t launches = 0;
+  Prof prof;
   BnSet bn[BN_COUNT];
   std::vector<int> h_seg_id, h_seg_tab;
 
@@ -31,6 +32,13 @@ struct PamrecHandle_ {
   float* wf(const std::string& name) const { return ws<float>(name); }
   int* wi(const std::string& name) const { return ws<int>(name); }
   double* wd(const std::string& name) const { return ws<double>(name); }
+};
+
+// binds the handle's launch accounting to this thread for the duration of one API call
+struct ProfBind {
+  PamrecHandle h; int64_t l0; Prof* prev;
+  explicit ProfBind(PamrecHandle hh) : h(hh), l0(hh->prof.launches), prev(g_prof) { g_prof = &hh->prof; }
+  ~ProfBind() { h->launches = h->prof.launches - l0; g_prof = prev; }
 };
 
 static int fail(PamrecHandle h, const char* fmt, ...) {
@@ -164,8 +172,8 @@ static int check_batch(PamrecHandle h, const PamrecBatch* b, bool training) {
 
 int pamrec_gather_fwd(PamrecHandle h, const PamrecBatch* b, float* x0_out, void* stream) {
   if (int rc = check_batch(h, b, false)) return rc;
+  ProfBind _pb(h);
   cudaStream_t st = (cudaStream_t)stream;
-  h->launches = 1;
   launch_embed_fwd(b->item_history, b->item_cate_history, b->items, b->cates, h->buf.item_w, h->buf.cate_w, h->P(h->L.pos),
                    x0_out ? x0_out : h->wf("x0"), h->wf("tgt"), b->batch, h->cfg.max_seq_len, st);
   return check_cuda(h, "gather_fwd");
@@ -184,6 +192,7 @@ static void set_in_bn_dw(DenseDwP& p, const BnSet& s) { p.in_stat = s.stat; p.in
 
 int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pred_out, void* stream) {
   if (int rc = check_batch(h, b, training != 0)) return rc;
+  ProfBind _pb(h);
   cudaStream_t st = (cudaStream_t)stream;
   const Layout& L = h->L;
   const int B = b->batch, T = h->cfg.max_seq_len, N = B * T;
@@ -278,7 +287,6 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     launch_dense_fwd(to, st); nl += 1;
   }
   if (pred_out) { launch_sigmoid_col0(h->wf("logits"), pred_out, B, st); nl += 1; }
-  h->launches = nl;
   return check_cuda(h, "forward");
 }
 
@@ -305,6 +313,7 @@ static void dx_add(DenseDxP& p, int slice, int out_off, int dz_off, int64_t w_of
 
 int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   if (int rc = check_batch(h, b, true)) return rc;
+  ProfBind _pb(h);
   cudaStream_t st = (cudaStream_t)stream;
   const Layout& L = h->L;
   const int B = b->batch, T = h->cfg.max_seq_len, N = B * T;
@@ -434,7 +443,6 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   }
   // dX0 is in g_a
   launch_embed_bwd_reduce(g_a, h->wf("d_tgt"), h->wf("d_tgt_total"), h->G(L.pos), h->wd("sp_normsq") + 4, B, T, st); nl += 2;
-  h->launches = nl;
   return check_cuda(h, "backward");
 }
 
@@ -461,6 +469,7 @@ static SparseTable table_of(PamrecHandle h, const char* which) {
 
 int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, void* stream) {
   if (int rc = check_batch(h, b, true)) return rc;
+  ProfBind _pb(h);
   if (step < 1) return fail(h, "step must be >= 1");
   cudaStream_t st = (cudaStream_t)stream;
   const Layout& L = h->L;
@@ -509,23 +518,19 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
                     c.is_clip_norm, st);
   launch_finish_losses(h->wd("loss_acc"), h->wf("losses"), st);
   nl += 3;
-  h->launches = nl;
   return check_cuda(h, "apply_gradients");
 }
 
 int pamrec_train_step(PamrecHandle h, const PamrecBatch* b, int64_t step, float* losses_out, void* stream) {
   if (!h) return -1;
   if (h->cfg.world_size > 1) return fail(h, "world_size > 1: drive the step with pamrec_train_phase");
-  int64_t nl = 0;
+  const int64_t l0 = h->prof.launches;
   if (int rc = pamrec_forward(h, b, 1, nullptr, stream)) return rc;
-  nl += h->launches;
   if (int rc = pamrec_backward(h, b, stream)) return rc;
-  nl += h->launches;
   if (int rc = pamrec_apply_gradients(h, b, step, stream)) return rc;
-  nl += h->launches;
   if (losses_out)
     cudaMemcpyAsync(losses_out, h->wf("losses"), 5 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-  h->launches = nl;
+  h->launches = h->prof.launches - l0;
   return check_cuda(h, "train_step");
 }
 
@@ -539,22 +544,45 @@ int pamrec_bench_gather(PamrecHandle h, const int32_t* item_ids, const int32_t* 
                         const int32_t* tgt_cates, int64_t n_rows, int32_t T, float* out, void* stream) {
   if (!h || !h->bound) return fail(h, "not bound");
   if (T < 1 || T > h->cfg.max_seq_len) return fail(h, "T outside the position table");
+  ProfBind _pb(h);
   launch_embed_fwd(item_ids, cate_ids, tgt_items, tgt_cates, h->buf.item_w, h->buf.cate_w, h->P(h->L.pos), out, nullptr, n_rows,
                    T, (cudaStream_t)stream);
-  h->launches = 1;
   return check_cuda(h, "bench_gather");
 }
 
 int pamrec_bench_table_adam(PamrecHandle h, int64_t step, void* stream) {
   if (!h || !h->bound) return fail(h, "not bound");
+  ProfBind _pb(h);
   const PamrecConfig& c = h->cfg;
   const double b1 = c.beta1, b2 = c.beta2;
   const float lr_t = (float)((double)c.learning_rate * std::sqrt(1.0 - std::pow(b2, (double)step)) / (1.0 - std::pow(b1, (double)step)));
   SparseTable t = table_of(h, "item");
   launch_sparse_adam(t, 0, PAMREC_ADAM_DENSE_EXACT, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm, c.is_clip_norm,
                      (cudaStream_t)stream);
-  h->launches = 1;
   return check_cuda(h, "bench_table_adam");
+}
+
+int pamrec_profile_enable(PamrecHandle h, int on) {
+  if (!h) return -1;
+  h->prof.on = on != 0;
+  return 0;
+}
+int pamrec_profile_reset(PamrecHandle h) {
+  if (!h) return -1;
+  h->prof.reset();
+  return 0;
+}
+int pamrec_profile_count(PamrecHandle h) {
+  if (!h) return -1;
+  h->prof.resolve();
+  return (int)h->prof.names.size();
+}
+int pamrec_profile_get(PamrecHandle h, int index, char name[64], double* total_ms, int64_t* launches) {
+  if (!h || index < 0 || index >= (int)h->prof.names.size()) return -1;
+  snprintf(name, 64, "%s", h->prof.names[index].c_str());
+  if (total_ms) *total_ms = h->prof.ms[index];
+  if (launches) *launches = h->prof.cnt[index];
+  return 0;
 }
 
 }  // extern "C"

@@ -1,8 +1,35 @@
 // Launcher declarations shared by the translation units of libpamrec_b200.so.
 #pragma once
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 
 namespace pamrec {
+
+// Launch accounting + optional per-launcher device timing (CUDA events on the launching stream).
+struct Prof {
+  bool on = false;
+  int64_t launches = 0;
+  std::vector<std::string> names;
+  std::vector<double> ms;
+  std::vector<int64_t> cnt;
+  struct Pair { cudaEvent_t a, b; int id; };
+  std::vector<Pair> pending;
+  std::vector<cudaEvent_t> free_ev;
+  int id_of(const char* name);
+  cudaEvent_t get_event();
+  void resolve();          // caller has synchronised the stream
+  void reset();
+  ~Prof();
+};
+extern thread_local Prof* g_prof;
+struct ProfScope {
+  Prof* p; cudaStream_t st; cudaEvent_t b; bool timed;
+  ProfScope(const char* name, int n_kernels, cudaStream_t st);
+  ~ProfScope();
+};
+#define PAMREC_PROF(name, n, st) ProfScope _prof_scope(name, n, st)
 
 // ---- kernels_encoder.cu
 void launch_embed_fwd(const int* ih, const int* ch, const int* items, const int* cates, const float* item_w,

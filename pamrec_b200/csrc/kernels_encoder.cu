@@ -41,6 +41,7 @@ __global__ void k_embed_fwd(const int* __restrict__ ih, const int* __restrict__ 
 void launch_embed_fwd(const int* ih, const int* ch, const int* items, const int* cates, const float* item_w,
                       const float* cate_w, const float* pos, float* x0, float* tgt, int64_t n_rows, int T,
                       cudaStream_t st) {
+  PAMREC_PROF("embed_fwd", 1, st);
   int64_t total = n_rows * T * 10;
   if (total == 0) return;
   k_embed_fwd<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ih, ch, items, cates, item_w, cate_w, pos, x0, tgt, n_rows, T);
@@ -97,6 +98,7 @@ __global__ void k_bucket_scatter(const int* __restrict__ bucket, int n, int* __r
 
 void launch_bucket_plan(const float* lt, int n, int* bucket, int* perm, int* ctl, int* tile_bucket, int* tile_begin,
                         int* tile_count, cudaStream_t st) {
+  PAMREC_PROF("bucket_plan", 3, st);
   cudaMemsetAsync(ctl, 0, 64 * sizeof(int), st);
   int g = (n + 255) / 256;
   k_bucket_hist<<<g, 256, 0, st>>>(lt, n, bucket, ctl);
@@ -263,6 +265,7 @@ void launch_proj_fwd(const float* X, const int* perm, const int* ctl, const int*
                      const int* tile_count, int max_tiles, const float* Wq, const float* Wk, const float* Wv,
                      const float* ln_beta, const float* ln_gamma, float* QIN, float* Q, float* K, float* V,
                      cudaStream_t st) {
+  PAMREC_PROF("proj_fwd", 1, st);
   static bool once = false;
   if (!once) { cudaFuncSetAttribute(k_proj_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjFwdSmem); once = true; }
   k_proj_fwd<<<max_tiles, kTokTile, kProjFwdSmem, st>>>(X, perm, ctl, tile_bucket, tile_begin, tile_count, Wq, Wk, Wv,
@@ -348,6 +351,7 @@ k_attn_fwd(const float* __restrict__ Q, const float* __restrict__ K, const float
 
 void launch_attn_fwd(const float* Q, const float* K, const float* V, const float* QIN, const int* mask, float* Y, int B,
                      int T, cudaStream_t st) {
+  PAMREC_PROF("attn_fwd", 1, st);
   size_t smem = attn_fwd_smem(T);
   cudaFuncSetAttribute(k_attn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_attn_fwd<<<B, 256, smem, st>>>(Q, K, V, QIN, mask, Y, T);
@@ -402,6 +406,7 @@ k_ffn_fwd(const float* __restrict__ Y, const float* __restrict__ W1, const float
 
 void launch_ffn_fwd(const float* Y, const float* W1, const float* b1, const float* W2, const float* b2,
                     const float* ln_beta, const float* ln_gamma, float* OUT, int n_tok, cudaStream_t st) {
+  PAMREC_PROF("ffn_fwd", 1, st);
   static bool once = false;
   if (!once) { cudaFuncSetAttribute(k_ffn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnFwdSmem); once = true; }
   k_ffn_fwd<<<(n_tok + kTokTile - 1) / kTokTile, kTokTile, kFfnFwdSmem, st>>>(Y, W1, b1, W2, b2, ln_beta, ln_gamma, OUT, n_tok);
@@ -515,6 +520,7 @@ k_ffn_bwd(const float* __restrict__ Y, const float* __restrict__ dOUT, const flo
 void launch_ffn_bwd(const float* Y, const float* dOUT, const float* W1, const float* b1, const float* W2,
                     const float* ln_beta, const float* ln_gamma, float* dY, float* dW1, float* db1, float* dW2,
                     float* db2, float* dbeta, float* dgamma, int n_tok, cudaStream_t st) {
+  PAMREC_PROF("ffn_bwd", 1, st);
   static bool once = false;
   if (!once) { cudaFuncSetAttribute(k_ffn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnBwdSmem); once = true; }
   k_ffn_bwd<<<(n_tok + kTokTile - 1) / kTokTile, kTokTile, kFfnBwdSmem, st>>>(Y, dOUT, W1, b1, W2, ln_beta, ln_gamma, dY, dW1,
@@ -659,6 +665,7 @@ k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float
 
 void launch_attn_bwd(const float* Q, const float* K, const float* V, const float* dY, const int* mask, float* dQ,
                      float* dK, float* dV, int B, int T, cudaStream_t st) {
+  PAMREC_PROF("attn_bwd", 1, st);
   size_t smem = attn_bwd_smem(T);
   cudaFuncSetAttribute(k_attn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_attn_bwd<<<B, 256, smem, st>>>(Q, K, V, dY, mask, dQ, dK, dV, T);
@@ -766,6 +773,7 @@ void launch_proj_bwd(const float* X, const float* dY, const float* dQ, const flo
                      const int* ctl, const int* tile_bucket, const int* tile_begin, const int* tile_count, int max_tiles,
                      const float* Wq, const float* Wk, const float* Wv, const float* ln_beta, const float* ln_gamma,
                      float* dX, float* dWq, float* dWk, float* dWv, float* dbeta, float* dgamma, cudaStream_t st) {
+  PAMREC_PROF("proj_bwd", 1, st);
   static bool once = false;
   if (!once) { cudaFuncSetAttribute(k_proj_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjBwdSmem); once = true; }
   k_proj_bwd<<<max_tiles, kTokTile, kProjBwdSmem, st>>>(X, dY, dQ, dK, dV, perm, ctl, tile_bucket, tile_begin, tile_count, Wq,

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kRows) k_dense_fwd(const DenseP p) {
   }
 }
 
-void launch_dense_fwd(const DenseP& p, cudaStream_t st) {
+void launch_dense_fwd(const DenseP& p, cudaStream_t st) { PAMREC_PROF("dense_fwd", 1, st);
   static int smem_set = 0;
   int smem = (p.K * (kXs + kNc) + 4) * 4;
   if (smem > smem_set) { cudaFuncSetAttribute(k_dense_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set = smem; }
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kRows) k_dense_dx(const DenseDxP p) {
   }
 }
 
-void launch_dense_dx(const DenseDxP& p, cudaStream_t st) {
+void launch_dense_dx(const DenseDxP& p, cudaStream_t st) { PAMREC_PROF("dense_dx", 1, st);
   static int smem_set = 0;
   int maxN = 1;
   for (int s = 0; s < p.n_slices; ++s)
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kRows) k_dense_dw(const DenseDwP p) {
   }
 }
 
-void launch_dense_dw(const DenseDwP& p, cudaStream_t st) {
+void launch_dense_dw(const DenseDwP& p, cudaStream_t st) { PAMREC_PROF("dense_dw", 1, st);
   static int smem_set = 0;
   int Np = (p.N + kNc - 1) / kNc * kNc;
   int smem = kRows * (p.K + 1 + Np) * 4;
@@ -226,7 +226,7 @@ __global__ void k_bn_finalize(BnSet s, double count) {
   s.sums[2 * c] = 0.0;
   s.sums[2 * c + 1] = 0.0;
 }
-void launch_bn_finalize(const BnSet& s, double count, cudaStream_t st) {
+void launch_bn_finalize(const BnSet& s, double count, cudaStream_t st) { PAMREC_PROF("bn_finalize", 1, st);
   k_bn_finalize<<<(s.C + 127) / 128, 128, 0, st>>>(s, count);
 }
 __global__ void k_bn_eval_stat(BnSet s) {
@@ -235,7 +235,7 @@ __global__ void k_bn_eval_stat(BnSet s) {
   s.stat[2 * c] = s.mmean[c];
   s.stat[2 * c + 1] = 1.0f / sqrtf(s.mvar[c] + kBnEps);
 }
-void launch_bn_eval_stat(const BnSet& s, cudaStream_t st) { k_bn_eval_stat<<<(s.C + 127) / 128, 128, 0, st>>>(s); }
+void launch_bn_eval_stat(const BnSet& s, cudaStream_t st) { PAMREC_PROF("bn_eval_stat", 1, st); k_bn_eval_stat<<<(s.C + 127) / 128, 128, 0, st>>>(s); }
 
 constexpr int kBnRowsPerBlock = 1024;
 __global__ void __launch_bounds__(256) k_bn_bwd_stats(BnSet s, const float* __restrict__ dA, const float* __restrict__ Z, int M) {
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats(BnSet s, const float* __re
     atomicAdd(s.bsums + 2 * col + 1, s2);
   }
 }
-void launch_bn_bwd_stats(const BnSet& s, const float* dA, const float* Z, int M, cudaStream_t st) {
+void launch_bn_bwd_stats(const BnSet& s, const float* dA, const float* Z, int M, cudaStream_t st) { PAMREC_PROF("bn_bwd_stats", 1, st);
   int cb = s.C < 32 ? s.C : 32;
   dim3 grid((s.C + cb - 1) / cb, (M + kBnRowsPerBlock - 1) / kBnRowsPerBlock);
   k_bn_bwd_stats<<<grid, 256, 0, st>>>(s, dA, Z, M);
@@ -289,7 +289,7 @@ __global__ void k_bn_param_grad(BnSet s, float scale) {
   s.bsums[2 * c] = 0.0;
   s.bsums[2 * c + 1] = 0.0;
 }
-void launch_bn_bwd_apply(const BnSet& s, float* dA, const float* Z, int M, double count, float grad_scale, cudaStream_t st) {
+void launch_bn_bwd_apply(const BnSet& s, float* dA, const float* Z, int M, double count, float grad_scale, cudaStream_t st) { PAMREC_PROF("bn_bwd_apply", 2, st);
   int64_t total = (int64_t)M * s.C;
   k_bn_bwd_apply<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s, dA, Z, total, count);
   k_bn_param_grad<<<(s.C + 127) / 128, 128, 0, st>>>(s, grad_scale);
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(128) k_pool_fwd(const float* __restrict__ H, c
   }
 }
 void launch_pool_fwd(const float* H, const float* Z2, const BnSet& s1, const int* mask, float* new_long, int B, int T,
-                     cudaStream_t st) {
+                     cudaStream_t st) { PAMREC_PROF("pool_fwd", 1, st);
   k_pool_fwd<<<(B + 3) / 4, 128, 0, st>>>(H, Z2, s1, mask, new_long, B, T);
 }
 
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(128) k_pool_bwd(const float* __restrict__ H, c
     }
 }
 void launch_pool_bwd(const float* H, const float* Z2, const BnSet& s1, const int* mask, const float* dNL, float* dA2,
-                     float* dH, int B, int T, cudaStream_t st) {
+                     float* dH, int B, int T, cudaStream_t st) { PAMREC_PROF("pool_bwd", 1, st);
   k_pool_bwd<<<(B + 3) / 4, 128, 0, st>>>(H, Z2, s1, mask, dNL, dA2, dH, B, T);
 }
 
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(64) k_combine_fwd(const float* __restrict__ ZE
   if (c < kE) { float t = tgt[(int64_t)b * kE + c]; u[64 + c] = t; u[148 + c] = t; }
 }
 void launch_combine_fwd(const float* ZE1, const float* ZG1, const BnSet& e1, const BnSet& g1, const float* tgt, float* U,
-                        int B, cudaStream_t st) {
+                        int B, cudaStream_t st) { PAMREC_PROF("combine_fwd", 1, st);
   k_combine_fwd<<<B, 64, 0, st>>>(ZE1, ZG1, e1, g1, tgt, U, B);
 }
 
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(64) k_combine_bwd(const float* __restrict__ ZE
   if (c < 10) dG1[(int64_t)b * 10 + c] = red[0][c] + red[1][c];
 }
 void launch_combine_bwd(const float* ZE1, const float* ZG1, const BnSet& e1, const BnSet& g1, const float* dU, float* dE1,
-                        float* dG1, float* dTgt, int B, cudaStream_t st) {
+                        float* dG1, float* dTgt, int B, cudaStream_t st) { PAMREC_PROF("combine_bwd", 1, st);
   k_combine_bwd<<<B, 64, 0, st>>>(ZE1, ZG1, e1, g1, dU, dE1, dG1, dTgt, B);
 }
 
@@ -577,7 +577,7 @@ k_loss(const float* __restrict__ logits, const float* __restrict__ y_sat, const 
   }
 }
 void launch_loss(const float* logits, const float* y_sat, const float* y_play, const float* plays, float* d_logits,
-                 double* loss_acc, int B, int B_global, int n_valid, float fuzhu_w, float order_w, cudaStream_t st) {
+                 double* loss_acc, int B, int B_global, int n_valid, float fuzhu_w, float order_w, cudaStream_t st) { PAMREC_PROF("loss", 1, st);
   k_loss<<<1, 1024, 0, st>>>(logits, y_sat, y_play, plays, d_logits, loss_acc, B, B_global, n_valid, fuzhu_w, order_w);
 }
 
@@ -585,7 +585,7 @@ __global__ void k_sigmoid_col0(const float* __restrict__ logits, float* __restri
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) pred[b] = sigmoidf_(logits[3 * b]);
 }
-void launch_sigmoid_col0(const float* logits, float* pred, int B, cudaStream_t st) {
+void launch_sigmoid_col0(const float* logits, float* pred, int B, cudaStream_t st) { PAMREC_PROF("sigmoid", 1, st);
   k_sigmoid_col0<<<(B + 255) / 256, 256, 0, st>>>(logits, pred, B);
 }
 

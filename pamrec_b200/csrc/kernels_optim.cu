@@ -44,7 +44,7 @@ __global__ void k_pos_grad(const float* __restrict__ dX0, float* __restrict__ dP
   atomicAdd(dPos + e, s);
 }
 void launch_embed_bwd_reduce(const float* dX0, const float* dTgtHead, float* dTgtTotal, float* dPos, double* pos_normsq,
-                             int B, int T, cudaStream_t st) {
+                             int B, int T, cudaStream_t st) { PAMREC_PROF("embed_bwd_reduce", 2, st);
   k_dtgt_total<<<B, 128, 0, st>>>(dX0, dTgtHead, dTgtTotal, pos_normsq, T);
   dim3 grid((T * kD + 127) / 128, (B + kPosRows - 1) / kPosRows);
   k_pos_grad<<<grid, 128, 0, st>>>(dX0, dPos, B, T);
@@ -134,7 +134,7 @@ k_seg_reduce(const int* __restrict__ skeys, const int* __restrict__ sidx, const 
 
 int launch_sparse_reduce(const SparseTable& t, const int* hist_ids, const int* tgt_ids, int64_t n_hist, int64_t n_tgt,
                          const float* hist_grad, int hist_ld, int hist_col, const float* tgt_grad, int tgt_ld, int tgt_col,
-                         void* cub_temp, size_t cub_bytes, cudaStream_t st) {
+                         void* cub_temp, size_t cub_bytes, cudaStream_t st) { PAMREC_PROF("sparse_sort_reduce", 4, st);
   const int64_t n = n_hist + n_tgt;
   if (n == 0) return 0;
   const unsigned g256 = (unsigned)((n + 255) / 256);
@@ -188,7 +188,7 @@ k_sparse_l2norm(const int* __restrict__ ukeys, const int* __restrict__ nuniq, co
     }
   }
 }
-void launch_sparse_l2norm(const SparseTable& t, int64_t n_keys, float l2, double* reg_acc, cudaStream_t st) {
+void launch_sparse_l2norm(const SparseTable& t, int64_t n_keys, float l2, double* reg_acc, cudaStream_t st) { PAMREC_PROF("sparse_l2norm", 1, st);
   int64_t total = n_keys * (t.width / 4);
   unsigned g = (unsigned)((total + 255) / 256);
   if (t.width == 16) k_sparse_l2norm<16><<<g, 256, 0, st>>>(t.ukeys, t.nuniq, t.w, l2, t.normsq, reg_acc);
@@ -276,12 +276,12 @@ static void sparse_adam_w(const SparseTable& t, int64_t n_keys, int mode, float 
   }
 }
 void launch_sparse_adam(const SparseTable& t, int64_t n_keys, int mode, float l2, float lr_t, float b1, float b2, float eps,
-                        float clip, int is_clip, cudaStream_t st) {
+                        float clip, int is_clip, cudaStream_t st) { PAMREC_PROF("sparse_adam", 1, st);
   if (t.width == 16) sparse_adam_w<16>(t, n_keys, mode, l2, lr_t, b1, b2, eps, clip, is_clip, st);
   else if (t.width == 4) sparse_adam_w<4>(t, n_keys, mode, l2, lr_t, b1, b2, eps, clip, is_clip, st);
   else sparse_adam_w<20>(t, n_keys, mode, l2, lr_t, b1, b2, eps, clip, is_clip, st);
 }
-void launch_slot_reset(const SparseTable& t, int64_t n_keys, cudaStream_t st) {
+void launch_slot_reset(const SparseTable& t, int64_t n_keys, cudaStream_t st) { PAMREC_PROF("slot_reset", 1, st);
   k_slot_reset<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(t.ukeys, t.nuniq, t.slot);
 }
 
@@ -313,7 +313,7 @@ k_dense_norm(const float* __restrict__ P, const float* __restrict__ G, const int
   }
 }
 void launch_dense_norm(const float* P, const float* G, const int* seg_tab, int n_seg, float layer_l2, double* seg_normsq,
-                       const double* pos_normsq, double* reg_acc, cudaStream_t st) {
+                       const double* pos_normsq, double* reg_acc, cudaStream_t st) { PAMREC_PROF("dense_norm", 1, st);
   k_dense_norm<<<n_seg, 256, 0, st>>>(P, G, seg_tab, layer_l2, seg_normsq, pos_normsq, reg_acc);
 }
 
@@ -345,7 +345,7 @@ k_dense_adam(float* __restrict__ P, const float* __restrict__ G, float* __restri
 }
 void launch_dense_adam(float* P, const float* G, float* M, float* V, const int* seg_id, const int* seg_tab,
                        const double* seg_normsq, int64_t n, float layer_l2, float lr_t, float b1, float b2, float eps,
-                       float clip, int is_clip, cudaStream_t st) {
+                       float clip, int is_clip, cudaStream_t st) { PAMREC_PROF("dense_adam", 1, st);
   k_dense_adam<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, G, M, V, seg_id, seg_tab, seg_normsq, n, layer_l2, lr_t, b1, b2,
                                                            eps, clip, is_clip);
 }
@@ -358,6 +358,6 @@ __global__ void k_finish_losses(const double* __restrict__ acc, float* __restric
   losses[3] = (float)acc[1];
   losses[4] = (float)acc[2];
 }
-void launch_finish_losses(const double* loss_acc, float* losses, cudaStream_t st) { k_finish_losses<<<1, 1, 0, st>>>(loss_acc, losses); }
+void launch_finish_losses(const double* loss_acc, float* losses, cudaStream_t st) { PAMREC_PROF("finish_losses", 1, st); k_finish_losses<<<1, 1, 0, st>>>(loss_acc, losses); }
 
 }  // namespace pamrec

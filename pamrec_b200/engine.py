@@ -183,22 +183,60 @@ class Engine:
         return st
 
     # ------------------------------------------------------------------ batches
-    def upload(self, feed, training=True):
-        """feed: the reference's feed dict with string keys (io/sequential_iterator.py:1155-1175)."""
+    def upload(self, feed, training=True, staged=False):
+        """feed: the reference's feed dict with string keys (io/sequential_iterator.py:1155-1175).
+
+        staged=False allocates fresh device tensors (a batch that stays resident).  staged=True packs every field into
+        one pinned host buffer and issues ONE host->device copy into a reusable device buffer (two slots, alternating):
+        the streaming path used by PAMRECModel.train / eval."""
         B = int(np.asarray(feed["items"]).shape[0])
         T = self.dims[3]
-        tensors = {}
+        need = ("item_history", "item_cate_history", "item_loop_times_history", "mask", "items", "cates")
+        fields = []
         for name, dt, is_seq in BATCH_FIELDS:
             if name not in feed:
-                if training or name in ("item_history", "item_cate_history", "item_loop_times_history", "mask", "items", "cates"):
+                if training or name in need:
                     raise KeyError(f"feed is missing {name}")
                 continue
-            a = np.ascontiguousarray(np.asarray(feed[name]).reshape((B, T) if is_seq else (B,)).astype(dt, copy=False))
-            tensors[name] = torch.from_numpy(a).to(self.device, non_blocking=True)
+            fields.append((name, dt, (B, T) if is_seq else (B,)))
+        if B > self.dims[4]:
+            raise PamrecError(f"batch {B} outside [1, {self.dims[4]}]")
+        tensors = {}
+        if not staged:
+            for name, dt, shape in fields:
+                a = np.ascontiguousarray(np.asarray(feed[name]).reshape(shape).astype(dt, copy=False))
+                tensors[name] = torch.from_numpy(a).to(self.device, non_blocking=True)
+            nbytes = sum(t.numel() * 4 for t in tensors.values())
+        else:
+            if not hasattr(self, "_stage"):
+                cap = (4 * self.dims[4] * T + 6 * self.dims[4]) * 4 + 16 * 256
+                self._stage = [dict(host=torch.empty(cap, dtype=torch.uint8).pin_memory(),
+                                    dev=torch.empty(cap, dtype=torch.uint8, device=self.device),
+                                    done=torch.cuda.Event()) for _ in range(2)]
+                self._stage_i = 0
+            slot = self._stage[self._stage_i]
+            self._stage_i ^= 1
+            slot["done"].synchronize()                       # the previous copy out of this pinned slot has finished
+            host_np = slot["host"].numpy()
+            off = 0
+            views = []
+            for name, dt, shape in fields:
+                n = int(np.prod(shape)) * 4
+                np.copyto(host_np[off:off + n].view(dt).reshape(shape), np.asarray(feed[name]).reshape(shape), casting="unsafe")
+                views.append((name, dt, shape, off))
+                off += (n + 255) // 256 * 256
+            slot["dev"][:off].copy_(slot["host"][:off], non_blocking=True)
+            slot["done"].record(torch.cuda.current_stream(self.device))
+            for name, dt, shape, o in views:
+                n = int(np.prod(shape)) * 4
+                tdt = torch.int32 if dt == np.int32 else torch.float32
+                tensors[name] = slot["dev"][o:o + n].view(tdt).view(shape)
+            nbytes = off
         for name, _, _ in BATCH_FIELDS:          # scoring: unused pointers stay null
             if name not in tensors:
                 tensors[name] = torch.empty(0, device=self.device)
         db = DeviceBatch(tensors, B)
+        db.h2d_bytes = nbytes
         for name, _, _ in BATCH_FIELDS:
             if tensors[name].numel() == 0:
                 setattr(db.struct, name, None)
@@ -231,6 +269,21 @@ class Engine:
         self._check(self.lib.pamrec_train_step(self.handle, C.byref(db.struct), self.step,
                                                C.c_void_p(losses_out.data_ptr()), self._stream()))
         return losses_out
+
+    def profile(self, on=True):
+        self._check(self.lib.pamrec_profile_enable(self.handle, int(on)))
+        self._check(self.lib.pamrec_profile_reset(self.handle))
+
+    def profile_table(self):
+        """{launcher: (total_ms, timed launches)}; synchronises the device first."""
+        torch.cuda.synchronize(self.device)
+        out = {}
+        name = C.create_string_buffer(64)
+        ms, n = C.c_double(), C.c_int64()
+        for i in range(self.lib.pamrec_profile_count(self.handle)):
+            self._check(self.lib.pamrec_profile_get(self.handle, i, name, C.byref(ms), C.byref(n)))
+            out[name.value.decode()] = (ms.value, n.value)
+        return out
 
     def launches(self):
         return int(self.lib.pamrec_last_launch_count(self.handle))

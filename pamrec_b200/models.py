@@ -197,7 +197,7 @@ class SequentialBaseModel(BaseModel):
 
     # ------------------------------------------------------------------ device steps
     def _score(self, feed_dict):
-        db = self.engine.upload(feed_dict, training=False)
+        db = self.engine.upload(feed_dict, training=False, staged=True)
         return self.engine.forward(db, training=False).cpu().numpy().reshape(-1, 1)
 
     def eval(self, sess, feed_dict):
@@ -366,7 +366,7 @@ class PAMRECModel(SequentialBaseModel):
     def train(self, sess, feed_dict):
         """PAM:426-453: one optimisation step.  Returns the reference's 8-tuple
         (update, extra_update_ops, loss, data_loss, regular_loss, auxiliary_data_loss, order_loss, summary)."""
-        db = self.engine.upload(feed_dict, training=True)
+        db = self.engine.upload(feed_dict, training=True, staged=True)
         losses = self.engine.train_step(db).cpu().numpy()
         return [None, None, float(losses[0]), float(losses[1]), float(losses[2]), float(losses[3]), float(losses[4]), None]
 

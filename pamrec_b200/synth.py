@@ -79,3 +79,46 @@ def generate(root, dataset="wechat", n_users=None, n_items=None, n_cates=None, m
                     ni = int(rng.integers(1, NI + 1))
                     out.write("\t".join(["0", "0", str(u), str(ni), str(item_cate[ni]), f"{item_dur[ni]:.1f}", hist]) + "\n")
     return d
+
+
+def array_batch(seed, B, T, n_users, n_items, n_cates, grouped=True, min_len=1, zipf_a=1.1, n_buckets=10):
+    """Array-level synthetic feed in the layout of io/sequential_iterator.py:1111-1135 (live keys only), for
+    benchmarks at sizes where the text path would dominate (cfg 3).  grouped=True gives the
+    training layout: 5 consecutive rows share one history (io/sequential_iterator.py:645-684)."""
+    rng = np.random.default_rng(seed)
+    G = 5
+    assert not grouped or B % G == 0
+    n_hist = B // G if grouped else B
+    lens = rng.integers(min_len, T + 1, size=n_hist)
+    col = np.arange(T)[None, :]
+    mask = (col < lens[:, None]).astype(np.int32)
+    ih = (_zipf(rng, zipf_a, (n_hist, T), max(n_items - 1, 1)) * mask).astype(np.int32)
+    ch = (_zipf(rng, zipf_a, (n_hist, T), max(n_cates - 1, 1)) * mask).astype(np.int32)
+    bk = (rng.integers(0, n_buckets, size=(n_hist, T)) * mask).astype(np.float32)
+    rep = G if grouped else 1
+    return {
+        "item_history": np.repeat(ih, rep, axis=0),
+        "item_cate_history": np.repeat(ch, rep, axis=0),
+        "item_loop_times_history": np.repeat(bk, rep, axis=0),
+        "mask": np.repeat(mask, rep, axis=0).astype(np.float32),
+        "users": np.repeat(rng.integers(1, n_users, size=n_hist), rep).astype(np.float32),
+        "items": _zipf(rng, zipf_a, B, max(n_items - 1, 1)).astype(np.int32),
+        "cates": _zipf(rng, zipf_a, B, max(n_cates - 1, 1)).astype(np.int32),
+        "labels_satisfied": rng.integers(0, 2, size=(B, 1)).astype(np.float32),
+        "labels_play": rng.integers(0, 2, size=(B, 1)).astype(np.float32),
+        "plays": rng.integers(0, n_buckets, size=(B, 1)).astype(np.float32),
+    }
+
+
+def write_vocab_only(root, dataset, n_users, n_items, n_cates):
+    """Just the files a model needs to be constructed (vocab pickles + meta csv), for array-level benchmarks."""
+    d = os.path.join(root, dataset)
+    os.makedirs(d, exist_ok=True)
+    vocab = lambda n, dflt: {dflt: 0, **{str(i): i for i in range(1, n)}}
+    for name, voc in (("user_vocab.pkl", vocab(n_users, "default_uid")), ("item_vocab.pkl", vocab(n_items, "default_mid")),
+                      ("category_vocab.pkl", vocab(n_cates, "default_cat"))):
+        with open(os.path.join(d, name), "wb") as f:
+            pickle.dump(voc, f)
+    with open(os.path.join(d, f"{dataset}_business_recommenders.csv"), "w") as f:
+        f.write("1\t1\t10.0\n")
+    return d
