@@ -1,0 +1,5 @@
+class ShareBottomModel:
+    """Baseline model of the reference, outside the PAMRec hot path."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("ShareBottomModel is out of scope of pamrec_b200; only PAMRECModel is implemented")

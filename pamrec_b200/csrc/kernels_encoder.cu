@@ -278,6 +278,7 @@ void launch_proj_fwd(const float* X, const int* perm, const int* ctl, const int*
 __host__ __device__ inline int attn_tp(int T) { return (T + 3) & ~3; }
 inline size_t attn_fwd_smem(int T) { return (size_t)(3 * T * kAttnStride + 8 * attn_tp(T)) * 4 + (size_t)T * 4; }
 
+template <int NJ>
 __global__ void __launch_bounds__(256)
 k_attn_fwd(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
            const float* __restrict__ QIN, const int* __restrict__ mask, float* __restrict__ Y, int T) {
@@ -305,10 +306,10 @@ k_attn_fwd(const float* __restrict__ Q, const float* __restrict__ K, const float
     float4 q[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) q[i] = ld4(Qs + t * kAttnStride + 4 * i);
-    float s[8];
+    float s[NJ];
     float m = -INFINITY;
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
+    for (int jj = 0; jj < NJ; ++jj) {
       int j = jj * 32 + lane;
       float val = -INFINITY;
       if (j < T) {
@@ -323,7 +324,7 @@ k_attn_fwd(const float* __restrict__ Q, const float* __restrict__ K, const float
     m = warp_max(m);
     float sum = 0.f;
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
+    for (int jj = 0; jj < NJ; ++jj) {
       int j = jj * 32 + lane;
       float e = (j < T) ? expf(s[jj] - m) : 0.f;
       s[jj] = e;
@@ -331,7 +332,7 @@ k_attn_fwd(const float* __restrict__ Q, const float* __restrict__ K, const float
     }
     sum = warp_sum(sum);
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
+    for (int jj = 0; jj < NJ; ++jj) {
       int j = jj * 32 + lane;
       if (j < T) pw[j] = s[jj] / sum;
     }
@@ -349,12 +350,27 @@ k_attn_fwd(const float* __restrict__ Q, const float* __restrict__ K, const float
   }
 }
 
+template <int NJ>
+static void attn_fwd_nj(const float* Q, const float* K, const float* V, const float* QIN, const int* mask, float* Y, int B,
+                        int T, size_t smem, cudaStream_t st) {
+  static size_t smem_set = 0;
+  if (smem > smem_set) { cudaFuncSetAttribute(k_attn_fwd<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); smem_set = smem; }
+  k_attn_fwd<NJ><<<B, 256, smem, st>>>(Q, K, V, QIN, mask, Y, T);
+}
 void launch_attn_fwd(const float* Q, const float* K, const float* V, const float* QIN, const int* mask, float* Y, int B,
                      int T, cudaStream_t st) {
   PAMREC_PROF("attn_fwd", 1, st);
   size_t smem = attn_fwd_smem(T);
-  cudaFuncSetAttribute(k_attn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_attn_fwd<<<B, 256, smem, st>>>(Q, K, V, QIN, mask, Y, T);
+  switch ((T + 31) / 32) {
+    case 1: attn_fwd_nj<1>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
+    case 2: attn_fwd_nj<2>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
+    case 3: attn_fwd_nj<3>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
+    case 4: attn_fwd_nj<4>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
+    case 5: attn_fwd_nj<5>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
+    case 6: attn_fwd_nj<6>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
+    case 7: attn_fwd_nj<7>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
+    default: attn_fwd_nj<8>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -533,6 +549,7 @@ void launch_ffn_bwd(const float* Y, const float* dOUT, const float* W1, const fl
 // key) recomputes the column from the saved row statistics and forms dK, dV.
 inline size_t attn_bwd_smem(int T) { return (size_t)(4 * T * kAttnStride + 16 * attn_tp(T) + 3 * T) * 4 + (size_t)T * 4; }
 
+template <int NJ>
 __global__ void __launch_bounds__(256)
 k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
            const float* __restrict__ dY, const int* __restrict__ mask, float* __restrict__ dQ, float* __restrict__ dK,
@@ -569,10 +586,10 @@ k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float
     float4 q[10], g[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) { q[i] = ld4(Qs + t * kAttnStride + 4 * i); g[i] = ld4(Gs + t * kAttnStride + 4 * i); }
-    float s[8], dp[8];
+    float s[NJ], dp[NJ];
     float m = -INFINITY;
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
+    for (int jj = 0; jj < NJ; ++jj) {
       int j = jj * 32 + lane;
       float val = -INFINITY, dpv = 0.f;
       if (j < T) {
@@ -589,7 +606,7 @@ k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float
     m = warp_max(m);
     float sum = 0.f;
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
+    for (int jj = 0; jj < NJ; ++jj) {
       int j = jj * 32 + lane;
       float e = (j < T) ? expf(s[jj] - m) : 0.f;
       s[jj] = e;
@@ -598,7 +615,7 @@ k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float
     sum = warp_sum(sum);
     float Dv = 0.f;
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
+    for (int jj = 0; jj < NJ; ++jj) {
       int j = jj * 32 + lane;
       float p = (j < T) ? s[jj] / sum : 0.f;
       s[jj] = p;
@@ -607,7 +624,7 @@ k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float
     Dv = warp_sum(Dv);
     if (lane == 0) { rowm[t] = m; rowl[t] = sum; rowD[t] = Dv; }
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
+    for (int jj = 0; jj < NJ; ++jj) {
       int j = jj * 32 + lane;
       if (j < T) pw[j] = mk[j] ? s[jj] * (dp[jj] - Dv) / scale : 0.f;
     }
@@ -630,7 +647,7 @@ k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float
     for (int i = 0; i < 10; ++i) { kj[i] = ld4(Ks + j * kAttnStride + 4 * i); vj[i] = ld4(Vs + j * kAttnStride + 4 * i); }
     const int mkj = mk[j];
 #pragma unroll
-    for (int tt = 0; tt < 8; ++tt) {
+    for (int tt = 0; tt < NJ; ++tt) {
       int t = tt * 32 + lane;
       if (t < T) {
         float d = 0.f, dpv = 0.f;
@@ -663,12 +680,27 @@ k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float
   }
 }
 
+template <int NJ>
+static void attn_bwd_nj(const float* Q, const float* K, const float* V, const float* dY, const int* mask, float* dQ, float* dK,
+                        float* dV, int B, int T, size_t smem, cudaStream_t st) {
+  static size_t smem_set = 0;
+  if (smem > smem_set) { cudaFuncSetAttribute(k_attn_bwd<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); smem_set = smem; }
+  k_attn_bwd<NJ><<<B, 256, smem, st>>>(Q, K, V, dY, mask, dQ, dK, dV, T);
+}
 void launch_attn_bwd(const float* Q, const float* K, const float* V, const float* dY, const int* mask, float* dQ,
                      float* dK, float* dV, int B, int T, cudaStream_t st) {
   PAMREC_PROF("attn_bwd", 1, st);
   size_t smem = attn_bwd_smem(T);
-  cudaFuncSetAttribute(k_attn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_attn_bwd<<<B, 256, smem, st>>>(Q, K, V, dY, mask, dQ, dK, dV, T);
+  switch ((T + 31) / 32) {
+    case 1: attn_bwd_nj<1>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;
+    case 2: attn_bwd_nj<2>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;
+    case 3: attn_bwd_nj<3>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;
+    case 4: attn_bwd_nj<4>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;
+    case 5: attn_bwd_nj<5>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;
+    case 6: attn_bwd_nj<6>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;
+    case 7: attn_bwd_nj<7>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;
+    default: attn_bwd_nj<8>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -237,22 +237,27 @@ __global__ void k_bn_eval_stat(BnSet s) {
 }
 void launch_bn_eval_stat(const BnSet& s, cudaStream_t st) { PAMREC_PROF("bn_eval_stat", 1, st); k_bn_eval_stat<<<(s.C + 127) / 128, 128, 0, st>>>(s); }
 
-constexpr int kBnRowsPerBlock = 1024;
+constexpr int kBnRowsPerThread = 8;
 __global__ void __launch_bounds__(256) k_bn_bwd_stats(BnSet s, const float* __restrict__ dA, const float* __restrict__ Z, int M) {
   __shared__ double sh[2][256];
   const int cb = min(s.C, 32), rl = 256 / cb;
   const int tid = threadIdx.x, ry = tid / cb, cx = tid % cb;
   const int col = blockIdx.x * cb + cx;
+  const int rpb = rl * kBnRowsPerThread;
   double s1 = 0.0, s2 = 0.0;
   if (ry < rl && col < s.C) {
     const float mean = s.stat[2 * col], inv = s.stat[2 * col + 1], g = s.gamma[col], be = s.beta[col];
-    const int r1 = min(M, (int)(blockIdx.y + 1) * kBnRowsPerBlock);
-    for (int r = blockIdx.y * kBnRowsPerBlock + ry; r < r1; r += rl) {
-      float xh = (Z[(int64_t)r * s.C + col] - mean) * inv;
-      float y = fmaf(g, xh, be);
-      float dy = y > 0.f ? dA[(int64_t)r * s.C + col] : 0.f;
-      s1 += (double)dy;
-      s2 += (double)dy * (double)xh;
+    const int r0 = blockIdx.y * rpb + ry;
+#pragma unroll
+    for (int k = 0; k < kBnRowsPerThread; ++k) {
+      int r = r0 + k * rl;
+      if (r < M) {
+        float xh = (Z[(int64_t)r * s.C + col] - mean) * inv;
+        float y = fmaf(g, xh, be);
+        float dy = y > 0.f ? dA[(int64_t)r * s.C + col] : 0.f;
+        s1 += (double)dy;
+        s2 += (double)dy * (double)xh;
+      }
     }
   }
   sh[0][tid] = s1; sh[1][tid] = s2;
@@ -265,7 +270,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats(BnSet s, const float* __re
 }
 void launch_bn_bwd_stats(const BnSet& s, const float* dA, const float* Z, int M, cudaStream_t st) { PAMREC_PROF("bn_bwd_stats", 1, st);
   int cb = s.C < 32 ? s.C : 32;
-  dim3 grid((s.C + cb - 1) / cb, (M + kBnRowsPerBlock - 1) / kBnRowsPerBlock);
+  int rpb = (256 / cb) * kBnRowsPerThread;
+  dim3 grid((s.C + cb - 1) / cb, (M + rpb - 1) / rpb);
   k_bn_bwd_stats<<<grid, 256, 0, st>>>(s, dA, Z, M);
 }
 
