@@ -86,7 +86,7 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_model(w, tmp, sparse_adam="dense_exact"):
+def build_model(w, tmp, sparse_adam="dense_exact", **extra):
     from pamrec_b200 import synth
     from pamrec_b200.deeprec_utils import prepare_hparams
     from pamrec_b200.models import PAMRECModel
@@ -99,7 +99,7 @@ def build_model(w, tmp, sparse_adam="dense_exact"):
                          item_vocab=os.path.join(d, "item_vocab.pkl"), cate_vocab=os.path.join(d, "category_vocab.pkl"),
                          train_num_ngs=0, max_seq_length=w["T"], pairwise_metrics=[], weighted_metrics=["wauc"], fuzhu_weight=0.5,
                          fine_tune=False, eval_step=10 ** 9, noise_train_hist=0, noise_train_listwise=0, noise_only_predict=0,
-                         write_tfevents=False, sparse_adam=sparse_adam)
+                         write_tfevents=False, sparse_adam=sparse_adam, **extra)
     return PAMRECModel(hp, SequentialIterator, seed=8)
 
 
@@ -158,7 +158,9 @@ def run_ours(args, w, rank, world):
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
     dev = torch.device("cuda", torch.cuda.current_device())
     tmp = tempfile.mkdtemp(prefix="pamrec_bench_")
-    model = build_model(w, tmp)
+    # N > 1: weak scaling — every rank trains on its own B rows of a global batch of N*B rows (listwise groups are
+    # independent); tables row-sharded over the ranks, BN statistics / clip norms / losses / dense grads all-reduced.
+    model = build_model(w, tmp, **({"dp_feed": "local"} if world > 1 else {}))
     eng = model.engine
     B, T = w["B"], w["T"]
     feeds = [synth.array_batch(1000 + 17 * i + rank, B, T, w["n_users"], w["n_items"], w["n_cates"]) for i in range(N_POOL)]
@@ -238,7 +240,7 @@ def run_ours(args, w, rank, world):
             ach = units / (per_launch_ms / 1e3) / 1e9
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                     "traffic": None, "peak_source": pk["source"]}
-    hbm = hbm_microbench(eng, pk)
+    hbm = hbm_microbench(eng, pk) if world == 1 else None
 
     out = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -246,6 +248,9 @@ def run_ours(args, w, rank, world):
         "data": "synthetic", "impl": "pamrec_b200",
         "config": {"workload": args.workload, "batch_per_gpu": B, "seq_len": T, "group": 5, "n_items": w["n_items"],
                    "n_cates": w["n_cates"], "n_users": w["n_users"], "sparse_adam": "dense_exact",
+                   "global_batch": B * world, "tables": eng.tables,
+                   "parallelism": "single GPU" if world == 1 else f"dp{world}: groups sharded over ranks, tables row-sharded "
+                                  "(id % N) with NCCL all-to-all of rows / row gradients, sync-BN + dense all-reduce",
                    "l2": "flushed between timed steps (256 MiB write); per-step working set also exceeds L2",
                    "batch_note": "BASELINE batch 1024 rounded to 1025: batches must be multiples of 5"},
         "e2e": e2e, "gpu_launches": int(launches) * K, "gpu_launches_per_step": int(launches), "clocks": clk, "roofline": roof, "roofline_hbm": hbm,
@@ -322,13 +327,17 @@ def main():
             print(json.dumps(out), flush=True)
         return
     if world > 1:
-        raise SystemExit("bench.py: data-parallel multi-GPU step is not wired into the bench yet (N=1 only)")
-    out, _ = run_ours(args, w, rank, world)
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(local)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out, model = run_ours(args, w, rank, world)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(w)
         print(json.dumps(out), flush=True)
     if world > 1:
+        torch.distributed.barrier()
+        model.engine.close()
         torch.distributed.destroy_process_group()
 
 

@@ -46,6 +46,11 @@ typedef struct PamrecHandle_* PamrecHandle;
 enum { PAMREC_ADAM_DENSE_EXACT = 0, /* tf.train.AdamOptimizer: decay + update EVERY row     */
        PAMREC_ADAM_LAZY = 1 };      /* touched rows only (tf.contrib.opt.LazyAdamOptimizer) */
 
+/* embedding-table placement */
+enum { PAMREC_TABLES_LOCAL = 0,     /* whole tables on this GPU, direct gather (world_size must be 1)          */
+       PAMREC_TABLES_SHARDED = 1 }; /* row r lives on rank r % world_size at local row r / world_size; rows
+                                       and row gradients travel by all-to-all (works with world_size 1 too) */
+
 typedef struct PamrecConfig {
   int32_t n_users, n_items, n_cates; /* vocabulary sizes = table rows (sequential_base_model.py:565-567) */
   int32_t max_seq_len;               /* T, hparams.max_seq_length                                       */
@@ -57,10 +62,13 @@ typedef struct PamrecConfig {
   float fuzhu_weight;                /* pamrec.py:106                                                   */
   float order_weight;                /* hparams.discrepancy_loss_weight, pamrec.py:79                   */
   int32_t sparse_adam_mode;          /* PAMREC_ADAM_*                                                   */
-  /* data parallel (one process per GPU): this rank's share of one global batch.  With
-   * world_size > 1 the host all-reduces the buffers named by pamrec_sync_info between
-   * phases; single GPU uses pamrec_train_step.                                          */
+  /* data parallel over listwise groups, one process per GPU (no reference counterpart: the
+   * reference is single-device).  Each rank passes its share of one GLOBAL batch; batch-norm
+   * statistics, clip norms, loss means and dense gradients are all-reduced inside the step,
+   * so the result equals the single-GPU step on the concatenated batch.  world_size > 1
+   * needs pamrec_comm_init and table_mode = PAMREC_TABLES_SHARDED.                        */
   int32_t world_size, rank;
+  int32_t table_mode;                /* PAMREC_TABLES_*                                                 */
 } PamrecConfig;
 
 /* One batch, device pointers (layouts of io/sequential_iterator.py:1111-1135). */
@@ -76,16 +84,19 @@ typedef struct PamrecBatch {
   const float* labels_satisfied;      /* [B]  (train only)                                     */
   const float* labels_play;           /* [B]  (train only)                                     */
   const float* plays;                 /* [B]  bucket index as float (train only)               */
+  int32_t global_batch;               /* rows of the whole global batch over all ranks; 0 = batch * world_size.
+                                         batch may be 0 on a rank that only takes part in the collectives   */
 } PamrecBatch;
 
 /* Caller-owned device memory handed to the library once. */
 typedef struct PamrecBuffers {
   float* dense_param; float* dense_grad; float* dense_m; float* dense_v; /* [dense_numel] each      */
   float* bn_moving;                                                      /* [bn_numel] mean|var sets */
-  float* item_w; float* item_m; float* item_v;                           /* [n_items,16]            */
-  float* cate_w; float* cate_m; float* cate_v;                           /* [n_cates,4]             */
-  float* ulong_w; float* ulong_m; float* ulong_v;                        /* [n_users,20]            */
-  float* ushort_w; float* ushort_m; float* ushort_v;                     /* [n_users,20]            */
+  /* tables: [rows,width] with rows = vocabulary size (PAMREC_TABLES_LOCAL) or pamrec_shard_rows (SHARDED) */
+  float* item_w; float* item_m; float* item_v;                           /* [rows(n_items),16]      */
+  float* cate_w; float* cate_m; float* cate_v;                           /* [rows(n_cates),4]       */
+  float* ulong_w; float* ulong_m; float* ulong_v;                        /* [rows(n_users),20]      */
+  float* ushort_w; float* ushort_m; float* ushort_v;                     /* [rows(n_users),20]      */
   void* workspace; size_t workspace_bytes;                               /* >= pamrec_workspace_bytes */
 } PamrecBuffers;
 
@@ -128,11 +139,18 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
 /* forward + backward + apply; losses_out (device, 5 floats): loss, data, regular, auxiliary, order (pamrec.py:444-448) */
 int pamrec_train_step(PamrecHandle h, const PamrecBatch* b, int64_t step, float* losses_out, void* stream);
 
-/* Data-parallel phases (world_size > 1): the host runs an NCCL all-reduce(sum) on the
- * workspace tensor named by `sync_name` after each phase returns 1, then calls the next
- * phase; returns 0 when the step is complete.  Phase ids are opaque and sequential. */
-int pamrec_train_phase(PamrecHandle h, const PamrecBatch* b, int64_t step, int phase, float* losses_out,
-                       char sync_name[160], void* stream);
+/* Multi-GPU plumbing.  The library talks to NCCL directly (dlopen of the libnccl.so.2 that PyTorch ships;
+ * `nccl_path` may be NULL to use the loader's search path).  Rank 0 creates the unique id, the host broadcasts
+ * the 128 bytes (torch.distributed), every rank calls pamrec_comm_init; afterwards forward / backward /
+ * apply_gradients / train_step are collective calls that every rank must make in the same order. */
+#define PAMREC_COMM_ID_BYTES 128
+int pamrec_comm_unique_id(const char* nccl_path, char id_out[PAMREC_COMM_ID_BYTES]);
+int pamrec_comm_init(PamrecHandle h, const char* nccl_path, const char id[PAMREC_COMM_ID_BYTES]);
+int pamrec_comm_destroy(PamrecHandle h);
+/* rows of this rank's shard of a table with `vocab_rows` rows: ceil(vocab_rows / world_size) (all ranks equal, tail padded) */
+int64_t pamrec_shard_rows(PamrecHandle h, int64_t vocab_rows);
+/* sum-all-reduce of a caller buffer over the handle's communicator (dtype PAMREC_F32 / PAMREC_F64 / PAMREC_I32) */
+int pamrec_comm_all_reduce(PamrecHandle h, void* dptr, int64_t count, int dtype, void* stream);
 
 /* Stand-alone HBM kernels for roofline measurement (same kernels the step uses). */
 int pamrec_bench_gather(PamrecHandle h, const int32_t* item_ids, const int32_t* cate_ids, const int32_t* tgt_items,

@@ -10,6 +10,8 @@ POOL_DENSE, POOL_BN, POOL_WORKSPACE = 0, 1, 2
 F32, I32, F64, U8 = 0, 1, 2, 3
 SEG_L2, SEG_POS, SEG_DEAD = 1, 2, 4
 ADAM_DENSE_EXACT, ADAM_LAZY = 0, 1
+TABLES_LOCAL, TABLES_SHARDED = 0, 1
+COMM_ID_BYTES = 128
 GROUP = 5
 
 
@@ -20,7 +22,7 @@ class PamrecConfig(C.Structure):
         ("learning_rate", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
         ("embed_l2", C.c_float), ("layer_l2", C.c_float), ("max_grad_norm", C.c_float), ("is_clip_norm", C.c_int32),
         ("fuzhu_weight", C.c_float), ("order_weight", C.c_float), ("sparse_adam_mode", C.c_int32),
-        ("world_size", C.c_int32), ("rank", C.c_int32),
+        ("world_size", C.c_int32), ("rank", C.c_int32), ("table_mode", C.c_int32),
     ]
 
 
@@ -30,6 +32,7 @@ class PamrecBatch(C.Structure):
         ("item_history", C.c_void_p), ("item_cate_history", C.c_void_p), ("item_loop_times_history", C.c_void_p),
         ("mask", C.c_void_p), ("users", C.c_void_p), ("items", C.c_void_p), ("cates", C.c_void_p),
         ("labels_satisfied", C.c_void_p), ("labels_play", C.c_void_p), ("plays", C.c_void_p),
+        ("global_batch", C.c_int32),
     ]
 
 
@@ -61,7 +64,11 @@ EXPORTS = {
     "pamrec_backward": (C.c_int, [C.c_void_p, C.POINTER(PamrecBatch), C.c_void_p]),
     "pamrec_apply_gradients": (C.c_int, [C.c_void_p, C.POINTER(PamrecBatch), C.c_int64, C.c_void_p]),
     "pamrec_train_step": (C.c_int, [C.c_void_p, C.POINTER(PamrecBatch), C.c_int64, C.c_void_p, C.c_void_p]),
-    "pamrec_train_phase": (C.c_int, [C.c_void_p, C.POINTER(PamrecBatch), C.c_int64, C.c_int, C.c_void_p, C.c_char_p, C.c_void_p]),
+    "pamrec_comm_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "pamrec_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "pamrec_comm_destroy": (C.c_int, [C.c_void_p]),
+    "pamrec_shard_rows": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "pamrec_comm_all_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "pamrec_bench_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                       C.c_void_p, C.c_void_p]),
     "pamrec_bench_table_adam": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),

@@ -6,12 +6,37 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpamrec_b200.so")
-SOURCES = ["api.cu", "prof.cu", "kernels_encoder.cu", "kernels_head.cu", "kernels_optim.cu"]
-HEADERS = ["common.cuh", "kernels.h", "layout.h", os.path.join("..", "..", "include", "pamrec_b200.h")]
+SOURCES = ["api.cu", "prof.cu", "comm.cu", "kernels_encoder.cu", "kernels_head.cu", "kernels_optim.cu", "kernels_shard.cu"]
+HEADERS = ["common.cuh", "kernels.h", "layout.h", "comm.h", os.path.join("..", "..", "include", "pamrec_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr",
 ]
+
+
+def nccl_include():
+    """nccl.h matching the libnccl.so.2 that PyTorch loads (types only: the functions are resolved with dlsym)."""
+    try:
+        import nvidia
+        for p in nvidia.__path__:
+            inc = os.path.join(p, "nccl", "include")
+            if os.path.exists(os.path.join(inc, "nccl.h")):
+                return ["-I", inc]
+    except Exception:
+        pass
+    return []
+
+
+def nccl_library():
+    try:
+        import nvidia
+        for p in nvidia.__path__:
+            lib = os.path.join(p, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(lib):
+                return lib
+    except Exception:
+        pass
+    return None
 
 
 def _stale(target, deps):
@@ -33,7 +58,7 @@ def build(verbose=False, force=False, extra=()):
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
+            cmd = [nvcc, *NVCC_FLAGS, *nccl_include(), *extra, "-c", src, "-o", obj]
             if verbose:
                 print(" ".join(cmd), file=sys.stderr)
             procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -44,7 +69,7 @@ def build(verbose=False, force=False, extra=()):
         if verbose and out.strip():
             print(out, file=sys.stderr)
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}")

@@ -6,13 +6,17 @@
 #include <string>
 #include <vector>
 
+#include "comm.h"
 #include "kernels.h"
 #include "layout.h"
 
-namespace pamrec {
-void launch_slot_reset(const SparseTable& t, int64_t n_keys, cudaStream_t st);
-}
 using namespace pamrec;
+
+// host view of one table's all-to-all for the current batch (element = one id / one row)
+struct Xchg {
+  std::vector<int64_t> soff, scnt, roff, rcnt;
+  int64_t n_send = 0, n_recv = 0;
+};
 
 struct PamrecHandle_ {
   PamrecConfig cfg;
@@ -24,6 +28,12 @@ struct PamrecHandle_ {
   Prof prof;
   BnSet bn[BN_COUNT];
   std::vector<int> h_seg_id, h_seg_tab;
+  Comm comm;
+  int* h_counts = nullptr;      // pinned [2][world][4]: send | recv counts of the current batch (sharded tables)
+  Xchg xc[3];                   // item, cate, user
+  bool xc_users = false;        // the current exchange carried user ids (training)
+  bool sharded() const { return cfg.table_mode == PAMREC_TABLES_SHARDED; }
+  ~PamrecHandle_() { if (h_counts) cudaFreeHost(h_counts); }
 
   float* P(int64_t off) const { return buf.dense_param + off; }
   float* G(int64_t off) const { return buf.dense_grad + off; }
@@ -66,9 +76,19 @@ int pamrec_create(const PamrecConfig* cfg, PamrecHandle* out) {
   if (cfg->n_users < 1 || cfg->n_items < 1 || cfg->n_cates < 1) return -2;
   if (cfg->max_seq_len < 1 || cfg->max_seq_len > PAMREC_MAX_T) return -3;
   if (cfg->max_batch < 1) return -4;
+  const int world = cfg->world_size < 1 ? 1 : cfg->world_size;
+  if (world > 64 || cfg->rank < 0 || cfg->rank >= world) return -5;
+  if (cfg->table_mode != PAMREC_TABLES_LOCAL && cfg->table_mode != PAMREC_TABLES_SHARDED) return -6;
+  if (world > 1 && cfg->table_mode != PAMREC_TABLES_SHARDED) return -6;      // multi-GPU = row-sharded tables
+  {
+    // sharded keys are owner * rows_per_shard + local row: must fit an int32
+    int64_t big = cfg->n_items > cfg->n_users ? cfg->n_items : cfg->n_users;
+    if (cfg->n_cates > big) big = cfg->n_cates;
+    if (((big + world - 1) / world) * world >= ((int64_t)1 << 31)) return -7;
+  }
   PamrecHandle h = new PamrecHandle_();
   h->cfg = *cfg;
-  if (h->cfg.world_size < 1) h->cfg.world_size = 1;
+  h->cfg.world_size = world;
   h->L.build(h->cfg);
   const int n_seg = (int)h->L.dense.size();
   h->h_seg_id.assign((size_t)h->L.dense_numel, 0);
@@ -93,6 +113,23 @@ int64_t pamrec_dense_numel(PamrecHandle h) { return h ? h->L.dense_numel : -1; }
 int64_t pamrec_bn_numel(PamrecHandle h) { return h ? h->L.bn_numel : -1; }
 size_t pamrec_workspace_bytes(PamrecHandle h) { return h ? h->L.ws_bytes : 0; }
 int64_t pamrec_last_launch_count(PamrecHandle h) { return h ? h->launches : -1; }
+int64_t pamrec_shard_rows(PamrecHandle h, int64_t vocab_rows) { return h ? h->L.rows_of(vocab_rows) : -1; }
+
+int pamrec_comm_unique_id(const char* nccl_path, char id_out[PAMREC_COMM_ID_BYTES]) {
+  std::string err;
+  if (Comm::unique_id(nccl_path, id_out, &err)) { fprintf(stderr, "pamrec_comm_unique_id: %s\n", err.c_str()); return -1; }
+  return 0;
+}
+int pamrec_comm_init(PamrecHandle h, const char* nccl_path, const char id[PAMREC_COMM_ID_BYTES]) {
+  if (!h || !id) return -1;
+  if (h->comm.init(nccl_path, id, h->cfg.world_size, h->cfg.rank)) { h->err = "comm_init: " + h->comm.err; return -1; }
+  return 0;
+}
+int pamrec_comm_destroy(PamrecHandle h) {
+  if (!h) return -1;
+  h->comm.destroy();
+  return 0;
+}
 
 static const std::vector<TensorDesc>* pool_of(PamrecHandle h, int pool) {
   if (!h) return nullptr;
@@ -142,14 +179,16 @@ int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
   h->buf = *bufs;
   static const char* names[BN_COUNT] = {"s0", "s1", "e0", "g0", "e1", "g1", "t0", "t1"};
   for (int i = 0; i < BN_COUNT; ++i) h->bn[i] = make_bn(h, i, names[i]);
-  const int64_t NK = (int64_t)h->cfg.max_batch * h->cfg.max_seq_len + h->cfg.max_batch;
-  size_t need = sparse_temp_bytes(NK);
+  size_t need = sparse_temp_bytes(h->L.cub_keys);
   size_t have = (size_t)h->L.ws[h->L.ws_index["cub_temp"]].numel;
   if (need > have) return fail(h, "cub temp storage: need %zu have %zu", need, have);
   cudaMemsetAsync(h->buf.workspace, 0, h->L.ws_bytes, st);
-  cudaMemsetAsync(h->wi("sp.item.slot"), 0xFF, (size_t)h->cfg.n_items * 4, st);
-  cudaMemsetAsync(h->wi("sp.cate.slot"), 0xFF, (size_t)h->cfg.n_cates * 4, st);
-  cudaMemsetAsync(h->wi("sp.user.slot"), 0xFF, (size_t)h->cfg.n_users * 4, st);
+  cudaMemsetAsync(h->wi("sp.item.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_items) * 4, st);
+  cudaMemsetAsync(h->wi("sp.cate.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_cates) * 4, st);
+  cudaMemsetAsync(h->wi("sp.user.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_users) * 4, st);
+  if (h->sharded() && !h->h_counts &&
+      cudaMallocHost(&h->h_counts, sizeof(int) * 8 * (size_t)h->cfg.world_size) != cudaSuccess)
+    return fail(h, "cudaMallocHost for the exchange counts failed");
   cudaMemcpyAsync(h->wi("seg_id"), h->h_seg_id.data(), h->h_seg_id.size() * 4, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(h->wi("seg_tab"), h->h_seg_tab.data(), h->h_seg_tab.size() * 4, cudaMemcpyHostToDevice, st);
   cudaStreamSynchronize(st);
@@ -161,6 +200,7 @@ static int check_batch(PamrecHandle h, const PamrecBatch* b, bool training) {
   if (!h) return -1;
   if (!h->bound) return fail(h, "pamrec_bind has not been called");
   if (!b) return fail(h, "null batch");
+  if (b->batch == 0 && h->sharded()) return 0;          // this rank only takes part in the collectives
   if (b->batch < 1 || b->batch > h->cfg.max_batch) return fail(h, "batch %d outside [1, %d]", b->batch, h->cfg.max_batch);
   if (training && b->batch % PAMREC_GROUP != 0)
     return fail(h, "training batch %d is not a multiple of %d (pamrec.py:73-75)", b->batch, PAMREC_GROUP);
@@ -170,12 +210,156 @@ static int check_batch(PamrecHandle h, const PamrecBatch* b, bool training) {
   return 0;
 }
 
+static SparseTable table_of(PamrecHandle h, const char* which) {
+  SparseTable t;
+  memset(&t, 0, sizeof t);
+  std::string w = which;
+  std::string p = (w == "item" || w == "cate") ? "sp." + w + "." : "sp.user.";
+  t.keys = h->wi(p + "keys"); t.idx = h->wi(p + "idx"); t.skeys = h->wi(p + "skeys"); t.sidx = h->wi(p + "sidx");
+  t.uidx = h->wi(p + "uidx"); t.ukeys = h->wi(p + "ukeys"); t.slot = h->wi(p + "slot");
+  int* nu = h->wi("sp.nuniq");
+  double* ns = h->wd("sp_normsq");
+  if (w == "item") { t.width = kI; t.n_rows = h->cfg.n_items; t.w = h->buf.item_w; t.m = h->buf.item_m; t.v = h->buf.item_v;
+                     t.accum = h->wf("sp.item.accum"); t.nuniq = nu; t.normsq = ns; }
+  else if (w == "cate") { t.width = kC; t.n_rows = h->cfg.n_cates; t.w = h->buf.cate_w; t.m = h->buf.cate_m; t.v = h->buf.cate_v;
+                          t.accum = h->wf("sp.cate.accum"); t.nuniq = nu + 1; t.normsq = ns + 1; }
+  else if (w == "ulong") { t.width = PAMREC_USER_DIM; t.n_rows = h->cfg.n_users; t.w = h->buf.ulong_w; t.m = h->buf.ulong_m;
+                           t.v = h->buf.ulong_v; t.accum = nullptr; t.nuniq = nu + 2; t.normsq = ns + 2; }
+  else { t.width = PAMREC_USER_DIM; t.n_rows = h->cfg.n_users; t.w = h->buf.ushort_w; t.m = h->buf.ushort_m;
+         t.v = h->buf.ushort_v; t.accum = nullptr; t.nuniq = nu + 2; t.normsq = ns + 3; }
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------
+// Row-sharded tables (PAMREC_TABLES_SHARDED): plan of this rank's lookups, exchange with the owners.
+static const char* const kShardName[3] = {"item", "cate", "user"};
+static const ShardDim& shard_dim(PamrecHandle h, int t) { return t == 0 ? h->L.sh_item : (t == 1 ? h->L.sh_cate : h->L.sh_user); }
+
+// requester side: the "sp.*" arrays describe this rank's own lookups; keys are sharded-table addresses
+static SparseTable req_table(PamrecHandle h, int t) {
+  SparseTable s;
+  memset(&s, 0, sizeof s);
+  const ShardDim& d = shard_dim(h, t);
+  std::string p = std::string("sp.") + kShardName[t] + ".";
+  s.keys = h->wi(p + "keys"); s.idx = h->wi(p + "idx"); s.skeys = h->wi(p + "skeys"); s.sidx = h->wi(p + "sidx");
+  s.uidx = h->wi(p + "uidx"); s.ukeys = h->wi(p + "ukeys");
+  s.width = d.width; s.n_rows = d.rps * h->cfg.world_size;
+  s.accum = d.width ? h->wf(p + "accum") : nullptr;
+  s.nuniq = h->wi("sp.nuniq") + t;
+  s.normsq = h->wd("sp_normsq") + t;
+  return s;
+}
+// owner side: the "so.*" arrays describe the rows other ranks asked this rank for, bound to the local shard
+static SparseTable own_table(PamrecHandle h, int t, bool user_short = false) {
+  SparseTable s;
+  memset(&s, 0, sizeof s);
+  const ShardDim& d = shard_dim(h, t);
+  std::string q = std::string("so.") + kShardName[t] + ".";
+  s.keys = h->wi(q + "keys"); s.idx = h->wi(q + "idx"); s.skeys = h->wi(q + "skeys"); s.sidx = h->wi(q + "sidx");
+  s.uidx = h->wi(q + "uidx"); s.ukeys = h->wi(q + "ukeys");
+  s.slot = h->wi(std::string("sp.") + kShardName[t] + ".slot");
+  s.n_rows = d.rps;
+  s.nuniq = h->wi("sp.nuniq") + 4 + t;
+  double* ns = h->wd("sp_normsq");
+  if (t == 0) { s.width = kI; s.w = h->buf.item_w; s.m = h->buf.item_m; s.v = h->buf.item_v; s.accum = h->wf(q + "accum"); s.normsq = ns; }
+  else if (t == 1) { s.width = kC; s.w = h->buf.cate_w; s.m = h->buf.cate_m; s.v = h->buf.cate_v; s.accum = h->wf(q + "accum"); s.normsq = ns + 1; }
+  else if (!user_short) { s.width = PAMREC_USER_DIM; s.w = h->buf.ulong_w; s.m = h->buf.ulong_m; s.v = h->buf.ulong_v; s.normsq = ns + 2; }
+  else { s.width = PAMREC_USER_DIM; s.w = h->buf.ushort_w; s.m = h->buf.ushort_m; s.v = h->buf.ushort_v; s.normsq = ns + 3; }
+  return s;
+}
+
+// Forward half of the exchange: unique ids of the batch -> owners; owners' rows -> "sh.<table>.rows", one row per
+// unique id, in the order of the plan's unique list ("sh.<table>.inv" maps every lookup position to its row).
+// ONE host synchronisation: the per-peer counts must reach the host before the variable all-to-alls can be posted.
+static int shard_exchange_fwd(PamrecHandle h, const PamrecBatch* b, bool training, cudaStream_t st) {
+  const int W = h->cfg.world_size, B = b->batch, T = h->cfg.max_seq_len;
+  const int64_t N = (int64_t)B * T;
+  void* tmp = h->ws<char>("cub_temp");
+  const size_t tmp_bytes = (size_t)h->L.ws[h->L.ws_index.at("cub_temp")].numel;
+  int* cs = h->wi("sh.counts_send");
+  int* cr = h->wi("sh.counts_recv");
+  cudaMemsetAsync(cs, 0, sizeof(int) * 4 * W, st);
+  const int nt = training ? 3 : 2;
+  h->xc_users = training;
+  for (int t = 0; t < nt; ++t) {
+    const ShardDim& d = shard_dim(h, t);
+    SparseTable req = req_table(h, t);
+    const int* hist = t == 0 ? b->item_history : (t == 1 ? b->item_cate_history : b->users);
+    const int* tgt = t == 0 ? b->items : (t == 1 ? b->cates : nullptr);
+    const int64_t n_hist = t < 2 ? N : B, n_tgt = t < 2 ? B : 0;
+    if (launch_sparse_plan(req, hist, tgt, n_hist, n_tgt, W, d.rps, d.rps * W, false, tmp, tmp_bytes, st))
+      return fail(h, "cub sort failed");
+    std::string p = std::string("sh.") + kShardName[t] + ".";
+    launch_shard_route(req, n_hist + n_tgt, W, d.rps, h->wi(p + "off"), cs, t, h->wi(p + "send_ids"), h->wi(p + "inv"), st);
+  }
+  {
+    PAMREC_PROF("xchg_counts", 1, st);
+    if (h->comm.all_to_all(cs, cr, 4, COMM_I32, st)) return fail(h, "nccl: %s", h->comm.err.c_str());
+    cudaMemcpyAsync(h->h_counts, cs, sizeof(int) * 4 * W, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(h->h_counts + 4 * W, cr, sizeof(int) * 4 * W, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return check_cuda(h, "exchange counts");
+  }
+  for (int t = 0; t < 3; ++t) {
+    Xchg& x = h->xc[t];
+    x.soff.assign(W, 0); x.scnt.assign(W, 0); x.roff.assign(W, 0); x.rcnt.assign(W, 0);
+    int64_t so = 0, ro = 0;
+    for (int p = 0; p < W; ++p) {
+      x.scnt[p] = t < nt ? h->h_counts[4 * p + t] : 0;
+      x.rcnt[p] = t < nt ? h->h_counts[4 * W + 4 * p + t] : 0;
+      x.soff[p] = so; so += x.scnt[p];
+      x.roff[p] = ro; ro += x.rcnt[p];
+    }
+    x.n_send = so; x.n_recv = ro;
+    if (ro > shard_dim(h, t).cap_recv) return fail(h, "exchange overflow on table %s: %lld rows", kShardName[t], (long long)ro);
+  }
+  {
+    PAMREC_PROF("xchg_ids", 1, st);
+    h->comm.group_start();
+    for (int t = 0; t < nt; ++t) {
+      const Xchg& x = h->xc[t];
+      std::string p = std::string("sh.") + kShardName[t] + ".";
+      if (h->comm.all_to_all_v(h->wi(p + "send_ids"), x.soff.data(), x.scnt.data(), h->wi(p + "recv_ids"), x.roff.data(),
+                               x.rcnt.data(), 1, COMM_I32, st)) return fail(h, "nccl: %s", h->comm.err.c_str());
+    }
+    if (h->comm.group_end()) return fail(h, "nccl: %s", h->comm.err.c_str());
+  }
+  launch_serve_rows(h->buf.item_w, h->wi("sh.item.recv_ids"), h->xc[0].n_recv, kI, h->wf("sh.item.xrows"), st);
+  launch_serve_rows(h->buf.cate_w, h->wi("sh.cate.recv_ids"), h->xc[1].n_recv, kC, h->wf("sh.cate.xrows"), st);
+  {
+    PAMREC_PROF("xchg_rows", 1, st);
+    h->comm.group_start();
+    for (int t = 0; t < 2; ++t) {
+      const Xchg& x = h->xc[t];
+      std::string p = std::string("sh.") + kShardName[t] + ".";
+      if (h->comm.all_to_all_v(h->wf(p + "xrows"), x.roff.data(), x.rcnt.data(), h->wf(p + "rows"), x.soff.data(),
+                               x.scnt.data(), shard_dim(h, t).width, COMM_F32, st)) return fail(h, "nccl: %s", h->comm.err.c_str());
+    }
+    if (h->comm.group_end()) return fail(h, "nccl: %s", h->comm.err.c_str());
+  }
+  return 0;
+}
+
+// x0 / tgt of this rank's batch, from whole local tables or through the exchange
+static int embed_forward(PamrecHandle h, const PamrecBatch* b, bool training, float* x0, cudaStream_t st) {
+  const int B = b->batch, T = h->cfg.max_seq_len;
+  if (!h->sharded()) {
+    launch_embed_fwd(b->item_history, b->item_cate_history, b->items, b->cates, h->buf.item_w, h->buf.cate_w, h->P(h->L.pos), x0,
+                     h->wf("tgt"), B, T, st);
+    return 0;
+  }
+  if (int rc = shard_exchange_fwd(h, b, training, st)) return rc;
+  const int64_t N = (int64_t)B * T;
+  const int* ii = h->wi("sh.item.inv");
+  const int* ci = h->wi("sh.cate.inv");
+  launch_embed_fwd(ii, ci, ii + N, ci + N, h->wf("sh.item.rows"), h->wf("sh.cate.rows"), h->P(h->L.pos), x0, h->wf("tgt"), B, T, st);
+  return 0;
+}
+
 int pamrec_gather_fwd(PamrecHandle h, const PamrecBatch* b, float* x0_out, void* stream) {
   if (int rc = check_batch(h, b, false)) return rc;
   ProfBind _pb(h);
   cudaStream_t st = (cudaStream_t)stream;
-  launch_embed_fwd(b->item_history, b->item_cate_history, b->items, b->cates, h->buf.item_w, h->buf.cate_w, h->P(h->L.pos),
-                   x0_out ? x0_out : h->wf("x0"), h->wf("tgt"), b->batch, h->cfg.max_seq_len, st);
+  if (int rc = embed_forward(h, b, false, x0_out ? x0_out : h->wf("x0"), st)) return rc;
   return check_cuda(h, "gather_fwd");
 }
 
@@ -197,11 +381,26 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
   const Layout& L = h->L;
   const int B = b->batch, T = h->cfg.max_seq_len, N = B * T;
   const int W = h->cfg.world_size;
-  const double cntN = (double)N * W, cntB = (double)B * W;
+  const int Bg = b->global_batch > 0 ? b->global_batch : B * W;
+  const double cntN = (double)Bg * T, cntB = (double)Bg;
   int64_t nl = 0;
+  int crc = 0;
+  // data parallel: batch-norm sums of the listed sets (plus, once, the listwise-group count) summed over ranks
+  auto sync_sums = [&](std::initializer_list<int> ids, bool with_scalars) {
+    if (!training || W == 1 || crc) return;
+    PAMREC_PROF("allreduce_bn_fwd", 1, st);
+    crc |= h->comm.group_start();
+    for (int id : ids) crc |= h->comm.all_reduce(h->bn[id].sums, 2 * (int64_t)h->bn[id].C, COMM_F64, st);
+    if (with_scalars) crc |= h->comm.all_reduce(h->wd("dp.scalars"), 8, COMM_F64, st);
+    crc |= h->comm.group_end();
+  };
   float* x0 = h->wf("x0");
-  launch_embed_fwd(b->item_history, b->item_cate_history, b->items, b->cates, h->buf.item_w, h->buf.cate_w, h->P(L.pos), x0,
-                   h->wf("tgt"), B, T, st); nl += 1;
+  if (int rc = embed_forward(h, b, training != 0, x0, st)) return rc;
+  nl += 1;
+  if (training && W > 1) {
+    cudaMemsetAsync(h->wd("dp.scalars"), 0, 8 * sizeof(double), st);
+    launch_count_valid_groups(b->plays, B, h->wd("dp.scalars"), st);
+  }
   int* ctl = h->wi("bucket_ctl");
   launch_bucket_plan(b->item_loop_times_history, N, h->wi("bucket"), h->wi("perm"), ctl, h->wi("tile_bucket"),
                      h->wi("tile_begin"), h->wi("tile_count"), st); nl += 3;
@@ -233,11 +432,13 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     DenseP p = dense_p(H, kD, N, 1, kD, 20, h->P(L.score.w0), 0, h->P(L.score.b0), 0, h->wf("z1"), 20);
     p.out_sums = training ? bn[BN_S0].sums : nullptr;
     launch_dense_fwd(p, st); nl += 1;
+    sync_sums({BN_S0}, true);
     fin(BN_S0, cntN);
     DenseP q = dense_p(h->wf("z1"), 20, N, 1, 20, 1, h->P(L.score.w1), 0, h->P(L.score.b1), 0, h->wf("z2"), 1);
     set_in_bn(q, bn[BN_S0]);
     q.out_sums = training ? bn[BN_S1].sums : nullptr;
     launch_dense_fwd(q, st); nl += 1;
+    sync_sums({BN_S1}, false);
     fin(BN_S1, cntN);
   }
   launch_pool_fwd(H, h->wf("z2"), bn[BN_S1], b->mask, h->wf("new_long"), B, T, st); nl += 1;
@@ -252,6 +453,7 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     g0.out_sums = training ? bn[BN_G0].sums : nullptr;
     launch_dense_fwd(g0, st);
     nl += 2;
+    sync_sums({BN_E0, BN_G0}, false);
     fin(BN_E0, cntB); fin(BN_G0, cntB);
     DenseP e1 = dense_p(h->wf("ze0"), 500, B, 5, 100, 64, h->P(L.expert.w1), 6400, h->P(L.expert.b1), 64, h->wf("ze1"), 320);
     for (int g = 0; g < 5; ++g) { e1.x_off[g] = g * 100; e1.z_off[g] = g * 64; }
@@ -264,6 +466,7 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     g1.out_sums = training ? bn[BN_G1].sums : nullptr;
     launch_dense_fwd(g1, st);
     nl += 2;
+    sync_sums({BN_E1, BN_G1}, false);
     fin(BN_E1, cntB); fin(BN_G1, cntB);
   }
   launch_combine_fwd(h->wf("ze1"), h->wf("zg1"), bn[BN_E1], bn[BN_G1], h->wf("tgt"), h->wf("u"), B, st); nl += 1;
@@ -274,12 +477,14 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     for (int g = 0; g < 3; ++g) t0.z_off[g] = g * 100;
     t0.out_sums = training ? bn[BN_T0].sums : nullptr;
     launch_dense_fwd(t0, st); nl += 1;
+    sync_sums({BN_T0}, false);
     fin(BN_T0, cntB);
     DenseP t1 = dense_p(h->wf("zt0"), 300, B, 3, 100, 64, h->P(L.tower.w1), 6400, h->P(L.tower.b1), 64, h->wf("zt1"), 192);
     for (int g = 0; g < 3; ++g) { t1.x_off[g] = g * 100; t1.z_off[g] = g * 64; }
     set_in_bn(t1, bn[BN_T0]);
     t1.out_sums = training ? bn[BN_T1].sums : nullptr;
     launch_dense_fwd(t1, st); nl += 1;
+    sync_sums({BN_T1}, false);
     fin(BN_T1, cntB);
     DenseP to = dense_p(h->wf("zt1"), 192, B, 3, 64, 1, h->P(L.tower.wout), 64, h->P(L.tower.bout), 1, h->wf("logits"), 3);
     for (int g = 0; g < 3; ++g) { to.x_off[g] = g * 64; to.z_off[g] = g; }
@@ -287,6 +492,7 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     launch_dense_fwd(to, st); nl += 1;
   }
   if (pred_out) { launch_sigmoid_col0(h->wf("logits"), pred_out, B, st); nl += 1; }
+  if (crc) return fail(h, "nccl: %s", h->comm.err.c_str());
   return check_cuda(h, "forward");
 }
 
@@ -318,21 +524,31 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   const Layout& L = h->L;
   const int B = b->batch, T = h->cfg.max_seq_len, N = B * T;
   const int W = h->cfg.world_size;
-  const double cntN = (double)N * W, cntB = (double)B * W;
-  const float gs = 1.0f / (float)W;
+  const int Bg = b->global_batch > 0 ? b->global_batch : B * W;
+  const double cntN = (double)Bg * T, cntB = (double)Bg;
+  const float gs = 1.0f / (float)W;    // BN parameter gradients are already global: the dense all-reduce sums W copies
   BnSet* bn = h->bn;
   int64_t nl = 0;
+  int crc = 0;
   const float* Pb = h->buf.dense_param;
   cudaMemsetAsync(h->buf.dense_grad, 0, (size_t)L.dense_numel * 4, st);
   cudaMemsetAsync(h->wd("loss_acc"), 0, 8 * sizeof(double), st);
   cudaMemsetAsync(h->wd("sp_normsq"), 0, 8 * sizeof(double), st);
-  launch_loss(h->wf("logits"), b->labels_satisfied, b->labels_play, b->plays, h->wf("d_logits"), h->wd("loss_acc"), B, B * W,
-              W > 1 ? -2 : -1, h->cfg.fuzhu_weight, h->cfg.order_weight, st); nl += 1;
-  auto bn_bwd = [&](int id, float* dA, const float* Z, int M, double cnt) {
-    launch_bn_bwd_stats(bn[id], dA, Z, M, st);
-    launch_bn_bwd_apply(bn[id], dA, Z, M, cnt, gs, st);
-    nl += 3;
+  launch_loss(h->wf("logits"), b->labels_satisfied, b->labels_play, b->plays, h->wf("d_logits"), h->wd("loss_acc"), B, Bg,
+              W > 1 ? h->wd("dp.scalars") : nullptr, h->cfg.fuzhu_weight, h->cfg.order_weight, st); nl += 1;
+  // batch-norm backward of one or two sets: column sums, (data parallel) sum over ranks, then the apply pass
+  struct BnJob { int id; float* dA; const float* Z; };
+  auto bn_bwd_n = [&](std::initializer_list<BnJob> jobs, int M, double cnt) {
+    for (const BnJob& j : jobs) launch_bn_bwd_stats(bn[j.id], j.dA, j.Z, M, st);
+    if (W > 1 && !crc) {
+      PAMREC_PROF("allreduce_bn_bwd", 1, st);
+      crc |= h->comm.group_start();
+      for (const BnJob& j : jobs) crc |= h->comm.all_reduce(bn[j.id].bsums, 2 * (int64_t)bn[j.id].C, COMM_F64, st);
+      crc |= h->comm.group_end();
+    }
+    for (const BnJob& j : jobs) { launch_bn_bwd_apply(bn[j.id], j.dA, j.Z, M, cnt, gs, st); nl += 3; }
   };
+  auto bn_bwd = [&](int id, float* dA, const float* Z, int M, double cnt) { bn_bwd_n({{id, dA, Z}}, M, cnt); };
   // ---- towers
   {
     DenseDwP w = dw_p(h->wf("zt1"), 192, B, 3, 64, 1, h->wf("d_logits"), 3, h->G(L.tower.wout), 64, h->G(L.tower.bout), 1);
@@ -368,8 +584,7 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
                      h->wf("d_tgt"), B, st); nl += 1;
   // ---- MMoE
   {
-    bn_bwd(BN_E1, h->wf("d_e1"), h->wf("ze1"), B, cntB);
-    bn_bwd(BN_G1, h->wf("d_g1"), h->wf("zg1"), B, cntB);
+    bn_bwd_n({{BN_E1, h->wf("d_e1"), h->wf("ze1")}, {BN_G1, h->wf("d_g1"), h->wf("zg1")}}, B, cntB);
     DenseDwP we = dw_p(h->wf("ze0"), 500, B, 5, 100, 64, h->wf("d_e1"), 320, h->G(L.expert.w1), 6400, h->G(L.expert.b1), 64);
     for (int g = 0; g < 5; ++g) { we.x_off[g] = g * 100; we.z_off[g] = g * 64; }
     set_in_bn_dw(we, bn[BN_E0]);
@@ -385,8 +600,7 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
     for (int g = 0; g < 2; ++g) dx_add(xg, g, g * 64, g * 5, L.gate.w1 + (int64_t)g * 320, 5);
     launch_dense_dx(xg, st);
     nl += 4;
-    bn_bwd(BN_E0, h->wf("d_e0"), h->wf("ze0"), B, cntB);
-    bn_bwd(BN_G0, h->wf("d_g0"), h->wf("zg0"), B, cntB);
+    bn_bwd_n({{BN_E0, h->wf("d_e0"), h->wf("ze0")}, {BN_G0, h->wf("d_g0"), h->wf("zg0")}}, B, cntB);
     DenseDwP we0 = dw_p(h->wf("new_long"), kD, B, 5, kD, 100, h->wf("d_e0"), 500, h->G(L.expert.w0), 4000, h->G(L.expert.b0), 100);
     for (int g = 0; g < 5; ++g) { we0.x_off[g] = 0; we0.z_off[g] = g * 100; }
     launch_dense_dw(we0, st);
@@ -443,30 +657,11 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   }
   // dX0 is in g_a
   launch_embed_bwd_reduce(g_a, h->wf("d_tgt"), h->wf("d_tgt_total"), h->G(L.pos), h->wd("sp_normsq") + 4, B, T, st); nl += 2;
+  if (crc) return fail(h, "nccl: %s", h->comm.err.c_str());
   return check_cuda(h, "backward");
 }
 
 // ------------------------------------------------------------------------------------------
-static SparseTable table_of(PamrecHandle h, const char* which) {
-  SparseTable t;
-  memset(&t, 0, sizeof t);
-  std::string w = which;
-  std::string p = (w == "item" || w == "cate") ? "sp." + w + "." : "sp.user.";
-  t.keys = h->wi(p + "keys"); t.idx = h->wi(p + "idx"); t.skeys = h->wi(p + "skeys"); t.sidx = h->wi(p + "sidx");
-  t.uidx = h->wi(p + "uidx"); t.ukeys = h->wi(p + "ukeys"); t.slot = h->wi(p + "slot");
-  int* nu = h->wi("sp.nuniq");
-  double* ns = h->wd("sp_normsq");
-  if (w == "item") { t.width = kI; t.n_rows = h->cfg.n_items; t.w = h->buf.item_w; t.m = h->buf.item_m; t.v = h->buf.item_v;
-                     t.accum = h->wf("sp.item.accum"); t.nuniq = nu; t.normsq = ns; }
-  else if (w == "cate") { t.width = kC; t.n_rows = h->cfg.n_cates; t.w = h->buf.cate_w; t.m = h->buf.cate_m; t.v = h->buf.cate_v;
-                          t.accum = h->wf("sp.cate.accum"); t.nuniq = nu + 1; t.normsq = ns + 1; }
-  else if (w == "ulong") { t.width = PAMREC_USER_DIM; t.n_rows = h->cfg.n_users; t.w = h->buf.ulong_w; t.m = h->buf.ulong_m;
-                           t.v = h->buf.ulong_v; t.accum = nullptr; t.nuniq = nu + 2; t.normsq = ns + 2; }
-  else { t.width = PAMREC_USER_DIM; t.n_rows = h->cfg.n_users; t.w = h->buf.ushort_w; t.m = h->buf.ushort_m;
-         t.v = h->buf.ushort_v; t.accum = nullptr; t.nuniq = nu + 2; t.normsq = ns + 3; }
-  return t;
-}
-
 int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, void* stream) {
   if (int rc = check_batch(h, b, true)) return rc;
   ProfBind _pb(h);
@@ -484,6 +679,56 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
   int64_t nl = 0;
   const float* dX0 = h->wf("g_a");
   const float* dT = h->wf("d_tgt_total");
+  if (h->sharded()) {
+    // ---- row-sharded tables: local pre-reduction, row gradients to their owners, owner-side merge + Adam
+    Comm& cm = h->comm;
+    int crc = 0;
+    for (int t = 0; t < 2; ++t) {
+      SparseTable req = req_table(h, t);
+      const int col = t == 0 ? 0 : kI;
+      launch_sparse_segreduce(req, N + B, N, dX0, kD, col, dT, kE, col, req.normsq, st);
+    }
+    {
+      PAMREC_PROF("xchg_grads", 1, st);
+      crc |= cm.group_start();
+      for (int t = 0; t < 2; ++t) {
+        const Xchg& x = h->xc[t];
+        std::string p = std::string("sh.") + kShardName[t] + ".";
+        crc |= cm.all_to_all_v(req_table(h, t).accum, x.soff.data(), x.scnt.data(), h->wf(p + "xrows"), x.roff.data(), x.rcnt.data(),
+                               shard_dim(h, t).width, COMM_F32, st);
+      }
+      crc |= cm.group_end();
+    }
+    if (!h->xc_users) return fail(h, "apply_gradients needs pamrec_forward(training=1) on the same batch");
+    for (int t = 0; t < 3; ++t) {
+      SparseTable own = own_table(h, t);
+      const int64_t nr = h->xc[t].n_recv;
+      std::string p = std::string("sh.") + kShardName[t] + ".";
+      if (launch_sparse_plan(own, h->wi(p + "recv_ids"), nullptr, nr, 0, 1, 0, own.n_rows, true, tmp, tmp_bytes, st))
+        return fail(h, "cub sort failed");
+      if (t < 2) launch_sparse_segreduce(own, nr, nr, h->wf(p + "xrows"), own.width, 0, nullptr, 0, 0, h->wd("sh.scratch"), st);
+      launch_sparse_l2norm(own, nr, c.embed_l2, reg, st);
+      if (t == 2) launch_sparse_l2norm(own_table(h, 2, true), nr, c.embed_l2, reg, st);
+    }
+    {
+      PAMREC_PROF("allreduce_grads", 1, st);
+      crc |= cm.group_start();
+      crc |= cm.all_reduce(h->buf.dense_grad, L.dense_numel, COMM_F32, st);
+      crc |= cm.all_reduce(h->wd("sp_normsq"), 8, COMM_F64, st);
+      crc |= cm.all_reduce(h->wd("loss_acc"), 4, COMM_F64, st);     // data, aux, order, embedding part of the L2 term
+      crc |= cm.group_end();
+    }
+    if (crc) return fail(h, "nccl: %s", cm.err.c_str());
+    for (int t = 0; t < 3; ++t) {
+      SparseTable own = own_table(h, t);
+      const int64_t nr = h->xc[t].n_recv;
+      launch_sparse_adam(own, nr, c.sparse_adam_mode, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm, c.is_clip_norm, st);
+      if (t == 2)
+        launch_sparse_adam(own_table(h, 2, true), nr, c.sparse_adam_mode, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon,
+                           c.max_grad_norm, c.is_clip_norm, st);
+      launch_slot_reset(own, nr, st);
+    }
+  } else {
   {
     SparseTable t = table_of(h, "item");
     if (launch_sparse_reduce(t, b->item_history, b->items, N, B, dX0, kD, 0, dT, kE, 0, tmp, tmp_bytes, st)) return fail(h, "cub sort failed");
@@ -510,6 +755,7 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
     launch_slot_reset(tl, B, st);
     nl += 8;
   }
+  }
   const int n_seg = (int)L.dense.size();
   launch_dense_norm(h->buf.dense_param, h->buf.dense_grad, h->wi("seg_tab"), n_seg, c.layer_l2, h->wd("seg_normsq"),
                     h->wd("sp_normsq") + 4, reg, st);
@@ -523,7 +769,6 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
 
 int pamrec_train_step(PamrecHandle h, const PamrecBatch* b, int64_t step, float* losses_out, void* stream) {
   if (!h) return -1;
-  if (h->cfg.world_size > 1) return fail(h, "world_size > 1: drive the step with pamrec_train_phase");
   const int64_t l0 = h->prof.launches;
   if (int rc = pamrec_forward(h, b, 1, nullptr, stream)) return rc;
   if (int rc = pamrec_backward(h, b, stream)) return rc;
@@ -534,10 +779,11 @@ int pamrec_train_step(PamrecHandle h, const PamrecBatch* b, int64_t step, float*
   return check_cuda(h, "train_step");
 }
 
-int pamrec_train_phase(PamrecHandle h, const PamrecBatch* b, int64_t step, int phase, float* losses_out, char sync_name[160],
-                       void* stream) {
-  (void)b; (void)step; (void)phase; (void)losses_out; (void)sync_name; (void)stream;
-  return fail(h, "pamrec_train_phase: not built yet");
+int pamrec_comm_all_reduce(PamrecHandle h, void* dptr, int64_t count, int dtype, void* stream) {
+  if (!h) return -1;
+  CommType t = dtype == PAMREC_F64 ? COMM_F64 : (dtype == PAMREC_I32 ? COMM_I32 : COMM_F32);
+  if (h->comm.all_reduce(dptr, count, t, (cudaStream_t)stream)) return fail(h, "nccl: %s", h->comm.err.c_str());
+  return 0;
 }
 
 int pamrec_bench_gather(PamrecHandle h, const int32_t* item_ids, const int32_t* cate_ids, const int32_t* tgt_items,

@@ -72,7 +72,7 @@ void launch_combine_bwd(const float* ZE1, const float* ZG1, const BnSet& e1, con
                         float* dG1, float* dTgt, int B, cudaStream_t st);
 // loss_acc (double[8]): [0] data [1] aux [2] order (all already weighted / averaged)
 void launch_loss(const float* logits, const float* y_sat, const float* y_play, const float* plays, float* d_logits,
-                 double* loss_acc, int B, int B_global, int n_valid_global_or_neg, float fuzhu_w, float order_w,
+                 double* loss_acc, int B, int B_global, const double* n_valid_global, float fuzhu_w, float order_w,
                  cudaStream_t st);
 void launch_sigmoid_col0(const float* logits, float* pred, int B, cudaStream_t st);
 
@@ -93,6 +93,12 @@ size_t sparse_temp_bytes(int64_t n_keys);
 int launch_sparse_reduce(const SparseTable& t, const int* hist_ids, const int* tgt_ids, int64_t n_hist, int64_t n_tgt,
                          const float* hist_grad, int hist_ld, int hist_col, const float* tgt_grad, int tgt_ld, int tgt_col,
                          void* cub_temp, size_t cub_bytes, cudaStream_t st);
+int launch_sparse_plan(const SparseTable& t, const int* hist_ids, const int* tgt_ids, int64_t n_hist, int64_t n_tgt,
+                       int world, int64_t rps, int64_t key_range, bool fill_slot, void* cub_temp, size_t cub_bytes,
+                       cudaStream_t st);
+void launch_sparse_segreduce(const SparseTable& t, int64_t n, int64_t n_hist, const float* hist_grad, int hist_ld, int hist_col,
+                             const float* tgt_grad, int tgt_ld, int tgt_col, double* normsq, cudaStream_t st);
+void launch_slot_reset(const SparseTable& t, int64_t n_keys, cudaStream_t st);
 // L2 rows of the unique ids: adds their squared norm to normsq and 0.5*l2*|w|^2 to reg_acc
 void launch_sparse_l2norm(const SparseTable& t, int64_t n_keys, float l2, double* reg_acc, cudaStream_t st);
 void launch_sparse_adam(const SparseTable& t, int64_t n_keys, int mode, float l2, float lr_t, float b1, float b2, float eps,
@@ -103,5 +109,11 @@ void launch_dense_adam(float* P, const float* G, float* M, float* V, const int* 
                        const double* seg_normsq, int64_t n, float layer_l2, float lr_t, float b1, float b2, float eps,
                        float clip, int is_clip, cudaStream_t st);
 void launch_finish_losses(const double* loss_acc, float* losses, cudaStream_t st);
+
+// ---- kernels_shard.cu (row-sharded tables)
+void launch_shard_route(const SparseTable& req, int64_t n, int world, int64_t rps, int* off, int* counts, int slot, int* send_ids,
+                        int* inv, cudaStream_t st);
+void launch_serve_rows(const float* shard, const int* ids, int64_t n, int width, float* out, cudaStream_t st);
+void launch_count_valid_groups(const float* plays, int B, double* out, cudaStream_t st);
 
 }  // namespace pamrec

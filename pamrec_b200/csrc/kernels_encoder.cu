@@ -100,6 +100,7 @@ void launch_bucket_plan(const float* lt, int n, int* bucket, int* perm, int* ctl
                         int* tile_count, cudaStream_t st) {
   PAMREC_PROF("bucket_plan", 3, st);
   cudaMemsetAsync(ctl, 0, 64 * sizeof(int), st);
+  if (n == 0) return;
   int g = (n + 255) / 256;
   k_bucket_hist<<<g, 256, 0, st>>>(lt, n, bucket, ctl);
   k_bucket_plan<<<1, 32, 0, st>>>(ctl, tile_bucket, tile_begin, tile_count);
@@ -360,6 +361,7 @@ static void attn_fwd_nj(const float* Q, const float* K, const float* V, const fl
 void launch_attn_fwd(const float* Q, const float* K, const float* V, const float* QIN, const int* mask, float* Y, int B,
                      int T, cudaStream_t st) {
   PAMREC_PROF("attn_fwd", 1, st);
+  if (B == 0) return;
   size_t smem = attn_fwd_smem(T);
   switch ((T + 31) / 32) {
     case 1: attn_fwd_nj<1>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
@@ -423,6 +425,7 @@ k_ffn_fwd(const float* __restrict__ Y, const float* __restrict__ W1, const float
 void launch_ffn_fwd(const float* Y, const float* W1, const float* b1, const float* W2, const float* b2,
                     const float* ln_beta, const float* ln_gamma, float* OUT, int n_tok, cudaStream_t st) {
   PAMREC_PROF("ffn_fwd", 1, st);
+  if (n_tok == 0) return;
   static bool once = false;
   if (!once) { cudaFuncSetAttribute(k_ffn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnFwdSmem); once = true; }
   k_ffn_fwd<<<(n_tok + kTokTile - 1) / kTokTile, kTokTile, kFfnFwdSmem, st>>>(Y, W1, b1, W2, b2, ln_beta, ln_gamma, OUT, n_tok);
@@ -537,6 +540,7 @@ void launch_ffn_bwd(const float* Y, const float* dOUT, const float* W1, const fl
                     const float* ln_beta, const float* ln_gamma, float* dY, float* dW1, float* db1, float* dW2,
                     float* db2, float* dbeta, float* dgamma, int n_tok, cudaStream_t st) {
   PAMREC_PROF("ffn_bwd", 1, st);
+  if (n_tok == 0) return;
   static bool once = false;
   if (!once) { cudaFuncSetAttribute(k_ffn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnBwdSmem); once = true; }
   k_ffn_bwd<<<(n_tok + kTokTile - 1) / kTokTile, kTokTile, kFfnBwdSmem, st>>>(Y, dOUT, W1, b1, W2, ln_beta, ln_gamma, dY, dW1,
@@ -690,6 +694,7 @@ static void attn_bwd_nj(const float* Q, const float* K, const float* V, const fl
 void launch_attn_bwd(const float* Q, const float* K, const float* V, const float* dY, const int* mask, float* dQ,
                      float* dK, float* dV, int B, int T, cudaStream_t st) {
   PAMREC_PROF("attn_bwd", 1, st);
+  if (B == 0) return;
   size_t smem = attn_bwd_smem(T);
   switch ((T + 31) / 32) {
     case 1: attn_bwd_nj<1>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;

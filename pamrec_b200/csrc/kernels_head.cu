@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kRows) k_dense_fwd(const DenseP p) {
 }
 
 void launch_dense_fwd(const DenseP& p, cudaStream_t st) { PAMREC_PROF("dense_fwd", 1, st);
+  if (p.M == 0) return;
   static int smem_set = 0;
   int smem = (p.K * (kXs + kNc) + 4) * 4;
   if (smem > smem_set) { cudaFuncSetAttribute(k_dense_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set = smem; }
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(kRows) k_dense_dx(const DenseDxP p) {
 }
 
 void launch_dense_dx(const DenseDxP& p, cudaStream_t st) { PAMREC_PROF("dense_dx", 1, st);
+  if (p.M == 0) return;
   static int smem_set = 0;
   int maxN = 1;
   for (int s = 0; s < p.n_slices; ++s)
@@ -203,6 +205,7 @@ __global__ void __launch_bounds__(kRows) k_dense_dw(const DenseDwP p) {
 }
 
 void launch_dense_dw(const DenseDwP& p, cudaStream_t st) { PAMREC_PROF("dense_dw", 1, st);
+  if (p.M == 0) return;
   static int smem_set = 0;
   int Np = (p.N + kNc - 1) / kNc * kNc;
   int smem = kRows * (p.K + 1 + Np) * 4;
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats(BnSet s, const float* __re
   }
 }
 void launch_bn_bwd_stats(const BnSet& s, const float* dA, const float* Z, int M, cudaStream_t st) { PAMREC_PROF("bn_bwd_stats", 1, st);
+  if (M == 0) return;
   int cb = s.C < 32 ? s.C : 32;
   int rpb = (256 / cb) * kBnRowsPerThread;
   dim3 grid((s.C + cb - 1) / cb, (M + rpb - 1) / rpb);
@@ -297,7 +301,7 @@ __global__ void k_bn_param_grad(BnSet s, float scale) {
 }
 void launch_bn_bwd_apply(const BnSet& s, float* dA, const float* Z, int M, double count, float grad_scale, cudaStream_t st) { PAMREC_PROF("bn_bwd_apply", 2, st);
   int64_t total = (int64_t)M * s.C;
-  k_bn_bwd_apply<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s, dA, Z, total, count);
+  if (total > 0) k_bn_bwd_apply<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s, dA, Z, total, count);
   k_bn_param_grad<<<(s.C + 127) / 128, 128, 0, st>>>(s, grad_scale);
 }
 
@@ -359,6 +363,7 @@ __global__ void __launch_bounds__(128) k_pool_fwd(const float* __restrict__ H, c
 }
 void launch_pool_fwd(const float* H, const float* Z2, const BnSet& s1, const int* mask, float* new_long, int B, int T,
                      cudaStream_t st) { PAMREC_PROF("pool_fwd", 1, st);
+  if (B == 0) return;
   k_pool_fwd<<<(B + 3) / 4, 128, 0, st>>>(H, Z2, s1, mask, new_long, B, T);
 }
 
@@ -409,6 +414,7 @@ __global__ void __launch_bounds__(128) k_pool_bwd(const float* __restrict__ H, c
 }
 void launch_pool_bwd(const float* H, const float* Z2, const BnSet& s1, const int* mask, const float* dNL, float* dA2,
                      float* dH, int B, int T, cudaStream_t st) { PAMREC_PROF("pool_bwd", 1, st);
+  if (B == 0) return;
   k_pool_bwd<<<(B + 3) / 4, 128, 0, st>>>(H, Z2, s1, mask, dNL, dA2, dH, B, T);
 }
 
@@ -434,6 +440,7 @@ __global__ void __launch_bounds__(64) k_combine_fwd(const float* __restrict__ ZE
 }
 void launch_combine_fwd(const float* ZE1, const float* ZG1, const BnSet& e1, const BnSet& g1, const float* tgt, float* U,
                         int B, cudaStream_t st) { PAMREC_PROF("combine_fwd", 1, st);
+  if (B == 0) return;
   k_combine_fwd<<<B, 64, 0, st>>>(ZE1, ZG1, e1, g1, tgt, U, B);
 }
 
@@ -460,6 +467,7 @@ __global__ void __launch_bounds__(64) k_combine_bwd(const float* __restrict__ ZE
 }
 void launch_combine_bwd(const float* ZE1, const float* ZG1, const BnSet& e1, const BnSet& g1, const float* dU, float* dE1,
                         float* dG1, float* dTgt, int B, cudaStream_t st) { PAMREC_PROF("combine_bwd", 1, st);
+  if (B == 0) return;
   k_combine_bwd<<<B, 64, 0, st>>>(ZE1, ZG1, e1, g1, dU, dE1, dG1, dTgt, B);
 }
 
@@ -489,7 +497,7 @@ __device__ double block_sum_d(double v, double* sh) {
 __global__ void __launch_bounds__(1024)
 k_loss(const float* __restrict__ logits, const float* __restrict__ y_sat, const float* __restrict__ y_play,
        const float* __restrict__ plays, float* __restrict__ d_logits, double* __restrict__ loss_acc, int B, int B_global,
-       int n_valid_in, float fuzhu_w, float order_w) {
+       const double* __restrict__ n_valid_global, float fuzhu_w, float order_w) {
   __shared__ double sh[32];
   const int tid = threadIdx.x;
   const int G = B / PAMREC_GROUP;
@@ -501,7 +509,7 @@ k_loss(const float* __restrict__ logits, const float* __restrict__ y_sat, const 
     cnt += (s > 0.f) ? 1.0 : 0.0;
   }
   double nval_local = block_sum_d(cnt, sh);
-  const double nval = n_valid_in >= 0 ? (double)n_valid_in : nval_local;
+  const double nval = n_valid_global ? *n_valid_global : nval_local;   // data parallel: count over all ranks
   const float inv_b = 1.0f / (float)B_global;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
   for (int b = tid; b < B; b += blockDim.x) {
@@ -583,8 +591,9 @@ k_loss(const float* __restrict__ logits, const float* __restrict__ y_sat, const 
   }
 }
 void launch_loss(const float* logits, const float* y_sat, const float* y_play, const float* plays, float* d_logits,
-                 double* loss_acc, int B, int B_global, int n_valid, float fuzhu_w, float order_w, cudaStream_t st) { PAMREC_PROF("loss", 1, st);
-  k_loss<<<1, 1024, 0, st>>>(logits, y_sat, y_play, plays, d_logits, loss_acc, B, B_global, n_valid, fuzhu_w, order_w);
+                 double* loss_acc, int B, int B_global, const double* n_valid_global, float fuzhu_w, float order_w,
+                 cudaStream_t st) { PAMREC_PROF("loss", 1, st);
+  k_loss<<<1, 1024, 0, st>>>(logits, y_sat, y_play, plays, d_logits, loss_acc, B, B_global, n_valid_global, fuzhu_w, order_w);
 }
 
 __global__ void k_sigmoid_col0(const float* __restrict__ logits, float* __restrict__ pred, int B) {
@@ -592,6 +601,7 @@ __global__ void k_sigmoid_col0(const float* __restrict__ logits, float* __restri
   if (b < B) pred[b] = sigmoidf_(logits[3 * b]);
 }
 void launch_sigmoid_col0(const float* logits, float* pred, int B, cudaStream_t st) { PAMREC_PROF("sigmoid", 1, st);
+  if (B == 0) return;
   k_sigmoid_col0<<<(B + 255) / 256, 256, 0, st>>>(logits, pred, B);
 }
 

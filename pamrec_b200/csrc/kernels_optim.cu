@@ -45,6 +45,7 @@ __global__ void k_pos_grad(const float* __restrict__ dX0, float* __restrict__ dP
 }
 void launch_embed_bwd_reduce(const float* dX0, const float* dTgtHead, float* dTgtTotal, float* dPos, double* pos_normsq,
                              int B, int T, cudaStream_t st) { PAMREC_PROF("embed_bwd_reduce", 2, st);
+  if (B == 0) return;
   k_dtgt_total<<<B, 128, 0, st>>>(dX0, dTgtHead, dTgtTotal, pos_normsq, T);
   dim3 grid((T * kD + 127) / 128, (B + kPosRows - 1) / kPosRows);
   k_pos_grad<<<grid, 128, 0, st>>>(dX0, dPos, B, T);
@@ -59,11 +60,13 @@ size_t sparse_temp_bytes(int64_t n_keys) {
   return a > b ? a : b;
 }
 
+// world > 1: the key is the row's address in the sharded table, owner * rows_per_shard + local row (kernels_shard.cu)
 __global__ void k_build_keys(const int* __restrict__ hist_ids, const int* __restrict__ tgt_ids, int64_t n_hist,
-                             int64_t n_tgt, int* __restrict__ keys, int* __restrict__ idx) {
+                             int64_t n_tgt, int world, int64_t rps, int* __restrict__ keys, int* __restrict__ idx) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_hist + n_tgt) return;
-  keys[p] = p < n_hist ? hist_ids[p] : tgt_ids[p - n_hist];
+  int id = p < n_hist ? hist_ids[p] : tgt_ids[p - n_hist];
+  keys[p] = world > 1 ? (int)((int64_t)(id % world) * rps + id / world) : id;
   idx[p] = (int)p;
 }
 __global__ void k_head_flags(const int* __restrict__ skeys, int64_t n, int* __restrict__ flags) {
@@ -78,7 +81,7 @@ __global__ void k_unique_fill(const int* __restrict__ skeys, const int* __restri
   if (p == 0 || skeys[p] != skeys[p - 1]) {
     int u = uidx[p] - 1;
     ukeys[u] = skeys[p];
-    slot[skeys[p]] = u;
+    if (slot != nullptr) slot[skeys[p]] = u;
   }
   if (p == n - 1) *nuniq = uidx[p];
 }
@@ -132,32 +135,48 @@ k_seg_reduce(const int* __restrict__ skeys, const int* __restrict__ sidx, const 
   if (lane == 0 && s != 0.0) atomicAdd(normsq, s);
 }
 
-int launch_sparse_reduce(const SparseTable& t, const int* hist_ids, const int* tgt_ids, int64_t n_hist, int64_t n_tgt,
-                         const float* hist_grad, int hist_ld, int hist_col, const float* tgt_grad, int tgt_ld, int tgt_col,
-                         void* cub_temp, size_t cub_bytes, cudaStream_t st) { PAMREC_PROF("sparse_sort_reduce", 4, st);
+// keys (history ids then target ids) -> sorted -> unique list (ukeys, nuniq), rank of every position (uidx) and,
+// when the table has a slot map, row -> unique index.  key_range = number of distinct key values.
+int launch_sparse_plan(const SparseTable& t, const int* hist_ids, const int* tgt_ids, int64_t n_hist, int64_t n_tgt,
+                       int world, int64_t rps, int64_t key_range, bool fill_slot, void* cub_temp, size_t cub_bytes,
+                       cudaStream_t st) { PAMREC_PROF("sparse_plan", 3, st);
   const int64_t n = n_hist + n_tgt;
-  if (n == 0) return 0;
+  if (n == 0) { cudaMemsetAsync(t.nuniq, 0, sizeof(int), st); return 0; }
   const unsigned g256 = (unsigned)((n + 255) / 256);
-  k_build_keys<<<g256, 256, 0, st>>>(hist_ids, tgt_ids, n_hist, n_tgt, t.keys, t.idx);
+  k_build_keys<<<g256, 256, 0, st>>>(hist_ids, tgt_ids, n_hist, n_tgt, world, rps, t.keys, t.idx);
   int bits = 1;
-  while (bits < 31 && ((int64_t)1 << bits) < t.n_rows) ++bits;
+  while (bits < 31 && ((int64_t)1 << bits) < key_range) ++bits;
   size_t bytes = cub_bytes;
   if (cub::DeviceRadixSort::SortPairs(cub_temp, bytes, t.keys, t.skeys, t.idx, t.sidx, (int)n, 0, bits, st) != cudaSuccess)
     return -1;
   k_head_flags<<<g256, 256, 0, st>>>(t.skeys, n, t.keys);          // keys buffer reused as head flags
   bytes = cub_bytes;
   if (cub::DeviceScan::InclusiveSum(cub_temp, bytes, t.keys, t.uidx, (int)n, st) != cudaSuccess) return -1;
-  k_unique_fill<<<g256, 256, 0, st>>>(t.skeys, t.uidx, n, t.ukeys, t.slot, t.nuniq);
-  if (t.accum != nullptr && hist_grad != nullptr) {
-    cudaMemsetAsync(t.accum, 0, (size_t)n * t.width * sizeof(float), st);
-    const unsigned gw = (unsigned)((n + 255) / 256);               // 8 warps x 32 positions per CTA
-    if (t.width == 16)
-      k_seg_reduce<16><<<gw, 256, 0, st>>>(t.skeys, t.sidx, t.uidx, n, n_hist, hist_grad, hist_ld, hist_col, tgt_grad, tgt_ld,
-                                           tgt_col, t.accum, t.normsq);
-    else
-      k_seg_reduce<4><<<gw, 256, 0, st>>>(t.skeys, t.sidx, t.uidx, n, n_hist, hist_grad, hist_ld, hist_col, tgt_grad, tgt_ld,
-                                          tgt_col, t.accum, t.normsq);
-  }
+  k_unique_fill<<<g256, 256, 0, st>>>(t.skeys, t.uidx, n, t.ukeys, fill_slot ? t.slot : nullptr, t.nuniq);
+  return 0;
+}
+
+// duplicate rows summed into accum[unique index]; normsq += sum of squares of every (un-deduplicated) row
+void launch_sparse_segreduce(const SparseTable& t, int64_t n, int64_t n_hist, const float* hist_grad, int hist_ld, int hist_col,
+                             const float* tgt_grad, int tgt_ld, int tgt_col, double* normsq, cudaStream_t st) {
+  PAMREC_PROF("sparse_segreduce", 1, st);
+  if (n == 0) return;
+  cudaMemsetAsync(t.accum, 0, (size_t)n * t.width * sizeof(float), st);
+  const unsigned gw = (unsigned)((n + 255) / 256);               // 8 warps x 32 positions per CTA
+  if (t.width == 16)
+    k_seg_reduce<16><<<gw, 256, 0, st>>>(t.skeys, t.sidx, t.uidx, n, n_hist, hist_grad, hist_ld, hist_col, tgt_grad, tgt_ld,
+                                         tgt_col, t.accum, normsq);
+  else
+    k_seg_reduce<4><<<gw, 256, 0, st>>>(t.skeys, t.sidx, t.uidx, n, n_hist, hist_grad, hist_ld, hist_col, tgt_grad, tgt_ld,
+                                        tgt_col, t.accum, normsq);
+}
+
+int launch_sparse_reduce(const SparseTable& t, const int* hist_ids, const int* tgt_ids, int64_t n_hist, int64_t n_tgt,
+                         const float* hist_grad, int hist_ld, int hist_col, const float* tgt_grad, int tgt_ld, int tgt_col,
+                         void* cub_temp, size_t cub_bytes, cudaStream_t st) {
+  if (launch_sparse_plan(t, hist_ids, tgt_ids, n_hist, n_tgt, 1, 0, t.n_rows, true, cub_temp, cub_bytes, st)) return -1;
+  if (t.accum != nullptr && hist_grad != nullptr)
+    launch_sparse_segreduce(t, n_hist + n_tgt, n_hist, hist_grad, hist_ld, hist_col, tgt_grad, tgt_ld, tgt_col, t.normsq, st);
   return 0;
 }
 
@@ -190,6 +209,7 @@ k_sparse_l2norm(const int* __restrict__ ukeys, const int* __restrict__ nuniq, co
 }
 void launch_sparse_l2norm(const SparseTable& t, int64_t n_keys, float l2, double* reg_acc, cudaStream_t st) { PAMREC_PROF("sparse_l2norm", 1, st);
   int64_t total = n_keys * (t.width / 4);
+  if (total == 0) return;
   unsigned g = (unsigned)((total + 255) / 256);
   if (t.width == 16) k_sparse_l2norm<16><<<g, 256, 0, st>>>(t.ukeys, t.nuniq, t.w, l2, t.normsq, reg_acc);
   else if (t.width == 4) k_sparse_l2norm<4><<<g, 256, 0, st>>>(t.ukeys, t.nuniq, t.w, l2, t.normsq, reg_acc);
@@ -271,6 +291,7 @@ static void sparse_adam_w(const SparseTable& t, int64_t n_keys, int mode, float 
     k_table_adam_dense<W><<<g, 256, 0, st>>>(t.w, t.m, t.v, t.slot, t.accum, t.normsq, t.n_rows, l2, lr, b1, b2, eps, clip, is_clip);
   } else {
     int64_t total = n_keys * (W / 4);
+    if (total == 0) return;
     k_table_adam_lazy<W><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t.w, t.m, t.v, t.ukeys, t.nuniq, t.accum, t.normsq, l2,
                                                                         lr, b1, b2, eps, clip, is_clip);
   }
@@ -282,6 +303,7 @@ void launch_sparse_adam(const SparseTable& t, int64_t n_keys, int mode, float l2
   else sparse_adam_w<20>(t, n_keys, mode, l2, lr_t, b1, b2, eps, clip, is_clip, st);
 }
 void launch_slot_reset(const SparseTable& t, int64_t n_keys, cudaStream_t st) { PAMREC_PROF("slot_reset", 1, st);
+  if (n_keys == 0) return;
   k_slot_reset<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(t.ukeys, t.nuniq, t.slot);
 }
 

@@ -27,8 +27,15 @@ struct BnOff { int C; int64_t gamma, beta, mm, mv; };
 
 enum BnId { BN_S0 = 0, BN_S1, BN_E0, BN_G0, BN_E1, BN_G1, BN_T0, BN_T1, BN_COUNT };
 
+// one row-sharded table as seen by the exchange (PAMREC_TABLES_SHARDED)
+struct ShardDim { int64_t vocab = 0, rps = 0, nk = 0, cap_recv = 0; int width = 0; };
+
 struct Layout {
   int n_users = 0, n_items = 0, n_cates = 0, T = 0, Bcap = 0;
+  int world = 1, table_mode = 0;
+  ShardDim sh_item, sh_cate, sh_user;
+  int64_t cub_keys = 0;                         // largest key count handed to cub
+  int64_t rows_of(int64_t vocab) const { return table_mode == PAMREC_TABLES_SHARDED ? (vocab + world - 1) / world : vocab; }
   std::vector<TensorDesc> dense, bn, ws;
   int64_t dense_numel = 0, bn_numel = 0;
   size_t ws_bytes = 0;
@@ -110,6 +117,7 @@ struct Layout {
 
   void build(const PamrecConfig& c) {
     n_users = c.n_users; n_items = c.n_items; n_cates = c.n_cates; T = c.max_seq_len; Bcap = c.max_batch;
+    world = c.world_size < 1 ? 1 : c.world_size; table_mode = c.table_mode;
     const int L2 = PAMREC_SEG_L2;
     // ---- dense pool: encoder first so that every float4-loaded matrix starts on a 16-byte boundary
     pos = add_dense("sequential/embedding/position_embedding", {T, kD}, PAMREC_SEG_POS);
@@ -206,7 +214,8 @@ struct Layout {
     add_ws("seg_tab", PAMREC_I32, {(int64_t)dense.size(), 4});   // off, numel, flags, -
     add_ws("seg_normsq", PAMREC_F64, {(int64_t)dense.size()});
     add_ws("sp_normsq", PAMREC_F64, {8});          // 0 item 1 cate 2 ulong 3 ushort 4 pos
-    // sparse path: keys = history ids then target ids
+    // sparse path: keys = history ids then target ids.  "sp.*" is the plan of THIS rank's lookups; the slot map
+    // (table row -> unique index) always covers the rows this rank owns.
     const int64_t NK = N + B;
     for (const char* t : {"item", "cate"}) {
       std::string p = std::string("sp.") + t + ".";
@@ -217,7 +226,7 @@ struct Layout {
       add_ws(p + "uidx", PAMREC_I32, {NK});
       add_ws(p + "ukeys", PAMREC_I32, {NK});
       add_ws(p + "accum", PAMREC_F32, {NK, t[0] == 'i' ? kI : kC});
-      add_ws(p + "slot", PAMREC_I32, {t[0] == 'i' ? (int64_t)n_items : (int64_t)n_cates});
+      add_ws(p + "slot", PAMREC_I32, {rows_of(t[0] == 'i' ? n_items : n_cates)});
     }
     add_ws("sp.user.keys", PAMREC_I32, {B});
     add_ws("sp.user.idx", PAMREC_I32, {B});
@@ -225,9 +234,41 @@ struct Layout {
     add_ws("sp.user.sidx", PAMREC_I32, {B});
     add_ws("sp.user.uidx", PAMREC_I32, {B});
     add_ws("sp.user.ukeys", PAMREC_I32, {B});
-    add_ws("sp.user.slot", PAMREC_I32, {(int64_t)n_users});
-    add_ws("sp.nuniq", PAMREC_I32, {8});           // 0 item 1 cate 2 user
-    add_ws("cub_temp", PAMREC_U8, {(int64_t)(16u << 20) + 16 * NK});
+    add_ws("sp.user.slot", PAMREC_I32, {rows_of(n_users)});
+    add_ws("sp.nuniq", PAMREC_I32, {8});           // 0 item 1 cate 2 user ; 4 5 6 = owner-side plans (sharded tables)
+    add_ws("dp.scalars", PAMREC_F64, {8});         // [0] listwise groups with a non-zero label sum over all ranks
+    cub_keys = NK;
+    if (table_mode == PAMREC_TABLES_SHARDED) {
+      // exchange buffers ("sh.*") and the owner-side plan of the rows other ranks asked this rank for ("so.*")
+      auto dim = [&](int64_t vocab, int64_t nk, int width) {
+        ShardDim d;
+        d.vocab = vocab; d.rps = rows_of(vocab); d.nk = nk; d.width = width;
+        d.cap_recv = (int64_t)world * (nk < d.rps ? nk : d.rps);   // a rank can ask for at most min(nk, rps) distinct rows
+        return d;
+      };
+      sh_item = dim(n_items, NK, kI); sh_cate = dim(n_cates, NK, kC); sh_user = dim(n_users, B, 0);
+      const ShardDim* dims[3] = {&sh_item, &sh_cate, &sh_user};
+      const char* names[3] = {"item", "cate", "user"};
+      for (int i = 0; i < 3; ++i) {
+        const ShardDim& d = *dims[i];
+        std::string p = std::string("sh.") + names[i] + ".", q = std::string("so.") + names[i] + ".";
+        add_ws(p + "inv", PAMREC_I32, {d.nk});
+        add_ws(p + "send_ids", PAMREC_I32, {d.nk});
+        add_ws(p + "off", PAMREC_I32, {128});
+        add_ws(p + "recv_ids", PAMREC_I32, {d.cap_recv});
+        if (d.width) {
+          add_ws(p + "rows", PAMREC_F32, {d.nk, d.width});          // rows received from their owners (forward)
+          add_ws(p + "xrows", PAMREC_F32, {d.cap_recv, d.width});   // owner: rows served (forward) / row gradients received
+          add_ws(q + "accum", PAMREC_F32, {d.cap_recv, d.width});
+        }
+        for (const char* n : {"keys", "idx", "skeys", "sidx", "uidx", "ukeys"}) add_ws(q + n, PAMREC_I32, {d.cap_recv});
+        if (d.cap_recv > cub_keys) cub_keys = d.cap_recv;
+      }
+      add_ws("sh.counts_send", PAMREC_I32, {(int64_t)world * 4});
+      add_ws("sh.counts_recv", PAMREC_I32, {(int64_t)world * 4});
+      add_ws("sh.scratch", PAMREC_F64, {8});
+    }
+    add_ws("cub_temp", PAMREC_U8, {(int64_t)(16u << 20) + 16 * cub_keys});
   }
 };
 

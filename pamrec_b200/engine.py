@@ -6,6 +6,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from . import dist as D
 
 EMB = "sequential/embedding/"
 TABLES = {
@@ -41,10 +42,11 @@ class PamrecError(RuntimeError):
 class DeviceBatch:
     """Device copies of one feed dict plus the PamrecBatch struct pointing at them."""
 
-    def __init__(self, tensors, batch):
+    def __init__(self, tensors, batch, global_batch=0):
         self.tensors = tensors
         self.batch = batch
-        self.struct = L.PamrecBatch(batch=batch, **{k: C.c_void_p(v.data_ptr()) for k, v in tensors.items()})
+        self.struct = L.PamrecBatch(batch=batch, global_batch=int(global_batch),
+                                    **{k: C.c_void_p(v.data_ptr()) for k, v in tensors.items()})
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in self.tensors.values())
@@ -52,8 +54,16 @@ class DeviceBatch:
 
 class Engine:
     def __init__(self, n_users, n_items, n_cates, max_seq_len, max_batch, hp=None, sparse_adam="dense_exact",
-                 world_size=1, rank=0):
+                 world_size=1, rank=0, tables=None):
+        """tables: "local" (whole tables on this GPU) or "sharded" (row r on rank r % world_size, rows and row gradients
+        exchanged by all-to-all; required for world_size > 1, also runs on one GPU)."""
         self.lib = L.load()
+        self.world, self.rank = int(world_size), int(rank)
+        if tables is None:
+            tables = "sharded" if self.world > 1 else "local"
+        if self.world > 1 and tables != "sharded":
+            raise PamrecError("world_size > 1 needs tables='sharded'")
+        self.tables = tables
         h = dict(DEFAULT_HP)
         if hp:
             h.update(hp)
@@ -65,11 +75,13 @@ class Engine:
             learning_rate=h["learning_rate"], beta1=h["beta1"], beta2=h["beta2"], epsilon=h["epsilon"],
             embed_l2=h["embed_l2"], layer_l2=h["layer_l2"], max_grad_norm=h["max_grad_norm"],
             is_clip_norm=int(h["is_clip_norm"]), fuzhu_weight=h["fuzhu_weight"],
-            order_weight=h["discrepancy_loss_weight"], sparse_adam_mode=mode, world_size=world_size, rank=rank)
+            order_weight=h["discrepancy_loss_weight"], sparse_adam_mode=mode, world_size=world_size, rank=rank,
+            table_mode=L.TABLES_SHARDED if tables == "sharded" else L.TABLES_LOCAL)
         self.handle = C.c_void_p()
         rc = self.lib.pamrec_create(C.byref(self.cfg), C.byref(self.handle))
         if rc != 0:
-            raise PamrecError(f"pamrec_create failed ({rc}): check vocabulary sizes, max_seq_len <= 256, max_batch")
+            raise PamrecError(f"pamrec_create failed ({rc}): check vocabulary sizes, max_seq_len <= 256, max_batch, "
+                              "world_size <= 64, rank, table mode")
         self.dense_numel = self.lib.pamrec_dense_numel(self.handle)
         self.bn_numel = self.lib.pamrec_bn_numel(self.handle)
         self.workspace_bytes = self.lib.pamrec_workspace_bytes(self.handle)
@@ -114,7 +126,7 @@ class Engine:
         self.pool["bn_moving"] = z(self.bn_numel)
         for pre, rows, w in (("item", ni, 16), ("cate", nc, 4), ("ulong", nu, 20), ("ushort", nu, 20)):
             for s in ("w", "m", "v"):
-                self.pool[f"{pre}_{s}"] = z(rows, w)
+                self.pool[f"{pre}_{s}"] = z(self.table_rows(rows), w)
         self.pool["workspace"] = torch.zeros(self.workspace_bytes, dtype=torch.uint8, device=self.device)
         bufs = L.PamrecBuffers(workspace_bytes=self.workspace_bytes,
                                **{k: C.c_void_p(v.data_ptr()) for k, v in self.pool.items()})
@@ -123,6 +135,49 @@ class Engine:
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def table_rows(self, vocab_rows):
+        """Rows of this rank's buffer for a table of ``vocab_rows`` rows."""
+        return int(self.lib.pamrec_shard_rows(self.handle, int(vocab_rows)))
+
+    def init_comm(self):
+        """Collective over torch.distributed's default group (any backend): rank 0 creates the NCCL unique id, everyone
+        joins.  torch.distributed is the rendezvous; the step's collectives run on the library's own communicator."""
+        if self.world == 1:
+            return self
+        import torch.distributed as dist
+        from .build import nccl_library
+        if not dist.is_initialized() or dist.get_world_size() != self.world or dist.get_rank() != self.rank:
+            raise PamrecError("init_comm needs torch.distributed initialised with the engine's world_size / rank")
+        path = nccl_library()
+        cpath = path.encode() if path else None
+        box = [None]
+        if self.rank == 0:
+            buf = C.create_string_buffer(L.COMM_ID_BYTES)
+            if self.lib.pamrec_comm_unique_id(cpath, buf) != 0:
+                raise PamrecError("pamrec_comm_unique_id failed (libnccl.so.2 not loadable?)")
+            box[0] = buf.raw
+        dist.broadcast_object_list(box, src=0)
+        torch.cuda.set_device(self.device)
+        self._check(self.lib.pamrec_comm_init(self.handle, cpath, box[0]))
+        return self
+
+    def all_reduce_(self, t):
+        """In-place sum over ranks of a float32 / float64 / int32 device tensor on the library's communicator."""
+        dt = {torch.float32: L.F32, torch.float64: L.F64, torch.int32: L.I32}[t.dtype]
+        self._check(self.lib.pamrec_comm_all_reduce(self.handle, C.c_void_p(t.data_ptr()), t.numel(), dt, self._stream()))
+        return t
+
+    def _gather_table(self, shard, vocab_rows):
+        """Full [vocab_rows, width] host array from every rank's shard (collective when world > 1)."""
+        if self.tables != "sharded":
+            return shard.detach().cpu().numpy().copy()
+        if self.world == 1:
+            return D.unshard_table([shard.detach().cpu().numpy()], vocab_rows)
+        full = torch.zeros((self.world,) + tuple(shard.shape), dtype=shard.dtype, device=self.device)
+        full[self.rank].copy_(shard)
+        self.all_reduce_(full)
+        return D.unshard_table(list(full.cpu().numpy()), vocab_rows)
 
     def dense(self, name, which="dense_param"):
         d = self.info[L.POOL_DENSE][name]
@@ -149,6 +204,8 @@ class Engine:
         for name, val in variables.items():
             t = torch.as_tensor(np.asarray(val, dtype=np.float32))
             if name in TABLES:
+                if self.tables == "sharded":
+                    t = torch.from_numpy(D.shard_table(t.numpy(), self.world, self.rank))
                 self.pool[TABLES[name][0] + "_w"].copy_(t.to(self.device))
             elif name in self.info[L.POOL_DENSE]:
                 self.dense(name).copy_(t.to(self.device).view(self.dense(name).shape))
@@ -165,7 +222,7 @@ class Engine:
             for name in self.info[L.POOL_DENSE]:
                 out[name] = self.dense(name).detach().cpu().numpy().copy()
             for name, (pre, _) in TABLES.items():
-                out[name] = self.pool[pre + "_w"].detach().cpu().numpy().copy()
+                out[name] = self._gather_table(self.pool[pre + "_w"], self._vocab(pre))
             out.update({n: a.copy() for n, a in self.frozen.items()})
         if "bn" in pools:
             for name in self.info[L.POOL_BN]:
@@ -178,13 +235,18 @@ class Engine:
             st[name + "/Adam"] = self.dense(name, "dense_m").detach().cpu().numpy().copy()
             st[name + "/Adam_1"] = self.dense(name, "dense_v").detach().cpu().numpy().copy()
         for name, (pre, _) in TABLES.items():
-            st[name + "/Adam"] = self.pool[pre + "_m"].detach().cpu().numpy().copy()
-            st[name + "/Adam_1"] = self.pool[pre + "_v"].detach().cpu().numpy().copy()
+            st[name + "/Adam"] = self._gather_table(self.pool[pre + "_m"], self._vocab(pre))
+            st[name + "/Adam_1"] = self._gather_table(self.pool[pre + "_v"], self._vocab(pre))
         return st
 
+    def _vocab(self, pre):
+        nu, ni, nc, _, _ = self.dims
+        return {"item": ni, "cate": nc, "ulong": nu, "ushort": nu}[pre]
+
     # ------------------------------------------------------------------ batches
-    def upload(self, feed, training=True, staged=False):
-        """feed: the reference's feed dict with string keys (io/sequential_iterator.py:1155-1175).
+    def upload(self, feed, training=True, staged=False, global_batch=0):
+        """feed: the reference's feed dict with string keys (io/sequential_iterator.py:1155-1175); with world_size > 1 it is
+        this rank's share and ``global_batch`` the row count over all ranks (0 = batch * world_size).
 
         staged=False allocates fresh device tensors (a batch that stays resident).  staged=True packs every field into
         one pinned host buffer and issues ONE host->device copy into a reusable device buffer (two slots, alternating):
@@ -235,7 +297,7 @@ class Engine:
         for name, _, _ in BATCH_FIELDS:          # scoring: unused pointers stay null
             if name not in tensors:
                 tensors[name] = torch.empty(0, device=self.device)
-        db = DeviceBatch(tensors, B)
+        db = DeviceBatch(tensors, B, global_batch)
         db.h2d_bytes = nbytes
         for name, _, _ in BATCH_FIELDS:
             if tensors[name].numel() == 0:

@@ -18,6 +18,7 @@ import time
 import numpy as np
 import torch
 
+from . import dist as D
 from .deeprec_utils import cal_metric, cal_weighted_metric, filter_single_class_users, load_dict
 from .engine import Engine, EMB, TABLES
 
@@ -98,9 +99,11 @@ class Saver:
         d = os.path.dirname(save_path)
         if d:
             os.makedirs(d, exist_ok=True)
-        variables = self.model.engine.get_variables()
-        np.savez(save_path + ".npz", **{k.replace("/", "|"): v for k, v in variables.items()})
+        variables = self.model.engine.get_variables()          # collective when the tables are sharded over ranks
         self.kept.append(save_path)
+        if self.model.engine.rank != 0:
+            return save_path
+        np.savez(save_path + ".npz", **{k.replace("/", "|"): v for k, v in variables.items()})
         while len(self.kept) > self.max_to_keep:
             old = self.kept.pop(0)
             if os.path.exists(old + ".npz"):
@@ -197,8 +200,16 @@ class SequentialBaseModel(BaseModel):
 
     # ------------------------------------------------------------------ device steps
     def _score(self, feed_dict):
-        db = self.engine.upload(feed_dict, training=False, staged=True)
-        return self.engine.forward(db, training=False).cpu().numpy().reshape(-1, 1)
+        eng = self.engine
+        if eng.world > 1 and self.feed_is_global:
+            # data-parallel scoring: rank r scores rows r, r + W, ... of the batch; the scores are summed back into place
+            local, n = D.split_feed(feed_dict, eng.world, eng.rank, grouped=False)
+            db = eng.upload(local, training=False, staged=True, global_batch=n)
+            full = torch.zeros(n, dtype=torch.float32, device=eng.device)
+            full[eng.rank::eng.world] = eng.forward(db, training=False)
+            return eng.all_reduce_(full).cpu().numpy().reshape(-1, 1)
+        db = eng.upload(feed_dict, training=False, staged=True)
+        return eng.forward(db, training=False).cpu().numpy().reshape(-1, 1)
 
     def eval(self, sess, feed_dict):
         """SBM:415-418 / BM:373-386 -> (pred [B,1], labels [B,1])."""
@@ -359,15 +370,34 @@ class PAMRECModel(SequentialBaseModel):
             max_grad_norm=float(hp.max_grad_norm), is_clip_norm=int(bool(hp.is_clip_norm)),
             fuzhu_weight=float(hp.fuzhu_weight), discrepancy_loss_weight=float(hp.discrepancy_loss_weight))
         mode = getattr(hp, "sparse_adam", "dense_exact")
-        self.engine = Engine(n_users, n_items, n_cates, hp.max_seq_length, hp.batch_size, hp=engine_hp, sparse_adam=mode)
-        self.engine.allocate(getattr(hp, "device", "cuda:0"))
+        # data parallel (no reference counterpart): one process per GPU under torchrun.  hparams.batch_size stays the GLOBAL
+        # batch when feeds come from the iterator (every rank reads the same file and trains on its groups of each batch);
+        # dp_feed="local" means the caller hands each rank its own share (bench.py's weak-scaling arrays).
+        world, rank = 1, 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        self.feed_is_global = getattr(hp, "dp_feed", "global") != "local"
+        cap = hp.batch_size
+        if world > 1 and self.feed_is_global:
+            cap = max(-(-(hp.batch_size // 5) // world) * 5, -(-hp.batch_size // world))
+        tables = getattr(hp, "tables", None)
+        self.engine = Engine(n_users, n_items, n_cates, hp.max_seq_length, cap, hp=engine_hp, sparse_adam=mode,
+                             world_size=world, rank=rank, tables=tables)
+        default_dev = "cuda:{}".format(int(os.environ.get("LOCAL_RANK", 0))) if world > 1 else "cuda:0"
+        self.engine.allocate(getattr(hp, "device", default_dev))
+        self.engine.init_comm()
         self.engine.set_variables(initial_variables(self.engine.variable_shapes(), hp, self.seed))
 
     def train(self, sess, feed_dict):
         """PAM:426-453: one optimisation step.  Returns the reference's 8-tuple
         (update, extra_update_ops, loss, data_loss, regular_loss, auxiliary_data_loss, order_loss, summary)."""
-        db = self.engine.upload(feed_dict, training=True, staged=True)
-        losses = self.engine.train_step(db).cpu().numpy()
+        eng = self.engine
+        if eng.world > 1 and self.feed_is_global:
+            local, n = D.split_feed(feed_dict, eng.world, eng.rank, grouped=True)
+            db = eng.upload(local, training=True, staged=True, global_batch=n)
+        else:
+            db = eng.upload(feed_dict, training=True, staged=True)
+        losses = eng.train_step(db).cpu().numpy()
         return [None, None, float(losses[0]), float(losses[1]), float(losses[2]), float(losses[3]), float(losses[4]), None]
 
     def step_train(self, step, step_result):

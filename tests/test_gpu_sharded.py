@@ -1,0 +1,84 @@
+"""Row-sharded tables and the data-parallel step.
+
+* one GPU: the whole exchange path (plan by owner, id / row / row-gradient all-to-all degenerated to local copies,
+  owner-side merge and Adam) against the fp64 oracle and against the direct-gather path;
+* two GPUs (skipped on a one-GPU box): tests/dist_worker.py under torch.distributed.run, NCCL over NVLink."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pamrec_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMB = "sequential/embedding/"
+
+
+def _engine(om, nu, ni, nc, T, B, tables, sparse_adam="dense_exact"):
+    from pamrec_b200.engine import Engine
+    eng = Engine(nu, ni, nc, T, B, tables=tables, sparse_adam=sparse_adam).allocate()
+    eng.set_variables({n: t.numpy() for n, t in om.params.items()})
+    eng.set_variables({n: t.numpy() for n, t in om.bn_state.items()})
+    return eng
+
+
+@pytest.mark.parametrize("sparse_adam", ["dense_exact", "lazy"])
+def test_sharded_path_on_one_gpu(sparse_adam):
+    nu, ni, nc, T, B = 300, 3000, 50, 50, 100
+    om = O.OracleModel(nu, ni, nc, T, seed=3)
+    O.perturb_params(om.params, om.bn_state, seed=4)
+    sh = _engine(om, nu, ni, nc, T, B, "sharded", sparse_adam)
+    lo = _engine(om, nu, ni, nc, T, B, "local", sparse_adam)
+    # gather through the exchange is bit-exact
+    batch = O.make_batch(5, B, T, nu, ni, nc)
+    assert torch.equal(sh.gather(sh.upload(batch)), lo.gather(lo.upload(batch)))
+    for step in range(3):
+        batch = O.make_batch(100 + step, B, T, nu, ni, nc)
+        a = sh.train_step(sh.upload(batch)).cpu().numpy()
+        b = lo.train_step(lo.upload(batch)).cpu().numpy()
+        assert np.allclose(a, b, rtol=2e-6, atol=1e-7), (step, a, b)
+        if sparse_adam == "dense_exact":
+            ref = om.train_step(batch)
+            for i, k in enumerate(("loss", "data_loss", "regular_loss", "auxiliary_data_loss", "order_loss")):
+                r = ref["losses"][k]
+                assert abs(a[i] - r) <= 2e-5 * max(abs(r), 1e-3), (step, k, a[i], r)
+    va, vb = sh.get_variables(), lo.get_variables()
+    for name in (EMB + "item_embedding", EMB + "cate_embedding", EMB + "user_long_embedding", EMB + "user_short_embedding"):
+        assert va[name].shape == vb[name].shape
+        # Adam normalises every coordinate's gradient, so fp32 summation-order noise on a nearly cancelling gradient moves
+        # the weight by a fraction of lr (1e-3): compare on that scale (1 % of one step), not on the weight's scale.
+        assert np.abs(va[name] - vb[name]).max() <= 1e-5, name
+        if sparse_adam == "dense_exact":
+            assert np.abs(va[name] - om.params[name].numpy()).max() <= 5e-5, name   # fp32 step vs fp64 oracle, 3 steps
+    ev = O.make_batch(999, 77, T, nu, ni, nc, grouped=False)
+    pa = sh.forward(sh.upload(ev, training=False), training=False).cpu().numpy()
+    pb = lo.forward(lo.upload(ev, training=False), training=False).cpu().numpy()
+    assert np.abs(pa - pb).max() <= 1e-5
+    sh.close(); lo.close()
+
+
+def test_sharded_empty_share_is_refused_without_peers_but_not_fatal():
+    """batch = 0 is legal on a sharded handle (a rank with no groups in a tail batch): scoring returns nothing."""
+    nu, ni, nc, T, B = 50, 300, 20, 12, 20
+    om = O.OracleModel(nu, ni, nc, T, seed=1)
+    eng = _engine(om, nu, ni, nc, T, B, "sharded")
+    ev = O.make_batch(1, 10, T, nu, ni, nc, grouped=False)
+    empty = {k: v[:0] for k, v in ev.items()}
+    out = eng.forward(eng.upload(empty, training=False), training=False)
+    assert out.numel() == 0
+    torch.cuda.synchronize()
+    eng.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_two_rank_step_matches_oracle():
+    n = min(torch.cuda.device_count(), int(os.environ.get("PAMREC_TEST_RANKS", "2")))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", os.path.join(ROOT, "tests", "dist_worker.py")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0 and "DIST_PARITY_OK" in r.stdout, r.stdout[-3000:]
