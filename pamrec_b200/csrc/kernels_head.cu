@@ -10,73 +10,152 @@
 
 namespace pamrec {
 
-constexpr int kRows = 128;     // rows per CTA (thread == row)
-constexpr int kXs = 129;       // smem stride of the transposed input tile
-constexpr int kNc = 16;        // output columns per CTA
+// The dense layers of the head are small GEMMs (M = B or B*T rows, K and N <= 100).  All three kernels share one
+// shape: a CTA of 128 threads owns a 32 x 32 output tile, thread (ty, tx) = (tid / 8, tid % 8) keeps a 2 x 4 patch of
+// accumulators, and the two operands sit in shared memory as As[kk][32] / Bs[kk][32] with the contraction index kk
+// leading, so one LDS.64 (4 distinct addresses per warp) and one LDS.128 (128 contiguous bytes per warp) feed 8 FMAs.
+// Grids are (row tiles) x (groups x column tiles): hundreds of CTAs even at B = 1025, every global load of a tile is
+// issued before the first use (the layers are latency-bound, not FLOP-bound).
+constexpr int kTM = 32;        // output rows per tile
+constexpr int kTN = 32;        // output columns per tile
+constexpr int kKMax = 104;     // largest contraction length held in shared memory at once
+constexpr int kHT = 128;       // threads per CTA
 
 __device__ __forceinline__ float bn_relu(float z, const float* stat, const float* gamma, const float* beta, int col) {
   float xh = (z - stat[2 * col]) * stat[2 * col + 1];
   return fmaxf(fmaf(gamma[col], xh, beta[col]), 0.f);
 }
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// acc[2][4] += sum_kk As[kk][2ty .. 2ty+1] (x) Bs[kk][4tx .. 4tx+3]
+__device__ __forceinline__ void tile_mma(const float* __restrict__ As, const float* __restrict__ Bs, int kk_n, int ty, int tx,
+                                         float (&acc)[2][4]) {
+#pragma unroll 4
+  for (int kk = 0; kk < kk_n; ++kk) {
+    const float2 a = *reinterpret_cast<const float2*>(As + kk * kTM + 2 * ty);
+    const float4 b = ld4(Bs + kk * kTN + 4 * tx);
+    acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+    acc[0][2] = fmaf(a.x, b.z, acc[0][2]); acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
+    acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+    acc[1][2] = fmaf(a.y, b.z, acc[1][2]); acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
+  }
+}
+
+// Stage rows [m0, m0+32) x columns [c0, c0+cn) of a row-major matrix (leading dimension ld) TRANSPOSED into
+// dst[c][32] (c = column offset), zero-filling rows >= rows_valid.  f(value, column offset) is applied on the way.
+// Thread i handles row i % 32: the transposed store is bank-conflict free; the strided 16-byte reads hit L1/L2.
+template <typename F>
+__device__ __forceinline__ void stage_rows_T(float* __restrict__ dst, const float* __restrict__ src, int ld, int rows_valid,
+                                             int cn, int tid, F f) {
+  const bool vec = ((ld | cn) & 3) == 0 && aligned16(src);
+  if (vec) {
+    const int n4 = cn >> 2, total = kTM * n4;
+    constexpr int IT = (kTM * (kKMax / 4) + kHT - 1) / kHT;
+    float4 v[IT];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const int i = tid + it * kHT;
+      const int r = i % kTM, c4 = i / kTM;
+      v[it] = (i < total && r < rows_valid) ? ld4(src + (int64_t)r * ld + 4 * c4) : f4_zero();
+    }
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const int i = tid + it * kHT;
+      const int r = i % kTM, c4 = i / kTM;
+      if (i < total) {
+        const bool ok = r < rows_valid;
+        dst[(4 * c4 + 0) * kTM + r] = ok ? f(v[it].x, 4 * c4 + 0) : 0.f;
+        dst[(4 * c4 + 1) * kTM + r] = ok ? f(v[it].y, 4 * c4 + 1) : 0.f;
+        dst[(4 * c4 + 2) * kTM + r] = ok ? f(v[it].z, 4 * c4 + 2) : 0.f;
+        dst[(4 * c4 + 3) * kTM + r] = ok ? f(v[it].w, 4 * c4 + 3) : 0.f;
+      }
+    }
+  } else {
+    const int total = kTM * cn;
+    for (int i = tid; i < total; i += kHT) {
+      const int r = i % kTM, c = i / kTM;
+      dst[c * kTM + r] = (r < rows_valid) ? f(src[(int64_t)r * ld + c], c) : 0.f;
+    }
+  }
+}
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRows) k_dense_fwd(const DenseP p) {
-  extern __shared__ __align__(16) float sm[];
-  float* Xs = sm;                       // [K][129]
-  float* Wc = Xs + ((p.K * kXs + 3) & ~3);   // [K][16], 16-byte aligned
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int nchunk = (p.N + kNc - 1) / kNc;
-  const int g = blockIdx.y / nchunk, c0 = (blockIdx.y % nchunk) * kNc;
-  const int nc = min(kNc, p.N - c0);
-  const int m0 = blockIdx.x * kRows;
-  const int rows = min(kRows, p.M - m0);
+// Z[m, zo+n] = sum_k act(X[m, xo+k]) W_g[k][n] + b_g[n]   (+ fp64 column sums of Z for the next batch norm)
+__global__ void __launch_bounds__(kHT) k_dense_fwd(const DenseP p, int tiles_m) {
+  __shared__ __align__(16) float As[kKMax * kTM];
+  __shared__ __align__(16) float Bs[kKMax * kTN];
+  __shared__ double red[2][kHT / 8][kTN];
+  const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
+  const int nchunk = (p.N + kTN - 1) / kTN;
+  const int g = blockIdx.y / nchunk, c0 = (blockIdx.y % nchunk) * kTN;
+  const int nc = min(kTN, p.N - c0);
   const int xo = p.x_off[g], zo = p.z_off[g] + c0;
   const float* W = p.W + (int64_t)g * p.w_stride;
-  for (int i = tid; i < kRows * p.K; i += kRows) {
-    int r = i / p.K, k = i % p.K;
-    float v = 0.f;
-    if (r < rows) {
-      v = p.X[(int64_t)(m0 + r) * p.ldx + xo + k];
-      if (p.in_stat) v = bn_relu(v, p.in_stat, p.in_gamma, p.in_beta, xo + k);
-    }
-    Xs[k * kXs + r] = v;
-  }
-  for (int i = tid; i < p.K * kNc; i += kRows) {
-    int k = i / kNc, c = i % kNc;
-    Wc[i] = (c < nc) ? W[(int64_t)k * p.N + c0 + c] : 0.f;
-  }
-  __syncthreads();
-  float acc[kNc];
-#pragma unroll
-  for (int c = 0; c < kNc; ++c) acc[c] = (c < nc) ? p.bias[(int64_t)g * p.b_stride + c0 + c] : 0.f;
-  for (int k = 0; k < p.K; ++k) {
-    float a = Xs[k * kXs + tid];
-#pragma unroll
-    for (int c4 = 0; c4 < kNc / 4; ++c4) {
-      float4 w = ld4(Wc + k * kNc + 4 * c4);
-      acc[4 * c4] = fmaf(a, w.x, acc[4 * c4]);
-      acc[4 * c4 + 1] = fmaf(a, w.y, acc[4 * c4 + 1]);
-      acc[4 * c4 + 2] = fmaf(a, w.z, acc[4 * c4 + 2]);
-      acc[4 * c4 + 3] = fmaf(a, w.w, acc[4 * c4 + 3]);
+  // weight tile Bs[k][n] = W[k][c0+n]
+  {
+    const bool vec = ((p.N | c0) & 3) == 0 && (nc & 3) == 0 && aligned16(W);
+    if (vec) {
+      const int n4 = nc >> 2;
+      for (int i = tid; i < p.K * (kTN / 4); i += kHT) {
+        const int k = i / (kTN / 4), q = i % (kTN / 4);
+        st4(Bs + k * kTN + 4 * q, q < n4 ? ld4(W + (int64_t)k * p.N + c0 + 4 * q) : f4_zero());
+      }
+    } else {
+      for (int i = tid; i < p.K * kTN; i += kHT) {
+        const int k = i / kTN, n = i % kTN;
+        Bs[i] = n < nc ? W[(int64_t)k * p.N + c0 + n] : 0.f;
+      }
     }
   }
-  const bool valid = tid < rows;
-  if (valid) {
-    float* z = p.Z + (int64_t)(m0 + tid) * p.ldz + zo;
+  float bias[4];
 #pragma unroll
-    for (int c = 0; c < kNc; ++c)
-      if (c < nc) z[c] = acc[c];
+  for (int j = 0; j < 4; ++j) bias[j] = (4 * tx + j < nc) ? p.bias[(int64_t)g * p.b_stride + c0 + 4 * tx + j] : 0.f;
+  double cs[4] = {0.0, 0.0, 0.0, 0.0}, cq[4] = {0.0, 0.0, 0.0, 0.0};
+  const bool vec_out = ((p.ldz | zo) & 3) == 0 && aligned16(p.Z) && (nc & 3) == 0;
+  for (int tm = blockIdx.x; tm < tiles_m; tm += gridDim.x) {
+    const int m0 = tm * kTM;
+    const int rows = min(kTM, p.M - m0);
+    __syncthreads();                                  // previous tile's As fully consumed (and Bs written, first pass)
+    const float* X = p.X + (int64_t)m0 * p.ldx + xo;
+    if (p.in_stat) {
+      const float* st = p.in_stat; const float* ga = p.in_gamma; const float* be = p.in_beta;
+      stage_rows_T(As, X, p.ldx, rows, p.K, tid, [=](float v, int k) { return bn_relu(v, st, ga, be, xo + k); });
+    } else {
+      stage_rows_T(As, X, p.ldx, rows, p.K, tid, [](float v, int) { return v; });
+    }
+    __syncthreads();
+    float acc[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = bias[j];
+    tile_mma(As, Bs, p.K, ty, tx, acc);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = 2 * ty + i;
+      if (r < rows) {
+        float* z = p.Z + (int64_t)(m0 + r) * p.ldz + zo + 4 * tx;
+        if (vec_out) { if (4 * tx < nc) st4(z, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3])); }
+        else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (4 * tx + j < nc) z[j] = acc[i][j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { cs[j] += (double)acc[i][j]; cq[j] += (double)acc[i][j] * (double)acc[i][j]; }
+      }
+    }
   }
   if (p.out_sums) {
 #pragma unroll
-    for (int c = 0; c < kNc; ++c) {
-      if (c < nc) {                                   // nc is CTA-uniform
-        double v = valid ? (double)acc[c] : 0.0;
-        double s = warp_sum_d(v), q = warp_sum_d(v * v);
-        if (lane == 0) {
-          atomicAdd(p.out_sums + 2 * (zo + c), s);
-          atomicAdd(p.out_sums + 2 * (zo + c) + 1, q);
-        }
+    for (int j = 0; j < 4; ++j) { red[0][ty][4 * tx + j] = cs[j]; red[1][ty][4 * tx + j] = cq[j]; }
+    __syncthreads();
+    if (tid < 2 * kTN) {
+      const int which = tid / kTN, n = tid % kTN;
+      if (n < nc) {
+        double t = 0.0;
+#pragma unroll
+        for (int y = 0; y < kHT / 8; ++y) t += red[which][y][n];
+        atomicAdd(p.out_sums + 2 * (zo + n) + which, t);
       }
     }
   }
@@ -84,134 +163,159 @@ __global__ void __launch_bounds__(kRows) k_dense_fwd(const DenseP p) {
 
 void launch_dense_fwd(const DenseP& p, cudaStream_t st) { PAMREC_PROF("dense_fwd", 1, st);
   if (p.M == 0) return;
-  static int smem_set = 0;
-  int smem = (p.K * (kXs + kNc) + 4) * 4;
-  if (smem > smem_set) { cudaFuncSetAttribute(k_dense_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set = smem; }
-  int nchunk = (p.N + kNc - 1) / kNc;
-  dim3 grid((p.M + kRows - 1) / kRows, p.n_groups * nchunk);
-  k_dense_fwd<<<grid, kRows, smem, st>>>(p);
+  const int tiles_m = (p.M + kTM - 1) / kTM;
+  const int ny = p.n_groups * ((p.N + kTN - 1) / kTN);
+  const int cap = (148 * 8 + ny - 1) / ny;            // enough CTAs to fill the GPU; long matrices loop over row tiles
+  const int per_cta = (tiles_m + cap - 1) / cap;
+  const int gx = (tiles_m + per_cta - 1) / per_cta;
+  k_dense_fwd<<<dim3(gx, ny), kHT, 0, st>>>(p, tiles_m);
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRows) k_dense_dx(const DenseDxP p) {
-  extern __shared__ __align__(16) float sm[];
-  const int tid = threadIdx.x;
-  const int kchunk = (p.K + kNc - 1) / kNc;
-  const int s = blockIdx.y / kchunk, k0 = (blockIdx.y % kchunk) * kNc;
-  const int kc = min(kNc, p.K - k0);
-  const int m0 = blockIdx.x * kRows;
-  const int rows = min(kRows, p.M - m0);
-  float acc[kNc];
+// dX[m, out_off[s]+k] (+)= sum over contributions c of slice s: sum_n dZ[m, dz_off+n] W_c[k][n]
+__global__ void __launch_bounds__(kHT) k_dense_dx(const DenseDxP p) {
+  __shared__ __align__(16) float As[kKMax * kTM];   // dZ tile, transposed: As[n][m]
+  __shared__ __align__(16) float Bs[kKMax * kTN];   // Bs[n][kk] = W[k0+kk][n]
+  const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
+  const int kchunk = (p.K + kTN - 1) / kTN;
+  const int s = blockIdx.y / kchunk, k0 = (blockIdx.y % kchunk) * kTN;
+  const int kc = min(kTN, p.K - k0);
+  const int m0 = blockIdx.x * kTM;
+  const int rows = min(kTM, p.M - m0);
+  float acc[2][4];
 #pragma unroll
-  for (int c = 0; c < kNc; ++c) acc[c] = 0.f;
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int ci = 0; ci < p.n_contrib[s]; ++ci) {
     const int N = p.Ncon[s][ci], dzo = p.dz_off[s][ci];
     const float* W = p.Wbase + p.w_off[s][ci];
-    float* Gs = sm;                 // [N][129]
-    float* Wt = Gs + ((N * kXs + 3) & ~3);   // [N][16]  Wt[n][kk] = W[k0+kk][n]  (16-byte aligned)
     __syncthreads();
-    for (int i = tid; i < kRows * N; i += kRows) {
-      int r = i / N, n = i % N;
-      Gs[n * kXs + r] = (r < rows) ? p.dZ[(int64_t)(m0 + r) * p.lddz + dzo + n] : 0.f;
-    }
-    for (int i = tid; i < N * kNc; i += kRows) {
-      int n = i / kNc, kk = i % kNc;
-      Wt[i] = (kk < kc) ? W[(int64_t)(k0 + kk) * N + n] : 0.f;
-    }
+    stage_rows_T(As, p.dZ + (int64_t)m0 * p.lddz + dzo, p.lddz, rows, N, tid, [](float v, int) { return v; });
+    // rows of W are the "rows" to transpose: Bs[n][kk] = W[(k0+kk)*N + n]
+    stage_rows_T(Bs, W + (int64_t)k0 * N, N, kc, N, tid, [](float v, int) { return v; });
     __syncthreads();
-    for (int n = 0; n < N; ++n) {
-      float a = Gs[n * kXs + tid];
+    tile_mma(As, Bs, N, ty, tx, acc);
+  }
+  const int oo = p.out_off[s] + k0;
+  const bool vec_out = ((p.lddx | oo) & 3) == 0 && aligned16(p.dX) && (kc & 3) == 0;
 #pragma unroll
-      for (int c4 = 0; c4 < kNc / 4; ++c4) {
-        float4 w = ld4(Wt + n * kNc + 4 * c4);
-        acc[4 * c4] = fmaf(a, w.x, acc[4 * c4]);
-        acc[4 * c4 + 1] = fmaf(a, w.y, acc[4 * c4 + 1]);
-        acc[4 * c4 + 2] = fmaf(a, w.z, acc[4 * c4 + 2]);
-        acc[4 * c4 + 3] = fmaf(a, w.w, acc[4 * c4 + 3]);
+  for (int i = 0; i < 2; ++i) {
+    const int r = 2 * ty + i;
+    if (r < rows) {
+      float* o = p.dX + (int64_t)(m0 + r) * p.lddx + oo + 4 * tx;
+      if (vec_out) {
+        if (4 * tx < kc) {
+          float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+          if (p.accumulate) { float4 q = ld4(o); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+          st4(o, v);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (4 * tx + j < kc) o[j] = p.accumulate ? o[j] + acc[i][j] : acc[i][j];
       }
     }
-  }
-  if (tid < rows) {
-    float* o = p.dX + (int64_t)(m0 + tid) * p.lddx + p.out_off[s] + k0;
-#pragma unroll
-    for (int c = 0; c < kNc; ++c)
-      if (c < kc) o[c] = p.accumulate ? o[c] + acc[c] : acc[c];
   }
 }
 
 void launch_dense_dx(const DenseDxP& p, cudaStream_t st) { PAMREC_PROF("dense_dx", 1, st);
   if (p.M == 0) return;
-  static int smem_set = 0;
-  int maxN = 1;
-  for (int s = 0; s < p.n_slices; ++s)
-    for (int c = 0; c < p.n_contrib[s]; ++c) maxN = max(maxN, p.Ncon[s][c]);
-  int smem = (maxN * (kXs + kNc) + 4) * 4;
-  if (smem > smem_set) { cudaFuncSetAttribute(k_dense_dx, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set = smem; }
-  int kchunk = (p.K + kNc - 1) / kNc;
-  dim3 grid((p.M + kRows - 1) / kRows, p.n_slices * kchunk);
-  k_dense_dx<<<grid, kRows, smem, st>>>(p);
+  const int kchunk = (p.K + kTN - 1) / kTN;
+  dim3 grid((p.M + kTM - 1) / kTM, p.n_slices * kchunk);
+  k_dense_dx<<<grid, kHT, 0, st>>>(p);
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRows) k_dense_dw(const DenseDwP p) {
-  extern __shared__ __align__(16) float sm[];
-  const int tid = threadIdx.x;
-  const int g = blockIdx.y;
-  const int K = p.K, N = p.N;
-  const int Kp = K + 1, Np = (N + kNc - 1) / kNc * kNc;
-  float* As = sm;                   // [128][Kp]
-  float* Gs = As + kRows * Kp;      // [128][Np]
-  const int m0 = blockIdx.x * kRows;
-  const int rows = min(kRows, p.M - m0);
-  const int xo = p.x_off[g], zo = p.z_off[g];
-  for (int i = tid; i < rows * K; i += kRows) {
-    int r = i / K, k = i % K;
-    float v = p.X[(int64_t)(m0 + r) * p.ldx + xo + k];
-    if (p.in_stat) v = bn_relu(v, p.in_stat, p.in_gamma, p.in_beta, xo + k);
-    As[r * Kp + k] = v;
-  }
-  for (int i = tid; i < rows * Np; i += kRows) {
-    int r = i / Np, n = i % Np;
-    Gs[i] = (n < N) ? p.dZ[(int64_t)(m0 + r) * p.lddz + zo + n] : 0.f;
-  }
-  __syncthreads();
-  const int nchunk = Np / kNc;
-  float* dW = p.dW + (int64_t)g * p.w_stride;
-  for (int u = tid; u < K * nchunk; u += kRows) {
-    int k = u % K, n0 = (u / K) * kNc;
-    float acc[kNc];
+// dW_g[k][n] += sum_m act(X[m, xo+k]) dZ[m, zo+n];  db_g[n] += sum_m dZ[m, zo+n].  The contraction runs over rows:
+// a CTA takes `rows_per_cta` rows in sub-chunks of 32 and one 32 x 32 tile of (k, n); partial sums leave by atomicAdd.
+__global__ void __launch_bounds__(kHT) k_dense_dw(const DenseDwP p, int rows_per_cta) {
+  __shared__ __align__(16) float As[kTM * kTM];     // As[r][kk] = act(X[m0+r, xo+k0+kk])
+  __shared__ __align__(16) float Bs[kTM * kTN];     // Bs[r][nn] = dZ[m0+r, zo+n0+nn]
+  const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
+  const int ktiles = (p.K + kTM - 1) / kTM, ntiles = (p.N + kTN - 1) / kTN;
+  int y = blockIdx.y;
+  const int nt = y % ntiles; y /= ntiles;
+  const int kt = y % ktiles;
+  const int g = y / ktiles;
+  const int k0 = kt * kTM, n0 = nt * kTN;
+  const int kc = min(kTM, p.K - k0), nc = min(kTN, p.N - n0);
+  const int xo = p.x_off[g] + k0, zo = p.z_off[g] + n0;
+  const int m_begin = blockIdx.x * rows_per_cta, m_end = min(p.M, m_begin + rows_per_cta);
+  const bool vecA = ((p.ldx | xo) & 3) == 0 && (kc & 3) == 0 && aligned16(p.X);
+  const bool vecB = ((p.lddz | zo) & 3) == 0 && (nc & 3) == 0 && aligned16(p.dZ);
+  float acc[2][4];
 #pragma unroll
-    for (int c = 0; c < kNc; ++c) acc[c] = 0.f;
-    for (int r = 0; r < rows; ++r) {
-      float a = As[r * Kp + k];
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int c4 = 0; c4 < kNc / 4; ++c4) {
-        float4 gq = ld4(Gs + r * Np + n0 + 4 * c4);
-        acc[4 * c4] = fmaf(a, gq.x, acc[4 * c4]);
-        acc[4 * c4 + 1] = fmaf(a, gq.y, acc[4 * c4 + 1]);
-        acc[4 * c4 + 2] = fmaf(a, gq.z, acc[4 * c4 + 2]);
-        acc[4 * c4 + 3] = fmaf(a, gq.w, acc[4 * c4 + 3]);
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float dbv = 0.f;
+  for (int m0 = m_begin; m0 < m_end; m0 += kTM) {
+    const int rows = min(kTM, m_end - m0);
+    __syncthreads();
+    // each thread stages 2 float4 (or 8 scalars) of each operand: row r = i / 8, quad q = i % 8
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int i = tid + it * kHT;
+      const int r = i >> 3, q = i & 7;
+      float4 a = f4_zero(), b = f4_zero();
+      if (r < rows) {
+        const float* xa = p.X + (int64_t)(m0 + r) * p.ldx + xo + 4 * q;
+        const float* zb = p.dZ + (int64_t)(m0 + r) * p.lddz + zo + 4 * q;
+        if (vecA) { if (4 * q < kc) a = ld4(xa); }
+        else {
+          if (4 * q + 0 < kc) a.x = xa[0];
+          if (4 * q + 1 < kc) a.y = xa[1];
+          if (4 * q + 2 < kc) a.z = xa[2];
+          if (4 * q + 3 < kc) a.w = xa[3];
+        }
+        if (p.in_stat) {
+          const int col = xo + 4 * q;
+          if (4 * q + 0 < kc) a.x = bn_relu(a.x, p.in_stat, p.in_gamma, p.in_beta, col + 0);
+          if (4 * q + 1 < kc) a.y = bn_relu(a.y, p.in_stat, p.in_gamma, p.in_beta, col + 1);
+          if (4 * q + 2 < kc) a.z = bn_relu(a.z, p.in_stat, p.in_gamma, p.in_beta, col + 2);
+          if (4 * q + 3 < kc) a.w = bn_relu(a.w, p.in_stat, p.in_gamma, p.in_beta, col + 3);
+        }
+        if (vecB) { if (4 * q < nc) b = ld4(zb); }
+        else {
+          if (4 * q + 0 < nc) b.x = zb[0];
+          if (4 * q + 1 < nc) b.y = zb[1];
+          if (4 * q + 2 < nc) b.z = zb[2];
+          if (4 * q + 3 < nc) b.w = zb[3];
+        }
       }
+      st4(As + r * kTM + 4 * q, a);
+      st4(Bs + r * kTN + 4 * q, b);
     }
+    __syncthreads();
+    tile_mma(As, Bs, kTM, ty, tx, acc);       // rows beyond `rows` are zero-filled
+    if (kt == 0 && tid < kTN) {
+#pragma unroll 8
+      for (int r = 0; r < kTM; ++r) dbv += Bs[r * kTN + tid];
+    }
+  }
+  float* dW = p.dW + (int64_t)g * p.w_stride;
 #pragma unroll
-    for (int c = 0; c < kNc; ++c)
-      if (n0 + c < N) atomicAdd(dW + (int64_t)k * N + n0 + c, acc[c]);
+  for (int i = 0; i < 2; ++i) {
+    const int k = 2 * ty + i;
+    if (k < kc) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (4 * tx + j < nc) atomicAdd(dW + (int64_t)(k0 + k) * p.N + n0 + 4 * tx + j, acc[i][j]);
+    }
   }
-  if (tid < N) {
-    float s = 0.f;
-    for (int r = 0; r < rows; ++r) s += Gs[r * Np + tid];
-    atomicAdd(p.db + (int64_t)g * p.b_stride + tid, s);
-  }
+  if (kt == 0 && tid < nc) atomicAdd(p.db + (int64_t)g * p.b_stride + n0 + tid, dbv);
 }
 
 void launch_dense_dw(const DenseDwP& p, cudaStream_t st) { PAMREC_PROF("dense_dw", 1, st);
   if (p.M == 0) return;
-  static int smem_set = 0;
-  int Np = (p.N + kNc - 1) / kNc * kNc;
-  int smem = kRows * (p.K + 1 + Np) * 4;
-  if (smem > smem_set) { cudaFuncSetAttribute(k_dense_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); smem_set = smem; }
-  dim3 grid((p.M + kRows - 1) / kRows, p.n_groups);
-  k_dense_dw<<<grid, kRows, smem, st>>>(p);
+  const int ny = p.n_groups * ((p.K + kTM - 1) / kTM) * ((p.N + kTN - 1) / kTN);
+  int chunks = (148 * 6 + ny - 1) / ny;                         // row chunks so that the grid fills the GPU
+  const int max_chunks = (p.M + kTM - 1) / kTM;
+  if (chunks > max_chunks) chunks = max_chunks;
+  int rows_per_cta = ((p.M + chunks - 1) / chunks + kTM - 1) / kTM * kTM;
+  chunks = (p.M + rows_per_cta - 1) / rows_per_cta;
+  k_dense_dw<<<dim3(chunks, ny), kHT, 0, st>>>(p, rows_per_cta);
 }
 
 // ------------------------------------------------------------------------------------------
