@@ -412,7 +412,7 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     launch_proj_fwd(xin, h->wi("perm"), ctl, h->wi("tile_bucket"), h->wi("tile_begin"), h->wi("tile_count"), max_tiles,
                     h->P(o.wq), h->P(o.wk), h->P(o.wv), h->P(o.ln_a_beta), h->P(o.ln_a_gamma), h->wf(p + "qin"), h->wf(p + "Q"),
                     h->wf(p + "K"), h->wf(p + "V"), st);
-    launch_attn_fwd(h->wf(p + "Q"), h->wf(p + "K"), h->wf(p + "V"), h->wf(p + "qin"), b->mask, h->wf(p + "y"), B, T, st);
+    launch_attn_fwd(h->wf(p + "Q"), h->wf(p + "K"), h->wf(p + "V"), h->wf(p + "qin"), b->mask, h->wf(p + "y"), h->wf(p + "ml"), B, T, st);
     launch_ffn_fwd(h->wf(p + "y"), h->P(o.w1), h->P(o.b1), h->P(o.w2), h->P(o.b2), h->P(o.ln_b_beta), h->P(o.ln_b_gamma),
                    h->wf(p + "out"), N, st);
     nl += 3;
@@ -648,8 +648,8 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
     float* gin = k == 1 ? g_b : g_a;
     launch_ffn_bwd(h->wf(p + "y"), gout, h->P(o.w1), h->P(o.b1), h->P(o.w2), h->P(o.ln_b_beta), h->P(o.ln_b_gamma), h->wf("d_y"),
                    h->G(o.w1), h->G(o.b1), h->G(o.w2), h->G(o.b2), h->G(o.ln_b_beta), h->G(o.ln_b_gamma), N, st);
-    launch_attn_bwd(h->wf(p + "Q"), h->wf(p + "K"), h->wf(p + "V"), h->wf("d_y"), b->mask, h->wf("d_Q"), h->wf("d_K"),
-                    h->wf("d_V"), B, T, st);
+    launch_attn_bwd(h->wf(p + "Q"), h->wf(p + "K"), h->wf(p + "V"), h->wf("d_y"), h->wf(p + "y"), h->wf(p + "qin"), h->wf(p + "ml"),
+                    b->mask, h->wf("d_Q"), h->wf("d_K"), h->wf("d_V"), B, T, st);
     launch_proj_bwd(xin, h->wf("d_y"), h->wf("d_Q"), h->wf("d_K"), h->wf("d_V"), h->wi("perm"), ctl, h->wi("tile_bucket"),
                     h->wi("tile_begin"), h->wi("tile_count"), max_tiles, h->P(o.wq), h->P(o.wk), h->P(o.wv), h->P(o.ln_a_beta),
                     h->P(o.ln_a_gamma), gin, h->G(o.wq), h->G(o.wk), h->G(o.wv), h->G(o.ln_a_beta), h->G(o.ln_a_gamma), st);

@@ -309,104 +309,109 @@ void launch_proj_fwd(const float* X, const int* perm, const int* ctl, const int*
 
 // ------------------------------------------------------------------------------------------
 // A2-A4 forward: P = softmax_j(mask ? Q K^T / sqrt(40) : -(2^32)+1);  y = P V + qin  (pamrec.py:768-810)
-// CTA per sample, warp per query row, lanes over keys; P.V with a (3 key-groups x 10 chunks) lane map.
-__host__ __device__ inline int attn_tp(int T) { return (T + 3) & ~3; }
-inline size_t attn_fwd_smem(int T) { return (size_t)(3 * T * kAttnStride + 8 * attn_tp(T)) * 4 + (size_t)T * 4; }
+//
+// ONE THREAD == ONE QUERY ROW.  The 40 query values, the 40 output accumulators and a chunk of 8 scores live in
+// registers; every lane of a warp reads the SAME key / value row from shared memory (a broadcast: one wavefront per
+// LDS.128, no bank conflicts, no shuffles), so a key costs 20 LDS.128 for 80 FMAs and the 40 independent FMA chains
+// hide the latency at low occupancy.  Scores go through a chunked online softmax (one rescale per 8 keys); the row
+// maximum m and the row sum l are saved for the backward pass.  NW warps serve one sample, SPB samples share a CTA.
+constexpr int kAttnCh = 8;
+__host__ __device__ inline int attn_nw(int T) { return (T + 31) / 32; }
+__host__ __device__ inline int attn_spb(int T) { int nw = attn_nw(T); return nw >= 4 ? 1 : 4 / nw; }
+__host__ __device__ inline int attn_fwd_per(int T) { return 2 * T * kAttnStride + ((T + 3) & ~3); }   // floats per sample, 16-byte multiple
+inline size_t attn_fwd_smem(int T) { return (size_t)attn_spb(T) * attn_fwd_per(T) * 4; }
 
-template <int NJ>
+__device__ __forceinline__ float dot40(const float4 (&q)[10], const float* __restrict__ row) {
+  float d = 0.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) d += f4_dot(q[i], ld4(row + 4 * i));
+  return d;
+}
+
 __global__ void __launch_bounds__(256)
 k_attn_fwd(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
-           const float* __restrict__ QIN, const int* __restrict__ mask, float* __restrict__ Y, int T) {
+           const float* __restrict__ QIN, const int* __restrict__ mask, float* __restrict__ Y, float* __restrict__ ML,
+           int B, int T) {
   extern __shared__ __align__(16) float sm[];
-  const int Tp = attn_tp(T);
-  float* Ks = sm;
-  float* Vs = Ks + T * kAttnStride;
-  float* Qs = Vs + T * kAttnStride;
-  float* Ps = Qs + T * kAttnStride;
-  int* mk = reinterpret_cast<int*>(Ps + 8 * Tp);
-  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const int64_t base = (int64_t)blockIdx.x * T;
-  for (int i = tid; i < T * 10; i += 256) {
-    int r = i / 10, c = i % 10;
-    st4(Ks + r * kAttnStride + 4 * c, ld4(K + (base + r) * kD + 4 * c));
-    st4(Vs + r * kAttnStride + 4 * c, ld4(V + (base + r) * kD + 4 * c));
-    st4(Qs + r * kAttnStride + 4 * c, ld4(Q + (base + r) * kD + 4 * c));
+  const int nw = attn_nw(T), spb = attn_spb(T), tps = nw * 32;
+  const int per = attn_fwd_per(T);                          // floats per sample: K | V | mask
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * spb;
+  const int ns = min(spb, B - b0);
+  for (int i = tid; i < ns * T * 10; i += blockDim.x) {
+    const int sl = i / (T * 10), rc = i % (T * 10), r = rc / 10, c = rc % 10;
+    const int64_t g = ((int64_t)(b0 + sl) * T + r) * kD + 4 * c;
+    float* base = sm + sl * per;
+    st4(base + r * kAttnStride + 4 * c, ld4(K + g));
+    st4(base + T * kAttnStride + r * kAttnStride + 4 * c, ld4(V + g));
   }
-  for (int i = tid; i < T; i += 256) mk[i] = mask[base + i];
+  for (int i = tid; i < ns * T; i += blockDim.x) {
+    const int sl = i / T, r = i % T;
+    reinterpret_cast<int*>(sm + sl * per + 2 * T * kAttnStride)[r] = mask[(int64_t)(b0 + sl) * T + r];
+  }
   __syncthreads();
+  const int sl = tid / tps, t = tid % tps;
+  if (sl >= ns || t >= T) return;
+  const float* Ks = sm + sl * per;
+  const float* Vs = Ks + T * kAttnStride;
+  const int* mk = reinterpret_cast<const int*>(Vs + T * kAttnStride);
+  const int64_t row = ((int64_t)(b0 + sl) * T + t) * kD;
+  float4 q[10], o[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) { q[i] = ld4(Q + row + 4 * i); o[i] = f4_zero(); }
   const float scale = sqrtf((float)kD);
-  float* pw = Ps + w * Tp;
-  const int jg = lane / 10, c = lane % 10;
-  for (int t = w; t < T; t += 8) {
-    float4 q[10];
+  float m = -INFINITY, l = 0.f;
+  for (int j0 = 0; j0 < T; j0 += kAttnCh) {
+    float sc[kAttnCh];
+    float cm = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 10; ++i) q[i] = ld4(Qs + t * kAttnStride + 4 * i);
-    float s[NJ];
-    float m = -INFINITY;
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      int j = jj * 32 + lane;
+    for (int jj = 0; jj < kAttnCh; ++jj) {
+      const int j = j0 + jj;
       float val = -INFINITY;
       if (j < T) {
-        float d = 0.f;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) d += f4_dot(q[i], ld4(Ks + j * kAttnStride + 4 * i));
+        const float d = dot40(q, Ks + j * kAttnStride);
         val = mk[j] ? d / scale : kMaskNeg;
       }
-      s[jj] = val;
-      m = fmaxf(m, val);
+      sc[jj] = val;
+      cm = fmaxf(cm, val);
     }
-    m = warp_max(m);
-    float sum = 0.f;
+    const float mn = fmaxf(m, cm);
+    const float corr = expf(m - mn);                       // first chunk: exp(-inf) = 0 on empty accumulators
+    l *= corr;
 #pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      int j = jj * 32 + lane;
-      float e = (j < T) ? expf(s[jj] - m) : 0.f;
-      s[jj] = e;
-      sum += e;
-    }
-    sum = warp_sum(sum);
+    for (int i = 0; i < 10; ++i) { o[i].x *= corr; o[i].y *= corr; o[i].z *= corr; o[i].w *= corr; }
 #pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      int j = jj * 32 + lane;
-      if (j < T) pw[j] = s[jj] / sum;
+    for (int jj = 0; jj < kAttnCh; ++jj) {
+      const int j = j0 + jj;
+      if (j < T) {
+        const float pj = expf(sc[jj] - mn);
+        l += pj;
+        const float* vr = Vs + j * kAttnStride;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) f4_fma(o[i], pj, ld4(vr + 4 * i));
+      }
     }
-    __syncwarp();
-    float4 acc = f4_zero();
-    if (lane < 30)
-      for (int j = jg; j < T; j += 3) f4_fma(acc, pw[j], ld4(Vs + j * kAttnStride + 4 * c));
-    float4 a1 = f4_shfl_down(acc, 10), a2 = f4_shfl_down(acc, 20);
-    if (lane < 10) {
-      float4 r = ld4(QIN + (base + t) * kD + 4 * c);
-      acc.x += a1.x + a2.x + r.x; acc.y += a1.y + a2.y + r.y; acc.z += a1.z + a2.z + r.z; acc.w += a1.w + a2.w + r.w;
-      st4(Y + (base + t) * kD + 4 * c, acc);
-    }
-    __syncwarp();
+    m = mn;
   }
+  const float inv = 1.0f / l;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const float4 r = ld4(QIN + row + 4 * i);
+    st4(Y + row + 4 * i, make_float4(fmaf(o[i].x, inv, r.x), fmaf(o[i].y, inv, r.y), fmaf(o[i].z, inv, r.z), fmaf(o[i].w, inv, r.w)));
+  }
+  ML[2 * ((int64_t)(b0 + sl) * T + t)] = m;
+  ML[2 * ((int64_t)(b0 + sl) * T + t) + 1] = l;
 }
 
-template <int NJ>
-static void attn_fwd_nj(const float* Q, const float* K, const float* V, const float* QIN, const int* mask, float* Y, int B,
-                        int T, size_t smem, cudaStream_t st) {
-  static size_t smem_set = 0;
-  if (smem > smem_set) { cudaFuncSetAttribute(k_attn_fwd<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); smem_set = smem; }
-  k_attn_fwd<NJ><<<B, 256, smem, st>>>(Q, K, V, QIN, mask, Y, T);
-}
-void launch_attn_fwd(const float* Q, const float* K, const float* V, const float* QIN, const int* mask, float* Y, int B,
-                     int T, cudaStream_t st) {
+void launch_attn_fwd(const float* Q, const float* K, const float* V, const float* QIN, const int* mask, float* Y, float* ML,
+                     int B, int T, cudaStream_t st) {
   PAMREC_PROF("attn_fwd", 1, st);
   if (B == 0) return;
-  size_t smem = attn_fwd_smem(T);
-  switch ((T + 31) / 32) {
-    case 1: attn_fwd_nj<1>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
-    case 2: attn_fwd_nj<2>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
-    case 3: attn_fwd_nj<3>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
-    case 4: attn_fwd_nj<4>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
-    case 5: attn_fwd_nj<5>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
-    case 6: attn_fwd_nj<6>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
-    case 7: attn_fwd_nj<7>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
-    default: attn_fwd_nj<8>(Q, K, V, QIN, mask, Y, B, T, smem, st); break;
-  }
+  static size_t smem_set = 0;
+  const size_t smem = attn_fwd_smem(T);
+  if (smem > smem_set) { cudaFuncSetAttribute(k_attn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); smem_set = smem; }
+  const int spb = attn_spb(T), threads = spb * attn_nw(T) * 32;
+  k_attn_fwd<<<(B + spb - 1) / spb, threads, smem, st>>>(Q, K, V, QIN, mask, Y, ML, B, T);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -582,164 +587,114 @@ void launch_ffn_bwd(const float* Y, const float* dOUT, const float* W1, const fl
 }
 
 // ------------------------------------------------------------------------------------------
-// Attention backward.  In: Q, K, V, dY (grad of y = P V + qin).  Out: dQ, dK, dV.
-// Pass A (warp per query row) recomputes the softmax row, forms dS and dQ; pass B (warp per
-// key) recomputes the column from the saved row statistics and forms dK, dV.
-inline size_t attn_bwd_smem(int T) { return (size_t)(4 * T * kAttnStride + 16 * attn_tp(T) + 3 * T) * 4 + (size_t)T * 4; }
+// Attention backward.  In: Q, K, V, dY (grad of y = P V + qin), the forward's y, qin and row statistics (m, l).
+// Out: dQ, dK, dV.  Same thread mapping as the forward: with D_t = dy_t . (y_t - qin_t) (= sum_j p_tj dP_tj) known
+// up front, pass A (thread == query row t) forms dQ_t in one sweep over the keys and pass B (thread == key j) forms
+// dK_j and dV_j in one sweep over the queries; both recompute p = exp(s - m_t) / l_t from the saved statistics, all
+// shared-memory reads are warp-wide broadcasts.
+inline size_t attn_bwd_smem(int T) { return (size_t)attn_spb(T) * ((size_t)4 * T * kAttnStride + 4 * T) * 4; }
 
-template <int NJ>
 __global__ void __launch_bounds__(256)
 k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
-           const float* __restrict__ dY, const int* __restrict__ mask, float* __restrict__ dQ, float* __restrict__ dK,
-           float* __restrict__ dV, int T) {
+           const float* __restrict__ dY, const float* __restrict__ Y, const float* __restrict__ QIN,
+           const float* __restrict__ ML, const int* __restrict__ mask, float* __restrict__ dQ, float* __restrict__ dK,
+           float* __restrict__ dV, int B, int T) {
   extern __shared__ __align__(16) float sm[];
-  const int Tp = attn_tp(T);
-  float* Ks = sm;
-  float* Vs = Ks + T * kAttnStride;
-  float* Qs = Vs + T * kAttnStride;
-  float* Gs = Qs + T * kAttnStride;
-  float* Ps = Gs + T * kAttnStride;   // 8 x Tp
-  float* Ds = Ps + 8 * Tp;            // 8 x Tp
-  float* rowm = Ds + 8 * Tp;
-  float* rowl = rowm + T;
-  float* rowD = rowl + T;
-  int* mk = reinterpret_cast<int*>(rowD + T);
-  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const int64_t base = (int64_t)blockIdx.x * T;
-  for (int i = tid; i < T * 10; i += 256) {
-    int r = i / 10, c = i % 10;
-    st4(Ks + r * kAttnStride + 4 * c, ld4(K + (base + r) * kD + 4 * c));
-    st4(Vs + r * kAttnStride + 4 * c, ld4(V + (base + r) * kD + 4 * c));
-    st4(Qs + r * kAttnStride + 4 * c, ld4(Q + (base + r) * kD + 4 * c));
-    st4(Gs + r * kAttnStride + 4 * c, ld4(dY + (base + r) * kD + 4 * c));
+  const int nw = attn_nw(T), spb = attn_spb(T), tps = nw * 32;
+  const int TS = T * kAttnStride;
+  const int per = 4 * TS + 4 * T;                           // K | V | Q | dY | m | l | D | mask
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * spb;
+  const int ns = min(spb, B - b0);
+  for (int i = tid; i < ns * T * 10; i += blockDim.x) {
+    const int sl = i / (T * 10), rc = i % (T * 10), r = rc / 10, c = rc % 10;
+    const int64_t g = ((int64_t)(b0 + sl) * T + r) * kD + 4 * c;
+    float* base = sm + sl * per + r * kAttnStride + 4 * c;
+    st4(base, ld4(K + g));
+    st4(base + TS, ld4(V + g));
+    st4(base + 2 * TS, ld4(Q + g));
+    st4(base + 3 * TS, ld4(dY + g));
   }
-  for (int i = tid; i < T; i += 256) mk[i] = mask[base + i];
+  const int sl = tid / tps, t = tid % tps;
+  const bool active = sl < ns && t < T;
+  float* S = sm + sl * per;
+  if (active) {
+    const int64_t tok = (int64_t)(b0 + sl) * T + t;
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const float4 g = ld4(dY + tok * kD + 4 * i), y = ld4(Y + tok * kD + 4 * i), r = ld4(QIN + tok * kD + 4 * i);
+      d = fmaf(g.x, y.x - r.x, d); d = fmaf(g.y, y.y - r.y, d); d = fmaf(g.z, y.z - r.z, d); d = fmaf(g.w, y.w - r.w, d);
+    }
+    S[4 * TS + t] = ML[2 * tok];
+    S[4 * TS + T + t] = ML[2 * tok + 1];
+    S[4 * TS + 2 * T + t] = d;
+    reinterpret_cast<int*>(S + 4 * TS + 3 * T)[t] = mask[tok];
+  }
   __syncthreads();
+  if (!active) return;
+  const float* Ks = S;
+  const float* Vs = S + TS;
+  const float* Qs = S + 2 * TS;
+  const float* Gs = S + 3 * TS;
+  const float* rm = S + 4 * TS;
+  const float* rl = rm + T;
+  const float* rD = rl + T;
+  const int* mk = reinterpret_cast<const int*>(rD + T);
   const float scale = sqrtf((float)kD);
-  float* pw = Ps + w * Tp;
-  float* dw = Ds + w * Tp;
-  const int jg = lane / 10, c = lane % 10;
-  // ---- pass A
-  for (int t = w; t < T; t += 8) {
-    float4 q[10], g[10];
+  const int64_t row = ((int64_t)(b0 + sl) * T + t) * kD;
+  // ---- pass A: dQ_t
+  {
+    float4 q[10], g[10], acc[10];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) { q[i] = ld4(Qs + t * kAttnStride + 4 * i); g[i] = ld4(Gs + t * kAttnStride + 4 * i); }
-    float s[NJ], dp[NJ];
-    float m = -INFINITY;
+    for (int i = 0; i < 10; ++i) { q[i] = ld4(Qs + t * kAttnStride + 4 * i); g[i] = ld4(Gs + t * kAttnStride + 4 * i); acc[i] = f4_zero(); }
+    const float mt = rm[t], il = 1.0f / rl[t], Dt = rD[t];
+#pragma unroll 2
+    for (int j = 0; j < T; ++j) {
+      if (mk[j]) {                                         // masked keys: p > 0 but dS = 0 (constant score)
+        const float* kr = Ks + j * kAttnStride;
+        const float sv = dot40(q, kr) / scale;
+        const float p = expf(sv - mt) * il;
+        const float dp = dot40(g, Vs + j * kAttnStride);
+        const float ds = p * (dp - Dt) / scale;
 #pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      int j = jj * 32 + lane;
-      float val = -INFINITY, dpv = 0.f;
-      if (j < T) {
-        float d = 0.f;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) d += f4_dot(q[i], ld4(Ks + j * kAttnStride + 4 * i));
-        val = mk[j] ? d / scale : kMaskNeg;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) dpv += f4_dot(g[i], ld4(Vs + j * kAttnStride + 4 * i));
+        for (int i = 0; i < 10; ++i) f4_fma(acc[i], ds, ld4(kr + 4 * i));
       }
-      s[jj] = val; dp[jj] = dpv;
-      m = fmaxf(m, val);
     }
-    m = warp_max(m);
-    float sum = 0.f;
 #pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      int j = jj * 32 + lane;
-      float e = (j < T) ? expf(s[jj] - m) : 0.f;
-      s[jj] = e;
-      sum += e;
-    }
-    sum = warp_sum(sum);
-    float Dv = 0.f;
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      int j = jj * 32 + lane;
-      float p = (j < T) ? s[jj] / sum : 0.f;
-      s[jj] = p;
-      Dv = fmaf(p, dp[jj], Dv);
-    }
-    Dv = warp_sum(Dv);
-    if (lane == 0) { rowm[t] = m; rowl[t] = sum; rowD[t] = Dv; }
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      int j = jj * 32 + lane;
-      if (j < T) pw[j] = mk[j] ? s[jj] * (dp[jj] - Dv) / scale : 0.f;
-    }
-    __syncwarp();
-    float4 acc = f4_zero();
-    if (lane < 30)
-      for (int j = jg; j < T; j += 3) f4_fma(acc, pw[j], ld4(Ks + j * kAttnStride + 4 * c));
-    float4 a1 = f4_shfl_down(acc, 10), a2 = f4_shfl_down(acc, 20);
-    if (lane < 10) {
-      acc.x += a1.x + a2.x; acc.y += a1.y + a2.y; acc.z += a1.z + a2.z; acc.w += a1.w + a2.w;
-      st4(dQ + (base + t) * kD + 4 * c, acc);
-    }
-    __syncwarp();
+    for (int i = 0; i < 10; ++i) st4(dQ + row + 4 * i, acc[i]);
   }
-  __syncthreads();
-  // ---- pass B
-  for (int j = w; j < T; j += 8) {
-    float4 kj[10], vj[10];
+  // ---- pass B: dK_j, dV_j  (this thread's row index now plays the key)
+  {
+    const int j = t;
+    float4 kj[10], vj[10], ak[10], av[10];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) { kj[i] = ld4(Ks + j * kAttnStride + 4 * i); vj[i] = ld4(Vs + j * kAttnStride + 4 * i); }
+    for (int i = 0; i < 10; ++i) { kj[i] = ld4(Ks + j * kAttnStride + 4 * i); vj[i] = ld4(Vs + j * kAttnStride + 4 * i); ak[i] = f4_zero(); av[i] = f4_zero(); }
     const int mkj = mk[j];
+    for (int tt = 0; tt < T; ++tt) {
+      const float* qr = Qs + tt * kAttnStride;
+      const float* gr = Gs + tt * kAttnStride;
+      const float sv = mkj ? dot40(kj, qr) / scale : kMaskNeg;
+      const float p = expf(sv - rm[tt]) / rl[tt];
+      const float dp = dot40(vj, gr);
+      const float ds = mkj ? p * (dp - rD[tt]) / scale : 0.f;
 #pragma unroll
-    for (int tt = 0; tt < NJ; ++tt) {
-      int t = tt * 32 + lane;
-      if (t < T) {
-        float d = 0.f, dpv = 0.f;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) d += f4_dot(ld4(Qs + t * kAttnStride + 4 * i), kj[i]);
-#pragma unroll
-        for (int i = 0; i < 10; ++i) dpv += f4_dot(ld4(Gs + t * kAttnStride + 4 * i), vj[i]);
-        float sv = mkj ? d / scale : kMaskNeg;
-        float p = expf(sv - rowm[t]) / rowl[t];
-        pw[t] = p;
-        dw[t] = mkj ? p * (dpv - rowD[t]) / scale : 0.f;
-      }
+      for (int i = 0; i < 10; ++i) { f4_fma(ak[i], ds, ld4(qr + 4 * i)); f4_fma(av[i], p, ld4(gr + 4 * i)); }
     }
-    __syncwarp();
-    float4 aK = f4_zero(), aV = f4_zero();
-    if (lane < 30)
-      for (int t = jg; t < T; t += 3) {
-        f4_fma(aK, dw[t], ld4(Qs + t * kAttnStride + 4 * c));
-        f4_fma(aV, pw[t], ld4(Gs + t * kAttnStride + 4 * c));
-      }
-    float4 k1 = f4_shfl_down(aK, 10), k2 = f4_shfl_down(aK, 20);
-    float4 v1 = f4_shfl_down(aV, 10), v2 = f4_shfl_down(aV, 20);
-    if (lane < 10) {
-      aK.x += k1.x + k2.x; aK.y += k1.y + k2.y; aK.z += k1.z + k2.z; aK.w += k1.w + k2.w;
-      aV.x += v1.x + v2.x; aV.y += v1.y + v2.y; aV.z += v1.z + v2.z; aV.w += v1.w + v2.w;
-      st4(dK + (base + j) * kD + 4 * c, aK);
-      st4(dV + (base + j) * kD + 4 * c, aV);
-    }
-    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 10; ++i) { st4(dK + row + 4 * i, ak[i]); st4(dV + row + 4 * i, av[i]); }
   }
 }
 
-template <int NJ>
-static void attn_bwd_nj(const float* Q, const float* K, const float* V, const float* dY, const int* mask, float* dQ, float* dK,
-                        float* dV, int B, int T, size_t smem, cudaStream_t st) {
-  static size_t smem_set = 0;
-  if (smem > smem_set) { cudaFuncSetAttribute(k_attn_bwd<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); smem_set = smem; }
-  k_attn_bwd<NJ><<<B, 256, smem, st>>>(Q, K, V, dY, mask, dQ, dK, dV, T);
-}
-void launch_attn_bwd(const float* Q, const float* K, const float* V, const float* dY, const int* mask, float* dQ,
-                     float* dK, float* dV, int B, int T, cudaStream_t st) {
+void launch_attn_bwd(const float* Q, const float* K, const float* V, const float* dY, const float* Y, const float* QIN,
+                     const float* ML, const int* mask, float* dQ, float* dK, float* dV, int B, int T, cudaStream_t st) {
   PAMREC_PROF("attn_bwd", 1, st);
   if (B == 0) return;
-  size_t smem = attn_bwd_smem(T);
-  switch ((T + 31) / 32) {
-    case 1: attn_bwd_nj<1>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;
-    case 2: attn_bwd_nj<2>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;
-    case 3: attn_bwd_nj<3>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;
-    case 4: attn_bwd_nj<4>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;
-    case 5: attn_bwd_nj<5>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;
-    case 6: attn_bwd_nj<6>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;
-    case 7: attn_bwd_nj<7>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;
-    default: attn_bwd_nj<8>(Q, K, V, dY, mask, dQ, dK, dV, B, T, smem, st); break;
-  }
+  static size_t smem_set = 0;
+  const size_t smem = attn_bwd_smem(T);
+  if (smem > smem_set) { cudaFuncSetAttribute(k_attn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); smem_set = smem; }
+  const int spb = attn_spb(T), threads = spb * attn_nw(T) * 32;
+  k_attn_bwd<<<(B + spb - 1) / spb, threads, smem, st>>>(Q, K, V, dY, Y, QIN, ML, mask, dQ, dK, dV, B, T);
 }
 
 // ------------------------------------------------------------------------------------------

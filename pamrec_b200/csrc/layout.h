@@ -167,6 +167,7 @@ struct Layout {
     for (int b = 0; b < 2; ++b) {
       std::string p = "blk" + std::to_string(b) + ".";
       for (const char* n : {"qin", "Q", "K", "V", "y", "out"}) add_ws(p + n, PAMREC_F32, {B, T, kD});
+      add_ws(p + "ml", PAMREC_F32, {B, T, 2});   // softmax row maximum and row sum, kept for the backward pass
     }
     add_ws("z1", PAMREC_F32, {B, T, 20});
     add_ws("z2", PAMREC_F32, {B, T});
