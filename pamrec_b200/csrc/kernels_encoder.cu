@@ -196,22 +196,57 @@ __device__ __forceinline__ void tile_colsum_atomic(const float* __restrict__ G, 
   for (int r = 0; r < cnt; ++r) s += G[r * kRowPad + tid];
   atomicAdd(db + tid, s);
 }
-// cooperative load of `cnt` token rows (global, 40 floats each) into a stride-41 tile
+// cooperative load of `cnt` token rows (global, 40 floats each) into a stride-41 tile.  All ten 16-byte loads of a
+// thread are issued before the first shared-memory store: the tile arrives after ONE memory round trip instead of ten.
+constexpr int kTileIt = (kTokTile * 10 + kTokTile - 1) / kTokTile;   // float4 per thread for a full tile (= 10)
 __device__ __forceinline__ void load_tile_perm(float* __restrict__ dst, const float* __restrict__ src, const int* toks,
                                                int cnt, int tid) {
-  for (int i = tid; i < cnt * 10; i += kTokTile) {
-    int r = i / 10, c = i % 10;
-    float4 v = ld4(src + (int64_t)toks[r] * kD + 4 * c);
-    float* d = dst + r * kRowPad + 4 * c;
-    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  float4 v[kTileIt];
+#pragma unroll
+  for (int it = 0; it < kTileIt; ++it) {
+    const int i = tid + it * kTokTile;
+    if (i < cnt * 10) v[it] = ld4(src + (int64_t)toks[i / 10] * kD + 4 * (i % 10));
+  }
+#pragma unroll
+  for (int it = 0; it < kTileIt; ++it) {
+    const int i = tid + it * kTokTile;
+    if (i < cnt * 10) {
+      float* d = dst + (i / 10) * kRowPad + 4 * (i % 10);
+      d[0] = v[it].x; d[1] = v[it].y; d[2] = v[it].z; d[3] = v[it].w;
+    }
   }
 }
 __device__ __forceinline__ void load_tile_lin(float* __restrict__ dst, const float* __restrict__ src, int cnt, int tid) {
-  for (int i = tid; i < cnt * 10; i += kTokTile) {
-    int r = i / 10, c = i % 10;
-    float4 v = ld4(src + (int64_t)r * kD + 4 * c);
-    float* d = dst + r * kRowPad + 4 * c;
-    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  float4 v[kTileIt];
+#pragma unroll
+  for (int it = 0; it < kTileIt; ++it) {
+    const int i = tid + it * kTokTile;
+    if (i < cnt * 10) v[it] = ld4(src + 4 * (int64_t)i);          // rows are contiguous: element i is float4 number i
+  }
+#pragma unroll
+  for (int it = 0; it < kTileIt; ++it) {
+    const int i = tid + it * kTokTile;
+    if (i < cnt * 10) {
+      float* d = dst + (i / 10) * kRowPad + 4 * (i % 10);
+      d[0] = v[it].x; d[1] = v[it].y; d[2] = v[it].z; d[3] = v[it].w;
+    }
+  }
+}
+// n_mat 40x40 matrices (contiguous in smem, each from its own global pointer) with batched loads
+__device__ __forceinline__ void load_mats(float* __restrict__ dst, const float* __restrict__ m0, const float* __restrict__ m1,
+                                          const float* __restrict__ m2, int n_mat, int tid) {
+  constexpr int IT = (3 * (kDD / 4) + kTokTile - 1) / kTokTile;      // 10
+  float4 v[IT];
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int i = tid + it * kTokTile;
+    const int m = i / (kDD / 4), j = i % (kDD / 4);
+    if (m < n_mat) v[it] = ld4((m == 0 ? m0 : (m == 1 ? m1 : m2)) + 4 * j);
+  }
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int i = tid + it * kTokTile;
+    if (i / (kDD / 4) < n_mat) st4(dst + 4 * i, v[it]);
   }
 }
 __device__ __forceinline__ void store_row(float* __restrict__ dst, const float (&acc)[kD]) {
@@ -249,11 +284,7 @@ k_proj_fwd(const float* __restrict__ X, const int* __restrict__ perm, const int*
   __shared__ int toks[kTokTile];
   const int tid = threadIdx.x;
   const int k = tile_bucket[tile], begin = tile_begin[tile], cnt = tile_count[tile];
-  for (int i = tid; i < 3 * (kDD / 4); i += kTokTile) {
-    int m = i / (kDD / 4), j = i % (kDD / 4);
-    const float* src = (m == 0 ? Wq : (m == 1 ? Wk : Wv)) + (int64_t)k * kDD;
-    st4(Ws + m * kDD + 4 * j, ld4(src + 4 * j));
-  }
+  load_mats(Ws, Wq + (int64_t)k * kDD, Wk + (int64_t)k * kDD, Wv + (int64_t)k * kDD, 3, tid);
   if (tid < kD) { lnp[tid] = ln_beta[tid]; lnp[kD + tid] = ln_gamma[tid]; }
   if (tid < cnt) toks[tid] = perm[begin + tid];
   __syncthreads();
@@ -321,11 +352,16 @@ __host__ __device__ inline int attn_spb(int T) { int nw = attn_nw(T); return nw 
 __host__ __device__ inline int attn_fwd_per(int T) { return 2 * T * kAttnStride + ((T + 3) & ~3); }   // floats per sample, 16-byte multiple
 inline size_t attn_fwd_smem(int T) { return (size_t)attn_spb(T) * attn_fwd_per(T) * 4; }
 
+// 40-wide dot product as four independent FMA chains of ten (a single chain of 40 would serialise on FMA latency)
 __device__ __forceinline__ float dot40(const float4 (&q)[10], const float* __restrict__ row) {
-  float d = 0.f;
+  float4 r = ld4(row);
+  float4 a = make_float4(q[0].x * r.x, q[0].y * r.y, q[0].z * r.z, q[0].w * r.w);
 #pragma unroll
-  for (int i = 0; i < 10; ++i) d += f4_dot(q[i], ld4(row + 4 * i));
-  return d;
+  for (int i = 1; i < 10; ++i) {
+    r = ld4(row + 4 * i);
+    a.x = fmaf(q[i].x, r.x, a.x); a.y = fmaf(q[i].y, r.y, a.y); a.z = fmaf(q[i].z, r.z, a.z); a.w = fmaf(q[i].w, r.w, a.w);
+  }
+  return (a.x + a.y) + (a.z + a.w);
 }
 
 __global__ void __launch_bounds__(256)
@@ -359,7 +395,7 @@ k_attn_fwd(const float* __restrict__ Q, const float* __restrict__ K, const float
   float4 q[10], o[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) { q[i] = ld4(Q + row + 4 * i); o[i] = f4_zero(); }
-  const float scale = sqrtf((float)kD);
+  const float rscale = 1.0f / sqrtf((float)kD);
   float m = -INFINITY, l = 0.f;
   for (int j0 = 0; j0 < T; j0 += kAttnCh) {
     float sc[kAttnCh];
@@ -370,7 +406,7 @@ k_attn_fwd(const float* __restrict__ Q, const float* __restrict__ K, const float
       float val = -INFINITY;
       if (j < T) {
         const float d = dot40(q, Ks + j * kAttnStride);
-        val = mk[j] ? d / scale : kMaskNeg;
+        val = mk[j] ? d * rscale : kMaskNeg;
       }
       sc[jj] = val;
       cm = fmaxf(cm, val);
@@ -430,10 +466,7 @@ k_ffn_fwd(const float* __restrict__ Y, const float* __restrict__ W1, const float
   const int tid = threadIdx.x;
   const int64_t tok0 = (int64_t)blockIdx.x * kTokTile;
   const int cnt = (int)min((int64_t)kTokTile, (int64_t)n_tok - tok0);
-  for (int i = tid; i < kDD / 4; i += kTokTile) {
-    st4(W1s + 4 * i, ld4(W1 + 4 * i));
-    st4(W2s + 4 * i, ld4(W2 + 4 * i));
-  }
+  load_mats(W1s, W1, W2, nullptr, 2, tid);
   if (tid < kD) { pr[tid] = b1[tid]; pr[kD + tid] = b2[tid]; pr[2 * kD + tid] = ln_beta[tid]; pr[3 * kD + tid] = ln_gamma[tid]; }
   load_tile_lin(ys, Y + tok0 * kD, cnt, tid);
   __syncthreads();
@@ -492,10 +525,7 @@ k_ffn_bwd(const float* __restrict__ Y, const float* __restrict__ dOUT, const flo
   const int tid = threadIdx.x, lane = tid & 31;
   const int64_t tok0 = (int64_t)blockIdx.x * kTokTile;
   const int cnt = (int)min((int64_t)kTokTile, (int64_t)n_tok - tok0);
-  for (int i = tid; i < kDD / 4; i += kTokTile) {
-    st4(W1s + 4 * i, ld4(W1 + 4 * i));
-    st4(W2s + 4 * i, ld4(W2 + 4 * i));
-  }
+  load_mats(W1s, W1, W2, nullptr, 2, tid);
   if (tid < kD) { pr[tid] = b1[tid]; pr[2 * kD + tid] = ln_beta[tid]; pr[3 * kD + tid] = ln_gamma[tid]; }
   if (tid < 2 * kD) red[tid] = 0.f;
   load_tile_lin(fs, Y + tok0 * kD, cnt, tid);
@@ -627,7 +657,7 @@ k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float
       d = fmaf(g.x, y.x - r.x, d); d = fmaf(g.y, y.y - r.y, d); d = fmaf(g.z, y.z - r.z, d); d = fmaf(g.w, y.w - r.w, d);
     }
     S[4 * TS + t] = ML[2 * tok];
-    S[4 * TS + T + t] = ML[2 * tok + 1];
+    S[4 * TS + T + t] = 1.0f / ML[2 * tok + 1];
     S[4 * TS + 2 * T + t] = d;
     reinterpret_cast<int*>(S + 4 * TS + 3 * T)[t] = mask[tok];
   }
@@ -638,25 +668,25 @@ k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float
   const float* Qs = S + 2 * TS;
   const float* Gs = S + 3 * TS;
   const float* rm = S + 4 * TS;
-  const float* rl = rm + T;
-  const float* rD = rl + T;
+  const float* ril = rm + T;                               // 1 / row sum
+  const float* rD = ril + T;
   const int* mk = reinterpret_cast<const int*>(rD + T);
-  const float scale = sqrtf((float)kD);
+  const float rscale = 1.0f / sqrtf((float)kD);
   const int64_t row = ((int64_t)(b0 + sl) * T + t) * kD;
   // ---- pass A: dQ_t
   {
     float4 q[10], g[10], acc[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) { q[i] = ld4(Qs + t * kAttnStride + 4 * i); g[i] = ld4(Gs + t * kAttnStride + 4 * i); acc[i] = f4_zero(); }
-    const float mt = rm[t], il = 1.0f / rl[t], Dt = rD[t];
+    const float mt = rm[t], il = ril[t], Dt = rD[t];
 #pragma unroll 2
     for (int j = 0; j < T; ++j) {
       if (mk[j]) {                                         // masked keys: p > 0 but dS = 0 (constant score)
         const float* kr = Ks + j * kAttnStride;
-        const float sv = dot40(q, kr) / scale;
+        const float sv = dot40(q, kr) * rscale;
         const float p = expf(sv - mt) * il;
         const float dp = dot40(g, Vs + j * kAttnStride);
-        const float ds = p * (dp - Dt) / scale;
+        const float ds = p * (dp - Dt) * rscale;
 #pragma unroll
         for (int i = 0; i < 10; ++i) f4_fma(acc[i], ds, ld4(kr + 4 * i));
       }
@@ -674,10 +704,10 @@ k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float
     for (int tt = 0; tt < T; ++tt) {
       const float* qr = Qs + tt * kAttnStride;
       const float* gr = Gs + tt * kAttnStride;
-      const float sv = mkj ? dot40(kj, qr) / scale : kMaskNeg;
-      const float p = expf(sv - rm[tt]) / rl[tt];
+      const float sv = mkj ? dot40(kj, qr) * rscale : kMaskNeg;
+      const float p = expf(sv - rm[tt]) * ril[tt];
       const float dp = dot40(vj, gr);
-      const float ds = mkj ? p * (dp - rD[tt]) / scale : 0.f;
+      const float ds = mkj ? p * (dp - rD[tt]) * rscale : 0.f;
 #pragma unroll
       for (int i = 0; i < 10; ++i) { f4_fma(ak[i], ds, ld4(qr + 4 * i)); f4_fma(av[i], p, ld4(gr + 4 * i)); }
     }
@@ -721,11 +751,7 @@ k_proj_bwd(const float* __restrict__ X, const float* __restrict__ dY, const floa
   __shared__ int toks[kTokTile];
   const int tid = threadIdx.x, lane = tid & 31;
   const int k = tile_bucket[tile], begin = tile_begin[tile], cnt = tile_count[tile];
-  for (int i = tid; i < 3 * (kDD / 4); i += kTokTile) {
-    int m = i / (kDD / 4), j = i % (kDD / 4);
-    const float* src = (m == 0 ? Wq : (m == 1 ? Wk : Wv)) + (int64_t)k * kDD;
-    st4(Ws + m * kDD + 4 * j, ld4(src + 4 * j));
-  }
+  load_mats(Ws, Wq + (int64_t)k * kDD, Wk + (int64_t)k * kDD, Wv + (int64_t)k * kDD, 3, tid);
   if (tid < kD) { lnp[tid] = ln_beta[tid]; lnp[kD + tid] = ln_gamma[tid]; }
   if (tid < 2 * kD) red[tid] = 0.f;
   if (tid < cnt) toks[tid] = perm[begin + tid];
