@@ -9,6 +9,7 @@
 // bucket-sorted first so that a CTA needs exactly one (Wq,Wk,Wv)[bucket] triple:
 // the reference instead materialises a [B,T,40,40] gather per matrix (pamrec.py:714-728).
 #include "kernels.h"
+#include "mma.cuh"
 
 namespace pamrec {
 
@@ -451,47 +452,146 @@ void launch_attn_fwd(const float* Q, const float* K, const float* V, const float
 }
 
 // ------------------------------------------------------------------------------------------
+// Tensor-core token tiles (mma.cuh).  A CTA owns 128 consecutive tokens, warp w the rows 32w .. 32w+31; activation
+// tiles live in shared memory with row stride 44 (16-byte aligned rows; the m16n8k8 A-fragment pattern (row g, column t)
+// maps to banks 12g + t: conflict free), 40x40 weights as TF32 hi / lo halves with their natural stride 40.
+constexpr int kTS = 44;
+// split a 40x40 fp32 matrix into TF32 halves in shared memory
+__device__ __forceinline__ void load_split_mat(uint32_t* __restrict__ hi, uint32_t* __restrict__ lo, const float* __restrict__ W,
+                                               int tid) {
+  constexpr int IT = (kDD / 4 + kTokTile - 1) / kTokTile;   // 4
+  float4 v[IT];
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int i = tid + it * kTokTile;
+    if (i < kDD / 4) v[it] = ld4(W + 4 * i);
+  }
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int i = tid + it * kTokTile;
+    if (i < kDD / 4) {
+      uint4 h, l;
+      split_tf32(v[it].x, h.x, l.x); split_tf32(v[it].y, h.y, l.y); split_tf32(v[it].z, h.z, l.z); split_tf32(v[it].w, h.w, l.w);
+      *reinterpret_cast<uint4*>(hi + 4 * i) = h;
+      *reinterpret_cast<uint4*>(lo + 4 * i) = l;
+    }
+  }
+}
+// rows [0, cnt) of a [*, 40] global matrix into a stride-44 tile, rows >= cnt zero-filled; toks == nullptr: consecutive rows
+__device__ __forceinline__ void load_tile44(float* __restrict__ dst, const float* __restrict__ src, const int* toks, int cnt, int tid) {
+  float4 v[kTileIt];
+#pragma unroll
+  for (int it = 0; it < kTileIt; ++it) {
+    const int i = tid + it * kTokTile;
+    const int r = i / 10, c = i % 10;
+    v[it] = f4_zero();
+    if (r < cnt) v[it] = toks ? ld4(src + (int64_t)toks[r] * kD + 4 * c) : ld4(src + 4 * (int64_t)i);
+  }
+#pragma unroll
+  for (int it = 0; it < kTileIt; ++it) {
+    const int i = tid + it * kTokTile;
+    st4(dst + (i / 10) * kTS + 4 * (i % 10), v[it]);
+  }
+}
+// LayerNorm of one stride-44 row held by one lane (pamrec.py:659-662): returns mean / rstd and rewrites the row in place
+// as f = gamma * xhat + beta (kLnWriteF) or as xhat (kLnWriteXhat)
+constexpr int kLnWriteF = 1, kLnWriteXhat = 2;
+__device__ __forceinline__ void ln_row44(float* __restrict__ row, const float* __restrict__ beta, const float* __restrict__ gamma,
+                                         float& mean, float& rstd, int write) {
+  float4 x[10];
+  float sacc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) { x[i] = ld4(row + 4 * i); sacc += (x[i].x + x[i].y) + (x[i].z + x[i].w); }
+  mean = sacc * (1.0f / kD);
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+    v = fmaf(a, a, v); v = fmaf(b, b, v); v = fmaf(c, c, v); v = fmaf(d, d, v);
+  }
+  rstd = 1.0f / sqrtf(v * (1.0f / kD) + kLnEps);
+  if (write == kLnWriteXhat) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+      st4(row + 4 * i, make_float4((x[i].x - mean) * rstd, (x[i].y - mean) * rstd, (x[i].z - mean) * rstd, (x[i].w - mean) * rstd));
+  } else if (write == kLnWriteF) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const float4 g = ld4(gamma + 4 * i), b = ld4(beta + 4 * i);
+      st4(row + 4 * i, make_float4(fmaf(g.x, (x[i].x - mean) * rstd, b.x), fmaf(g.y, (x[i].y - mean) * rstd, b.y),
+                                   fmaf(g.z, (x[i].z - mean) * rstd, b.z), fmaf(g.w, (x[i].w - mean) * rstd, b.w)));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // N1 + F1 forward: f = LN_b(y); out = relu(f W1 + b1) W2 + b2 + f     (pamrec.py:534-535,565-577)
-constexpr int kFfnFwdSmem = (2 * kDD + 2 * kTokTile * kRowPad + 4 * kD) * 4;
+constexpr int kFfnFwdSmem = (4 * kDD + 2 * kTokTile * kTS + 4 * kD) * 4;
 __global__ void __launch_bounds__(kTokTile)
 k_ffn_fwd(const float* __restrict__ Y, const float* __restrict__ W1, const float* __restrict__ b1,
           const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ ln_beta,
           const float* __restrict__ ln_gamma, float* __restrict__ OUT, int n_tok) {
   extern __shared__ __align__(16) float sm[];
-  float* W1s = sm;
-  float* W2s = W1s + kDD;
-  float* ys = W2s + kDD;
-  float* fs = ys + kTokTile * kRowPad;
-  float* pr = fs + kTokTile * kRowPad;   // b1 | b2 | beta | gamma
-  const int tid = threadIdx.x;
+  uint32_t* W1hi = reinterpret_cast<uint32_t*>(sm);
+  uint32_t* W1lo = W1hi + kDD;
+  uint32_t* W2hi = W1lo + kDD;
+  uint32_t* W2lo = W2hi + kDD;
+  float* fs = sm + 4 * kDD;                     // y, then f = LN(y)
+  float* hs = fs + kTokTile * kTS;              // relu(f W1 + b1)
+  float* pr = hs + kTokTile * kTS;              // b1 | b2 | beta | gamma
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int64_t tok0 = (int64_t)blockIdx.x * kTokTile;
   const int cnt = (int)min((int64_t)kTokTile, (int64_t)n_tok - tok0);
-  load_mats(W1s, W1, W2, nullptr, 2, tid);
+  load_split_mat(W1hi, W1lo, W1, tid);
+  load_split_mat(W2hi, W2lo, W2, tid);
   if (tid < kD) { pr[tid] = b1[tid]; pr[kD + tid] = b2[tid]; pr[2 * kD + tid] = ln_beta[tid]; pr[3 * kD + tid] = ln_gamma[tid]; }
-  load_tile_lin(ys, Y + tok0 * kD, cnt, tid);
+  load_tile44(fs, Y + tok0 * kD, nullptr, cnt, tid);
   __syncthreads();
-  if (tid >= cnt) return;
-  float* yr = ys + tid * kRowPad;
-  float* fr = fs + tid * kRowPad;
-  float mean, rstd;
-  row_stats(yr, mean, rstd);
-#pragma unroll
-  for (int i = 0; i < kD; ++i) fr[i] = fmaf(pr[3 * kD + i], (yr[i] - mean) * rstd, pr[2 * kD + i]);
   {
-    float acc[kD];
-#pragma unroll
-    for (int i = 0; i < kD; ++i) acc[i] = pr[i];
-    mv_fwd(fr, W1s, acc);
-#pragma unroll
-    for (int i = 0; i < kD; ++i) yr[i] = fmaxf(acc[i], 0.f);
+    float mean, rstd;
+    ln_row44(fs + tid * kTS, pr + 2 * kD, pr + 3 * kD, mean, rstd, kLnWriteF);  // lane r of warp w normalises row 32w + r
   }
-  {
-    float acc[kD];
+  __syncwarp();
+  const int g = lane >> 2, t = lane & 3;
+  const float* fw = fs + 32 * w * kTS;
+  float* hw = hs + 32 * w * kTS;
+  float c[2][5][4];
 #pragma unroll
-    for (int i = 0; i < kD; ++i) acc[i] = pr[kD + i] + fr[i];
-    mv_fwd(yr, W2s, acc);
-    store_row(OUT + (tok0 + tid) * kD, acc);
-  }
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt) {
+      const float b0 = pr[8 * nt + 2 * t], bb1 = pr[8 * nt + 2 * t + 1];
+      c[mt][nt][0] = b0; c[mt][nt][1] = bb1; c[mt][nt][2] = b0; c[mt][nt][3] = bb1;
+    }
+  warp_gemm_32x40x40<false>(c, [&](int r, int k) { return fw[r * kTS + k]; }, W1hi, W1lo, lane);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt) {
+      const int r = 16 * mt + g, col = 8 * nt + 2 * t;
+      *reinterpret_cast<float2*>(hw + r * kTS + col) = make_float2(fmaxf(c[mt][nt][0], 0.f), fmaxf(c[mt][nt][1], 0.f));
+      *reinterpret_cast<float2*>(hw + (r + 8) * kTS + col) = make_float2(fmaxf(c[mt][nt][2], 0.f), fmaxf(c[mt][nt][3], 0.f));
+    }
+  __syncwarp();
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt) {
+      const int r = 16 * mt + g, col = 8 * nt + 2 * t;
+      const float2 f0 = *reinterpret_cast<const float2*>(fw + r * kTS + col);
+      const float2 f1 = *reinterpret_cast<const float2*>(fw + (r + 8) * kTS + col);
+      const float b0 = pr[kD + col], bb1 = pr[kD + col + 1];
+      c[mt][nt][0] = b0 + f0.x; c[mt][nt][1] = bb1 + f0.y; c[mt][nt][2] = b0 + f1.x; c[mt][nt][3] = bb1 + f1.y;
+    }
+  warp_gemm_32x40x40<false>(c, [&](int r, int k) { return hw[r * kTS + k]; }, W2hi, W2lo, lane);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt) {
+      const int r = 32 * w + 16 * mt + g, col = 8 * nt + 2 * t;
+      if (r < cnt) *reinterpret_cast<float2*>(OUT + (tok0 + r) * kD + col) = make_float2(c[mt][nt][0], c[mt][nt][1]);
+      if (r + 8 < cnt) *reinterpret_cast<float2*>(OUT + (tok0 + r + 8) * kD + col) = make_float2(c[mt][nt][2], c[mt][nt][3]);
+    }
 }
 
 void launch_ffn_fwd(const float* Y, const float* W1, const float* b1, const float* W2, const float* b2,
@@ -504,9 +604,81 @@ void launch_ffn_fwd(const float* Y, const float* W1, const float* b1, const floa
 }
 
 // ------------------------------------------------------------------------------------------
+// shared pieces of the two backward kernels
+// LayerNorm backward in C-fragment layout.  d[mt][nt][4] holds dF (grad wrt f = gamma * xhat + beta) of the warp's 32 rows;
+// xw is the warp's xhat tile, rstd_w its per-row 1/std.  On return d holds dY (grad wrt the LN input); the column sums
+// dbeta = sum dF and dgamma = sum dF * xhat of the warp's rows are added to red[0..39] / red[40..79] (shared memory).
+__device__ __forceinline__ void ln_bwd_frag(float (&d)[2][5][4], const float* __restrict__ xw, const float* __restrict__ rstd_w,
+                                            const float* __restrict__ gamma, float* __restrict__ red, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  float sb[5][2], sg[5][2];
+#pragma unroll
+  for (int nt = 0; nt < 5; ++nt) { sb[nt][0] = sb[nt][1] = sg[nt][0] = sg[nt][1] = 0.f; }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                       // h = 0: row g, h = 1: row g + 8
+      const int r = 16 * mt + g + 8 * h;
+      float m1 = 0.f, m2 = 0.f;
+      float xh[5][2];
+#pragma unroll
+      for (int nt = 0; nt < 5; ++nt) {
+        const int col = 8 * nt + 2 * t;
+        const float2 x = *reinterpret_cast<const float2*>(xw + r * kTS + col);
+        xh[nt][0] = x.x; xh[nt][1] = x.y;
+        const float d0 = d[mt][nt][2 * h], d1 = d[mt][nt][2 * h + 1];
+        sb[nt][0] += d0; sb[nt][1] += d1;
+        sg[nt][0] = fmaf(d0, x.x, sg[nt][0]); sg[nt][1] = fmaf(d1, x.y, sg[nt][1]);
+        const float e0 = d0 * gamma[col], e1 = d1 * gamma[col + 1];
+        m1 += e0 + e1;
+        m2 = fmaf(e0, x.x, m2); m2 = fmaf(e1, x.y, m2);
+      }
+      m1 += __shfl_xor_sync(0xffffffffu, m1, 1); m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
+      m2 += __shfl_xor_sync(0xffffffffu, m2, 1); m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+      m1 *= (1.0f / kD); m2 *= (1.0f / kD);
+      const float rs = rstd_w[r];
+#pragma unroll
+      for (int nt = 0; nt < 5; ++nt) {
+        const int col = 8 * nt + 2 * t;
+        d[mt][nt][2 * h] = rs * (d[mt][nt][2 * h] * gamma[col] - m1 - xh[nt][0] * m2);
+        d[mt][nt][2 * h + 1] = rs * (d[mt][nt][2 * h + 1] * gamma[col + 1] - m1 - xh[nt][1] * m2);
+      }
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float a = sb[nt][j], b = sg[nt][j];
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+      if (g == 0) { atomicAdd(red + 8 * nt + 2 * t + j, a); atomicAdd(red + kD + 8 * nt + 2 * t + j, b); }
+    }
+}
+// store the warp's 32 x 40 C fragments to rows tok0 + r (r < cnt) of a [*, 40] global matrix; toks != nullptr: permuted rows
+__device__ __forceinline__ void store_frag_rows(float* __restrict__ dst, const float (&c)[2][5][4], int64_t tok0, const int* toks,
+                                                int row_base, int cnt, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = row_base + 16 * mt + g + 8 * h;
+      if (r < cnt) {
+        float* o = dst + (toks ? (int64_t)toks[r] : tok0 + r) * kD + 2 * t;
+#pragma unroll
+        for (int nt = 0; nt < 5; ++nt) *reinterpret_cast<float2*>(o + 8 * nt) = make_float2(c[mt][nt][2 * h], c[mt][nt][2 * h + 1]);
+      }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // FFN + LN_b backward.  In: dOUT (grad of block output), Y.  Out: dY, and atomically
-// accumulated dW1, db1, dW2, db2, dbeta, dgamma.
-constexpr int kFfnBwdSmem = (2 * kDD + 4 * kTokTile * kRowPad + 4 * kD + 2 * kD) * 4;
+// accumulated dW1, db1, dW2, db2, dbeta, dgamma.  Five 3xTF32 tensor-core GEMMs per 128-token tile:
+//   h = relu(f W1 + b1) [recomputed],  dH = dOUT W2^T,  dF = dOUT + (dH o relu') W1^T,
+//   [dW2; db2] = [h 1]^T dOUT,  [dW1; db1] = [f 1]^T (dH o relu')      (weight gradients: warp-private 32-token slices,
+//   merged in shared memory, one global atomic per element and CTA).
+constexpr int kFfnBwdSmem = (4 * kDD + 3 * kTokTile * kTS + 2 * 41 * kD + 4 * kD + 2 * kD + kTokTile) * 4;
 __global__ void __launch_bounds__(kTokTile)
 k_ffn_bwd(const float* __restrict__ Y, const float* __restrict__ dOUT, const float* __restrict__ W1,
           const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ ln_beta,
@@ -514,95 +686,138 @@ k_ffn_bwd(const float* __restrict__ Y, const float* __restrict__ dOUT, const flo
           float* __restrict__ dW2, float* __restrict__ db2, float* __restrict__ dbeta, float* __restrict__ dgamma,
           int n_tok) {
   extern __shared__ __align__(16) float sm[];
-  float* W1s = sm;
-  float* W2s = W1s + kDD;
-  float* fs = W2s + kDD;                       // y, then f
-  float* hs = fs + kTokTile * kRowPad;         // relu(f W1 + b1)
-  float* gs = hs + kTokTile * kRowPad;         // dOUT
-  float* ps = gs + kTokTile * kRowPad;         // d(pre-activation)
-  float* pr = ps + kTokTile * kRowPad;         // b1 | - | beta | gamma
-  float* red = pr + 4 * kD;                    // dbeta | dgamma partials
-  const int tid = threadIdx.x, lane = tid & 31;
+  uint32_t* W1hi = reinterpret_cast<uint32_t*>(sm);
+  uint32_t* W1lo = W1hi + kDD;
+  uint32_t* W2hi = W1lo + kDD;
+  uint32_t* W2lo = W2hi + kDD;
+  float* xs = sm + 4 * kDD;                    // y, then xhat
+  float* hs = xs + kTokTile * kTS;             // h = relu(f W1 + b1), later dH o relu'
+  float* gs = hs + kTokTile * kTS;             // dOUT
+  float* acc2 = gs + kTokTile * kTS;           // [41][40]: dW2 rows 0..39, db2 row 40
+  float* acc1 = acc2 + 41 * kD;                // [41][40]: dW1, db1
+  float* pr = acc1 + 41 * kD;                  // b1 | - | beta | gamma
+  float* red = pr + 4 * kD;                    // dbeta | dgamma
+  float* rstd_s = red + 2 * kD;                // per-row 1/std
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
   const int64_t tok0 = (int64_t)blockIdx.x * kTokTile;
   const int cnt = (int)min((int64_t)kTokTile, (int64_t)n_tok - tok0);
-  load_mats(W1s, W1, W2, nullptr, 2, tid);
+  load_split_mat(W1hi, W1lo, W1, tid);
+  load_split_mat(W2hi, W2lo, W2, tid);
   if (tid < kD) { pr[tid] = b1[tid]; pr[2 * kD + tid] = ln_beta[tid]; pr[3 * kD + tid] = ln_gamma[tid]; }
   if (tid < 2 * kD) red[tid] = 0.f;
-  load_tile_lin(fs, Y + tok0 * kD, cnt, tid);
-  load_tile_lin(gs, dOUT + tok0 * kD, cnt, tid);
+  for (int i = tid; i < 2 * 41 * kD; i += kTokTile) acc2[i] = 0.f;
+  load_tile44(xs, Y + tok0 * kD, nullptr, cnt, tid);
+  load_tile44(gs, dOUT + tok0 * kD, nullptr, cnt, tid);
   __syncthreads();
-  float df[kD];
-  float mean = 0.f, rstd = 0.f;
-  const bool active = tid < cnt;
-  float* fr = fs + tid * kRowPad;
-  float* hr = hs + tid * kRowPad;
-  float* gr = gs + tid * kRowPad;
-  float* pp = ps + tid * kRowPad;
-#pragma unroll
-  for (int i = 0; i < kD; ++i) df[i] = 0.f;
-  if (active) {
-    row_stats(fr, mean, rstd);
-#pragma unroll
-    for (int i = 0; i < kD; ++i) fr[i] = fmaf(pr[3 * kD + i], (fr[i] - mean) * rstd, pr[2 * kD + i]);
-    {
-      float acc[kD];
-#pragma unroll
-      for (int i = 0; i < kD; ++i) acc[i] = pr[i];
-      mv_fwd(fr, W1s, acc);
-#pragma unroll
-      for (int i = 0; i < kD; ++i) hr[i] = fmaxf(acc[i], 0.f);
-    }
-    {
-      float dh[kD];
-#pragma unroll
-      for (int i = 0; i < kD; ++i) dh[i] = 0.f;
-      mv_bwd(gr, W2s, dh);
-#pragma unroll
-      for (int i = 0; i < kD; ++i) pp[i] = hr[i] > 0.f ? dh[i] : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < kD; ++i) df[i] = gr[i];
-    mv_bwd(pp, W1s, df);
+  {
+    float mean, rstd;
+    ln_row44(xs + tid * kTS, pr + 2 * kD, pr + 3 * kD, mean, rstd, kLnWriteXhat);
+    rstd_s[tid] = rstd;
   }
-  // LN backward (needs xhat = (y - mean) * rstd: y re-read from global, L2-resident)
-  float m1 = 0.f, m2 = 0.f;
-  float xh[kD];
+  __syncwarp();
+  const float* xw = xs + 32 * w * kTS;
+  float* hw = hs + 32 * w * kTS;
+  const float* gw = gs + 32 * w * kTS;
+  const float* beta = pr + 2 * kD;
+  const float* gamma = pr + 3 * kD;
+  auto f_elem = [&](int r, int k) { return fmaf(gamma[k], xw[r * kTS + k], beta[k]); };
+  float c[2][5][4];
+  // ---- h = relu(f W1 + b1)
 #pragma unroll
-  for (int i = 0; i < kD; ++i) xh[i] = 0.f;
-  if (active) {
-    const float* yg = Y + (tok0 + tid) * kD;
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int j = 0; j < kD / 4; ++j) {
-      float4 v = ld4(yg + 4 * j);
-      xh[4 * j] = (v.x - mean) * rstd; xh[4 * j + 1] = (v.y - mean) * rstd;
-      xh[4 * j + 2] = (v.z - mean) * rstd; xh[4 * j + 3] = (v.w - mean) * rstd;
+    for (int nt = 0; nt < 5; ++nt) {
+      const float b0 = pr[8 * nt + 2 * t], bb1 = pr[8 * nt + 2 * t + 1];
+      c[mt][nt][0] = b0; c[mt][nt][1] = bb1; c[mt][nt][2] = b0; c[mt][nt][3] = bb1;
     }
+  warp_gemm_32x40x40<false>(c, f_elem, W1hi, W1lo, lane);
 #pragma unroll
-    for (int i = 0; i < kD; ++i) {
-      float dxh = df[i] * pr[3 * kD + i];
-      m1 += dxh;
-      m2 = fmaf(dxh, xh[i], m2);
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt) {
+      const int r = 16 * mt + g, col = 8 * nt + 2 * t;
+      *reinterpret_cast<float2*>(hw + r * kTS + col) = make_float2(fmaxf(c[mt][nt][0], 0.f), fmaxf(c[mt][nt][1], 0.f));
+      *reinterpret_cast<float2*>(hw + (r + 8) * kTS + col) = make_float2(fmaxf(c[mt][nt][2], 0.f), fmaxf(c[mt][nt][3], 0.f));
     }
-    m1 *= (1.0f / kD);
-    m2 *= (1.0f / kD);
-    float out[kD];
+  __syncwarp();
+  // ---- dH = dOUT W2^T, masked by relu'
 #pragma unroll
-    for (int i = 0; i < kD; ++i) out[i] = rstd * (df[i] * pr[3 * kD + i] - m1 - xh[i] * m2);
-    store_row(dY + (tok0 + tid) * kD, out);
-  }
-  // dbeta = sum df, dgamma = sum df * xhat  (all lanes take part; inactive lanes carry zeros)
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-  for (int i = 0; i < kD; ++i) {
-    float sb = warp_sum(df[i]);
-    float sg = warp_sum(df[i] * xh[i]);
-    if (lane == 0) { atomicAdd(red + i, sb); atomicAdd(red + kD + i, sg); }
+    for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c[mt][nt][q] = 0.f;
+  warp_gemm_32x40x40<true>(c, [&](int r, int k) { return gw[r * kTS + k]; }, W2hi, W2lo, lane);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt) {
+      const int r = 16 * mt + g, col = 8 * nt + 2 * t;
+      const float2 h0 = *reinterpret_cast<const float2*>(hw + r * kTS + col);
+      const float2 h1 = *reinterpret_cast<const float2*>(hw + (r + 8) * kTS + col);
+      if (!(h0.x > 0.f)) c[mt][nt][0] = 0.f;
+      if (!(h0.y > 0.f)) c[mt][nt][1] = 0.f;
+      if (!(h1.x > 0.f)) c[mt][nt][2] = 0.f;
+      if (!(h1.y > 0.f)) c[mt][nt][3] = 0.f;
+    }
+  // ---- [dW2; db2] += [h 1]^T dOUT over this warp's 32 tokens
+  {
+    float cw[3][5][4];
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cw[mt][nt][q] = 0.f;
+    warp_gemm_tn_48x40(cw, 32, [&](int r, int i) { return i < kD ? hw[r * kTS + i] : (i == kD ? 1.f : 0.f); },
+                       [&](int r, int n) { return gw[r * kTS + n]; }, lane);
+    tn_flush_smem(cw, acc2, lane);
   }
+  __syncwarp();
+  // ---- hs <- dH o relu'
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt) {
+      const int r = 16 * mt + g, col = 8 * nt + 2 * t;
+      *reinterpret_cast<float2*>(hw + r * kTS + col) = make_float2(c[mt][nt][0], c[mt][nt][1]);
+      *reinterpret_cast<float2*>(hw + (r + 8) * kTS + col) = make_float2(c[mt][nt][2], c[mt][nt][3]);
+    }
+  __syncwarp();
+  // ---- dF = dOUT + (dH o relu') W1^T
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt) {
+      const int r = 16 * mt + g, col = 8 * nt + 2 * t;
+      const float2 g0 = *reinterpret_cast<const float2*>(gw + r * kTS + col);
+      const float2 g1 = *reinterpret_cast<const float2*>(gw + (r + 8) * kTS + col);
+      c[mt][nt][0] = g0.x; c[mt][nt][1] = g0.y; c[mt][nt][2] = g1.x; c[mt][nt][3] = g1.y;
+    }
+  warp_gemm_32x40x40<true>(c, [&](int r, int k) { return hw[r * kTS + k]; }, W1hi, W1lo, lane);
+  // ---- [dW1; db1] += [f 1]^T (dH o relu')
+  {
+    float cw[3][5][4];
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cw[mt][nt][q] = 0.f;
+    warp_gemm_tn_48x40(cw, 32, [&](int r, int i) { return i < kD ? f_elem(r, i) : (i == kD ? 1.f : 0.f); },
+                       [&](int r, int n) { return hw[r * kTS + n]; }, lane);
+    tn_flush_smem(cw, acc1, lane);
+  }
+  // ---- LN_b backward, dY out
+  ln_bwd_frag(c, xw, rstd_s + 32 * w, gamma, red, lane);
+  store_frag_rows(dY, c, tok0, nullptr, 32 * w, cnt, lane);
   __syncthreads();
-  tile_outer_atomic(hs, gs, cnt, dW2, tid);
-  tile_outer_atomic(fs, ps, cnt, dW1, tid);
-  tile_colsum_atomic(gs, cnt, db2, tid);
-  tile_colsum_atomic(ps, cnt, db1, tid);
-  if (tid < kD) { atomicAdd(dbeta + tid, red[tid]); atomicAdd(dgamma + tid, red[kD + tid]); }
+  for (int i = tid; i < kDD; i += kTokTile) { atomicAdd(dW2 + i, acc2[i]); atomicAdd(dW1 + i, acc1[i]); }
+  if (tid < kD) {
+    atomicAdd(db2 + tid, acc2[kDD + tid]); atomicAdd(db1 + tid, acc1[kDD + tid]);
+    atomicAdd(dbeta + tid, red[tid]); atomicAdd(dgamma + tid, red[kD + tid]);
+  }
 }
 
 void launch_ffn_bwd(const float* Y, const float* dOUT, const float* W1, const float* b1, const float* W2,
