@@ -268,7 +268,18 @@ __device__ __forceinline__ void row_stats(const float* __restrict__ x, float& me
 
 // ------------------------------------------------------------------------------------------
 // N1 + A1 forward: qin = LN_a(x); Q = qin Wq[k], K = x Wk[k], V = x Wv[k]   (pamrec.py:521-522,714-728)
-constexpr int kProjFwdSmem = (3 * kDD + 2 * kTokTile * kRowPad + 2 * kD) * 4;
+// One bucket-sorted tile of up to 128 tokens per CTA, three 3xTF32 tensor-core GEMMs per warp (32 tokens each).
+// (definitions of kTS, load_split_mat, load_tile44, ln_row44 are further down with the FFN kernels)
+constexpr int kTS = 44;
+__device__ __forceinline__ void load_split_mat(uint32_t* __restrict__ hi, uint32_t* __restrict__ lo, const float* __restrict__ W, int tid);
+__device__ __forceinline__ void load_tile44(float* __restrict__ dst, const float* __restrict__ src, const int* toks, int cnt, int tid);
+constexpr int kLnWriteF = 1, kLnWriteXhat = 2;
+__device__ __forceinline__ void ln_row44(float* __restrict__ row, const float* __restrict__ beta, const float* __restrict__ gamma,
+                                         float& mean, float& rstd, int write);
+__device__ __forceinline__ void store_frag_rows(float* __restrict__ dst, const float (&c)[2][5][4], int64_t tok0, const int* toks,
+                                                int row_base, int cnt, int lane);
+
+constexpr int kProjFwdSmem = (6 * kDD + 2 * kTokTile * kTS + 2 * kD) * 4;
 __global__ void __launch_bounds__(kTokTile)
 k_proj_fwd(const float* __restrict__ X, const int* __restrict__ perm, const int* __restrict__ ctl,
            const int* __restrict__ tile_bucket, const int* __restrict__ tile_begin, const int* __restrict__ tile_count,
@@ -278,53 +289,51 @@ k_proj_fwd(const float* __restrict__ X, const int* __restrict__ perm, const int*
   int tile = blockIdx.x;
   if (tile >= ctl[32]) return;
   extern __shared__ __align__(16) float sm[];
-  float* Ws = sm;
-  float* xs = Ws + 3 * kDD;
-  float* qs = xs + kTokTile * kRowPad;
-  float* lnp = qs + kTokTile * kRowPad;
+  uint32_t* Whi = reinterpret_cast<uint32_t*>(sm);          // q | k | v
+  uint32_t* Wlo = Whi + 3 * kDD;
+  float* xs = sm + 6 * kDD;                                 // x
+  float* qs = xs + kTokTile * kTS;                          // qin = LN_a(x)
+  float* lnp = qs + kTokTile * kTS;                         // beta | gamma
   __shared__ int toks[kTokTile];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int k = tile_bucket[tile], begin = tile_begin[tile], cnt = tile_count[tile];
-  load_mats(Ws, Wq + (int64_t)k * kDD, Wk + (int64_t)k * kDD, Wv + (int64_t)k * kDD, 3, tid);
+  load_split_mat(Whi, Wlo, Wq + (int64_t)k * kDD, tid);
+  load_split_mat(Whi + kDD, Wlo + kDD, Wk + (int64_t)k * kDD, tid);
+  load_split_mat(Whi + 2 * kDD, Wlo + 2 * kDD, Wv + (int64_t)k * kDD, tid);
   if (tid < kD) { lnp[tid] = ln_beta[tid]; lnp[kD + tid] = ln_gamma[tid]; }
   if (tid < cnt) toks[tid] = perm[begin + tid];
   __syncthreads();
-  load_tile_perm(xs, X, toks, cnt, tid);
+  load_tile44(xs, X, toks, cnt, tid);
   __syncthreads();
-  if (tid >= cnt) return;
-  const float* xr = xs + tid * kRowPad;
-  float* qr = qs + tid * kRowPad;
-  float mean, rstd;
-  row_stats(xr, mean, rstd);
-#pragma unroll
-  for (int i = 0; i < kD; ++i) qr[i] = fmaf(lnp[kD + i], (xr[i] - mean) * rstd, lnp[i]);
-  const int64_t tok = toks[tid];
   {
-    float acc[kD];
+    // lane r of warp w: row 32w + r.  qin row -> shared (A operand of the Q GEMM) and -> global
+    float* xr = xs + tid * kTS;
+    float* qr = qs + tid * kTS;
 #pragma unroll
-    for (int i = 0; i < kD; ++i) acc[i] = qr[i];
-    store_row(QIN + tok * kD, acc);
+    for (int i = 0; i < 10; ++i) st4(qr + 4 * i, ld4(xr + 4 * i));
+    float mean, rstd;
+    ln_row44(qr, lnp, lnp + kD, mean, rstd, kLnWriteF);
+    if (tid < cnt) {
+      float* o = QIN + (int64_t)toks[tid] * kD;
+#pragma unroll
+      for (int i = 0; i < 10; ++i) st4(o + 4 * i, ld4(qr + 4 * i));
+    }
   }
-  {
-    float acc[kD];
+  __syncwarp();
+  const float* xw = xs + 32 * w * kTS;
+  const float* qw = qs + 32 * w * kTS;
+#pragma unroll 1
+  for (int m = 0; m < 3; ++m) {
+    float c[2][5][4];
 #pragma unroll
-    for (int i = 0; i < kD; ++i) acc[i] = 0.f;
-    mv_fwd(qr, Ws, acc);
-    store_row(Q + tok * kD, acc);
-  }
-  {
-    float acc[kD];
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int i = 0; i < kD; ++i) acc[i] = 0.f;
-    mv_fwd(xr, Ws + kDD, acc);
-    store_row(K + tok * kD, acc);
-  }
-  {
-    float acc[kD];
+      for (int nt = 0; nt < 5; ++nt)
 #pragma unroll
-    for (int i = 0; i < kD; ++i) acc[i] = 0.f;
-    mv_fwd(xr, Ws + 2 * kDD, acc);
-    store_row(V + tok * kD, acc);
+        for (int q = 0; q < 4; ++q) c[mt][nt][q] = 0.f;
+    const float* aw = m == 0 ? qw : xw;
+    warp_gemm_32x40x40<false>(c, [&](int r, int kk) { return aw[r * kTS + kk]; }, Whi + m * kDD, Wlo + m * kDD, lane);
+    store_frag_rows(m == 0 ? Q : (m == 1 ? K : V), c, 0, toks, 32 * w, cnt, lane);
   }
 }
 
@@ -455,7 +464,6 @@ void launch_attn_fwd(const float* Q, const float* K, const float* V, const float
 // Tensor-core token tiles (mma.cuh).  A CTA owns 128 consecutive tokens, warp w the rows 32w .. 32w+31; activation
 // tiles live in shared memory with row stride 44 (16-byte aligned rows; the m16n8k8 A-fragment pattern (row g, column t)
 // maps to banks 12g + t: conflict free), 40x40 weights as TF32 hi / lo halves with their natural stride 40.
-constexpr int kTS = 44;
 // split a 40x40 fp32 matrix into TF32 halves in shared memory
 __device__ __forceinline__ void load_split_mat(uint32_t* __restrict__ hi, uint32_t* __restrict__ lo, const float* __restrict__ W,
                                                int tid) {
@@ -495,7 +503,6 @@ __device__ __forceinline__ void load_tile44(float* __restrict__ dst, const float
 }
 // LayerNorm of one stride-44 row held by one lane (pamrec.py:659-662): returns mean / rstd and rewrites the row in place
 // as f = gamma * xhat + beta (kLnWriteF) or as xhat (kLnWriteXhat)
-constexpr int kLnWriteF = 1, kLnWriteXhat = 2;
 __device__ __forceinline__ void ln_row44(float* __restrict__ row, const float* __restrict__ beta, const float* __restrict__ gamma,
                                          float& mean, float& rstd, int write) {
   float4 x[10];
@@ -606,9 +613,10 @@ void launch_ffn_fwd(const float* Y, const float* W1, const float* b1, const floa
 // ------------------------------------------------------------------------------------------
 // shared pieces of the two backward kernels
 // LayerNorm backward in C-fragment layout.  d[mt][nt][4] holds dF (grad wrt f = gamma * xhat + beta) of the warp's 32 rows;
-// xw is the warp's xhat tile, rstd_w its per-row 1/std.  On return d holds dY (grad wrt the LN input); the column sums
+// xhat2(r, col) returns xhat[r][col .. col+1] of the warp's rows, rstd_w is their 1/std.  On return d holds dY (grad wrt the LN input); the column sums
 // dbeta = sum dF and dgamma = sum dF * xhat of the warp's rows are added to red[0..39] / red[40..79] (shared memory).
-__device__ __forceinline__ void ln_bwd_frag(float (&d)[2][5][4], const float* __restrict__ xw, const float* __restrict__ rstd_w,
+template <typename XF>
+__device__ __forceinline__ void ln_bwd_frag(float (&d)[2][5][4], XF xhat2, const float* __restrict__ rstd_w,
                                             const float* __restrict__ gamma, float* __restrict__ red, int lane) {
   const int g = lane >> 2, t = lane & 3;
   float sb[5][2], sg[5][2];
@@ -624,7 +632,7 @@ __device__ __forceinline__ void ln_bwd_frag(float (&d)[2][5][4], const float* __
 #pragma unroll
       for (int nt = 0; nt < 5; ++nt) {
         const int col = 8 * nt + 2 * t;
-        const float2 x = *reinterpret_cast<const float2*>(xw + r * kTS + col);
+        const float2 x = xhat2(r, col);                 // xhat[r][col], xhat[r][col + 1]
         xh[nt][0] = x.x; xh[nt][1] = x.y;
         const float d0 = d[mt][nt][2 * h], d1 = d[mt][nt][2 * h + 1];
         sb[nt][0] += d0; sb[nt][1] += d1;
@@ -810,7 +818,7 @@ k_ffn_bwd(const float* __restrict__ Y, const float* __restrict__ dOUT, const flo
     tn_flush_smem(cw, acc1, lane);
   }
   // ---- LN_b backward, dY out
-  ln_bwd_frag(c, xw, rstd_s + 32 * w, gamma, red, lane);
+  ln_bwd_frag(c, [&](int r, int col) { return *reinterpret_cast<const float2*>(xw + r * kTS + col); }, rstd_s + 32 * w, gamma, red, lane);
   store_frag_rows(dY, c, tok0, nullptr, 32 * w, cnt, lane);
   __syncthreads();
   for (int i = tid; i < kDD; i += kTokTile) { atomicAdd(dW2 + i, acc2[i]); atomicAdd(dW1 + i, acc1[i]); }
@@ -943,9 +951,10 @@ void launch_attn_bwd(const float* Q, const float* K, const float* V, const float
 }
 
 // ------------------------------------------------------------------------------------------
-// Projection + LN_a backward (bucket-sorted tiles).  In: X (block input), dY (residual path
-// into qin), dQ, dK, dV.  Out: dX; atomically accumulated dWq/dWk/dWv[bucket], dbeta, dgamma.
-constexpr int kProjBwdSmem = (3 * kDD + 3 * kTokTile * kRowPad + 2 * kD + 2 * kD) * 4;
+// Projection + LN_a backward (bucket-sorted tiles).  In: X (block input), dY (residual path into qin), dQ, dK, dV.
+// Out: dX; atomically accumulated dWq/dWk/dWv[bucket], dbeta, dgamma.  Six 3xTF32 tensor-core GEMMs per tile:
+//   dqin = dY + dQ Wq^T,   dX = dK Wk^T + dV Wv^T + LN_a'(dqin),   dWq = qin^T dQ,  dWk = x^T dK,  dWv = x^T dV.
+constexpr int kProjBwdSmem = (6 * kDD + 2 * kTokTile * kTS + 3 * kDD + 2 * kD + 2 * kD + 2 * kTokTile) * 4;
 __global__ void __launch_bounds__(kTokTile)
 k_proj_bwd(const float* __restrict__ X, const float* __restrict__ dY, const float* __restrict__ dQ,
            const float* __restrict__ dK, const float* __restrict__ dV, const int* __restrict__ perm,
@@ -957,82 +966,107 @@ k_proj_bwd(const float* __restrict__ X, const float* __restrict__ dY, const floa
   int tile = blockIdx.x;
   if (tile >= ctl[32]) return;
   extern __shared__ __align__(16) float sm[];
-  float* Ws = sm;
-  float* xs = Ws + 3 * kDD;
-  float* qs = xs + kTokTile * kRowPad;
-  float* gs = qs + kTokTile * kRowPad;
-  float* lnp = gs + kTokTile * kRowPad;
-  float* red = lnp + 2 * kD;
+  uint32_t* Whi = reinterpret_cast<uint32_t*>(sm);          // q | k | v
+  uint32_t* Wlo = Whi + 3 * kDD;
+  float* xs = sm + 6 * kDD;                                 // x (raw)
+  float* gs = xs + kTokTile * kTS;                          // dQ, then dK, then dV
+  float* acc = gs + kTokTile * kTS;                         // [3][40][40] weight-gradient partial sums of this CTA
+  float* lnp = acc + 3 * kDD;                               // beta | gamma
+  float* red = lnp + 2 * kD;                                // dbeta | dgamma
+  float* mean_s = red + 2 * kD;
+  float* rstd_s = mean_s + kTokTile;
   __shared__ int toks[kTokTile];
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
   const int k = tile_bucket[tile], begin = tile_begin[tile], cnt = tile_count[tile];
-  load_mats(Ws, Wq + (int64_t)k * kDD, Wk + (int64_t)k * kDD, Wv + (int64_t)k * kDD, 3, tid);
+  load_split_mat(Whi, Wlo, Wq + (int64_t)k * kDD, tid);
+  load_split_mat(Whi + kDD, Wlo + kDD, Wk + (int64_t)k * kDD, tid);
+  load_split_mat(Whi + 2 * kDD, Wlo + 2 * kDD, Wv + (int64_t)k * kDD, tid);
   if (tid < kD) { lnp[tid] = ln_beta[tid]; lnp[kD + tid] = ln_gamma[tid]; }
   if (tid < 2 * kD) red[tid] = 0.f;
+  for (int i = tid; i < 3 * kDD; i += kTokTile) acc[i] = 0.f;
   if (tid < cnt) toks[tid] = perm[begin + tid];
   __syncthreads();
-  load_tile_perm(xs, X, toks, cnt, tid);
-  load_tile_perm(gs, dQ, toks, cnt, tid);
+  load_tile44(xs, X, toks, cnt, tid);
+  load_tile44(gs, dQ, toks, cnt, tid);
   __syncthreads();
-  const bool active = tid < cnt;
-  const float* xr = xs + tid * kRowPad;
-  float* qr = qs + tid * kRowPad;
-  const float* gr = gs + tid * kRowPad;
-  float mean = 0.f, rstd = 0.f;
-  float dqin[kD], dx[kD];
-#pragma unroll
-  for (int i = 0; i < kD; ++i) { dqin[i] = 0.f; dx[i] = 0.f; }
-  if (active) {
-    row_stats(xr, mean, rstd);
-#pragma unroll
-    for (int i = 0; i < kD; ++i) qr[i] = fmaf(lnp[kD + i], (xr[i] - mean) * rstd, lnp[i]);
-    mv_bwd(gr, Ws, dqin);
+  {
+    float mean, rstd;
+    ln_row44(xs + tid * kTS, lnp, lnp + kD, mean, rstd, 0);
+    mean_s[tid] = mean; rstd_s[tid] = rstd;
   }
-  __syncthreads();                                   // qs complete
-  tile_outer_atomic(qs, gs, cnt, dWq + (int64_t)k * kDD, tid);
-  __syncthreads();
-  load_tile_perm(gs, dK, toks, cnt, tid);
-  __syncthreads();
-  if (active) mv_bwd(gr, Ws + kDD, dx);
-  tile_outer_atomic(xs, gs, cnt, dWk + (int64_t)k * kDD, tid);
-  __syncthreads();
-  load_tile_perm(gs, dV, toks, cnt, tid);
-  __syncthreads();
-  if (active) mv_bwd(gr, Ws + 2 * kDD, dx);
-  tile_outer_atomic(xs, gs, cnt, dWv + (int64_t)k * kDD, tid);
-  // LN_a backward
-  float xh[kD];
+  __syncwarp();
+  const float* xw = xs + 32 * w * kTS;
+  const float* gw = gs + 32 * w * kTS;
+  const float* mw = mean_s + 32 * w;
+  const float* rw = rstd_s + 32 * w;
+  const float* beta = lnp;
+  const float* gamma = lnp + kD;
+  auto xhat = [&](int r, int i) { return (xw[r * kTS + i] - mw[r]) * rw[r]; };
+  auto g_elem = [&](int r, int kk) { return gw[r * kTS + kk]; };
+  float dqin[2][5][4], dx[2][5][4];
+  // ---- dqin = dY + dQ Wq^T
 #pragma unroll
-  for (int i = 0; i < kD; ++i) xh[i] = 0.f;
-  if (active) {
-    const int64_t tok = toks[tid];
-    const float* yg = dY + tok * kD;
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int j = 0; j < kD / 4; ++j) {
-      float4 v = ld4(yg + 4 * j);
-      dqin[4 * j] += v.x; dqin[4 * j + 1] += v.y; dqin[4 * j + 2] += v.z; dqin[4 * j + 3] += v.w;
+    for (int h = 0; h < 2; ++h) {
+      const int r = 32 * w + 16 * mt + g + 8 * h;
+      const float* src = dY + (int64_t)toks[r < cnt ? r : 0] * kD + 2 * t;
+#pragma unroll
+      for (int nt = 0; nt < 5; ++nt) {
+        const float2 v = r < cnt ? *reinterpret_cast<const float2*>(src + 8 * nt) : make_float2(0.f, 0.f);
+        dqin[mt][nt][2 * h] = v.x; dqin[mt][nt][2 * h + 1] = v.y;
+      }
     }
-    float m1 = 0.f, m2 = 0.f;
+  warp_gemm_32x40x40<true>(dqin, g_elem, Whi, Wlo, lane);
+  {
+    float cw[3][5][4];
 #pragma unroll
-    for (int i = 0; i < kD; ++i) {
-      xh[i] = (xr[i] - mean) * rstd;
-      float dxh = dqin[i] * lnp[kD + i];
-      m1 += dxh;
-      m2 = fmaf(dxh, xh[i], m2);
-    }
-    m1 *= (1.0f / kD);
-    m2 *= (1.0f / kD);
+    for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
-    for (int i = 0; i < kD; ++i) dx[i] += rstd * (dqin[i] * lnp[kD + i] - m1 - xh[i] * m2);
-    store_row(dX + tok * kD, dx);
+      for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cw[mt][nt][q] = 0.f;
+    warp_gemm_tn_48x40(cw, 32, [&](int r, int i) { return i < kD ? fmaf(gamma[i], xhat(r, i), beta[i]) : 0.f; }, g_elem, lane);
+    tn_flush_smem(cw, acc, lane, kD - 1);
   }
+  // ---- dX = dK Wk^T + dV Wv^T (+ LN backward below)
 #pragma unroll
-  for (int i = 0; i < kD; ++i) {
-    float sb = warp_sum(dqin[i]);
-    float sg = warp_sum(dqin[i] * xh[i]);
-    if (lane == 0) { atomicAdd(red + i, sb); atomicAdd(red + kD + i, sg); }
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dx[mt][nt][q] = 0.f;
+#pragma unroll 1
+  for (int m = 1; m < 3; ++m) {
+    __syncthreads();                                    // every warp is done with the previous gradient tile
+    load_tile44(gs, m == 1 ? dK : dV, toks, cnt, tid);
+    __syncthreads();
+    warp_gemm_32x40x40<true>(dx, g_elem, Whi + m * kDD, Wlo + m * kDD, lane);
+    float cw[3][5][4];
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cw[mt][nt][q] = 0.f;
+    warp_gemm_tn_48x40(cw, 32, [&](int r, int i) { return i < kD ? xw[r * kTS + i] : 0.f; }, g_elem, lane);
+    tn_flush_smem(cw, acc + m * kDD, lane, kD - 1);
   }
+  // ---- LN_a backward of dqin, added to dX
+  ln_bwd_frag(dqin, [&](int r, int col) { return make_float2(xhat(r, col), xhat(r, col + 1)); }, rw, gamma, red, lane);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dx[mt][nt][q] += dqin[mt][nt][q];
+  store_frag_rows(dX, dx, 0, toks, 32 * w, cnt, lane);
   __syncthreads();
+  float* dWs[3] = {dWq + (int64_t)k * kDD, dWk + (int64_t)k * kDD, dWv + (int64_t)k * kDD};
+  for (int i = tid; i < kDD; i += kTokTile) {
+    atomicAdd(dWs[0] + i, acc[i]); atomicAdd(dWs[1] + i, acc[kDD + i]); atomicAdd(dWs[2] + i, acc[2 * kDD + i]);
+  }
   if (tid < kD) { atomicAdd(dbeta + tid, red[tid]); atomicAdd(dgamma + tid, red[kD + tid]); }
 }
 

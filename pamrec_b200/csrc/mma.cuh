@@ -99,16 +99,16 @@ __device__ __forceinline__ void warp_gemm_tn_48x40(float (&c)[3][5][4], int n_ro
     }
   }
 }
-// add the 41 x 40 useful part of such an accumulator into a row-major [41][40] shared-memory buffer
-__device__ __forceinline__ void tn_flush_smem(const float (&c)[3][5][4], float* __restrict__ acc, int lane) {
+// add rows 0 .. last_row of such an accumulator into a row-major [last_row + 1][40] shared-memory buffer
+__device__ __forceinline__ void tn_flush_smem(const float (&c)[3][5][4], float* __restrict__ acc, int lane, int last_row = 40) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 5; ++nt) {
       const int r = 16 * mt + g, col = 8 * nt + 2 * t;
-      if (r <= 40) { atomicAdd(acc + r * 40 + col, c[mt][nt][0]); atomicAdd(acc + r * 40 + col + 1, c[mt][nt][1]); }
-      if (r + 8 <= 40) { atomicAdd(acc + (r + 8) * 40 + col, c[mt][nt][2]); atomicAdd(acc + (r + 8) * 40 + col + 1, c[mt][nt][3]); }
+      if (r <= last_row) { atomicAdd(acc + r * 40 + col, c[mt][nt][0]); atomicAdd(acc + r * 40 + col + 1, c[mt][nt][1]); }
+      if (r + 8 <= last_row) { atomicAdd(acc + (r + 8) * 40 + col, c[mt][nt][2]); atomicAdd(acc + (r + 8) * 40 + col + 1, c[mt][nt][3]); }
     }
 }
 
