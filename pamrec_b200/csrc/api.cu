@@ -163,7 +163,7 @@ static BnSet make_bn(PamrecHandle h, int id, const char* name) {
   s.dgamma = h->G(o.gamma); s.dbeta = h->G(o.beta);
   s.mmean = h->buf.bn_moving + o.mm; s.mvar = h->buf.bn_moving + o.mv;
   std::string p = std::string("bn.") + name;
-  s.sums = h->wd(p + ".sums"); s.stat = h->wf(p + ".stat"); s.bsums = h->wd(p + ".bsums");
+  s.sums = h->wd(p + ".sums"); s.stat = h->wf(p + ".stat"); s.bsums = h->wd("bn.bsums") + h->L.bn_bsums_off[id];
   return s;
 }
 
@@ -536,19 +536,28 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   cudaMemsetAsync(h->wd("sp_normsq"), 0, 8 * sizeof(double), st);
   launch_loss(h->wf("logits"), b->labels_satisfied, b->labels_play, b->plays, h->wf("d_logits"), h->wd("loss_acc"), B, Bg,
               W > 1 ? h->wd("dp.scalars") : nullptr, h->cfg.fuzhu_weight, h->cfg.order_weight, st); nl += 1;
-  // batch-norm backward of one or two sets: column sums, (data parallel) sum over ranks, then the apply pass
-  struct BnJob { int id; float* dA; const float* Z; };
-  auto bn_bwd_n = [&](std::initializer_list<BnJob> jobs, int M, double cnt) {
-    for (const BnJob& j : jobs) launch_bn_bwd_stats(bn[j.id], j.dA, j.Z, M, st);
-    if (W > 1 && !crc) {
-      PAMREC_PROF("allreduce_bn_bwd", 1, st);
-      crc |= h->comm.group_start();
-      for (const BnJob& j : jobs) crc |= h->comm.all_reduce(bn[j.id].bsums, 2 * (int64_t)bn[j.id].C, COMM_F64, st);
-      crc |= h->comm.group_end();
-    }
-    for (const BnJob& j : jobs) { launch_bn_bwd_apply(bn[j.id], j.dA, j.Z, M, cnt, gs, st); nl += 3; }
+  // Batch-norm backward is folded into the dense kernels (common.cuh: BnGrad / BnGradOut): the kernel that produces a
+  // gradient buffer also accumulates the two column sums of its layer's BN, the consumers turn dA into dz while loading.
+  // Buffers produced by the mixing / pooling kernels get their sums from k_bn_bwd_stats.  Data parallel: sums over ranks.
+  cudaMemsetAsync(h->wd("bn.bsums"), 0, (size_t)L.ws[L.ws_index.at("bn.bsums")].numel * sizeof(double), st);
+  auto sync_bsums = [&](std::initializer_list<int> ids) {
+    if (W == 1 || crc) return;
+    PAMREC_PROF("allreduce_bn_bwd", 1, st);
+    crc |= h->comm.group_start();
+    for (int id : ids) crc |= h->comm.all_reduce(bn[id].bsums, 2 * (int64_t)bn[id].C, COMM_F64, st);
+    crc |= h->comm.group_end();
   };
-  auto bn_bwd = [&](int id, float* dA, const float* Z, int M, double cnt) { bn_bwd_n({{id, dA, Z}}, M, cnt); };
+  auto grad_of = [&](int id, const float* Z, double cnt) {
+    BnGrad g; g.Z = Z; g.stat = bn[id].stat; g.gamma = bn[id].gamma; g.beta = bn[id].beta; g.bsums = bn[id].bsums; g.count = cnt;
+    return g;
+  };
+  auto out_of = [&](int id, const float* Z) {
+    BnGradOut o; o.Z = Z; o.stat = bn[id].stat; o.gamma = bn[id].gamma; o.beta = bn[id].beta; o.bsums = bn[id].bsums;
+    return o;
+  };
+  auto dw_bn = [&](DenseDwP& w, int id, const float* Z, double cnt) {
+    w.g = grad_of(id, Z, cnt); w.g_dgamma = bn[id].dgamma; w.g_dbeta = bn[id].dbeta; w.g_C = bn[id].C; w.g_scale = gs;
+  };
   // ---- towers
   {
     DenseDwP w = dw_p(h->wf("zt1"), 192, B, 3, 64, 1, h->wf("d_logits"), 3, h->G(L.tower.wout), 64, h->G(L.tower.bout), 1);
@@ -557,26 +566,32 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
     launch_dense_dw(w, st);
     DenseDxP x = dx_p(h->wf("d_logits"), 3, B, 64, Pb, h->wf("d_t1"), 192, 0);
     for (int g = 0; g < 3; ++g) dx_add(x, g, g * 64, g, L.tower.wout + g * 64, 1);
+    x.o = out_of(BN_T1, h->wf("zt1"));
     launch_dense_dx(x, st);
     nl += 2;
-    bn_bwd(BN_T1, h->wf("d_t1"), h->wf("zt1"), B, cntB);
+    sync_bsums({BN_T1});
     DenseDwP w1 = dw_p(h->wf("zt0"), 300, B, 3, 100, 64, h->wf("d_t1"), 192, h->G(L.tower.w1), 6400, h->G(L.tower.b1), 64);
     for (int g = 0; g < 3; ++g) { w1.x_off[g] = g * 100; w1.z_off[g] = g * 64; }
     set_in_bn_dw(w1, bn[BN_T0]);
+    dw_bn(w1, BN_T1, h->wf("zt1"), cntB);
     launch_dense_dw(w1, st);
     DenseDxP x1 = dx_p(h->wf("d_t1"), 192, B, 100, Pb, h->wf("d_t0"), 300, 0);
     for (int g = 0; g < 3; ++g) dx_add(x1, g, g * 100, g * 64, L.tower.w1 + (int64_t)g * 6400, 64);
+    x1.g = grad_of(BN_T1, h->wf("zt1"), cntB);
+    x1.o = out_of(BN_T0, h->wf("zt0"));
     launch_dense_dx(x1, st);
     nl += 2;
-    bn_bwd(BN_T0, h->wf("d_t0"), h->wf("zt0"), B, cntB);
+    sync_bsums({BN_T0});
     DenseDwP w0 = dw_p(h->wf("u"), 168, B, 3, 84, 100, h->wf("d_t0"), 300, h->G(L.tower.w0), 8400, h->G(L.tower.b0), 100);
     w0.x_off[0] = 0; w0.x_off[1] = 84; w0.x_off[2] = 0;
     for (int g = 0; g < 3; ++g) w0.z_off[g] = g * 100;
+    dw_bn(w0, BN_T0, h->wf("zt0"), cntB);
     launch_dense_dw(w0, st);
     DenseDxP x0 = dx_p(h->wf("d_t0"), 300, B, 84, Pb, h->wf("d_u"), 168, 0);
     dx_add(x0, 0, 0, 0, L.tower.w0, 100);
     dx_add(x0, 0, 0, 200, L.tower.w0 + 2 * 8400, 100);
     dx_add(x0, 1, 84, 100, L.tower.w0 + 8400, 100);
+    x0.g = grad_of(BN_T0, h->wf("zt0"), cntB);
     launch_dense_dx(x0, st);
     nl += 2;
   }
@@ -584,34 +599,47 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
                      h->wf("d_tgt"), B, st); nl += 1;
   // ---- MMoE
   {
-    bn_bwd_n({{BN_E1, h->wf("d_e1"), h->wf("ze1")}, {BN_G1, h->wf("d_g1"), h->wf("zg1")}}, B, cntB);
+    launch_bn_bwd_stats(bn[BN_E1], h->wf("d_e1"), h->wf("ze1"), B, st);
+    launch_bn_bwd_stats(bn[BN_G1], h->wf("d_g1"), h->wf("zg1"), B, st);
+    nl += 2;
+    sync_bsums({BN_E1, BN_G1});
     DenseDwP we = dw_p(h->wf("ze0"), 500, B, 5, 100, 64, h->wf("d_e1"), 320, h->G(L.expert.w1), 6400, h->G(L.expert.b1), 64);
     for (int g = 0; g < 5; ++g) { we.x_off[g] = g * 100; we.z_off[g] = g * 64; }
     set_in_bn_dw(we, bn[BN_E0]);
+    dw_bn(we, BN_E1, h->wf("ze1"), cntB);
     launch_dense_dw(we, st);
     DenseDxP xe = dx_p(h->wf("d_e1"), 320, B, 100, Pb, h->wf("d_e0"), 500, 0);
     for (int g = 0; g < 5; ++g) dx_add(xe, g, g * 100, g * 64, L.expert.w1 + (int64_t)g * 6400, 64);
+    xe.g = grad_of(BN_E1, h->wf("ze1"), cntB);
+    xe.o = out_of(BN_E0, h->wf("ze0"));
     launch_dense_dx(xe, st);
     DenseDwP wg = dw_p(h->wf("zg0"), 128, B, 2, 64, 5, h->wf("d_g1"), 10, h->G(L.gate.w1), 320, h->G(L.gate.b1), 5);
     for (int g = 0; g < 2; ++g) { wg.x_off[g] = g * 64; wg.z_off[g] = g * 5; }
     set_in_bn_dw(wg, bn[BN_G0]);
+    dw_bn(wg, BN_G1, h->wf("zg1"), cntB);
     launch_dense_dw(wg, st);
     DenseDxP xg = dx_p(h->wf("d_g1"), 10, B, 64, Pb, h->wf("d_g0"), 128, 0);
     for (int g = 0; g < 2; ++g) dx_add(xg, g, g * 64, g * 5, L.gate.w1 + (int64_t)g * 320, 5);
+    xg.g = grad_of(BN_G1, h->wf("zg1"), cntB);
+    xg.o = out_of(BN_G0, h->wf("zg0"));
     launch_dense_dx(xg, st);
     nl += 4;
-    bn_bwd_n({{BN_E0, h->wf("d_e0"), h->wf("ze0")}, {BN_G0, h->wf("d_g0"), h->wf("zg0")}}, B, cntB);
+    sync_bsums({BN_E0, BN_G0});
     DenseDwP we0 = dw_p(h->wf("new_long"), kD, B, 5, kD, 100, h->wf("d_e0"), 500, h->G(L.expert.w0), 4000, h->G(L.expert.b0), 100);
     for (int g = 0; g < 5; ++g) { we0.x_off[g] = 0; we0.z_off[g] = g * 100; }
+    dw_bn(we0, BN_E0, h->wf("ze0"), cntB);
     launch_dense_dw(we0, st);
     DenseDwP wg0 = dw_p(h->wf("new_long"), kD, B, 2, kD, 64, h->wf("d_g0"), 128, h->G(L.gate.w0), 2560, h->G(L.gate.b0), 64);
     for (int g = 0; g < 2; ++g) { wg0.x_off[g] = 0; wg0.z_off[g] = g * 64; }
+    dw_bn(wg0, BN_G0, h->wf("zg0"), cntB);
     launch_dense_dw(wg0, st);
     DenseDxP xe0 = dx_p(h->wf("d_e0"), 500, B, kD, Pb, h->wf("d_new_long"), kD, 0);
     for (int g = 0; g < 5; ++g) dx_add(xe0, 0, 0, g * 100, L.expert.w0 + (int64_t)g * 4000, 100);
+    xe0.g = grad_of(BN_E0, h->wf("ze0"), cntB);
     launch_dense_dx(xe0, st);
     DenseDxP xg0 = dx_p(h->wf("d_g0"), 128, B, kD, Pb, h->wf("d_new_long"), kD, 1);
     for (int g = 0; g < 2; ++g) dx_add(xg0, 0, 0, g * 64, L.gate.w0 + (int64_t)g * 2560, 64);
+    xg0.g = grad_of(BN_G0, h->wf("zg0"), cntB);
     launch_dense_dx(xg0, st);
     nl += 4;
   }
@@ -621,19 +649,25 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   float* g_b = h->wf("g_b");
   {
     launch_pool_bwd(H, h->wf("z2"), bn[BN_S1], b->mask, h->wf("d_new_long"), h->wf("d_z2"), g_a, B, T, st); nl += 1;
-    bn_bwd(BN_S1, h->wf("d_z2"), h->wf("z2"), N, cntN);
+    launch_bn_bwd_stats(bn[BN_S1], h->wf("d_z2"), h->wf("z2"), N, st); nl += 1;
+    sync_bsums({BN_S1});
     DenseDwP w1 = dw_p(h->wf("z1"), 20, N, 1, 20, 1, h->wf("d_z2"), 1, h->G(L.score.w1), 0, h->G(L.score.b1), 0);
     set_in_bn_dw(w1, bn[BN_S0]);
+    dw_bn(w1, BN_S1, h->wf("z2"), cntN);
     launch_dense_dw(w1, st);
     DenseDxP x1 = dx_p(h->wf("d_z2"), 1, N, 20, Pb, h->wf("d_a1"), 20, 0);
     dx_add(x1, 0, 0, 0, L.score.w1, 1);
+    x1.g = grad_of(BN_S1, h->wf("z2"), cntN);
+    x1.o = out_of(BN_S0, h->wf("z1"));
     launch_dense_dx(x1, st);
     nl += 2;
-    bn_bwd(BN_S0, h->wf("d_a1"), h->wf("z1"), N, cntN);
+    sync_bsums({BN_S0});
     DenseDwP w0 = dw_p(H, kD, N, 1, kD, 20, h->wf("d_a1"), 20, h->G(L.score.w0), 0, h->G(L.score.b0), 0);
+    dw_bn(w0, BN_S0, h->wf("z1"), cntN);
     launch_dense_dw(w0, st);
     DenseDxP x0 = dx_p(h->wf("d_a1"), 20, N, kD, Pb, g_a, kD, 1);
     dx_add(x0, 0, 0, 0, L.score.w0, 20);
+    x0.g = grad_of(BN_S0, h->wf("z1"), cntN);
     launch_dense_dx(x0, st);
     nl += 2;
   }

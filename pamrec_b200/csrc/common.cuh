@@ -76,6 +76,20 @@ struct DenseP {
 };
 
 // dX[m, out_off+k] (+)= sum over contributions c: sum_n dZ[m, dz_off[c]+n] * W_c[k][n]
+// Batch-norm backward folded into the consumers of a gradient buffer.  The buffer holds dA, the gradient wrt the
+// layer's post-BN-ReLU activation, laid out exactly like the layer's pre-BN output Z; the gradient wrt Z,
+//   dz = gamma * invstd * (dy - S1/n - xhat * S2/n),  dy = relu'(gamma * xhat + beta) * dA,
+// is evaluated while a consumer loads its operand (S1 = sum dy, S2 = sum dy * xhat: bsums, complete before the launch).
+struct BnGrad {
+  const float* Z;            // null: the buffer already holds dz
+  const float* stat; const float* gamma; const float* beta;
+  const double* bsums; double count;
+};
+// Column sums S1, S2 of a gradient buffer that a kernel PRODUCES (the batch norm of the previous layer), or Z == null
+struct BnGradOut {
+  const float* Z; const float* stat; const float* gamma; const float* beta;
+  double* bsums;
+};
 struct DenseDxP {
   const float* dZ; int lddz; int M;
   int n_slices; int K;
@@ -83,6 +97,8 @@ struct DenseDxP {
   int dz_off[8][8]; int64_t w_off[8][8]; int Ncon[8][8];
   const float* Wbase;
   float* dX; int lddx; int accumulate;
+  BnGrad g;                  // of dZ
+  BnGradOut o;               // of dX (same layout as o.Z, leading dimension lddx)
 };
 
 // dW_g[k][n] += sum_m act(X[m, x_off[g]+k]) * dZ[m, z_off[g]+n];  db_g[n] += sum_m dZ[m, z_off[g]+n]
@@ -93,6 +109,9 @@ struct DenseDwP {
   const float* dZ; int lddz;
   const float* in_stat; const float* in_gamma; const float* in_beta;
   float* dW; int w_stride; float* db; int b_stride;
+  BnGrad g;                  // of dZ
+  // the CTA (0, 0) of this launch also emits the BN parameter gradients of dZ's layer: dbeta += S1 * scale, dgamma += S2 * scale
+  float* g_dgamma; float* g_dbeta; int g_C; float g_scale;
 };
 
 }  // namespace pamrec

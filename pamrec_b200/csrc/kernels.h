@@ -60,8 +60,6 @@ void launch_dense_dw(const DenseDwP& p, cudaStream_t st);
 void launch_bn_finalize(const BnSet& s, double count, cudaStream_t st);   // training: sums -> stat, moving update, sums := 0
 void launch_bn_eval_stat(const BnSet& s, cudaStream_t st);                // inference: stat from moving stats
 void launch_bn_bwd_stats(const BnSet& s, const float* dA, const float* Z, int M, cudaStream_t st);
-void launch_bn_bwd_apply(const BnSet& s, float* dA_inout, const float* Z, int M, double count, float grad_scale,
-                         cudaStream_t st);
 void launch_pool_fwd(const float* H, const float* Z2, const BnSet& s1, const int* mask, float* new_long, int B, int T,
                      cudaStream_t st);
 void launch_pool_bwd(const float* H, const float* Z2, const BnSet& s1, const int* mask, const float* d_new_long, float* dA2,

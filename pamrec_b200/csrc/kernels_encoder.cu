@@ -1,13 +1,12 @@
 // Encoder kernels: embedding gather, bucket planning, time-aware Q/K/V projection,
 // key-masked attention, LayerNorm + point-wise FFN — forward and backward.
 //
-// Mapping used by every token-parallel kernel: ONE THREAD == ONE TOKEN.  A CTA stages a
-// tile of 128 token rows (40 floats each) in shared memory with row stride 41 (so the 32
-// lanes of a warp walking the same column hit 32 different banks), keeps the 40 output
-// accumulators of a row in registers, and reads the 40x40 weight matrix from shared memory
-// with warp-uniform float4 loads (one broadcast wavefront feeds 128 FMAs).  Tokens are
-// bucket-sorted first so that a CTA needs exactly one (Wq,Wk,Wv)[bucket] triple:
-// the reference instead materialises a [B,T,40,40] gather per matrix (pamrec.py:714-728).
+// Token-parallel kernels (projection, FFN): a CTA owns a tile of 128 token rows (40 floats each, shared-memory row
+// stride 44), warp w the rows 32w .. 32w+31, and every [tokens x 40] x [40 x 40] contraction - forward, input gradient
+// and weight gradient - runs on the tensor cores as an error-compensated 3xTF32 mma.sync (mma.cuh); LayerNorm and
+// its backward are evaluated in the MMA fragment layout (row sums are 4-lane shuffles).  Tokens are bucket-sorted
+// first so that a CTA needs exactly one (Wq,Wk,Wv)[bucket] triple: the reference instead materialises a
+// [B,T,40,40] gather per matrix (pamrec.py:714-728).  Attention: one thread per query row, see k_attn_fwd.
 #include "kernels.h"
 #include "mma.cuh"
 
@@ -143,128 +142,7 @@ void launch_bucket_plan(const float* lt, int n, int* bucket, int* perm, int* ctl
 }
 
 // ------------------------------------------------------------------------------------------
-// register-tile helpers (thread == token)
-// acc[j] += sum_i in[i] * W[i][j]
-__device__ __forceinline__ void mv_fwd(const float* __restrict__ in, const float* __restrict__ W, float (&acc)[kD]) {
-#pragma unroll 4
-  for (int i = 0; i < kD; ++i) {
-    float a = in[i];
-#pragma unroll
-    for (int j = 0; j < kD / 4; ++j) {
-      float4 w = ld4(W + i * kD + 4 * j);
-      acc[4 * j + 0] = fmaf(a, w.x, acc[4 * j + 0]);
-      acc[4 * j + 1] = fmaf(a, w.y, acc[4 * j + 1]);
-      acc[4 * j + 2] = fmaf(a, w.z, acc[4 * j + 2]);
-      acc[4 * j + 3] = fmaf(a, w.w, acc[4 * j + 3]);
-    }
-  }
-}
-// acc[i] += sum_j g[j] * W[i][j]
-__device__ __forceinline__ void mv_bwd(const float* __restrict__ g, const float* __restrict__ W, float (&acc)[kD]) {
-#pragma unroll 2
-  for (int j = 0; j < kD / 4; ++j) {
-    float4 gv = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
-#pragma unroll
-    for (int i = 0; i < kD; ++i) acc[i] += f4_dot(gv, ld4(W + i * kD + 4 * j));
-  }
-}
-// dW[40][40] += A^T G over `cnt` rows of two stride-41 tiles; 100 threads own a 2x8 patch each.
-__device__ __forceinline__ void tile_outer_atomic(const float* __restrict__ A, const float* __restrict__ G, int cnt,
-                                                  float* __restrict__ dW, int tid) {
-  if (tid >= 100) return;
-  int i0 = 2 * (tid / 5), j0 = 8 * (tid % 5);
-  float a0[8], a1[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) a0[q] = a1[q] = 0.f;
-  for (int r = 0; r < cnt; ++r) {
-    float x0 = A[r * kRowPad + i0], x1 = A[r * kRowPad + i0 + 1];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float g = G[r * kRowPad + j0 + q];
-      a0[q] = fmaf(x0, g, a0[q]);
-      a1[q] = fmaf(x1, g, a1[q]);
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    atomicAdd(dW + i0 * kD + j0 + q, a0[q]);
-    atomicAdd(dW + (i0 + 1) * kD + j0 + q, a1[q]);
-  }
-}
-__device__ __forceinline__ void tile_colsum_atomic(const float* __restrict__ G, int cnt, float* __restrict__ db, int tid) {
-  if (tid >= kD) return;
-  float s = 0.f;
-  for (int r = 0; r < cnt; ++r) s += G[r * kRowPad + tid];
-  atomicAdd(db + tid, s);
-}
-// cooperative load of `cnt` token rows (global, 40 floats each) into a stride-41 tile.  All ten 16-byte loads of a
-// thread are issued before the first shared-memory store: the tile arrives after ONE memory round trip instead of ten.
-constexpr int kTileIt = (kTokTile * 10 + kTokTile - 1) / kTokTile;   // float4 per thread for a full tile (= 10)
-__device__ __forceinline__ void load_tile_perm(float* __restrict__ dst, const float* __restrict__ src, const int* toks,
-                                               int cnt, int tid) {
-  float4 v[kTileIt];
-#pragma unroll
-  for (int it = 0; it < kTileIt; ++it) {
-    const int i = tid + it * kTokTile;
-    if (i < cnt * 10) v[it] = ld4(src + (int64_t)toks[i / 10] * kD + 4 * (i % 10));
-  }
-#pragma unroll
-  for (int it = 0; it < kTileIt; ++it) {
-    const int i = tid + it * kTokTile;
-    if (i < cnt * 10) {
-      float* d = dst + (i / 10) * kRowPad + 4 * (i % 10);
-      d[0] = v[it].x; d[1] = v[it].y; d[2] = v[it].z; d[3] = v[it].w;
-    }
-  }
-}
-__device__ __forceinline__ void load_tile_lin(float* __restrict__ dst, const float* __restrict__ src, int cnt, int tid) {
-  float4 v[kTileIt];
-#pragma unroll
-  for (int it = 0; it < kTileIt; ++it) {
-    const int i = tid + it * kTokTile;
-    if (i < cnt * 10) v[it] = ld4(src + 4 * (int64_t)i);          // rows are contiguous: element i is float4 number i
-  }
-#pragma unroll
-  for (int it = 0; it < kTileIt; ++it) {
-    const int i = tid + it * kTokTile;
-    if (i < cnt * 10) {
-      float* d = dst + (i / 10) * kRowPad + 4 * (i % 10);
-      d[0] = v[it].x; d[1] = v[it].y; d[2] = v[it].z; d[3] = v[it].w;
-    }
-  }
-}
-// n_mat 40x40 matrices (contiguous in smem, each from its own global pointer) with batched loads
-__device__ __forceinline__ void load_mats(float* __restrict__ dst, const float* __restrict__ m0, const float* __restrict__ m1,
-                                          const float* __restrict__ m2, int n_mat, int tid) {
-  constexpr int IT = (3 * (kDD / 4) + kTokTile - 1) / kTokTile;      // 10
-  float4 v[IT];
-#pragma unroll
-  for (int it = 0; it < IT; ++it) {
-    const int i = tid + it * kTokTile;
-    const int m = i / (kDD / 4), j = i % (kDD / 4);
-    if (m < n_mat) v[it] = ld4((m == 0 ? m0 : (m == 1 ? m1 : m2)) + 4 * j);
-  }
-#pragma unroll
-  for (int it = 0; it < IT; ++it) {
-    const int i = tid + it * kTokTile;
-    if (i / (kDD / 4) < n_mat) st4(dst + 4 * i, v[it]);
-  }
-}
-__device__ __forceinline__ void store_row(float* __restrict__ dst, const float (&acc)[kD]) {
-#pragma unroll
-  for (int j = 0; j < kD / 4; ++j) st4(dst + 4 * j, make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
-}
-// population mean / rstd of a 40-wide smem row (pamrec.py:659-662)
-__device__ __forceinline__ void row_stats(const float* __restrict__ x, float& mean, float& rstd) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < kD; ++i) s += x[i];
-  mean = s * (1.0f / kD);
-  float v = 0.f;
-#pragma unroll
-  for (int i = 0; i < kD; ++i) { float d = x[i] - mean; v = fmaf(d, d, v); }
-  rstd = 1.0f / sqrtf(v * (1.0f / kD) + kLnEps);
-}
+constexpr int kTileIt = (kTokTile * 10 + kTokTile - 1) / kTokTile;   // float4 per thread for a full 128 x 40 tile (= 10)
 
 // ------------------------------------------------------------------------------------------
 // N1 + A1 forward: qin = LN_a(x); Q = qin Wq[k], K = x Wk[k], V = x Wv[k]   (pamrec.py:521-522,714-728)

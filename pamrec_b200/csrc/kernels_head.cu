@@ -79,6 +79,63 @@ __device__ __forceinline__ void stage_rows_T(float* __restrict__ dst, const floa
   }
 }
 
+// dz from (dA, z) with the per-column coefficients of the layer's BN (BnGrad, common.cuh) staged in shared memory:
+// co[6c .. 6c+5] = mean, invstd, gamma, beta, S1/n, S2/n  (the two fp64 divisions happen once per column and CTA)
+__device__ __forceinline__ void bn_dz_coef(float* __restrict__ co, const BnGrad& g, int col0, int n, int tid) {
+  for (int c = tid; c < n; c += kHT) {
+    const int cc = col0 + c;
+    co[6 * c + 0] = g.stat[2 * cc]; co[6 * c + 1] = g.stat[2 * cc + 1];
+    co[6 * c + 2] = g.gamma[cc]; co[6 * c + 3] = g.beta[cc];
+    co[6 * c + 4] = (float)(g.bsums[2 * cc] / g.count); co[6 * c + 5] = (float)(g.bsums[2 * cc + 1] / g.count);
+  }
+}
+__device__ __forceinline__ float bn_dz(float da, float z, const float* __restrict__ co, int c) {
+  const float inv = co[6 * c + 1], ga = co[6 * c + 2];
+  const float xh = (z - co[6 * c]) * inv;
+  const float dy = fmaf(ga, xh, co[6 * c + 3]) > 0.f ? da : 0.f;
+  return ga * inv * (dy - co[6 * c + 4] - xh * co[6 * c + 5]);
+}
+// stage_rows_T over two matrices with the same layout: dst[c][r] = f(a[r][c], b[r][c], c)
+template <typename F>
+__device__ __forceinline__ void stage_rows_T2(float* __restrict__ dst, const float* __restrict__ srcA, const float* __restrict__ srcB,
+                                              int ld, int rows_valid, int cn, int tid, F f) {
+  const bool vec = ((ld | cn) & 3) == 0 && aligned16(srcA) && aligned16(srcB);
+  if (vec) {
+    const int n4 = cn >> 2, total = kTM * n4;
+    constexpr int IT = (kTM * (kKMax / 4) + kHT - 1) / kHT;
+#pragma unroll 1
+    for (int it0 = 0; it0 < IT; it0 += 4) {             // 4 x 2 float4 in flight per thread
+      float4 va[4], vb[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = tid + (it0 + q) * kHT;
+        const int r = i % kTM, c4 = i / kTM;
+        const bool ok = i < total && r < rows_valid;
+        va[q] = ok ? ld4(srcA + (int64_t)r * ld + 4 * c4) : f4_zero();
+        vb[q] = ok ? ld4(srcB + (int64_t)r * ld + 4 * c4) : f4_zero();
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = tid + (it0 + q) * kHT;
+        const int r = i % kTM, c4 = i / kTM;
+        if (i < total) {
+          const bool ok = r < rows_valid;
+          dst[(4 * c4 + 0) * kTM + r] = ok ? f(va[q].x, vb[q].x, 4 * c4 + 0) : 0.f;
+          dst[(4 * c4 + 1) * kTM + r] = ok ? f(va[q].y, vb[q].y, 4 * c4 + 1) : 0.f;
+          dst[(4 * c4 + 2) * kTM + r] = ok ? f(va[q].z, vb[q].z, 4 * c4 + 2) : 0.f;
+          dst[(4 * c4 + 3) * kTM + r] = ok ? f(va[q].w, vb[q].w, 4 * c4 + 3) : 0.f;
+        }
+      }
+    }
+  } else {
+    const int total = kTM * cn;
+    for (int i = tid; i < total; i += kHT) {
+      const int r = i % kTM, c = i / kTM;
+      dst[c * kTM + r] = (r < rows_valid) ? f(srcA[(int64_t)r * ld + c], srcB[(int64_t)r * ld + c], c) : 0.f;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Z[m, zo+n] = sum_k act(X[m, xo+k]) W_g[k][n] + b_g[n]   (+ fp64 column sums of Z for the next batch norm)
 __global__ void __launch_bounds__(kHT) k_dense_fwd(const DenseP p, int tiles_m) {
@@ -176,6 +233,7 @@ void launch_dense_fwd(const DenseP& p, cudaStream_t st) { PAMREC_PROF("dense_fwd
 __global__ void __launch_bounds__(kHT) k_dense_dx(const DenseDxP p) {
   __shared__ __align__(16) float As[kKMax * kTM];   // dZ tile, transposed: As[n][m]
   __shared__ __align__(16) float Bs[kKMax * kTN];   // Bs[n][kk] = W[k0+kk][n]
+  __shared__ float co[6 * kKMax];                   // BN-backward coefficients of the dZ columns in flight
   const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
   const int kchunk = (p.K + kTN - 1) / kTN;
   const int s = blockIdx.y / kchunk, k0 = (blockIdx.y % kchunk) * kTN;
@@ -191,7 +249,14 @@ __global__ void __launch_bounds__(kHT) k_dense_dx(const DenseDxP p) {
     const int N = p.Ncon[s][ci], dzo = p.dz_off[s][ci];
     const float* W = p.Wbase + p.w_off[s][ci];
     __syncthreads();
-    stage_rows_T(As, p.dZ + (int64_t)m0 * p.lddz + dzo, p.lddz, rows, N, tid, [](float v, int) { return v; });
+    if (p.g.Z) {
+      bn_dz_coef(co, p.g, dzo, N, tid);
+      __syncthreads();
+      stage_rows_T2(As, p.dZ + (int64_t)m0 * p.lddz + dzo, p.g.Z + (int64_t)m0 * p.lddz + dzo, p.lddz, rows, N, tid,
+                    [&](float da, float z, int c) { return bn_dz(da, z, co, c); });
+    } else {
+      stage_rows_T(As, p.dZ + (int64_t)m0 * p.lddz + dzo, p.lddz, rows, N, tid, [](float v, int) { return v; });
+    }
     // rows of W are the "rows" to transpose: Bs[n][kk] = W[(k0+kk)*N + n]
     stage_rows_T(Bs, W + (int64_t)k0 * N, N, kc, N, tid, [](float v, int) { return v; });
     __syncthreads();
@@ -199,21 +264,50 @@ __global__ void __launch_bounds__(kHT) k_dense_dx(const DenseDxP p) {
   }
   const int oo = p.out_off[s] + k0;
   const bool vec_out = ((p.lddx | oo) & 3) == 0 && aligned16(p.dX) && (kc & 3) == 0;
+  double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int r = 2 * ty + i;
     if (r < rows) {
       float* o = p.dX + (int64_t)(m0 + r) * p.lddx + oo + 4 * tx;
-      if (vec_out) {
-        if (4 * tx < kc) {
-          float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-          if (p.accumulate) { float4 q = ld4(o); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
-          st4(o, v);
-        }
-      } else {
+      if (p.accumulate) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (4 * tx + j < kc) o[j] = p.accumulate ? o[j] + acc[i][j] : acc[i][j];
+          if (4 * tx + j < kc) acc[i][j] += o[j];
+      }
+      if (vec_out) { if (4 * tx < kc) st4(o, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3])); }
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (4 * tx + j < kc) o[j] = acc[i][j];
+      }
+      if (p.o.Z) {                                     // BN-backward sums of the buffer just produced
+        const float* z = p.o.Z + (int64_t)(m0 + r) * p.lddx + oo + 4 * tx;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (4 * tx + j < kc) {
+            const int c = oo + 4 * tx + j;
+            const float xh = (z[j] - p.o.stat[2 * c]) * p.o.stat[2 * c + 1];
+            const float dy = fmaf(p.o.gamma[c], xh, p.o.beta[c]) > 0.f ? acc[i][j] : 0.f;
+            s1[j] += (double)dy;
+            s2[j] += (double)dy * (double)xh;
+          }
+      }
+    }
+  }
+  if (p.o.Z) {
+    double* red = reinterpret_cast<double*>(As);       // [2][16][32] doubles = 8 KB, As is free now
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red[ty * kTN + 4 * tx + j] = s1[j]; red[(kHT / 8) * kTN + ty * kTN + 4 * tx + j] = s2[j]; }
+    __syncthreads();
+    if (tid < 2 * kTN) {
+      const int which = tid / kTN, n = tid % kTN;
+      if (n < kc) {
+        double tsum = 0.0;
+#pragma unroll
+        for (int y = 0; y < kHT / 8; ++y) tsum += red[which * (kHT / 8) * kTN + y * kTN + n];
+        atomicAdd(p.o.bsums + 2 * (oo + n) + which, tsum);
       }
     }
   }
@@ -232,6 +326,7 @@ void launch_dense_dx(const DenseDxP& p, cudaStream_t st) { PAMREC_PROF("dense_dx
 __global__ void __launch_bounds__(kHT) k_dense_dw(const DenseDwP p, int rows_per_cta) {
   __shared__ __align__(16) float As[kTM * kTM];     // As[r][kk] = act(X[m0+r, xo+k0+kk])
   __shared__ __align__(16) float Bs[kTM * kTN];     // Bs[r][nn] = dZ[m0+r, zo+n0+nn]
+  __shared__ float co[6 * kTN];                     // BN-backward coefficients of this tile's dZ columns
   const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
   const int ktiles = (p.K + kTM - 1) / kTM, ntiles = (p.N + kTN - 1) / kTN;
   int y = blockIdx.y;
@@ -250,6 +345,7 @@ __global__ void __launch_bounds__(kHT) k_dense_dw(const DenseDwP p, int rows_per
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float dbv = 0.f;
+  if (p.g.Z) bn_dz_coef(co, p.g, zo, nc, tid);       // visible after the first barrier of the loop
   for (int m0 = m_begin; m0 < m_end; m0 += kTM) {
     const int rows = min(kTM, m_end - m0);
     __syncthreads();
@@ -283,6 +379,13 @@ __global__ void __launch_bounds__(kHT) k_dense_dw(const DenseDwP p, int rows_per
           if (4 * q + 2 < nc) b.z = zb[2];
           if (4 * q + 3 < nc) b.w = zb[3];
         }
+        if (p.g.Z) {
+          const float* zz = p.g.Z + (int64_t)(m0 + r) * p.lddz + zo + 4 * q;
+          if (4 * q + 0 < nc) b.x = bn_dz(b.x, zz[0], co, 4 * q + 0);
+          if (4 * q + 1 < nc) b.y = bn_dz(b.y, zz[1], co, 4 * q + 1);
+          if (4 * q + 2 < nc) b.z = bn_dz(b.z, zz[2], co, 4 * q + 2);
+          if (4 * q + 3 < nc) b.w = bn_dz(b.w, zz[3], co, 4 * q + 3);
+        }
       }
       st4(As + r * kTM + 4 * q, a);
       st4(Bs + r * kTN + 4 * q, b);
@@ -305,6 +408,12 @@ __global__ void __launch_bounds__(kHT) k_dense_dw(const DenseDwP p, int rows_per
     }
   }
   if (kt == 0 && tid < nc) atomicAdd(p.db + (int64_t)g * p.b_stride + n0 + tid, dbv);
+  if (p.g_dgamma && blockIdx.x == 0 && blockIdx.y == 0) {
+    for (int c = tid; c < p.g_C; c += kHT) {
+      p.g_dbeta[c] += (float)p.g.bsums[2 * c] * p.g_scale;
+      p.g_dgamma[c] += (float)p.g.bsums[2 * c + 1] * p.g_scale;
+    }
+  }
 }
 
 void launch_dense_dw(const DenseDwP& p, cudaStream_t st) { PAMREC_PROF("dense_dw", 1, st);
@@ -381,32 +490,6 @@ void launch_bn_bwd_stats(const BnSet& s, const float* dA, const float* Z, int M,
   int rpb = (256 / cb) * kBnRowsPerThread;
   dim3 grid((s.C + cb - 1) / cb, (M + rpb - 1) / rpb);
   k_bn_bwd_stats<<<grid, 256, 0, st>>>(s, dA, Z, M);
-}
-
-// dz = gamma * invstd * (dy - S1/n - xhat * S2/n), in place over dA
-__global__ void k_bn_bwd_apply(BnSet s, float* __restrict__ dA, const float* __restrict__ Z, int64_t total, double count) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int col = (int)(i % s.C);
-  const float mean = s.stat[2 * col], inv = s.stat[2 * col + 1], g = s.gamma[col], be = s.beta[col];
-  float xh = (Z[i] - mean) * inv;
-  float y = fmaf(g, xh, be);
-  float dy = y > 0.f ? dA[i] : 0.f;
-  float m1 = (float)(s.bsums[2 * col] / count), m2 = (float)(s.bsums[2 * col + 1] / count);
-  dA[i] = g * inv * (dy - m1 - xh * m2);
-}
-__global__ void k_bn_param_grad(BnSet s, float scale) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= s.C) return;
-  s.dbeta[c] += (float)s.bsums[2 * c] * scale;
-  s.dgamma[c] += (float)s.bsums[2 * c + 1] * scale;
-  s.bsums[2 * c] = 0.0;
-  s.bsums[2 * c + 1] = 0.0;
-}
-void launch_bn_bwd_apply(const BnSet& s, float* dA, const float* Z, int M, double count, float grad_scale, cudaStream_t st) { PAMREC_PROF("bn_bwd_apply", 2, st);
-  int64_t total = (int64_t)M * s.C;
-  if (total > 0) k_bn_bwd_apply<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s, dA, Z, total, count);
-  k_bn_param_grad<<<(s.C + 127) / 128, 128, 0, st>>>(s, grad_scale);
 }
 
 // ------------------------------------------------------------------------------------------

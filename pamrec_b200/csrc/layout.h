@@ -43,6 +43,7 @@ struct Layout {
   BlockOff blk[2];
   MlpOff score, expert, gate, tower;
   BnOff bnoff[BN_COUNT];
+  int64_t bn_bsums_off[BN_COUNT];
   std::map<std::string, size_t> ws_index;
 
   int64_t add_dense(const std::string& name, std::initializer_list<int64_t> shape, int flags) {
@@ -204,12 +205,15 @@ struct Layout {
     add_ws("d_V", PAMREC_F32, {B, T, kD});
     // batch-norm statistics
     const char* bn_names[BN_COUNT] = {"s0", "s1", "e0", "g0", "e1", "g1", "t0", "t1"};
+    int64_t bn_c = 0;
     for (int i = 0; i < BN_COUNT; ++i) {
       std::string p = std::string("bn.") + bn_names[i];
       add_ws(p + ".sums", PAMREC_F64, {bnoff[i].C, 2});
       add_ws(p + ".stat", PAMREC_F32, {bnoff[i].C, 2});
-      add_ws(p + ".bsums", PAMREC_F64, {bnoff[i].C, 2});
+      bn_bsums_off[i] = 2 * bn_c;
+      bn_c += bnoff[i].C;
     }
+    add_ws("bn.bsums", PAMREC_F64, {bn_c, 2});   // backward sums (sum dy, sum dy*xhat) of all sets: one memset per step
     // optimiser scratch
     add_ws("seg_id", PAMREC_I32, {dense_numel});
     add_ws("seg_tab", PAMREC_I32, {(int64_t)dense.size(), 4});   // off, numel, flags, -
