@@ -33,7 +33,34 @@ struct PamrecHandle_ {
   Xchg xc[3];                   // item, cate, user
   bool xc_users = false;        // the current exchange carried user ids (training)
   bool sharded() const { return cfg.table_mode == PAMREC_TABLES_SHARDED; }
-  ~PamrecHandle_() { if (h_counts) cudaFreeHost(h_counts); }
+  // Internal side stream: work that is off the critical path of a step (the id sort of the sparse plan, the weight-gradient
+  // GEMMs of the head) is forked from the caller's stream with events and joined back before anything consumes it.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_side[12] = {};
+  cudaEvent_t ev_join = nullptr, ev_plan = nullptr;
+  int ev_next = 0;
+  const void* plan_for = nullptr;   // batch whose sparse plan is in flight / ready on the side stream (local tables)
+  int plan_rows = -1;
+  ~PamrecHandle_() {
+    if (h_counts) cudaFreeHost(h_counts);
+    for (auto e : ev_side) if (e) cudaEventDestroy(e);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (ev_plan) cudaEventDestroy(ev_plan);
+    if (side) cudaStreamDestroy(side);
+  }
+  // run fn(side) after everything enqueued on `main` so far
+  template <typename F>
+  void fork(cudaStream_t main, F fn) {
+    cudaEvent_t e = ev_side[ev_next];
+    ev_next = (ev_next + 1) % 12;
+    cudaEventRecord(e, main);
+    cudaStreamWaitEvent(side, e, 0);
+    fn(side);
+  }
+  void join(cudaStream_t main) {
+    cudaEventRecord(ev_join, side);
+    cudaStreamWaitEvent(main, ev_join, 0);
+  }
 
   float* P(int64_t off) const { return buf.dense_param + off; }
   float* G(int64_t off) const { return buf.dense_grad + off; }
@@ -177,6 +204,12 @@ int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(h, "no CUDA device: the CUDA path is the only path"); }
   h->buf = *bufs;
+  if (!h->side) {
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) return fail(h, "cannot create the side stream");
+    for (auto& e : h->ev_side) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_plan, cudaEventDisableTiming);
+  }
   static const char* names[BN_COUNT] = {"s0", "s1", "e0", "g0", "e1", "g1", "t0", "t1"};
   for (int i = 0; i < BN_COUNT; ++i) h->bn[i] = make_bn(h, i, names[i]);
   size_t need = sparse_temp_bytes(h->L.cub_keys);
@@ -397,6 +430,21 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
   float* x0 = h->wf("x0");
   if (int rc = embed_forward(h, b, training != 0, x0, st)) return rc;
   nl += 1;
+  if (training && !h->sharded()) {
+    // the id sort / unique pass of the sparse backward depends on the batch only: run it beside the forward pass
+    int prc = 0;
+    h->fork(st, [&](cudaStream_t s2) {
+      void* tmp = h->ws<char>("cub_temp");
+      const size_t tmp_bytes = (size_t)L.ws[L.ws_index.at("cub_temp")].numel;
+      SparseTable ti = table_of(h, "item"), tc = table_of(h, "cate"), tu = table_of(h, "ulong");
+      prc |= launch_sparse_plan(ti, b->item_history, b->items, N, B, 1, 0, ti.n_rows, true, tmp, tmp_bytes, s2);
+      prc |= launch_sparse_plan(tc, b->item_cate_history, b->cates, N, B, 1, 0, tc.n_rows, true, tmp, tmp_bytes, s2);
+      prc |= launch_sparse_plan(tu, b->users, nullptr, B, 0, 1, 0, tu.n_rows, true, tmp, tmp_bytes, s2);
+      cudaEventRecord(h->ev_plan, s2);
+    });
+    if (prc) return fail(h, "cub sort failed");
+    h->plan_for = b->item_history; h->plan_rows = B;
+  }
   if (training && W > 1) {
     cudaMemsetAsync(h->wd("dp.scalars"), 0, 8 * sizeof(double), st);
     launch_count_valid_groups(b->plays, B, h->wd("dp.scalars"), st);
@@ -563,7 +611,7 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
     DenseDwP w = dw_p(h->wf("zt1"), 192, B, 3, 64, 1, h->wf("d_logits"), 3, h->G(L.tower.wout), 64, h->G(L.tower.bout), 1);
     for (int g = 0; g < 3; ++g) { w.x_off[g] = g * 64; w.z_off[g] = g; }
     set_in_bn_dw(w, bn[BN_T1]);
-    launch_dense_dw(w, st);
+    h->fork(st, [&](cudaStream_t s2) { launch_dense_dw(w, s2); });
     DenseDxP x = dx_p(h->wf("d_logits"), 3, B, 64, Pb, h->wf("d_t1"), 192, 0);
     for (int g = 0; g < 3; ++g) dx_add(x, g, g * 64, g, L.tower.wout + g * 64, 1);
     x.o = out_of(BN_T1, h->wf("zt1"));
@@ -574,7 +622,7 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
     for (int g = 0; g < 3; ++g) { w1.x_off[g] = g * 100; w1.z_off[g] = g * 64; }
     set_in_bn_dw(w1, bn[BN_T0]);
     dw_bn(w1, BN_T1, h->wf("zt1"), cntB);
-    launch_dense_dw(w1, st);
+    h->fork(st, [&](cudaStream_t s2) { launch_dense_dw(w1, s2); });
     DenseDxP x1 = dx_p(h->wf("d_t1"), 192, B, 100, Pb, h->wf("d_t0"), 300, 0);
     for (int g = 0; g < 3; ++g) dx_add(x1, g, g * 100, g * 64, L.tower.w1 + (int64_t)g * 6400, 64);
     x1.g = grad_of(BN_T1, h->wf("zt1"), cntB);
@@ -586,7 +634,7 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
     w0.x_off[0] = 0; w0.x_off[1] = 84; w0.x_off[2] = 0;
     for (int g = 0; g < 3; ++g) w0.z_off[g] = g * 100;
     dw_bn(w0, BN_T0, h->wf("zt0"), cntB);
-    launch_dense_dw(w0, st);
+    h->fork(st, [&](cudaStream_t s2) { launch_dense_dw(w0, s2); });
     DenseDxP x0 = dx_p(h->wf("d_t0"), 300, B, 84, Pb, h->wf("d_u"), 168, 0);
     dx_add(x0, 0, 0, 0, L.tower.w0, 100);
     dx_add(x0, 0, 0, 200, L.tower.w0 + 2 * 8400, 100);
@@ -607,7 +655,7 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
     for (int g = 0; g < 5; ++g) { we.x_off[g] = g * 100; we.z_off[g] = g * 64; }
     set_in_bn_dw(we, bn[BN_E0]);
     dw_bn(we, BN_E1, h->wf("ze1"), cntB);
-    launch_dense_dw(we, st);
+    h->fork(st, [&](cudaStream_t s2) { launch_dense_dw(we, s2); });
     DenseDxP xe = dx_p(h->wf("d_e1"), 320, B, 100, Pb, h->wf("d_e0"), 500, 0);
     for (int g = 0; g < 5; ++g) dx_add(xe, g, g * 100, g * 64, L.expert.w1 + (int64_t)g * 6400, 64);
     xe.g = grad_of(BN_E1, h->wf("ze1"), cntB);
@@ -617,7 +665,7 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
     for (int g = 0; g < 2; ++g) { wg.x_off[g] = g * 64; wg.z_off[g] = g * 5; }
     set_in_bn_dw(wg, bn[BN_G0]);
     dw_bn(wg, BN_G1, h->wf("zg1"), cntB);
-    launch_dense_dw(wg, st);
+    h->fork(st, [&](cudaStream_t s2) { launch_dense_dw(wg, s2); });
     DenseDxP xg = dx_p(h->wf("d_g1"), 10, B, 64, Pb, h->wf("d_g0"), 128, 0);
     for (int g = 0; g < 2; ++g) dx_add(xg, g, g * 64, g * 5, L.gate.w1 + (int64_t)g * 320, 5);
     xg.g = grad_of(BN_G1, h->wf("zg1"), cntB);
@@ -628,11 +676,11 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
     DenseDwP we0 = dw_p(h->wf("new_long"), kD, B, 5, kD, 100, h->wf("d_e0"), 500, h->G(L.expert.w0), 4000, h->G(L.expert.b0), 100);
     for (int g = 0; g < 5; ++g) { we0.x_off[g] = 0; we0.z_off[g] = g * 100; }
     dw_bn(we0, BN_E0, h->wf("ze0"), cntB);
-    launch_dense_dw(we0, st);
+    h->fork(st, [&](cudaStream_t s2) { launch_dense_dw(we0, s2); });
     DenseDwP wg0 = dw_p(h->wf("new_long"), kD, B, 2, kD, 64, h->wf("d_g0"), 128, h->G(L.gate.w0), 2560, h->G(L.gate.b0), 64);
     for (int g = 0; g < 2; ++g) { wg0.x_off[g] = 0; wg0.z_off[g] = g * 64; }
     dw_bn(wg0, BN_G0, h->wf("zg0"), cntB);
-    launch_dense_dw(wg0, st);
+    h->fork(st, [&](cudaStream_t s2) { launch_dense_dw(wg0, s2); });
     DenseDxP xe0 = dx_p(h->wf("d_e0"), 500, B, kD, Pb, h->wf("d_new_long"), kD, 0);
     for (int g = 0; g < 5; ++g) dx_add(xe0, 0, 0, g * 100, L.expert.w0 + (int64_t)g * 4000, 100);
     xe0.g = grad_of(BN_E0, h->wf("ze0"), cntB);
@@ -654,7 +702,7 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
     DenseDwP w1 = dw_p(h->wf("z1"), 20, N, 1, 20, 1, h->wf("d_z2"), 1, h->G(L.score.w1), 0, h->G(L.score.b1), 0);
     set_in_bn_dw(w1, bn[BN_S0]);
     dw_bn(w1, BN_S1, h->wf("z2"), cntN);
-    launch_dense_dw(w1, st);
+    h->fork(st, [&](cudaStream_t s2) { launch_dense_dw(w1, s2); });
     DenseDxP x1 = dx_p(h->wf("d_z2"), 1, N, 20, Pb, h->wf("d_a1"), 20, 0);
     dx_add(x1, 0, 0, 0, L.score.w1, 1);
     x1.g = grad_of(BN_S1, h->wf("z2"), cntN);
@@ -664,7 +712,7 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
     sync_bsums({BN_S0});
     DenseDwP w0 = dw_p(H, kD, N, 1, kD, 20, h->wf("d_a1"), 20, h->G(L.score.w0), 0, h->G(L.score.b0), 0);
     dw_bn(w0, BN_S0, h->wf("z1"), cntN);
-    launch_dense_dw(w0, st);
+    h->fork(st, [&](cudaStream_t s2) { launch_dense_dw(w0, s2); });
     DenseDxP x0 = dx_p(h->wf("d_a1"), 20, N, kD, Pb, g_a, kD, 1);
     dx_add(x0, 0, 0, 0, L.score.w0, 20);
     x0.g = grad_of(BN_S0, h->wf("z1"), cntN);
@@ -691,6 +739,7 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   }
   // dX0 is in g_a
   launch_embed_bwd_reduce(g_a, h->wf("d_tgt"), h->wf("d_tgt_total"), h->G(L.pos), h->wd("sp_normsq") + 4, B, T, st); nl += 2;
+  h->join(st);                    // the head's weight-gradient GEMMs (side stream) are complete from here on
   if (crc) return fail(h, "nccl: %s", h->comm.err.c_str());
   return check_cuda(h, "backward");
 }
@@ -763,9 +812,13 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
       launch_slot_reset(own, nr, st);
     }
   } else {
+  const bool planned = h->plan_for == b->item_history && h->plan_rows == B;
+  h->plan_for = nullptr;
+  if (planned) cudaStreamWaitEvent(st, h->ev_plan, 0);       // plans of all three tables were sorted beside the forward pass
   {
     SparseTable t = table_of(h, "item");
-    if (launch_sparse_reduce(t, b->item_history, b->items, N, B, dX0, kD, 0, dT, kE, 0, tmp, tmp_bytes, st)) return fail(h, "cub sort failed");
+    if (!planned && launch_sparse_plan(t, b->item_history, b->items, N, B, 1, 0, t.n_rows, true, tmp, tmp_bytes, st)) return fail(h, "cub sort failed");
+    launch_sparse_segreduce(t, N + B, N, dX0, kD, 0, dT, kE, 0, t.normsq, st);
     launch_sparse_l2norm(t, N + B, c.embed_l2, reg, st);
     launch_sparse_adam(t, N + B, c.sparse_adam_mode, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm, c.is_clip_norm, st);
     launch_slot_reset(t, N + B, st);
@@ -773,7 +826,8 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
   }
   {
     SparseTable t = table_of(h, "cate");
-    if (launch_sparse_reduce(t, b->item_cate_history, b->cates, N, B, dX0, kD, kI, dT, kE, kI, tmp, tmp_bytes, st)) return fail(h, "cub sort failed");
+    if (!planned && launch_sparse_plan(t, b->item_cate_history, b->cates, N, B, 1, 0, t.n_rows, true, tmp, tmp_bytes, st)) return fail(h, "cub sort failed");
+    launch_sparse_segreduce(t, N + B, N, dX0, kD, kI, dT, kE, kI, t.normsq, st);
     launch_sparse_l2norm(t, N + B, c.embed_l2, reg, st);
     launch_sparse_adam(t, N + B, c.sparse_adam_mode, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm, c.is_clip_norm, st);
     launch_slot_reset(t, N + B, st);
@@ -781,7 +835,7 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
   }
   {
     SparseTable tl = table_of(h, "ulong"), ts = table_of(h, "ushort");
-    if (launch_sparse_reduce(tl, b->users, nullptr, B, 0, nullptr, 0, 0, nullptr, 0, 0, tmp, tmp_bytes, st)) return fail(h, "cub sort failed");
+    if (!planned && launch_sparse_plan(tl, b->users, nullptr, B, 0, 1, 0, tl.n_rows, true, tmp, tmp_bytes, st)) return fail(h, "cub sort failed");
     launch_sparse_l2norm(tl, B, c.embed_l2, reg, st);
     launch_sparse_l2norm(ts, B, c.embed_l2, reg, st);
     launch_sparse_adam(tl, B, c.sparse_adam_mode, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm, c.is_clip_norm, st);
