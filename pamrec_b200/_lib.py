@@ -12,6 +12,7 @@ SEG_L2, SEG_POS, SEG_DEAD = 1, 2, 4
 ADAM_DENSE_EXACT, ADAM_LAZY = 0, 1
 TABLES_LOCAL, TABLES_SHARDED = 0, 1
 COMM_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 GROUP = 5
 
 
@@ -67,6 +68,8 @@ EXPORTS = {
     "pamrec_comm_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
     "pamrec_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "pamrec_comm_destroy": (C.c_int, [C.c_void_p]),
+    "pamrec_comm_mailbox_create": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "pamrec_comm_mailbox_open": (C.c_int, [C.c_void_p, C.c_char_p]),
     "pamrec_shard_rows": (C.c_int64, [C.c_void_p, C.c_int64]),
     "pamrec_comm_all_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "pamrec_bench_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,

@@ -41,8 +41,21 @@ struct PamrecHandle_ {
   int ev_next = 0;
   const void* plan_for = nullptr;   // batch whose sparse plan is in flight / ready on the side stream (local tables)
   int plan_rows = -1;
+  // peer-memory mailboxes for the small all-reduces (kernels_p2p.cu); payload | flags | error word
+  void* mbox = nullptr;
+  void* mbox_peer[kP2PMaxWorld] = {};
+  bool mbox_open = false;
+  uint32_t mbox_epoch[kP2PSlots] = {};
+  double* mbox_slots(int p) const { return static_cast<double*>(mbox_peer[p]); }
+  uint32_t* mbox_flags(int p) const {
+    return reinterpret_cast<uint32_t*>(static_cast<char*>(mbox_peer[p]) + (size_t)kP2PSlots * cfg.world_size * kP2PMaxDoubles * sizeof(double));
+  }
+  uint32_t* mbox_err() const { return mbox_flags(cfg.rank) + kP2PSlots * cfg.world_size; }
   ~PamrecHandle_() {
     if (h_counts) cudaFreeHost(h_counts);
+    for (int p = 0; p < kP2PMaxWorld; ++p)
+      if (mbox_peer[p] && mbox_peer[p] != mbox) cudaIpcCloseMemHandle(mbox_peer[p]);
+    if (mbox) cudaFree(mbox);
     for (auto e : ev_side) if (e) cudaEventDestroy(e);
     if (ev_join) cudaEventDestroy(ev_join);
     if (ev_plan) cudaEventDestroy(ev_plan);
@@ -152,6 +165,34 @@ int pamrec_comm_init(PamrecHandle h, const char* nccl_path, const char id[PAMREC
   if (h->comm.init(nccl_path, id, h->cfg.world_size, h->cfg.rank)) { h->err = "comm_init: " + h->comm.err; return -1; }
   return 0;
 }
+int pamrec_comm_mailbox_create(PamrecHandle h, char handle_out[PAMREC_IPC_HANDLE_BYTES]) {
+  if (!h || !handle_out) return -1;
+  static_assert(sizeof(cudaIpcMemHandle_t) == PAMREC_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+  if (h->cfg.world_size > kP2PMaxWorld) return fail(h, "mailboxes support at most %d ranks", kP2PMaxWorld);
+  if (!h->mbox) {
+    const size_t bytes = p2p_mailbox_bytes(h->cfg.world_size);
+    if (cudaMalloc(&h->mbox, bytes) != cudaSuccess) return check_cuda(h, "mailbox alloc");
+    cudaMemset(h->mbox, 0, bytes);
+    cudaDeviceSynchronize();
+  }
+  cudaIpcMemHandle_t ih;
+  if (cudaIpcGetMemHandle(&ih, h->mbox) != cudaSuccess) return check_cuda(h, "cudaIpcGetMemHandle");
+  memcpy(handle_out, &ih, sizeof ih);
+  return 0;
+}
+int pamrec_comm_mailbox_open(PamrecHandle h, const char* handles) {
+  if (!h || !handles || !h->mbox) return -1;
+  for (int p = 0; p < h->cfg.world_size; ++p) {
+    if (p == h->cfg.rank) { h->mbox_peer[p] = h->mbox; continue; }
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, handles + (size_t)p * PAMREC_IPC_HANDLE_BYTES, sizeof ih);
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return check_cuda(h, "cudaIpcOpenMemHandle");
+    h->mbox_peer[p] = ptr;
+  }
+  h->mbox_open = true;
+  return 0;
+}
 int pamrec_comm_destroy(PamrecHandle h) {
   if (!h) return -1;
   h->comm.destroy();
@@ -220,7 +261,7 @@ int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
   cudaMemsetAsync(h->wi("sp.cate.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_cates) * 4, st);
   cudaMemsetAsync(h->wi("sp.user.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_users) * 4, st);
   if (h->sharded() && !h->h_counts &&
-      cudaMallocHost(&h->h_counts, sizeof(int) * 8 * (size_t)h->cfg.world_size) != cudaSuccess)
+      cudaMallocHost(&h->h_counts, sizeof(int) * (8 * (size_t)h->cfg.world_size + 4)) != cudaSuccess)
     return fail(h, "cudaMallocHost for the exchange counts failed");
   cudaMemcpyAsync(h->wi("seg_id"), h->h_seg_id.data(), h->h_seg_id.size() * 4, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(h->wi("seg_tab"), h->h_seg_tab.data(), h->h_seg_tab.size() * 4, cudaMemcpyHostToDevice, st);
@@ -330,7 +371,10 @@ static int shard_exchange_fwd(PamrecHandle h, const PamrecBatch* b, bool trainin
     if (h->comm.all_to_all(cs, cr, 4, COMM_I32, st)) return fail(h, "nccl: %s", h->comm.err.c_str());
     cudaMemcpyAsync(h->h_counts, cs, sizeof(int) * 4 * W, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(h->h_counts + 4 * W, cr, sizeof(int) * 4 * W, cudaMemcpyDeviceToHost, st);
+    h->h_counts[8 * W] = 0;
+    if (h->mbox_open) cudaMemcpyAsync(h->h_counts + 8 * W, h->mbox_err(), sizeof(int), cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) return check_cuda(h, "exchange counts");
+    if (h->h_counts[8 * W]) return fail(h, "peer mailbox all-reduce timed out at sync point %d (a rank left the step?)", h->h_counts[8 * W] - 1);
   }
   for (int t = 0; t < 3; ++t) {
     Xchg& x = h->xc[t];
@@ -355,6 +399,20 @@ static int shard_exchange_fwd(PamrecHandle h, const PamrecBatch* b, bool trainin
                                x.rcnt.data(), 1, COMM_I32, st)) return fail(h, "nccl: %s", h->comm.err.c_str());
     }
     if (h->comm.group_end()) return fail(h, "nccl: %s", h->comm.err.c_str());
+  }
+  if (training) {
+    // owner-side unique / slot plan of the rows other ranks asked for: needed by apply_gradients only, so it is sorted on the
+    // side stream while the forward and backward passes run (the requester plans above are done with the cub scratch)
+    int prc = 0;
+    h->fork(st, [&](cudaStream_t s2) {
+      for (int t = 0; t < 3; ++t) {
+        SparseTable own = own_table(h, t);
+        std::string p = std::string("sh.") + kShardName[t] + ".";
+        prc |= launch_sparse_plan(own, h->wi(p + "recv_ids"), nullptr, h->xc[t].n_recv, 0, 1, 0, own.n_rows, true, tmp, tmp_bytes, s2);
+      }
+      cudaEventRecord(h->ev_plan, s2);
+    });
+    if (prc) return fail(h, "cub sort failed");
   }
   launch_serve_rows(h->buf.item_w, h->wi("sh.item.recv_ids"), h->xc[0].n_recv, kI, h->wf("sh.item.xrows"), st);
   launch_serve_rows(h->buf.cate_w, h->wi("sh.cate.recv_ids"), h->xc[1].n_recv, kC, h->wf("sh.cate.xrows"), st);
@@ -418,14 +476,31 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
   const double cntN = (double)Bg * T, cntB = (double)Bg;
   int64_t nl = 0;
   int crc = 0;
-  // data parallel: batch-norm sums of the listed sets (plus, once, the listwise-group count) summed over ranks
-  auto sync_sums = [&](std::initializer_list<int> ids, bool with_scalars) {
-    if (!training || W == 1 || crc) return;
-    PAMREC_PROF("allreduce_bn_fwd", 1, st);
-    crc |= h->comm.group_start();
-    for (int id : ids) crc |= h->comm.all_reduce(h->bn[id].sums, 2 * (int64_t)h->bn[id].C, COMM_F64, st);
-    if (with_scalars) crc |= h->comm.all_reduce(h->wd("dp.scalars"), 8, COMM_F64, st);
-    crc |= h->comm.group_end();
+  // Training: batch statistics of the listed sets -> (mean, invstd), moving averages.  Data parallel: the column sums
+  // (plus, once, the listwise-group count) are first summed over ranks - through the peer mailboxes in ONE kernel that also
+  // finalises (kernels_p2p.cu), else NCCL all-reduce + finalize launches.
+  int p2p_slot = 0;
+  auto sync_finalize = [&](std::initializer_list<int> ids, double cnt, bool with_scalars) {
+    if (!training) return;
+    if (W > 1 && h->mbox_open) {
+      P2PArgs a;
+      memset(&a, 0, sizeof a);
+      for (int id : ids) { a.buf[a.nbuf] = h->bn[id].sums; a.n[a.nbuf++] = 2 * h->bn[id].C; a.bn[a.nbn] = h->bn[id]; a.count[a.nbn++] = cnt; }
+      if (with_scalars) { a.buf[a.nbuf] = h->wd("dp.scalars"); a.n[a.nbuf++] = 8; }
+      for (int p = 0; p < W; ++p) { a.peer_slots[p] = h->mbox_slots(p); a.peer_flags[p] = h->mbox_flags(p); }
+      a.world = W; a.rank = h->cfg.rank; a.slot = p2p_slot; a.epoch = ++h->mbox_epoch[p2p_slot]; a.err = h->mbox_err();
+      ++p2p_slot;
+      launch_p2p_allreduce(a, st); nl += 1;
+      return;
+    }
+    if (W > 1 && !crc) {
+      PAMREC_PROF("allreduce_bn_fwd", 1, st);
+      crc |= h->comm.group_start();
+      for (int id : ids) crc |= h->comm.all_reduce(h->bn[id].sums, 2 * (int64_t)h->bn[id].C, COMM_F64, st);
+      if (with_scalars) crc |= h->comm.all_reduce(h->wd("dp.scalars"), 8, COMM_F64, st);
+      crc |= h->comm.group_end();
+    }
+    for (int id : ids) { launch_bn_finalize(h->bn[id], cnt, st); nl += 1; }
   };
   float* x0 = h->wf("x0");
   if (int rc = embed_forward(h, b, training != 0, x0, st)) return rc;
@@ -472,22 +547,17 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     for (int i = 0; i < BN_COUNT; ++i) launch_bn_eval_stat(bn[i], st);
     nl += BN_COUNT;
   }
-  auto fin = [&](int id, double cnt) {
-    if (training) { launch_bn_finalize(bn[id], cnt, st); nl += 1; }
-  };
   // attention pooling score MLP (pamrec.py:273)
   {
     DenseP p = dense_p(H, kD, N, 1, kD, 20, h->P(L.score.w0), 0, h->P(L.score.b0), 0, h->wf("z1"), 20);
     p.out_sums = training ? bn[BN_S0].sums : nullptr;
     launch_dense_fwd(p, st); nl += 1;
-    sync_sums({BN_S0}, true);
-    fin(BN_S0, cntN);
+    sync_finalize({BN_S0}, cntN, true);
     DenseP q = dense_p(h->wf("z1"), 20, N, 1, 20, 1, h->P(L.score.w1), 0, h->P(L.score.b1), 0, h->wf("z2"), 1);
     set_in_bn(q, bn[BN_S0]);
     q.out_sums = training ? bn[BN_S1].sums : nullptr;
     launch_dense_fwd(q, st); nl += 1;
-    sync_sums({BN_S1}, false);
-    fin(BN_S1, cntN);
+    sync_finalize({BN_S1}, cntN, false);
   }
   launch_pool_fwd(H, h->wf("z2"), bn[BN_S1], b->mask, h->wf("new_long"), B, T, st); nl += 1;
   // MMoE (pamrec.py:26-50)
@@ -501,8 +571,7 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     g0.out_sums = training ? bn[BN_G0].sums : nullptr;
     launch_dense_fwd(g0, st);
     nl += 2;
-    sync_sums({BN_E0, BN_G0}, false);
-    fin(BN_E0, cntB); fin(BN_G0, cntB);
+    sync_finalize({BN_E0, BN_G0}, cntB, false);
     DenseP e1 = dense_p(h->wf("ze0"), 500, B, 5, 100, 64, h->P(L.expert.w1), 6400, h->P(L.expert.b1), 64, h->wf("ze1"), 320);
     for (int g = 0; g < 5; ++g) { e1.x_off[g] = g * 100; e1.z_off[g] = g * 64; }
     set_in_bn(e1, bn[BN_E0]);
@@ -514,8 +583,7 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     g1.out_sums = training ? bn[BN_G1].sums : nullptr;
     launch_dense_fwd(g1, st);
     nl += 2;
-    sync_sums({BN_E1, BN_G1}, false);
-    fin(BN_E1, cntB); fin(BN_G1, cntB);
+    sync_finalize({BN_E1, BN_G1}, cntB, false);
   }
   launch_combine_fwd(h->wf("ze1"), h->wf("zg1"), bn[BN_E1], bn[BN_G1], h->wf("tgt"), h->wf("u"), B, st); nl += 1;
   // towers: logit_fcn(main|tgt), valid_logit_fcn(sub|tgt), xilidu_logit_fcn(main|tgt)   pamrec.py:212-215, 71
@@ -525,15 +593,13 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     for (int g = 0; g < 3; ++g) t0.z_off[g] = g * 100;
     t0.out_sums = training ? bn[BN_T0].sums : nullptr;
     launch_dense_fwd(t0, st); nl += 1;
-    sync_sums({BN_T0}, false);
-    fin(BN_T0, cntB);
+    sync_finalize({BN_T0}, cntB, false);
     DenseP t1 = dense_p(h->wf("zt0"), 300, B, 3, 100, 64, h->P(L.tower.w1), 6400, h->P(L.tower.b1), 64, h->wf("zt1"), 192);
     for (int g = 0; g < 3; ++g) { t1.x_off[g] = g * 100; t1.z_off[g] = g * 64; }
     set_in_bn(t1, bn[BN_T0]);
     t1.out_sums = training ? bn[BN_T1].sums : nullptr;
     launch_dense_fwd(t1, st); nl += 1;
-    sync_sums({BN_T1}, false);
-    fin(BN_T1, cntB);
+    sync_finalize({BN_T1}, cntB, false);
     DenseP to = dense_p(h->wf("zt1"), 192, B, 3, 64, 1, h->P(L.tower.wout), 64, h->P(L.tower.bout), 1, h->wf("logits"), 3);
     for (int g = 0; g < 3; ++g) { to.x_off[g] = g * 64; to.z_off[g] = g; }
     set_in_bn(to, bn[BN_T1]);
@@ -588,8 +654,19 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   // gradient buffer also accumulates the two column sums of its layer's BN, the consumers turn dA into dz while loading.
   // Buffers produced by the mixing / pooling kernels get their sums from k_bn_bwd_stats.  Data parallel: sums over ranks.
   cudaMemsetAsync(h->wd("bn.bsums"), 0, (size_t)L.ws[L.ws_index.at("bn.bsums")].numel * sizeof(double), st);
+  int p2p_slot = 6;
   auto sync_bsums = [&](std::initializer_list<int> ids) {
     if (W == 1 || crc) return;
+    if (h->mbox_open) {
+      P2PArgs a;
+      memset(&a, 0, sizeof a);
+      for (int id : ids) { a.buf[a.nbuf] = bn[id].bsums; a.n[a.nbuf++] = 2 * bn[id].C; }
+      for (int p = 0; p < W; ++p) { a.peer_slots[p] = h->mbox_slots(p); a.peer_flags[p] = h->mbox_flags(p); }
+      a.world = W; a.rank = h->cfg.rank; a.slot = p2p_slot; a.epoch = ++h->mbox_epoch[p2p_slot]; a.err = h->mbox_err();
+      ++p2p_slot;
+      launch_p2p_allreduce(a, st);
+      return;
+    }
     PAMREC_PROF("allreduce_bn_bwd", 1, st);
     crc |= h->comm.group_start();
     for (int id : ids) crc |= h->comm.all_reduce(bn[id].bsums, 2 * (int64_t)bn[id].C, COMM_F64, st);
@@ -783,12 +860,11 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
       crc |= cm.group_end();
     }
     if (!h->xc_users) return fail(h, "apply_gradients needs pamrec_forward(training=1) on the same batch");
+    cudaStreamWaitEvent(st, h->ev_plan, 0);            // owner-side plans (side stream, forked in the forward exchange)
     for (int t = 0; t < 3; ++t) {
       SparseTable own = own_table(h, t);
       const int64_t nr = h->xc[t].n_recv;
       std::string p = std::string("sh.") + kShardName[t] + ".";
-      if (launch_sparse_plan(own, h->wi(p + "recv_ids"), nullptr, nr, 0, 1, 0, own.n_rows, true, tmp, tmp_bytes, st))
-        return fail(h, "cub sort failed");
       if (t < 2) launch_sparse_segreduce(own, nr, nr, h->wf(p + "xrows"), own.width, 0, nullptr, 0, 0, h->wd("sh.scratch"), st);
       launch_sparse_l2norm(own, nr, c.embed_l2, reg, st);
       if (t == 2) launch_sparse_l2norm(own_table(h, 2, true), nr, c.embed_l2, reg, st);

@@ -108,6 +108,23 @@ void launch_dense_adam(float* P, const float* G, float* M, float* V, const int* 
                        float clip, int is_clip, cudaStream_t st);
 void launch_finish_losses(const double* loss_acc, float* losses, cudaStream_t st);
 
+// ---- kernels_p2p.cu (small all-reduces through NVLink peer mailboxes)
+constexpr int kP2PMaxDoubles = 2048;     // payload capacity of one mailbox slot (expert + gate layer-0 sums: 1256)
+constexpr int kP2PSlots = 16;            // sync points per step (each has its own slot)
+constexpr int kP2PMaxWorld = 8;
+struct P2PArgs {
+  double* buf[3]; int n[3]; int nbuf;                     // buffers reduced in place (concatenated in the slot)
+  double* peer_slots[kP2PMaxWorld];                       // every rank's mailbox payload area [slot][rank][kP2PMaxDoubles]
+  uint32_t* peer_flags[kP2PMaxWorld];                     // every rank's mailbox flags [slot][rank]
+  int world, rank, slot; uint32_t epoch;
+  uint32_t* err;                                          // this rank's error word (0 = ok)
+  BnSet bn[2]; double count[2]; int nbn;                  // optional fused batch-norm finalize
+};
+void launch_p2p_allreduce(const P2PArgs& a, cudaStream_t st);
+inline size_t p2p_mailbox_bytes(int world) {
+  return (size_t)kP2PSlots * world * kP2PMaxDoubles * sizeof(double) + (size_t)kP2PSlots * world * sizeof(uint32_t) + 256;
+}
+
 // ---- kernels_shard.cu (row-sharded tables)
 void launch_shard_route(const SparseTable& req, int64_t n, int world, int64_t rps, int* off, int* counts, int slot, int* send_ids,
                         int* inv, cudaStream_t st);

@@ -1,6 +1,7 @@
 """Device engine: owns the torch-allocated pools, binds them to libpamrec_b200.so and drives one
 train / score step through the C ABI.  PyTorch is used for device memory and streams only."""
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -160,6 +161,14 @@ class Engine:
         dist.broadcast_object_list(box, src=0)
         torch.cuda.set_device(self.device)
         self._check(self.lib.pamrec_comm_init(self.handle, cpath, box[0]))
+        if self.world <= 8 and os.environ.get("PAMREC_NO_MAILBOX", "0") != "1":
+            # NVLink peer mailboxes for the small all-reduces (kernels_p2p.cu): exchange the cudaIpc handles
+            buf = C.create_string_buffer(L.IPC_HANDLE_BYTES)
+            self._check(self.lib.pamrec_comm_mailbox_create(self.handle, buf))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, buf.raw)
+            self._check(self.lib.pamrec_comm_mailbox_open(self.handle, b"".join(handles)))
+            self.mailbox = True
         return self
 
     def all_reduce_(self, t):

@@ -79,10 +79,13 @@ def test_sharded_empty_share_is_refused_without_peers_but_not_fatal():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
-def test_two_rank_step_matches_oracle():
+@pytest.mark.parametrize("small_allreduce", ["mailbox", "nccl"])
+def test_two_rank_step_matches_oracle(small_allreduce):
+    """small_allreduce: batch-norm sums through the NVLink peer mailboxes (fused with finalize) or through NCCL."""
     n = min(torch.cuda.device_count(), int(os.environ.get("PAMREC_TEST_RANKS", "2")))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-           "--master-port", "29611", os.path.join(ROOT, "tests", "dist_worker.py")]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+           "--master-port", "29611" if small_allreduce == "mailbox" else "29613", os.path.join(ROOT, "tests", "dist_worker.py")]
+    env = dict(os.environ, PAMREC_NO_MAILBOX="0" if small_allreduce == "mailbox" else "1")
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     print(r.stdout[-3000:])
     assert r.returncode == 0 and "DIST_PARITY_OK" in r.stdout, r.stdout[-3000:]
