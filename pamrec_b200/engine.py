@@ -288,21 +288,34 @@ class Engine:
             slot = self._stage[self._stage_i]
             self._stage_i ^= 1
             slot["done"].synchronize()                       # the previous copy out of this pinned slot has finished
-            host_np = slot["host"].numpy()
-            off = 0
-            views = []
-            for name, dt, shape in fields:
-                n = int(np.prod(shape)) * 4
-                np.copyto(host_np[off:off + n].view(dt).reshape(shape), np.asarray(feed[name]).reshape(shape), casting="unsafe")
-                views.append((name, dt, shape, off))
-                off += (n + 255) // 256 * 256
+            key = (B, tuple(name for name, _, _ in fields))
+            cached = slot.get("layout")
+            if cached is None or cached[0] != key:
+                # (re)build the views of this slot for this batch shape: host numpy views, device tensors, the C struct
+                host_np = slot["host"].numpy()
+                off, hv, dv = 0, [], {}
+                for name, dt, shape in fields:
+                    n = int(np.prod(shape)) * 4
+                    hv.append((name, host_np[off:off + n].view(dt).reshape(shape)))
+                    tdt = torch.int32 if dt == np.int32 else torch.float32
+                    dv[name] = slot["dev"][off:off + n].view(tdt).view(shape)
+                    off += (n + 255) // 256 * 256
+                for name, _, _ in BATCH_FIELDS:
+                    if name not in dv:
+                        dv[name] = torch.empty(0, device=self.device)
+                db = DeviceBatch(dv, B, global_batch)
+                for name, _, _ in BATCH_FIELDS:
+                    if dv[name].numel() == 0:
+                        setattr(db.struct, name, None)
+                db.h2d_bytes = off
+                cached = slot["layout"] = (key, hv, db, off)
+            _, hv, db, off = cached
+            for name, view in hv:
+                np.copyto(view, np.asarray(feed[name]).reshape(view.shape), casting="unsafe")
             slot["dev"][:off].copy_(slot["host"][:off], non_blocking=True)
             slot["done"].record(torch.cuda.current_stream(self.device))
-            for name, dt, shape, o in views:
-                n = int(np.prod(shape)) * 4
-                tdt = torch.int32 if dt == np.int32 else torch.float32
-                tensors[name] = slot["dev"][o:o + n].view(tdt).view(shape)
-            nbytes = off
+            db.struct.global_batch = int(global_batch)
+            return db
         for name, _, _ in BATCH_FIELDS:          # scoring: unused pointers stay null
             if name not in tensors:
                 tensors[name] = torch.empty(0, device=self.device)

@@ -110,11 +110,44 @@ def array_batch(seed, B, T, n_users, n_items, n_cates, grouped=True, min_len=1, 
     }
 
 
+class SyntheticVocab:
+    """dict-like `token -> index` vocabulary of `n` entries ("default_*" -> 0, "i" -> i) that pickles in a few bytes:
+    array-level benchmarks on 10 M-row tables need `len(vocab)` (sequential_base_model.py:565-567), not 10 M dict entries."""
+
+    def __init__(self, n, default):
+        self.n, self.default = int(n), default
+
+    def __len__(self):
+        return self.n
+
+    def _index(self, key):
+        if key == self.default:
+            return 0
+        try:
+            i = int(key)
+        except (TypeError, ValueError):
+            return None
+        return i if 0 < i < self.n else None
+
+    def __contains__(self, key):
+        return self._index(key) is not None
+
+    def __getitem__(self, key):
+        i = self._index(key)
+        if i is None:
+            raise KeyError(key)
+        return i
+
+    def get(self, key, default=None):
+        i = self._index(key)
+        return default if i is None else i
+
+
 def write_vocab_only(root, dataset, n_users, n_items, n_cates):
     """Just the files a model needs to be constructed (vocab pickles + meta csv), for array-level benchmarks."""
     d = os.path.join(root, dataset)
     os.makedirs(d, exist_ok=True)
-    vocab = lambda n, dflt: {dflt: 0, **{str(i): i for i in range(1, n)}}
+    vocab = lambda n, dflt: SyntheticVocab(n, dflt) if n > 1_000_000 else {dflt: 0, **{str(i): i for i in range(1, n)}}
     for name, voc in (("user_vocab.pkl", vocab(n_users, "default_uid")), ("item_vocab.pkl", vocab(n_items, "default_mid")),
                       ("category_vocab.pkl", vocab(n_cates, "default_cat"))):
         with open(os.path.join(d, name), "wb") as f:
