@@ -171,6 +171,31 @@ int pamrec_profile_reset(PamrecHandle h);
 int pamrec_profile_count(PamrecHandle h);
 int pamrec_profile_get(PamrecHandle h, int index, char name[64], double* total_ms, int64_t* launches);
 
+/* ---- Host input pipeline (no GPU needed).  The batching algorithm of the reference's SequentialIterator over a file that the
+ * host has tokenised once into flat columns: io/sequential_iterator.py:475-763 (train branch: per-user history state, listwise
+ * groups of 5, round-robin passes, tail batch), :375-474 (eval branch) and :1009-1141 (_convert_data: padding, masks, buckets,
+ * satisfied-only compaction).  Output is bit-identical to the reference's 19 feed arrays.  Python's `random` stays with the
+ * caller: it passes the shuffled order of the qualifying users and their warm-up lengths (IT:542-545, IT:622). */
+typedef struct PamrecBatcher_* PamrecBatcher;
+typedef struct PamrecLines {
+  int64_t n_lines;
+  const int64_t* offsets;       /* [n_lines + 1] into the five history columns (all five have equal length per line)  */
+  const int32_t* items; const int32_t* cates;              /* vocabulary indices                                        */
+  const double* durs; const double* sats; const double* plays;  /* seconds / 0-1 flags / seconds, as parsed (float64)  */
+  const int32_t* user_ids;      /* [n_lines]                                                                           */
+  /* eval files (one impression per line); NULL for train files */
+  const double* label_sat; const double* label_play; const int32_t* tgt_item; const int32_t* tgt_cate; const double* tgt_dur;
+} PamrecLines;
+/* the caller keeps the column arrays alive for the batcher's lifetime; borders = decile borders of play / duration (IT:24-42) */
+int pamrec_batcher_create(const PamrecLines* lines, const double* borders, int n_borders, int max_seq_len, PamrecBatcher* out);
+int pamrec_batcher_destroy(PamrecBatcher b);
+/* one training epoch: order[k] = line of the k-th user after random.shuffle, begin_loc[k] = its warm-up length */
+int pamrec_batcher_begin_train(PamrecBatcher b, const int64_t* order, const int32_t* begin_loc, int64_t n);
+int pamrec_batcher_begin_eval(PamrecBatcher b, int min_seq_length);
+/* fills up to batch_size rows of the 19 arrays (order of SequentialIterator.gen_feed_dict, IT:1155-1175; int32 ids, float32
+ * values, [rows] or [rows, max_seq_len]); returns the rows written, 0 when the pass is exhausted, < 0 on error */
+int pamrec_batcher_next(PamrecBatcher b, int batch_size, void* const* arrays);
+
 /* number of kernel launches issued by the last device call on this handle */
 int64_t pamrec_last_launch_count(PamrecHandle h);
 

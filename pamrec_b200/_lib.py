@@ -44,6 +44,13 @@ class PamrecBuffers(C.Structure):
         "ulong_w", "ulong_m", "ulong_v", "ushort_w", "ushort_m", "ushort_v", "workspace")] + [("workspace_bytes", C.c_size_t)]
 
 
+class PamrecLines(C.Structure):
+    _fields_ = [("n_lines", C.c_int64), ("offsets", C.c_void_p), ("items", C.c_void_p), ("cates", C.c_void_p),
+                ("durs", C.c_void_p), ("sats", C.c_void_p), ("plays", C.c_void_p), ("user_ids", C.c_void_p),
+                ("label_sat", C.c_void_p), ("label_play", C.c_void_p), ("tgt_item", C.c_void_p), ("tgt_cate", C.c_void_p),
+                ("tgt_dur", C.c_void_p)]
+
+
 class PamrecTensorInfo(C.Structure):
     _fields_ = [("name", C.c_char * 160), ("pool", C.c_int32), ("dtype", C.c_int32), ("flags", C.c_int32),
                 ("offset", C.c_int64), ("numel", C.c_int64), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
@@ -80,6 +87,11 @@ EXPORTS = {
     "pamrec_profile_count": (C.c_int, [C.c_void_p]),
     "pamrec_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pamrec_last_launch_count": (C.c_int64, [C.c_void_p]),
+    "pamrec_batcher_create": (C.c_int, [C.POINTER(PamrecLines), C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "pamrec_batcher_destroy": (C.c_int, [C.c_void_p]),
+    "pamrec_batcher_begin_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "pamrec_batcher_begin_eval": (C.c_int, [C.c_void_p, C.c_int]),
+    "pamrec_batcher_next": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
 }
 
 _lib = None

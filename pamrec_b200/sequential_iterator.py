@@ -3,11 +3,15 @@ sequential_iterator.py in the reference tree): same text formats, same batching 
 ``random`` call order, so batches are bit-identical to the reference's feed dicts — but the yielded
 mapping is keyed by strings (the placeholder names of IT:120-163) and there is no TensorFlow.
 
-Differences in HOW, not WHAT: a file is tokenised once into per-line numpy columns, the play-ratio
-bucket of every history element is computed once when the line is parsed (vectorised ``lisan``), and a
-training group writes its shared history window straight into the five rows of the batch arrays instead
-of deep-copying six Python lists five times (IT:677-682).
+Differences in HOW, not WHAT: a file is tokenised once into flat columns and the batching itself - the per-user
+history state machine of the training branch, the listwise groups, padding, masks, play-ratio buckets and the
+satisfied-only compaction - runs in native code (``csrc/batcher.cu``, host only, ``pamrec_batcher_*`` in
+include/pamrec_b200.h).  Python keeps the file parsing and every ``random`` call, in the reference's order.  The
+pure-Python batcher below is the same algorithm written out; it is used when noise injection is on (it draws from
+``np.random`` per element), when a file has ragged history columns, or with ``PAMREC_PY_ITERATOR=1``, and the tests
+hold the two implementations bit-identical.
 """
+import ctypes as C
 import os
 import random
 
@@ -147,10 +151,90 @@ class SequentialIterator:
         if batch_num_ngs > 0:
             # the reference's in-batch negative sampler is a commented-out block ending in exit(-1) (IT:801-1008)
             raise NotImplementedError("batch_num_ngs > 0 is not executable in the reference (IT:1008)")
+        native = self._native(infile, lines)
         if self.train:
-            yield from self._train_batches(lines)
+            yield from (self._train_batches_native(native, lines) if native else self._train_batches(lines))
         else:
-            yield from self._eval_batches(lines, min_seq_length)
+            yield from (self._eval_batches_native(native, min_seq_length) if native else self._eval_batches(lines, min_seq_length))
+
+    # ------------------------------------------------------------------ native batcher (csrc/batcher.cu)
+    def _native(self, infile, lines):
+        """Flat columns + a pamrec_batcher handle for this file, or None when the pure-Python path must be used."""
+        if os.environ.get("PAMREC_PY_ITERATOR", "0") == "1":
+            return None
+        if self.noise_train_hist != 0 or self.noise_train_listwise != 0 or self.batch_size % 5:
+            return None
+        cache = self.__dict__.setdefault("_native_cache", {})
+        key = (infile, self.train)
+        if key in cache:
+            return cache[key]
+        from . import _lib
+        lib = _lib.load()
+        h = 1 if self.train else 6                                   # first history column inside a parsed line
+        rows = [ln for ln in lines if ln]
+        lens = [len(ln[h]) for ln in rows]
+        if any(not (len(ln[h + 1]) == len(ln[h + 2]) == len(ln[h + 3]) == len(ln[h + 4]) == n) for ln, n in zip(rows, lens)):
+            cache[key] = None                                        # ragged columns: the reference zips them, keep Python
+            return None
+        cat = lambda j, dt: (np.concatenate([np.asarray(ln[j], dtype=dt) for ln in rows]) if rows else np.zeros(0, dt))
+        col = {"offsets": np.concatenate([[0], np.cumsum(lens)]).astype(np.int64), "items": cat(h, np.int32), "cates": cat(h + 1, np.int32),
+               "durs": cat(h + 2, np.float64), "sats": cat(h + 3, np.float64), "plays": cat(h + 4, np.float64)}
+        if self.train:
+            col["user_ids"] = np.asarray([ln[0] for ln in rows], np.int32)
+        else:
+            col["user_ids"] = np.asarray([ln[2] for ln in rows], np.int32)
+            col["label_sat"] = np.asarray([ln[0] for ln in rows], np.float64)
+            col["label_play"] = np.asarray([ln[1] for ln in rows], np.float64)
+            col["tgt_item"] = np.asarray([ln[3] for ln in rows], np.int32)
+            col["tgt_cate"] = np.asarray([ln[4] for ln in rows], np.int32)
+            col["tgt_dur"] = np.asarray([ln[5] for ln in rows], np.float64)
+        desc = _lib.PamrecLines(n_lines=len(rows), **{k: v.ctypes.data for k, v in col.items()})
+        borders = np.asarray(_borders(self.dataset, self.bucket_num), np.float64)
+        handle = C.c_void_p()
+        if lib.pamrec_batcher_create(C.byref(desc), borders.ctypes.data, len(borders), self.max_seq_length, C.byref(handle)) != 0:
+            raise RuntimeError("pamrec_batcher_create failed")
+        nat = dict(lib=lib, handle=handle, col=col, borders=borders, desc=desc, n=len(rows))
+        if self.train:
+            nat["sat_num"] = np.add.reduceat(col["sats"], col["offsets"][:-1]) if len(rows) else np.zeros(0)
+            nat["sat_num"] = np.where(np.asarray(lens) > 0, nat["sat_num"], 0.0)
+        cache[key] = nat
+        return nat
+
+    _FEED_DTYPES = (np.float32, np.float32, np.float32, np.float32, np.int32, np.int32, np.float32, np.int32, np.int32,
+                    np.float32, np.float32, np.float32, np.float32, np.float32, np.int32, np.int32, np.float32, np.float32, np.float32)
+
+    def _native_batches(self, nat):
+        T, bs = self.max_seq_length, self.batch_size
+        while True:
+            arrs = [np.empty((bs, T) if i >= 7 else ((bs, 1) if i < 3 else (bs,)), dt) for i, dt in enumerate(self._FEED_DTYPES)]
+            ptrs = (C.c_void_p * 19)(*[a.ctypes.data for a in arrs])
+            n = nat["lib"].pamrec_batcher_next(nat["handle"], bs, ptrs)
+            if n < 0:
+                raise RuntimeError(f"pamrec_batcher_next failed ({n})")
+            if n == 0:
+                return
+            yield {k: (a if n == bs else a[:n]) for k, a in zip(FEED_KEYS, arrs)}
+
+    def _train_batches_native(self, nat, lines):
+        G = self.BEGIN_HISTORY_LEN_MAX
+        order, begin = [], []
+        for idx, sn in enumerate(nat["sat_num"]):                    # file order: the RNG call sequence of IT:538-545
+            if sn < 2:
+                continue
+            begin.append(1 if sn <= G else random.randint(1, G))
+            order.append(idx)
+        pairs = list(zip(order, begin))
+        random.shuffle(pairs)                                        # IT:622 (a shuffle permutes by position only)
+        order = np.asarray([p[0] for p in pairs], np.int64)
+        begin = np.asarray([p[1] for p in pairs], np.int32)
+        if nat["lib"].pamrec_batcher_begin_train(nat["handle"], order.ctypes.data, begin.ctypes.data, len(order)) != 0:
+            raise RuntimeError("pamrec_batcher_begin_train failed")
+        yield from self._native_batches(nat)
+
+    def _eval_batches_native(self, nat, min_seq_length):
+        if nat["lib"].pamrec_batcher_begin_eval(nat["handle"], int(min_seq_length)) != 0:
+            raise RuntimeError("pamrec_batcher_begin_eval failed")
+        yield from self._native_batches(nat)
 
     def _new_acc(self):
         return {"sat": [], "lplay": [], "plays": [], "users": [], "items": [], "cates": [], "durs": [], "hist": []}

@@ -150,3 +150,74 @@ def test_iterator_edge_cases(tmp_path):
     with pytest.raises(NotImplementedError):
         next(it.load_data_from_file(str(d / "valid_data"), batch_num_ngs=4))
     assert list(it.load_data_from_file(str(d / "valid_data"), min_seq_length=1000)) == []
+
+
+@pytest.mark.parametrize("case", list(G.CASES))
+def test_native_batcher_equals_python_batcher(case, monkeypatch):
+    """csrc/batcher.cu against the pure-Python batcher of the same module: every array of every batch, two epochs
+    (the RNG state carries over) and the eval pass; then zero-duration / unsatisfied-eviction / long-history lines."""
+    with tempfile.TemporaryDirectory() as tmp:
+        data_dir = G.synth_case(case, tmp)
+        hp = G.hparams_for(case, data_dir)
+        monkeypatch.setenv("PAMREC_PY_ITERATOR", "1")
+        py = G.run_iterator(lambda: IT.SequentialIterator(hp, None), data_dir)
+        monkeypatch.setenv("PAMREC_PY_ITERATOR", "0")
+        it_holder = {}
+
+        def make():
+            it_holder["it"] = IT.SequentialIterator(hp, None)
+            return it_holder["it"]
+        nat = G.run_iterator(make, data_dir)
+        assert it_holder["it"].__dict__.get("_native_cache"), "the native batcher was not used"
+        assert all(v is not None for v in it_holder["it"]._native_cache.values())
+    for split in ("train", "valid"):
+        assert len(py[split]) == len(nat[split]) > 0
+        for i, (a, b) in enumerate(zip(py[split], nat[split])):
+            assert list(a) == list(b)
+            for k in a:
+                assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape, (split, i, k)
+                assert np.array_equal(a[k], b[k], equal_nan=True), (split, i, k)
+
+
+def test_native_batcher_hard_lines(tmp_path, monkeypatch):
+    """Lines built to hit the branches of add_a_item_to_hist (IT:479-522): > 100 kept items with and without
+    unsatisfied entries to evict, plays under 8 s that are dropped, zero durations (inf / NaN ratios)."""
+    import pickle
+    import random
+    d = tmp_path / "takatak"
+    d.mkdir()
+    rng = np.random.default_rng(5)
+    pickle.dump({"default_uid": 0, **{f"u{i}": i for i in range(1, 40)}}, open(d / "user_vocab.pkl", "wb"))
+    pickle.dump({"default_mid": 0, **{str(i): i for i in range(1, 500)}}, open(d / "item_vocab.pkl", "wb"))
+    pickle.dump({"default_cat": 0, **{f"c{i}": i for i in range(1, 9)}}, open(d / "category_vocab.pkl", "wb"))
+    (d / "takatak_business_recommenders.csv").write_text("1\t1\t10.0\n")
+    tr, ev = [], []
+    for u in range(1, 40):
+        n = int(rng.integers(8, 400))
+        items = rng.integers(1, 520, size=n)                       # some unknown tokens (>= 500)
+        cates = rng.integers(1, 9, size=n)
+        durs = rng.choice([0.0, 5.0, 12.5, 30.0], size=n, p=[0.05, 0.3, 0.35, 0.3])
+        p_sat = [0.0, 0.2, 0.6, 1.0][u % 4]                        # users with none / few / many / all satisfied
+        sats = (rng.random(n) < p_sat).astype(int)
+        plays = (rng.choice([500, 3000, 7999, 8000, 20000, 90000], size=n)).astype(int)
+        j = lambda a: ",".join(str(x) for x in a)
+        tr.append("\t".join([f"u{u}", j(items), j(f"c{c}" for c in cates), j(durs), j(sats), j(plays)]))
+        ev.append("\t".join([str(sats[-1]), str(plays[-1]), f"u{u}", str(items[-1]), f"c{cates[-1]}", str(durs[-1]), j(items[:-1]),
+                             j(f"c{c}" for c in cates[:-1]), j(durs[:-1]), j(sats[:-1]), j(plays[:-1])]))
+    (d / "train_data").write_text("\n".join(tr) + "\n")
+    (d / "valid_data").write_text("\n".join(ev) + "\n")
+    hp = DU.prepare_hparams(None, model_type="mmoe", dataset="takatak", bucket_num=10, batch_size=35, max_seq_length=50,
+                            noise_train_hist=0, noise_train_listwise=0, noise_only_predict=0, user_vocab=str(d / "user_vocab.pkl"),
+                            item_vocab=str(d / "item_vocab.pkl"), cate_vocab=str(d / "category_vocab.pkl"))
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PAMREC_PY_ITERATOR", mode)
+        random.seed(8)
+        it = IT.SequentialIterator(hp, None)
+        out[mode] = [list(it.load_data_from_file(str(d / "train_data"))) for _ in range(2)] + \
+                    [list(it.load_data_from_file(str(d / "valid_data"), min_seq_length=20))]
+    for pa, na in zip(out["1"], out["0"]):
+        assert len(pa) == len(na) > 0
+        for a, b in zip(pa, na):
+            for k in a:
+                assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k], equal_nan=True), k
