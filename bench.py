@@ -172,6 +172,39 @@ def hbm_microbench(pk, dev):
                                          peak=pk["hbm"], unit="GB/s", frac=byts / ms / 1e6 / pk["hbm"], bytes_per_row=6 * 64 + 4,
                                          note="TF-exact sparse Adam: m, v, w of EVERY row read and written (6 x 64 B) + 4 B slot")
     eng.close()
+    del eng
+    torch.cuda.empty_cache()
+    # ---- the sparse backward ("scatter") inside a real step at a batch large enough to be bandwidth-bound:
+    # 65 535 rows x 50 = 3.3 M lookups per table on the 10 M-item table, per-launcher CUDA events
+    from pamrec_b200 import synth
+    B2 = 65535
+    eng = Engine(50000, ni, nc, T, B2).allocate(str(dev))
+    eng.pool["item_w"].normal_(0, 0.01)
+    eng.pool["cate_w"].normal_(0, 0.01)
+    eng.pool["dense_param"].normal_(0, 0.05)
+    feed = synth.array_batch(77, B2, T, 50000, ni, nc, zipf_a=1.05)
+    db = eng.upload(feed)
+    for _ in range(2):
+        eng.train_step(db)
+    eng.profile(True)
+    reps = 3
+    for _ in range(reps):
+        eng.train_step(db)
+    tab = eng.profile_table()
+    eng.profile(False)
+    n_look = B2 * T + B2
+    ms = tab["sparse_segreduce"][0] / reps                   # item (16 floats) + cate (4 floats) launches of one step
+    byts = n_look * ((64 + 8) + (16 + 8))                    # gradient row + sorted key / source index, per lookup and table
+    out["sparse_scatter_segreduce"] = dict(kernel="k_seg_reduce<16> + k_seg_reduce<4>", lookups=n_look, ms=ms, achieved=byts / ms / 1e6,
+                                           peak=pk["hbm"], unit="GB/s", frac=byts / ms / 1e6 / pk["hbm"], bytes_per_lookup=96,
+                                           note="inside a full train step at B=65535, T=50 (Zipf 1.05 ids over 10 M items): 80 B of "
+                                                "gradient row + 16 B of sorted key / index per lookup; duplicate rows merge in-warp, "
+                                                "run tails leave by red.global.add.v4.f32")
+    ms = tab["embed_fwd"][0] / reps
+    byts = 248 * B2 * T
+    out["embed_fwd_in_step"] = dict(kernel="k_embed_fwd", lookups=B2 * T, ms=ms, achieved=byts / ms / 1e6, peak=pk["hbm"], unit="GB/s",
+                                    frac=byts / ms / 1e6 / pk["hbm"], note="same step; Zipf ids, so hot rows hit L2")
+    eng.close()
     return out
 
 
@@ -201,10 +234,19 @@ def run_ours(args, w, rank, world):
         torch.cuda.synchronize()
 
     # ---- value: inputs resident in HBM, device-timed per step, L2 flushed between steps
+    clocks = ClockSampler(torch.cuda.current_device()).start()      # sampled from the warm-up on: nvidia-smi needs ~0.2 s to start
     for i in range(W):
         eng.train_step(resident[i % N_POOL])
     barrier()
-    clocks = ClockSampler(torch.cuda.current_device()).start()
+    for _ in range(400):                                            # at least one clock sample before the timed region;
+        have = torch.tensor([1 if clocks.rows else 0], device=dev)  # every rank takes the same number of extra warm-up steps
+        if world > 1:
+            torch.distributed.all_reduce(have, op=torch.distributed.ReduceOp.MIN)
+        if int(have.item()):
+            break
+        eng.train_step(resident[0])
+        torch.cuda.synchronize()
+    barrier()
     evs = []
     t_wall0 = time.perf_counter()
     for i in range(K):

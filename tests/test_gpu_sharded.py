@@ -87,5 +87,6 @@ def test_two_rank_step_matches_oracle(small_allreduce):
            "--master-port", "29611" if small_allreduce == "mailbox" else "29613", os.path.join(ROOT, "tests", "dist_worker.py")]
     env = dict(os.environ, PAMREC_NO_MAILBOX="0" if small_allreduce == "mailbox" else "1")
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
-    print(r.stdout[-3000:])
-    assert r.returncode == 0 and "DIST_PARITY_OK" in r.stdout, r.stdout[-3000:]
+    fails = [ln for ln in r.stdout.splitlines() if "DIST_PARITY_FAIL" in ln]
+    print("\n".join(fails) or r.stdout[-3000:])
+    assert r.returncode == 0 and "DIST_PARITY_OK" in r.stdout, "\n".join(fails) + "\n" + r.stdout[-6000:]
