@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -64,6 +65,8 @@ struct PamrecHandle_ {
   // run fn(side) after everything enqueued on `main` so far
   template <typename F>
   void fork(cudaStream_t main, F fn) {
+    static const bool inline_side = getenv("PAMREC_NO_SIDE_STREAM") != nullptr;   // debugging aid: everything on one stream
+    if (inline_side) { fn(main); return; }
     cudaEvent_t e = ev_side[ev_next];
     ev_next = (ev_next + 1) % 12;
     cudaEventRecord(e, main);
@@ -71,6 +74,7 @@ struct PamrecHandle_ {
     fn(side);
   }
   void join(cudaStream_t main) {
+    if (getenv("PAMREC_NO_SIDE_STREAM") != nullptr) return;
     cudaEventRecord(ev_join, side);
     cudaStreamWaitEvent(main, ev_join, 0);
   }

@@ -13,7 +13,10 @@ constexpr int kE = PAMREC_EMB_DIM;    // 20
 constexpr int kD = PAMREC_D;          // 40
 constexpr int kNB = PAMREC_NBUCKET;   // 10
 constexpr int kDD = kD * kD;          // 1600
-constexpr int kTokTile = 128;         // tokens per CTA in the token-parallel kernels (thread == token)
+constexpr int kMT = 1;                // 16-row MMA tiles per warp in the token-tile kernels
+constexpr int kWarpRows = 16 * kMT;   // token rows owned by one warp
+constexpr int kTokThreads = 128;      // threads per CTA of the token-tile kernels (4 warps)
+constexpr int kTokTile = 4 * kWarpRows;  // tokens per CTA tile (64: three CTAs per SM, ~1.8 waves at the bench workload)
 constexpr int kRowPad = 41;           // smem row stride (floats) for thread==token tiles: conflict-free column walks
 constexpr int kAttnStride = 44;       // smem row stride for float4 row reads in the attention kernels
 constexpr float kMaskNeg = -4294967295.0f;  // -(2**32)+1, pamrec.py:276,780

@@ -2,7 +2,7 @@
 // key-masked attention, LayerNorm + point-wise FFN — forward and backward.
 //
 // Token-parallel kernels (projection, FFN): a CTA owns a tile of 128 token rows (40 floats each, shared-memory row
-// stride 44), warp w the rows 32w .. 32w+31, and every [tokens x 40] x [40 x 40] contraction - forward, input gradient
+// stride 44) of 64 tokens, warp w the rows 16w .. 16w+15, and every [tokens x 40] x [40 x 40] contraction - forward, input gradient
 // and weight gradient - runs on the tensor cores as an error-compensated 3xTF32 mma.sync (mma.cuh); LayerNorm and
 // its backward are evaluated in the MMA fragment layout (row sums are 4-lane shuffles).  Tokens are bucket-sorted
 // first so that a CTA needs exactly one (Wq,Wk,Wv)[bucket] triple: the reference instead materialises a
@@ -142,11 +142,11 @@ void launch_bucket_plan(const float* lt, int n, int* bucket, int* perm, int* ctl
 }
 
 // ------------------------------------------------------------------------------------------
-constexpr int kTileIt = (kTokTile * 10 + kTokTile - 1) / kTokTile;   // float4 per thread for a full 128 x 40 tile (= 10)
+constexpr int kTileIt = (kTokTile * 10 + kTokThreads - 1) / kTokThreads;   // float4 per thread for a full token tile
 
 // ------------------------------------------------------------------------------------------
 // N1 + A1 forward: qin = LN_a(x); Q = qin Wq[k], K = x Wk[k], V = x Wv[k]   (pamrec.py:521-522,714-728)
-// One bucket-sorted tile of up to 128 tokens per CTA, three 3xTF32 tensor-core GEMMs per warp (32 tokens each).
+// One bucket-sorted tile of up to kTokTile tokens per CTA, three 3xTF32 tensor-core GEMMs per warp (kWarpRows tokens each).
 // (definitions of kTS, load_split_mat, load_tile44, ln_row44 are further down with the FFN kernels)
 constexpr int kTS = 44;
 __device__ __forceinline__ void load_split_mat(uint32_t* __restrict__ hi, uint32_t* __restrict__ lo, const float* __restrict__ W, int tid);
@@ -154,11 +154,11 @@ __device__ __forceinline__ void load_tile44(float* __restrict__ dst, const float
 constexpr int kLnWriteF = 1, kLnWriteXhat = 2;
 __device__ __forceinline__ void ln_row44(float* __restrict__ row, const float* __restrict__ beta, const float* __restrict__ gamma,
                                          float& mean, float& rstd, int write);
-__device__ __forceinline__ void store_frag_rows(float* __restrict__ dst, const float (&c)[2][5][4], int64_t tok0, const int* toks,
+__device__ __forceinline__ void store_frag_rows(float* __restrict__ dst, const float (&c)[kMT][5][4], int64_t tok0, const int* toks,
                                                 int row_base, int cnt, int lane);
 
 constexpr int kProjFwdSmem = (6 * kDD + 2 * kTokTile * kTS + 2 * kD) * 4;
-__global__ void __launch_bounds__(kTokTile)
+__global__ void __launch_bounds__(kTokThreads)
 k_proj_fwd(const float* __restrict__ X, const int* __restrict__ perm, const int* __restrict__ ctl,
            const int* __restrict__ tile_bucket, const int* __restrict__ tile_begin, const int* __restrict__ tile_count,
            const float* __restrict__ Wq, const float* __restrict__ Wk, const float* __restrict__ Wv,
@@ -183,8 +183,8 @@ k_proj_fwd(const float* __restrict__ X, const int* __restrict__ perm, const int*
   __syncthreads();
   load_tile44(xs, X, toks, cnt, tid);
   __syncthreads();
-  {
-    // lane r of warp w: row 32w + r.  qin row -> shared (A operand of the Q GEMM) and -> global
+  if (tid < kTokTile) {
+    // thread r: row r.  qin row -> shared (A operand of the Q GEMM) and -> global
     float* xr = xs + tid * kTS;
     float* qr = qs + tid * kTS;
 #pragma unroll
@@ -197,21 +197,21 @@ k_proj_fwd(const float* __restrict__ X, const int* __restrict__ perm, const int*
       for (int i = 0; i < 10; ++i) st4(o + 4 * i, ld4(qr + 4 * i));
     }
   }
-  __syncwarp();
-  const float* xw = xs + 32 * w * kTS;
-  const float* qw = qs + 32 * w * kTS;
+  __syncthreads();
+  const float* xw = xs + kWarpRows * w * kTS;
+  const float* qw = qs + kWarpRows * w * kTS;
 #pragma unroll 1
   for (int m = 0; m < 3; ++m) {
-    float c[2][5][4];
+    float c[kMT][5][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 5; ++nt)
 #pragma unroll
         for (int q = 0; q < 4; ++q) c[mt][nt][q] = 0.f;
     const float* aw = m == 0 ? qw : xw;
-    warp_gemm_32x40x40<false>(c, [&](int r, int kk) { return aw[r * kTS + kk]; }, Whi + m * kDD, Wlo + m * kDD, lane);
-    store_frag_rows(m == 0 ? Q : (m == 1 ? K : V), c, 0, toks, 32 * w, cnt, lane);
+    warp_gemm_rows_x40x40<kMT, false>(c, [&](int r, int kk) { return aw[r * kTS + kk]; }, Whi + m * kDD, Wlo + m * kDD, lane);
+    store_frag_rows(m == 0 ? Q : (m == 1 ? K : V), c, 0, toks, kWarpRows * w, cnt, lane);
   }
 }
 
@@ -222,7 +222,7 @@ void launch_proj_fwd(const float* X, const int* perm, const int* ctl, const int*
   PAMREC_PROF("proj_fwd", 1, st);
   static bool once = false;
   if (!once) { cudaFuncSetAttribute(k_proj_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjFwdSmem); once = true; }
-  k_proj_fwd<<<max_tiles, kTokTile, kProjFwdSmem, st>>>(X, perm, ctl, tile_bucket, tile_begin, tile_count, Wq, Wk, Wv,
+  k_proj_fwd<<<max_tiles, kTokThreads, kProjFwdSmem, st>>>(X, perm, ctl, tile_bucket, tile_begin, tile_count, Wq, Wk, Wv,
                                                         ln_beta, ln_gamma, QIN, Q, K, V);
 }
 
@@ -339,22 +339,22 @@ void launch_attn_fwd(const float* Q, const float* K, const float* V, const float
 }
 
 // ------------------------------------------------------------------------------------------
-// Tensor-core token tiles (mma.cuh).  A CTA owns 128 consecutive tokens, warp w the rows 32w .. 32w+31; activation
+// Tensor-core token tiles (mma.cuh).  A CTA owns kTokTile consecutive tokens, warp w the rows kWarpRows*w ..; activation
 // tiles live in shared memory with row stride 44 (16-byte aligned rows; the m16n8k8 A-fragment pattern (row g, column t)
 // maps to banks 12g + t: conflict free), 40x40 weights as TF32 hi / lo halves with their natural stride 40.
 // split a 40x40 fp32 matrix into TF32 halves in shared memory
 __device__ __forceinline__ void load_split_mat(uint32_t* __restrict__ hi, uint32_t* __restrict__ lo, const float* __restrict__ W,
                                                int tid) {
-  constexpr int IT = (kDD / 4 + kTokTile - 1) / kTokTile;   // 4
+  constexpr int IT = (kDD / 4 + kTokThreads - 1) / kTokThreads;   // 4
   float4 v[IT];
 #pragma unroll
   for (int it = 0; it < IT; ++it) {
-    const int i = tid + it * kTokTile;
+    const int i = tid + it * kTokThreads;
     if (i < kDD / 4) v[it] = ld4(W + 4 * i);
   }
 #pragma unroll
   for (int it = 0; it < IT; ++it) {
-    const int i = tid + it * kTokTile;
+    const int i = tid + it * kTokThreads;
     if (i < kDD / 4) {
       uint4 h, l;
       split_tf32(v[it].x, h.x, l.x); split_tf32(v[it].y, h.y, l.y); split_tf32(v[it].z, h.z, l.z); split_tf32(v[it].w, h.w, l.w);
@@ -368,14 +368,14 @@ __device__ __forceinline__ void load_tile44(float* __restrict__ dst, const float
   float4 v[kTileIt];
 #pragma unroll
   for (int it = 0; it < kTileIt; ++it) {
-    const int i = tid + it * kTokTile;
+    const int i = tid + it * kTokThreads;
     const int r = i / 10, c = i % 10;
     v[it] = f4_zero();
     if (r < cnt) v[it] = toks ? ld4(src + (int64_t)toks[r] * kD + 4 * c) : ld4(src + 4 * (int64_t)i);
   }
 #pragma unroll
   for (int it = 0; it < kTileIt; ++it) {
-    const int i = tid + it * kTokTile;
+    const int i = tid + it * kTokThreads;
     st4(dst + (i / 10) * kTS + 4 * (i % 10), v[it]);
   }
 }
@@ -412,7 +412,7 @@ __device__ __forceinline__ void ln_row44(float* __restrict__ row, const float* _
 // ------------------------------------------------------------------------------------------
 // N1 + F1 forward: f = LN_b(y); out = relu(f W1 + b1) W2 + b2 + f     (pamrec.py:534-535,565-577)
 constexpr int kFfnFwdSmem = (4 * kDD + 2 * kTokTile * kTS + 4 * kD) * 4;
-__global__ void __launch_bounds__(kTokTile)
+__global__ void __launch_bounds__(kTokThreads)
 k_ffn_fwd(const float* __restrict__ Y, const float* __restrict__ W1, const float* __restrict__ b1,
           const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ ln_beta,
           const float* __restrict__ ln_gamma, float* __restrict__ OUT, int n_tok) {
@@ -432,25 +432,25 @@ k_ffn_fwd(const float* __restrict__ Y, const float* __restrict__ W1, const float
   if (tid < kD) { pr[tid] = b1[tid]; pr[kD + tid] = b2[tid]; pr[2 * kD + tid] = ln_beta[tid]; pr[3 * kD + tid] = ln_gamma[tid]; }
   load_tile44(fs, Y + tok0 * kD, nullptr, cnt, tid);
   __syncthreads();
-  {
+  if (tid < kTokTile) {
     float mean, rstd;
-    ln_row44(fs + tid * kTS, pr + 2 * kD, pr + 3 * kD, mean, rstd, kLnWriteF);  // lane r of warp w normalises row 32w + r
+    ln_row44(fs + tid * kTS, pr + 2 * kD, pr + 3 * kD, mean, rstd, kLnWriteF);  // thread r normalises row r
   }
-  __syncwarp();
+  __syncthreads();
   const int g = lane >> 2, t = lane & 3;
-  const float* fw = fs + 32 * w * kTS;
-  float* hw = hs + 32 * w * kTS;
-  float c[2][5][4];
+  const float* fw = fs + kWarpRows * w * kTS;
+  float* hw = hs + kWarpRows * w * kTS;
+  float c[kMT][5][4];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 5; ++nt) {
       const float b0 = pr[8 * nt + 2 * t], bb1 = pr[8 * nt + 2 * t + 1];
       c[mt][nt][0] = b0; c[mt][nt][1] = bb1; c[mt][nt][2] = b0; c[mt][nt][3] = bb1;
     }
-  warp_gemm_32x40x40<false>(c, [&](int r, int k) { return fw[r * kTS + k]; }, W1hi, W1lo, lane);
+  warp_gemm_rows_x40x40<kMT, false>(c, [&](int r, int k) { return fw[r * kTS + k]; }, W1hi, W1lo, lane);
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 5; ++nt) {
       const int r = 16 * mt + g, col = 8 * nt + 2 * t;
@@ -459,7 +459,7 @@ k_ffn_fwd(const float* __restrict__ Y, const float* __restrict__ W1, const float
     }
   __syncwarp();
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 5; ++nt) {
       const int r = 16 * mt + g, col = 8 * nt + 2 * t;
@@ -468,12 +468,12 @@ k_ffn_fwd(const float* __restrict__ Y, const float* __restrict__ W1, const float
       const float b0 = pr[kD + col], bb1 = pr[kD + col + 1];
       c[mt][nt][0] = b0 + f0.x; c[mt][nt][1] = bb1 + f0.y; c[mt][nt][2] = b0 + f1.x; c[mt][nt][3] = bb1 + f1.y;
     }
-  warp_gemm_32x40x40<false>(c, [&](int r, int k) { return hw[r * kTS + k]; }, W2hi, W2lo, lane);
+  warp_gemm_rows_x40x40<kMT, false>(c, [&](int r, int k) { return hw[r * kTS + k]; }, W2hi, W2lo, lane);
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 5; ++nt) {
-      const int r = 32 * w + 16 * mt + g, col = 8 * nt + 2 * t;
+      const int r = kWarpRows * w + 16 * mt + g, col = 8 * nt + 2 * t;
       if (r < cnt) *reinterpret_cast<float2*>(OUT + (tok0 + r) * kD + col) = make_float2(c[mt][nt][0], c[mt][nt][1]);
       if (r + 8 < cnt) *reinterpret_cast<float2*>(OUT + (tok0 + r + 8) * kD + col) = make_float2(c[mt][nt][2], c[mt][nt][3]);
     }
@@ -485,23 +485,23 @@ void launch_ffn_fwd(const float* Y, const float* W1, const float* b1, const floa
   if (n_tok == 0) return;
   static bool once = false;
   if (!once) { cudaFuncSetAttribute(k_ffn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnFwdSmem); once = true; }
-  k_ffn_fwd<<<(n_tok + kTokTile - 1) / kTokTile, kTokTile, kFfnFwdSmem, st>>>(Y, W1, b1, W2, b2, ln_beta, ln_gamma, OUT, n_tok);
+  k_ffn_fwd<<<(n_tok + kTokTile - 1) / kTokTile, kTokThreads, kFfnFwdSmem, st>>>(Y, W1, b1, W2, b2, ln_beta, ln_gamma, OUT, n_tok);
 }
 
 // ------------------------------------------------------------------------------------------
 // shared pieces of the two backward kernels
-// LayerNorm backward in C-fragment layout.  d[mt][nt][4] holds dF (grad wrt f = gamma * xhat + beta) of the warp's 32 rows;
+// LayerNorm backward in C-fragment layout.  d[mt][nt][4] holds dF (grad wrt f = gamma * xhat + beta) of the warp's rows;
 // xhat2(r, col) returns xhat[r][col .. col+1] of the warp's rows, rstd_w is their 1/std.  On return d holds dY (grad wrt the LN input); the column sums
 // dbeta = sum dF and dgamma = sum dF * xhat of the warp's rows are added to red[0..39] / red[40..79] (shared memory).
 template <typename XF>
-__device__ __forceinline__ void ln_bwd_frag(float (&d)[2][5][4], XF xhat2, const float* __restrict__ rstd_w,
+__device__ __forceinline__ void ln_bwd_frag(float (&d)[kMT][5][4], XF xhat2, const float* __restrict__ rstd_w,
                                             const float* __restrict__ gamma, float* __restrict__ red, int lane) {
   const int g = lane >> 2, t = lane & 3;
   float sb[5][2], sg[5][2];
 #pragma unroll
   for (int nt = 0; nt < 5; ++nt) { sb[nt][0] = sb[nt][1] = sg[nt][0] = sg[nt][1] = 0.f; }
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
+  for (int mt = 0; mt < kMT; ++mt) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {                       // h = 0: row g, h = 1: row g + 8
       const int r = 16 * mt + g + 8 * h;
@@ -542,11 +542,11 @@ __device__ __forceinline__ void ln_bwd_frag(float (&d)[2][5][4], XF xhat2, const
     }
 }
 // store the warp's 32 x 40 C fragments to rows tok0 + r (r < cnt) of a [*, 40] global matrix; toks != nullptr: permuted rows
-__device__ __forceinline__ void store_frag_rows(float* __restrict__ dst, const float (&c)[2][5][4], int64_t tok0, const int* toks,
+__device__ __forceinline__ void store_frag_rows(float* __restrict__ dst, const float (&c)[kMT][5][4], int64_t tok0, const int* toks,
                                                 int row_base, int cnt, int lane) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int r = row_base + 16 * mt + g + 8 * h;
@@ -560,12 +560,12 @@ __device__ __forceinline__ void store_frag_rows(float* __restrict__ dst, const f
 
 // ------------------------------------------------------------------------------------------
 // FFN + LN_b backward.  In: dOUT (grad of block output), Y.  Out: dY, and atomically
-// accumulated dW1, db1, dW2, db2, dbeta, dgamma.  Five 3xTF32 tensor-core GEMMs per 128-token tile:
+// accumulated dW1, db1, dW2, db2, dbeta, dgamma.  Five 3xTF32 tensor-core GEMMs per token tile:
 //   h = relu(f W1 + b1) [recomputed],  dH = dOUT W2^T,  dF = dOUT + (dH o relu') W1^T,
 //   [dW2; db2] = [h 1]^T dOUT,  [dW1; db1] = [f 1]^T (dH o relu')      (weight gradients: warp-private 32-token slices,
 //   merged in shared memory, one global atomic per element and CTA).
 constexpr int kFfnBwdSmem = (4 * kDD + 3 * kTokTile * kTS + 2 * 41 * kD + 4 * kD + 2 * kD + kTokTile) * 4;
-__global__ void __launch_bounds__(kTokTile)
+__global__ void __launch_bounds__(kTokThreads)
 k_ffn_bwd(const float* __restrict__ Y, const float* __restrict__ dOUT, const float* __restrict__ W1,
           const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ ln_beta,
           const float* __restrict__ ln_gamma, float* __restrict__ dY, float* __restrict__ dW1, float* __restrict__ db1,
@@ -592,34 +592,34 @@ k_ffn_bwd(const float* __restrict__ Y, const float* __restrict__ dOUT, const flo
   load_split_mat(W2hi, W2lo, W2, tid);
   if (tid < kD) { pr[tid] = b1[tid]; pr[2 * kD + tid] = ln_beta[tid]; pr[3 * kD + tid] = ln_gamma[tid]; }
   if (tid < 2 * kD) red[tid] = 0.f;
-  for (int i = tid; i < 2 * 41 * kD; i += kTokTile) acc2[i] = 0.f;
+  for (int i = tid; i < 2 * 41 * kD; i += kTokThreads) acc2[i] = 0.f;
   load_tile44(xs, Y + tok0 * kD, nullptr, cnt, tid);
   load_tile44(gs, dOUT + tok0 * kD, nullptr, cnt, tid);
   __syncthreads();
-  {
+  if (tid < kTokTile) {
     float mean, rstd;
     ln_row44(xs + tid * kTS, pr + 2 * kD, pr + 3 * kD, mean, rstd, kLnWriteXhat);
     rstd_s[tid] = rstd;
   }
-  __syncwarp();
-  const float* xw = xs + 32 * w * kTS;
-  float* hw = hs + 32 * w * kTS;
-  const float* gw = gs + 32 * w * kTS;
+  __syncthreads();
+  const float* xw = xs + kWarpRows * w * kTS;
+  float* hw = hs + kWarpRows * w * kTS;
+  const float* gw = gs + kWarpRows * w * kTS;
   const float* beta = pr + 2 * kD;
   const float* gamma = pr + 3 * kD;
   auto f_elem = [&](int r, int k) { return fmaf(gamma[k], xw[r * kTS + k], beta[k]); };
-  float c[2][5][4];
+  float c[kMT][5][4];
   // ---- h = relu(f W1 + b1)
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 5; ++nt) {
       const float b0 = pr[8 * nt + 2 * t], bb1 = pr[8 * nt + 2 * t + 1];
       c[mt][nt][0] = b0; c[mt][nt][1] = bb1; c[mt][nt][2] = b0; c[mt][nt][3] = bb1;
     }
-  warp_gemm_32x40x40<false>(c, f_elem, W1hi, W1lo, lane);
+  warp_gemm_rows_x40x40<kMT, false>(c, f_elem, W1hi, W1lo, lane);
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 5; ++nt) {
       const int r = 16 * mt + g, col = 8 * nt + 2 * t;
@@ -629,14 +629,14 @@ k_ffn_bwd(const float* __restrict__ Y, const float* __restrict__ dOUT, const flo
   __syncwarp();
   // ---- dH = dOUT W2^T, masked by relu'
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 5; ++nt)
 #pragma unroll
       for (int q = 0; q < 4; ++q) c[mt][nt][q] = 0.f;
-  warp_gemm_32x40x40<true>(c, [&](int r, int k) { return gw[r * kTS + k]; }, W2hi, W2lo, lane);
+  warp_gemm_rows_x40x40<kMT, true>(c, [&](int r, int k) { return gw[r * kTS + k]; }, W2hi, W2lo, lane);
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 5; ++nt) {
       const int r = 16 * mt + g, col = 8 * nt + 2 * t;
@@ -656,14 +656,14 @@ k_ffn_bwd(const float* __restrict__ Y, const float* __restrict__ dOUT, const flo
       for (int nt = 0; nt < 5; ++nt)
 #pragma unroll
         for (int q = 0; q < 4; ++q) cw[mt][nt][q] = 0.f;
-    warp_gemm_tn_48x40(cw, 32, [&](int r, int i) { return i < kD ? hw[r * kTS + i] : (i == kD ? 1.f : 0.f); },
+    warp_gemm_tn_48x40(cw, kWarpRows, [&](int r, int i) { return i < kD ? hw[r * kTS + i] : (i == kD ? 1.f : 0.f); },
                        [&](int r, int n) { return gw[r * kTS + n]; }, lane);
     tn_flush_smem(cw, acc2, lane);
   }
   __syncwarp();
   // ---- hs <- dH o relu'
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 5; ++nt) {
       const int r = 16 * mt + g, col = 8 * nt + 2 * t;
@@ -673,7 +673,7 @@ k_ffn_bwd(const float* __restrict__ Y, const float* __restrict__ dOUT, const flo
   __syncwarp();
   // ---- dF = dOUT + (dH o relu') W1^T
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 5; ++nt) {
       const int r = 16 * mt + g, col = 8 * nt + 2 * t;
@@ -681,7 +681,7 @@ k_ffn_bwd(const float* __restrict__ Y, const float* __restrict__ dOUT, const flo
       const float2 g1 = *reinterpret_cast<const float2*>(gw + (r + 8) * kTS + col);
       c[mt][nt][0] = g0.x; c[mt][nt][1] = g0.y; c[mt][nt][2] = g1.x; c[mt][nt][3] = g1.y;
     }
-  warp_gemm_32x40x40<true>(c, [&](int r, int k) { return hw[r * kTS + k]; }, W1hi, W1lo, lane);
+  warp_gemm_rows_x40x40<kMT, true>(c, [&](int r, int k) { return hw[r * kTS + k]; }, W1hi, W1lo, lane);
   // ---- [dW1; db1] += [f 1]^T (dH o relu')
   {
     float cw[3][5][4];
@@ -691,15 +691,15 @@ k_ffn_bwd(const float* __restrict__ Y, const float* __restrict__ dOUT, const flo
       for (int nt = 0; nt < 5; ++nt)
 #pragma unroll
         for (int q = 0; q < 4; ++q) cw[mt][nt][q] = 0.f;
-    warp_gemm_tn_48x40(cw, 32, [&](int r, int i) { return i < kD ? f_elem(r, i) : (i == kD ? 1.f : 0.f); },
+    warp_gemm_tn_48x40(cw, kWarpRows, [&](int r, int i) { return i < kD ? f_elem(r, i) : (i == kD ? 1.f : 0.f); },
                        [&](int r, int n) { return hw[r * kTS + n]; }, lane);
     tn_flush_smem(cw, acc1, lane);
   }
   // ---- LN_b backward, dY out
-  ln_bwd_frag(c, [&](int r, int col) { return *reinterpret_cast<const float2*>(xw + r * kTS + col); }, rstd_s + 32 * w, gamma, red, lane);
-  store_frag_rows(dY, c, tok0, nullptr, 32 * w, cnt, lane);
+  ln_bwd_frag(c, [&](int r, int col) { return *reinterpret_cast<const float2*>(xw + r * kTS + col); }, rstd_s + kWarpRows * w, gamma, red, lane);
+  store_frag_rows(dY, c, tok0, nullptr, kWarpRows * w, cnt, lane);
   __syncthreads();
-  for (int i = tid; i < kDD; i += kTokTile) { atomicAdd(dW2 + i, acc2[i]); atomicAdd(dW1 + i, acc1[i]); }
+  for (int i = tid; i < kDD; i += kTokThreads) { atomicAdd(dW2 + i, acc2[i]); atomicAdd(dW1 + i, acc1[i]); }
   if (tid < kD) {
     atomicAdd(db2 + tid, acc2[kDD + tid]); atomicAdd(db1 + tid, acc1[kDD + tid]);
     atomicAdd(dbeta + tid, red[tid]); atomicAdd(dgamma + tid, red[kD + tid]);
@@ -713,7 +713,7 @@ void launch_ffn_bwd(const float* Y, const float* dOUT, const float* W1, const fl
   if (n_tok == 0) return;
   static bool once = false;
   if (!once) { cudaFuncSetAttribute(k_ffn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnBwdSmem); once = true; }
-  k_ffn_bwd<<<(n_tok + kTokTile - 1) / kTokTile, kTokTile, kFfnBwdSmem, st>>>(Y, dOUT, W1, b1, W2, ln_beta, ln_gamma, dY, dW1,
+  k_ffn_bwd<<<(n_tok + kTokTile - 1) / kTokTile, kTokThreads, kFfnBwdSmem, st>>>(Y, dOUT, W1, b1, W2, ln_beta, ln_gamma, dY, dW1,
                                                                              db1, dW2, db2, dbeta, dgamma, n_tok);
 }
 
@@ -832,8 +832,8 @@ void launch_attn_bwd(const float* Q, const float* K, const float* V, const float
 // Projection + LN_a backward (bucket-sorted tiles).  In: X (block input), dY (residual path into qin), dQ, dK, dV.
 // Out: dX; atomically accumulated dWq/dWk/dWv[bucket], dbeta, dgamma.  Six 3xTF32 tensor-core GEMMs per tile:
 //   dqin = dY + dQ Wq^T,   dX = dK Wk^T + dV Wv^T + LN_a'(dqin),   dWq = qin^T dQ,  dWk = x^T dK,  dWv = x^T dV.
-constexpr int kProjBwdSmem = (6 * kDD + 2 * kTokTile * kTS + 3 * kDD + 2 * kD + 2 * kD + 2 * kTokTile) * 4;
-__global__ void __launch_bounds__(kTokTile)
+constexpr int kProjBwdSmem = (6 * kDD + 2 * kTokTile * kTS + kDD + 2 * kD + 2 * kD + 2 * kTokTile) * 4;
+__global__ void __launch_bounds__(kTokThreads)
 k_proj_bwd(const float* __restrict__ X, const float* __restrict__ dY, const float* __restrict__ dQ,
            const float* __restrict__ dK, const float* __restrict__ dV, const int* __restrict__ perm,
            const int* __restrict__ ctl, const int* __restrict__ tile_bucket, const int* __restrict__ tile_begin,
@@ -848,8 +848,8 @@ k_proj_bwd(const float* __restrict__ X, const float* __restrict__ dY, const floa
   uint32_t* Wlo = Whi + 3 * kDD;
   float* xs = sm + 6 * kDD;                                 // x (raw)
   float* gs = xs + kTokTile * kTS;                          // dQ, then dK, then dV
-  float* acc = gs + kTokTile * kTS;                         // [3][40][40] weight-gradient partial sums of this CTA
-  float* lnp = acc + 3 * kDD;                               // beta | gamma
+  float* acc = gs + kTokTile * kTS;                         // [40][40] weight-gradient partial sums of this CTA (one matrix at a time)
+  float* lnp = acc + kDD;                                   // beta | gamma
   float* red = lnp + 2 * kD;                                // dbeta | dgamma
   float* mean_s = red + 2 * kD;
   float* rstd_s = mean_s + kTokTile;
@@ -862,33 +862,33 @@ k_proj_bwd(const float* __restrict__ X, const float* __restrict__ dY, const floa
   load_split_mat(Whi + 2 * kDD, Wlo + 2 * kDD, Wv + (int64_t)k * kDD, tid);
   if (tid < kD) { lnp[tid] = ln_beta[tid]; lnp[kD + tid] = ln_gamma[tid]; }
   if (tid < 2 * kD) red[tid] = 0.f;
-  for (int i = tid; i < 3 * kDD; i += kTokTile) acc[i] = 0.f;
+  for (int i = tid; i < kDD; i += kTokThreads) acc[i] = 0.f;
   if (tid < cnt) toks[tid] = perm[begin + tid];
   __syncthreads();
   load_tile44(xs, X, toks, cnt, tid);
   load_tile44(gs, dQ, toks, cnt, tid);
   __syncthreads();
-  {
+  if (tid < kTokTile) {
     float mean, rstd;
     ln_row44(xs + tid * kTS, lnp, lnp + kD, mean, rstd, 0);
     mean_s[tid] = mean; rstd_s[tid] = rstd;
   }
-  __syncwarp();
-  const float* xw = xs + 32 * w * kTS;
-  const float* gw = gs + 32 * w * kTS;
-  const float* mw = mean_s + 32 * w;
-  const float* rw = rstd_s + 32 * w;
+  __syncthreads();
+  const float* xw = xs + kWarpRows * w * kTS;
+  const float* gw = gs + kWarpRows * w * kTS;
+  const float* mw = mean_s + kWarpRows * w;
+  const float* rw = rstd_s + kWarpRows * w;
   const float* beta = lnp;
   const float* gamma = lnp + kD;
   auto xhat = [&](int r, int i) { return (xw[r * kTS + i] - mw[r]) * rw[r]; };
   auto g_elem = [&](int r, int kk) { return gw[r * kTS + kk]; };
-  float dqin[2][5][4], dx[2][5][4];
+  float dqin[kMT][5][4], dx[kMT][5][4];
   // ---- dqin = dY + dQ Wq^T
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int r = 32 * w + 16 * mt + g + 8 * h;
+      const int r = kWarpRows * w + 16 * mt + g + 8 * h;
       const float* src = dY + (int64_t)toks[r < cnt ? r : 0] * kD + 2 * t;
 #pragma unroll
       for (int nt = 0; nt < 5; ++nt) {
@@ -896,7 +896,7 @@ k_proj_bwd(const float* __restrict__ X, const float* __restrict__ dY, const floa
         dqin[mt][nt][2 * h] = v.x; dqin[mt][nt][2 * h + 1] = v.y;
       }
     }
-  warp_gemm_32x40x40<true>(dqin, g_elem, Whi, Wlo, lane);
+  warp_gemm_rows_x40x40<kMT, true>(dqin, g_elem, Whi, Wlo, lane);
   {
     float cw[3][5][4];
 #pragma unroll
@@ -905,12 +905,19 @@ k_proj_bwd(const float* __restrict__ X, const float* __restrict__ dY, const floa
       for (int nt = 0; nt < 5; ++nt)
 #pragma unroll
         for (int q = 0; q < 4; ++q) cw[mt][nt][q] = 0.f;
-    warp_gemm_tn_48x40(cw, 32, [&](int r, int i) { return i < kD ? fmaf(gamma[i], xhat(r, i), beta[i]) : 0.f; }, g_elem, lane);
+    warp_gemm_tn_48x40(cw, kWarpRows, [&](int r, int i) { return i < kD ? fmaf(gamma[i], xhat(r, i), beta[i]) : 0.f; }, g_elem, lane);
     tn_flush_smem(cw, acc, lane, kD - 1);
   }
+  float* dWs[3] = {dWq + (int64_t)k * kDD, dWk + (int64_t)k * kDD, dWv + (int64_t)k * kDD};
+  // one global atomic per element and CTA; the accumulator is cleared for the next matrix (barriers: top of the loop below)
+  auto flush_acc = [&](float* dW) {
+    __syncthreads();
+    for (int i = tid; i < kDD; i += kTokThreads) { atomicAdd(dW + i, acc[i]); acc[i] = 0.f; }
+  };
+  flush_acc(dWs[0]);
   // ---- dX = dK Wk^T + dV Wv^T (+ LN backward below)
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 5; ++nt)
 #pragma unroll
@@ -920,7 +927,7 @@ k_proj_bwd(const float* __restrict__ X, const float* __restrict__ dY, const floa
     __syncthreads();                                    // every warp is done with the previous gradient tile
     load_tile44(gs, m == 1 ? dK : dV, toks, cnt, tid);
     __syncthreads();
-    warp_gemm_32x40x40<true>(dx, g_elem, Whi + m * kDD, Wlo + m * kDD, lane);
+    warp_gemm_rows_x40x40<kMT, true>(dx, g_elem, Whi + m * kDD, Wlo + m * kDD, lane);
     float cw[3][5][4];
 #pragma unroll
     for (int mt = 0; mt < 3; ++mt)
@@ -928,23 +935,20 @@ k_proj_bwd(const float* __restrict__ X, const float* __restrict__ dY, const floa
       for (int nt = 0; nt < 5; ++nt)
 #pragma unroll
         for (int q = 0; q < 4; ++q) cw[mt][nt][q] = 0.f;
-    warp_gemm_tn_48x40(cw, 32, [&](int r, int i) { return i < kD ? xw[r * kTS + i] : 0.f; }, g_elem, lane);
-    tn_flush_smem(cw, acc + m * kDD, lane, kD - 1);
+    warp_gemm_tn_48x40(cw, kWarpRows, [&](int r, int i) { return i < kD ? xw[r * kTS + i] : 0.f; }, g_elem, lane);
+    tn_flush_smem(cw, acc, lane, kD - 1);
+    flush_acc(dWs[m]);
   }
   // ---- LN_a backward of dqin, added to dX
   ln_bwd_frag(dqin, [&](int r, int col) { return make_float2(xhat(r, col), xhat(r, col + 1)); }, rw, gamma, red, lane);
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 5; ++nt)
 #pragma unroll
       for (int q = 0; q < 4; ++q) dx[mt][nt][q] += dqin[mt][nt][q];
-  store_frag_rows(dX, dx, 0, toks, 32 * w, cnt, lane);
+  store_frag_rows(dX, dx, 0, toks, kWarpRows * w, cnt, lane);
   __syncthreads();
-  float* dWs[3] = {dWq + (int64_t)k * kDD, dWk + (int64_t)k * kDD, dWv + (int64_t)k * kDD};
-  for (int i = tid; i < kDD; i += kTokTile) {
-    atomicAdd(dWs[0] + i, acc[i]); atomicAdd(dWs[1] + i, acc[kDD + i]); atomicAdd(dWs[2] + i, acc[2 * kDD + i]);
-  }
   if (tid < kD) { atomicAdd(dbeta + tid, red[tid]); atomicAdd(dgamma + tid, red[kD + tid]); }
 }
 
@@ -955,7 +959,7 @@ void launch_proj_bwd(const float* X, const float* dY, const float* dQ, const flo
   PAMREC_PROF("proj_bwd", 1, st);
   static bool once = false;
   if (!once) { cudaFuncSetAttribute(k_proj_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjBwdSmem); once = true; }
-  k_proj_bwd<<<max_tiles, kTokTile, kProjBwdSmem, st>>>(X, dY, dQ, dK, dV, perm, ctl, tile_bucket, tile_begin, tile_count, Wq,
+  k_proj_bwd<<<max_tiles, kTokThreads, kProjBwdSmem, st>>>(X, dY, dQ, dK, dV, perm, ctl, tile_bucket, tile_begin, tile_count, Wq,
                                                         Wk, Wv, ln_beta, ln_gamma, dX, dWq, dWk, dWv, dbeta, dgamma);
 }
 

@@ -38,21 +38,21 @@ __device__ __forceinline__ void mma_3xtf32(float (&d)[4], const uint32_t (&ahi)[
   mma_tf32(d, ahi, bhi);
 }
 
-// C[32 x 40] += A[32 x 40] * B[40 x 40] for one warp.
-//   a_elem(r, k): element of the warp's 32 x 40 A operand (r in 0..31), evaluated once per element;
+// C[16 MT x 40] += A[16 MT x 40] * B[40 x 40] for one warp.
+//   a_elem(r, k): element of the warp's A operand (r in 0 .. 16 MT - 1), evaluated once per element;
 //   Bhi / Blo   : the 40 x 40 B operand pre-split into TF32 halves, row major with leading dimension 40;
 //                 TRANS_B multiplies by B^T instead (B[n][k] is read where B[k][n] would be).
 //   c[mt][nt][4]: accumulator fragments, row tile mt (16 rows), column tile nt (8 columns).
-template <bool TRANS_B, typename AF>
-__device__ __forceinline__ void warp_gemm_32x40x40(float (&c)[2][5][4], AF a_elem, const uint32_t* __restrict__ Bhi,
-                                                   const uint32_t* __restrict__ Blo, int lane) {
+template <int MT, bool TRANS_B, typename AF>
+__device__ __forceinline__ void warp_gemm_rows_x40x40(float (&c)[MT][5][4], AF a_elem, const uint32_t* __restrict__ Bhi,
+                                                      const uint32_t* __restrict__ Blo, int lane) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int k0 = 0; k0 < 5; ++k0) {
     const int k = 8 * k0;
-    uint32_t ahi[2][4], alo[2][4];
+    uint32_t ahi[MT][4], alo[MT][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
       const int r = 16 * mt + g;
       split_tf32(a_elem(r, k + t), ahi[mt][0], alo[mt][0]);
       split_tf32(a_elem(r + 8, k + t), ahi[mt][1], alo[mt][1]);
@@ -67,7 +67,7 @@ __device__ __forceinline__ void warp_gemm_32x40x40(float (&c)[2][5][4], AF a_ele
       const uint32_t bh[2] = {Bhi[i0], Bhi[i1]};
       const uint32_t bl[2] = {Blo[i0], Blo[i1]};
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) mma_3xtf32(c[mt][nt], ahi[mt], alo[mt], bh, bl);
+      for (int mt = 0; mt < MT; ++mt) mma_3xtf32(c[mt][nt], ahi[mt], alo[mt], bh, bl);
     }
   }
 }

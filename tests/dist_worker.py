@@ -1,8 +1,19 @@
 """One rank of the multi-GPU parity check (launched by tests/test_gpu_sharded.py through torch.distributed.run).
 
 Every rank builds the SAME oracle and the SAME global batches from seeds, trains on its own share (listwise groups dealt
-round-robin, tables row-sharded), and rank 0 compares losses, the gathered tables, dense variables, BN statistics and a
-data-parallel scoring pass with the fp64 oracle run on the whole global batch."""
+round-robin, tables row-sharded), and compares with the fp64 oracle run on the whole global batch:
+
+* step 0 (same weights): losses, the all-reduced dense gradients, the global clip norms of the sparse tables, Adam's first
+  moment of every table row (= the owner-side merge of the row gradients of all ranks) - Adam is invariant to the scale of a
+  gradient, so these are checked directly rather than through the weights;
+* steps 1, 2: losses, then tables / dense variables / BN moving statistics on the scale of one optimiser step;
+* replicated dense parameters bit-identical on every rank; a step in which the last rank has NO rows; data-parallel scoring.
+
+ReLU kinks.  The gradient of the head is discontinuous where a batch-normalised pre-activation crosses 0, and every step has
+a few of the ~250 K such values within 1e-5 of 0 - inside the fp32 rounding of the forward pass.  When this implementation
+and the fp64 oracle land on different sides, one unit's gradient differs at O(1) and, through the batch statistics, every
+row's a little: neither is wrong.  The worker detects exactly that (it compares the ReLU masks of the two forward passes)
+and, if it happens, repeats the whole comparison on the next seed set instead of comparing beyond the kink."""
 import os
 import sys
 
@@ -14,8 +25,166 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 from oracle import pamrec_oracle as O  # noqa: E402  (checker only)
+from pamrec_b200 import _lib as L  # noqa: E402
 from pamrec_b200 import dist as D  # noqa: E402
 from pamrec_b200.engine import Engine  # noqa: E402
+
+EMB = "sequential/embedding/"
+NAMES = ("loss", "data_loss", "regular_loss", "auxiliary_data_loss", "order_loss")
+P_ = "sequential/pamrec/"
+# head BN layers: engine pre-activation buffer, its BN statistics, columns per member, (oracle tag, TF scope of the member)
+HEAD_BN = [
+    ("ze0", "e0", 100, [(f"expert{j}.z0", f"{P_}expert_{j}/nn_part/batch_normalization") for j in range(5)]),
+    ("ze1", "e1", 64, [(f"expert{j}.z1", f"{P_}expert_{j}/nn_part/batch_normalization_1") for j in range(5)]),
+    ("zg0", "g0", 64, [(f"gate_{g}.z0", f"{P_}gate_{g}/nn_part/batch_normalization") for g in ("main", "sub")]),
+    ("zg1", "g1", 5, [(f"gate_{g}.z1", f"{P_}gate_{g}/nn_part/batch_normalization_1") for g in ("main", "sub")]),
+    ("zt0", "t0", 100, [(f"tower{g}.z0", s + "/nn_part/batch_normalization") for g, s in
+                        enumerate(("sequential/logit_fcn", "sequential/valid_logit_fcn", "xilidu_logit_fcn"))]),
+    ("zt1", "t1", 64, [(f"tower{g}.z1", s + "/nn_part/batch_normalization_1") for g, s in
+                       enumerate(("sequential/logit_fcn", "sequential/valid_logit_fcn", "xilidu_logit_fcn"))]),
+]
+
+
+def relu_mask_mismatches(eng, ref, params0, rows, dev):
+    """Number of head units (over all ranks) whose ReLU is on in one forward pass and off in the other."""
+    n_bad = 0
+    Bl = len(rows)
+    for zbuf, bn, width, members in HEAD_BN:
+        if not Bl:
+            break
+        z = eng.ws(zbuf, Bl).double().cpu().numpy()
+        st = eng.ws(f"bn.{bn}.stat").double().cpu().numpy()
+        for m, (tag, scope) in enumerate(members):
+            sl = slice(m * width, (m + 1) * width)
+            gam, bet = params0[scope + "/gamma"].double().numpy(), params0[scope + "/beta"].double().numpy()
+            y_e = gam * ((z[:, sl] - st[sl, 0]) * st[sl, 1]) + bet
+            zo = ref["t"][tag].detach().double().numpy()[rows]
+            mean, var = (x.double().numpy() for x in ref["new_bn"][scope])
+            y_o = gam * ((zo - mean) / np.sqrt(var + O.BN_EPS)) + bet
+            n_bad += int(((y_e > 0) != (y_o > 0)).sum())
+    t = torch.tensor([n_bad], device=dev, dtype=torch.int64)
+    dist.all_reduce(t)
+    return int(t.item())
+
+
+def attempt(k, rank, world, local):
+    """One full comparison on seed set k.  Returns None when a ReLU-kink disagreement made it meaningless, else a summary."""
+    nu, ni, nc, T = 301, 3001, 53, 50
+    Bg = 5 * (8 * world + 3)                    # groups do not divide evenly: ranks get different shares
+    om = O.OracleModel(nu, ni, nc, T, seed=3 + k)
+    O.perturb_params(om.params, om.bn_state, seed=4 + k)
+    cap = -(-(Bg // 5) // world) * 5
+    eng = Engine(nu, ni, nc, T, max(cap, 40), world_size=world, rank=rank).allocate(f"cuda:{local}")
+    eng.init_comm()
+    eng.set_variables({n: t.numpy() for n, t in om.params.items()})
+    eng.set_variables({n: t.numpy() for n, t in om.bn_state.items()})
+    dev = eng.device
+    worst = {}
+
+    def note(name, got, ref, atol):
+        # Adam normalises each coordinate's gradient: rounding noise on a nearly cancelling gradient moves a weight by a fraction
+        # of lr (1e-3), up to 2 lr per step where a ~0 gradient changes sign.  Variables are compared on that scale:
+        # 99.9 % of the entries within `atol`, none further than one step per step taken.
+        got = np.asarray(got, np.float64)
+        ref = np.asarray(ref, np.float64).reshape(got.shape)
+        d = np.abs(got - ref)
+        err = float(np.quantile(d, 0.999))
+        worst[name] = max(worst.get(name, 0.0), err)
+        assert np.isfinite(got).all() and err <= atol and d.max() <= 3e-3, f"{name}: q999 {err:.3e} max {d.max():.3e} > {atol:.1e}"
+
+    def one_step(batch, step):
+        """forward / (mask check) / backward / apply through the phase entry points; returns (losses, ref, P0) or None."""
+        P0 = eng.pool["dense_param"].clone()
+        O0 = {n: t.clone() for n, t in om.params.items()}
+        tags = tuple(tag for _, _, _, mem in HEAD_BN for tag, _ in mem)
+        ref = om.train_step(batch, keep=tags)
+        mine, n = D.split_feed(batch, world, rank)
+        db = eng.upload(mine, global_batch=n)
+        eng.forward(db, training=True, want_pred=False)
+        n_kink = relu_mask_mismatches(eng, ref, O0, D.group_rows(n, world, rank), dev)
+        eng.backward(db)
+        got = eng.apply_gradients(db).cpu().numpy()
+        if n_kink:
+            if rank == 0:
+                print(f"KINK seed_set={k} step={step}: {n_kink} head unit(s) on opposite sides of the ReLU kink in the fp32 and the "
+                      f"fp64 forward pass (oracle margin {ref['kink_margin']:.1e}); repeating on the next seed set", flush=True)
+            return None
+        return got, ref, P0
+
+    def finish(result):
+        eng.close()
+        return result
+
+    for step in range(3):
+        out = one_step(O.make_batch(100 + step + 1000 * k, Bg, T, nu, ni, nc), step)
+        if out is None:
+            return finish(None)
+        got, ref, P0 = out
+        tol = 2e-5 if step == 0 else 1e-4            # same weights: 2e-5; later steps: trajectories drift (see test_gpu_parity)
+        for i, name in enumerate(NAMES):
+            r = ref["losses"][name]
+            assert abs(got[i] - r) <= tol * max(abs(r), 1e-3), (rank, step, name, float(got[i]), r)
+        if step == 0:
+            l2 = om.hp["layer_l2"]
+            gmax = max(float(ref["grads"][nm].abs().max()) for nm in eng.info[L.POOL_DENSE])
+            for nm, d in eng.info[L.POOL_DENSE].items():
+                g = eng.dense(nm, "dense_grad").cpu().numpy().astype(np.float64)
+                if d["flags"] & L.SEG_L2:
+                    o, cnt = d["offset"], d["numel"]
+                    g = g + l2 * P0[o:o + cnt].view(d["shape"]).cpu().numpy().astype(np.float64)
+                gr = ref["grads"][nm].numpy().reshape(g.shape)
+                err = np.abs(g - gr).max()
+                assert np.isfinite(g).all() and err <= 1e-4 * np.abs(gr).max() + 2e-6 * gmax, ("dense grad", nm, err, float(np.abs(gr).max()))
+            spn = eng.ws("sp_normsq").cpu().numpy()
+            for i, nm in enumerate(("item_embedding", "cate_embedding", "user_long_embedding", "user_short_embedding", "position_embedding")):
+                want = ref["sqnorms"][EMB + nm]
+                assert abs(spn[i] - want) <= 2e-4 * want + 1e-30, ("clip norm", nm, float(spn[i]), want)
+            st1 = eng.get_optimizer_state()
+            for nm in ("item_embedding", "cate_embedding", "user_long_embedding", "user_short_embedding"):
+                a = st1[EMB + nm + "/Adam"].astype(np.float64)
+                b_ = om.m[EMB + nm].numpy().astype(np.float64)
+                d = np.abs(a - b_)
+                bad = np.nonzero(d.max(1) > 2e-4 * np.abs(b_).max())[0]
+                assert bad.size == 0, (nm, "first moment after one step", float(d.max()), float(np.abs(b_).max()), "bad rows per owner",
+                                       [int((bad % world == r).sum()) for r in range(world)], bad[:12].tolist())
+    # variables after the steps (collective gathers)
+    var = eng.get_variables()
+    for name in ("item_embedding", "cate_embedding", "user_long_embedding", "user_short_embedding"):
+        note(name, var[EMB + name], om.params[EMB + name].numpy(), 5e-5)   # 5 % of one lr step over 3 steps
+    for name in om.params:
+        if name in var and "embedding/" not in name:
+            if name.rsplit("/", 1)[-1].startswith("b_nn_layer"):
+                continue                                # bias in front of BN: zero data gradient, Adam follows fp32 noise
+            note(name, var[name], om.params[name].numpy(), 1e-4)
+    for name, t in om.bn_state.items():
+        atol = 2e-4 if name.endswith("moving_mean") else 1e-6
+        assert np.allclose(var[name], t.numpy(), rtol=1e-4, atol=atol), name
+    # replicated dense parameters must be bit-identical on every rank
+    dp = eng.pool["dense_param"].clone()
+    lo, hi = dp.clone(), dp.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi), "dense parameters diverged between ranks"
+    # a step in which the last rank has nothing to train on (B = 0): it still serves rows and joins the all-reduces
+    # (batch norm over so few rows is ill-conditioned, so after this step only a loose bound on the tables is meaningful)
+    out = one_step(O.make_batch(500 + 1000 * k, 5 * (world - 1) if world > 1 else 5, T, nu, ni, nc), 3)
+    if out is None:
+        return finish(None)
+    got, ref, _ = out
+    assert abs(got[0] - ref["losses"]["loss"]) <= 1e-4 * abs(ref["losses"]["loss"]), (rank, float(got[0]), ref["losses"]["loss"])
+    item = eng.get_variables()[EMB + "item_embedding"]
+    assert np.abs(item - om.params[EMB + "item_embedding"].numpy()).max() <= 3e-3
+    # data-parallel scoring
+    ev = O.make_batch(999, 37, T, nu, ni, nc, grouped=False)
+    want = om.eval_forward(ev).t["pred"].numpy().reshape(-1)
+    mine, n = D.split_feed(ev, world, rank, grouped=False)
+    full = torch.zeros(n, dtype=torch.float32, device=dev)
+    full[rank::world] = eng.forward(eng.upload(mine, training=False, global_batch=n), training=False)
+    pred = eng.all_reduce_(full).cpu().numpy()
+    assert np.abs(pred - want).max() <= 1e-4, float(np.abs(pred - want).max())
+    dist.barrier()
+    top = sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+    return finish(" ".join(f"{n_.rsplit('/', 1)[-1]}={v:.1e}" for n_, v in top))
 
 
 def main():
@@ -23,81 +192,14 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    nu, ni, nc, T = 301, 3001, 53, 50
-    Bg = 5 * (8 * world + 3)                    # groups do not divide evenly: ranks get different shares
-    steps = 3
-    om = O.OracleModel(nu, ni, nc, T, seed=3)
-    O.perturb_params(om.params, om.bn_state, seed=4)
-    cap = -(-(Bg // 5) // world) * 5
-    eng = Engine(nu, ni, nc, T, max(cap, 40), world_size=world, rank=rank).allocate(f"cuda:{local}")
-    eng.init_comm()
-    eng.set_variables({n: t.numpy() for n, t in om.params.items()})
-    eng.set_variables({n: t.numpy() for n, t in om.bn_state.items()})
-    worst = {}
-
-    def note(name, got, ref, atol):
-        # Adam normalises each coordinate's gradient: summation-order noise on a nearly cancelling gradient moves a weight by a
-        # fraction of lr (1e-3), so variables are compared on the scale of one optimiser step, not of the weight.
-        # (up to 2 lr where a ~0 gradient changes sign): 99.9 % of the entries within `atol`, none further than one step.
-        got = np.asarray(got, np.float64)
-        ref = np.asarray(ref, np.float64).reshape(got.shape)
-        d = np.abs(got - ref)
-        err = float(np.quantile(d, 0.999))
-        worst[name] = max(worst.get(name, 0.0), err)
-        assert np.isfinite(got).all() and err <= atol and d.max() <= 1e-3, f"{name}: q999 {err:.3e} max {d.max():.3e} > {atol:.1e}"
-
-    for step in range(steps):
-        batch = O.make_batch(100 + step, Bg, T, nu, ni, nc)
-        ref = om.train_step(batch)
-        mine, n = D.split_feed(batch, world, rank)
-        got = eng.train_step(eng.upload(mine, global_batch=n)).cpu().numpy()
-        tol = 2e-5 if step == 0 else 1e-4            # same weights: 2e-5; later steps: trajectories drift (see test_gpu_parity)
-        for i, k in enumerate(("loss", "data_loss", "regular_loss", "auxiliary_data_loss", "order_loss")):
-            r = ref["losses"][k]
-            assert abs(got[i] - r) <= tol * max(abs(r), 1e-3), (rank, step, k, float(got[i]), r)
-    # variables after the steps (collective gathers)
-    var = eng.get_variables()
-    for name in ("item_embedding", "cate_embedding", "user_long_embedding", "user_short_embedding"):
-        note(name, var["sequential/embedding/" + name], om.params["sequential/embedding/" + name].numpy(), 5e-5)   # 5 % of one lr step over 3 steps
-    for name in om.params:
-        if name in var and "embedding/" not in name:
-            ref_v = om.params[name].numpy()
-            leaf = name.rsplit("/", 1)[-1]
-            if leaf.startswith("b_nn_layer"):
-                continue                                # bias in front of BN: zero data gradient, Adam follows fp32 noise
-            note(name, var[name], ref_v, 1e-4)
-    for name, t in om.bn_state.items():
-        got_bn = var[name]
-        atol = 2e-4 if name.endswith("moving_mean") else 1e-6
-        assert np.allclose(got_bn, t.numpy(), rtol=1e-4, atol=atol), name
-    # a step in which the last rank has nothing to train on (B = 0): it still serves rows and joins the all-reduces
-    small = O.make_batch(500, 5 * (world - 1), T, nu, ni, nc) if world > 1 else O.make_batch(500, 5, T, nu, ni, nc)
-    ref = om.train_step(small)
-    mine, n = D.split_feed(small, world, rank)
-    got = eng.train_step(eng.upload(mine, global_batch=n)).cpu().numpy()
-    assert abs(got[0] - ref["losses"]["loss"]) <= 1e-4 * abs(ref["losses"]["loss"]), (rank, float(got[0]), ref["losses"]["loss"])
-    # (batch norm over so few rows is ill-conditioned, so after this step only a loose bound on the tables is meaningful)
-    item = eng.get_variables()["sequential/embedding/item_embedding"]
-    assert np.abs(item - om.params["sequential/embedding/item_embedding"].numpy()).max() <= 1e-3
-    # replicated dense parameters must be bit-identical on every rank
-    dp = eng.pool["dense_param"].clone()
-    lo, hi = dp.clone(), dp.clone()
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-    assert torch.equal(lo, hi), "dense parameters diverged between ranks"
-    # data-parallel scoring
-    ev = O.make_batch(999, 37, T, nu, ni, nc, grouped=False)
-    want = om.eval_forward(ev).t["pred"].numpy().reshape(-1)
-    mine, n = D.split_feed(ev, world, rank, grouped=False)
-    full = torch.zeros(n, dtype=torch.float32, device=eng.device)
-    full[rank::world] = eng.forward(eng.upload(mine, training=False, global_batch=n), training=False)
-    pred = eng.all_reduce_(full).cpu().numpy()
-    assert np.abs(pred - want).max() <= 1e-4, float(np.abs(pred - want).max())
-    dist.barrier()
-    if rank == 0:
-        top = sorted(worst.items(), key=lambda kv: -kv[1])[:5]
-        print("DIST_PARITY_OK world=%d" % world, " ".join(f"{k.rsplit('/', 1)[-1]}={v:.1e}" for k, v in top), flush=True)
-    eng.close()
+    for k in range(6):
+        summary = attempt(k, rank, world, local)
+        if summary is not None:
+            if rank == 0:
+                print(f"DIST_PARITY_OK world={world} seed_set={k} {summary}", flush=True)
+            break
+    else:
+        raise RuntimeError("six seed sets in a row hit a ReLU-kink disagreement: that is not chance")
     dist.destroy_process_group()
 
 
