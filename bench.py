@@ -123,6 +123,11 @@ def flops_bytes(w):
     }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the `ncu --set full` capture of this workload
+# (profiles/r01e_ncu_encoder_full.csv, takatak_b1025_t50); null for kernels / workloads without a capture
+NCU_TRAFFIC = {"takatak_b1025_t50": {"attn_bwd": 49.85e6 + 1.04e6, "proj_bwd": 41.67e6 + 0.08e6, "ffn_bwd": 16.51e6 + 0.0}}
+
+
 def hbm_microbench(pk, dev):
     """Stand-alone HBM kernels on the BASELINE configs[2] table shape (10 M items x 16, 100 K categories x 4: far above the
     126 MB L2), the same kernels the step launches: the fused embedding gather and the full-table (dense_exact) Adam sweep."""
@@ -309,6 +314,8 @@ def run_ours(args, w, rank, world):
         else:
             roof = {"kernel": dom, "bound": "tensor", "achieved": tf, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
                     "frac": tf / pk["tensor_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained bf16"}
+        roof["traffic"] = NCU_TRAFFIC.get(args.workload, {}).get(dom)
+        roof["traffic_note"] = "bytes per launch, ncu --set full (profiles/r01e_ncu_encoder_full.csv); most of the written tensors stay in the 126 MB L2"
         roof["also"] = {"algorithmic_GB_per_s": gb, "hbm_frac": gb / pk["hbm"], "algorithmic_TFLOP_per_s": tf,
                         "fp32_ffma_peak_TFLOP_per_s": fp32_peak, "fp32_frac": tf / fp32_peak}
         roof["note"] = ("3xTF32 mma.sync kernel: 3 tensor-core MMAs per algorithmic product; K = 40 GEMMs fused with LayerNorm epilogues "

@@ -377,9 +377,9 @@ class PAMRECModel(SequentialBaseModel):
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
         self.feed_is_global = getattr(hp, "dp_feed", "global") != "local"
-        cap = hp.batch_size
+        cap = hp.batch_size * (1 + max(int(hp.train_num_ngs or 0), 0))      # in-batch negatives multiply the rows of a batch
         if world > 1 and self.feed_is_global:
-            cap = max(-(-(hp.batch_size // 5) // world) * 5, -(-hp.batch_size // world))
+            cap = max(-(-(cap // 5) // world) * 5, -(-cap // world))
         tables = getattr(hp, "tables", None)
         self.engine = Engine(n_users, n_items, n_cates, hp.max_seq_length, cap, hp=engine_hp, sparse_adam=mode,
                              world_size=world, rank=rank, tables=tables)

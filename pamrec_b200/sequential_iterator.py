@@ -148,14 +148,50 @@ class SequentialIterator:
         if infile not in self.iter_data:
             self.iter_data[infile] = self.parse_file(infile)
         lines = self.iter_data[infile]
-        if batch_num_ngs > 0:
-            # the reference's in-batch negative sampler is a commented-out block ending in exit(-1) (IT:801-1008)
-            raise NotImplementedError("batch_num_ngs > 0 is not executable in the reference (IT:1008)")
         native = self._native(infile, lines)
         if self.train:
-            yield from (self._train_batches_native(native, lines) if native else self._train_batches(lines))
+            gen = self._train_batches_native(native, lines) if native else self._train_batches(lines)
         else:
-            yield from (self._eval_batches_native(native, min_seq_length) if native else self._eval_batches(lines, min_seq_length))
+            gen = self._eval_batches_native(native, min_seq_length) if native else self._eval_batches(lines, min_seq_length)
+        if batch_num_ngs > 0:
+            if not self.train:
+                # evaluation files carry their negatives as extra lines after each positive (QS:483,493)
+                raise NotImplementedError("batch_num_ngs > 0 applies to the training file only")
+            gen = (self._with_negatives(b, batch_num_ngs) for b in gen)
+        yield from gen
+
+    def _with_negatives(self, res, ngs):
+        """In-batch negative sampling as SPECIFIED by the reference's disabled block (IT:801-1007; the live code there is
+        `exit(-1)`, so there is no executable behaviour to match - this follows the commented statements literally):
+        every row is followed by `ngs` negatives whose target (item, category, duration) is that of a row drawn with
+        `random.randint(0, n - 1)`, redrawn while the drawn item is in `item_list[i // 5 : i // 5 + 5]` (sic, IT:949);
+        negatives carry labels 0 / 0 / 0 and the positive's history.  With ngs = 4 a listwise group of 5 rows is one positive
+        and its four negatives.  (The block forgets `item_loop_times_history`; it is replicated like the other histories.)"""
+        n = int(res["items"].shape[0])
+        if n < self.BEGIN_HISTORY_LEN_MAX:                                   # IT:802-804 returns None
+            return {}
+        items, cates, durs = res["items"], res["cates"], res["durations"]
+        item_list = items.tolist()
+        src = np.empty(n * (ngs + 1), np.int64)                              # row whose target each output row takes
+        for i in range(n):
+            src[i * (ngs + 1)] = i
+            group = item_list[i // 5: i // 5 + 5]
+            if len(set(item_list) - set(group)) == 0:
+                raise ValueError("in-batch negative sampling cannot terminate: every target of the batch is in the positive slice")
+            count = 0
+            while count < ngs:
+                rv = random.randint(0, n - 1)
+                if item_list[rv] in group:
+                    continue
+                count += 1
+                src[i * (ngs + 1) + count] = rv
+        rep = lambda a: np.repeat(a, ngs + 1, axis=0)
+        is_pos = (np.arange(n * (ngs + 1)) % (ngs + 1) == 0)
+        lab = lambda a: np.where(is_pos[:, None], rep(a), 0).astype(np.float32)
+        out = {k: rep(v) for k, v in res.items()}                            # histories, masks, users: the positive's
+        out["labels_satisfied"], out["labels_play"], out["plays"] = lab(res["labels_satisfied"]), lab(res["labels_play"]), lab(res["plays"])
+        out["items"], out["cates"], out["durations"] = items[src], cates[src], durs[src]
+        return out
 
     # ------------------------------------------------------------------ native batcher (csrc/batcher.cu)
     def _native(self, infile, lines):

@@ -148,7 +148,7 @@ def test_iterator_edge_cases(tmp_path):
     assert va[0]["item_history"][0].tolist() == [1 + i % 49 for i in range(n - 8, n)]
     assert va[0]["labels_play"][0, 0] == 1.0 and va[0]["plays"][0, 0] == 12.0
     with pytest.raises(NotImplementedError):
-        next(it.load_data_from_file(str(d / "valid_data"), batch_num_ngs=4))
+        next(it.load_data_from_file(str(d / "valid_data"), batch_num_ngs=4))      # negatives are sampled for the train file only
     assert list(it.load_data_from_file(str(d / "valid_data"), min_seq_length=1000)) == []
 
 
@@ -221,3 +221,39 @@ def test_native_batcher_hard_lines(tmp_path, monkeypatch):
         for a, b in zip(pa, na):
             for k in a:
                 assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+def test_in_batch_negative_sampler_follows_the_disabled_reference_block():
+    """IT:801-1007 is a comment ending in exit(-1): there is no behaviour to pin, only statements to follow."""
+    import random
+    with tempfile.TemporaryDirectory() as tmp:
+        data_dir = G.synth_case("wechat_small", tmp) if "wechat_small" in G.CASES else G.synth_case(list(G.CASES)[0], tmp)
+        hp = G.hparams_for(list(G.CASES)[0], data_dir)
+        train = os.path.join(data_dir, "train_data")
+        random.seed(8)
+        base = list(IT.SequentialIterator(hp, None).load_data_from_file(train, batch_num_ngs=0))
+        random.seed(8)
+        it = IT.SequentialIterator(hp, None)
+        neg = list(it.load_data_from_file(train, batch_num_ngs=4))
+    assert len(neg) == len(base)
+    b0, n0 = base[0], neg[0]
+    n = b0["items"].shape[0]
+    assert n0["items"].shape[0] == 5 * n and n0["item_history"].shape == (5 * n, b0["item_history"].shape[1])
+    assert list(n0) == list(b0)                                         # same 19 feed keys
+    pos = np.arange(0, 5 * n, 5)
+    for k in ("items", "cates", "durations", "labels_satisfied", "labels_play", "plays"):
+        assert np.array_equal(n0[k][pos], b0[k]), k                      # row 0 of every group of 5 is the positive
+    neg_rows = np.setdiff1d(np.arange(5 * n), pos)
+    for k in ("labels_satisfied", "labels_play", "plays"):
+        assert not n0[k][neg_rows].any(), k
+    for k in ("item_history", "item_cate_history", "mask", "item_loop_times_history", "users"):
+        a = n0[k].reshape(n, 5, *n0[k].shape[1:])
+        assert (a == a[:, :1]).all() and np.array_equal(a[:, 0], b0[k]), k   # negatives share the positive's history
+    items = b0["items"].tolist()
+    pair = {(int(i), int(c), float(d)) for i, c, d in zip(b0["items"], b0["cates"], b0["durations"])}
+    for i in range(n):
+        group = items[i // 5: i // 5 + 5]
+        for j in range(1, 5):
+            r = 5 * i + j
+            assert int(n0["items"][r]) not in group                     # the rejection rule of IT:949-951, slice as written
+            assert (int(n0["items"][r]), int(n0["cates"][r]), float(n0["durations"][r])) in pair
