@@ -10,6 +10,8 @@
 //    only the looked-up rows.
 #include <cub/cub.cuh>
 
+#include <climits>
+
 #include "kernels.h"
 
 namespace pamrec {
@@ -94,44 +96,79 @@ __device__ __forceinline__ void atomic_add4(float* p, const float4& v) {
 #endif
 }
 
-// warp-level segmented reduction over 32 consecutive sorted positions
+// Warp-level segmented reduction over sorted positions.  A warp walks `iters` consecutive blocks of 32 positions and carries
+// the sum of the run that is still open at lane 31 into the next block, so a run of equal keys costs one red.global.add per
+// warp walk instead of one per 32 positions: with a Zipf id distribution (and the padding id 0 in every short history) the
+// hottest rows own runs of 10^5..10^6 positions and their atomics on a single 64-byte line were the whole kernel time.
 template <int W>
 __global__ void __launch_bounds__(256)
 k_seg_reduce(const int* __restrict__ skeys, const int* __restrict__ sidx, const int* __restrict__ uidx, int64_t n,
              int64_t n_hist, const float* __restrict__ hist_grad, int hist_ld, int hist_col,
              const float* __restrict__ tgt_grad, int tgt_ld, int tgt_col, float* __restrict__ accum,
-             double* __restrict__ normsq) {
+             double* __restrict__ normsq, int iters) {
+  constexpr int CH = W / 4;
   const int lane = threadIdx.x & 31;
-  const int64_t p = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
-  const bool valid = p < n;
-  int key = -1 - lane;
-  const float* row = nullptr;
-  int u = 0;
-  if (valid) {
-    key = skeys[p];
-    int src = sidx[p];
-    row = src < n_hist ? hist_grad + (int64_t)src * hist_ld + hist_col
-                       : tgt_grad + (int64_t)(src - n_hist) * tgt_ld + tgt_col;
-    u = uidx[p] - 1;
-  }
-  const int key_next = __shfl_down_sync(0xffffffffu, key, 1);
-  const bool tail = valid && (lane == 31 || key_next != key);
+  const int64_t warp0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 * iters;
+  float4 carry[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) carry[c] = f4_zero();
+  int carry_key = 0, carry_u = 0;
+  bool carry_open = false;                       // warp-uniform
   float sq = 0.f;
-#pragma unroll
-  for (int c = 0; c < W / 4; ++c) {
-    float4 g = valid ? ld4(row + 4 * c) : f4_zero();
-    sq += f4_dot(g, g);
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      float4 o;
-      o.x = __shfl_up_sync(0xffffffffu, g.x, d); o.y = __shfl_up_sync(0xffffffffu, g.y, d);
-      o.z = __shfl_up_sync(0xffffffffu, g.z, d); o.w = __shfl_up_sync(0xffffffffu, g.w, d);
-      int ko = __shfl_up_sync(0xffffffffu, key, d);
-      if (lane >= d && ko == key) { g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w; }
+  for (int it = 0; it < iters; ++it) {
+    const int64_t p = warp0 + (int64_t)it * 32 + lane;
+    if (warp0 + (int64_t)it * 32 >= n) break;    // warp-uniform
+    const bool valid = p < n;
+    int key = INT_MAX - lane;                    // positions past the end: distinct keys above every real one
+    const float* row = nullptr;
+    int u = 0;
+    if (valid) {
+      key = skeys[p];
+      const int src = sidx[p];
+      row = src < n_hist ? hist_grad + (int64_t)src * hist_ld + hist_col
+                         : tgt_grad + (int64_t)(src - n_hist) * tgt_ld + tgt_col;
+      u = uidx[p] - 1;
     }
-    if (tail) atomic_add4(accum + (int64_t)u * W + 4 * c, g);
+    const int key0 = __shfl_sync(0xffffffffu, key, 0);
+    if (carry_open && key0 != carry_key) {       // the open run ended exactly at the block boundary
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) atomic_add4(accum + (int64_t)carry_u * W + 4 * c, carry[c]);
+      }
+      carry_open = false;
+    }
+    const bool joins_carry = carry_open && key == carry_key;       // keys are sorted: lanes 0..k of the block
+    const int key_next = __shfl_down_sync(0xffffffffu, key, 1);
+    const bool tail = valid && lane < 31 && key_next != key;        // lane 31 stays open until the next block decides
+    float4 gl[CH];                                                  // the whole row first: CH independent 16-byte loads in flight
+#pragma unroll
+    for (int c = 0; c < CH; ++c) gl[c] = valid ? ld4(row + 4 * c) : f4_zero();
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      float4 g = gl[c];
+      sq += f4_dot(g, g);
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        float4 o;
+        o.x = __shfl_up_sync(0xffffffffu, g.x, d); o.y = __shfl_up_sync(0xffffffffu, g.y, d);
+        o.z = __shfl_up_sync(0xffffffffu, g.z, d); o.w = __shfl_up_sync(0xffffffffu, g.w, d);
+        const int ko = __shfl_up_sync(0xffffffffu, key, d);
+        if (lane >= d && ko == key) { g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w; }
+      }
+      if (joins_carry) { g.x += carry[c].x; g.y += carry[c].y; g.z += carry[c].z; g.w += carry[c].w; }
+      if (tail) atomic_add4(accum + (int64_t)u * W + 4 * c, g);
+      carry[c].x = __shfl_sync(0xffffffffu, g.x, 31); carry[c].y = __shfl_sync(0xffffffffu, g.y, 31);
+      carry[c].z = __shfl_sync(0xffffffffu, g.z, 31); carry[c].w = __shfl_sync(0xffffffffu, g.w, 31);
+    }
+    carry_key = __shfl_sync(0xffffffffu, key, 31);
+    carry_u = __shfl_sync(0xffffffffu, u, 31);
+    carry_open = __shfl_sync(0xffffffffu, valid ? 1 : 0, 31) != 0;
   }
-  double s = warp_sum_d((double)sq);
+  if (carry_open && lane == 0) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) atomic_add4(accum + (int64_t)carry_u * W + 4 * c, carry[c]);
+  }
+  const double s = warp_sum_d((double)sq);
   if (lane == 0 && s != 0.0) atomicAdd(normsq, s);
 }
 
@@ -162,13 +199,17 @@ void launch_sparse_segreduce(const SparseTable& t, int64_t n, int64_t n_hist, co
   PAMREC_PROF("sparse_segreduce", 1, st);
   if (n == 0) return;
   cudaMemsetAsync(t.accum, 0, (size_t)n * t.width * sizeof(float), st);
-  const unsigned gw = (unsigned)((n + 255) / 256);               // 8 warps x 32 positions per CTA
+  // blocks of 32 positions per warp walk: 1 while the grid would not fill the GPU otherwise, up to 16 for large batches
+  int64_t iters = n / (148 * 8 * 8 * 32);
+  iters = iters < 1 ? 1 : (iters > 16 ? 16 : iters);
+  const int64_t per_cta = 8 * 32 * iters;                        // 8 warps per CTA
+  const unsigned gw = (unsigned)((n + per_cta - 1) / per_cta);
   if (t.width == 16)
     k_seg_reduce<16><<<gw, 256, 0, st>>>(t.skeys, t.sidx, t.uidx, n, n_hist, hist_grad, hist_ld, hist_col, tgt_grad, tgt_ld,
-                                         tgt_col, t.accum, normsq);
+                                         tgt_col, t.accum, normsq, (int)iters);
   else
     k_seg_reduce<4><<<gw, 256, 0, st>>>(t.skeys, t.sidx, t.uidx, n, n_hist, hist_grad, hist_ld, hist_col, tgt_grad, tgt_ld,
-                                        tgt_col, t.accum, normsq);
+                                        tgt_col, t.accum, normsq, (int)iters);
 }
 
 int launch_sparse_reduce(const SparseTable& t, const int* hist_ids, const int* tgt_ids, int64_t n_hist, int64_t n_tgt,
