@@ -69,6 +69,15 @@ def get_model(f, model_path, summary_path, user_vocab, item_vocab, cate_vocab):
 
 def main(argv):
     f = FLAGS
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # torchrun --nproc-per-node N sequential.py ...: one process per GPU, every rank reads the same files and trains on
+        # its listwise groups of every batch (pamrec_b200/dist.py); no counterpart in the reference (single device)
+        import torch
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    chief = int(os.environ.get("RANK", "0")) == 0
     data_path = os.path.join(f.data_path, f.dataset)
     train_file, valid_file, test_file = (os.path.join(data_path, n) for n in ("train_data", "valid_data", "test_data"))
     vocabs = [os.path.join(data_path, n) for n in ("user_vocab.pkl", "item_vocab.pkl", "category_vocab.pkl")]
@@ -77,17 +86,23 @@ def main(argv):
     model = get_model(f, model_path, summary_path, *vocabs)
     if f.only_test:
         model.load_model(tf.train.latest_checkpoint(model_path))
-        print(model.run_weighted_eval(test_file, num_ngs=f.test_num_ngs))
+        res = model.run_weighted_eval(test_file, num_ngs=f.test_num_ngs)
+        if chief:
+            print(res)
         return
     t0 = time.time()
     model = model.fit_step(train_file, valid_file, valid_num_ngs=f.val_num_ngs, eval_metric=f.eval_metric)
-    print("Time cost for training is {0:.2f} mins".format((time.time() - t0) / 60.0))
+    if chief:
+        print("Time cost for training is {0:.2f} mins".format((time.time() - t0) / 60.0))
     ckpt = tf.train.latest_checkpoint(model_path)
-    print(ckpt)
+    if chief:
+        print(ckpt)
     if ckpt:
         model.load_model(ckpt)
-    print(f.name)
-    print(model.run_weighted_eval(test_file, num_ngs=f.test_num_ngs))
+    res = model.run_weighted_eval(test_file, num_ngs=f.test_num_ngs)
+    if chief:
+        print(f.name)
+        print("TEST_METRICS", {k: float(v) for k, v in res.items()})
     if f.write_prediction_to_file:
         model.predict(test_file, os.path.join(data_path, "output.txt"))
 

@@ -102,6 +102,7 @@ class Saver:
         variables = self.model.engine.get_variables()          # collective when the tables are sharded over ranks
         self.kept.append(save_path)
         if self.model.engine.rank != 0:
+            torch.distributed.barrier()                          # rank 0 finishes writing before anyone may restore
             return save_path
         np.savez(save_path + ".npz", **{k.replace("/", "|"): v for k, v in variables.items()})
         while len(self.kept) > self.max_to_keep:
@@ -112,6 +113,8 @@ class Saver:
             f.write('model_checkpoint_path: "{}"\n'.format(os.path.basename(save_path)))
             for p in self.kept:
                 f.write('all_model_checkpoint_paths: "{}"\n'.format(os.path.basename(p)))
+        if self.model.engine.world > 1:
+            torch.distributed.barrier()
         return save_path
 
     def restore(self, sess, path):
@@ -346,13 +349,19 @@ class SequentialBaseModel(BaseModel):
         return res
 
     def predict(self, infile_name, outfile_name):
-        """SBM:534-555: one score per line."""
-        with open(outfile_name, "w") as wt:
+        """SBM:534-555: one score per line (data parallel: every rank scores, rank 0 writes)."""
+        writer = self.engine.rank == 0
+        wt = open(outfile_name, "w") if writer else None
+        try:
             for feed in self.iterator.load_data_from_file(infile_name, batch_num_ngs=0):
                 if feed:
                     step_pred = np.reshape(self.infer(self.sess, feed), -1)
-                    wt.write("\n".join(map(str, step_pred)))
-                    wt.write("\n")
+                    if writer:
+                        wt.write("\n".join(map(str, step_pred)))
+                        wt.write("\n")
+        finally:
+            if wt:
+                wt.close()
         return self
 
 

@@ -90,3 +90,35 @@ def test_two_rank_step_matches_oracle(small_allreduce):
     fails = [ln for ln in r.stdout.splitlines() if "DIST_PARITY_FAIL" in ln]
     print("\n".join(fails) or r.stdout[-3000:])
     assert r.returncode == 0 and "DIST_PARITY_OK" in r.stdout, "\n".join(fails) + "\n" + r.stdout[-6000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_driver_under_torchrun_matches_single_process(tmp_path):
+    """The quick-start driver (compat/example/00_quick_start/sequential.py) from text files, once as one process and once as
+    two ranks under torchrun: same global batches, rank r trains on its listwise groups, tables row-sharded, rank 0 writes
+    checkpoints and predictions.  The final test metrics agree to the resolution two fp32 trajectories can agree."""
+    import ast
+    from pamrec_b200 import synth
+    root = tmp_path / "data"
+    synth.generate(str(root), "wechat", n_users=400, n_items=3000, n_cates=40, mean_len=60, seed=7, eval_per_user=2)
+    drv = os.path.join(ROOT, "compat", "example", "00_quick_start", "sequential.py")
+    common = ["--dataset", "wechat", "--data_path", str(root), "--epochs", "1", "--batch_size", "100", "--eval_step", "5", "--show_step", "1000",
+              "--write_prediction_to_file"]
+
+    def run(prefix, tag):
+        cmd = prefix + [drv] + common + ["--save_path", str(tmp_path / tag)]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, cwd=os.path.dirname(drv))
+        assert r.returncode == 0, r.stdout[-3000:]
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("TEST_METRICS")]
+        assert len(line) == 1, r.stdout[-3000:]
+        preds = np.loadtxt(os.path.join(str(root), "wechat", "output.txt"))
+        return ast.literal_eval(line[0][len("TEST_METRICS"):].strip()), preds
+
+    one, p1 = run([sys.executable], "one")
+    two, p2 = run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                   "--master-port", "29631"], "two")
+    print("single:", one, "\ntwo ranks:", two, "\nmax |pred diff|:", float(np.abs(p1 - p2).max()))
+    assert set(one) == set(two)
+    for k in one:
+        assert abs(one[k] - two[k]) <= 3e-3, (k, one[k], two[k])
+    assert p1.shape == p2.shape and np.abs(p1 - p2).max() <= 5e-3
