@@ -3,17 +3,19 @@
 Every rank builds the SAME oracle and the SAME global batches from seeds, trains on its own share (listwise groups dealt
 round-robin, tables row-sharded), and compares with the fp64 oracle run on the whole global batch:
 
-* step 0 (same weights): losses, the all-reduced dense gradients, the global clip norms of the sparse tables, Adam's first
-  moment of every table row (= the owner-side merge of the row gradients of all ranks) - Adam is invariant to the scale of a
-  gradient, so these are checked directly rather than through the weights;
-* steps 1, 2: losses, then tables / dense variables / BN moving statistics on the scale of one optimiser step;
+* step 0 (same weights) against the fp64 oracle: losses, the all-reduced dense gradients, the global clip norms of the
+  sparse tables, Adam's first moment of every table row (= the owner-side merge of the row gradients of all ranks) - Adam is
+  invariant to the scale of a gradient, so these are checked directly rather than through the weights;
+* every step against a SINGLE-GPU engine that rank 0 runs on the whole global batch (same kernels, same fp32 arithmetic up
+  to summation order, so the two trajectories stay together where fp32-vs-fp64 ones drift): losses per step, then tables,
+  dense variables and BN moving statistics after the last step;
 * replicated dense parameters bit-identical on every rank; a step in which the last rank has NO rows; data-parallel scoring.
 
 ReLU kinks.  The gradient of the head is discontinuous where a batch-normalised pre-activation crosses 0, and every step has
 a few of the ~250 K such values within 1e-5 of 0 - inside the fp32 rounding of the forward pass.  When this implementation
 and the fp64 oracle land on different sides, one unit's gradient differs at O(1) and, through the batch statistics, every
-row's a little: neither is wrong.  The worker detects exactly that (it compares the ReLU masks of the two forward passes)
-and, if it happens, repeats the whole comparison on the next seed set instead of comparing beyond the kink."""
+row's a little: neither is wrong.  The worker detects exactly that at step 0 (it compares the ReLU masks of the two forward
+passes) and, if it happens, repeats the whole comparison on the next seed set instead of comparing beyond the kink."""
 import os
 import sys
 
@@ -80,6 +82,11 @@ def attempt(k, rank, world, local):
     eng.set_variables({n: t.numpy() for n, t in om.bn_state.items()})
     dev = eng.device
     worst = {}
+    solo = None
+    if rank == 0:                                    # the same model on ONE GPU, fed the whole global batch
+        solo = Engine(nu, ni, nc, T, Bg, tables="sharded").allocate(f"cuda:{local}")
+        solo.set_variables({n: t.numpy() for n, t in om.params.items()})
+        solo.set_variables({n: t.numpy() for n, t in om.bn_state.items()})
 
     def note(name, got, ref, atol):
         # Adam normalises each coordinate's gradient: rounding noise on a nearly cancelling gradient moves a weight by a fraction
@@ -101,9 +108,13 @@ def attempt(k, rank, world, local):
         mine, n = D.split_feed(batch, world, rank)
         db = eng.upload(mine, global_batch=n)
         eng.forward(db, training=True, want_pred=False)
-        n_kink = relu_mask_mismatches(eng, ref, O0, D.group_rows(n, world, rank), dev)
+        n_kink = relu_mask_mismatches(eng, ref, O0, D.group_rows(n, world, rank), dev) if step == 0 else 0
         eng.backward(db)
         got = eng.apply_gradients(db).cpu().numpy()
+        if solo is not None:
+            one = solo.train_step(solo.upload(batch)).cpu().numpy()
+            for i, name in enumerate(NAMES):
+                assert abs(got[i] - one[i]) <= 1e-5 * max(abs(one[i]), 1e-3), ("vs single GPU", step, name, float(got[i]), float(one[i]))
         if n_kink:
             if rank == 0:
                 print(f"KINK seed_set={k} step={step}: {n_kink} head unit(s) on opposite sides of the ReLU kink in the fp32 and the "
@@ -113,6 +124,8 @@ def attempt(k, rank, world, local):
 
     def finish(result):
         eng.close()
+        if solo is not None:
+            solo.close()
         return result
 
     for step in range(3):
@@ -120,7 +133,7 @@ def attempt(k, rank, world, local):
         if out is None:
             return finish(None)
         got, ref, P0 = out
-        tol = 2e-5 if step == 0 else 1e-4            # same weights: 2e-5; later steps: trajectories drift (see test_gpu_parity)
+        tol = 2e-5 if step == 0 else 1e-3            # same weights: 2e-5; later steps vs the ORACLE are a sanity bound only
         for i, name in enumerate(NAMES):
             r = ref["losses"][name]
             assert abs(got[i] - r) <= tol * max(abs(r), 1e-3), (rank, step, name, float(got[i]), r)
@@ -147,18 +160,17 @@ def attempt(k, rank, world, local):
                 bad = np.nonzero(d.max(1) > 2e-4 * np.abs(b_).max())[0]
                 assert bad.size == 0, (nm, "first moment after one step", float(d.max()), float(np.abs(b_).max()), "bad rows per owner",
                                        [int((bad % world == r).sum()) for r in range(world)], bad[:12].tolist())
-    # variables after the steps (collective gathers)
+    # variables after the steps (collective gathers) against the single-GPU run
     var = eng.get_variables()
-    for name in ("item_embedding", "cate_embedding", "user_long_embedding", "user_short_embedding"):
-        note(name, var[EMB + name], om.params[EMB + name].numpy(), 5e-5)   # 5 % of one lr step over 3 steps
-    for name in om.params:
-        if name in var and "embedding/" not in name:
+    if solo is not None:
+        one = solo.get_variables()
+        for name in one:
             if name.rsplit("/", 1)[-1].startswith("b_nn_layer"):
                 continue                                # bias in front of BN: zero data gradient, Adam follows fp32 noise
-            note(name, var[name], om.params[name].numpy(), 1e-4)
-    for name, t in om.bn_state.items():
-        atol = 2e-4 if name.endswith("moving_mean") else 1e-6
-        assert np.allclose(var[name], t.numpy(), rtol=1e-4, atol=atol), name
+            if name.endswith("moving_mean") or name.endswith("moving_variance"):
+                assert np.allclose(var[name], one[name], rtol=1e-5, atol=2e-5), name
+            else:
+                note(name, var[name], one[name], 2e-5)  # 2 % of one lr step
     # replicated dense parameters must be bit-identical on every rank
     dp = eng.pool["dense_param"].clone()
     lo, hi = dp.clone(), dp.clone()
@@ -171,9 +183,10 @@ def attempt(k, rank, world, local):
     if out is None:
         return finish(None)
     got, ref, _ = out
-    assert abs(got[0] - ref["losses"]["loss"]) <= 1e-4 * abs(ref["losses"]["loss"]), (rank, float(got[0]), ref["losses"]["loss"])
+    assert abs(got[0] - ref["losses"]["loss"]) <= 1e-3 * abs(ref["losses"]["loss"]), (rank, float(got[0]), ref["losses"]["loss"])
     item = eng.get_variables()[EMB + "item_embedding"]
-    assert np.abs(item - om.params[EMB + "item_embedding"].numpy()).max() <= 3e-3
+    if solo is not None:
+        assert np.abs(item - solo.get_variables()[EMB + "item_embedding"]).max() <= 3e-3
     # data-parallel scoring
     ev = O.make_batch(999, 37, T, nu, ni, nc, grouped=False)
     want = om.eval_forward(ev).t["pred"].numpy().reshape(-1)

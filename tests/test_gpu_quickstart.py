@@ -21,10 +21,13 @@ def data_root(tmp_path_factory):
     return str(root)
 
 
-def test_driver_runs_as_subprocess(data_root, tmp_path):
-    """The repo's driver with the reference's flag names (compat/example/00_quick_start/sequential.py)."""
+@pytest.mark.parametrize("train_num_ngs", [0, 4])
+def test_driver_runs_as_subprocess(data_root, tmp_path, train_num_ngs):
+    """The repo's driver with the reference's flag names (compat/example/00_quick_start/sequential.py); train_num_ngs = 4 is
+    the 1 positive + 4 in-batch negatives layout (every row of a batch of 20 becomes a listwise group of 5)."""
     drv = os.path.join(ROOT, "compat", "example", "00_quick_start", "sequential.py")
-    cmd = [sys.executable, drv, "--dataset", "wechat", "--data_path", data_root, "--epochs", "1", "--batch_size", "100",
+    cmd = [sys.executable, drv, "--dataset", "wechat", "--data_path", data_root, "--epochs", "1",
+           "--batch_size", "100" if train_num_ngs == 0 else "20", "--train_num_ngs", str(train_num_ngs),
            "--eval_step", "5", "--show_step", "5", "--save_path", str(tmp_path / "ranking"), "--write_prediction_to_file"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=os.path.dirname(drv))
     assert r.returncode == 0, r.stdout[-3000:]
