@@ -115,6 +115,9 @@ typedef struct PamrecTensorInfo {
 } PamrecTensorInfo;
 
 const char* pamrec_version(void);
+/* sizeof of the structs of this header as compiled into the library, in the order PamrecConfig, PamrecBatch, PamrecBuffers,
+ * PamrecTensorInfo, PamrecLines: lets a foreign-language binding check its mirror of the layouts before the first call */
+int pamrec_abi_sizes(int64_t out[5]);
 
 /* Host-only: allowed without a GPU. */
 int pamrec_create(const PamrecConfig* cfg, PamrecHandle* out);

@@ -58,6 +58,7 @@ class PamrecTensorInfo(C.Structure):
 
 EXPORTS = {
     "pamrec_version": (C.c_char_p, []),
+    "pamrec_abi_sizes": (C.c_int, [C.POINTER(C.c_int64)]),
     "pamrec_create": (C.c_int, [C.POINTER(PamrecConfig), C.POINTER(C.c_void_p)]),
     "pamrec_destroy": (C.c_int, [C.c_void_p]),
     "pamrec_last_error": (C.c_char_p, [C.c_void_p]),
@@ -111,5 +112,10 @@ def load():
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    sizes = (C.c_int64 * 5)()
+    lib.pamrec_abi_sizes(sizes)
+    mirror = [C.sizeof(t) for t in (PamrecConfig, PamrecBatch, PamrecBuffers, PamrecTensorInfo, PamrecLines)]
+    if list(sizes) != mirror:
+        raise RuntimeError(f"ctypes mirrors disagree with include/pamrec_b200.h as compiled: {list(sizes)} vs {mirror} (rebuild the library)")
     _lib = lib
     return lib

@@ -114,6 +114,13 @@ extern "C" {
 
 const char* pamrec_version(void) { return "pamrec_b200 0.1 (sm_100a)"; }
 
+int pamrec_abi_sizes(int64_t out[5]) {
+  if (!out) return -1;
+  out[0] = sizeof(PamrecConfig); out[1] = sizeof(PamrecBatch); out[2] = sizeof(PamrecBuffers);
+  out[3] = sizeof(PamrecTensorInfo); out[4] = sizeof(PamrecLines);
+  return 0;
+}
+
 int pamrec_create(const PamrecConfig* cfg, PamrecHandle* out) {
   if (!cfg || !out) return -1;
   *out = nullptr;

@@ -21,6 +21,7 @@ import torch
 from . import dist as D
 from .deeprec_utils import cal_metric, cal_weighted_metric, filter_single_class_users, load_dict
 from .engine import Engine, EMB, TABLES
+from .prefetch import Prefetcher
 
 __all__ = ["PAMRECModel", "SequentialBaseModel", "BaseModel", "latest_checkpoint", "initial_variables"]
 
@@ -247,8 +248,8 @@ class SequentialBaseModel(BaseModel):
         best_metric, self.best_epoch = 0, 0
         for epoch in range(1, self.hparams.epochs + 1):
             self.hparams.current_epoch = epoch
-            file_iterator = self.iterator.load_data_from_file(train_file, min_seq_length=self.min_seq_length,
-                                                              batch_num_ngs=self.train_num_ngs)
+            file_iterator = Prefetcher(self.iterator.load_data_from_file(train_file, min_seq_length=self.min_seq_length,
+                                                                         batch_num_ngs=self.train_num_ngs))
             self.batch_train(file_iterator, self.sess)
             valid_res = self.run_weighted_eval(valid_file, valid_num_ngs)
             print("eval valid at epoch {0}: {1}".format(epoch, ",".join(str(k) + ":" + str(v) for k, v in valid_res.items())))
@@ -280,8 +281,8 @@ class SequentialBaseModel(BaseModel):
             if break_flag:
                 break
             self.hparams.current_epoch = epoch
-            file_iterator = self.iterator.load_data_from_file(train_file, min_seq_length=self.min_seq_length,
-                                                              batch_num_ngs=self.train_num_ngs)
+            file_iterator = Prefetcher(self.iterator.load_data_from_file(train_file, min_seq_length=self.min_seq_length,
+                                                                         batch_num_ngs=self.train_num_ngs))
             for batch_data_input in file_iterator:
                 if not batch_data_input:
                     continue
@@ -302,6 +303,7 @@ class SequentialBaseModel(BaseModel):
                     elif early_stop > 0 and step - self.best_step >= early_stop * self.hparams.eval_step:
                         print("early stop at epoch {0}, step {1}!".format(epoch, step))
                         break_flag = True
+                        file_iterator.close()
                         break
                     self._maybe_save(progress, "step_" + str(step))
         print(eval_info)
@@ -312,7 +314,7 @@ class SequentialBaseModel(BaseModel):
         """SBM:380-413."""
         preds, labels, group_preds, group_labels = [], [], [], []
         group = num_ngs + 1
-        for feed in self.iterator.load_data_from_file(filename, min_seq_length=self.min_seq_length, batch_num_ngs=0):
+        for feed in Prefetcher(self.iterator.load_data_from_file(filename, min_seq_length=self.min_seq_length, batch_num_ngs=0)):
             if feed:
                 step_pred, step_labels = self.eval(self.sess, feed)
                 preds.extend(np.reshape(step_pred, -1))
@@ -330,7 +332,7 @@ class SequentialBaseModel(BaseModel):
             raise NotImplementedError("alpha outputs belong to the CLSR models, not to PAMRec (SBM:518-532)")
         users, preds, labels, group_preds, group_labels = [], [], [], [], []
         group = num_ngs + 1
-        for feed in self.iterator.load_data_from_file(filename, min_seq_length=self.min_seq_length, batch_num_ngs=0):
+        for feed in Prefetcher(self.iterator.load_data_from_file(filename, min_seq_length=self.min_seq_length, batch_num_ngs=0)):
             if not feed:
                 continue
             step_user, step_pred, step_labels = self.eval_with_user(self.sess, feed)
@@ -353,7 +355,7 @@ class SequentialBaseModel(BaseModel):
         writer = self.engine.rank == 0
         wt = open(outfile_name, "w") if writer else None
         try:
-            for feed in self.iterator.load_data_from_file(infile_name, batch_num_ngs=0):
+            for feed in Prefetcher(self.iterator.load_data_from_file(infile_name, batch_num_ngs=0)):
                 if feed:
                     step_pred = np.reshape(self.infer(self.sess, feed), -1)
                     if writer:

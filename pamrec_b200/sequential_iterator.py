@@ -144,17 +144,18 @@ class SequentialIterator:
     # ------------------------------------------------------------------ batches
     def load_data_from_file(self, infile, batch_num_ngs=0, min_seq_length=1):
         """Generator of feed mappings (IT:334-763).  The mode switch is on the file's basename (IT:361-364)."""
-        self.train = os.path.basename(infile) == "train_data"
-        if infile not in self.iter_data:
+        train = os.path.basename(infile) == "train_data"
+        self.train = train                       # read by parser_one_line; everything below uses the local flag, so a scoring
+        if infile not in self.iter_data:         # pass may start on this iterator while a training generator is suspended
             self.iter_data[infile] = self.parse_file(infile)
         lines = self.iter_data[infile]
-        native = self._native(infile, lines)
-        if self.train:
+        native = self._native(infile, lines, train)
+        if train:
             gen = self._train_batches_native(native, lines) if native else self._train_batches(lines)
         else:
             gen = self._eval_batches_native(native, min_seq_length) if native else self._eval_batches(lines, min_seq_length)
         if batch_num_ngs > 0:
-            if not self.train:
+            if not train:
                 # evaluation files carry their negatives as extra lines after each positive (QS:483,493)
                 raise NotImplementedError("batch_num_ngs > 0 applies to the training file only")
             gen = (self._with_negatives(b, batch_num_ngs) for b in gen)
@@ -194,19 +195,19 @@ class SequentialIterator:
         return out
 
     # ------------------------------------------------------------------ native batcher (csrc/batcher.cu)
-    def _native(self, infile, lines):
+    def _native(self, infile, lines, train):
         """Flat columns + a pamrec_batcher handle for this file, or None when the pure-Python path must be used."""
         if os.environ.get("PAMREC_PY_ITERATOR", "0") == "1":
             return None
         if self.noise_train_hist != 0 or self.noise_train_listwise != 0 or self.batch_size % 5:
             return None
         cache = self.__dict__.setdefault("_native_cache", {})
-        key = (infile, self.train)
+        key = (infile, train)
         if key in cache:
             return cache[key]
         from . import _lib
         lib = _lib.load()
-        h = 1 if self.train else 6                                   # first history column inside a parsed line
+        h = 1 if train else 6                                        # first history column inside a parsed line
         rows = [ln for ln in lines if ln]
         lens = [len(ln[h]) for ln in rows]
         if any(not (len(ln[h + 1]) == len(ln[h + 2]) == len(ln[h + 3]) == len(ln[h + 4]) == n) for ln, n in zip(rows, lens)):
@@ -215,7 +216,7 @@ class SequentialIterator:
         cat = lambda j, dt: (np.concatenate([np.asarray(ln[j], dtype=dt) for ln in rows]) if rows else np.zeros(0, dt))
         col = {"offsets": np.concatenate([[0], np.cumsum(lens)]).astype(np.int64), "items": cat(h, np.int32), "cates": cat(h + 1, np.int32),
                "durs": cat(h + 2, np.float64), "sats": cat(h + 3, np.float64), "plays": cat(h + 4, np.float64)}
-        if self.train:
+        if train:
             col["user_ids"] = np.asarray([ln[0] for ln in rows], np.int32)
         else:
             col["user_ids"] = np.asarray([ln[2] for ln in rows], np.int32)
@@ -230,7 +231,7 @@ class SequentialIterator:
         if lib.pamrec_batcher_create(C.byref(desc), borders.ctypes.data, len(borders), self.max_seq_length, C.byref(handle)) != 0:
             raise RuntimeError("pamrec_batcher_create failed")
         nat = dict(lib=lib, handle=handle, col=col, borders=borders, desc=desc, n=len(rows))
-        if self.train:
+        if train:
             nat["sat_num"] = np.add.reduceat(col["sats"], col["offsets"][:-1]) if len(rows) else np.zeros(0)
             nat["sat_num"] = np.where(np.asarray(lens) > 0, nat["sat_num"], 0.0)
         cache[key] = nat

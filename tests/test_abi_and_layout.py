@@ -23,6 +23,19 @@ def test_header_symbols_exported(lib_built):
     assert b"sm_100a" in _lib.load().pamrec_version()
 
 
+def test_struct_layouts_match_the_header(lib_built):
+    """The ctypes mirrors have the sizes the compiler gave the header's structs (checked again at every load)."""
+    import ctypes as C
+    from pamrec_b200 import _lib as L
+    lib = L.load()
+    sizes = (C.c_int64 * 5)()
+    assert lib.pamrec_abi_sizes(sizes) == 0
+    assert list(sizes) == [C.sizeof(t) for t in (L.PamrecConfig, L.PamrecBatch, L.PamrecBuffers, L.PamrecTensorInfo, L.PamrecLines)]
+    # field offsets that a binding in another language is most likely to get wrong (padding after int32 members)
+    assert L.PamrecBatch.item_history.offset == 8 and L.PamrecBatch.global_batch.offset == 8 + 10 * 8
+    assert L.PamrecTensorInfo.offset.offset % 8 == 0 and L.PamrecLines.offsets.offset == 8
+
+
 def test_inventory_matches_oracle(lib_built):
     from pamrec_b200.engine import Engine
     eng = Engine(n_users=37, n_items=211, n_cates=13, max_seq_len=50, max_batch=25)
