@@ -1,8 +1,8 @@
 // Encoder kernels: embedding gather, bucket planning, time-aware Q/K/V projection,
 // key-masked attention, LayerNorm + point-wise FFN — forward and backward.
 //
-// Token-parallel kernels (projection, FFN): a CTA owns a tile of 128 token rows (40 floats each, shared-memory row
-// stride 44) of 64 tokens, warp w the rows 16w .. 16w+15, and every [tokens x 40] x [40 x 40] contraction - forward, input gradient
+// Token-parallel kernels (projection, FFN): a CTA owns a tile of kTokTile = 64 token rows (40 floats each, shared-memory row
+// stride 44), warp w the rows 16w .. 16w+15, and every [tokens x 40] x [40 x 40] contraction - forward, input gradient
 // and weight gradient - runs on the tensor cores as an error-compensated 3xTF32 mma.sync (mma.cuh); LayerNorm and
 // its backward are evaluated in the MMA fragment layout (row sums are 4-lane shuffles).  Tokens are bucket-sorted
 // first so that a CTA needs exactly one (Wq,Wk,Wv)[bucket] triple: the reference instead materialises a
