@@ -117,7 +117,7 @@ typedef struct PamrecTensorInfo {
 const char* pamrec_version(void);
 /* sizeof of the structs of this header as compiled into the library, in the order PamrecConfig, PamrecBatch, PamrecBuffers,
  * PamrecTensorInfo, PamrecLines: lets a foreign-language binding check its mirror of the layouts before the first call */
-int pamrec_abi_sizes(int64_t out[5]);
+int pamrec_abi_sizes(int64_t out[6]);
 
 /* Host-only: allowed without a GPU. */
 int pamrec_create(const PamrecConfig* cfg, PamrecHandle* out);
@@ -198,6 +198,29 @@ int pamrec_batcher_begin_eval(PamrecBatcher b, int min_seq_length);
 /* fills up to batch_size rows of the 19 arrays (order of SequentialIterator.gen_feed_dict, IT:1155-1175; int32 ids, float32
  * values, [rows] or [rows, max_seq_len]); returns the rows written, 0 when the pass is exhausted, < 0 on error */
 int pamrec_batcher_next(PamrecBatcher b, int batch_size, void* const* arrays);
+
+/* ---- Tokeniser (host only): parser_one_line / parse_file of the reference (io/sequential_iterator.py:195-332) over a whole
+ * data file, producing the flat columns of PamrecLines.  `train` selects the 6-column line (one user per line) or the
+ * 11-column line (one impression per line).  A vocabulary is the reference's pickled dict given as UTF-8 key bytes:
+ * key i = bytes[offsets[i] .. offsets[i+1]), index values[i]; unknown tokens map to 0 (`dict.get(token, 0)`).
+ * Returns 0, < 0 on IO / argument errors, or PAMREC_TOK_FALLBACK when the file holds anything outside the strict subset this
+ * parser converts bit-identically to Python (non-ASCII bytes, a lone CR, numeric tokens other than plain decimals, ragged or
+ * missing columns): the caller then runs the Python parser, which also raises the reference's exceptions for bad lines. */
+#define PAMREC_TOK_FALLBACK 1
+typedef struct PamrecTokens_* PamrecTokens;
+typedef struct PamrecVocab { int64_t n; const char* bytes; const int64_t* offsets; const int32_t* values; } PamrecVocab;
+int pamrec_tokenize_file(const char* path, int train, const PamrecVocab* users, const PamrecVocab* items, const PamrecVocab* cates,
+                         int n_threads /* 0 = all host cores */, PamrecTokens* out, int64_t* n_lines, int64_t* n_tokens);
+/* copies the columns into caller-allocated arrays: dst->n_lines must equal n_lines, offsets has n_lines + 1 entries, the five
+ * history columns n_tokens each, the per-line columns n_lines each (the five eval columns are ignored for a train file) */
+int pamrec_tokens_read(PamrecTokens t, const PamrecLines* dst);
+int pamrec_tokens_free(PamrecTokens t);
+
+/* ---- Checkpoint support (host only): CRC-32C (Castagnoli) as stored, masked, in TensorFlow tensor-bundle checkpoints - the
+ * format the reference's tf.train.Saver writes (models/base_model.py:62, :401-417).  `crc` is the value returned for the bytes
+ * before `data` (0 to start).  The _portable variant never uses the CPU's crc32 instruction (the two are tested equal). */
+uint32_t pamrec_crc32c(uint32_t crc, const void* data, size_t n);
+uint32_t pamrec_crc32c_portable(uint32_t crc, const void* data, size_t n);
 
 /* number of kernel launches issued by the last device call on this handle */
 int64_t pamrec_last_launch_count(PamrecHandle h);

@@ -51,6 +51,10 @@ class PamrecLines(C.Structure):
                 ("tgt_dur", C.c_void_p)]
 
 
+class PamrecVocab(C.Structure):
+    _fields_ = [("n", C.c_int64), ("bytes", C.c_void_p), ("offsets", C.c_void_p), ("values", C.c_void_p)]
+
+
 class PamrecTensorInfo(C.Structure):
     _fields_ = [("name", C.c_char * 160), ("pool", C.c_int32), ("dtype", C.c_int32), ("flags", C.c_int32),
                 ("offset", C.c_int64), ("numel", C.c_int64), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
@@ -93,6 +97,12 @@ EXPORTS = {
     "pamrec_batcher_begin_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "pamrec_batcher_begin_eval": (C.c_int, [C.c_void_p, C.c_int]),
     "pamrec_batcher_next": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "pamrec_tokenize_file": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(PamrecVocab), C.POINTER(PamrecVocab), C.POINTER(PamrecVocab),
+                                       C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "pamrec_tokens_read": (C.c_int, [C.c_void_p, C.POINTER(PamrecLines)]),
+    "pamrec_tokens_free": (C.c_int, [C.c_void_p]),
+    "pamrec_crc32c": (C.c_uint32, [C.c_uint32, C.c_void_p, C.c_size_t]),
+    "pamrec_crc32c_portable": (C.c_uint32, [C.c_uint32, C.c_void_p, C.c_size_t]),
 }
 
 _lib = None
@@ -112,9 +122,9 @@ def load():
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    sizes = (C.c_int64 * 5)()
+    sizes = (C.c_int64 * 6)()
     lib.pamrec_abi_sizes(sizes)
-    mirror = [C.sizeof(t) for t in (PamrecConfig, PamrecBatch, PamrecBuffers, PamrecTensorInfo, PamrecLines)]
+    mirror = [C.sizeof(t) for t in (PamrecConfig, PamrecBatch, PamrecBuffers, PamrecTensorInfo, PamrecLines, PamrecVocab)]
     if list(sizes) != mirror:
         raise RuntimeError(f"ctypes mirrors disagree with include/pamrec_b200.h as compiled: {list(sizes)} vs {mirror} (rebuild the library)")
     _lib = lib

@@ -114,10 +114,10 @@ extern "C" {
 
 const char* pamrec_version(void) { return "pamrec_b200 0.1 (sm_100a)"; }
 
-int pamrec_abi_sizes(int64_t out[5]) {
+int pamrec_abi_sizes(int64_t out[6]) {
   if (!out) return -1;
   out[0] = sizeof(PamrecConfig); out[1] = sizeof(PamrecBatch); out[2] = sizeof(PamrecBuffers);
-  out[3] = sizeof(PamrecTensorInfo); out[4] = sizeof(PamrecLines);
+  out[3] = sizeof(PamrecTensorInfo); out[4] = sizeof(PamrecLines); out[5] = sizeof(PamrecVocab);
   return 0;
 }
 

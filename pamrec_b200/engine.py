@@ -248,6 +248,28 @@ class Engine:
             st[name + "/Adam_1"] = self._gather_table(self.pool[pre + "_v"], self._vocab(pre))
         return st
 
+    def set_optimizer_state(self, st):
+        """Inverse of get_optimizer_state: TF slot names (``<var>/Adam`` = m, ``<var>/Adam_1`` = v) and ``step``.  Slots that are
+        missing keep their value; unknown names raise."""
+        for key, val in st.items():
+            if key == "step":
+                self.step = int(np.asarray(val).reshape(-1)[0])
+                continue
+            name, _, slot = key.rpartition("/")
+            which = {"Adam": "m", "Adam_1": "v"}.get(slot)
+            if which is None:
+                raise KeyError(f"unknown optimizer slot {key}")
+            t = torch.as_tensor(np.asarray(val, dtype=np.float32))
+            if name in TABLES:
+                if self.tables == "sharded":
+                    t = torch.from_numpy(D.shard_table(t.numpy(), self.world, self.rank))
+                self.pool[f"{TABLES[name][0]}_{which}"].copy_(t.to(self.device))
+            elif name in self.info[L.POOL_DENSE]:
+                dst = self.dense(name, "dense_" + which)
+                dst.copy_(t.to(self.device).view(dst.shape))
+            else:
+                raise KeyError(f"unknown optimizer slot {key}")
+
     def _vocab(self, pre):
         nu, ni, nc, _, _ = self.dims
         return {"item": ni, "cate": nc, "ulong": nu, "ushort": nu}[pre]

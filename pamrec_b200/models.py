@@ -18,6 +18,7 @@ import time
 import numpy as np
 import torch
 
+from . import checkpoint as CK
 from . import dist as D
 from .deeprec_utils import cal_metric, cal_weighted_metric, filter_single_class_users, load_dict
 from .engine import Engine, EMB, TABLES
@@ -87,40 +88,61 @@ def latest_checkpoint(model_dir):
 
 
 class Saver:
-    """Counterpart of ``tf.train.Saver(max_to_keep=epochs)`` (BM:62).  One ``<path>.npz`` per checkpoint keyed by TF
-    variable name: model variables + BN moving statistics — exactly the Saver's var-list in the reference, which is
-    built before the optimizer exists, so Adam slots are NOT part of a checkpoint."""
+    """Counterpart of ``tf.train.Saver(max_to_keep=epochs)`` (BM:62).  One checkpoint per ``save_path`` keyed by TF variable
+    name: model variables + BN moving statistics — exactly the Saver's var-list in the reference, which is built before the
+    optimizer exists, so Adam slots are NOT part of a checkpoint.  File formats: pamrec_b200/checkpoint.py
+    (``hparams.checkpoint_format``: "safetensors" by default, "tf" for a TensorFlow tensor-bundle, "npz" legacy;
+    ``hparams.save_optimizer`` adds the Adam state under the ``optimizer/`` key-space so that training can resume exactly -
+    an extension, off by default like in the reference).  ``restore`` reads any of the formats."""
 
     def __init__(self, model, max_to_keep=5):
         self.model = model
         self.max_to_keep = max(int(max_to_keep), 1)
         self.kept = []
+        self.fmt = getattr(model.hparams, "checkpoint_format", "safetensors")
+        self.with_optimizer = bool(getattr(model.hparams, "save_optimizer", False))
+        if self.fmt not in CK.FORMATS:
+            raise ValueError("checkpoint_format must be one of {}".format(CK.FORMATS))
 
     def save(self, sess=None, save_path=None):
         d = os.path.dirname(save_path)
         if d:
             os.makedirs(d, exist_ok=True)
-        variables = self.model.engine.get_variables()          # collective when the tables are sharded over ranks
+        eng = self.model.engine
+        variables = eng.get_variables()                          # collective when the tables are sharded over ranks
+        optimizer = eng.get_optimizer_state() if self.with_optimizer else None
+        if save_path in self.kept:
+            self.kept.remove(save_path)
         self.kept.append(save_path)
-        if self.model.engine.rank != 0:
+        if eng.rank != 0:
             torch.distributed.barrier()                          # rank 0 finishes writing before anyone may restore
             return save_path
-        np.savez(save_path + ".npz", **{k.replace("/", "|"): v for k, v in variables.items()})
+        CK.remove(save_path)                                     # a path written earlier in another format
+        CK.save(save_path, variables, fmt=self.fmt, optimizer=optimizer)
         while len(self.kept) > self.max_to_keep:
-            old = self.kept.pop(0)
-            if os.path.exists(old + ".npz"):
-                os.remove(old + ".npz")
-        with open(os.path.join(d, "checkpoint"), "w") as f:
+            CK.remove(self.kept.pop(0))
+        with open(os.path.join(d, "checkpoint"), "w") as f:      # the CheckpointState text proto tf.train.latest_checkpoint reads
             f.write('model_checkpoint_path: "{}"\n'.format(os.path.basename(save_path)))
             for p in self.kept:
                 f.write('all_model_checkpoint_paths: "{}"\n'.format(os.path.basename(p)))
-        if self.model.engine.world > 1:
+        if eng.world > 1:
             torch.distributed.barrier()
         return save_path
 
     def restore(self, sess, path):
-        with np.load(path + ".npz") as z:
-            self.model.engine.set_variables({k.replace("|", "/"): z[k] for k in z.files})
+        variables, optimizer = CK.load(path)
+        known = self.model.engine.variable_shapes()
+        # a checkpoint written by the reference's Saver holds every global variable of ITS graph; names this graph does not
+        # have (none for PAMRec as shipped) are reported, not silently dropped
+        extra = sorted(set(variables) - set(known))
+        if extra:
+            raise KeyError("checkpoint {} holds variables this model does not have: {}".format(path, extra[:5]))
+        for name, val in variables.items():
+            if tuple(val.shape) != tuple(known[name]):
+                raise ValueError("checkpoint {}: {} has shape {}, the model expects {}".format(path, name, val.shape, known[name]))
+        self.model.engine.set_variables(variables)
+        if optimizer is not None:
+            self.model.engine.set_optimizer_state(optimizer)
 
 
 class _Session:
@@ -388,7 +410,10 @@ class PAMRECModel(SequentialBaseModel):
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
         self.feed_is_global = getattr(hp, "dp_feed", "global") != "local"
-        cap = hp.batch_size * (1 + max(int(hp.train_num_ngs or 0), 0))      # in-batch negatives multiply the rows of a batch
+        ngs = max(int(hp.train_num_ngs or 0), 0)                             # in-batch negatives multiply the rows of a batch;
+        if ngs < 1 and hp.need_sample:                                       # fit / fit_step force one negative when sampling
+            ngs = 1                                                          # is "needed" (SBM:153-154, SBM:257-258)
+        cap = hp.batch_size * (1 + ngs)
         if world > 1 and self.feed_is_global:
             cap = max(-(-(cap // 5) // world) * 5, -(-cap // world))
         tables = getattr(hp, "tables", None)

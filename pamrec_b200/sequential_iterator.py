@@ -142,18 +142,21 @@ class SequentialIterator:
         return [self.parser_one_line(line) for line in lines if line]
 
     # ------------------------------------------------------------------ batches
+    def _lines(self, infile):
+        """The file parsed by the Python parser, once (IT:366-370 caches per file the same way)."""
+        if infile not in self.iter_data:
+            self.iter_data[infile] = self.parse_file(infile)
+        return self.iter_data[infile]
+
     def load_data_from_file(self, infile, batch_num_ngs=0, min_seq_length=1):
         """Generator of feed mappings (IT:334-763).  The mode switch is on the file's basename (IT:361-364)."""
         train = os.path.basename(infile) == "train_data"
         self.train = train                       # read by parser_one_line; everything below uses the local flag, so a scoring
-        if infile not in self.iter_data:         # pass may start on this iterator while a training generator is suspended
-            self.iter_data[infile] = self.parse_file(infile)
-        lines = self.iter_data[infile]
-        native = self._native(infile, lines, train)
+        native = self._native(infile, train)     # pass may start on this iterator while a training generator is suspended
         if train:
-            gen = self._train_batches_native(native, lines) if native else self._train_batches(lines)
+            gen = self._train_batches_native(native) if native else self._train_batches(self._lines(infile))
         else:
-            gen = self._eval_batches_native(native, min_seq_length) if native else self._eval_batches(lines, min_seq_length)
+            gen = self._eval_batches_native(native, min_seq_length) if native else self._eval_batches(self._lines(infile), min_seq_length)
         if batch_num_ngs > 0:
             if not train:
                 # evaluation files carry their negatives as extra lines after each positive (QS:483,493)
@@ -178,7 +181,8 @@ class SequentialIterator:
             src[i * (ngs + 1)] = i
             group = item_list[i // 5: i // 5 + 5]
             if len(set(item_list) - set(group)) == 0:
-                raise ValueError("in-batch negative sampling cannot terminate: every target of the batch is in the positive slice")
+                return {}            # (a tail batch of one group) no admissible negative exists: the block would spin forever;
+                                     # the batch is dropped like the too-short one above - the loops skip empty feeds
             count = 0
             while count < ngs:
                 rv = random.randint(0, n - 1)
@@ -195,23 +199,68 @@ class SequentialIterator:
         return out
 
     # ------------------------------------------------------------------ native batcher (csrc/batcher.cu)
-    def _native(self, infile, lines, train):
-        """Flat columns + a pamrec_batcher handle for this file, or None when the pure-Python path must be used."""
-        if os.environ.get("PAMREC_PY_ITERATOR", "0") == "1":
+    def _native_vocab(self, lib_mod):
+        """The three vocabularies as (PamrecVocab, keep-alive arrays), or None when one of them is not a plain
+        {str: int32} dict (then `dict.get` semantics cannot be reproduced from key bytes and Python parses)."""
+        if "_native_vocab_cache" in self.__dict__:
+            return self._native_vocab_cache
+        out = []
+        for d in (self.userdict, self.itemdict, self.catedict):
+            ok = type(d) is dict and all(type(k) is str for k in d) and all(type(v) is int and -2 ** 31 <= v < 2 ** 31 for v in d.values())
+            if ok:
+                try:
+                    keys = [k.encode("utf-8") for k in d]
+                except UnicodeEncodeError:
+                    ok = False
+            if not ok:
+                out = None
+                break
+            blob = np.frombuffer(b"".join(keys) or b"\0", np.uint8)
+            offs = np.concatenate([[0], np.cumsum([len(k) for k in keys])]).astype(np.int64)
+            vals = np.fromiter(d.values(), np.int32, len(d))
+            out.append((lib_mod.PamrecVocab(n=len(d), bytes=blob.ctypes.data, offsets=offs.ctypes.data, values=vals.ctypes.data),
+                        (blob, offs, vals)))
+        self._native_vocab_cache = out
+        return out
+
+    def _tokenize_native(self, infile, train):
+        """Flat columns of the file from the native tokenizer (csrc/tokenizer.cu), or None when the file (or the configuration)
+        is outside what it converts bit-identically to `parser_one_line` - then the Python parser runs."""
+        if os.environ.get("PAMREC_PY_TOKENIZER", "0") == "1" or self.noise_only_predict != 0 or self.col_spliter != "\t":
             return None
-        if self.noise_train_hist != 0 or self.noise_train_listwise != 0 or self.batch_size % 5:
-            return None
-        cache = self.__dict__.setdefault("_native_cache", {})
-        key = (infile, train)
-        if key in cache:
-            return cache[key]
         from . import _lib
         lib = _lib.load()
+        voc = self._native_vocab(_lib)
+        if voc is None:
+            return None
+        handle, n_lines, n_tok = C.c_void_p(), C.c_int64(), C.c_int64()
+        rc = lib.pamrec_tokenize_file(os.fsencode(infile), int(train), C.byref(voc[0][0]), C.byref(voc[1][0]), C.byref(voc[2][0]),
+                                      int(os.environ.get("PAMREC_TOKENIZER_THREADS", "0")), C.byref(handle), C.byref(n_lines), C.byref(n_tok))
+        if rc == -2:
+            raise FileNotFoundError(infile)      # what open() raises in parse_file
+        if rc != 0:
+            return None
+        try:
+            n, m = n_lines.value, n_tok.value
+            col = {"offsets": np.empty(n + 1, np.int64), "items": np.empty(m, np.int32), "cates": np.empty(m, np.int32),
+                   "durs": np.empty(m, np.float64), "sats": np.empty(m, np.float64), "plays": np.empty(m, np.float64),
+                   "user_ids": np.empty(n, np.int32)}
+            if not train:
+                col.update(label_sat=np.empty(n, np.float64), label_play=np.empty(n, np.float64), tgt_item=np.empty(n, np.int32),
+                           tgt_cate=np.empty(n, np.int32), tgt_dur=np.empty(n, np.float64))
+            desc = _lib.PamrecLines(n_lines=n, **{k: v.ctypes.data for k, v in col.items()})
+            if lib.pamrec_tokens_read(handle, C.byref(desc)) != 0:
+                raise RuntimeError("pamrec_tokens_read failed")
+        finally:
+            lib.pamrec_tokens_free(handle)
+        return col
+
+    def _flatten(self, lines, train):
+        """The same columns from lines parsed in Python; None for ragged history columns (the reference zips them)."""
         h = 1 if train else 6                                        # first history column inside a parsed line
         rows = [ln for ln in lines if ln]
         lens = [len(ln[h]) for ln in rows]
         if any(not (len(ln[h + 1]) == len(ln[h + 2]) == len(ln[h + 3]) == len(ln[h + 4]) == n) for ln, n in zip(rows, lens)):
-            cache[key] = None                                        # ragged columns: the reference zips them, keep Python
             return None
         cat = lambda j, dt: (np.concatenate([np.asarray(ln[j], dtype=dt) for ln in rows]) if rows else np.zeros(0, dt))
         col = {"offsets": np.concatenate([[0], np.cumsum(lens)]).astype(np.int64), "items": cat(h, np.int32), "cates": cat(h + 1, np.int32),
@@ -225,15 +274,39 @@ class SequentialIterator:
             col["tgt_item"] = np.asarray([ln[3] for ln in rows], np.int32)
             col["tgt_cate"] = np.asarray([ln[4] for ln in rows], np.int32)
             col["tgt_dur"] = np.asarray([ln[5] for ln in rows], np.float64)
-        desc = _lib.PamrecLines(n_lines=len(rows), **{k: v.ctypes.data for k, v in col.items()})
+        return col
+
+    def _native(self, infile, train):
+        """Flat columns + a pamrec_batcher handle for this file, or None when the pure-Python path must be used."""
+        if os.environ.get("PAMREC_PY_ITERATOR", "0") == "1":
+            return None
+        if self.noise_train_hist != 0 or self.noise_train_listwise != 0 or self.batch_size % 5:
+            return None
+        cache = self.__dict__.setdefault("_native_cache", {})
+        key = (infile, train)
+        if key in cache:
+            return cache[key]
+        from . import _lib
+        lib = _lib.load()
+        col = self._tokenize_native(infile, train)
+        if col is None:
+            col = self._flatten(self._lines(infile), train)
+        if col is None:
+            cache[key] = None
+            return None
+        n = len(col["user_ids"])
+        desc = _lib.PamrecLines(n_lines=n, **{k: v.ctypes.data for k, v in col.items()})
         borders = np.asarray(_borders(self.dataset, self.bucket_num), np.float64)
         handle = C.c_void_p()
         if lib.pamrec_batcher_create(C.byref(desc), borders.ctypes.data, len(borders), self.max_seq_length, C.byref(handle)) != 0:
             raise RuntimeError("pamrec_batcher_create failed")
-        nat = dict(lib=lib, handle=handle, col=col, borders=borders, desc=desc, n=len(rows))
+        nat = dict(lib=lib, handle=handle, col=col, borders=borders, desc=desc, n=n)
         if train:
-            nat["sat_num"] = np.add.reduceat(col["sats"], col["offsets"][:-1]) if len(rows) else np.zeros(0)
-            nat["sat_num"] = np.where(np.asarray(lens) > 0, nat["sat_num"], 0.0)
+            off = col["offsets"]
+            nonempty = off[1:] > off[:-1]
+            nat["sat_num"] = np.zeros(n)
+            if nonempty.any():                                       # sum(sats) per line, in file order like the builtin
+                nat["sat_num"][nonempty] = np.add.reduceat(col["sats"], off[:-1][nonempty])
         cache[key] = nat
         return nat
 
@@ -252,7 +325,7 @@ class SequentialIterator:
                 return
             yield {k: (a if n == bs else a[:n]) for k, a in zip(FEED_KEYS, arrs)}
 
-    def _train_batches_native(self, nat, lines):
+    def _train_batches_native(self, nat):
         G = self.BEGIN_HISTORY_LEN_MAX
         order, begin = [], []
         for idx, sn in enumerate(nat["sat_num"]):                    # file order: the RNG call sequence of IT:538-545

@@ -28,9 +28,9 @@ def test_struct_layouts_match_the_header(lib_built):
     import ctypes as C
     from pamrec_b200 import _lib as L
     lib = L.load()
-    sizes = (C.c_int64 * 5)()
+    sizes = (C.c_int64 * 6)()
     assert lib.pamrec_abi_sizes(sizes) == 0
-    assert list(sizes) == [C.sizeof(t) for t in (L.PamrecConfig, L.PamrecBatch, L.PamrecBuffers, L.PamrecTensorInfo, L.PamrecLines)]
+    assert list(sizes) == [C.sizeof(t) for t in (L.PamrecConfig, L.PamrecBatch, L.PamrecBuffers, L.PamrecTensorInfo, L.PamrecLines, L.PamrecVocab)]
     # field offsets that a binding in another language is most likely to get wrong (padding after int32 members)
     assert L.PamrecBatch.item_history.offset == 8 and L.PamrecBatch.global_batch.offset == 8 + 10 * 8
     assert L.PamrecTensorInfo.offset.offset % 8 == 0 and L.PamrecLines.offsets.offset == 8

@@ -59,7 +59,7 @@ def test_fit_checkpoint_eval_match_oracle(data_root, tmp_path):
     valid, test = os.path.join(d, "valid_data"), os.path.join(d, "test_data")
     assert model.fit_step(os.path.join(d, "train_data"), valid, valid_num_ngs=0, eval_metric="auc") is model
     ckpt = tf.train.latest_checkpoint(model_dir)
-    assert ckpt and os.path.exists(ckpt + ".npz")
+    assert ckpt and os.path.exists(ckpt + ".safetensors")
     final = model.run_weighted_eval(test, num_ngs=0)
     for k in ("auc", "logloss", "wauc", "wmrr", "wndcg@2", "whit@4"):
         assert k in final and np.isfinite(final[k]), (k, final)
@@ -88,3 +88,61 @@ def test_fit_checkpoint_eval_match_oracle(data_root, tmp_path):
         want.append(om.eval_forward(f2).t["pred"].numpy().reshape(-1))
     got, want = np.concatenate(got), np.concatenate(want)
     assert got.shape == want.shape and np.abs(got - want).max() <= 1e-4, float(np.abs(got - want).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["safetensors", "tf"])
+def test_resume_from_a_checkpoint_with_optimizer_state(data_root, tmp_path, fmt):
+    """hparams.save_optimizer (an extension: the reference's Saver never holds Adam slots, BM:61-63) stores m, v and the step
+    under `optimizer/`; a fresh model restored from it continues like the uninterrupted run, in either file format."""
+    import random
+    sys.path.insert(0, os.path.join(ROOT, "compat"))
+    from reco_utils.recommender.deeprec.deeprec_utils import prepare_hparams
+    from reco_utils.recommender.deeprec.io.sequential_iterator import SequentialIterator
+    from reco_utils.recommender.deeprec.models.sequential.pamrec import PAMRECModel
+    d = os.path.join(data_root, "wechat")
+    model_dir = str(tmp_path / "model") + "/"
+
+    def make(seed, **kw):
+        hp = prepare_hparams(os.path.join(ROOT, "pamrec_b200", "config", "mmoe.yaml"), dataset="wechat", bucket_num=10, add_feature=False,
+                             embed_l2=1e-6, layer_l2=1e-6, discrepancy_loss_weight=0.1, learning_rate=0.001, epochs=1, is_clip_norm=1,
+                             batch_size=100, show_step=10 ** 9, MODEL_DIR=model_dir, SUMMARIES_DIR=str(tmp_path / "s") + "/",
+                             user_vocab=os.path.join(d, "user_vocab.pkl"), item_vocab=os.path.join(d, "item_vocab.pkl"),
+                             cate_vocab=os.path.join(d, "category_vocab.pkl"), train_num_ngs=0, max_seq_length=50, pairwise_metrics=[],
+                             weighted_metrics=["wauc"], fuzhu_weight=0.5, fine_tune=False, noise_train_hist=0, noise_train_listwise=0,
+                             noise_only_predict=0, write_tfevents=False, **kw)
+        return PAMRECModel(hp, SequentialIterator, seed=seed)
+    a = make(8)
+    random.seed(5)
+    feeds = []
+    for f in a.iterator.load_data_from_file(os.path.join(d, "train_data")):
+        feeds.append(f)
+        if len(feeds) == 6:
+            break
+    assert len(feeds) == 6
+    for f in feeds:
+        a.train(None, f)
+    want = a.engine.get_variables()
+    b = make(8, save_optimizer=True, checkpoint_format=fmt)
+    for f in feeds[:3]:
+        b.train(None, f)
+    path = b.saver.save(save_path=model_dir + "mid")
+    c = make(99)                                                  # other initial values, no optimizer history
+    c.load_model(path)
+    assert c.engine.step == 3
+    for f in feeds[3:]:
+        c.train(None, f)
+    got = c.engine.get_variables()
+    worst = max(float(np.abs(got[n] - want[n]).max()) for n in want)
+    assert worst <= 1e-5, worst                                   # fp32 atomics reorder sums between runs; a lost Adam state is ~1e-3
+    # the same checkpoint without the optimizer key-space (what the reference's Saver writes) restarts Adam from zero
+    from pamrec_b200 import checkpoint as CK
+    variables, opt = CK.load(path)
+    assert opt is not None and int(opt["step"]) == 3
+    CK.save(model_dir + "weights_only", variables, fmt=fmt)
+    e = make(99)
+    e.load_model(model_dir + "weights_only")
+    for f in feeds[3:]:
+        e.train(None, f)
+    cold = e.engine.get_variables()
+    assert max(float(np.abs(cold[n] - want[n]).max()) for n in want) > 1e-4

@@ -257,3 +257,7 @@ def test_in_batch_negative_sampler_follows_the_disabled_reference_block():
             r = 5 * i + j
             assert int(n0["items"][r]) not in group                     # the rejection rule of IT:949-951, slice as written
             assert (int(n0["items"][r]), int(n0["cates"][r]), float(n0["durations"][r])) in pair
+    # a batch in which every target is in the positive's slice admits no negative (the block would spin forever): it is dropped,
+    # like the batch of fewer than 5 rows the block itself returns None for
+    lone = {k: v[:5] for k, v in b0.items()}
+    assert it._with_negatives(lone, 4) == {} and it._with_negatives({k: v[:3] for k, v in b0.items()}, 4) == {}
