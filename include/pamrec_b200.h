@@ -198,6 +198,14 @@ int pamrec_batcher_begin_eval(PamrecBatcher b, int min_seq_length);
 /* fills up to batch_size rows of the 19 arrays (order of SequentialIterator.gen_feed_dict, IT:1155-1175; int32 ids, float32
  * values, [rows] or [rows, max_seq_len]); returns the rows written, 0 when the pass is exhausted, < 0 on error */
 int pamrec_batcher_next(PamrecBatcher b, int batch_size, void* const* arrays);
+/* data parallel: the same GLOBAL batch is drawn, but only the units rank `rank` of `world` trains on / scores are written
+ * (listwise groups rank, rank + world, ... of a training batch; rows likewise of an eval batch), compacted to the front of
+ * the arrays.  Returns this rank's rows (may be 0 while *global_rows > 0); *global_rows = 0 when the pass is exhausted.
+ * Every rank running the same pass with its own rank sees the same sequence of global batches.  global_labels_satisfied /
+ * global_users (optional, batch_size floats each) receive those two columns for EVERY row of the global batch: the scoring
+ * loops compute their metrics over all rows on every rank (sequential_base_model.py:440-464). */
+int pamrec_batcher_next_shard(PamrecBatcher b, int batch_size, int world, int rank, void* const* arrays,
+                              float* global_labels_satisfied, float* global_users, int* global_rows);
 
 /* ---- Tokeniser (host only): parser_one_line / parse_file of the reference (io/sequential_iterator.py:195-332) over a whole
  * data file, producing the flat columns of PamrecLines.  `train` selects the 6-column line (one user per line) or the

@@ -97,6 +97,8 @@ EXPORTS = {
     "pamrec_batcher_begin_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "pamrec_batcher_begin_eval": (C.c_int, [C.c_void_p, C.c_int]),
     "pamrec_batcher_next": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "pamrec_batcher_next_shard": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p,
+                                            C.POINTER(C.c_int)]),
     "pamrec_tokenize_file": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(PamrecVocab), C.POINTER(PamrecVocab), C.POINTER(PamrecVocab),
                                        C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "pamrec_tokens_read": (C.c_int, [C.c_void_p, C.POINTER(PamrecLines)]),

@@ -188,13 +188,22 @@ int pamrec_batcher_begin_eval(PamrecBatcher b, int min_seq_length) {
   return 0;
 }
 
-int pamrec_batcher_next(PamrecBatcher b, int batch_size, void* const* arrays) {
-  if (!b || !arrays || batch_size < 1 || !b->active) return -1;
+}  // extern "C"
+
+namespace {
+
+// One GLOBAL batch of up to batch_size rows is drawn from the pass; the units rank `rank` of `world` owns (listwise groups
+// g = rank, rank + world, ... of a training batch, rows likewise of an eval batch: pamrec_b200/dist.py split_feed) are written,
+// compacted, into the arrays.  The history state of every user advances whether or not its group is written: the expensive
+// part - padding, bucketing and compacting T entries for 12 arrays - is done for owned units only.
+int next_impl(PamrecBatcher b, int batch_size, int world, int rank, void* const* arrays, float* g_labels, float* g_users,
+              int* global_rows) {
+  if (!b || !arrays || batch_size < 1 || !b->active || world < 1 || rank < 0 || rank >= world) return -1;
   Out o;
   static_assert(sizeof(Out) == 19 * sizeof(void*), "19 feed arrays");
   memcpy(&o, arrays, sizeof o);
   const PamrecLines& L = b->L;
-  int64_t rows = 0;
+  int64_t rows = 0, local = 0;                                // rows of the global batch so far / rows written here
   if (b->training) {
     if (batch_size % kGroup) return -3;
     while (rows < batch_size) {
@@ -210,9 +219,14 @@ int pamrec_batcher_next(PamrecBatcher b, int batch_size, void* const* arrays) {
       const int64_t hi = L.offsets[u.line + 1];
       const int64_t future = hi - u.cursor;
       if (future < kGroup) continue;
-      for (int q = 0; q < kGroup; ++q) {                       // IT:645-676
+      const bool mine = (rows / kGroup) % world == rank;
+      for (int q = 0; q < kGroup; ++q) {                       // what the metrics need of every row of the global batch
+        if (g_labels) g_labels[rows + q] = (float)L.sats[u.cursor + q];
+        if (g_users) g_users[rows + q] = (float)u.user;
+      }
+      for (int q = 0; mine && q < kGroup; ++q) {               // IT:645-676
         const int64_t k = u.cursor + q;
-        const int64_t r = rows + q;
+        const int64_t r = local + q;
         o.labels_satisfied[r] = (float)L.sats[k];
         o.labels_play[r] = L.plays[k] >= kValidThreshold ? 1.0f : 0.0f;
         o.plays[r] = (float)b->lisan(L.plays[k] / L.durs[k]);
@@ -220,9 +234,12 @@ int pamrec_batcher_next(PamrecBatcher b, int batch_size, void* const* arrays) {
         o.items[r] = L.items[k]; o.cates[r] = L.cates[k];
         o.durations[r] = (float)L.durs[k];
       }
-      write_history(*b, o, rows, kGroup, (int64_t)u.items.size(), [&](int64_t k) { return u.items[(size_t)k]; },
-                    [&](int64_t k) { return u.cates[(size_t)k]; },
-                    [&](int which, int64_t k) { return which == 0 ? u.durs[(size_t)k] : (which == 1 ? u.sats[(size_t)k] : u.plays[(size_t)k]); });
+      if (mine) {
+        write_history(*b, o, local, kGroup, (int64_t)u.items.size(), [&](int64_t k) { return u.items[(size_t)k]; },
+                      [&](int64_t k) { return u.cates[(size_t)k]; },
+                      [&](int which, int64_t k) { return which == 0 ? u.durs[(size_t)k] : (which == 1 ? u.sats[(size_t)k] : u.plays[(size_t)k]); });
+        local += kGroup;
+      }
       rows += kGroup;
       if (future > kGroup) {                                   // IT:719-741
         for (int q = 0; q < kGroup; ++q) b->push(u, u.cursor + q);
@@ -235,7 +252,10 @@ int pamrec_batcher_next(PamrecBatcher b, int batch_size, void* const* arrays) {
       const int64_t ln = b->eval_line++;
       const int64_t lo = L.offsets[ln], hi = L.offsets[ln + 1];
       if (hi - lo < b->min_seq) continue;                      // IT:406-407
-      const int64_t r = rows;
+      if (g_labels) g_labels[rows] = (float)L.label_sat[ln];
+      if (g_users) g_users[rows] = (float)L.user_ids[ln];
+      if (rows % world != rank) { rows += 1; continue; }
+      const int64_t r = local;
       o.labels_satisfied[r] = (float)L.label_sat[ln];
       o.labels_play[r] = L.label_play[ln] >= 10.0 ? 1.0f : 0.0f;   // IT:410 (10 s at eval, 8 s at train)
       o.plays[r] = (float)L.label_play[ln];                    // IT:411 seconds, not a bucket
@@ -245,10 +265,26 @@ int pamrec_batcher_next(PamrecBatcher b, int batch_size, void* const* arrays) {
       write_history(*b, o, r, 1, hi - lo, [&](int64_t k) { return L.items[lo + k]; }, [&](int64_t k) { return L.cates[lo + k]; },
                     [&](int which, int64_t k) { return which == 0 ? L.durs[lo + k] : (which == 1 ? L.sats[lo + k] : L.plays[lo + k]); });
       rows += 1;
+      local += 1;
     }
   }
   if (rows == 0) b->active = false;
-  return (int)rows;
+  if (global_rows) *global_rows = (int)rows;
+  return (int)local;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pamrec_batcher_next(PamrecBatcher b, int batch_size, void* const* arrays) {
+  return next_impl(b, batch_size, 1, 0, arrays, nullptr, nullptr, nullptr);
+}
+
+int pamrec_batcher_next_shard(PamrecBatcher b, int batch_size, int world, int rank, void* const* arrays,
+                              float* global_labels_satisfied, float* global_users, int* global_rows) {
+  if (!global_rows) return -1;
+  return next_impl(b, batch_size, world, rank, arrays, global_labels_satisfied, global_users, global_rows);
 }
 
 }  // extern "C"

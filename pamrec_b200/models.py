@@ -23,6 +23,7 @@ from . import dist as D
 from .deeprec_utils import cal_metric, cal_weighted_metric, filter_single_class_users, load_dict
 from .engine import Engine, EMB, TABLES
 from .prefetch import Prefetcher
+from .sequential_iterator import LocalFeed
 
 __all__ = ["PAMRECModel", "SequentialBaseModel", "BaseModel", "latest_checkpoint", "initial_variables"]
 
@@ -227,6 +228,13 @@ class SequentialBaseModel(BaseModel):
     # ------------------------------------------------------------------ device steps
     def _score(self, feed_dict):
         eng = self.engine
+        if isinstance(feed_dict, LocalFeed):
+            # the iterator already dealt this rank its rows (r, r + W, ...) of a batch of global_rows rows
+            n = feed_dict.global_rows
+            db = eng.upload(feed_dict, training=False, staged=True, global_batch=n)
+            full = torch.zeros(n, dtype=torch.float32, device=eng.device)
+            full[eng.rank::eng.world] = eng.forward(db, training=False)
+            return eng.all_reduce_(full).cpu().numpy().reshape(-1, 1)
         if eng.world > 1 and self.feed_is_global:
             # data-parallel scoring: rank r scores rows r, r + W, ... of the batch; the scores are summed back into place
             local, n = D.split_feed(feed_dict, eng.world, eng.rank, grouped=False)
@@ -237,14 +245,20 @@ class SequentialBaseModel(BaseModel):
         db = eng.upload(feed_dict, training=False, staged=True)
         return eng.forward(db, training=False).cpu().numpy().reshape(-1, 1)
 
+    @staticmethod
+    def _labels_users(feed_dict):
+        if isinstance(feed_dict, LocalFeed):                     # every row of the global batch, not just this rank's
+            return feed_dict.global_labels_satisfied, feed_dict.global_users
+        return feed_dict["labels_satisfied"], feed_dict["users"]
+
     def eval(self, sess, feed_dict):
         """SBM:415-418 / BM:373-386 -> (pred [B,1], labels [B,1])."""
-        return self._score(feed_dict), np.asarray(feed_dict["labels_satisfied"], np.float32).reshape(-1, 1)
+        return self._score(feed_dict), np.asarray(self._labels_users(feed_dict)[0], np.float32).reshape(-1, 1)
 
     def eval_with_user(self, sess, feed_dict):
         """SBM:502-516 -> (users [B], pred [B,1], labels [B,1])."""
-        users = np.asarray(feed_dict["users"]).astype(np.int32)
-        return users, self._score(feed_dict), np.asarray(feed_dict["labels_satisfied"], np.float32).reshape(-1, 1)
+        labels, users = self._labels_users(feed_dict)
+        return np.asarray(users).astype(np.int32), self._score(feed_dict), np.asarray(labels, np.float32).reshape(-1, 1)
 
     def infer(self, sess, feed_dict):
         """SBM:557-560 / BM:388-399 -> [pred]."""
@@ -423,12 +437,16 @@ class PAMRECModel(SequentialBaseModel):
         self.engine.allocate(getattr(hp, "device", default_dev))
         self.engine.init_comm()
         self.engine.set_variables(initial_variables(self.engine.variable_shapes(), hp, self.seed))
+        if world > 1 and self.feed_is_global and hasattr(self.iterator, "shard"):
+            self.iterator.shard = (world, rank)      # the native batcher materialises this rank's rows only (LocalFeed)
 
     def train(self, sess, feed_dict):
         """PAM:426-453: one optimisation step.  Returns the reference's 8-tuple
         (update, extra_update_ops, loss, data_loss, regular_loss, auxiliary_data_loss, order_loss, summary)."""
         eng = self.engine
-        if eng.world > 1 and self.feed_is_global:
+        if isinstance(feed_dict, LocalFeed):
+            db = eng.upload(feed_dict, training=True, staged=True, global_batch=feed_dict.global_rows)
+        elif eng.world > 1 and self.feed_is_global:
             local, n = D.split_feed(feed_dict, eng.world, eng.rank, grouped=True)
             db = eng.upload(local, training=True, staged=True, global_batch=n)
         else:

@@ -19,7 +19,7 @@ import numpy as np
 
 from .deeprec_utils import load_dict
 
-__all__ = ["SequentialIterator", "lisan", "bar_border_list", "takatak_bar_border_list_dict"]
+__all__ = ["SequentialIterator", "LocalFeed", "lisan", "bar_border_list", "takatak_bar_border_list_dict"]
 
 # decile borders of play_time / duration (IT:24-42)
 bar_border_list = [0.00000000e+00, 4.09545455e-02, 1.28786778e-01, 3.27894289e-01,
@@ -66,6 +66,16 @@ def _ratio64(play, dur):
         return np.asarray(play, np.float64) / np.asarray(dur, np.float64)
 
 
+class LocalFeed(dict):
+    """One rank's share of a global batch (same 19 keys).  ``global_rows`` = rows of the whole batch; ``global_users`` [rows] /
+    ``global_labels_satisfied`` [rows, 1] = those two columns for every row of it (what the scoring loops return per row)."""
+    global_rows = 0
+    world = 1
+    rank = 0
+    global_users = None
+    global_labels_satisfied = None
+
+
 class SequentialIterator:
     """``SequentialIterator(hparams, graph)`` — ``graph`` is accepted and ignored (IT:56)."""
 
@@ -95,6 +105,7 @@ class SequentialIterator:
                 if iid not in self.meta_dict:
                     self.meta_dict[iid] = [int(parts[1]), float(parts[2])]
         self.train = False
+        self.shard = None                        # (world, rank) under data parallelism, see load_data_from_file
         self.col_spliter = col_spliter
         self.userdict = load_dict(hparams.user_vocab)
         self.itemdict = load_dict(hparams.item_vocab)
@@ -153,10 +164,13 @@ class SequentialIterator:
         train = os.path.basename(infile) == "train_data"
         self.train = train                       # read by parser_one_line; everything below uses the local flag, so a scoring
         native = self._native(infile, train)     # pass may start on this iterator while a training generator is suspended
+        # data parallel (set by the model under torch.distributed): materialise this rank's share only.  Negatives are drawn
+        # from the whole batch's targets, so that path keeps global feeds (the model splits them).
+        shard = self.shard if (native and batch_num_ngs == 0 and self.shard and self.shard[0] > 1) else None
         if train:
-            gen = self._train_batches_native(native) if native else self._train_batches(self._lines(infile))
+            gen = self._train_batches_native(native, shard) if native else self._train_batches(self._lines(infile))
         else:
-            gen = self._eval_batches_native(native, min_seq_length) if native else self._eval_batches(self._lines(infile), min_seq_length)
+            gen = self._eval_batches_native(native, min_seq_length, shard) if native else self._eval_batches(self._lines(infile), min_seq_length)
         if batch_num_ngs > 0:
             if not train:
                 # evaluation files carry their negatives as extra lines after each positive (QS:483,493)
@@ -313,19 +327,36 @@ class SequentialIterator:
     _FEED_DTYPES = (np.float32, np.float32, np.float32, np.float32, np.int32, np.int32, np.float32, np.int32, np.int32,
                     np.float32, np.float32, np.float32, np.float32, np.float32, np.int32, np.int32, np.float32, np.float32, np.float32)
 
-    def _native_batches(self, nat):
+    def _native_batches(self, nat, train, shard=None):
+        """shard = (world, rank): every rank draws the same global batches but materialises only the rows it trains on / scores
+        (``LocalFeed``; groups of 5 stay whole in training batches, pamrec_b200/dist.py split_feed is the same selection)."""
         T, bs = self.max_seq_length, self.batch_size
+        cap = bs
+        if shard:
+            world, rank = shard
+            cap = max(-(-(bs // 5) // world) * 5 if train else -(-bs // world), 1)
         while True:
-            arrs = [np.empty((bs, T) if i >= 7 else ((bs, 1) if i < 3 else (bs,)), dt) for i, dt in enumerate(self._FEED_DTYPES)]
+            arrs = [np.empty((cap, T) if i >= 7 else ((cap, 1) if i < 3 else (cap,)), dt) for i, dt in enumerate(self._FEED_DTYPES)]
             ptrs = (C.c_void_p * 19)(*[a.ctypes.data for a in arrs])
-            n = nat["lib"].pamrec_batcher_next(nat["handle"], bs, ptrs)
+            if shard:
+                g_lab, g_usr, g_rows = np.empty(bs, np.float32), np.empty(bs, np.float32), C.c_int(0)
+                n = nat["lib"].pamrec_batcher_next_shard(nat["handle"], bs, world, rank, ptrs, g_lab.ctypes.data, g_usr.ctypes.data,
+                                                         C.byref(g_rows))
+                total = g_rows.value
+            else:
+                total = n = nat["lib"].pamrec_batcher_next(nat["handle"], bs, ptrs)
             if n < 0:
                 raise RuntimeError(f"pamrec_batcher_next failed ({n})")
-            if n == 0:
+            if total == 0:
                 return
-            yield {k: (a if n == bs else a[:n]) for k, a in zip(FEED_KEYS, arrs)}
+            feed = {k: (a if n == cap else a[:n]) for k, a in zip(FEED_KEYS, arrs)}
+            if shard:
+                feed = LocalFeed(feed)
+                feed.global_rows, feed.world, feed.rank = total, world, rank
+                feed.global_labels_satisfied, feed.global_users = g_lab[:total].reshape(-1, 1), g_usr[:total]
+            yield feed
 
-    def _train_batches_native(self, nat):
+    def _train_batches_native(self, nat, shard=None):
         G = self.BEGIN_HISTORY_LEN_MAX
         order, begin = [], []
         for idx, sn in enumerate(nat["sat_num"]):                    # file order: the RNG call sequence of IT:538-545
@@ -339,12 +370,12 @@ class SequentialIterator:
         begin = np.asarray([p[1] for p in pairs], np.int32)
         if nat["lib"].pamrec_batcher_begin_train(nat["handle"], order.ctypes.data, begin.ctypes.data, len(order)) != 0:
             raise RuntimeError("pamrec_batcher_begin_train failed")
-        yield from self._native_batches(nat)
+        yield from self._native_batches(nat, True, shard)
 
-    def _eval_batches_native(self, nat, min_seq_length):
+    def _eval_batches_native(self, nat, min_seq_length, shard=None):
         if nat["lib"].pamrec_batcher_begin_eval(nat["handle"], int(min_seq_length)) != 0:
             raise RuntimeError("pamrec_batcher_begin_eval failed")
-        yield from self._native_batches(nat)
+        yield from self._native_batches(nat, False, shard)
 
     def _new_acc(self):
         return {"sat": [], "lplay": [], "plays": [], "users": [], "items": [], "cates": [], "durs": [], "hist": []}
