@@ -53,6 +53,21 @@ class DeviceBatch:
         return sum(t.numel() * t.element_size() for t in self.tensors.values())
 
 
+class PendingLosses:
+    """The five losses of a queued step; ``result()`` waits for their device->host copy and returns them as float32[5]."""
+
+    def __init__(self, slot):
+        self._slot, self._value = slot, None
+
+    def result(self):
+        if self._value is None:
+            self._slot["event"].synchronize()
+            self._value = self._slot["host"].numpy().copy()
+            self._slot["owner"] = None
+            self._slot = None
+        return self._value
+
+
 class Engine:
     def __init__(self, n_users, n_items, n_cates, max_seq_len, max_batch, hp=None, sparse_adam="dense_exact",
                  world_size=1, rank=0, tables=None):
@@ -375,6 +390,23 @@ class Engine:
         self._check(self.lib.pamrec_train_step(self.handle, C.byref(db.struct), self.step,
                                                C.c_void_p(losses_out.data_ptr()), self._stream()))
         return losses_out
+
+    def train_step_async(self, db):
+        """train_step whose losses travel to pinned host memory behind the step's kernels; returns a PendingLosses.  The caller
+        can stage and queue the next batch while this step runs (the pipelined form of pamrec.py:440-453's blocking sess.run)."""
+        if not hasattr(self, "_loss_ring"):
+            self._loss_ring = [dict(host=torch.empty(5, dtype=torch.float32).pin_memory(), event=torch.cuda.Event(), owner=None)
+                               for _ in range(4)]
+            self._loss_i = 0
+        slot = self._loss_ring[self._loss_i]
+        self._loss_i = (self._loss_i + 1) % len(self._loss_ring)
+        if slot["owner"] is not None:
+            slot["owner"].result()                          # an unread result four steps old: read it before its slot is reused
+        dev = self.train_step(db)
+        slot["host"].copy_(dev, non_blocking=True)
+        slot["event"].record(torch.cuda.current_stream(self.device))
+        slot["owner"] = PendingLosses(slot)
+        return slot["owner"]
 
     def profile(self, on=True):
         self._check(self.lib.pamrec_profile_enable(self.handle, int(on)))

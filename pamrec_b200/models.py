@@ -319,13 +319,18 @@ class SequentialBaseModel(BaseModel):
             self.hparams.current_epoch = epoch
             file_iterator = Prefetcher(self.iterator.load_data_from_file(train_file, min_seq_length=self.min_seq_length,
                                                                          batch_num_ngs=self.train_num_ngs))
+            pending = None                                   # the step in flight: its losses are read after the next is queued
             for batch_data_input in file_iterator:
                 if not batch_data_input:
                     continue
-                step_result = self.train(self.sess, batch_data_input)
-                self.step_train(step, step_result)
+                queued = self.train_async(self.sess, batch_data_input)
+                if pending is not None:
+                    self.step_train(step - 1, pending.result())
+                pending = queued
                 step += 1
                 if step % self.hparams.eval_step == 0:
+                    self.step_train(step - 1, pending.result())
+                    pending = None
                     valid_res = self.run_weighted_eval(valid_file, valid_num_ngs)
                     print("eval valid at epoch {0} step {1}: {2}".format(
                         epoch, step, ",".join(str(k) + ":" + str(v) for k, v in valid_res.items())))
@@ -342,6 +347,8 @@ class SequentialBaseModel(BaseModel):
                         file_iterator.close()
                         break
                     self._maybe_save(progress, "step_" + str(step))
+            if pending is not None:
+                self.step_train(step - 1, pending.result())
         print(eval_info)
         print("best step: {0}".format(self.best_step))
         return self
@@ -403,6 +410,15 @@ class SequentialBaseModel(BaseModel):
         return self
 
 
+class _PendingStep:
+    def __init__(self, pending):
+        self._pending = pending
+
+    def result(self):
+        l = self._pending.result()
+        return [None, None, float(l[0]), float(l[1]), float(l[2]), float(l[3]), float(l[4]), None]
+
+
 class PAMRECModel(SequentialBaseModel):
     """PAM:25: the playback-duration-augmented model.  The graph (embeddings, time-aware 2-block encoder, attention
     pooling, MMoE, three towers, four-term loss, per-tensor clip + Adam) is libpamrec_b200.so."""
@@ -443,6 +459,12 @@ class PAMRECModel(SequentialBaseModel):
     def train(self, sess, feed_dict):
         """PAM:426-453: one optimisation step.  Returns the reference's 8-tuple
         (update, extra_update_ops, loss, data_loss, regular_loss, auxiliary_data_loss, order_loss, summary)."""
+        return self.train_async(sess, feed_dict).result()
+
+    def train_async(self, sess, feed_dict):
+        """train() split in two: the feed is staged, copied to the device and the step queued; ``.result()`` of the returned
+        handle waits for the losses and gives train()'s 8-tuple.  Queuing step i + 1 before reading step i keeps the device busy
+        while the host packs the next feed (fit_step / batch_train below and bench.py's e2e loop run one step ahead)."""
         eng = self.engine
         if isinstance(feed_dict, LocalFeed):
             db = eng.upload(feed_dict, training=True, staged=True, global_batch=feed_dict.global_rows)
@@ -451,8 +473,7 @@ class PAMRECModel(SequentialBaseModel):
             db = eng.upload(local, training=True, staged=True, global_batch=n)
         else:
             db = eng.upload(feed_dict, training=True, staged=True)
-        losses = eng.train_step(db).cpu().numpy()
-        return [None, None, float(losses[0]), float(losses[1]), float(losses[2]), float(losses[3]), float(losses[4]), None]
+        return _PendingStep(eng.train_step_async(db))
 
     def step_train(self, step, step_result):
         """PAM:455-465."""
@@ -464,12 +485,20 @@ class PAMRECModel(SequentialBaseModel):
     def batch_train(self, file_iterator, train_sess):
         """PAM:467-503 (the reference unpacks a 7-tuple from an 8-tuple there and would raise; this version works)."""
         step, epoch_loss = 0, 0.0
+
+        def account(step, r):
+            if step % self.hparams.show_step == 0:
+                print("step {0:d} , total_loss: {1:.4f}, data_loss: {2:.4f}, auxiliary_data_loss: {3:.4f}".format(
+                    step, r[2], r[3], r[5]))
+            return r[2]
+        pending = None
         for feed in file_iterator:
             if feed:
-                r = self.train(train_sess, feed)
-                epoch_loss += r[2]
+                queued = self.train_async(train_sess, feed)
+                if pending is not None:
+                    epoch_loss += account(step, pending.result())
+                pending = queued
                 step += 1
-                if step % self.hparams.show_step == 0:
-                    print("step {0:d} , total_loss: {1:.4f}, data_loss: {2:.4f}, auxiliary_data_loss: {3:.4f}".format(
-                        step, r[2], r[3], r[5]))
+        if pending is not None:
+            epoch_loss += account(step, pending.result())
         return epoch_loss

@@ -146,3 +146,39 @@ def test_resume_from_a_checkpoint_with_optimizer_state(data_root, tmp_path, fmt)
         e.train(None, f)
     cold = e.engine.get_variables()
     assert max(float(np.abs(cold[n] - want[n]).max()) for n in want) > 1e-4
+
+
+@pytest.mark.gpu
+def test_train_async_one_step_ahead_equals_blocking_train(data_root):
+    """PAMRECModel.train_async (what fit_step and the bench's e2e loop drive) against train() on a second model with the same
+    initial values: same losses step by step (fp32 atomics reorder sums between runs, nothing more), same variables at the end."""
+    import random
+    sys.path.insert(0, os.path.join(ROOT, "compat"))
+    from reco_utils.recommender.deeprec.deeprec_utils import prepare_hparams
+    from reco_utils.recommender.deeprec.io.sequential_iterator import SequentialIterator
+    from reco_utils.recommender.deeprec.models.sequential.pamrec import PAMRECModel
+    d = os.path.join(data_root, "wechat")
+    hp = prepare_hparams(os.path.join(ROOT, "pamrec_b200", "config", "mmoe.yaml"), dataset="wechat", bucket_num=10, add_feature=False,
+                         embed_l2=1e-6, layer_l2=1e-6, discrepancy_loss_weight=0.1, learning_rate=0.001, epochs=1, is_clip_norm=1,
+                         batch_size=100, show_step=10 ** 9, save_model=False, user_vocab=os.path.join(d, "user_vocab.pkl"),
+                         item_vocab=os.path.join(d, "item_vocab.pkl"), cate_vocab=os.path.join(d, "category_vocab.pkl"), train_num_ngs=0,
+                         max_seq_length=50, pairwise_metrics=[], weighted_metrics=["wauc"], fuzhu_weight=0.5, fine_tune=False,
+                         noise_train_hist=0, noise_train_listwise=0, noise_only_predict=0, write_tfevents=False)
+    a, b = PAMRECModel(hp, SequentialIterator, seed=8), PAMRECModel(hp, SequentialIterator, seed=8)
+    random.seed(5)
+    feeds = []
+    for f in a.iterator.load_data_from_file(os.path.join(d, "train_data")):
+        feeds.append(f)
+        if len(feeds) == 9:
+            break
+    blocking = [a.train(None, f) for f in feeds]
+    handles, ahead = [], []
+    for f in feeds:                                              # up to 9 steps queued before the first result is read: the
+        handles.append(b.train_async(None, f))                   # 4-slot loss ring must hand every step its own losses
+    ahead = [h.result() for h in handles]
+    assert handles[0].result() is not None and len(ahead) == 9
+    for r0, r1 in zip(blocking, ahead):
+        assert r0[:2] == r1[:2] == [None, None]
+        assert np.allclose(r0[2:7], r1[2:7], rtol=2e-6, atol=1e-7), (r0, r1)
+    va, vb = a.engine.get_variables(), b.engine.get_variables()
+    assert max(float(np.abs(va[n] - vb[n]).max()) for n in va) <= 1e-5

@@ -48,6 +48,10 @@ class StubEngine(E.Engine):
         base = 1.0 / self.step
         return torch.tensor([4 * base, base, base, base, base])
 
+    def train_step_async(self, db):
+        losses = self.train_step(db).numpy()
+        return types.SimpleNamespace(result=lambda: losses)
+
     def forward(self, db, training=False, want_pred=True):
         self.calls["forward"] += 1
         f = db.feed

@@ -34,10 +34,15 @@ res = []
 for epoch in range(3):
     t0 = time.perf_counter()
     n = steps = 0
+    pending = None
     for feed in Prefetcher(model.iterator.load_data_from_file(train, min_seq_length=1, batch_num_ngs=0)):
-        r = model.train(None, feed)
+        queued = model.train_async(None, feed)                   # one step ahead, like fit_step
+        if pending is not None:
+            r = pending.result()
+        pending = queued
         n += feed["items"].shape[0]
         steps += 1
+    r = pending.result()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     res.append(dict(epoch=epoch, samples=n, steps=steps, seconds=dt, samples_per_s=n / dt, ms_per_step=1e3 * dt / steps, loss=r[2]))
