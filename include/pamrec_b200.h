@@ -51,6 +51,10 @@ enum { PAMREC_TABLES_LOCAL = 0,     /* whole tables on this GPU, direct gather (
        PAMREC_TABLES_SHARDED = 1 }; /* row r lives on rank r % world_size at local row r / world_size; rows
                                        and row gradients travel by all-to-all (works with world_size 1 too) */
 
+/* hparams.loss */
+enum { PAMREC_LOSS_XENT = 0,        /* "cross_entropy_loss" (config/mmoe.yaml)                                  */
+       PAMREC_LOSS_SOFTMAX = 1 };   /* "softmax" over groups of train_num_ngs + 1 rows (base_model.py:222-242)  */
+
 typedef struct PamrecConfig {
   int32_t n_users, n_items, n_cates; /* vocabulary sizes = table rows (sequential_base_model.py:565-567) */
   int32_t max_seq_len;               /* T, hparams.max_seq_length                                       */
@@ -69,6 +73,13 @@ typedef struct PamrecConfig {
    * needs pamrec_comm_init and table_mode = PAMREC_TABLES_SHARDED.                        */
   int32_t world_size, rank;
   int32_t table_mode;                /* PAMREC_TABLES_*                                                 */
+  /* hparams.loss (base_model.py:195-242, pamrec.py:81-106): PAMREC_LOSS_XENT = "cross_entropy_loss" (mean sigmoid cross
+   * entropy, the quick start); PAMREC_LOSS_SOFTMAX = "softmax": -group * mean(log(where(label == 1, softmax over groups of
+   * `softmax_group` = train_num_ngs + 1 consecutive logits, 1))) for both the satisfied and the play head.  The order loss
+   * (groups of 5) and the L2 term are the same in both.  Batches must then be multiples of softmax_group; with
+   * world_size > 1 softmax_group must divide 5 (ranks hold whole listwise groups of 5).                                   */
+  int32_t loss_kind;
+  int32_t softmax_group;             /* used by PAMREC_LOSS_SOFTMAX only; 0 is read as 1                */
 } PamrecConfig;
 
 /* One batch, device pointers (layouts of io/sequential_iterator.py:1111-1135). */

@@ -394,14 +394,27 @@ def approx_ndcg_loss(labels, scores, alpha=10.0):
     return (losses * nonzero).sum() / den
 
 
+def softmax_pos_loss(logits, labels, group):
+    """hparams.loss == "softmax" (BM:222-242 for the satisfied head, PAM:97-105 for the play head):
+    -group * mean(log(where(labels == 1, softmax(logits reshaped [-1, group]), 1)))."""
+    x, y = logits.reshape(-1, group), labels.reshape(-1, group)
+    sm = torch.softmax(x, dim=-1)
+    pos = torch.where(y == 1, sm, torch.ones_like(sm))
+    return -group * torch.log(pos).mean()
+
+
 def compute_losses(ctx, batch, rows, hp):
     p, dtype = ctx.p, ctx.dtype
     logits = ctx.t["logits"]
     y_sat = torch.as_tensor(batch["labels_satisfied"]).to(dtype).reshape(-1)
     y_play = torch.as_tensor(batch["labels_play"]).to(dtype).reshape(-1)
     plays = torch.as_tensor(batch["plays"]).to(dtype).reshape(-1, GROUP)
-    data_loss = _sigmoid_xent(logits[:, 0], y_sat).mean()                                 # BM:196-205
-    aux = hp["fuzhu_weight"] * _sigmoid_xent(logits[:, 1], y_play).mean()                 # PAM:82-88,106
+    if hp.get("loss", "cross_entropy_loss") == "softmax":
+        data_loss = softmax_pos_loss(logits[:, 0], y_sat, int(hp["softmax_group"]))         # BM:222-242
+        aux = hp["fuzhu_weight"] * softmax_pos_loss(logits[:, 1], y_play, int(hp["softmax_group"]))   # PAM:97-106
+    else:
+        data_loss = _sigmoid_xent(logits[:, 0], y_sat).mean()                             # BM:196-205
+        aux = hp["fuzhu_weight"] * _sigmoid_xent(logits[:, 1], y_play).mean()             # PAM:82-88,106
     order = hp["discrepancy_loss_weight"] * approx_ndcg_loss(plays, torch.sigmoid(logits[:, 2]).reshape(-1, GROUP))  # PAM:70-79
     reg = torch.zeros((), dtype=dtype)
     for k in ("inv_item", "inv_cate", "inv_ulong", "inv_ushort"):                         # SBM:651,664  PAM:178,182

@@ -11,6 +11,7 @@ F32, I32, F64, U8 = 0, 1, 2, 3
 SEG_L2, SEG_POS, SEG_DEAD = 1, 2, 4
 ADAM_DENSE_EXACT, ADAM_LAZY = 0, 1
 TABLES_LOCAL, TABLES_SHARDED = 0, 1
+LOSS_XENT, LOSS_SOFTMAX = 0, 1
 COMM_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 GROUP = 5
@@ -24,6 +25,7 @@ class PamrecConfig(C.Structure):
         ("embed_l2", C.c_float), ("layer_l2", C.c_float), ("max_grad_norm", C.c_float), ("is_clip_norm", C.c_int32),
         ("fuzhu_weight", C.c_float), ("order_weight", C.c_float), ("sparse_adam_mode", C.c_int32),
         ("world_size", C.c_int32), ("rank", C.c_int32), ("table_mode", C.c_int32),
+        ("loss_kind", C.c_int32), ("softmax_group", C.c_int32),
     ]
 
 

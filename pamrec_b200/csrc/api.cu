@@ -131,6 +131,11 @@ int pamrec_create(const PamrecConfig* cfg, PamrecHandle* out) {
   if (world > 64 || cfg->rank < 0 || cfg->rank >= world) return -5;
   if (cfg->table_mode != PAMREC_TABLES_LOCAL && cfg->table_mode != PAMREC_TABLES_SHARDED) return -6;
   if (world > 1 && cfg->table_mode != PAMREC_TABLES_SHARDED) return -6;      // multi-GPU = row-sharded tables
+  if (cfg->loss_kind != PAMREC_LOSS_XENT && cfg->loss_kind != PAMREC_LOSS_SOFTMAX) return -8;
+  if (cfg->loss_kind == PAMREC_LOSS_SOFTMAX) {
+    const int g = cfg->softmax_group < 1 ? 1 : cfg->softmax_group;
+    if (g > 1024 || (world > 1 && PAMREC_GROUP % g != 0)) return -8;
+  }
   {
     // sharded keys are owner * rows_per_shard + local row: must fit an int32
     int64_t big = cfg->n_items > cfg->n_users ? cfg->n_items : cfg->n_users;
@@ -140,6 +145,7 @@ int pamrec_create(const PamrecConfig* cfg, PamrecHandle* out) {
   PamrecHandle h = new PamrecHandle_();
   h->cfg = *cfg;
   h->cfg.world_size = world;
+  if (h->cfg.softmax_group < 1) h->cfg.softmax_group = 1;
   h->L.build(h->cfg);
   const int n_seg = (int)h->L.dense.size();
   h->h_seg_id.assign((size_t)h->L.dense_numel, 0);
@@ -289,6 +295,8 @@ static int check_batch(PamrecHandle h, const PamrecBatch* b, bool training) {
   if (b->batch < 1 || b->batch > h->cfg.max_batch) return fail(h, "batch %d outside [1, %d]", b->batch, h->cfg.max_batch);
   if (training && b->batch % PAMREC_GROUP != 0)
     return fail(h, "training batch %d is not a multiple of %d (pamrec.py:73-75)", b->batch, PAMREC_GROUP);
+  if (training && h->cfg.loss_kind == PAMREC_LOSS_SOFTMAX && b->batch % h->cfg.softmax_group != 0)
+    return fail(h, "training batch %d is not a multiple of the softmax group %d (base_model.py:224-225)", b->batch, h->cfg.softmax_group);
   if (!b->item_history || !b->item_cate_history || !b->item_loop_times_history || !b->mask || !b->items || !b->cates)
     return fail(h, "null batch field");
   if (training && (!b->users || !b->labels_satisfied || !b->labels_play || !b->plays)) return fail(h, "null label field");
@@ -660,7 +668,8 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   cudaMemsetAsync(h->wd("loss_acc"), 0, 8 * sizeof(double), st);
   cudaMemsetAsync(h->wd("sp_normsq"), 0, 8 * sizeof(double), st);
   launch_loss(h->wf("logits"), b->labels_satisfied, b->labels_play, b->plays, h->wf("d_logits"), h->wd("loss_acc"), B, Bg,
-              W > 1 ? h->wd("dp.scalars") : nullptr, h->cfg.fuzhu_weight, h->cfg.order_weight, st); nl += 1;
+              W > 1 ? h->wd("dp.scalars") : nullptr, h->cfg.fuzhu_weight, h->cfg.order_weight,
+              h->cfg.loss_kind == PAMREC_LOSS_SOFTMAX ? h->cfg.softmax_group : 0, st); nl += 1;
   // Batch-norm backward is folded into the dense kernels (common.cuh: BnGrad / BnGradOut): the kernel that produces a
   // gradient buffer also accumulates the two column sums of its layer's BN, the consumers turn dA into dz while loading.
   // Buffers produced by the mixing / pooling kernels get their sums from k_bn_bwd_stats.  Data parallel: sums over ranks.

@@ -71,7 +71,7 @@ void launch_combine_bwd(const float* ZE1, const float* ZG1, const BnSet& e1, con
 // loss_acc (double[8]): [0] data [1] aux [2] order (all already weighted / averaged)
 void launch_loss(const float* logits, const float* y_sat, const float* y_play, const float* plays, float* d_logits,
                  double* loss_acc, int B, int B_global, const double* n_valid_global, float fuzhu_w, float order_w,
-                 cudaStream_t st);
+                 int softmax_group, cudaStream_t st);   // softmax_group = 0: sigmoid cross entropy heads
 void launch_sigmoid_col0(const float* logits, float* pred, int B, cudaStream_t st);
 
 // ---- kernels_optim.cu

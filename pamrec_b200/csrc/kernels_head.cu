@@ -684,7 +684,7 @@ __device__ double block_sum_d(double v, double* sh) {
 __global__ void __launch_bounds__(1024)
 k_loss(const float* __restrict__ logits, const float* __restrict__ y_sat, const float* __restrict__ y_play,
        const float* __restrict__ plays, float* __restrict__ d_logits, double* __restrict__ loss_acc, int B, int B_global,
-       const double* __restrict__ n_valid_global, float fuzhu_w, float order_w) {
+       const double* __restrict__ n_valid_global, float fuzhu_w, float order_w, int sm_group) {
   __shared__ double sh[32];
   const int tid = threadIdx.x;
   const int G = B / PAMREC_GROUP;
@@ -699,13 +699,37 @@ k_loss(const float* __restrict__ logits, const float* __restrict__ y_sat, const 
   const double nval = n_valid_global ? *n_valid_global : nval_local;   // data parallel: count over all ranks
   const float inv_b = 1.0f / (float)B_global;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-  for (int b = tid; b < B; b += blockDim.x) {
-    float x0 = logits[3 * b], x1 = logits[3 * b + 1];
-    float y0 = y_sat[b], y1 = y_play[b];
-    a0 += (double)xent_(x0, y0);
-    a1 += (double)xent_(x1, y1);
-    d_logits[3 * b] = (sigmoidf_(x0) - y0) * inv_b;
-    d_logits[3 * b + 1] = fuzhu_w * (sigmoidf_(x1) - y1) * inv_b;
+  if (sm_group == 0) {
+    for (int b = tid; b < B; b += blockDim.x) {
+      float x0 = logits[3 * b], x1 = logits[3 * b + 1];
+      float y0 = y_sat[b], y1 = y_play[b];
+      a0 += (double)xent_(x0, y0);
+      a1 += (double)xent_(x1, y1);
+      d_logits[3 * b] = (sigmoidf_(x0) - y0) * inv_b;
+      d_logits[3 * b + 1] = fuzhu_w * (sigmoidf_(x1) - y1) * inv_b;
+    }
+  } else {
+    // hparams.loss == "softmax" (base_model.py:222-242, pamrec.py:97-105):  -group * mean(log(where(y == 1, softmax, 1))) over all
+    // B elements = -(group / B) * sum over positives of log softmax;  d/dx_j = (group / B) * (n_pos * softmax_j - [y_j == 1])
+    const float scale = (float)sm_group * inv_b;
+    for (int u = tid; u < 2 * (B / sm_group); u += blockDim.x) {
+      const int head = u & 1, r0 = (u >> 1) * sm_group;
+      const float* y = head ? y_play : y_sat;
+      float mx = -INFINITY;
+      for (int i = 0; i < sm_group; ++i) mx = fmaxf(mx, logits[3 * (r0 + i) + head]);
+      float se = 0.f;
+      int n_pos = 0;
+      for (int i = 0; i < sm_group; ++i) { se += expf(logits[3 * (r0 + i) + head] - mx); n_pos += y[r0 + i] == 1.0f; }
+      const float lse = mx + logf(se), w = head ? fuzhu_w : 1.0f;
+      double acc = 0.0;
+      for (int i = 0; i < sm_group; ++i) {
+        const float x = logits[3 * (r0 + i) + head];
+        const bool pos = y[r0 + i] == 1.0f;
+        if (pos) acc += (double)(lse - x);
+        d_logits[3 * (r0 + i) + head] = w * scale * ((float)n_pos * expf(x - lse) - (pos ? 1.0f : 0.f));
+      }
+      if (head) a1 += acc * (double)sm_group; else a0 += acc * (double)sm_group;
+    }
   }
   const float alpha = 10.0f;
   for (int g = tid; g < G; g += blockDim.x) {
@@ -779,8 +803,9 @@ k_loss(const float* __restrict__ logits, const float* __restrict__ y_sat, const 
 }
 void launch_loss(const float* logits, const float* y_sat, const float* y_play, const float* plays, float* d_logits,
                  double* loss_acc, int B, int B_global, const double* n_valid_global, float fuzhu_w, float order_w,
-                 cudaStream_t st) { PAMREC_PROF("loss", 1, st);
-  k_loss<<<1, 1024, 0, st>>>(logits, y_sat, y_play, plays, d_logits, loss_acc, B, B_global, n_valid_global, fuzhu_w, order_w);
+                 int softmax_group, cudaStream_t st) { PAMREC_PROF("loss", 1, st);
+  k_loss<<<1, 1024, 0, st>>>(logits, y_sat, y_play, plays, d_logits, loss_acc, B, B_global, n_valid_global, fuzhu_w, order_w,
+                             softmax_group);
 }
 
 __global__ void k_sigmoid_col0(const float* __restrict__ logits, float* __restrict__ pred, int B) {

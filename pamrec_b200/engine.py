@@ -27,7 +27,8 @@ _TORCH_DTYPE = {L.F32: torch.float32, L.I32: torch.int32, L.F64: torch.float64, 
 _ESIZE = {L.F32: 4, L.I32: 4, L.F64: 8, L.U8: 1}
 
 DEFAULT_HP = dict(learning_rate=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8, embed_l2=1e-6, layer_l2=1e-6,
-                  max_grad_norm=2.0, is_clip_norm=1, fuzhu_weight=0.5, discrepancy_loss_weight=0.1)
+                  max_grad_norm=2.0, is_clip_norm=1, fuzhu_weight=0.5, discrepancy_loss_weight=0.1,
+                  loss="cross_entropy_loss", softmax_group=1)      # hparams.loss / train_num_ngs + 1 (base_model.py:195-242)
 
 BATCH_FIELDS = (  # name, dtype, per-row shape suffix, needed for scoring
     ("item_history", np.int32, True), ("item_cate_history", np.int32, True), ("item_loop_times_history", np.float32, True),
@@ -92,7 +93,8 @@ class Engine:
             embed_l2=h["embed_l2"], layer_l2=h["layer_l2"], max_grad_norm=h["max_grad_norm"],
             is_clip_norm=int(h["is_clip_norm"]), fuzhu_weight=h["fuzhu_weight"],
             order_weight=h["discrepancy_loss_weight"], sparse_adam_mode=mode, world_size=world_size, rank=rank,
-            table_mode=L.TABLES_SHARDED if tables == "sharded" else L.TABLES_LOCAL)
+            table_mode=L.TABLES_SHARDED if tables == "sharded" else L.TABLES_LOCAL,
+            loss_kind={"cross_entropy_loss": L.LOSS_XENT, "softmax": L.LOSS_SOFTMAX}[h["loss"]], softmax_group=int(h["softmax_group"]))
         self.handle = C.c_void_p()
         rc = self.lib.pamrec_create(C.byref(self.cfg), C.byref(self.handle))
         if rc != 0:

@@ -176,7 +176,8 @@ class BaseModel:
             if not cond:
                 raise ValueError("pamrec_b200: unsupported configuration: " + what)
         need(hp.method == "classification", "method must be classification (BM:93-113)")
-        need(hp.loss == "cross_entropy_loss", "loss must be cross_entropy_loss")
+        need(hp.loss in ("cross_entropy_loss", "softmax"), "loss must be cross_entropy_loss or softmax (BM:195-242; square_loss and "
+                                                            "log_loss have no auxiliary branch that PAMRec defines consistently)")
         need(hp.optimizer == "adam", "optimizer must be adam (BM:270-271)")
         need(hp.item_embedding_dim == 16 and hp.cate_embedding_dim == 4 and hp.user_embedding_dim == 20,
              "embedding dims must be 16 / 4 / 20 (config/mmoe.yaml:22-24)")
@@ -431,7 +432,8 @@ class PAMRECModel(SequentialBaseModel):
         engine_hp = dict(
             learning_rate=float(hp.learning_rate), embed_l2=float(hp.embed_l2), layer_l2=float(hp.layer_l2),
             max_grad_norm=float(hp.max_grad_norm), is_clip_norm=int(bool(hp.is_clip_norm)),
-            fuzhu_weight=float(hp.fuzhu_weight), discrepancy_loss_weight=float(hp.discrepancy_loss_weight))
+            fuzhu_weight=float(hp.fuzhu_weight), discrepancy_loss_weight=float(hp.discrepancy_loss_weight),
+            loss=hp.loss, softmax_group=int(hp.train_num_ngs or 0) + 1)
         mode = getattr(hp, "sparse_adam", "dense_exact")
         # data parallel (no reference counterpart): one process per GPU under torchrun.  hparams.batch_size stays the GLOBAL
         # batch when feeds come from the iterator (every rank reads the same file and trains on its groups of each batch);

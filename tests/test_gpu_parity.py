@@ -194,6 +194,47 @@ def test_multi_step_losses_and_eval():
     eng.close()
 
 
+@pytest.mark.parametrize("group", [5, 1, 2])
+def test_softmax_loss_branch(group):
+    """hparams.loss == "softmax" (BM:222-242, PAM:97-105) with groups of train_num_ngs + 1 rows: the two softmax terms, their
+    gradient at the logits, every dense gradient and three steps of losses against the oracle."""
+    nu, ni, nc, T, B = 120, 900, 25, 30, 40
+    hp = dict(loss="softmax", softmax_group=group)
+    om, eng = _setup(nu, ni, nc, T, B, seed=21, hp=hp)
+    batch = O.make_batch(9, B, T, nu, ni, nc)
+    if group == 5:                                                   # the in-batch sampler's layout: one positive, four negatives
+        for k in ("labels_satisfied", "labels_play"):
+            batch[k] = np.tile(np.asarray([1, 0, 0, 0, 0], np.float32), B // 5).reshape(batch[k].shape)
+    ref = om.train_step(batch, apply=False, keep=("logits",))
+    db = eng.upload(batch)
+    eng.forward(db, training=True, want_pred=False)
+    eng.backward(db)
+    torch.cuda.synchronize()
+    _close("d_logits", eng.ws("d_logits", B).cpu().numpy(), ref["t"]["logits"].grad.numpy(), rtol=2e-5)
+    from pamrec_b200 import _lib as L
+    gmax = max(float(ref["grads"][n].abs().max()) for n in eng.info[L.POOL_DENSE])
+    for name, d in eng.info[L.POOL_DENSE].items():
+        g = eng.dense(name, "dense_grad").cpu().numpy().astype(np.float64)
+        if d["flags"] & L.SEG_L2:
+            g = g + om.hp["layer_l2"] * eng.dense(name).cpu().numpy().astype(np.float64)
+        gr = ref["grads"][name].numpy().reshape(g.shape)
+        assert np.abs(g - gr).max() <= 1e-4 * np.abs(gr).max() + 2e-6 * gmax, name
+    eng2 = _setup(nu, ni, nc, T, B, seed=21, hp=hp)[1]
+    for step in range(3):
+        b = O.make_batch(30 + step, B, T, nu, ni, nc)
+        want = om.train_step(b)["losses"]
+        got = eng2.train_step(eng2.upload(b)).cpu().numpy()
+        for i, k in enumerate(("loss", "data_loss", "regular_loss", "auxiliary_data_loss", "order_loss")):
+            assert abs(got[i] - want[k]) <= 1e-4 * max(abs(want[k]), 1e-3), (step, k, got[i], want[k])
+    # a batch that is not a multiple of the group is refused like the reference's reshape would
+    if group == 2:
+        from pamrec_b200.engine import PamrecError
+        odd = O.make_batch(1, 15, T, nu, ni, nc)
+        with pytest.raises(PamrecError, match="softmax group"):
+            eng2.train_step(eng2.upload(odd))
+    eng.close(); eng2.close()
+
+
 def test_lazy_mode_touches_only_looked_up_rows():
     nu, ni, nc, T, B = 100, 4000, 30, 20, 25
     om, eng = _setup(nu, ni, nc, T, B, seed=5, sparse_adam="lazy")

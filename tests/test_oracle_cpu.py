@@ -135,3 +135,25 @@ def test_gradients_match_finite_differences():
     om.params[name] = base
     fd = (vals[0] - vals[1]) / (2 * h)
     assert abs(fd - float(ref["grads"][name][idx])) <= 1e-5 * max(abs(fd), 1e-6)
+
+
+def test_softmax_loss_hand_values():
+    """hparams.loss == "softmax" (BM:222-242): -group * mean(log(where(y == 1, softmax, 1)))."""
+    g = 5
+    x = torch.zeros(10, dtype=torch.float64)
+    y = torch.tensor([1.0, 0, 0, 0, 0, 0, 0, 1.0, 0, 0], dtype=torch.float64)
+    assert abs(float(O.softmax_pos_loss(x, y, g)) - math.log(5)) < 1e-12          # one positive per group, uniform softmax
+    y2 = torch.tensor([1.0, 1.0, 0, 0, 0, 0, 0, 0, 0, 0], dtype=torch.float64)    # two positives in one group, none in the other
+    assert abs(float(O.softmax_pos_loss(x, y2, g)) - math.log(5)) < 1e-12         # -5 * (2 * -ln 5) / 10
+    x3 = torch.tensor([2.0, 0.0, 0.0, 0.0, 0.0], dtype=torch.float64)
+    y3 = torch.tensor([1.0, 0, 0, 0, 0], dtype=torch.float64)
+    want = -(2.0 - math.log(math.exp(2.0) + 4.0))
+    assert abs(float(O.softmax_pos_loss(x3, y3, g)) - want) < 1e-12
+    assert float(O.softmax_pos_loss(x3, torch.zeros(5, dtype=torch.float64), g)) == 0.0
+    # through the model: only the two softmax terms differ from the cross-entropy configuration
+    om_x = O.OracleModel(40, 200, 12, 10, seed=1)
+    om_s = O.OracleModel(40, 200, 12, 10, seed=1, hp=dict(loss="softmax", softmax_group=5))
+    batch = O.make_batch(3, 20, 10, 40, 200, 12)
+    lx, ls = om_x.train_step(batch, apply=False)["losses"], om_s.train_step(batch, apply=False)["losses"]
+    assert lx["order_loss"] == ls["order_loss"] and lx["regular_loss"] == ls["regular_loss"]
+    assert lx["data_loss"] != ls["data_loss"] and lx["auxiliary_data_loss"] != ls["auxiliary_data_loss"]
