@@ -94,10 +94,12 @@ def _worst_difference(va, vb):
     """Largest |difference| over the variables two runs of the same steps can be compared on, with the variable's name.
     A bias in front of a batch norm (the `b_nn_layer*` of every BN MLP) has an exactly-zero data gradient: what reaches Adam is
     the fp32 rounding noise of a sum whose order the atomics change from run to run, and Adam normalises it to steps of
-    +-learning_rate - so those biases random-walk differently in ANY two runs and are left out."""
+    +-learning_rate - so those biases random-walk differently in ANY two runs and are left out, and with
+    them the BN moving means, which track the batch mean of `h W + b` and so inherit the walk (moving variances do not)."""
     worst, where = 0.0, None
     for n in va:
-        if n.rsplit("/", 1)[-1].startswith("b_nn_layer"):
+        leaf = n.rsplit("/", 1)[-1]
+        if leaf.startswith("b_nn_layer") or leaf == "moving_mean":
             continue
         d = float(np.abs(va[n] - vb[n]).max())
         if d > worst:
