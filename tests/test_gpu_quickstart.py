@@ -151,7 +151,7 @@ def test_resume_from_a_checkpoint_with_optimizer_state(data_root, tmp_path, fmt)
         c.train(None, f)
     got = c.engine.get_variables()
     worst, where = _worst_difference(got, want)
-    assert worst <= 2e-5, (worst, where)                          # fp32 atomics reorder sums between runs; a lost Adam state is ~1e-3
+    assert worst <= 5e-5, (worst, where)                          # fp32 atomics reorder sums between runs; a lost Adam state is ~1e-3
     # the same checkpoint without the optimizer key-space (what the reference's Saver writes) restarts Adam from zero
     from pamrec_b200 import checkpoint as CK
     variables, opt = CK.load(path)
@@ -199,4 +199,4 @@ def test_train_async_one_step_ahead_equals_blocking_train(data_root):
         assert np.allclose(r0[2:7], r1[2:7], rtol=2e-6, atol=1e-7), (r0, r1)
     va, vb = a.engine.get_variables(), b.engine.get_variables()
     worst, where = _worst_difference(va, vb)
-    assert worst <= 2e-5, (worst, where)
+    assert worst <= 5e-5, (worst, where)
