@@ -139,6 +139,33 @@ def hit_score(y_true, y_score, k=10):
     return sum(1 for i in top if i in positives) / len(top)
 
 
+_AUC_CACHE = {}
+
+
+def _group_auc(y_true, y_score):
+    """sklearn.metrics.roc_auc_score for the small groups of group_auc / wauc (DU:808-814, DU:873-881), memoised.
+
+    roc_auc_score sorts by score (stable, descending), merges equal scores into one threshold and works on the cumulative
+    positive / negative COUNTS from there on, so its float64 result is a function of the labels in score order and of where
+    the ties are - nothing else.  Thousands of two-to-ten-row user groups share a handful of such patterns; each pattern is
+    sent to sklearn once and its exact value reused (the per-call overhead of sklearn's input validation, ~2 ms, is what
+    made the reference's user-weighted metrics the slowest part of an evaluation pass)."""
+    y_true = np.asarray(y_true, dtype=np.float64)
+    y_score = np.asarray(y_score, dtype=np.float64)
+    n = y_true.shape[0]
+    if y_true.ndim != 1 or y_score.shape != y_true.shape or n > 128 or not np.isfinite(y_score).all():
+        return roc_auc_score(y_true, y_score)
+    order = np.argsort(y_score, kind="mergesort")[::-1]
+    s = y_score[order]
+    key = (y_true[order].tobytes(), (s[1:] != s[:-1]).tobytes())
+    val = _AUC_CACHE.get(key)
+    if val is None:
+        val = roc_auc_score(y_true, y_score)               # raises for a single-class group exactly like the reference
+        if len(_AUC_CACHE) < 200_000:
+            _AUC_CACHE[key] = val
+    return val
+
+
 def _ks(metric, default):
     parts = metric.split("@")
     return [int(t) for t in parts[1].split(";")] if len(parts) > 1 else default
@@ -170,7 +197,7 @@ def cal_metric(labels, preds, metrics):
             for k in _ks(metric, [1, 2]):
                 res["hit@{0}".format(k)] = round(np.mean([hit_score(l, p, k) for l, p in zip(labels, preds)]), 4)
         elif metric == "group_auc":
-            res["group_auc"] = round(np.mean([roc_auc_score(l, p) for l, p in zip(labels, preds)]), 4)
+            res["group_auc"] = round(np.mean([_group_auc(l, p) for l, p in zip(labels, preds)]), 4)
         else:
             raise ValueError("not define this metric {0}".format(metric))
     return res
@@ -206,7 +233,7 @@ def cal_weighted_metric(users, preds, labels, metrics):
 
     for metric in metrics:
         if metric == "wauc":
-            res["wauc"] = round(wsum(lambda l, p: roc_auc_score(l, p)), 4)
+            res["wauc"] = round(wsum(_group_auc), 4)
         elif metric == "wmrr":
             res["wmrr"] = round(wsum(mrr_score), 4)
         elif metric.startswith("wmrr"):

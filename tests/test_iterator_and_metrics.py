@@ -261,3 +261,42 @@ def test_in_batch_negative_sampler_follows_the_disabled_reference_block():
     # like the batch of fewer than 5 rows the block itself returns None for
     lone = {k: v[:5] for k, v in b0.items()}
     assert it._with_negatives(lone, 4) == {} and it._with_negatives({k: v[:3] for k, v in b0.items()}, 4) == {}
+
+
+def test_memoised_group_auc_is_sklearn_bit_for_bit():
+    """_group_auc sends every (labels in score order, tie structure) pattern to sklearn once: same float64 as a direct call for
+    every group, ties and unsorted input included; single-class groups raise what sklearn raises."""
+    from sklearn.metrics import roc_auc_score
+    rng = np.random.default_rng(4)
+    DU._AUC_CACHE.clear()
+    n_groups = 0
+    for _ in range(3000):
+        n = int(rng.integers(2, 12))
+        y = rng.integers(0, 2, n).astype(np.float64)
+        if y.min() == y.max():
+            y[0] = 1 - y[0]
+        p = np.round(rng.random(n), int(rng.integers(1, 4)))          # coarse rounding -> many ties
+        want = roc_auc_score(y, p)
+        assert DU._group_auc(y, p) == want
+        assert DU._group_auc(y.tolist(), (p * 0.5 + 0.25).tolist()) == want      # same pattern, other scores: served from the cache
+        n_groups += 1
+    assert 0 < len(DU._AUC_CACHE) < n_groups
+    def outcome(f):                                                  # sklearn < 1.5 raises for one class, later versions warn + nan
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                return repr(f(np.asarray([1.0, 1.0]), np.asarray([0.2, 0.3])))
+            except ValueError as e:
+                return "ValueError " + str(e)
+    assert outcome(DU._group_auc) == outcome(roc_auc_score) == outcome(DU._group_auc)
+    big_y, big_p = rng.integers(0, 2, 500).astype(np.float64), rng.random(500)
+    assert DU._group_auc(big_y, big_p) == roc_auc_score(big_y, big_p)            # large inputs bypass the cache
+    # and through the public functions
+    users = np.repeat(np.arange(400), 3)
+    labels = np.tile([1.0, 0.0, 0.0], 400)
+    preds = np.round(rng.random(1200), 2)
+    direct = sum(3 / 1200 * roc_auc_score(labels[users == u], preds[users == u]) for u in range(400))
+    assert DU.cal_weighted_metric(users, preds, labels, ["wauc"])["wauc"] == round(direct, 4)
+    groups_l, groups_p = list(labels.reshape(-1, 3)), list(preds.reshape(-1, 3))
+    assert DU.cal_metric(groups_l, groups_p, ["group_auc"])["group_auc"] == round(np.mean([roc_auc_score(l, p) for l, p in zip(groups_l, groups_p)]), 4)
