@@ -80,3 +80,60 @@ def test_no_cpu_fallback(lib_built):
     eng = Engine(n_users=10, n_items=10, n_cates=10, max_seq_len=10, max_batch=5)
     with pytest.raises(PamrecError):
         eng.allocate()
+
+
+def test_config_validation_and_calls_before_bind(lib_built):
+    """Error behaviour of the C ABI that needs no device: return codes of pamrec_create for every rejected field, the message of
+    a device call on an unbound handle, and the host-only entry points handed nonsense."""
+    import ctypes as C
+    import numpy as np
+    from pamrec_b200 import _lib as L
+    lib = L.load()
+    base = dict(n_users=10, n_items=20, n_cates=5, max_seq_len=8, max_batch=10, learning_rate=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8,
+                max_grad_norm=2.0, is_clip_norm=1, fuzhu_weight=0.5, order_weight=0.1, world_size=1, rank=0)
+
+    def create(**kw):
+        cfg = L.PamrecConfig(**{**base, **kw})
+        h = C.c_void_p()
+        rc = lib.pamrec_create(C.byref(cfg), C.byref(h))
+        if rc == 0:
+            lib.pamrec_destroy(h)
+        else:
+            assert not h.value                                    # no handle on failure
+        return rc
+    assert create() == 0
+    assert create(n_cates=0) == -2 and create(max_seq_len=257) == -3 and create(max_batch=0) == -4
+    assert create(world_size=2, rank=2, table_mode=L.TABLES_SHARDED) == -5 and create(world_size=65, table_mode=L.TABLES_SHARDED) == -5
+    assert create(table_mode=7) == -6 and create(world_size=2, table_mode=L.TABLES_LOCAL) == -6
+    assert create(loss_kind=2) == -8
+    assert create(loss_kind=L.LOSS_SOFTMAX, softmax_group=3) == 0                                   # one GPU: any group
+    assert create(loss_kind=L.LOSS_SOFTMAX, softmax_group=3, world_size=2, table_mode=L.TABLES_SHARDED) == -8   # ranks hold groups of 5
+    assert create(loss_kind=L.LOSS_SOFTMAX, softmax_group=5, world_size=2, table_mode=L.TABLES_SHARDED) == 0
+    assert lib.pamrec_create(None, None) == -1
+    # a device call before pamrec_bind: error code + message, no crash
+    cfg, h = L.PamrecConfig(**base), C.c_void_p()
+    assert lib.pamrec_create(C.byref(cfg), C.byref(h)) == 0
+    batch = L.PamrecBatch(batch=5)
+    assert lib.pamrec_train_step(h, C.byref(batch), 1, None, None) != 0
+    assert b"pamrec_bind" in lib.pamrec_last_error(h)
+    info = L.PamrecTensorInfo()
+    assert lib.pamrec_tensor_info(h, L.POOL_DENSE, 10 ** 6, C.byref(info)) != 0
+    lib.pamrec_destroy(h)
+    # batcher / tokenizer misuse
+    off = np.zeros(1, np.int64)
+    lines = L.PamrecLines(n_lines=0, offsets=off.ctypes.data)
+    borders = np.asarray([0.0, 1.0])
+    bh = C.c_void_p()
+    assert lib.pamrec_batcher_create(C.byref(lines), borders.ctypes.data, 2, 0, C.byref(bh)) == -1          # max_seq_len < 1
+    assert lib.pamrec_batcher_create(C.byref(lines), borders.ctypes.data, 2, 8, C.byref(bh)) == 0
+    ptrs = (C.c_void_p * 19)()
+    assert lib.pamrec_batcher_next(bh, 10, ptrs) == -1                                                       # no pass begun
+    assert lib.pamrec_batcher_begin_eval(bh, 1) == -1                                                        # a train file has no label columns
+    assert lib.pamrec_batcher_begin_train(bh, None, None, 0) == 0
+    assert lib.pamrec_batcher_next(bh, 7, ptrs) == -3                                                        # not a multiple of 5
+    n = C.c_int(-1)
+    assert lib.pamrec_batcher_next_shard(bh, 10, 2, 2, ptrs, None, None, C.byref(n)) == -1                  # rank outside the world
+    assert lib.pamrec_batcher_next_shard(bh, 10, 2, 1, ptrs, None, None, C.byref(n)) == 0 and n.value == 0  # empty pass
+    assert lib.pamrec_batcher_destroy(bh) == 0
+    assert lib.pamrec_tokenize_file(None, 1, None, None, None, 0, None, None, None) == -1
+    assert lib.pamrec_tokens_read(None, None) == -1 and lib.pamrec_tokens_free(None) == 0
