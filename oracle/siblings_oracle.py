@@ -1,0 +1,217 @@
+"""TEST INFRASTRUCTURE - CPU restatement (torch, fp64 by default) of the reference's sibling multi-task baselines that share
+PAMRec's input pipeline, MLP blocks and towers:
+
+    MMoEModel_original   models/sequential/mmoe.py        (MM)
+    PLEModel             models/sequential/ple.py         (PLE)
+    ShareBottomModel     models/sequential/sharebottom.py (SB)
+
+All three are: DIN-style attention pooling of the satisfied-only history ("long_term") and of the full history ("short_term")
+against the target item (`_attention_fcn`, MM:299-337), a mixing layer over concat(long, short, target) - MMoE (MM:26-50), PLE
+(PLE:25-59) or none (SB:196-203) -, and two towers (`logit_fcn` on the satisfied label, `valid_logit_fcn` on the play label,
+MM:175-179) trained with  loss = data + regular + 0.5 * auxiliary  (MM:52-82; the 0.5 is a literal, not hparams.fuzhu_weight).
+Optimizer, clipping, BN and L2 semantics are those of the shared base classes, restated in oracle/pamrec_oracle.py; this file
+adds only what differs: the variable inventory, the forward pass and the losses.
+
+PARITY UNPINNED: like the float half of oracle/pamrec_oracle.py (TensorFlow cannot run here; the reference has no tests or golden
+vectors for these models).  No product code exists for these models yet - this is the oracle the device path will be built
+against; only tests/ may import it.
+"""
+import numpy as np
+import torch
+
+from . import pamrec_oracle as O
+
+E_DIM = O.I_DIM + O.C_DIM                  # 20: item + category embedding = target / history token width
+ATT_SIZES = (80, 40)                       # config/mmoe.yaml att_fcn_layer_sizes
+MODELS = ("mmoe", "ple", "sharebottom")
+
+
+def param_spec(model, n_users, n_items, n_cates, expert_num=5, share_expert_num=3, independent_expert_num=2,
+               expert_sizes=(100, 64), gate_sizes=(64, 5), tower_sizes=(100, 64)):
+    """TF variable inventory -> (params [(name, shape, init, group)], bn layers [(scope, channels)]).
+    Groups as in pamrec_oracle.param_spec: `embed` tables get L2 on the rows a batch involves (SBM:651-664, MM:140-149),
+    `layer` variables get full L2 (everything trainable outside sequential/embedding, SBM:714-721), `frozen` ones neither
+    gradient nor L2 (user_embedding and play_lookup are created but never read, SBM:571, MM:118-122)."""
+    assert model in MODELS
+    emb = "sequential/embedding/"
+    P = [(emb + "user_embedding", (n_users, O.U_DIM), "tn", "frozen"),
+         (emb + "item_embedding", (n_items, O.I_DIM), "tn", "embed"),
+         (emb + "cate_embedding", (n_cates, O.C_DIM), "tn", "embed"),
+         (emb + "looptimes_embedding", (10, O.C_DIM), "tn", "frozen"),
+         (emb + "user_long_embedding", (n_users, O.U_DIM), "tn", "embed_l2only"),
+         (emb + "user_short_embedding", (n_users, O.U_DIM), "tn", "embed_l2only"),
+         (emb + "play_lookup", (10, 40), "tn", "frozen")]
+    BN = []
+
+    def mlp(prefix, in_dim, sizes, out=False):
+        s, b = O._mlp_spec(prefix, in_dim, sizes, out=out)
+        P.extend(s)
+        BN.extend(b)
+    for branch in ("long_term", "short_term"):                                    # MM:217-226
+        pre = f"sequential/clsr/{branch}/attention_fcn"
+        P.append((pre + "/attention_mat", (E_DIM, E_DIM), "tn", "layer"))         # MM:315-319
+        mlp(pre + "/att_fcn", 4 * E_DIM, ATT_SIZES, out=True)                     # MM:327-329 (_fcn_net: linear output)
+    x_dim = 3 * E_DIM
+    if model == "mmoe":
+        for j in range(expert_num):
+            mlp(f"sequential/clsr/expert_{j}", x_dim, expert_sizes)               # MM:38-41
+        for g in ("gate_main", "gate_sub"):
+            mlp(f"sequential/clsr/{g}", x_dim, gate_sizes)                        # MM:43-44
+        tower_in = expert_sizes[-1] + E_DIM                                       # MM:231-232
+    elif model == "ple":
+        for j in range(share_expert_num):
+            mlp(f"sequential/clsr/share_expert_{j}", x_dim, expert_sizes)         # PLE:38-40
+        for task in ("main", "sub"):
+            for j in range(independent_expert_num):
+                mlp(f"sequential/clsr/{task}_expert_{j}", x_dim, expert_sizes)    # PLE:44-49
+        for task in ("main", "sub"):
+            mlp(f"sequential/clsr/gate_{task}", x_dim, gate_sizes)                # PLE:53-54
+        tower_in = expert_sizes[-1] + E_DIM                                       # PLE:230-231
+    else:
+        tower_in = x_dim                                                          # SB:200-201
+    for tw in ("sequential/valid_logit_fcn", "sequential/logit_fcn"):             # MM:175-177 (creation order)
+        mlp(tw, tower_in, tower_sizes, out=True)
+    return P, BN
+
+
+def init_params(spec, bn_spec, seed=8, init_value=0.01):
+    g = torch.Generator().manual_seed(seed)
+    params, bn_state = {}, {}
+    for name, shape, init, _ in spec:
+        if init == "zeros":
+            t = torch.zeros(shape)
+        elif init == "ones":
+            t = torch.ones(shape)
+        else:
+            t = torch.empty(shape)
+            torch.nn.init.trunc_normal_(t, std=init_value, a=-2 * init_value, b=2 * init_value, generator=g)
+        params[name] = t
+    for scope, c in bn_spec:
+        bn_state[scope + "/moving_mean"] = torch.zeros(c)
+        bn_state[scope + "/moving_variance"] = torch.ones(c)
+    return params, bn_state
+
+
+def add_satisfied_fields(batch, seed=0):
+    """make_batch of pamrec_oracle leaves out the satisfied-only copies of the history (dead for PAMRec, IT:1069-1103): build
+    them the way `_convert_data` does - the satisfied entries of each row, compacted to the left, zero padded."""
+    rng = np.random.default_rng(seed)
+    ih, ch, mask = np.asarray(batch["item_history"]), np.asarray(batch["item_cate_history"]), np.asarray(batch["mask"])
+    sat = (rng.random(ih.shape) < 0.5) & (mask == 1)
+    order = np.argsort(~sat, axis=1, kind="stable")
+    keep = np.arange(ih.shape[1])[None, :] < sat.sum(1)[:, None]
+    out = dict(batch)
+    out["satisfied_item_history"] = np.where(keep, np.take_along_axis(ih, order, 1), 0).astype(np.int32)
+    out["satisfied_cate_history"] = np.where(keep, np.take_along_axis(ch, order, 1), 0).astype(np.int32)
+    out["satisfied_mask"] = keep.astype(np.int32)
+    return out
+
+
+def _attention_fcn(ctx, query, hist, mask, scope):
+    """MM:299-337.  query [B, 20], hist [B, T, 20], mask [B, T] -> hist * softmax weights [B, T, 20]."""
+    B, T, _ = hist.shape
+    att_inputs = hist @ ctx.p[scope + "/attention_mat"]                                    # tensordot over the feature axis
+    q = query[:, None, :].expand(B, T, query.shape[1])
+    feats = torch.cat([att_inputs, q, att_inputs - q, att_inputs * q], -1)                # [B, T, 80]
+    score = O._mlp(ctx, feats, scope + "/att_fcn", ATT_SIZES, out=True).squeeze(-1)        # BN statistics over all B*T rows
+    pad = torch.full_like(score, float(-(2 ** 32) + 1))
+    w = torch.softmax(torch.where(mask == 1, score, pad), dim=-1)                          # an all-padding row: uniform weights
+    return hist * w[..., None]
+
+
+def forward(model, p, bn_state, batch, training, dtype=torch.float64, rows=None, **sizes):
+    """-> ctx with ctx.t["logits"] [B, 2] = (logit of `labels` (satisfied), valid_logit of `labels_play`) and ctx.t["pred"]."""
+    expert_num = sizes.get("expert_num", 5)
+    share_n, indep_n = sizes.get("share_expert_num", 3), sizes.get("independent_expert_num", 2)
+    expert_sizes, gate_sizes = sizes.get("expert_sizes", (100, 64)), sizes.get("gate_sizes", (64, 5))
+    tower_sizes = sizes.get("tower_sizes", (100, 64))
+    ctx = O._Ctx(p, bn_state, training, dtype)
+    emb = "sequential/embedding/"
+    idx = lambda k: torch.as_tensor(np.asarray(batch[k])).long()
+    item_w, cate_w = p[emb + "item_embedding"], p[emb + "cate_embedding"]
+    if rows is None:
+        rows = {"hist_item": item_w[idx("item_history")], "hist_cate": cate_w[idx("item_cate_history")],
+                "sat_item": item_w[idx("satisfied_item_history")], "sat_cate": cate_w[idx("satisfied_cate_history")],
+                "tgt_item": item_w[idx("items")], "tgt_cate": cate_w[idx("cates")]}
+    target = torch.cat([rows["tgt_item"], rows["tgt_cate"]], -1)                            # SBM:669-671
+    long_in = torch.cat([rows["sat_item"], rows["sat_cate"]], -1)                           # MM:199-201
+    short_in = torch.cat([rows["hist_item"], rows["hist_cate"]], -1)                        # MM:208-210
+    long = _attention_fcn(ctx, target, long_in, idx("satisfied_mask"), "sequential/clsr/long_term/attention_fcn").sum(1)
+    short = _attention_fcn(ctx, target, short_in, idx("mask"), "sequential/clsr/short_term/attention_fcn").sum(1)
+    x = torch.cat([long, short, target], -1)                                                # [B, 60]
+    ctx.t["x"] = x
+
+    # a gate is a BN + ReLU MLP like any other (no softmax, MM:43-46): [B, E] x experts [B, E, 64] -> [B, 64]
+    if model == "mmoe":
+        scopes = [f"sequential/clsr/expert_{j}" for j in range(expert_num)]
+        experts = torch.stack([O._mlp(ctx, x, s, expert_sizes) for s in scopes], 1)
+        main = (O._mlp(ctx, x, "sequential/clsr/gate_main", gate_sizes)[:, None, :] @ experts).squeeze(1)
+        sub = (O._mlp(ctx, x, "sequential/clsr/gate_sub", gate_sizes)[:, None, :] @ experts).squeeze(1)
+    elif model == "ple":
+        share = [O._mlp(ctx, x, f"sequential/clsr/share_expert_{j}", expert_sizes) for j in range(share_n)]
+        own = {t: [O._mlp(ctx, x, f"sequential/clsr/{t}_expert_{j}", expert_sizes) for j in range(indep_n)] for t in ("main", "sub")}
+        outs = {}
+        for t in ("main", "sub"):                                                          # PLE:51-58: shared experts first
+            gate = O._mlp(ctx, x, f"sequential/clsr/gate_{t}", gate_sizes)
+            outs[t] = (gate[:, None, :] @ torch.stack(share + own[t], 1)).squeeze(1)
+        main, sub = outs["main"], outs["sub"]
+    else:
+        main = sub = None
+    if model == "sharebottom":
+        model_output = valid_output = x                                                    # SB:200-201
+    else:
+        model_output, valid_output = torch.cat([main, target], -1), torch.cat([sub, target], -1)
+    valid_logit = O._mlp(ctx, valid_output, "sequential/valid_logit_fcn", tower_sizes, out=True)    # MM:175
+    logit = O._mlp(ctx, model_output, "sequential/logit_fcn", tower_sizes, out=True)               # MM:177
+    ctx.t["logits"] = torch.cat([logit, valid_logit], -1)
+    ctx.t["pred"] = torch.sigmoid(logit)                                                           # BM:93-113
+    return ctx
+
+
+def losses(ctx, spec, batch, hp):
+    """MM:52-82 + BM:122-134 / SBM:714-721.  hp: embed_l2, layer_l2."""
+    p, dtype = ctx.p, ctx.dtype
+    logits = ctx.t["logits"]
+    y_sat = torch.as_tensor(np.asarray(batch["labels_satisfied"])).to(dtype).reshape(-1)
+    y_play = torch.as_tensor(np.asarray(batch["labels_play"])).to(dtype).reshape(-1)
+    data = O._sigmoid_xent(logits[:, 0], y_sat).mean()
+    aux = 0.5 * O._sigmoid_xent(logits[:, 1], y_play).mean()
+    emb = "sequential/embedding/"
+    cat = lambda *ks: torch.unique(torch.cat([torch.as_tensor(np.asarray(batch[k])).long().reshape(-1) for k in ks]))
+    involved = {emb + "item_embedding": cat("item_history", "items"),                       # SBM:640-664: the FULL history and the
+                emb + "cate_embedding": cat("item_cate_history", "cates"),                  # target; satisfied ids are a subset
+                emb + "user_long_embedding": cat("users"), emb + "user_short_embedding": cat("users")}
+    reg = torch.zeros((), dtype=dtype)
+    for name, ids in involved.items():
+        reg = reg + hp["embed_l2"] * 0.5 * (p[name][ids] ** 2).sum()
+    for name, _, _, grp in spec:
+        if grp == "layer":
+            reg = reg + hp["layer_l2"] * 0.5 * (p[name] ** 2).sum()
+    return {"loss": data + reg + aux, "data_loss": data, "regular_loss": reg, "auxiliary_data_loss": aux}
+
+
+class SiblingOracle:
+    """Weights + one differentiable evaluation of the loss; the update rule is pamrec_oracle.OracleModel's."""
+
+    def __init__(self, model, n_users, n_items, n_cates, hp=None, seed=8, dtype=torch.float64, **sizes):
+        self.model, self.sizes, self.dtype = model, sizes, dtype
+        self.hp = dict(embed_l2=1e-4, layer_l2=1e-4)
+        self.hp.update(hp or {})
+        self.spec, self.bn_spec = param_spec(model, n_users, n_items, n_cates,
+                                             **{k: v for k, v in sizes.items() if k in ("expert_num", "share_expert_num",
+                                                                                       "independent_expert_num", "expert_sizes",
+                                                                                       "gate_sizes", "tower_sizes")})
+        self.params, self.bn_state = init_params(self.spec, self.bn_spec, seed=seed)
+
+    def loss_and_grads(self, batch):
+        p = {n: t.detach().clone().to(self.dtype).requires_grad_(True) for n, t in self.params.items()}
+        ctx = forward(self.model, p, self.bn_state, batch, True, self.dtype, **self.sizes)
+        out = losses(ctx, self.spec, batch, self.hp)
+        out["loss"].backward()
+        grads = {n: (t.grad if t.grad is not None else torch.zeros_like(t)) for n, t in p.items()}
+        return {k: float(v.detach()) for k, v in out.items()}, grads, ctx
+
+    def eval_forward(self, batch):
+        with torch.no_grad():
+            p = {n: t.to(self.dtype) for n, t in self.params.items()}
+            return forward(self.model, p, self.bn_state, batch, False, self.dtype, **self.sizes)
