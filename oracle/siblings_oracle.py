@@ -4,8 +4,9 @@ PAMRec's input pipeline, MLP blocks and towers:
     MMoEModel_original   models/sequential/mmoe.py        (MM)
     PLEModel             models/sequential/ple.py         (PLE)
     ShareBottomModel     models/sequential/sharebottom.py (SB)
+    SASRecModel          models/sequential/sasrec.py      (SAS; single task, see the second half of this file)
 
-All three are: DIN-style attention pooling of the satisfied-only history ("long_term") and of the full history ("short_term")
+The first three are: DIN-style attention pooling of the satisfied-only history ("long_term") and of the full history ("short_term")
 against the target item (`_attention_fcn`, MM:299-337), a mixing layer over concat(long, short, target) - MMoE (MM:26-50), PLE
 (PLE:25-59) or none (SB:196-203) -, and two towers (`logit_fcn` on the satisfied label, `valid_logit_fcn` on the play label,
 MM:175-179) trained with  loss = data + regular + 0.5 * auxiliary  (MM:52-82; the 0.5 is a literal, not hparams.fuzhu_weight).
@@ -215,3 +216,91 @@ class SiblingOracle:
         with torch.no_grad():
             p = {n: t.to(self.dtype) for n, t in self.params.items()}
             return forward(self.model, p, self.bn_state, batch, False, self.dtype, **self.sizes)
+
+
+# ===================================================================================================================== SASRec
+# SASRecModel (SAS:16-96): the satisfied-only history (item || category, 20 wide) plus a learned position table goes through two
+# pre-LN self-attention blocks with DENSE projections (tf.layers.dense with bias, SAS:268-270 - PAMRec's time-aware tables
+# replace exactly these), one head, key mask = satisfied_mask, no query mask, no causality (SAS:89); the state at the last
+# satisfied position (SAS:72-78) is concatenated with the target and fed to one tower (`logit_fcn`, SBM:76-79).  Loss = data +
+# regular (BM:136-151 / SBM single task).
+SAS_D = E_DIM
+
+
+def sasrec_param_spec(n_users, n_items, n_cates, T, tower_sizes=(100, 64)):
+    emb = "sequential/embedding/"
+    P = [(emb + "user_embedding", (n_users, O.U_DIM), "tn", "frozen"),
+         (emb + "item_embedding", (n_items, O.I_DIM), "tn", "embed"),
+         (emb + "cate_embedding", (n_cates, O.C_DIM), "tn", "embed"),
+         (emb + "looptimes_embedding", (10, O.C_DIM), "tn", "frozen"),
+         (emb + "position_embedding", (T, SAS_D), "tn", "pos")]                          # SAS:29-34 (add_feature False)
+    for b in range(2):
+        pre = f"sequential/sasrec/num_blocks_{b}/"
+        P += [(pre + "ln/Variable", (SAS_D,), "zeros", "layer"), (pre + "ln/Variable_1", (SAS_D,), "ones", "layer")]
+        for name in ("dense", "dense_1", "dense_2"):                                      # Q, K, V in creation order
+            P += [(pre + f"self_attention/{name}/kernel", (SAS_D, SAS_D), "glorot", "layer"),
+                  (pre + f"self_attention/{name}/bias", (SAS_D,), "zeros", "layer")]
+        P += [(pre + "ln_1/Variable", (SAS_D,), "zeros", "layer"), (pre + "ln_1/Variable_1", (SAS_D,), "ones", "layer")]
+        for name in ("conv1d", "conv1d_1"):
+            P += [(pre + f"multihead_attention/{name}/kernel", (1, SAS_D, SAS_D), "glorot", "layer"),
+                  (pre + f"multihead_attention/{name}/bias", (SAS_D,), "zeros", "layer")]
+    s, BN = O._mlp_spec("sequential/logit_fcn", 2 * SAS_D, tower_sizes, out=True)
+    return P + s, BN
+
+
+def sasrec_init(spec, bn_spec, seed=8, init_value=0.01):
+    params, bn_state = init_params([x for x in spec if x[2] != "glorot"], bn_spec, seed=seed, init_value=init_value)
+    g = torch.Generator().manual_seed(seed + 1)
+    for name, shape, init, _ in spec:
+        if init == "glorot":                                                              # tf.layers default initializer
+            fan_in, fan_out = shape[-2], shape[-1]
+            lim = (6.0 / (fan_in + fan_out)) ** 0.5
+            params[name] = (torch.rand(shape, generator=g) * 2 - 1) * lim
+    return {n: params[n] for n, _, _, _ in spec}, bn_state
+
+
+def sasrec_forward(p, bn_state, batch, training, dtype=torch.float64, tower_sizes=(100, 64)):
+    ctx = O._Ctx(p, bn_state, training, dtype)
+    emb = "sequential/embedding/"
+    idx = lambda k: torch.as_tensor(np.asarray(batch[k])).long()
+    mask = idx("satisfied_mask")
+    seq = torch.cat([p[emb + "item_embedding"][idx("satisfied_item_history")],
+                     p[emb + "cate_embedding"][idx("satisfied_cate_history")]], -1) + p[emb + "position_embedding"][None]   # SAS:61-64
+    target = torch.cat([p[emb + "item_embedding"][idx("items")], p[emb + "cate_embedding"][idx("cates")]], -1)
+    pad = float(-(2 ** 32) + 1)
+    for b in range(2):
+        pre = f"sequential/sasrec/num_blocks_{b}/"
+        q_in = O._ln(seq, p[pre + "ln/Variable"], p[pre + "ln/Variable_1"])               # queries = LN(seq), keys = seq (SAS:89-90)
+        dense = lambda x, n: x @ p[pre + f"self_attention/{n}/kernel"] + p[pre + f"self_attention/{n}/bias"]
+        Q, K, V = dense(q_in, "dense"), dense(seq, "dense_1"), dense(seq, "dense_2")
+        s = Q @ K.transpose(1, 2) / (SAS_D ** 0.5)                                        # SAS:281-284
+        s = torch.where(mask[:, None, :] == 0, torch.full_like(s, pad), s)                # SAS:288-293 key mask only
+        y = torch.softmax(s, -1) @ V + q_in                                               # SAS:318-324 residual on the queries
+        f = O._ln(y, p[pre + "ln_1/Variable"], p[pre + "ln_1/Variable_1"])
+        hid = torch.relu(f @ p[pre + "multihead_attention/conv1d/kernel"][0] + p[pre + "multihead_attention/conv1d/bias"])
+        seq = hid @ p[pre + "multihead_attention/conv1d_1/kernel"][0] + p[pre + "multihead_attention/conv1d_1/bias"] + f   # SAS:127-141
+        ctx.t[f"blk{b}.out"] = seq
+    length = mask.sum(1)
+    # SAS:72-78 reads seq[b, length - 1]: index -1 for a row without any satisfied item, which tf.gather_nd rejects on CPU and
+    # answers with zeros on GPU.  The iterator can produce such rows; the restatement follows the GPU behaviour.
+    last = torch.clamp(length - 1, min=0)
+    final = seq[torch.arange(seq.shape[0]), last] * (length > 0).to(seq.dtype)[:, None]
+    ctx.t["final_state"] = final
+    logit = O._mlp(ctx, torch.cat([final, target], -1), "sequential/logit_fcn", tower_sizes, out=True)
+    ctx.t["logits"] = logit
+    ctx.t["pred"] = torch.sigmoid(logit)
+    return ctx
+
+
+def sasrec_losses(ctx, spec, batch, hp):
+    p, dtype = ctx.p, ctx.dtype
+    y = torch.as_tensor(np.asarray(batch["labels_satisfied"])).to(dtype).reshape(-1)
+    data = O._sigmoid_xent(ctx.t["logits"][:, 0], y).mean()                               # BM:195-205
+    emb = "sequential/embedding/"
+    cat = lambda *ks: torch.unique(torch.cat([torch.as_tensor(np.asarray(batch[k])).long().reshape(-1) for k in ks]))
+    reg = hp["embed_l2"] * 0.5 * ((p[emb + "item_embedding"][cat("item_history", "items")] ** 2).sum()
+                                  + (p[emb + "cate_embedding"][cat("item_cate_history", "cates")] ** 2).sum())
+    for name, _, _, grp in spec:
+        if grp == "layer":
+            reg = reg + hp["layer_l2"] * 0.5 * (p[name] ** 2).sum()                       # position table is under /embedding: no L2
+    return {"loss": data + reg, "data_loss": data, "regular_loss": reg}

@@ -120,3 +120,44 @@ def test_gradients_match_finite_differences(model):
         m.params[name] = base
         fd = (vals[0] - vals[1]) / 2e-6
         assert abs(fd - float(grads[name][idx])) <= 1e-5 * max(abs(fd), 1e-5), (name, fd, float(grads[name][idx]))
+
+
+def test_sasrec_restatement():
+    spec, bn = S.sasrec_param_spec(NU, NI, NC, T)
+    params, bn_state = S.sasrec_init(spec, bn, seed=3)
+    assert [n for n, _, _, _ in spec] == list(params) and len(set(params)) == len(params)
+    assert params["sequential/sasrec/num_blocks_1/self_attention/dense_2/kernel"].shape == (20, 20)
+    assert params["sequential/logit_fcn/nn_part/w_nn_layer0"].shape == (40, 100)
+    g = torch.Generator().manual_seed(5)
+    params = {n: t + 0.1 * torch.randn(t.shape, generator=g) for n, t in params.items()}
+    batch = _batch(9)
+    p = {n: t.double().requires_grad_(True) for n, t in params.items()}
+    ctx = S.sasrec_forward(p, bn_state, batch, True)
+    out = S.sasrec_losses(ctx, spec, batch, dict(embed_l2=1e-4, layer_l2=1e-4))
+    out["loss"].backward()
+    assert ctx.t["logits"].shape == (B, 1)
+    # the read-out is the block output at the last satisfied position; rows without one read zeros
+    length = np.asarray(batch["satisfied_mask"]).sum(1)
+    b = int(np.argmax(length > 0))
+    assert torch.equal(ctx.t["final_state"][b], ctx.t["blk1.out"][b, int(length[b]) - 1])
+    none = dict(batch)
+    sm = np.asarray(batch["satisfied_mask"]).copy(); sm[0] = 0
+    none["satisfied_mask"] = sm
+    with torch.no_grad():
+        assert not S.sasrec_forward({n: t.double() for n, t in params.items()}, bn_state, none, False).t["final_state"][0].any()
+    # key mask only: every query row (padded ones too) attends, so padded positions of the LAST block never reach the loss, while
+    # the keys they would contribute are masked out -> gradient of the position rows beyond every length is zero
+    longest = int(length.max())
+    gpos = p["sequential/embedding/position_embedding"].grad
+    assert gpos[:longest].abs().max() > 0 and (longest == T or not gpos[longest:].any())
+    # finite differences on a projection weight
+    name, idx = "sequential/sasrec/num_blocks_0/self_attention/dense_1/kernel", (4, 7)
+    vals = []
+    for sgn in (+1, -1):
+        q = {n: t.double().clone() for n, t in params.items()}
+        q[name][idx] += sgn * 1e-6
+        with torch.no_grad():
+            c = S.sasrec_forward(q, bn_state, batch, True)
+            vals.append(float(S.sasrec_losses(c, spec, batch, dict(embed_l2=1e-4, layer_l2=1e-4))["loss"]))
+    fd = (vals[0] - vals[1]) / 2e-6
+    assert abs(fd - float(p[name].grad[idx])) <= 1e-5 * max(abs(fd), 1e-5)
