@@ -47,6 +47,9 @@ flags.DEFINE_float("noise_train_hist", 0, "noise_train_hist")
 flags.DEFINE_float("noise_train_listwise", 0, "noise_train_listwise")
 flags.DEFINE_float("noise_only_predict", 0, "noise_only_predict")
 flags.DEFINE_string("sparse_adam", "dense_exact", "dense_exact (tf.train.AdamOptimizer semantics) or lazy")
+flags.DEFINE_string("checkpoint_format", "safetensors", "safetensors, tf (TensorFlow tensor bundle) or npz")
+flags.DEFINE_boolean("save_optimizer", False, "also checkpoint the Adam state (resume exactly; the reference's Saver does not)")
+flags.DEFINE_string("loss", "cross_entropy_loss", "cross_entropy_loss or softmax (over groups of train_num_ngs + 1 rows)")
 
 
 def get_model(f, model_path, summary_path, user_vocab, item_vocab, cate_vocab):
@@ -63,7 +66,8 @@ def get_model(f, model_path, summary_path, user_vocab, item_vocab, cate_vocab):
         item_vocab=item_vocab, cate_vocab=cate_vocab, train_num_ngs=f.train_num_ngs, max_seq_length=100,
         pairwise_metrics=[], weighted_metrics=weighted, fuzhu_weight=f.fuzhu_weight, fine_tune=False,
         eval_step=f.eval_step, noise_train_hist=f.noise_train_hist, noise_train_listwise=f.noise_train_listwise,
-        noise_only_predict=f.noise_only_predict, sparse_adam=f.sparse_adam)
+        noise_only_predict=f.noise_only_predict, sparse_adam=f.sparse_adam, checkpoint_format=f.checkpoint_format,
+        save_optimizer=f.save_optimizer, loss=f.loss)
     return PAMRECModel(hparams, SequentialIterator, seed=8)
 
 
