@@ -192,3 +192,58 @@ def test_vocabularies_that_are_not_plain_str_to_int_dicts_keep_python(tmp_path):
         _iterator(d)._tokenize_native(str(d / "nope"), True)
     it3 = _iterator(d, noise_only_predict=0.5)                               # draws from np.random per element while parsing
     assert it3._tokenize_native(str(d / "train_data"), True) is None
+
+
+def test_fuzz_native_accepts_only_what_it_parses_like_python(tmp_path):
+    """400 random small files mixing well-formed lines with every kind of irregularity (odd spellings, blanks, missing / extra /
+    ragged columns, CR, non-ASCII).  Whenever the native tokenizer ACCEPTS a file its columns must equal the Python parser's
+    byte for byte (so Python did not raise either); refusing is always allowed, but well-formed files must be accepted."""
+    d = tmp_path / "wechat"
+    d.mkdir()
+    it = _iterator(d)
+    rng = random.Random(2024)
+    num_ok = ["0", "1", "7", "12.5", "0.25", "3e2", "-1.5", "+2", "1E-3", "100000", ".5", "5.", "007", "1.0", "0.0"]
+    num_odd = ["", " 1", "1 ", "1_0", "nan", "inf", "-inf", "0x10", "1e", "e5", "--1", "1.2.3", "١", "1e400", "1,5".replace(",", ";"), "\t"]
+    ids = [str(i) for i in range(1, 30)] + ["zz", "", "c1", "c9", "u3", " 4", "ü"]
+    accepted = refused = 0
+    for case in range(400):
+        train = rng.random() < 0.5
+        clean = rng.random() < 0.35
+        rows = []
+        for _ in range(rng.randrange(1, 5)):
+            n = rng.randrange(1, 6)
+
+            def col(pool_ok, pool_odd, k=None):
+                k = n if k is None else k
+                return ",".join(rng.choice(pool_ok if clean or rng.random() < 0.93 else pool_odd) for _ in range(k))
+            ragged = (lambda: n) if clean or rng.random() < 0.9 else (lambda: rng.randrange(1, 6))
+            hist = [col(ids[:29], ids, ragged()), col(["c1", "c2", "c9"], ids, ragged()), col(num_ok, num_odd, ragged()),
+                    col(["0", "1", "1.0", "0.0"], num_odd, ragged()), col(["12000", "500", "7999.5", "8000"], num_odd, ragged())]
+            head = [f"u{rng.randrange(1, 45)}"] if train else [rng.choice(["0", "1"] if clean else ["0", "1", "1.0", " 1", "+1", "x"]),
+                                                                rng.choice(num_ok if clean else num_ok + num_odd[:6]), f"u{rng.randrange(1, 45)}",
+                                                                rng.choice(ids[:29]), "c2", rng.choice(num_ok)]
+            cols = head + hist
+            if not clean and rng.random() < 0.08:
+                cols = cols[:rng.randrange(1, len(cols))]                      # missing columns
+            if rng.random() < 0.1:
+                cols = cols + ["extra"]
+            line = "\t".join(cols)
+            if not clean and rng.random() < 0.1:
+                line = rng.choice([" ", "\t", ""]) + line + rng.choice([" ", "\t", "\x0b", ""])
+            rows.append(line)
+        sep = "\n" if clean else rng.choice(["\n", "\n", "\r\n", "\r", "\n\n"])
+        text = sep.join(rows) + rng.choice(["\n", ""])
+        path = d / ("train_data" if train else "valid_data")
+        path.write_bytes(text.encode("utf-8"))
+        nat = it._tokenize_native(str(path), train)
+        if nat is None:
+            assert not clean, text
+            refused += 1
+            continue
+        accepted += 1
+        it.train = train
+        py = it._flatten(it.parse_file(str(path)), train)              # must not raise: the native parser accepted the file
+        assert py is not None and list(nat) == list(py)
+        for k in py:
+            assert nat[k].dtype == py[k].dtype and nat[k].tobytes() == py[k].tobytes(), (case, k, text)
+    assert accepted > 100 and refused > 100, (accepted, refused)
