@@ -191,10 +191,11 @@ class SequentialIterator:
         items, cates, durs = res["items"], res["cates"], res["durations"]
         item_list = items.tolist()
         src = np.empty(n * (ngs + 1), np.int64)                              # row whose target each output row takes
+        distinct = set(item_list)
         for i in range(n):
             src[i * (ngs + 1)] = i
             group = item_list[i // 5: i // 5 + 5]
-            if len(set(item_list) - set(group)) == 0:
+            if distinct <= set(group):
                 return {}            # (a tail batch of one group) no admissible negative exists: the block would spin forever;
                                      # the batch is dropped like the too-short one above - the loops skip empty feeds
             count = 0
