@@ -13,7 +13,6 @@ whole step as hand-written CUDA kernels behind the C ABI.  There is no CPU path.
 import math
 import os
 import random
-import time
 
 import numpy as np
 import torch
@@ -21,7 +20,7 @@ import torch
 from . import checkpoint as CK
 from . import dist as D
 from .deeprec_utils import cal_metric, cal_weighted_metric, filter_single_class_users, load_dict
-from .engine import Engine, EMB, TABLES
+from .engine import Engine
 from .prefetch import Prefetcher
 from .sequential_iterator import LocalFeed
 
