@@ -440,14 +440,30 @@ class OracleModel:
         self.hp = dict(DEFAULT_HP)
         if hp:
             self.hp.update(hp)
-        self.spec, self.bn_spec = param_spec(*self.dims)
+        self.spec, self.bn_spec = self._spec()
         self.hp["_spec"] = self.spec
         self.group_of = {n: g for n, _, _, g in self.spec}
-        self.params, self.bn_state = init_params(*self.dims, seed=seed)
+        self.params, self.bn_state = self._init(seed)
         self.dtype = dtype
         self.step = 0
         self.m = {n: torch.zeros_like(t, dtype=dtype) for n, t in self.params.items()}
         self.v = {n: torch.zeros_like(t, dtype=dtype) for n, t in self.params.items()}
+
+    # ---- what a model family defines (the sibling baselines override these four, oracle/siblings_oracle.py)
+    def _spec(self):
+        return param_spec(*self.dims)
+
+    def _init(self, seed):
+        return init_params(*self.dims, seed=seed)
+
+    def _gather(self, p, batch):
+        return gather(p, batch)
+
+    def _forward(self, p, batch, training, rows=None):
+        return forward(p, self.bn_state, batch, training, rows=rows, dtype=self.dtype)
+
+    def _losses(self, ctx, batch, rows):
+        return compute_losses(ctx, batch, rows, self.hp)
 
     def cast_params(self, requires_grad):
         out = {}
@@ -461,19 +477,19 @@ class OracleModel:
     def eval_forward(self, batch):
         with torch.no_grad():
             p = self.cast_params(False)
-            return forward(p, self.bn_state, batch, False, dtype=self.dtype)
+            return self._forward(p, batch, False)
 
     def train_step(self, batch, apply=True, keep=()):
         """One optimisation step (PAM:426-453).  Returns dict with losses, intermediates,
         raw gradients (pre-clip) and the clip scales."""
         hp, dtype = self.hp, self.dtype
         p = self.cast_params(True)
-        g_idx, rows = gather(p, batch)
+        g_idx, rows = self._gather(p, batch)
         rows = {k: v.detach().clone().requires_grad_(True) for k, v in rows.items()}
-        ctx = forward(p, self.bn_state, batch, True, rows=rows, dtype=dtype)
+        ctx = self._forward(p, batch, True, rows=rows)
         for k in keep:
             ctx.t[k].retain_grad()
-        losses = compute_losses(ctx, batch, rows, hp)
+        losses = self._losses(ctx, batch, rows)
         losses["loss"].backward()
 
         clip = float(hp["max_grad_norm"])

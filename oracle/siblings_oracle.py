@@ -259,14 +259,20 @@ def sasrec_init(spec, bn_spec, seed=8, init_value=0.01):
     return {n: params[n] for n, _, _, _ in spec}, bn_state
 
 
-def sasrec_forward(p, bn_state, batch, training, dtype=torch.float64, tower_sizes=(100, 64)):
+def sasrec_forward(p, bn_state, batch, training, dtype=torch.float64, tower_sizes=(100, 64), rows=None):
+    """rows: optional pre-gathered lookups (sat_item, sat_cate, tgt_item, tgt_cate, pos [B, T, 20]) so that a caller can observe
+    their per-lookup gradients; by default they are read from the tables here."""
     ctx = O._Ctx(p, bn_state, training, dtype)
     emb = "sequential/embedding/"
     idx = lambda k: torch.as_tensor(np.asarray(batch[k])).long()
     mask = idx("satisfied_mask")
-    seq = torch.cat([p[emb + "item_embedding"][idx("satisfied_item_history")],
-                     p[emb + "cate_embedding"][idx("satisfied_cate_history")]], -1) + p[emb + "position_embedding"][None]   # SAS:61-64
-    target = torch.cat([p[emb + "item_embedding"][idx("items")], p[emb + "cate_embedding"][idx("cates")]], -1)
+    if rows is None:
+        rows = {"sat_item": p[emb + "item_embedding"][idx("satisfied_item_history")],
+                "sat_cate": p[emb + "cate_embedding"][idx("satisfied_cate_history")],
+                "tgt_item": p[emb + "item_embedding"][idx("items")], "tgt_cate": p[emb + "cate_embedding"][idx("cates")],
+                "pos": p[emb + "position_embedding"][None].expand(mask.shape[0], -1, -1)}   # SAS:39-44: tile(range(T)) lookup
+    seq = torch.cat([rows["sat_item"], rows["sat_cate"]], -1) + rows["pos"]                # SAS:61-64
+    target = torch.cat([rows["tgt_item"], rows["tgt_cate"]], -1)
     pad = float(-(2 ** 32) + 1)
     for b in range(2):
         pre = f"sequential/sasrec/num_blocks_{b}/"
@@ -304,3 +310,66 @@ def sasrec_losses(ctx, spec, batch, hp):
         if grp == "layer":
             reg = reg + hp["layer_l2"] * 0.5 * (p[name] ** 2).sum()                       # position table is under /embedding: no L2
     return {"loss": data + reg, "data_loss": data, "regular_loss": reg}
+
+
+# ===================================================================================================================== train step
+class SiblingOracleModel(O.OracleModel):
+    """pamrec_oracle.OracleModel (per-lookup sparse gradients, per-tensor tf.clip_by_norm, TF Adam with dense decay of sparse
+    variables, BN moving averages) driven by a sibling model's inventory, forward pass and losses.
+    model: "mmoe" | "ple" | "sharebottom" | "sasrec"."""
+
+    def __init__(self, model, n_users, n_items, n_cates, T, hp=None, seed=8, dtype=torch.float64, **sizes):
+        assert model in MODELS + ("sasrec",)
+        self.model, self.sizes = model, sizes
+        super().__init__(n_users, n_items, n_cates, T, hp=hp, seed=seed, dtype=dtype)
+
+    def _spec(self):
+        nu, ni, nc, T = self.dims
+        if self.model == "sasrec":
+            return sasrec_param_spec(nu, ni, nc, T, **{k: v for k, v in self.sizes.items() if k == "tower_sizes"})
+        return param_spec(self.model, nu, ni, nc, **self.sizes)
+
+    def _init(self, seed):
+        return sasrec_init(self.spec, self.bn_spec, seed=seed) if self.model == "sasrec" else init_params(self.spec, self.bn_spec, seed=seed)
+
+    def _gather(self, p, batch):
+        """Every embedding_lookup as its own tensor (SBM:598-668, MM:131-149): full history, satisfied-only history, target,
+        and the `involved` rows that only carry the L2 term."""
+        idx = lambda k: torch.as_tensor(np.asarray(batch[k])).long()
+        emb = "sequential/embedding/"
+        uniq = lambda *ks: torch.unique(torch.cat([idx(k).reshape(-1) for k in ks]))
+        g = {"hist_item": (emb + "item_embedding", idx("item_history")), "hist_cate": (emb + "cate_embedding", idx("item_cate_history")),
+             "sat_item": (emb + "item_embedding", idx("satisfied_item_history")),
+             "sat_cate": (emb + "cate_embedding", idx("satisfied_cate_history")),
+             "tgt_item": (emb + "item_embedding", idx("items")), "tgt_cate": (emb + "cate_embedding", idx("cates")),
+             "inv_item": (emb + "item_embedding", uniq("item_history", "items")),
+             "inv_cate": (emb + "cate_embedding", uniq("item_cate_history", "cates"))}
+        if self.model != "sasrec":
+            g["inv_ulong"] = (emb + "user_long_embedding", uniq("users"))
+            g["inv_ushort"] = (emb + "user_short_embedding", uniq("users"))
+        else:                                                     # SAS:39-44: one lookup row per (sample, position)
+            B, T = idx("satisfied_mask").shape
+            g["pos"] = (emb + "position_embedding", torch.arange(T)[None, :].expand(B, T))
+        return g, {k: p[name][i] for k, (name, i) in g.items()}
+
+    def _forward(self, p, batch, training, rows=None):
+        if self.model == "sasrec":
+            return sasrec_forward(p, self.bn_state, batch, training, self.dtype, rows=rows, **self.sizes)
+        return forward(self.model, p, self.bn_state, batch, training, self.dtype, rows=rows, **self.sizes)
+
+    def _losses(self, ctx, batch, rows):
+        dtype, hp = self.dtype, self.hp
+        y = lambda k: torch.as_tensor(np.asarray(batch[k])).to(dtype).reshape(-1)
+        out = {"data_loss": O._sigmoid_xent(ctx.t["logits"][:, 0], y("labels_satisfied")).mean()}
+        if self.model != "sasrec":
+            out["auxiliary_data_loss"] = 0.5 * O._sigmoid_xent(ctx.t["logits"][:, 1], y("labels_play")).mean()
+        reg = torch.zeros((), dtype=dtype)
+        for k in rows:
+            if k.startswith("inv_"):
+                reg = reg + hp["embed_l2"] * 0.5 * (rows[k] ** 2).sum()
+        for name, _, _, grp in self.spec:
+            if grp == "layer":
+                reg = reg + hp["layer_l2"] * 0.5 * (ctx.p[name] ** 2).sum()
+        out["regular_loss"] = reg
+        out["loss"] = sum(out.values())
+        return out

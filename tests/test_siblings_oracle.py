@@ -161,3 +161,39 @@ def test_sasrec_restatement():
             vals.append(float(S.sasrec_losses(c, spec, batch, dict(embed_l2=1e-4, layer_l2=1e-4))["loss"]))
     fd = (vals[0] - vals[1]) / 2e-6
     assert abs(fd - float(p[name].grad[idx])) <= 1e-5 * max(abs(fd), 1e-5)
+
+
+@pytest.mark.parametrize("model", S.MODELS + ("sasrec",))
+def test_full_train_step_of_every_sibling(model):
+    """SiblingOracleModel = the PAMRec oracle's update rule (per-lookup sparse gradients, per-tensor clip, TF Adam, BN moving
+    averages) around a sibling's graph: gradients agree with plain autograd through the tables, two steps move every live variable,
+    frozen ones stay put."""
+    hp = dict(embed_l2=1e-4, layer_l2=1e-4)
+    m = S.SiblingOracleModel(model, NU, NI, NC, T, hp=hp, seed=4)
+    O.perturb_params(m.params, m.bn_state, seed=5)
+    batch = _batch(11)
+    ref = m.train_step(batch, apply=False)
+    # the same loss differentiated straight through the embedding tables
+    p = {n: t.double().clone().requires_grad_(True) for n, t in m.params.items()}
+    if model == "sasrec":
+        ctx = S.sasrec_forward(p, m.bn_state, batch, True)
+        want = S.sasrec_losses(ctx, m.spec, batch, hp)
+    else:
+        ctx = S.forward(model, p, m.bn_state, batch, True)
+        want = S.losses(ctx, m.spec, batch, hp)
+    want["loss"].backward()
+    for k, v in want.items():
+        assert abs(float(v.detach()) - ref["losses"][k]) < 1e-12, k
+    for n, g in ref["grads"].items():
+        assert torch.allclose(g, p[n].grad, rtol=1e-10, atol=1e-14), n
+    # the clip norm of a table is taken over the un-deduplicated lookup rows (BM:297-303), not over the summed gradient
+    name = "sequential/embedding/item_embedding"
+    assert ref["sqnorms"][name] > 0 and abs(ref["sqnorms"][name] - float((ref["grads"][name] ** 2).sum())) > 0
+    before = {n: t.clone() for n, t in m.params.items()}
+    m.train_step(batch)
+    m.train_step(_batch(12))
+    assert m.step == 2
+    for n, _, _, grp in m.spec:
+        moved = bool((m.params[n] != before[n]).any())
+        assert moved == (grp != "frozen"), (n, grp)
+    assert all(bool((m.bn_state[s + "/moving_mean"] != 0).any()) for s, _ in m.bn_spec)
