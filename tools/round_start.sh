@@ -3,7 +3,7 @@
 #
 #  1 GPU  (~90 s):  tools/round_start.sh single
 #  8 GPUs (~90 s):  tools/round_start.sh parity8      # strict multi-rank parity (not re-run at the end of round 1)
-#  N GPUs         :  tools/scale_run.sh takatak_b1025_t50 "1 2 4 8"
+#  N GPUs         :  for n in 1 2 4 8; do tools/scale_run.sh $n takatak_b1025_t50; done
 #  1 GPU  (ncu)   :  tools/round_start.sh ncu          # launch list of one bench step, after the plain run exited 0
 set -u
 mkdir -p gpurun_out
