@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpamrec_b200.so")
 SOURCES = ["api.cu", "prof.cu", "comm.cu", "kernels_encoder.cu", "kernels_head.cu", "kernels_optim.cu", "kernels_shard.cu", "kernels_p2p.cu", "batcher.cu", "tokenizer.cu", "crc32c.cu"]
-HEADERS = ["common.cuh", "kernels.h", "layout.h", "comm.h", os.path.join("..", "..", "include", "pamrec_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))) + [os.path.join("..", "..", "include", "pamrec_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr",

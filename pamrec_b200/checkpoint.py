@@ -406,8 +406,15 @@ def exists(path):
     return any(p.endswith((".safetensors", ".npz", ".index")) for p in _files(path))
 
 
-def remove(path):
+def remove(path, keep_fmt=None):
+    """Delete the files of checkpoint `path`; with keep_fmt, only the files of the OTHER formats (called after a successful
+    save so that a crash between the two never leaves `path` without a complete checkpoint)."""
+    keep = {"safetensors": (".safetensors",), "npz": (".npz",), "tf": (".index", ".data-")}.get(keep_fmt, ())
+    base = os.path.basename(path)
     for p in _files(path):
+        tail = os.path.basename(p)[len(base):]
+        if any(tail.startswith(k) for k in keep):
+            continue
         os.remove(p)
 
 
@@ -423,7 +430,9 @@ def save(path, variables, fmt="safetensors", optimizer=None, metadata=None):
     elif fmt == "tf":
         save_tf_bundle(path, tensors)
     else:
-        np.savez(path + ".npz", **{k.replace("/", "|"): v for k, v in tensors.items()})
+        tmp = path + ".tmp.npz"
+        np.savez(tmp, **{k.replace("/", "|"): v for k, v in tensors.items()})
+        os.replace(tmp, path + ".npz")
     return path
 
 

@@ -65,8 +65,7 @@ struct PamrecHandle_ {
   // run fn(side) after everything enqueued on `main` so far
   template <typename F>
   void fork(cudaStream_t main, F fn) {
-    static const bool inline_side = getenv("PAMREC_NO_SIDE_STREAM") != nullptr;   // debugging aid: everything on one stream
-    if (inline_side) { fn(main); return; }
+    if (getenv("PAMREC_NO_SIDE_STREAM") != nullptr) { fn(main); return; }   // debugging aid: everything on one stream
     cudaEvent_t e = ev_side[ev_next];
     ev_next = (ev_next + 1) % 12;
     cudaEventRecord(e, main);
@@ -262,6 +261,7 @@ int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(h, "no CUDA device: the CUDA path is the only path"); }
   h->buf = *bufs;
+  if (init_encoder_kernels(h->cfg.max_seq_len)) return check_cuda(h, "shared-memory opt-in of the encoder kernels");
   if (!h->side) {
     if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) return fail(h, "cannot create the side stream");
     for (auto& e : h->ev_side) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -410,14 +410,15 @@ static int shard_exchange_fwd(PamrecHandle h, const PamrecBatch* b, bool trainin
   }
   {
     PAMREC_PROF("xchg_ids", 1, st);
-    h->comm.group_start();
-    for (int t = 0; t < nt; ++t) {
+    int xrc = h->comm.group_start();                  // the group is closed on every path (comm.cu: close_group)
+    for (int t = 0; t < nt && !xrc; ++t) {
       const Xchg& x = h->xc[t];
       std::string p = std::string("sh.") + kShardName[t] + ".";
-      if (h->comm.all_to_all_v(h->wi(p + "send_ids"), x.soff.data(), x.scnt.data(), h->wi(p + "recv_ids"), x.roff.data(),
-                               x.rcnt.data(), 1, COMM_I32, st)) return fail(h, "nccl: %s", h->comm.err.c_str());
+      xrc |= h->comm.all_to_all_v(h->wi(p + "send_ids"), x.soff.data(), x.scnt.data(), h->wi(p + "recv_ids"), x.roff.data(),
+                                  x.rcnt.data(), 1, COMM_I32, st);
     }
-    if (h->comm.group_end()) return fail(h, "nccl: %s", h->comm.err.c_str());
+    xrc |= h->comm.group_end();
+    if (xrc) return fail(h, "nccl: %s", h->comm.err.c_str());
   }
   if (training) {
     // owner-side unique / slot plan of the rows other ranks asked for: needed by apply_gradients only, so it is sorted on the
@@ -437,14 +438,15 @@ static int shard_exchange_fwd(PamrecHandle h, const PamrecBatch* b, bool trainin
   launch_serve_rows(h->buf.cate_w, h->wi("sh.cate.recv_ids"), h->xc[1].n_recv, kC, h->wf("sh.cate.xrows"), st);
   {
     PAMREC_PROF("xchg_rows", 1, st);
-    h->comm.group_start();
-    for (int t = 0; t < 2; ++t) {
+    int xrc = h->comm.group_start();
+    for (int t = 0; t < 2 && !xrc; ++t) {
       const Xchg& x = h->xc[t];
       std::string p = std::string("sh.") + kShardName[t] + ".";
-      if (h->comm.all_to_all_v(h->wf(p + "xrows"), x.roff.data(), x.rcnt.data(), h->wf(p + "rows"), x.soff.data(),
-                               x.scnt.data(), shard_dim(h, t).width, COMM_F32, st)) return fail(h, "nccl: %s", h->comm.err.c_str());
+      xrc |= h->comm.all_to_all_v(h->wf(p + "xrows"), x.roff.data(), x.rcnt.data(), h->wf(p + "rows"), x.soff.data(),
+                                  x.scnt.data(), shard_dim(h, t).width, COMM_F32, st);
     }
-    if (h->comm.group_end()) return fail(h, "nccl: %s", h->comm.err.c_str());
+    xrc |= h->comm.group_end();
+    if (xrc) return fail(h, "nccl: %s", h->comm.err.c_str());
   }
   return 0;
 }
@@ -863,6 +865,7 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
     // ---- row-sharded tables: local pre-reduction, row gradients to their owners, owner-side merge + Adam
     Comm& cm = h->comm;
     int crc = 0;
+    if (!h->xc_users) return fail(h, "apply_gradients needs pamrec_forward(training=1) on the same batch");   // before any collective
     for (int t = 0; t < 2; ++t) {
       SparseTable req = req_table(h, t);
       const int col = t == 0 ? 0 : kI;
@@ -879,7 +882,6 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
       }
       crc |= cm.group_end();
     }
-    if (!h->xc_users) return fail(h, "apply_gradients needs pamrec_forward(training=1) on the same batch");
     cudaStreamWaitEvent(st, h->ev_plan, 0);            // owner-side plans (side stream, forked in the forward exchange)
     for (int t = 0; t < 3; ++t) {
       SparseTable own = own_table(h, t);

@@ -15,6 +15,7 @@ struct Api {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -43,6 +44,7 @@ bool load_api(const char* path, std::string* err) {
   PAMREC_SYM(GetUniqueId, "ncclGetUniqueId")
   PAMREC_SYM(CommInitRank, "ncclCommInitRank")
   PAMREC_SYM(CommDestroy, "ncclCommDestroy")
+  PAMREC_SYM(CommAbort, "ncclCommAbort")
   PAMREC_SYM(AllReduce, "ncclAllReduce")
   PAMREC_SYM(Send, "ncclSend")
   PAMREC_SYM(Recv, "ncclRecv")
@@ -91,6 +93,22 @@ void Comm::destroy() {
   comm = nullptr;
 }
 
+// ends the NCCL group opened by the caller; `first` is the first error seen inside it (ncclSuccess = none)
+int Comm::close_group(int first, const char* where) {
+  ncclResult_t end = g_api.GroupEnd();
+  ncclResult_t r = first != ncclSuccess ? (ncclResult_t)first : end;
+  if (r == ncclSuccess) return 0;
+  err = std::string(where) + ": " + g_api.GetErrorString(r);
+  abort();
+  return -1;
+}
+
+// a fatal communication error: peers blocked in a collective fail instead of waiting for this rank forever
+void Comm::abort() {
+  if (comm && g_api.CommAbort) g_api.CommAbort((ncclComm_t)comm);
+  comm = nullptr;
+}
+
 int Comm::group_start() {
   if (world <= 1) return 0;
   PAMREC_NCCL(g_api.GroupStart());
@@ -116,13 +134,16 @@ int Comm::all_to_all(const void* send, void* recv, int64_t count, CommType t, cu
     return 0;
   }
   if (!comm) { err = "communicator not initialised (pamrec_comm_init)"; return -1; }
+  // An error inside an open group must still close it (and abort the communicator): a group left open queues every
+  // later collective of this thread forever while the peers wait in theirs.
   PAMREC_NCCL(g_api.GroupStart());
-  for (int p = 0; p < world; ++p) {
-    PAMREC_NCCL(g_api.Send(static_cast<const char*>(send) + (size_t)p * count * eb, (size_t)count, nccl_type(t), p, (ncclComm_t)comm, st));
-    PAMREC_NCCL(g_api.Recv(static_cast<char*>(recv) + (size_t)p * count * eb, (size_t)count, nccl_type(t), p, (ncclComm_t)comm, st));
+  ncclResult_t first = ncclSuccess;
+  for (int p = 0; p < world && first == ncclSuccess; ++p) {
+    first = g_api.Send(static_cast<const char*>(send) + (size_t)p * count * eb, (size_t)count, nccl_type(t), p, (ncclComm_t)comm, st);
+    if (first == ncclSuccess)
+      first = g_api.Recv(static_cast<char*>(recv) + (size_t)p * count * eb, (size_t)count, nccl_type(t), p, (ncclComm_t)comm, st);
   }
-  PAMREC_NCCL(g_api.GroupEnd());
-  return 0;
+  return close_group(first, "all_to_all");
 }
 
 int Comm::all_to_all_v(const void* send, const int64_t* soff, const int64_t* scnt, void* recv, const int64_t* roff,
@@ -137,16 +158,16 @@ int Comm::all_to_all_v(const void* send, const int64_t* soff, const int64_t* scn
   }
   if (!comm) { err = "communicator not initialised (pamrec_comm_init)"; return -1; }
   PAMREC_NCCL(g_api.GroupStart());
-  for (int p = 0; p < world; ++p) {
+  ncclResult_t first = ncclSuccess;
+  for (int p = 0; p < world && first == ncclSuccess; ++p) {
     if (scnt[p] > 0)
-      PAMREC_NCCL(g_api.Send(static_cast<const char*>(send) + (size_t)soff[p] * eb, (size_t)scnt[p] * width, nccl_type(t), p,
-                             (ncclComm_t)comm, st));
-    if (rcnt[p] > 0)
-      PAMREC_NCCL(g_api.Recv(static_cast<char*>(recv) + (size_t)roff[p] * eb, (size_t)rcnt[p] * width, nccl_type(t), p,
-                             (ncclComm_t)comm, st));
+      first = g_api.Send(static_cast<const char*>(send) + (size_t)soff[p] * eb, (size_t)scnt[p] * width, nccl_type(t), p,
+                         (ncclComm_t)comm, st);
+    if (first == ncclSuccess && rcnt[p] > 0)
+      first = g_api.Recv(static_cast<char*>(recv) + (size_t)roff[p] * eb, (size_t)rcnt[p] * width, nccl_type(t), p,
+                         (ncclComm_t)comm, st);
   }
-  PAMREC_NCCL(g_api.GroupEnd());
-  return 0;
+  return close_group(first, "all_to_all_v");
 }
 
 }  // namespace pamrec

@@ -26,6 +26,8 @@ struct Comm {
   // all collectives enqueue on `st`; 0 = ok
   int group_start();
   int group_end();
+  int close_group(int first_error, const char* where);   // GroupEnd even after an error inside the group, then abort
+  void abort();
   int all_reduce(void* buf, int64_t count, CommType t, cudaStream_t st);
   // fixed-size all-to-all: `count` elements to / from every rank
   int all_to_all(const void* send, void* recv, int64_t count, CommType t, cudaStream_t st);

@@ -32,6 +32,7 @@ struct ProfScope {
 #define PAMREC_PROF(name, n, st) ProfScope _prof_scope(name, n, st)
 
 // ---- kernels_encoder.cu
+int init_encoder_kernels(int max_T);   // per-device opt-in to > 48 KB dynamic shared memory (called by pamrec_bind)
 void launch_embed_fwd(const int* ih, const int* ch, const int* items, const int* cates, const float* item_w,
                       const float* cate_w, const float* pos, float* x0, float* tgt, int64_t n_rows, int T, cudaStream_t st);
 void launch_bucket_plan(const float* lt, int n, int* bucket, int* perm, int* ctl, int* tile_bucket, int* tile_begin,

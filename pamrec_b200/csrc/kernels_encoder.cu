@@ -220,8 +220,6 @@ void launch_proj_fwd(const float* X, const int* perm, const int* ctl, const int*
                      const float* ln_beta, const float* ln_gamma, float* QIN, float* Q, float* K, float* V,
                      cudaStream_t st) {
   PAMREC_PROF("proj_fwd", 1, st);
-  static bool once = false;
-  if (!once) { cudaFuncSetAttribute(k_proj_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjFwdSmem); once = true; }
   k_proj_fwd<<<max_tiles, kTokThreads, kProjFwdSmem, st>>>(X, perm, ctl, tile_bucket, tile_begin, tile_count, Wq, Wk, Wv,
                                                         ln_beta, ln_gamma, QIN, Q, K, V);
 }
@@ -331,9 +329,7 @@ void launch_attn_fwd(const float* Q, const float* K, const float* V, const float
                      int B, int T, cudaStream_t st) {
   PAMREC_PROF("attn_fwd", 1, st);
   if (B == 0) return;
-  static size_t smem_set = 0;
   const size_t smem = attn_fwd_smem(T);
-  if (smem > smem_set) { cudaFuncSetAttribute(k_attn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); smem_set = smem; }
   const int spb = attn_spb(T), threads = spb * attn_nw(T) * 32;
   k_attn_fwd<<<(B + spb - 1) / spb, threads, smem, st>>>(Q, K, V, QIN, mask, Y, ML, B, T);
 }
@@ -483,8 +479,6 @@ void launch_ffn_fwd(const float* Y, const float* W1, const float* b1, const floa
                     const float* ln_beta, const float* ln_gamma, float* OUT, int n_tok, cudaStream_t st) {
   PAMREC_PROF("ffn_fwd", 1, st);
   if (n_tok == 0) return;
-  static bool once = false;
-  if (!once) { cudaFuncSetAttribute(k_ffn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnFwdSmem); once = true; }
   k_ffn_fwd<<<(n_tok + kTokTile - 1) / kTokTile, kTokThreads, kFfnFwdSmem, st>>>(Y, W1, b1, W2, b2, ln_beta, ln_gamma, OUT, n_tok);
 }
 
@@ -711,8 +705,6 @@ void launch_ffn_bwd(const float* Y, const float* dOUT, const float* W1, const fl
                     float* db2, float* dbeta, float* dgamma, int n_tok, cudaStream_t st) {
   PAMREC_PROF("ffn_bwd", 1, st);
   if (n_tok == 0) return;
-  static bool once = false;
-  if (!once) { cudaFuncSetAttribute(k_ffn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnBwdSmem); once = true; }
   k_ffn_bwd<<<(n_tok + kTokTile - 1) / kTokTile, kTokThreads, kFfnBwdSmem, st>>>(Y, dOUT, W1, b1, W2, ln_beta, ln_gamma, dY, dW1,
                                                                              db1, dW2, db2, dbeta, dgamma, n_tok);
 }
@@ -821,9 +813,7 @@ void launch_attn_bwd(const float* Q, const float* K, const float* V, const float
                      const float* ML, const int* mask, float* dQ, float* dK, float* dV, int B, int T, cudaStream_t st) {
   PAMREC_PROF("attn_bwd", 1, st);
   if (B == 0) return;
-  static size_t smem_set = 0;
   const size_t smem = attn_bwd_smem(T);
-  if (smem > smem_set) { cudaFuncSetAttribute(k_attn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); smem_set = smem; }
   const int spb = attn_spb(T), threads = spb * attn_nw(T) * 32;
   k_attn_bwd<<<(B + spb - 1) / spb, threads, smem, st>>>(Q, K, V, dY, Y, QIN, ML, mask, dQ, dK, dV, B, T);
 }
@@ -957,10 +947,26 @@ void launch_proj_bwd(const float* X, const float* dY, const float* dQ, const flo
                      const float* Wq, const float* Wk, const float* Wv, const float* ln_beta, const float* ln_gamma,
                      float* dX, float* dWq, float* dWk, float* dWv, float* dbeta, float* dgamma, cudaStream_t st) {
   PAMREC_PROF("proj_bwd", 1, st);
-  static bool once = false;
-  if (!once) { cudaFuncSetAttribute(k_proj_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjBwdSmem); once = true; }
   k_proj_bwd<<<max_tiles, kTokThreads, kProjBwdSmem, st>>>(X, dY, dQ, dK, dV, perm, ctl, tile_bucket, tile_begin, tile_count, Wq,
                                                         Wk, Wv, ln_beta, ln_gamma, dX, dWq, dWk, dWv, dbeta, dgamma);
+}
+
+// Dynamic shared memory above 48 KB is an opt-in per kernel AND per device: pamrec_bind calls this on the handle's device, so
+// that no launcher keeps process-wide "already done" state (a second device in the same process gets its own opt-in).
+int init_encoder_kernels(int max_T) {
+  cudaError_t e = cudaSuccess;
+  auto set = [&](const void* fn, size_t bytes) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  };
+  set((const void*)k_proj_fwd, kProjFwdSmem);
+  set((const void*)k_ffn_fwd, kFfnFwdSmem);
+  set((const void*)k_ffn_bwd, kFfnBwdSmem);
+  set((const void*)k_proj_bwd, kProjBwdSmem);
+  size_t af = 0, ab = 0;
+  for (int T = 1; T <= max_T; ++T) { af = af > attn_fwd_smem(T) ? af : attn_fwd_smem(T); ab = ab > attn_bwd_smem(T) ? ab : attn_bwd_smem(T); }
+  set((const void*)k_attn_fwd, af);
+  set((const void*)k_attn_bwd, ab);
+  return e == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace pamrec

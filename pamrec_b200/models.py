@@ -114,13 +114,16 @@ class Saver:
         if save_path in self.kept:
             self.kept.remove(save_path)
         self.kept.append(save_path)
+        dropped = []
+        while len(self.kept) > self.max_to_keep:                 # every rank trims its list; rank 0 deletes the files
+            dropped.append(self.kept.pop(0))
         if eng.rank != 0:
             torch.distributed.barrier()                          # rank 0 finishes writing before anyone may restore
             return save_path
-        CK.remove(save_path)                                     # a path written earlier in another format
-        CK.save(save_path, variables, fmt=self.fmt, optimizer=optimizer)
-        while len(self.kept) > self.max_to_keep:
-            CK.remove(self.kept.pop(0))
+        CK.save(save_path, variables, fmt=self.fmt, optimizer=optimizer)   # tmp + os.replace: the old files stay valid until now
+        CK.remove(save_path, keep_fmt=self.fmt)                  # then a copy of this path written earlier in another format
+        for p in dropped:
+            CK.remove(p)
         with open(os.path.join(d, "checkpoint"), "w") as f:      # the CheckpointState text proto tf.train.latest_checkpoint reads
             f.write('model_checkpoint_path: "{}"\n'.format(os.path.basename(save_path)))
             for p in self.kept:
