@@ -33,8 +33,13 @@ WORKLOADS = {
     # configs[2]: 10 M items / 100 K categories, tables row-sharded over the ranks (also runs on one GPU)
     "sharded_10m_b1025_t50": dict(dataset="takatak", n_users=50000, n_items=10_000_000, n_cates=100_000, T=50, B=1025,
                                   tables="sharded", zipf=1.05),
+    # configs[4]: eval-only scoring of 1 positive + 99 negatives per impression (a "step" = one scoring batch of 40 impressions;
+    # e2e = run_weighted_eval over an 11-column text file with group = 100, sequential_base_model.py:437,456)
+    "eval_1p99": dict(dataset="takatak", n_users=50000, n_items=30000, n_cates=50, T=50, B=4000, kind="score", group=100,
+                      impressions=600),
 }
 METRIC = "train samples/sec"
+METRIC_SCORE = "scored samples/sec"
 N_POOL = 8            # distinct resident batches cycled through the timed steps
 
 
@@ -95,32 +100,58 @@ def build_model(w, tmp, sparse_adam="dense_exact", **extra):
     from pamrec_b200.models import PAMRECModel
     from pamrec_b200.sequential_iterator import SequentialIterator
     d = synth.write_vocab_only(tmp, w["dataset"], w["n_users"], w["n_items"], w["n_cates"])
-    hp = prepare_hparams(os.path.join(ROOT, "pamrec_b200", "config", "mmoe.yaml"), dataset=w["dataset"], bucket_num=10,
-                         add_feature=False, embed_l2=1e-6, layer_l2=1e-6, discrepancy_loss_weight=0.1, learning_rate=0.001,
-                         epochs=1, EARLY_STOP=5, is_clip_norm=1, batch_size=w["B"], show_step=10 ** 9, MODEL_DIR=os.path.join(tmp, "model/"),
-                         SUMMARIES_DIR=os.path.join(tmp, "summary/"), user_vocab=os.path.join(d, "user_vocab.pkl"),
-                         item_vocab=os.path.join(d, "item_vocab.pkl"), cate_vocab=os.path.join(d, "category_vocab.pkl"),
-                         train_num_ngs=0, max_seq_length=w["T"], pairwise_metrics=[], weighted_metrics=["wauc"], fuzhu_weight=0.5,
-                         fine_tune=False, eval_step=10 ** 9, noise_train_hist=0, noise_train_listwise=0, noise_only_predict=0,
-                         write_tfevents=False, sparse_adam=sparse_adam, **extra)
+    kw = dict(dataset=w["dataset"], bucket_num=10,
+              add_feature=False, embed_l2=1e-6, layer_l2=1e-6, discrepancy_loss_weight=0.1, learning_rate=0.001,
+              epochs=1, EARLY_STOP=5, is_clip_norm=1, batch_size=w["B"], show_step=10 ** 9, MODEL_DIR=os.path.join(tmp, "model/"),
+              SUMMARIES_DIR=os.path.join(tmp, "summary/"), user_vocab=os.path.join(d, "user_vocab.pkl"),
+              item_vocab=os.path.join(d, "item_vocab.pkl"), cate_vocab=os.path.join(d, "category_vocab.pkl"),
+              train_num_ngs=0, max_seq_length=w["T"], pairwise_metrics=[], weighted_metrics=["wauc"], fuzhu_weight=0.5,
+              fine_tune=False, eval_step=10 ** 9, noise_train_hist=0, noise_train_listwise=0, noise_only_predict=0,
+              write_tfevents=False, sparse_adam=sparse_adam)
+    kw.update(extra)
+    hp = prepare_hparams(os.path.join(ROOT, "pamrec_b200", "config", "mmoe.yaml"), **kw)
     return PAMRECModel(hp, SequentialIterator, seed=8)
 
 
 def flops_bytes(w):
-    """Algorithmic work per launch of the homogeneous launchers: name -> dict(flop, byte, pipe).
-    flop counts 2 per multiply-add of the minimal algorithm; byte = tensors that must be read + written once (fp32)."""
+    """Algorithmic work per STEP of every launcher: name -> dict(flop, byte, pipe, launches).
+    flop counts 2 per multiply-add of the minimal algorithm; byte = tensors that must be read + written once (fp32).
+    pipe: which unit the kernel's arithmetic runs on ("tensor" = 3xTF32 tensor-core MMAs, "fp32" = FFMA, "hbm" = no arithmetic
+    to speak of)."""
     B, T = w["B"], w["T"]
     N = B * T
     t = 160 * N                                  # bytes of one [N, 40] fp32 tensor
+    score = 2 * (40 * 20 + 20) * N               # attention-pooling MLP 40 -> 20 -> 1 over every position (pamrec.py:272-283)
+    mmoe = 2 * (5 * (40 * 100 + 100 * 64) + 2 * (40 * 64 + 64 * 5)) * B
+    tower = 2 * 3 * (84 * 100 + 100 * 64 + 64) * B
+    head_act = 4 * (N * 21 + B * (500 + 320 + 128 + 10 + 168 + 300 + 192 + 3))            # pre-activations written once
     return {
-        "attn_fwd": dict(flop=2 * (2 * T * T * 40) * B, byte=5 * t, pipe="fp32"),          # Q K^T, P V ; Q K V qin -> y
-        "attn_bwd": dict(flop=2 * (5 * T * T * 40) * B, byte=9 * t, pipe="fp32"),          # S, dP, dV, dQ, dK
-        "proj_fwd": dict(flop=2 * (3 * 1600) * N, byte=5 * t, pipe="tensor"),
-        "proj_bwd": dict(flop=2 * (6 * 1600) * N, byte=6 * t, pipe="tensor"),
-        "ffn_fwd": dict(flop=2 * (2 * 1600) * N, byte=2 * t, pipe="tensor"),
-        "ffn_bwd": dict(flop=2 * (5 * 1600) * N, byte=3 * t, pipe="tensor"),               # h recomputed + 2 dX + 2 dW GEMMs
-        "embed_fwd": dict(flop=0, byte=248 * N + 168 * B, pipe="hbm"),                      # 88 B read + 160 B written per lookup
+        "attn_fwd": dict(flop=2 * (2 * T * T * 40) * B * 2, byte=2 * 5 * t, pipe="fp32"),      # Q K^T, P V ; Q K V qin -> y  (x 2 blocks)
+        "attn_bwd": dict(flop=2 * (5 * T * T * 40) * B * 2, byte=2 * 9 * t, pipe="fp32"),      # S, dP, dV, dQ, dK
+        "proj_fwd": dict(flop=2 * (3 * 1600) * N * 2, byte=2 * 5 * t, pipe="tensor"),
+        "proj_bwd": dict(flop=2 * (6 * 1600) * N * 2, byte=2 * 6 * t, pipe="tensor"),
+        "ffn_fwd": dict(flop=2 * (2 * 1600) * N * 2, byte=2 * 2 * t, pipe="tensor"),
+        "ffn_bwd": dict(flop=2 * (5 * 1600) * N * 2, byte=2 * 3 * t, pipe="tensor"),           # h recomputed + 2 dX + 2 dW GEMMs
+        "embed_fwd": dict(flop=0, byte=248 * N + 168 * B, pipe="hbm"),                          # 88 B read + 160 B written per lookup
+        "dense_fwd": dict(flop=score + mmoe + tower, byte=t + head_act, pipe="fp32"),
+        "dense_dx": dict(flop=score + mmoe + tower, byte=t + 2 * head_act, pipe="fp32"),
+        "dense_dw": dict(flop=score + mmoe + tower, byte=t + 2 * head_act, pipe="fp32"),
+        "head_fwd": dict(flop=score + mmoe + tower, byte=t + head_act, pipe="fp32"),
+        "head_bwd": dict(flop=2 * (score + mmoe + tower), byte=2 * t + 3 * head_act, pipe="fp32"),
+        "sparse_segreduce": dict(flop=0, byte=96 * (N + B), pipe="hbm"),                       # 80 B gradient row + 16 B key / index per lookup
+        "sparse_scatter_adam": dict(flop=0, byte=96 * (N + B), pipe="hbm"),
+        "sparse_adam": dict(flop=0, byte=(6 * 64 + 4) * w["n_items"] + (6 * 16 + 4) * w["n_cates"] + 2 * (6 * 80 + 4) * w["n_users"], pipe="hbm"),
     }
+
+
+def step_work(w):
+    """Algorithmic flops and bytes of one whole step (sum of the launchers' minimal work, every tensor once): a training step, or
+    the forward pass of a scoring workload."""
+    fb = flops_bytes(w)
+    names = ("embed_fwd", "proj_fwd", "attn_fwd", "ffn_fwd", "head_fwd")
+    if w.get("kind") != "score":
+        names += ("head_bwd", "ffn_bwd", "attn_bwd", "proj_bwd", "sparse_scatter_adam", "sparse_adam")
+    return sum(fb[n]["flop"] for n in names), sum(fb[n]["byte"] for n in names)
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the `ncu --set full` capture of this workload
@@ -311,29 +342,7 @@ def run_ours(args, w, rank, world):
     tot = sum(ms for ms, _ in tab.values())
     kernels = {k: {"ms_per_step": ms / K, "share": ms / tot, "launches_per_step": n / K} for k, (ms, n) in
                sorted(tab.items(), key=lambda kv: -kv[1][0])}
-    fb = flops_bytes(w)
-    # dominant kernel = the most expensive launcher whose launches are all the same kernel on the same shapes
-    dom = next((k for k in kernels if k in fb), None)
-    roof = None
-    if dom:
-        per_launch_s = tab[dom][0] / tab[dom][1] / 1e3
-        wk = fb[dom]
-        tf, gb = wk["flop"] / per_launch_s / 1e12, wk["byte"] / per_launch_s / 1e9
-        fp32_peak = 148 * 128 * 2 * (clk["sm_max_mhz"] or 1965.0) * 1e6 / 1e12      # FFMA lanes x 2 flop x clock
-        if wk["pipe"] == "hbm" or tf / pk["tensor_sustained"] < gb / pk["hbm"]:
-            roof = {"kernel": dom, "bound": "hbm", "achieved": gb, "peak": pk["hbm"], "unit": "GB/s", "frac": gb / pk["hbm"],
-                    "traffic": None, "peak_source": pk["source"]}
-        else:
-            roof = {"kernel": dom, "bound": "tensor", "achieved": tf, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                    "frac": tf / pk["tensor_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained bf16"}
-        roof["traffic"] = NCU_TRAFFIC.get(args.workload, {}).get(dom)
-        roof["traffic_note"] = "bytes per launch, ncu --set full (profiles/r01e_ncu_encoder_full.csv); most of the written tensors stay in the 126 MB L2"
-        roof["also"] = {"algorithmic_GB_per_s": gb, "hbm_frac": gb / pk["hbm"], "algorithmic_TFLOP_per_s": tf,
-                        "fp32_ffma_peak_TFLOP_per_s": fp32_peak, "fp32_frac": tf / fp32_peak}
-        roof["note"] = ("3xTF32 mma.sync kernel: 3 tensor-core MMAs per algorithmic product; K = 40 GEMMs fused with LayerNorm epilogues "
-                        "are latency / issue bound, neither roofline binds" if wk["pipe"] == "tensor" else
-                        "fp32 FFMA kernel (thread per query row): tensor-pipe utilisation is 0, see also.fp32_frac"
-                        if wk["pipe"] == "fp32" else "")
+    roof, roof_step = rooflines(w, tab, K, total_ms / K, pk, clk, args.workload)
     hbm = hbm_microbench(pk, dev) if world == 1 else None
 
     out = {
@@ -349,29 +358,190 @@ def run_ours(args, w, rank, world):
                    "batch_note": "BASELINE batch 1024 rounded to 1025: batches must be multiples of 5",
                    "e2e_note": "PAMRECModel.train_async one step ahead (as fit_step runs): per step one pinned H2D of the feed, "
                                "the step, one D2H of its 5 losses"},
-        "e2e": e2e, "gpu_launches": int(launches) * K, "gpu_launches_per_step": int(launches), "clocks": clk, "roofline": roof, "roofline_hbm": hbm,
+        "e2e": e2e, "gpu_launches": int(launches) * K, "gpu_launches_per_step": int(launches), "clocks": clk, "roofline": roof,
+        "roofline_step": roof_step, "roofline_hbm": hbm,
         "kernels": kernels, "wall_s_timed_region": t_wall,
     }
     return out, model
 
 
-def cpu_baseline(w, seconds=20.0, rows=205):
+def rooflines(w, tab, K, ms_per_step, pk, clk, workload):
+    """`roofline` of the dominant launcher and `roofline_step` of the whole step.
+
+    The dominant launcher is the one with the largest share of the per-launcher device time.  It is judged against the unit its
+    arithmetic actually runs on: "hbm" kernels against the measured copy bandwidth, "tensor" kernels against the sustained bf16
+    dense peak (every algorithmic product costs three TF32 MMAs there, so frac counts useful flops only), FFMA kernels against
+    the fp32 FFMA peak (bound = "fp32": such a kernel can not reach either of the other two roofs and labelling it "hbm" hid
+    that in round 1)."""
+    fb = flops_bytes(w)
+    fp32_peak = 148 * 128 * 2 * (clk["sm_max_mhz"] or 1965.0) * 1e6 / 1e12      # FFMA lanes x 2 flop x clock
+    order = sorted(tab.items(), key=lambda kv: -kv[1][0])
+    dom = next((k for k, _ in order if k in fb), None)
+    roof = None
+    if dom:
+        wk = fb[dom]
+        launches_per_step = tab[dom][1] / K
+        per_step_s = tab[dom][0] / K / 1e3
+        per_launch_s = per_step_s / launches_per_step
+        tf, gb = wk["flop"] / per_step_s / 1e12, wk["byte"] / per_step_s / 1e9
+        if wk["pipe"] == "hbm":
+            roof = {"kernel": dom, "bound": "hbm", "achieved": gb, "peak": pk["hbm"], "unit": "GB/s", "frac": gb / pk["hbm"],
+                    "peak_source": pk["source"]}
+        elif wk["pipe"] == "tensor":
+            roof = {"kernel": dom, "bound": "tensor", "achieved": tf, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                    "frac": tf / pk["tensor_sustained"], "peak_source": pk["source"] + ", sustained bf16"}
+        else:
+            roof = {"kernel": dom, "bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak,
+                    "peak_source": "148 SMs x 128 FFMA lanes x 2 flop x max SM clock"}
+        roof["traffic"] = NCU_TRAFFIC.get(workload, {}).get(dom)
+        roof["launch_us"] = per_launch_s * 1e6
+        roof["launches_per_step"] = launches_per_step
+        roof["algorithmic_bytes_per_launch"] = wk["byte"] / launches_per_step
+        roof["algorithmic_flop_per_launch"] = wk["flop"] / launches_per_step
+        roof["also"] = {"algorithmic_GB_per_s": gb, "hbm_frac": gb / pk["hbm"], "algorithmic_TFLOP_per_s": tf,
+                        "fp32_frac": tf / fp32_peak, "tensor_frac": tf / pk["tensor_sustained"]}
+    flop, byte = step_work(w)
+    s_ = ms_per_step / 1e3
+    roof_step = {"algorithmic_GB_per_step": byte / 1e9, "algorithmic_GFLOP_per_step": flop / 1e9, "GB_per_s": byte / s_ / 1e9,
+                 "TFLOP_per_s": flop / s_ / 1e12, "hbm_frac": byte / s_ / 1e9 / pk["hbm"], "fp32_frac": flop / s_ / 1e12 / fp32_peak,
+                 "tensor_frac": flop / s_ / 1e12 / pk["tensor_sustained"],
+                 "note": "whole step: every tensor of the minimal algorithm read / written once, 2 flop per multiply-add; at this "
+                         "batch the step is bound by launch latency and occupancy, not by a roof"}
+    return roof, roof_step
+
+
+def score_batch(seed, w):
+    """One scoring batch in the eval layout: `group` consecutive rows (1 positive + group-1 negatives) share a history."""
+    from pamrec_b200 import synth
+    B, g = w["B"], w["group"]
+    a = synth.array_batch(seed, B // g, w["T"], w["n_users"], w["n_items"], w["n_cates"], grouped=False, zipf_a=w.get("zipf", 1.1))
+    rng = np.random.default_rng(seed + 1)
+    out = {k: np.repeat(a[k], g, axis=0) for k in ("item_history", "item_cate_history", "item_loop_times_history", "mask", "users")}
+    out["items"] = rng.integers(1, w["n_items"], size=B).astype(np.int32)
+    out["cates"] = rng.integers(1, w["n_cates"], size=B).astype(np.int32)
+    lab = np.zeros((B // g, g), np.float32); lab[:, 0] = 1.0
+    out["labels_satisfied"] = lab.reshape(B, 1)
+    out["labels_play"] = lab.reshape(B, 1).copy()
+    out["plays"] = (lab.reshape(B, 1) * 12.0).astype(np.float32)
+    return out
+
+
+def run_score(args, w, rank, world):
+    """BASELINE.json configs[4]: eval-only scoring, 1 positive + 99 negatives per impression.  value = forward passes (BN inference
+    mode) over resident batches, device-timed; e2e = run_weighted_eval (SBM:420-500) over an 11-column text file, host one batch
+    ahead of the device, including batching, H2D / D2H copies and the ranking metrics."""
+    from pamrec_b200 import synth
+    pk = peaks()
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    shared = os.path.join(tempfile.gettempdir(), "pamrec_bench_eval_" + os.environ.get("MASTER_PORT", str(os.getpid())))
+    os.makedirs(shared, exist_ok=True)
+    B, T, g = w["B"], w["T"], w["group"]
+    model = build_model(w, tempfile.mkdtemp(prefix="pamrec_bench_"), batch_size=B * world,
+                        pairwise_metrics=["mean_mrr", "ndcg@10", "hit@10", "group_auc"], weighted_metrics=["wauc"])
+    eng = model.engine
+    resident = [eng.upload(score_batch(1000 + 17 * i + rank, w), training=False) for i in range(N_POOL)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(torch.cuda.current_device()).start()
+    for i in range(W):
+        eng.forward(resident[i % N_POOL], training=False)
+    barrier()
+    evs = []
+    for i in range(K):
+        flush.fill_(i & 0xFF)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.forward(resident[i % N_POOL], training=False)
+        b.record()
+        evs.append((a, b))
+    barrier()
+    launches = eng.launches()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = B * world * K / (total_ms / 1e3)
+    # ---- e2e through the public scoring loop
+    path = os.path.join(shared, "test_data")
+    if rank == 0:
+        synth.write_eval_file(path, w["impressions"] * world, g - 1, T, w["n_users"], w["n_items"], w["n_cates"], seed=5)
+    barrier()
+    rows = w["impressions"] * world * g
+    res = model.run_weighted_eval(path, num_ngs=g - 1)           # first pass: tokenises the file (cached per file, IT:366-370)
+    barrier()
+    reps = max(1, -(-K * B * world // rows))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        res = model.run_weighted_eval(path, num_ngs=g - 1)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clk = clocks.stop()
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = resident[0].h2d_bytes
+    e2e = {"value": rows * reps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 * B,
+           "passes": reps, "rows_per_pass": rows, "metrics_of_last_pass": res}
+    eng.profile(True)
+    for i in range(K):
+        flush.fill_(i & 0xFF)
+        eng.forward(resident[i % N_POOL], training=False)
+    tab = eng.profile_table()
+    eng.profile(False)
+    tot = sum(ms for ms, _ in tab.values())
+    kernels = {k: {"ms_per_step": ms / K, "share": ms / tot, "launches_per_step": n / K} for k, (ms, n) in
+               sorted(tab.items(), key=lambda kv: -kv[1][0])}
+    roof, roof_step = rooflines(w, tab, K, total_ms / K, pk, clk, args.workload)
+    out = {
+        "metric": METRIC_SCORE, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "pamrec_b200",
+        "config": {"workload": args.workload, "batch_per_gpu": B, "seq_len": T, "group": g, "n_items": w["n_items"],
+                   "n_cates": w["n_cates"], "n_users": w["n_users"], "global_batch": B * world, "tables": eng.tables,
+                   "parallelism": "single GPU" if world == 1 else f"dp{world}: rows r, r + N, ... of every batch scored by rank r",
+                   "l2": "flushed between timed steps (256 MiB write)",
+                   "e2e_note": f"run_weighted_eval over a text file of {rows} lines ({w['impressions'] * world} impressions x {g}), batches of "
+                               f"{B * world} rows queued one ahead of the host, metrics auc / logloss / mean_mrr / ndcg@10 / hit@10 / group_auc / wauc included"},
+        "e2e": e2e, "gpu_launches": int(launches) * K, "gpu_launches_per_step": int(launches), "clocks": clk, "roofline": roof,
+        "roofline_step": roof_step, "kernels": kernels,
+    }
+    return out, model
+
+
+def sample_rows(w):
+    """Rows per CPU step: the whole batch when it fits the time budget (<= ~52 K tokens), else a bounded sample of whole groups."""
+    return w["B"] if w["B"] * w["T"] <= 52000 else max(5, (41000 // w["T"]) // 5 * 5)
+
+
+def cpu_baseline(w, seconds=20.0, rows=None):
     """The oracle port of the reference step (torch CPU fp32, all host threads) on a bounded sample of the workload."""
     from oracle import pamrec_oracle as O            # CPU baseline arm: the one place bench.py executes oracle/
     from pamrec_b200 import synth
     torch.set_num_threads(os.cpu_count() or 1)
+    rows = rows or sample_rows(w)
+    score = w.get("kind") == "score"
     om = O.OracleModel(w["n_users"], w["n_items"], w["n_cates"], w["T"], dtype=torch.float32)
-    feeds = [synth.array_batch(50 + i, rows, w["T"], w["n_users"], w["n_items"], w["n_cates"]) for i in range(4)]
+    feeds = [synth.array_batch(50 + i, rows, w["T"], w["n_users"], w["n_items"], w["n_cates"], grouped=not score) for i in range(4)]
     for f in feeds:
         f["mask"] = f["mask"].astype(np.int32); f["users"] = f["users"].astype(np.int32)
-    om.train_step(feeds[0])
+    step = om.eval_forward if score else om.train_step
+    step(feeds[0])
     n, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < seconds:
-        om.train_step(feeds[n % 4])
+        step(feeds[n % 4])
         n += 1
     dt = time.perf_counter() - t0
     return {"value": n * rows / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} steps of {rows} rows (T={w['T']}) of the same synthetic workload, {dt:.1f} s",
+            "sample": f"{n} {'scoring' if score else 'training'} steps of {rows} rows (T={w['T']}) of the same synthetic workload, {dt:.1f} s",
             "note": "restated CPU baseline (oracle/pamrec_oracle.py, torch CPU fp32): TF 2.4 is not installable offline"}
 
 
@@ -382,24 +552,28 @@ def run_reference(args, w, rank):
     from oracle import pamrec_oracle as O
     from pamrec_b200 import synth
     torch.set_num_threads(os.cpu_count() or 1)
-    rows = 205
+    rows = sample_rows(w)
+    score = w.get("kind") == "score"
     om = O.OracleModel(w["n_users"], w["n_items"], w["n_cates"], w["T"], dtype=torch.float32)
-    feeds = [synth.array_batch(50 + i, rows, w["T"], w["n_users"], w["n_items"], w["n_cates"]) for i in range(4)]
+    feeds = [synth.array_batch(50 + i, rows, w["T"], w["n_users"], w["n_items"], w["n_cates"], grouped=not score) for i in range(4)]
     for f in feeds:
         f["mask"] = f["mask"].astype(np.int32); f["users"] = f["users"].astype(np.int32)
+    step = om.eval_forward if score else om.train_step
     for i in range(args.warmup):
-        om.train_step(feeds[i % 4])
+        step(feeds[i % 4])
     t0 = time.perf_counter()
     for i in range(args.steps):
-        om.train_step(feeds[i % 4])
+        step(feeds[i % 4])
     dt = time.perf_counter() - t0
     v = args.steps * rows / dt
+    whole = rows == w["B"]
     cb = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-          "sample": f"each step = {rows} rows (41 listwise groups) of the {args.workload} workload"}
-    return {"metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "impl": "reference",
-            "config": {"workload": args.workload, "batch_per_step": rows, "seq_len": w["T"],
+          "sample": (f"each step = the whole {rows}-row batch" if whole else f"each step = {rows} rows (a bounded sample of the {w['B']}-row batch)")
+                    + f" of the {args.workload} workload"}
+    return {"metric": METRIC_SCORE if score else METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": args.workload, "batch_per_step": rows, "batch_per_gpu": w["B"], "seq_len": w["T"], "same_rows_as_gpu_arm": whole,
                        "note": "oracle port of the reference TF graph on host cores; TF 2.4 / tensorflow_ranking not installable offline"},
             "cpu_baseline": cb, "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
@@ -410,7 +584,7 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="pamrec_b200", choices=["pamrec_b200", "reference"])
     ap.add_argument("--workload", default="takatak_b1025_t50", choices=list(WORKLOADS))
@@ -438,7 +612,7 @@ def main():
         local = int(os.environ.get("LOCAL_RANK", rank))
         torch.cuda.set_device(local)
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
-    out, model = run_ours(args, w, rank, world)
+    out, model = (run_score if w.get("kind") == "score" else run_ours)(args, w, rank, world)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(w)

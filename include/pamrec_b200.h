@@ -178,6 +178,12 @@ int pamrec_bench_gather(PamrecHandle h, const int32_t* item_ids, const int32_t* 
                         const int32_t* tgt_cates, int64_t n_rows, int32_t T, float* out, void* stream);
 int pamrec_bench_table_adam(PamrecHandle h, int64_t step, void* stream);
 
+/* Test hooks.  PAMREC_DEBUG_SAVE_FFN_HIDDEN: pamrec_forward(training = 1) also stores relu(f W1 + b1) of encoder block 0 / 1 in
+ * the workspace tensors "d_Q" / "d_K" (backward-only scratch, overwritten by pamrec_backward), so that a checker can read the
+ * exact ReLU pattern of the point-wise FFN (pamrec.py:565-570).  Costs one extra [B,T,40] store per block; off by default. */
+#define PAMREC_DEBUG_SAVE_FFN_HIDDEN 1
+int pamrec_set_debug(PamrecHandle h, int flags);
+
 /* Per-launcher device timing: CUDA events recorded on the caller's stream around every launch while enabled.
  * Synchronise the stream, then read (name, accumulated ms, timed launches) per launcher. */
 int pamrec_profile_enable(PamrecHandle h, int on);

@@ -228,11 +228,30 @@ def _ln(x, beta, gamma):
 
 
 class _Ctx:
-    def __init__(self, p, bn_state, training, dtype):
+    def __init__(self, p, bn_state, training, dtype, relu_masks=None):
         self.p, self.bn_state, self.training, self.dtype = p, bn_state, training, dtype
         self.new_bn = {}
         self.t = {}          # named intermediates
         self.kink_margin = float("inf")   # smallest |BN output| in front of a ReLU over the [B, C] head layers (see _bn)
+        self.relu_masks = relu_masks or {}
+        self.relu_forced = 0              # units whose forced state differs from this forward pass's own sign
+
+
+def _act(ctx, y, key):
+    """ReLU, or - when the caller supplies the activation pattern of another forward pass under `key` - that pattern.
+
+    ReLU is not differentiable at 0.  Of the ~10^6 pre-activations of a step a few always lie inside the fp32 rounding of the
+    forward pass, so an fp32 implementation and this fp64 one can land on different sides; that unit's gradient then differs
+    at O(1) and, through the batch-norm statistics, every row's a little.  Neither is wrong: the gradient is only defined once
+    the side is fixed.  Parity tests therefore hand the implementation's own masks in (``relu_masks``: key -> bool array shaped
+    like y) and the gradient is taken of  y * mask,  the same piecewise-linear function on the same piece.  Forward values
+    change by at most the magnitude of the disputed pre-activations (~1e-7)."""
+    m = ctx.relu_masks.get(key)
+    if m is None:
+        return torch.relu(y)
+    m = torch.as_tensor(m).reshape(y.shape)
+    ctx.relu_forced += int((m != (y.detach() > 0)).sum())
+    return y * m.to(y.dtype)
 
 
 def _bn(ctx, z, scope):
@@ -263,7 +282,7 @@ def _mlp(ctx, x, prefix, sizes, out=False, tag=None):
         if tag:
             ctx.t[f"{tag}.z{i}"] = z
         bname = "batch_normalization" if i == 0 else f"batch_normalization_{i}"
-        h = torch.relu(_bn(ctx, z, f"{prefix}/nn_part/{bname}"))
+        h = _act(ctx, _bn(ctx, z, f"{prefix}/nn_part/{bname}"), f"{prefix}/nn_part/{bname}")
     if out:
         h = h @ ctx.p[f"{prefix}/nn_part/w_nn_output"] + ctx.p[f"{prefix}/nn_part/b_nn_output"]
     return h
@@ -297,10 +316,27 @@ def gather(p, batch):
     return g, rows
 
 
-def forward(p, bn_state, batch, training, rows=None, dtype=torch.float64):
+def _timeaware(x, table, bucket, proj):
+    """x[b,t,:] @ reshape(table[bucket[b,t]], (D, D))  (PAM:714-728).  proj="gather" materialises the [B,T,D,D] gather like the
+    reference's graph does (the CPU baseline keeps that cost shape); proj="grouped" multiplies the tokens of one bucket by
+    that bucket's matrix - the same sums, 1600 x less memory, which is what lets the fp64 check run at B = 4095, T = 200."""
+    B, T, _ = x.shape
+    if proj == "gather":
+        return torch.einsum("bti,btij->btj", x, table[bucket].reshape(B, T, D, D))
+    xf, bf = x.reshape(-1, D), bucket.reshape(-1)
+    order = torch.argsort(bf, stable=True)
+    counts = torch.bincount(bf, minlength=NB).tolist()
+    W = table.reshape(NB, D, D)
+    parts = [seg @ W[k] for k, seg in enumerate(torch.split(xf[order], counts)) if seg.shape[0]]
+    inv = torch.empty_like(order)
+    inv[order] = torch.arange(order.numel())
+    return torch.cat(parts, 0)[inv].reshape(B, T, D)
+
+
+def forward(p, bn_state, batch, training, rows=None, dtype=torch.float64, relu_masks=None, proj="gather"):
     """Returns ctx with .t = named intermediates (x0, blk{i}.{qin,Q,K,V,y,out}, h, z1, z2, att,
-    new_long, logits [B,3] = (logit, valid_logit, xilidu_logit), pred)."""
-    ctx = _Ctx(p, bn_state, training, dtype)
+    new_long, logits [B,3] = (logit, valid_logit, xilidu_logit), pred).  relu_masks: see _act."""
+    ctx = _Ctx(p, bn_state, training, dtype, relu_masks)
     if rows is None:
         _, rows = gather(p, batch)
     mask = torch.as_tensor(batch["mask"]).long()
@@ -315,18 +351,15 @@ def forward(p, bn_state, batch, training, rows=None, dtype=torch.float64):
     for b in range(2):                                                                 # PAM:516-543
         pre = f"sequential/pamrec/num_blocks_{b}/"
         qin = _ln(x, p[pre + "ln/Variable"], p[pre + "ln/Variable_1"])
-        Wq = p[pre + "self_attention/Q_timeaware_embedding"][bucket].reshape(B, T, D, D)   # PAM:714-717
-        Wk = p[pre + "self_attention/K_timeaware_embedding"][bucket].reshape(B, T, D, D)
-        Wv = p[pre + "self_attention/V_timeaware_embedding"][bucket].reshape(B, T, D, D)
-        Q = torch.einsum("bti,btij->btj", qin, Wq)                                     # PAM:726
-        K = torch.einsum("bti,btij->btj", x, Wk)                                       # PAM:727 (keys = un-normalised x)
-        V = torch.einsum("bti,btij->btj", x, Wv)
+        Q = _timeaware(qin, p[pre + "self_attention/Q_timeaware_embedding"], bucket, proj)   # PAM:714-717,726
+        K = _timeaware(x, p[pre + "self_attention/K_timeaware_embedding"], bucket, proj)     # PAM:727 (keys = un-normalised x)
+        V = _timeaware(x, p[pre + "self_attention/V_timeaware_embedding"], bucket, proj)
         S = Q @ K.transpose(1, 2) / (D ** 0.5)                                         # PAM:768-772
         S = torch.where(mask[:, None, :] == 0, torch.full_like(S, MASK_NEG), S)        # PAM:776-781
         Pm = torch.softmax(S, -1)                                                      # PAM:793
         y = Pm @ V + qin                                                               # PAM:804-810
         f = _ln(y, p[pre + "ln_1/Variable"], p[pre + "ln_1/Variable_1"])
-        hid = torch.relu(f @ p[pre + "multihead_attention/conv1d/kernel"][0] + p[pre + "multihead_attention/conv1d/bias"])
+        hid = _act(ctx, f @ p[pre + "multihead_attention/conv1d/kernel"][0] + p[pre + "multihead_attention/conv1d/bias"], f"blk{b}.ffn")
         out = hid @ p[pre + "multihead_attention/conv1d_1/kernel"][0] + p[pre + "multihead_attention/conv1d_1/bias"] + f  # PAM:565-577
         for k_, v_ in (("qin", qin), ("Q", Q), ("K", K), ("V", V), ("y", y), ("out", out)):
             t[f"blk{b}.{k_}"] = v_
@@ -336,9 +369,9 @@ def forward(p, bn_state, batch, training, rows=None, dtype=torch.float64):
     # attention pooling PAM:272-282
     sp = "sequential/pamrec/new_long/score_1"
     z1 = h @ p[sp + "/nn_part/w_nn_layer0"] + p[sp + "/nn_part/b_nn_layer0"]
-    a1 = torch.relu(_bn(ctx, z1, sp + "/nn_part/batch_normalization"))
+    a1 = _act(ctx, _bn(ctx, z1, sp + "/nn_part/batch_normalization"), sp + "/nn_part/batch_normalization")
     z2 = a1 @ p[sp + "/nn_part/w_nn_layer1"] + p[sp + "/nn_part/b_nn_layer1"]
-    s = torch.relu(_bn(ctx, z2, sp + "/nn_part/batch_normalization_1")).squeeze(-1)
+    s = _act(ctx, _bn(ctx, z2, sp + "/nn_part/batch_normalization_1"), sp + "/nn_part/batch_normalization_1").squeeze(-1)
     att = torch.softmax(torch.where(mask == 1, s, torch.full_like(s, MASK_NEG)), -1)
     new_long = (h * att[..., None]).sum(1)
     t["z1"], t["z2"], t["att"], t["new_long"] = z1, z2.squeeze(-1), att, new_long
@@ -445,6 +478,7 @@ class OracleModel:
         self.group_of = {n: g for n, _, _, g in self.spec}
         self.params, self.bn_state = self._init(seed)
         self.dtype = dtype
+        self.proj = "gather"             # "grouped": same sums without the [B,T,D,D] gather (see _timeaware)
         self.step = 0
         self.m = {n: torch.zeros_like(t, dtype=dtype) for n, t in self.params.items()}
         self.v = {n: torch.zeros_like(t, dtype=dtype) for n, t in self.params.items()}
@@ -459,8 +493,8 @@ class OracleModel:
     def _gather(self, p, batch):
         return gather(p, batch)
 
-    def _forward(self, p, batch, training, rows=None):
-        return forward(p, self.bn_state, batch, training, rows=rows, dtype=self.dtype)
+    def _forward(self, p, batch, training, rows=None, relu_masks=None):
+        return forward(p, self.bn_state, batch, training, rows=rows, dtype=self.dtype, relu_masks=relu_masks, proj=self.proj)
 
     def _losses(self, ctx, batch, rows):
         return compute_losses(ctx, batch, rows, self.hp)
@@ -479,14 +513,14 @@ class OracleModel:
             p = self.cast_params(False)
             return self._forward(p, batch, False)
 
-    def train_step(self, batch, apply=True, keep=()):
+    def train_step(self, batch, apply=True, keep=(), relu_masks=None):
         """One optimisation step (PAM:426-453).  Returns dict with losses, intermediates,
-        raw gradients (pre-clip) and the clip scales."""
+        raw gradients (pre-clip) and the clip scales.  relu_masks: activation pattern to differentiate on (see _act)."""
         hp, dtype = self.hp, self.dtype
         p = self.cast_params(True)
         g_idx, rows = self._gather(p, batch)
         rows = {k: v.detach().clone().requires_grad_(True) for k, v in rows.items()}
-        ctx = self._forward(p, batch, True, rows=rows)
+        ctx = self._forward(p, batch, True, rows=rows, relu_masks=relu_masks) if relu_masks else self._forward(p, batch, True, rows=rows)
         for k in keep:
             ctx.t[k].retain_grad()
         losses = self._losses(ctx, batch, rows)
@@ -524,7 +558,7 @@ class OracleModel:
             scales[name] = sc
 
         result = {"losses": {k: float(v.detach()) for k, v in losses.items()}, "t": ctx.t, "grads": grads, "scales": scales, "sqnorms": sqnorms,
-                  "new_bn": ctx.new_bn, "kink_margin": ctx.kink_margin}
+                  "new_bn": ctx.new_bn, "kink_margin": ctx.kink_margin, "relu_forced": ctx.relu_forced}
         if not apply:
             return result
 

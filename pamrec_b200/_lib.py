@@ -15,6 +15,7 @@ LOSS_XENT, LOSS_SOFTMAX = 0, 1
 COMM_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 GROUP = 5
+DEBUG_SAVE_FFN_HIDDEN = 1
 
 
 class PamrecConfig(C.Structure):
@@ -89,6 +90,7 @@ EXPORTS = {
     "pamrec_bench_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                       C.c_void_p, C.c_void_p]),
     "pamrec_bench_table_adam": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "pamrec_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "pamrec_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "pamrec_profile_reset": (C.c_int, [C.c_void_p]),
     "pamrec_profile_count": (C.c_int, [C.c_void_p]),

@@ -24,6 +24,7 @@ struct PamrecHandle_ {
   Layout L;
   PamrecBuffers buf;
   bool bound = false;
+  int debug = 0;                // PAMREC_DEBUG_* test hooks
   std::string err;
   int64_t launches = 0;
   Prof prof;
@@ -557,8 +558,9 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
                     h->P(o.wq), h->P(o.wk), h->P(o.wv), h->P(o.ln_a_beta), h->P(o.ln_a_gamma), h->wf(p + "qin"), h->wf(p + "Q"),
                     h->wf(p + "K"), h->wf(p + "V"), st);
     launch_attn_fwd(h->wf(p + "Q"), h->wf(p + "K"), h->wf(p + "V"), h->wf(p + "qin"), b->mask, h->wf(p + "y"), h->wf(p + "ml"), B, T, st);
+    float* hdbg = (training && (h->debug & PAMREC_DEBUG_SAVE_FFN_HIDDEN)) ? h->wf(k == 0 ? "d_Q" : "d_K") : nullptr;
     launch_ffn_fwd(h->wf(p + "y"), h->P(o.w1), h->P(o.b1), h->P(o.w2), h->P(o.b2), h->P(o.ln_b_beta), h->P(o.ln_b_gamma),
-                   h->wf(p + "out"), N, st);
+                   h->wf(p + "out"), hdbg, N, st);
     nl += 3;
     xin = h->wf(p + "out");
   }
@@ -994,6 +996,11 @@ int pamrec_bench_table_adam(PamrecHandle h, int64_t step, void* stream) {
   return check_cuda(h, "bench_table_adam");
 }
 
+int pamrec_set_debug(PamrecHandle h, int flags) {
+  if (!h) return -1;
+  h->debug = flags;
+  return 0;
+}
 int pamrec_profile_enable(PamrecHandle h, int on) {
   if (!h) return -1;
   h->prof.on = on != 0;

@@ -43,7 +43,7 @@ void launch_proj_fwd(const float* X, const int* perm, const int* ctl, const int*
 void launch_attn_fwd(const float* Q, const float* K, const float* V, const float* QIN, const int* mask, float* Y, float* ML,
                      int B, int T, cudaStream_t st);
 void launch_ffn_fwd(const float* Y, const float* W1, const float* b1, const float* W2, const float* b2,
-                    const float* ln_beta, const float* ln_gamma, float* OUT, int n_tok, cudaStream_t st);
+                    const float* ln_beta, const float* ln_gamma, float* OUT, float* Hdbg, int n_tok, cudaStream_t st);
 void launch_ffn_bwd(const float* Y, const float* dOUT, const float* W1, const float* b1, const float* W2,
                     const float* ln_beta, const float* ln_gamma, float* dY, float* dW1, float* db1, float* dW2,
                     float* db2, float* dbeta, float* dgamma, int n_tok, cudaStream_t st);

@@ -411,7 +411,7 @@ constexpr int kFfnFwdSmem = (4 * kDD + 2 * kTokTile * kTS + 4 * kD) * 4;
 __global__ void __launch_bounds__(kTokThreads)
 k_ffn_fwd(const float* __restrict__ Y, const float* __restrict__ W1, const float* __restrict__ b1,
           const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ ln_beta,
-          const float* __restrict__ ln_gamma, float* __restrict__ OUT, int n_tok) {
+          const float* __restrict__ ln_gamma, float* __restrict__ OUT, float* __restrict__ Hdbg, int n_tok) {
   extern __shared__ __align__(16) float sm[];
   uint32_t* W1hi = reinterpret_cast<uint32_t*>(sm);
   uint32_t* W1lo = W1hi + kDD;
@@ -454,6 +454,12 @@ k_ffn_fwd(const float* __restrict__ Y, const float* __restrict__ W1, const float
       *reinterpret_cast<float2*>(hw + (r + 8) * kTS + col) = make_float2(fmaxf(c[mt][nt][2], 0.f), fmaxf(c[mt][nt][3], 0.f));
     }
   __syncwarp();
+  if (Hdbg != nullptr) {                        // test hook (PAMREC_DEBUG_SAVE_FFN_HIDDEN): the hidden activations as computed here
+    for (int i = lane; i < kWarpRows * kD; i += 32) {
+      const int r = i / kD, col = i % kD;
+      if (kWarpRows * w + r < cnt) Hdbg[(tok0 + kWarpRows * w + r) * kD + col] = hw[r * kTS + col];
+    }
+  }
 #pragma unroll
   for (int mt = 0; mt < kMT; ++mt)
 #pragma unroll
@@ -476,10 +482,10 @@ k_ffn_fwd(const float* __restrict__ Y, const float* __restrict__ W1, const float
 }
 
 void launch_ffn_fwd(const float* Y, const float* W1, const float* b1, const float* W2, const float* b2,
-                    const float* ln_beta, const float* ln_gamma, float* OUT, int n_tok, cudaStream_t st) {
+                    const float* ln_beta, const float* ln_gamma, float* OUT, float* Hdbg, int n_tok, cudaStream_t st) {
   PAMREC_PROF("ffn_fwd", 1, st);
   if (n_tok == 0) return;
-  k_ffn_fwd<<<(n_tok + kTokTile - 1) / kTokTile, kTokThreads, kFfnFwdSmem, st>>>(Y, W1, b1, W2, b2, ln_beta, ln_gamma, OUT, n_tok);
+  k_ffn_fwd<<<(n_tok + kTokTile - 1) / kTokTile, kTokThreads, kFfnFwdSmem, st>>>(Y, W1, b1, W2, b2, ln_beta, ln_gamma, OUT, Hdbg, n_tok);
 }
 
 // ------------------------------------------------------------------------------------------

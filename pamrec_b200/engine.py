@@ -69,6 +69,21 @@ class PendingLosses:
         return self._value
 
 
+class PendingHost:
+    """A queued device->host copy (Engine.to_host_async)."""
+
+    def __init__(self, slot, n):
+        self._slot, self._n, self._value = slot, n, None
+
+    def result(self):
+        if self._value is None:
+            self._slot["event"].synchronize()
+            self._value = self._slot["host"][:self._n].numpy().copy()
+            self._slot["owner"] = None
+            self._slot = None
+        return self._value
+
+
 class Engine:
     def __init__(self, n_users, n_items, n_cates, max_seq_len, max_batch, hp=None, sparse_adam="dense_exact",
                  world_size=1, rank=0, tables=None):
@@ -409,6 +424,31 @@ class Engine:
         slot["event"].record(torch.cuda.current_stream(self.device))
         slot["owner"] = PendingLosses(slot)
         return slot["owner"]
+
+    def to_host_async(self, dev_tensor):
+        """Queue a device->host copy of a float32 device tensor into a pinned ring slot; ``.result()`` waits and returns numpy."""
+        n = dev_tensor.numel()
+        if not hasattr(self, "_host_ring"):
+            self._host_ring, self._host_i = [], 0
+        if len(self._host_ring) < 4:
+            self._host_ring.append(dict(host=torch.empty(max(n, self.dims[4] * max(self.world, 1)), dtype=torch.float32).pin_memory(),
+                                        event=torch.cuda.Event(), owner=None))
+            slot = self._host_ring[-1]
+        else:
+            slot = self._host_ring[self._host_i]
+            self._host_i = (self._host_i + 1) % len(self._host_ring)
+            if slot["owner"] is not None:
+                slot["owner"].result()
+        if slot["host"].numel() < n:
+            slot["host"] = torch.empty(n, dtype=torch.float32).pin_memory()
+        slot["host"][:n].copy_(dev_tensor.reshape(-1), non_blocking=True)
+        slot["event"].record(torch.cuda.current_stream(self.device))
+        slot["owner"] = PendingHost(slot, n)
+        return slot["owner"]
+
+    def set_debug(self, flags):
+        """Test hooks (include/pamrec_b200.h: PAMREC_DEBUG_*)."""
+        self._check(self.lib.pamrec_set_debug(self.handle, int(flags)))
 
     def profile(self, on=True):
         self._check(self.lib.pamrec_profile_enable(self.handle, int(on)))

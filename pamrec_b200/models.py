@@ -229,24 +229,44 @@ class SequentialBaseModel(BaseModel):
         super().__init__(hparams, iterator_creator, graph=graph, seed=seed)
 
     # ------------------------------------------------------------------ device steps
-    def _score(self, feed_dict):
+    def _score_async(self, feed_dict):
+        """Queue the scoring of one batch: staged H2D copy, forward pass (BN inference mode), D2H copy of the predictions into a
+        pinned ring slot.  Returns a handle whose ``result()`` waits for that copy and gives pred [B,1]: the eval loops queue
+        batch i + 1 before they read batch i, the way train_async pipelines sess.run (SBM:437-447 blocks per batch)."""
         eng = self.engine
+        n = None
         if isinstance(feed_dict, LocalFeed):
             # the iterator already dealt this rank its rows (r, r + W, ...) of a batch of global_rows rows
             n = feed_dict.global_rows
             db = eng.upload(feed_dict, training=False, staged=True, global_batch=n)
-            full = torch.zeros(n, dtype=torch.float32, device=eng.device)
-            full[eng.rank::eng.world] = eng.forward(db, training=False)
-            return eng.all_reduce_(full).cpu().numpy().reshape(-1, 1)
-        if eng.world > 1 and self.feed_is_global:
+        elif eng.world > 1 and self.feed_is_global:
             # data-parallel scoring: rank r scores rows r, r + W, ... of the batch; the scores are summed back into place
             local, n = D.split_feed(feed_dict, eng.world, eng.rank, grouped=False)
             db = eng.upload(local, training=False, staged=True, global_batch=n)
+        else:
+            db = eng.upload(feed_dict, training=False, staged=True)
+        pred = eng.forward(db, training=False)
+        if n is not None:
             full = torch.zeros(n, dtype=torch.float32, device=eng.device)
-            full[eng.rank::eng.world] = eng.forward(db, training=False)
-            return eng.all_reduce_(full).cpu().numpy().reshape(-1, 1)
-        db = eng.upload(feed_dict, training=False, staged=True)
-        return eng.forward(db, training=False).cpu().numpy().reshape(-1, 1)
+            full[eng.rank::eng.world] = pred
+            pred = eng.all_reduce_(full)
+        return eng.to_host_async(pred)
+
+    def _score(self, feed_dict):
+        return self._score_async(feed_dict).result().reshape(-1, 1)
+
+    def _scored(self, filename, **kw):
+        """(feed, pred [B,1]) over a file with the device one batch ahead of the host."""
+        pending = None
+        for feed in Prefetcher(self.iterator.load_data_from_file(filename, batch_num_ngs=0, **kw)):
+            if not feed:
+                continue
+            queued = (feed, self._score_async(feed))
+            if pending is not None:
+                yield pending[0], pending[1].result().reshape(-1, 1)
+            pending = queued
+        if pending is not None:
+            yield pending[0], pending[1].result().reshape(-1, 1)
 
     @staticmethod
     def _labels_users(feed_dict):
@@ -360,13 +380,12 @@ class SequentialBaseModel(BaseModel):
         """SBM:380-413."""
         preds, labels, group_preds, group_labels = [], [], [], []
         group = num_ngs + 1
-        for feed in Prefetcher(self.iterator.load_data_from_file(filename, min_seq_length=self.min_seq_length, batch_num_ngs=0)):
-            if feed:
-                step_pred, step_labels = self.eval(self.sess, feed)
-                preds.extend(np.reshape(step_pred, -1))
-                labels.extend(np.reshape(step_labels, -1))
-                group_preds.extend(np.reshape(step_pred, (-1, group)))
-                group_labels.extend(np.reshape(step_labels, (-1, group)))
+        for feed, step_pred in self._scored(filename, min_seq_length=self.min_seq_length):
+            step_labels = np.asarray(self._labels_users(feed)[0], np.float32).reshape(-1, 1)
+            preds.extend(np.reshape(step_pred, -1))
+            labels.extend(np.reshape(step_labels, -1))
+            group_preds.extend(np.reshape(step_pred, (-1, group)))
+            group_labels.extend(np.reshape(step_labels, (-1, group)))
         res = cal_metric(labels, preds, self.hparams.metrics)
         res.update(cal_metric(group_labels, group_preds, self.hparams.pairwise_metrics))
         return res
@@ -378,18 +397,17 @@ class SequentialBaseModel(BaseModel):
             raise NotImplementedError("alpha outputs belong to the CLSR models, not to PAMRec (SBM:518-532)")
         users, preds, labels, group_preds, group_labels = [], [], [], [], []
         group = num_ngs + 1
-        for feed in Prefetcher(self.iterator.load_data_from_file(filename, min_seq_length=self.min_seq_length, batch_num_ngs=0)):
-            if not feed:
-                continue
-            step_user, step_pred, step_labels = self.eval_with_user(self.sess, feed)
-            users.extend(np.reshape(step_user, -1))
+        for feed, step_pred in self._scored(filename, min_seq_length=self.min_seq_length):
+            step_labels, step_user = self._labels_users(feed)
+            step_labels = np.asarray(step_labels, np.float32).reshape(-1, 1)
+            users.extend(np.reshape(np.asarray(step_user).astype(np.int32), -1))
             preds.extend(np.reshape(step_pred, -1))
             labels.extend(np.reshape(step_labels, -1))
             gp = np.reshape(step_pred, (-1, group))
-            for i, ag in enumerate(np.reshape(step_labels, (-1, group))):
-                if sum(ag) != 0:
-                    group_preds.append(gp[i])
-                    group_labels.append(ag)
+            gl = np.reshape(step_labels, (-1, group))
+            keep = gl.sum(axis=1) != 0                           # SBM:456-460: groups without a positive are dropped
+            group_preds.extend(gp[keep])
+            group_labels.extend(gl[keep])
         users, preds, labels = filter_single_class_users(users, preds, labels)
         res = cal_metric(labels, preds, self.hparams.metrics)
         res.update(cal_metric(group_labels, group_preds, self.hparams.pairwise_metrics))
@@ -401,12 +419,11 @@ class SequentialBaseModel(BaseModel):
         writer = self.engine.rank == 0
         wt = open(outfile_name, "w") if writer else None
         try:
-            for feed in Prefetcher(self.iterator.load_data_from_file(infile_name, batch_num_ngs=0)):
-                if feed:
-                    step_pred = np.reshape(self.infer(self.sess, feed), -1)
-                    if writer:
-                        wt.write("\n".join(map(str, step_pred)))
-                        wt.write("\n")
+            for _, step_pred in self._scored(infile_name):
+                step_pred = np.reshape(step_pred, -1)
+                if writer:
+                    wt.write("\n".join(map(str, step_pred)))
+                    wt.write("\n")
         finally:
             if wt:
                 wt.close()

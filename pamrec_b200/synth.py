@@ -155,3 +155,29 @@ def write_vocab_only(root, dataset, n_users, n_items, n_cates):
     with open(os.path.join(d, f"{dataset}_business_recommenders.csv"), "w") as f:
         f.write("1\t1\t10.0\n")
     return d
+
+
+def write_eval_file(path, n_impressions, n_neg, T, n_users, n_items, n_cates, seed=5, zipf_a=1.1):
+    """An 11-column eval file (io/sequential_iterator.py:231-268) with one positive line followed by `n_neg` negative lines per
+    impression, all sharing the impression's history of up to T items - the layout run_weighted_eval(num_ngs=n_neg) expects
+    (sequential_base_model.py:437,456).  Token i is vocabulary index i (write_vocab_only / generate)."""
+    rng = np.random.default_rng(seed)
+    join = lambda a, fmt="{}": ",".join(fmt.format(x) for x in a)
+    with open(path, "w") as f:
+        for _ in range(n_impressions):
+            L = int(rng.integers(max(1, T // 2), T + 1))
+            items = _zipf(rng, zipf_a, L, max(n_items - 1, 1))
+            cates = _zipf(rng, zipf_a, L, max(n_cates - 1, 1))
+            durs = rng.integers(5, 61, size=L).astype(np.float64)
+            plays_ms = np.maximum((rng.random(L) * 2.0 * durs * 1000).astype(np.int64), 1)
+            sats = (plays_ms / 1000.0 >= durs).astype(np.int64)
+            hist = "\t".join([join(items), join(cates), join(durs, "{:.1f}"), join(sats), join(plays_ms)])
+            u = int(rng.integers(1, n_users))
+            tgt = rng.integers(1, n_items, size=n_neg + 1)
+            tc = rng.integers(1, n_cates, size=n_neg + 1)
+            lines = []
+            for k in range(n_neg + 1):
+                lab, play = ("1", "15000") if k == 0 else ("0", "0")
+                lines.append("\t".join([lab, play, str(u), str(tgt[k]), str(tc[k]), "20.0", hist]))
+            f.write("\n".join(lines) + "\n")
+    return path

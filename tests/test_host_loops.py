@@ -52,6 +52,10 @@ class StubEngine(E.Engine):
         losses = self.train_step(db).numpy()
         return types.SimpleNamespace(result=lambda: losses)
 
+    def to_host_async(self, dev_tensor):
+        value = dev_tensor.numpy().copy()
+        return types.SimpleNamespace(result=lambda: value)
+
     def forward(self, db, training=False, want_pred=True):
         self.calls["forward"] += 1
         f = db.feed
