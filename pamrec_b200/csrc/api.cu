@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "comm.h"
+#include "headcoop.h"
 #include "kernels.h"
 #include "layout.h"
 
@@ -48,6 +49,13 @@ struct PamrecHandle_ {
   void* mbox_peer[kP2PMaxWorld] = {};
   bool mbox_open = false;
   uint32_t mbox_epoch[kP2PSlots] = {};
+  // persistent cooperative head kernels (kernels_headcoop.cu): device-resident programs, barrier words, grid size
+  HeadProgram* prog_fwd = nullptr;
+  HeadProgram* prog_bwd = nullptr;
+  unsigned* head_bar = nullptr;
+  int coop_grid = 0;
+  uint32_t coop_epoch = 0;          // mailbox epoch of the cooperative kernels (one per launch, all ranks in lockstep)
+  bool use_coop() const { return coop_grid > 0 && prog_fwd && (cfg.world_size == 1 || mbox_open); }
   double* mbox_slots(int p) const { return static_cast<double*>(mbox_peer[p]); }
   uint32_t* mbox_flags(int p) const {
     return reinterpret_cast<uint32_t*>(static_cast<char*>(mbox_peer[p]) + (size_t)kP2PSlots * cfg.world_size * kP2PMaxDoubles * sizeof(double));
@@ -58,6 +66,9 @@ struct PamrecHandle_ {
     for (int p = 0; p < kP2PMaxWorld; ++p)
       if (mbox_peer[p] && mbox_peer[p] != mbox) cudaIpcCloseMemHandle(mbox_peer[p]);
     if (mbox) cudaFree(mbox);
+    if (prog_fwd) cudaFree(prog_fwd);
+    if (prog_bwd) cudaFree(prog_bwd);
+    if (head_bar) cudaFree(head_bar);
     for (auto e : ev_side) if (e) cudaEventDestroy(e);
     if (ev_join) cudaEventDestroy(ev_join);
     if (ev_plan) cudaEventDestroy(ev_plan);
@@ -252,6 +263,9 @@ static BnSet make_bn(PamrecHandle h, int id, const char* name) {
   return s;
 }
 
+static int build_head_programs(PamrecHandle h, cudaStream_t st);
+static HeadDyn head_dyn(PamrecHandle h, const PamrecBatch* b, bool training, int slot0);
+
 int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
   if (!h || !bufs) return -1;
   cudaStream_t st = (cudaStream_t)stream;
@@ -283,6 +297,7 @@ int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
     return fail(h, "cudaMallocHost for the exchange counts failed");
   cudaMemcpyAsync(h->wi("seg_id"), h->h_seg_id.data(), h->h_seg_id.size() * 4, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(h->wi("seg_tab"), h->h_seg_tab.data(), h->h_seg_tab.size() * 4, cudaMemcpyHostToDevice, st);
+  if (int rc = build_head_programs(h, st)) return rc;
   cudaStreamSynchronize(st);
   h->bound = true;
   return check_cuda(h, "bind");
@@ -566,6 +581,13 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
   }
   const float* H = xin;
   BnSet* bn = h->bn;
+  if (h->use_coop()) {
+    // the whole head as ONE persistent cooperative kernel (kernels_headcoop.cu)
+    HeadDyn d = head_dyn(h, b, training != 0, 0);
+    if (launch_head_program(h->prog_fwd, d, h->coop_grid, training ? "head_fwd" : "head_score", st)) return check_cuda(h, "cooperative head launch");
+    if (pred_out) launch_sigmoid_col0(h->wf("logits"), pred_out, B, st);
+    return check_cuda(h, "forward");
+  }
   if (!training) {
     for (int i = 0; i < BN_COUNT; ++i) launch_bn_eval_stat(bn[i], st);
     nl += BN_COUNT;
@@ -654,6 +676,241 @@ static void dx_add(DenseDxP& p, int slice, int out_off, int dz_off, int64_t w_of
   p.dz_off[slice][c] = dz_off; p.w_off[slice][c] = w_off; p.Ncon[slice][c] = N;
 }
 
+// per-call values of the cooperative head kernels; slot0 = first mailbox slot of this kernel's barriers
+static HeadDyn head_dyn(PamrecHandle h, const PamrecBatch* b, bool training, int slot0) {
+  HeadDyn d;
+  memset(&d, 0, sizeof d);
+  const int W = h->cfg.world_size;
+  d.B = b->batch; d.T = h->cfg.max_seq_len; d.training = training ? 1 : 0; d.world = W; d.rank = h->cfg.rank;
+  d.Bg = b->global_batch > 0 ? b->global_batch : b->batch * W;
+  d.cntN = (double)d.Bg * d.T; d.cntB = (double)d.Bg;
+  d.mask = b->mask; d.y_sat = b->labels_satisfied; d.y_play = b->labels_play; d.plays = b->plays;
+  d.fuzhu_w = h->cfg.fuzhu_weight; d.order_w = h->cfg.order_weight;
+  d.sm_group = h->cfg.loss_kind == PAMREC_LOSS_SOFTMAX ? h->cfg.softmax_group : 0;
+  d.bar = h->head_bar;
+  if (W > 1) {
+    for (int p = 0; p < W; ++p) { d.peer_slots[p] = h->mbox_slots(p); d.peer_flags[p] = h->mbox_flags(p); }
+    d.p2p_epoch = ++h->coop_epoch; d.p2p_slot0 = slot0; d.p2p_err = h->mbox_err();
+  }
+  return d;
+}
+
+// The two programs of the persistent head kernels: the same layer descriptions as the stand-alone launch sequence further
+// down (which stays as the PAMREC_HEAD_LEGACY=1 path), grouped into barrier-separated phases.
+static int build_head_programs(PamrecHandle h, cudaStream_t st) {
+  static_assert(BN_S1 == BN_S1_ && BN_E1 == BN_E1_ && BN_G1 == BN_G1_ && BN_COUNT == BN_COUNT_, "headcoop.h mirrors layout.h:BnId");
+  if (getenv("PAMREC_HEAD_LEGACY") != nullptr) { h->coop_grid = 0; return 0; }
+  if (h->cfg.world_size > kP2PMaxWorld) { h->coop_grid = 0; return 0; }
+  int per_sm = 0;
+  const int grid = head_program_grid(&per_sm);
+  if (grid <= 0) { cudaGetLastError(); h->coop_grid = 0; return 0; }   // no cooperative launch on this device: stand-alone kernels
+  const Layout& L = h->L;
+  BnSet* bn = h->bn;
+  const float* Pb = h->buf.dense_param;
+  const float gs = 1.0f / (float)h->cfg.world_size;
+  std::vector<HeadPhase> F, K;
+  auto phase = [](int op, int rows_n) { HeadPhase p; memset(&p, 0, sizeof p); p.op = op; p.rows_n = rows_n; return p; };
+  auto fin = [](HeadPhase& p, std::initializer_list<int> ids, int rows_n) {
+    p.barrier = 1; p.fin_rows_n = rows_n;
+    for (int id : ids) { p.fin[p.n_fin++] = id; p.sync[p.n_sync++] = id; }
+  };
+  auto grad_of = [&](int id, const float* Z) {
+    BnGrad g; g.Z = Z; g.stat = bn[id].stat; g.gamma = bn[id].gamma; g.beta = bn[id].beta; g.bsums = bn[id].bsums; g.count = 0.0;
+    return g;
+  };
+  auto out_of = [&](int id, const float* Z) {
+    BnGradOut o; o.Z = Z; o.stat = bn[id].stat; o.gamma = bn[id].gamma; o.beta = bn[id].beta; o.bsums = bn[id].bsums;
+    return o;
+  };
+  auto dw_bn = [&](DenseDwP& w, int id, const float* Z) {
+    w.g = grad_of(id, Z); w.g_dgamma = bn[id].dgamma; w.g_dbeta = bn[id].dbeta; w.g_C = bn[id].C; w.g_scale = gs;
+  };
+  const float* H = h->wf("blk1.out");
+  // ------------------------------------------------------------------ forward
+  {
+    HeadPhase p = phase(HEAD_OP_NONE, 0); p.only = 2; p.barrier = 1; p.eval_stats = 1; F.push_back(p);
+  }
+  {
+    HeadPhase p = phase(HEAD_OP_DENSE_FWD, 1);
+    p.u.f = dense_p(H, kD, 0, 1, kD, 20, h->P(L.score.w0), 0, h->P(L.score.b0), 0, h->wf("z1"), 20);
+    p.u.f.out_sums = bn[BN_S0].sums;
+    fin(p, {BN_S0}, 1); p.sync_scalars = 1; F.push_back(p);
+    HeadPhase q = phase(HEAD_OP_DENSE_FWD, 1);
+    q.u.f = dense_p(h->wf("z1"), 20, 0, 1, 20, 1, h->P(L.score.w1), 0, h->P(L.score.b1), 0, h->wf("z2"), 1);
+    set_in_bn(q.u.f, bn[BN_S0]); q.u.f.out_sums = bn[BN_S1].sums;
+    fin(q, {BN_S1}, 1); F.push_back(q);
+    HeadPhase r = phase(HEAD_OP_POOL_FWD, 0);
+    r.u.pl.H = H; r.u.pl.Z2 = h->wf("z2"); r.u.pl.new_long = h->wf("new_long");
+    r.barrier = 1; F.push_back(r);
+  }
+  {
+    HeadPhase e0 = phase(HEAD_OP_DENSE_FWD, 0);
+    e0.u.f = dense_p(h->wf("new_long"), kD, 0, 5, kD, 100, h->P(L.expert.w0), 4000, h->P(L.expert.b0), 100, h->wf("ze0"), 500);
+    for (int g = 0; g < 5; ++g) { e0.u.f.x_off[g] = 0; e0.u.f.z_off[g] = g * 100; }
+    e0.u.f.out_sums = bn[BN_E0].sums; F.push_back(e0);
+    HeadPhase g0 = phase(HEAD_OP_DENSE_FWD, 0);
+    g0.u.f = dense_p(h->wf("new_long"), kD, 0, 2, kD, 64, h->P(L.gate.w0), 2560, h->P(L.gate.b0), 64, h->wf("zg0"), 128);
+    for (int g = 0; g < 2; ++g) { g0.u.f.x_off[g] = 0; g0.u.f.z_off[g] = g * 64; }
+    g0.u.f.out_sums = bn[BN_G0].sums;
+    fin(g0, {BN_E0, BN_G0}, 0); F.push_back(g0);
+    HeadPhase e1 = phase(HEAD_OP_DENSE_FWD, 0);
+    e1.u.f = dense_p(h->wf("ze0"), 500, 0, 5, 100, 64, h->P(L.expert.w1), 6400, h->P(L.expert.b1), 64, h->wf("ze1"), 320);
+    for (int g = 0; g < 5; ++g) { e1.u.f.x_off[g] = g * 100; e1.u.f.z_off[g] = g * 64; }
+    set_in_bn(e1.u.f, bn[BN_E0]); e1.u.f.out_sums = bn[BN_E1].sums; F.push_back(e1);
+    HeadPhase g1 = phase(HEAD_OP_DENSE_FWD, 0);
+    g1.u.f = dense_p(h->wf("zg0"), 128, 0, 2, 64, 5, h->P(L.gate.w1), 320, h->P(L.gate.b1), 5, h->wf("zg1"), 10);
+    for (int g = 0; g < 2; ++g) { g1.u.f.x_off[g] = g * 64; g1.u.f.z_off[g] = g * 5; }
+    set_in_bn(g1.u.f, bn[BN_G0]); g1.u.f.out_sums = bn[BN_G1].sums;
+    fin(g1, {BN_E1, BN_G1}, 0); F.push_back(g1);
+    HeadPhase c = phase(HEAD_OP_COMBINE_FWD, 0);
+    c.u.cb.ZE1 = h->wf("ze1"); c.u.cb.ZG1 = h->wf("zg1"); c.u.cb.tgt = h->wf("tgt"); c.u.cb.U = h->wf("u");
+    c.barrier = 1; F.push_back(c);
+  }
+  {
+    HeadPhase t0 = phase(HEAD_OP_DENSE_FWD, 0);
+    t0.u.f = dense_p(h->wf("u"), 168, 0, 3, 84, 100, h->P(L.tower.w0), 8400, h->P(L.tower.b0), 100, h->wf("zt0"), 300);
+    t0.u.f.x_off[0] = 0; t0.u.f.x_off[1] = 84; t0.u.f.x_off[2] = 0;
+    for (int g = 0; g < 3; ++g) t0.u.f.z_off[g] = g * 100;
+    t0.u.f.out_sums = bn[BN_T0].sums;
+    fin(t0, {BN_T0}, 0); F.push_back(t0);
+    HeadPhase t1 = phase(HEAD_OP_DENSE_FWD, 0);
+    t1.u.f = dense_p(h->wf("zt0"), 300, 0, 3, 100, 64, h->P(L.tower.w1), 6400, h->P(L.tower.b1), 64, h->wf("zt1"), 192);
+    for (int g = 0; g < 3; ++g) { t1.u.f.x_off[g] = g * 100; t1.u.f.z_off[g] = g * 64; }
+    set_in_bn(t1.u.f, bn[BN_T0]); t1.u.f.out_sums = bn[BN_T1].sums;
+    fin(t1, {BN_T1}, 0); F.push_back(t1);
+    HeadPhase to = phase(HEAD_OP_DENSE_FWD, 0);
+    to.u.f = dense_p(h->wf("zt1"), 192, 0, 3, 64, 1, h->P(L.tower.wout), 64, h->P(L.tower.bout), 1, h->wf("logits"), 3);
+    for (int g = 0; g < 3; ++g) { to.u.f.x_off[g] = g * 64; to.u.f.z_off[g] = g; }
+    set_in_bn(to.u.f, bn[BN_T1]); F.push_back(to);
+  }
+  // ------------------------------------------------------------------ backward
+  auto sync_b = [](HeadPhase& p, std::initializer_list<int> ids) {
+    p.barrier = 1; p.sync_bwd = 1;
+    for (int id : ids) p.sync[p.n_sync++] = id;
+  };
+  {
+    HeadPhase l = phase(HEAD_OP_LOSS, 0);
+    l.u.ls.logits = h->wf("logits"); l.u.ls.d_logits = h->wf("d_logits"); l.u.ls.loss_acc = h->wd("loss_acc");
+    l.u.ls.n_valid_global = h->wd("dp.scalars");
+    l.barrier = 1; K.push_back(l);
+  }
+  {  // towers
+    HeadPhase x = phase(HEAD_OP_DENSE_DX, 0);
+    x.u.x = dx_p(h->wf("d_logits"), 3, 0, 64, Pb, h->wf("d_t1"), 192, 0);
+    for (int g = 0; g < 3; ++g) dx_add(x.u.x, g, g * 64, g, L.tower.wout + g * 64, 1);
+    x.u.x.o = out_of(BN_T1, h->wf("zt1")); K.push_back(x);
+    HeadPhase w = phase(HEAD_OP_DENSE_DW, 0);
+    w.u.w = dw_p(h->wf("zt1"), 192, 0, 3, 64, 1, h->wf("d_logits"), 3, h->G(L.tower.wout), 64, h->G(L.tower.bout), 1);
+    for (int g = 0; g < 3; ++g) { w.u.w.x_off[g] = g * 64; w.u.w.z_off[g] = g; }
+    set_in_bn_dw(w.u.w, bn[BN_T1]);
+    sync_b(w, {BN_T1}); K.push_back(w);
+    HeadPhase x1 = phase(HEAD_OP_DENSE_DX, 0);
+    x1.u.x = dx_p(h->wf("d_t1"), 192, 0, 100, Pb, h->wf("d_t0"), 300, 0);
+    for (int g = 0; g < 3; ++g) dx_add(x1.u.x, g, g * 100, g * 64, L.tower.w1 + (int64_t)g * 6400, 64);
+    x1.u.x.g = grad_of(BN_T1, h->wf("zt1")); x1.u.x.o = out_of(BN_T0, h->wf("zt0")); K.push_back(x1);
+    HeadPhase w1 = phase(HEAD_OP_DENSE_DW, 0);
+    w1.u.w = dw_p(h->wf("zt0"), 300, 0, 3, 100, 64, h->wf("d_t1"), 192, h->G(L.tower.w1), 6400, h->G(L.tower.b1), 64);
+    for (int g = 0; g < 3; ++g) { w1.u.w.x_off[g] = g * 100; w1.u.w.z_off[g] = g * 64; }
+    set_in_bn_dw(w1.u.w, bn[BN_T0]); dw_bn(w1.u.w, BN_T1, h->wf("zt1"));
+    sync_b(w1, {BN_T0}); K.push_back(w1);
+    HeadPhase x0 = phase(HEAD_OP_DENSE_DX, 0);
+    x0.u.x = dx_p(h->wf("d_t0"), 300, 0, 84, Pb, h->wf("d_u"), 168, 0);
+    dx_add(x0.u.x, 0, 0, 0, L.tower.w0, 100);
+    dx_add(x0.u.x, 0, 0, 200, L.tower.w0 + 2 * 8400, 100);
+    dx_add(x0.u.x, 1, 84, 100, L.tower.w0 + 8400, 100);
+    x0.u.x.g = grad_of(BN_T0, h->wf("zt0")); K.push_back(x0);
+    HeadPhase w0 = phase(HEAD_OP_DENSE_DW, 0);
+    w0.u.w = dw_p(h->wf("u"), 168, 0, 3, 84, 100, h->wf("d_t0"), 300, h->G(L.tower.w0), 8400, h->G(L.tower.b0), 100);
+    w0.u.w.x_off[0] = 0; w0.u.w.x_off[1] = 84; w0.u.w.x_off[2] = 0;
+    for (int g = 0; g < 3; ++g) w0.u.w.z_off[g] = g * 100;
+    dw_bn(w0.u.w, BN_T0, h->wf("zt0"));
+    w0.barrier = 1; K.push_back(w0);
+  }
+  {  // mixing + MMoE
+    HeadPhase c = phase(HEAD_OP_COMBINE_BWD, 0);
+    c.u.cb.ZE1 = h->wf("ze1"); c.u.cb.ZG1 = h->wf("zg1"); c.u.cb.dU = h->wf("d_u"); c.u.cb.dE1 = h->wf("d_e1");
+    c.u.cb.dG1 = h->wf("d_g1"); c.u.cb.dTgt = h->wf("d_tgt");
+    sync_b(c, {BN_E1, BN_G1}); K.push_back(c);
+    HeadPhase xe = phase(HEAD_OP_DENSE_DX, 0);
+    xe.u.x = dx_p(h->wf("d_e1"), 320, 0, 100, Pb, h->wf("d_e0"), 500, 0);
+    for (int g = 0; g < 5; ++g) dx_add(xe.u.x, g, g * 100, g * 64, L.expert.w1 + (int64_t)g * 6400, 64);
+    xe.u.x.g = grad_of(BN_E1, h->wf("ze1")); xe.u.x.o = out_of(BN_E0, h->wf("ze0")); K.push_back(xe);
+    HeadPhase xg = phase(HEAD_OP_DENSE_DX, 0);
+    xg.u.x = dx_p(h->wf("d_g1"), 10, 0, 64, Pb, h->wf("d_g0"), 128, 0);
+    for (int g = 0; g < 2; ++g) dx_add(xg.u.x, g, g * 64, g * 5, L.gate.w1 + (int64_t)g * 320, 5);
+    xg.u.x.g = grad_of(BN_G1, h->wf("zg1")); xg.u.x.o = out_of(BN_G0, h->wf("zg0")); K.push_back(xg);
+    HeadPhase we = phase(HEAD_OP_DENSE_DW, 0);
+    we.u.w = dw_p(h->wf("ze0"), 500, 0, 5, 100, 64, h->wf("d_e1"), 320, h->G(L.expert.w1), 6400, h->G(L.expert.b1), 64);
+    for (int g = 0; g < 5; ++g) { we.u.w.x_off[g] = g * 100; we.u.w.z_off[g] = g * 64; }
+    set_in_bn_dw(we.u.w, bn[BN_E0]); dw_bn(we.u.w, BN_E1, h->wf("ze1")); K.push_back(we);
+    HeadPhase wg = phase(HEAD_OP_DENSE_DW, 0);
+    wg.u.w = dw_p(h->wf("zg0"), 128, 0, 2, 64, 5, h->wf("d_g1"), 10, h->G(L.gate.w1), 320, h->G(L.gate.b1), 5);
+    for (int g = 0; g < 2; ++g) { wg.u.w.x_off[g] = g * 64; wg.u.w.z_off[g] = g * 5; }
+    set_in_bn_dw(wg.u.w, bn[BN_G0]); dw_bn(wg.u.w, BN_G1, h->wf("zg1"));
+    sync_b(wg, {BN_E0, BN_G0}); K.push_back(wg);
+    HeadPhase xe0 = phase(HEAD_OP_DENSE_DX, 0);
+    xe0.u.x = dx_p(h->wf("d_e0"), 500, 0, kD, Pb, h->wf("d_new_long"), kD, 0);
+    for (int g = 0; g < 5; ++g) dx_add(xe0.u.x, 0, 0, g * 100, L.expert.w0 + (int64_t)g * 4000, 100);
+    xe0.u.x.g = grad_of(BN_E0, h->wf("ze0")); K.push_back(xe0);
+    HeadPhase we0 = phase(HEAD_OP_DENSE_DW, 0);
+    we0.u.w = dw_p(h->wf("new_long"), kD, 0, 5, kD, 100, h->wf("d_e0"), 500, h->G(L.expert.w0), 4000, h->G(L.expert.b0), 100);
+    for (int g = 0; g < 5; ++g) { we0.u.w.x_off[g] = 0; we0.u.w.z_off[g] = g * 100; }
+    dw_bn(we0.u.w, BN_E0, h->wf("ze0")); K.push_back(we0);
+    HeadPhase wg0 = phase(HEAD_OP_DENSE_DW, 0);
+    wg0.u.w = dw_p(h->wf("new_long"), kD, 0, 2, kD, 64, h->wf("d_g0"), 128, h->G(L.gate.w0), 2560, h->G(L.gate.b0), 64);
+    for (int g = 0; g < 2; ++g) { wg0.u.w.x_off[g] = 0; wg0.u.w.z_off[g] = g * 64; }
+    dw_bn(wg0.u.w, BN_G0, h->wf("zg0"));
+    wg0.barrier = 1; K.push_back(wg0);
+    HeadPhase xg0 = phase(HEAD_OP_DENSE_DX, 0);                  // accumulates onto the experts' part: its own barrier interval
+    xg0.u.x = dx_p(h->wf("d_g0"), 128, 0, kD, Pb, h->wf("d_new_long"), kD, 1);
+    for (int g = 0; g < 2; ++g) dx_add(xg0.u.x, 0, 0, g * 64, L.gate.w0 + (int64_t)g * 2560, 64);
+    xg0.u.x.g = grad_of(BN_G0, h->wf("zg0"));
+    xg0.barrier = 1; K.push_back(xg0);
+  }
+  {  // attention pooling
+    HeadPhase pb = phase(HEAD_OP_POOL_BWD, 0);
+    pb.u.pl.H = H; pb.u.pl.Z2 = h->wf("z2"); pb.u.pl.dNL = h->wf("d_new_long"); pb.u.pl.dA2 = h->wf("d_z2"); pb.u.pl.dH = h->wf("g_a");
+    sync_b(pb, {BN_S1}); K.push_back(pb);
+    HeadPhase x1 = phase(HEAD_OP_DENSE_DX, 1);
+    x1.u.x = dx_p(h->wf("d_z2"), 1, 0, 20, Pb, h->wf("d_a1"), 20, 0);
+    dx_add(x1.u.x, 0, 0, 0, L.score.w1, 1);
+    x1.u.x.g = grad_of(BN_S1, h->wf("z2")); x1.u.x.o = out_of(BN_S0, h->wf("z1")); K.push_back(x1);
+    HeadPhase w1 = phase(HEAD_OP_DENSE_DW, 1);
+    w1.u.w = dw_p(h->wf("z1"), 20, 0, 1, 20, 1, h->wf("d_z2"), 1, h->G(L.score.w1), 0, h->G(L.score.b1), 0);
+    set_in_bn_dw(w1.u.w, bn[BN_S0]); dw_bn(w1.u.w, BN_S1, h->wf("z2"));
+    sync_b(w1, {BN_S0}); K.push_back(w1);
+    HeadPhase x0 = phase(HEAD_OP_DENSE_DX, 1);
+    x0.u.x = dx_p(h->wf("d_a1"), 20, 0, kD, Pb, h->wf("g_a"), kD, 1);
+    dx_add(x0.u.x, 0, 0, 0, L.score.w0, 20);
+    x0.u.x.g = grad_of(BN_S0, h->wf("z1")); K.push_back(x0);
+    HeadPhase w0 = phase(HEAD_OP_DENSE_DW, 1);
+    w0.u.w = dw_p(H, kD, 0, 1, kD, 20, h->wf("d_a1"), 20, h->G(L.score.w0), 0, h->G(L.score.b0), 0);
+    dw_bn(w0.u.w, BN_S0, h->wf("z1")); K.push_back(w0);
+  }
+  if ((int)F.size() > kHeadMaxPhases || (int)K.size() > kHeadMaxPhases) return fail(h, "head program too long");
+  std::vector<HeadProgram> host(2);
+  for (int k = 0; k < 2; ++k) {
+    HeadProgram& P = host[k];
+    memset(&P, 0, sizeof P);
+    const std::vector<HeadPhase>& src = k == 0 ? F : K;
+    P.n = (int)src.size();
+    for (int i = 0; i < BN_COUNT; ++i) P.bn[i] = bn[i];
+    P.dp_scalars = h->wd("dp.scalars");
+    for (int i = 0; i < P.n; ++i) memcpy(&P.ph[i], &src[i], sizeof(HeadPhase));
+  }
+  if (!h->prog_fwd && cudaMalloc(&h->prog_fwd, sizeof(HeadProgram)) != cudaSuccess) return check_cuda(h, "head program alloc");
+  if (!h->prog_bwd && cudaMalloc(&h->prog_bwd, sizeof(HeadProgram)) != cudaSuccess) return check_cuda(h, "head program alloc");
+  if (!h->head_bar) {
+    if (cudaMalloc(&h->head_bar, 64) != cudaSuccess) return check_cuda(h, "head barrier alloc");
+    cudaMemsetAsync(h->head_bar, 0, 64, st);
+  }
+  cudaMemcpyAsync(h->prog_fwd, &host[0], sizeof(HeadProgram), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(h->prog_bwd, &host[1], sizeof(HeadProgram), cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);                            // `host` goes out of scope
+  h->coop_grid = grid;
+  return check_cuda(h, "head programs");
+}
+
 int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   if (int rc = check_batch(h, b, true)) return rc;
   ProfBind _pb(h);
@@ -671,13 +928,21 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   cudaMemsetAsync(h->buf.dense_grad, 0, (size_t)L.dense_numel * 4, st);
   cudaMemsetAsync(h->wd("loss_acc"), 0, 8 * sizeof(double), st);
   cudaMemsetAsync(h->wd("sp_normsq"), 0, 8 * sizeof(double), st);
+  const bool coop = h->use_coop();
+  if (!coop) {
   launch_loss(h->wf("logits"), b->labels_satisfied, b->labels_play, b->plays, h->wf("d_logits"), h->wd("loss_acc"), B, Bg,
               W > 1 ? h->wd("dp.scalars") : nullptr, h->cfg.fuzhu_weight, h->cfg.order_weight,
               h->cfg.loss_kind == PAMREC_LOSS_SOFTMAX ? h->cfg.softmax_group : 0, st); nl += 1;
+  }
   // Batch-norm backward is folded into the dense kernels (common.cuh: BnGrad / BnGradOut): the kernel that produces a
   // gradient buffer also accumulates the two column sums of its layer's BN, the consumers turn dA into dz while loading.
   // Buffers produced by the mixing / pooling kernels get their sums from k_bn_bwd_stats.  Data parallel: sums over ranks.
   cudaMemsetAsync(h->wd("bn.bsums"), 0, (size_t)L.ws[L.ws_index.at("bn.bsums")].numel * sizeof(double), st);
+  if (coop) {
+    // loss + the whole head backward (activation, weight and batch-norm gradients) as ONE persistent cooperative kernel
+    HeadDyn d = head_dyn(h, b, true, 12);
+    if (launch_head_program(h->prog_bwd, d, h->coop_grid, "head_bwd", st)) return check_cuda(h, "cooperative head launch");
+  }
   int p2p_slot = 6;
   auto sync_bsums = [&](std::initializer_list<int> ids) {
     if (W == 1 || crc) return;
@@ -707,6 +972,7 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   auto dw_bn = [&](DenseDwP& w, int id, const float* Z, double cnt) {
     w.g = grad_of(id, Z, cnt); w.g_dgamma = bn[id].dgamma; w.g_dbeta = bn[id].dbeta; w.g_C = bn[id].C; w.g_scale = gs;
   };
+  if (!coop) {
   // ---- towers
   {
     DenseDwP w = dw_p(h->wf("zt1"), 192, B, 3, 64, 1, h->wf("d_logits"), 3, h->G(L.tower.wout), 64, h->G(L.tower.bout), 1);
@@ -792,11 +1058,12 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
     launch_dense_dx(xg0, st);
     nl += 4;
   }
+  }  // !coop (towers, mixing, MMoE)
   // ---- attention pooling
   const float* H = h->wf("blk1.out");
   float* g_a = h->wf("g_a");
   float* g_b = h->wf("g_b");
-  {
+  if (!coop) {
     launch_pool_bwd(H, h->wf("z2"), bn[BN_S1], b->mask, h->wf("d_new_long"), h->wf("d_z2"), g_a, B, T, st); nl += 1;
     launch_bn_bwd_stats(bn[BN_S1], h->wf("d_z2"), h->wf("z2"), N, st); nl += 1;
     sync_bsums({BN_S1});

@@ -111,7 +111,7 @@ void launch_finish_losses(const double* loss_acc, float* losses, cudaStream_t st
 
 // ---- kernels_p2p.cu (small all-reduces through NVLink peer mailboxes)
 constexpr int kP2PMaxDoubles = 2048;     // payload capacity of one mailbox slot (expert + gate layer-0 sums: 1256)
-constexpr int kP2PSlots = 16;            // sync points per step (each has its own slot)
+constexpr int kP2PSlots = 24;            // sync points per step (each has its own slot): 12 forward + 12 backward barriers
 constexpr int kP2PMaxWorld = 8;
 struct P2PArgs {
   double* buf[3]; int n[3]; int nbuf;                     // buffers reduced in place (concatenated in the slot)
