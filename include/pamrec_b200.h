@@ -182,7 +182,12 @@ int pamrec_bench_table_adam(PamrecHandle h, int64_t step, void* stream);
  * the workspace tensors "d_Q" / "d_K" (backward-only scratch, overwritten by pamrec_backward), so that a checker can read the
  * exact ReLU pattern of the point-wise FFN (pamrec.py:565-570).  Costs one extra [B,T,40] store per block; off by default. */
 #define PAMREC_DEBUG_SAVE_FFN_HIDDEN 1
+/* PAMREC_DEBUG_HEAD_TRACE: the persistent head kernels stamp %globaltimer (ns) at their start and at every grid barrier;
+ * pamrec_head_trace copies the 32 stamps of the last forward (backward = 0) or backward (1) head kernel: [0 .. n-1] barrier
+ * releases, [29] n, [30] end of CTA 0, [31] start. */
+#define PAMREC_DEBUG_HEAD_TRACE 2
 int pamrec_set_debug(PamrecHandle h, int flags);
+int pamrec_head_trace(PamrecHandle h, int backward, uint64_t out[32]);
 
 /* Per-launcher device timing: CUDA events recorded on the caller's stream around every launch while enabled.
  * Synchronise the stream, then read (name, accumulated ms, timed launches) per launcher. */

@@ -16,6 +16,7 @@ COMM_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 GROUP = 5
 DEBUG_SAVE_FFN_HIDDEN = 1
+DEBUG_HEAD_TRACE = 2
 
 
 class PamrecConfig(C.Structure):
@@ -91,6 +92,7 @@ EXPORTS = {
                                       C.c_void_p, C.c_void_p]),
     "pamrec_bench_table_adam": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "pamrec_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
+    "pamrec_head_trace": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
     "pamrec_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "pamrec_profile_reset": (C.c_int, [C.c_void_p]),
     "pamrec_profile_count": (C.c_int, [C.c_void_p]),

@@ -52,7 +52,8 @@ struct PamrecHandle_ {
   // persistent cooperative head kernels (kernels_headcoop.cu): device-resident programs, barrier words, grid size
   HeadProgram* prog_fwd = nullptr;
   HeadProgram* prog_bwd = nullptr;
-  unsigned* head_bar = nullptr;
+  unsigned* head_bar = nullptr;      // 16 words of barrier state, then 2 x 32 trace stamps (forward, backward)
+  bool head_trace = false;
   int coop_grid = 0;
   uint32_t coop_epoch = 0;          // mailbox epoch of the cooperative kernels (one per launch, all ranks in lockstep)
   bool use_coop() const { return coop_grid > 0 && prog_fwd && (cfg.world_size == 1 || mbox_open); }
@@ -688,6 +689,7 @@ static HeadDyn head_dyn(PamrecHandle h, const PamrecBatch* b, bool training, int
   d.fuzhu_w = h->cfg.fuzhu_weight; d.order_w = h->cfg.order_weight;
   d.sm_group = h->cfg.loss_kind == PAMREC_LOSS_SOFTMAX ? h->cfg.softmax_group : 0;
   d.bar = h->head_bar;
+  d.trace = h->head_trace ? reinterpret_cast<unsigned long long*>(h->head_bar + 16) + (slot0 ? 32 : 0) : nullptr;
   if (W > 1) {
     for (int p = 0; p < W; ++p) { d.peer_slots[p] = h->mbox_slots(p); d.peer_flags[p] = h->mbox_flags(p); }
     d.p2p_epoch = ++h->coop_epoch; d.p2p_slot0 = slot0; d.p2p_err = h->mbox_err();
@@ -901,8 +903,8 @@ static int build_head_programs(PamrecHandle h, cudaStream_t st) {
   if (!h->prog_fwd && cudaMalloc(&h->prog_fwd, sizeof(HeadProgram)) != cudaSuccess) return check_cuda(h, "head program alloc");
   if (!h->prog_bwd && cudaMalloc(&h->prog_bwd, sizeof(HeadProgram)) != cudaSuccess) return check_cuda(h, "head program alloc");
   if (!h->head_bar) {
-    if (cudaMalloc(&h->head_bar, 64) != cudaSuccess) return check_cuda(h, "head barrier alloc");
-    cudaMemsetAsync(h->head_bar, 0, 64, st);
+    if (cudaMalloc(&h->head_bar, 64 + 2 * 32 * 8) != cudaSuccess) return check_cuda(h, "head barrier alloc");
+    cudaMemsetAsync(h->head_bar, 0, 64 + 2 * 32 * 8, st);
   }
   cudaMemcpyAsync(h->prog_fwd, &host[0], sizeof(HeadProgram), cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(h->prog_bwd, &host[1], sizeof(HeadProgram), cudaMemcpyHostToDevice, st);
@@ -1266,6 +1268,14 @@ int pamrec_bench_table_adam(PamrecHandle h, int64_t step, void* stream) {
 int pamrec_set_debug(PamrecHandle h, int flags) {
   if (!h) return -1;
   h->debug = flags;
+  h->head_trace = (flags & PAMREC_DEBUG_HEAD_TRACE) != 0;
+  return 0;
+}
+int pamrec_head_trace(PamrecHandle h, int backward, uint64_t out[32]) {
+  if (!h || !out || !h->head_bar) return -1;
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(out, reinterpret_cast<unsigned long long*>(h->head_bar + 16) + (backward ? 32 : 0), 32 * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return check_cuda(h, "head trace");
   return 0;
 }
 int pamrec_profile_enable(PamrecHandle h, int on) {

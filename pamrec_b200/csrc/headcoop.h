@@ -6,7 +6,7 @@
 
 namespace pamrec {
 
-constexpr int kHeadCtasPerSm = 2;          // resident CTAs per SM of the persistent grid (leaves room for side-stream kernels)
+constexpr int kHeadCtasPerSm = 4;          // resident CTAs per SM of the persistent grid (leaves room for side-stream kernels)
 constexpr int kHeadMaxPhases = 28;
 constexpr int BN_S1_ = 1, BN_E1_ = 4, BN_G1_ = 5, BN_COUNT_ = 8;   // mirror layout.h:BnId (static_assert in api.cu)
 
@@ -48,6 +48,7 @@ struct HeadDyn {
   unsigned* bar;                                    // [0] arrivals [1] release epoch [2] error word
   double* peer_slots[kP2PMaxWorld]; uint32_t* peer_flags[kP2PMaxWorld];
   uint32_t p2p_epoch; int p2p_slot0; uint32_t* p2p_err;
+  unsigned long long* trace;                        // [32] %globaltimer of the kernel start ([31]) and of every barrier release; may be null
 };
 
 int head_program_grid(int* ctas_per_sm_out);        // CTAs of the persistent grid on the current device, < 0 if unsupported

@@ -73,7 +73,7 @@ __device__ __forceinline__ void pool_weights_w(const float* __restrict__ Z2, con
   __syncwarp();
 }
 
-__device__ __forceinline__ void pool_fwd_item(const PoolP& p, const BnSet& s1, const int* __restrict__ mask, int B, int T, int item,
+__device__ __noinline__ void pool_fwd_item(const PoolP& p, const BnSet& s1, const int* __restrict__ mask, int B, int T, int item,
                                               unsigned char* smem) {
   float* aws = reinterpret_cast<float*>(smem);              // [4][PAMREC_MAX_T]
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,7 +95,7 @@ __device__ __forceinline__ void pool_fwd_item(const PoolP& p, const BnSet& s1, c
 }
 
 // backward of the pooling + the two column sums of the score layer-1 batch norm (C = 1) of the gradient it produces
-__device__ __forceinline__ void pool_bwd_item(const PoolP& p, const BnSet& s1, const int* __restrict__ mask, int B, int T, int item,
+__device__ __noinline__ void pool_bwd_item(const PoolP& p, const BnSet& s1, const int* __restrict__ mask, int B, int T, int item,
                                               unsigned char* smem) {
   float* aws = reinterpret_cast<float*>(smem);              // [4][PAMREC_MAX_T]
   float* dnls = aws + 4 * PAMREC_MAX_T;                     // [4][kD]
@@ -154,7 +154,7 @@ __device__ __forceinline__ void pool_bwd_item(const PoolP& p, const BnSet& s1, c
 
 // M1 mixing (pamrec.py:46-50, 315-316): two samples per item, 64 threads each
 constexpr int kCombineRows = 8;                              // samples per combine item (4 iterations of 2)
-__device__ __forceinline__ void combine_fwd_item(const CombineP& p, const BnSet& e1, const BnSet& g1, int B, int item, unsigned char* smem) {
+__device__ __noinline__ void combine_fwd_item(const CombineP& p, const BnSet& e1, const BnSet& g1, int B, int item, unsigned char* smem) {
   float* gt = reinterpret_cast<float*>(smem);               // [2][10]
   const int sub = threadIdx.x >> 6, c = threadIdx.x & 63;
   for (int it = 0; it < kCombineRows / 2; ++it) {
@@ -179,7 +179,7 @@ __device__ __forceinline__ void combine_fwd_item(const CombineP& p, const BnSet&
 }
 
 // backward of the mixing + the column sums of the expert / gate layer-1 batch norms of the gradients it produces
-__device__ __forceinline__ void combine_bwd_item(const CombineP& p, const BnSet& e1, const BnSet& g1, int B, int item, unsigned char* smem) {
+__device__ __noinline__ void combine_bwd_item(const CombineP& p, const BnSet& e1, const BnSet& g1, int B, int item, unsigned char* smem) {
   float* gt = reinterpret_cast<float*>(smem);               // [2][10]
   float* red = gt + 32;                                     // [2 samples][2 warps][10]
   const int sub = threadIdx.x >> 6, c = threadIdx.x & 63, lane = c & 31, w = c >> 5;
@@ -260,7 +260,7 @@ __device__ __forceinline__ double block_sum_d2(double v, double* sh) {
   for (int k = 0; k < kHT / 32; ++k) r += sh[k];
   return r;
 }
-__device__ __forceinline__ void loss_item(const LossP& p, const HeadDyn& d, int item, unsigned char* smem) {
+__device__ __noinline__ void loss_item(const LossP& p, const HeadDyn& d, int item, unsigned char* smem) {
   double* sh = reinterpret_cast<double*>(smem);
   const int tid = threadIdx.x, B = d.B;
   const int G = B / PAMREC_GROUP;
@@ -426,7 +426,7 @@ __device__ __forceinline__ void leader_p2p(const HeadDyn& d, int slot, double* c
   __syncthreads();
 }
 
-__device__ __forceinline__ void leader_work(const HeadProgram* prog, const HeadPhase& ph, const HeadDyn& d, int barrier_index) {
+__device__ __noinline__ void leader_work(const HeadProgram* prog, const HeadPhase& ph, const HeadDyn& d, int barrier_index) {
   const int tid = threadIdx.x;
   if (d.world > 1 && d.training && (ph.n_sync > 0 || ph.sync_scalars)) {
     double* buf[3]; int n[3]; int nb = 0;
@@ -479,7 +479,10 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& epoch, con
     leader_work(prog, ph, d, barrier_index);
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) { bar[0] = 0u; __threadfence(); st_release_u32(bar + 1, epoch + 1u); }
+    if (threadIdx.x == 0) {
+      if (d.trace != nullptr && barrier_index < 31) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); d.trace[barrier_index] = t; }
+      bar[0] = 0u; __threadfence(); st_release_u32(bar + 1, epoch + 1u);
+    }
   } else {
     if (threadIdx.x == 0) {
       atomicAdd(bar, 1u);
@@ -495,10 +498,11 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& epoch, con
 }
 
 // ------------------------------------------------------------------------------------------ the persistent kernel
-__global__ void __launch_bounds__(kHT) k_head_program(const HeadProgram* __restrict__ prog, const HeadDyn d) {
+__global__ void __launch_bounds__(kHT, kHeadCtasPerSm) k_head_program(const HeadProgram* __restrict__ prog, const HeadDyn d) {
   __shared__ __align__(16) unsigned char smem[kHeadSmemBytes];
   unsigned* bar = d.bar;
   __shared__ unsigned s_epoch;
+  if (threadIdx.x == 0 && blockIdx.x == 0 && d.trace != nullptr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); d.trace[31] = t; }
   if (threadIdx.x == 0) s_epoch = ld_acquire_u32(bar + 1);   // the previous launch on this stream has completed: every CTA reads the same value
   __syncthreads();
   unsigned epoch = s_epoch;
@@ -560,6 +564,7 @@ __global__ void __launch_bounds__(kHT) k_head_program(const HeadProgram* __restr
       ++n_barrier;
     }
   }
+  if (threadIdx.x == 0 && blockIdx.x == 0 && d.trace != nullptr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); d.trace[30] = t; d.trace[29] = (unsigned long long)n_barrier; }
 }
 
 // ------------------------------------------------------------------------------------------ host side

@@ -450,6 +450,14 @@ class Engine:
         """Test hooks (include/pamrec_b200.h: PAMREC_DEBUG_*)."""
         self._check(self.lib.pamrec_set_debug(self.handle, int(flags)))
 
+    def head_trace(self, backward=False):
+        """ns from the start of the last persistent head kernel to each of its barrier releases and to the end of CTA 0
+        (needs set_debug(DEBUG_HEAD_TRACE) before the step)."""
+        buf = (C.c_uint64 * 32)()
+        self._check(self.lib.pamrec_head_trace(self.handle, int(backward), buf))
+        n, t0 = int(buf[29]), int(buf[31])
+        return [int(buf[i]) - t0 for i in range(n)] + [int(buf[30]) - t0]
+
     def profile(self, on=True):
         self._check(self.lib.pamrec_profile_enable(self.handle, int(on)))
         self._check(self.lib.pamrec_profile_reset(self.handle))
