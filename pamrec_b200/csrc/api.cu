@@ -52,9 +52,11 @@ struct PamrecHandle_ {
   // persistent cooperative head kernels (kernels_headcoop.cu): device-resident programs, barrier words, grid size
   HeadProgram* prog_fwd = nullptr;
   HeadProgram* prog_bwd = nullptr;
-  unsigned* head_bar = nullptr;      // 16 words of barrier state, then 2 x 32 trace stamps (forward, backward)
+  unsigned* head_bar = nullptr;      // 64 words of barrier state, then 2 x 32 trace stamps (forward, backward)
   bool head_trace = false;
   int coop_grid = 0;
+  int n_sm = 148;
+  int attn_tc = 0;                  // 1: attention forward on tcgen05 (kernels_attn_tc.cu) where the sequence length allows it
   uint32_t coop_epoch = 0;          // mailbox epoch of the cooperative kernels (one per launch, all ranks in lockstep)
   bool use_coop() const { return coop_grid > 0 && prog_fwd && (cfg.world_size == 1 || mbox_open); }
   double* mbox_slots(int p) const { return static_cast<double*>(mbox_peer[p]); }
@@ -278,6 +280,14 @@ int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(h, "no CUDA device: the CUDA path is the only path"); }
   h->buf = *bufs;
   if (init_encoder_kernels(h->cfg.max_seq_len)) return check_cuda(h, "shared-memory opt-in of the encoder kernels");
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const char* a = getenv("PAMREC_ATTN");
+    h->attn_tc = (a != nullptr && std::string(a) == "tc") ? 1 : 0;
+    if (h->attn_tc && init_attn_tc_kernels(h->cfg.max_seq_len)) return check_cuda(h, "shared-memory opt-in of the tcgen05 attention kernel");
+  }
   if (!h->side) {
     if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) return fail(h, "cannot create the side stream");
     for (auto& e : h->ev_side) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -573,7 +583,11 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     launch_proj_fwd(xin, h->wi("perm"), ctl, h->wi("tile_bucket"), h->wi("tile_begin"), h->wi("tile_count"), max_tiles,
                     h->P(o.wq), h->P(o.wk), h->P(o.wv), h->P(o.ln_a_beta), h->P(o.ln_a_gamma), h->wf(p + "qin"), h->wf(p + "Q"),
                     h->wf(p + "K"), h->wf(p + "V"), st);
-    launch_attn_fwd(h->wf(p + "Q"), h->wf(p + "K"), h->wf(p + "V"), h->wf(p + "qin"), b->mask, h->wf(p + "y"), h->wf(p + "ml"), B, T, st);
+    if (h->attn_tc && attn_tc_supported(T))
+      launch_attn_fwd_tc(h->wf(p + "Q"), h->wf(p + "K"), h->wf(p + "V"), h->wf(p + "qin"), b->mask, h->wf(p + "y"), h->wf(p + "ml"), B, T,
+                         h->n_sm, reinterpret_cast<int*>(h->head_bar + 3), st);
+    else
+      launch_attn_fwd(h->wf(p + "Q"), h->wf(p + "K"), h->wf(p + "V"), h->wf(p + "qin"), b->mask, h->wf(p + "y"), h->wf(p + "ml"), B, T, st);
     float* hdbg = (training && (h->debug & PAMREC_DEBUG_SAVE_FFN_HIDDEN)) ? h->wf(k == 0 ? "d_Q" : "d_K") : nullptr;
     launch_ffn_fwd(h->wf(p + "y"), h->P(o.w1), h->P(o.b1), h->P(o.w2), h->P(o.b2), h->P(o.ln_b_beta), h->P(o.ln_b_gamma),
                    h->wf(p + "out"), hdbg, N, st);
@@ -689,7 +703,7 @@ static HeadDyn head_dyn(PamrecHandle h, const PamrecBatch* b, bool training, int
   d.fuzhu_w = h->cfg.fuzhu_weight; d.order_w = h->cfg.order_weight;
   d.sm_group = h->cfg.loss_kind == PAMREC_LOSS_SOFTMAX ? h->cfg.softmax_group : 0;
   d.bar = h->head_bar;
-  d.trace = h->head_trace ? reinterpret_cast<unsigned long long*>(h->head_bar + 16) + (slot0 ? 32 : 0) : nullptr;
+  d.trace = h->head_trace ? reinterpret_cast<unsigned long long*>(h->head_bar + 64) + (slot0 ? 32 : 0) : nullptr;
   if (W > 1) {
     for (int p = 0; p < W; ++p) { d.peer_slots[p] = h->mbox_slots(p); d.peer_flags[p] = h->mbox_flags(p); }
     d.p2p_epoch = ++h->coop_epoch; d.p2p_slot0 = slot0; d.p2p_err = h->mbox_err();
@@ -903,8 +917,8 @@ static int build_head_programs(PamrecHandle h, cudaStream_t st) {
   if (!h->prog_fwd && cudaMalloc(&h->prog_fwd, sizeof(HeadProgram)) != cudaSuccess) return check_cuda(h, "head program alloc");
   if (!h->prog_bwd && cudaMalloc(&h->prog_bwd, sizeof(HeadProgram)) != cudaSuccess) return check_cuda(h, "head program alloc");
   if (!h->head_bar) {
-    if (cudaMalloc(&h->head_bar, 64 + 2 * 32 * 8) != cudaSuccess) return check_cuda(h, "head barrier alloc");
-    cudaMemsetAsync(h->head_bar, 0, 64 + 2 * 32 * 8, st);
+    if (cudaMalloc(&h->head_bar, 256 + 2 * 32 * 8) != cudaSuccess) return check_cuda(h, "head barrier alloc");
+    cudaMemsetAsync(h->head_bar, 0, 256 + 2 * 32 * 8, st);
   }
   cudaMemcpyAsync(h->prog_fwd, &host[0], sizeof(HeadProgram), cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(h->prog_bwd, &host[1], sizeof(HeadProgram), cudaMemcpyHostToDevice, st);
@@ -1274,7 +1288,7 @@ int pamrec_set_debug(PamrecHandle h, int flags) {
 int pamrec_head_trace(PamrecHandle h, int backward, uint64_t out[32]) {
   if (!h || !out || !h->head_bar) return -1;
   cudaDeviceSynchronize();
-  if (cudaMemcpy(out, reinterpret_cast<unsigned long long*>(h->head_bar + 16) + (backward ? 32 : 0), 32 * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+  if (cudaMemcpy(out, reinterpret_cast<unsigned long long*>(h->head_bar + 64) + (backward ? 32 : 0), 32 * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
     return check_cuda(h, "head trace");
   return 0;
 }

@@ -17,7 +17,7 @@ struct PoolP { const float* H; const float* Z2; float* new_long; const float* dN
 struct CombineP { const float* ZE1; const float* ZG1; const float* tgt; float* U; const float* dU; float* dE1; float* dG1; float* dTgt; };
 struct LossP { const float* logits; float* d_logits; double* loss_acc; const double* n_valid_global; };
 
-struct HeadPhase {
+struct alignas(16) HeadPhase {
   int op;
   int rows_n;            // 1: the phase runs over B*T rows (score MLP), 0: over B rows
   int barrier;           // grid-wide barrier after this phase
@@ -45,7 +45,7 @@ struct HeadDyn {
   double cntN, cntB;
   const int* mask; const float* y_sat; const float* y_play; const float* plays;
   float fuzhu_w, order_w; int sm_group;
-  unsigned* bar;                                    // [0] arrivals [1] release epoch [2] error word
+  unsigned* bar;                                    // [0] arrivals [2] error word [32] release epoch (own 128-byte line)
   double* peer_slots[kP2PMaxWorld]; uint32_t* peer_flags[kP2PMaxWorld];
   uint32_t p2p_epoch; int p2p_slot0; uint32_t* p2p_err;
   unsigned long long* trace;                        // [32] %globaltimer of the kernel start ([31]) and of every barrier release; may be null

@@ -19,18 +19,23 @@
 
 namespace pamrec {
 
+// Spin loads are RELAXED (an acquire load makes the compiler invalidate the SM's whole L1 - CCTL.IVALL - after every poll, which
+// starved the CTAs of the same SM that were still working: ncu showed 45 % of the samples at the barrier and 10 % in CCTL); the
+// acquire happens once, by a fence, after the awaited value has been seen.
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_flag_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t ld_flag_sys(const uint32_t* p) {
+__device__ __forceinline__ uint32_t ld_flag_sys_relaxed(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 
 constexpr int kHeadSmemBytes = kDenseFwdSmem > kDenseDxSmem ? kDenseFwdSmem : kDenseDxSmem;
 static_assert(kHeadSmemBytes >= kDenseDwSmem && kHeadSmemBytes >= 4 * PAMREC_MAX_T * 4 + 4 * kD * 4 + 1024, "shared memory union");
@@ -409,10 +414,11 @@ __device__ __forceinline__ void leader_p2p(const HeadDyn& d, int slot, double* c
   if (tid < d.world) {
     const uint32_t* f = d.peer_flags[d.rank] + slot * d.world + tid;
     uint32_t spins = 0;
-    while ((int32_t)(ld_flag_sys(f) - d.p2p_epoch) < 0) {
-      if (++spins > (1u << 26)) { *d.p2p_err = 1u + (uint32_t)slot; break; }
-      __nanosleep(20);
+    while ((int32_t)(ld_flag_sys_relaxed(f) - d.p2p_epoch) < 0) {
+      if (++spins > (1u << 24)) { *d.p2p_err = 1u + (uint32_t)slot; break; }
+      __nanosleep(64);
     }
+    fence_acq_rel_sys();
   }
   __syncthreads();
   const double* mine = d.peer_slots[d.rank] + (size_t)slot * d.world * kP2PMaxDoubles;
@@ -461,36 +467,39 @@ __device__ __noinline__ void leader_work(const HeadProgram* prog, const HeadPhas
   }
 }
 
-// grid-wide barrier with a leader section.  bar[0] = arrivals (reset by the leader), bar[1] = release epoch (monotonic across
-// launches), bar[2] = error word.  `epoch` is this CTA's copy of the release epoch.
+// grid-wide barrier with a leader section.  bar[0] = arrivals (reset by the leader), bar[32] = release epoch (monotonic across
+// launches, on its own 128-byte line so that polls do not queue behind the arrival atomics), bar[2] = error word.  `epoch` is this CTA's copy of the release epoch.
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& epoch, const HeadProgram* prog, const HeadPhase& ph,
                                              const HeadDyn& d, int barrier_index) {
-  __threadfence();
   __syncthreads();
   if (blockIdx.x == 0) {
     if (threadIdx.x == 0) {
       unsigned spins = 0;
-      while (ld_acquire_u32(bar) < gridDim.x - 1) {
-        if (++spins > (1u << 26)) { bar[2] = 1u + (unsigned)barrier_index; break; }
-        __nanosleep(32);
+      while (ld_relaxed_u32(bar) < gridDim.x - 1) {
+        if (++spins > (1u << 24)) { bar[2] = 1u + (unsigned)barrier_index; break; }
+        __nanosleep(64);
       }
+      fence_acq_rel_gpu();                                  // every arrival's release (and what its CTA wrote) is visible from here
     }
     __syncthreads();
     leader_work(prog, ph, d, barrier_index);
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-      if (d.trace != nullptr && barrier_index < 31) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); d.trace[barrier_index] = t; }
-      bar[0] = 0u; __threadfence(); st_release_u32(bar + 1, epoch + 1u);
+      if (d.trace != nullptr && barrier_index < 29) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); d.trace[barrier_index] = t; }
+      bar[0] = 0u;
+      __threadfence();                                      // cumulative: orders the whole CTA's writes (seen through the CTA barrier)
+      st_release_u32(bar + 32, epoch + 1u);
     }
   } else {
     if (threadIdx.x == 0) {
+      __threadfence();                                      // this CTA's writes before its arrival
       atomicAdd(bar, 1u);
       unsigned spins = 0;
-      while ((int)(ld_acquire_u32(bar + 1) - (epoch + 1u)) < 0) {
-        if (++spins > (1u << 26)) { bar[2] = 1000u + (unsigned)barrier_index; break; }
-        __nanosleep(32);
+      while ((int)(ld_relaxed_u32(bar + 32) - (epoch + 1u)) < 0) {
+        if (++spins > (1u << 24)) { bar[2] = 1000u + (unsigned)barrier_index; break; }
+        __nanosleep(64);
       }
+      fence_acq_rel_gpu();
     }
     __syncthreads();
   }
@@ -503,15 +512,28 @@ __global__ void __launch_bounds__(kHT, kHeadCtasPerSm) k_head_program(const Head
   unsigned* bar = d.bar;
   __shared__ unsigned s_epoch;
   if (threadIdx.x == 0 && blockIdx.x == 0 && d.trace != nullptr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); d.trace[31] = t; }
-  if (threadIdx.x == 0) s_epoch = ld_acquire_u32(bar + 1);   // the previous launch on this stream has completed: every CTA reads the same value
+  if (threadIdx.x == 0) s_epoch = ld_relaxed_u32(bar + 32);   // the previous launch on this stream has completed: every CTA reads the same value
   __syncthreads();
   unsigned epoch = s_epoch;
   const int n_phase = prog->n;
   const int N = d.B * d.T;
   int n_barrier = 0;
   const int cap = (int)gridDim.x;                            // items per phase ~ one per resident CTA (one wave)
+  // Phase descriptors are read from SHARED memory: every field access from the device-resident program was an L2 round trip
+  // in a chain of dependent loads (ncu: 30 % of the samples on the long scoreboard).  The next descriptor is prefetched while
+  // the current phase runs.
+  static_assert(sizeof(HeadPhase) % 16 == 0, "HeadPhase is copied as uint4");
+  __shared__ __align__(16) unsigned char s_phase[2][sizeof(HeadPhase)];
+  auto fetch = [&](int k, int buf) {
+    const uint4* src = reinterpret_cast<const uint4*>(&prog->ph[k]);
+    uint4* dst = reinterpret_cast<uint4*>(s_phase[buf]);
+    for (int i = threadIdx.x; i < (int)(sizeof(HeadPhase) / 16); i += kHT) dst[i] = __ldg(src + i);
+  };
+  fetch(0, 0);
   for (int k = 0; k < n_phase; ++k) {
-    const HeadPhase& ph = prog->ph[k];
+    __syncthreads();                                         // descriptor k is complete; the other buffer (phase k - 1) is free
+    if (k + 1 < n_phase) fetch(k + 1, (k + 1) & 1);
+    const HeadPhase& ph = *reinterpret_cast<const HeadPhase*>(s_phase[k & 1]);
     const bool skip = (ph.only == 1 && !d.training) || (ph.only == 2 && d.training);
     if (!skip) {
       const int M = ph.rows_n ? N : d.B;
