@@ -138,7 +138,7 @@ def flops_bytes(w):
         "dense_dw": dict(flop=score + mmoe + tower, byte=t + 2 * head_act, pipe="fp32"),
         "head_fwd": dict(flop=score + mmoe + tower, byte=t + head_act, pipe="fp32"),
         "head_bwd": dict(flop=2 * (score + mmoe + tower), byte=2 * t + 3 * head_act, pipe="fp32"),
-        "sparse_segreduce": dict(flop=0, byte=96 * (N + B), pipe="hbm"),                       # 80 B gradient row + 16 B key / index per lookup
+        "sparse_walk": dict(flop=0, byte=96 * (N + B), pipe="hbm"),                            # 80 B gradient row + 16 B rank / index per lookup
         "sparse_scatter_adam": dict(flop=0, byte=96 * (N + B), pipe="hbm"),
         "sparse_adam": dict(flop=0, byte=(6 * 64 + 4) * w["n_items"] + (6 * 16 + 4) * w["n_cates"] + 2 * (6 * 80 + 4) * w["n_users"], pipe="hbm"),
     }
@@ -203,10 +203,11 @@ def hbm_microbench(pk, dev):
         step[0] += 1
         eng._check(eng.lib.pamrec_bench_table_adam(eng.handle, step[0], st))
     ms = timed(adam)
-    byts = ni * (6 * 64 + 4)
-    out["table_adam_dense_exact"] = dict(kernel="k_table_adam_dense<16>", table_rows=ni, ms=ms, achieved=byts / ms / 1e6,
+    byts = ni * (6 * 64 + 4) + nc * (6 * 16 + 4) + 2 * 1000 * (6 * 80 + 4)
+    out["table_adam_dense_exact"] = dict(kernel="k_sp2_adam_sweep<SP2_COMPACT>", table_rows=ni, ms=ms, achieved=byts / ms / 1e6,
                                          peak=pk["hbm"], unit="GB/s", frac=byts / ms / 1e6 / pk["hbm"], bytes_per_row=6 * 64 + 4,
-                                         note="TF-exact sparse Adam: m, v, w of EVERY row read and written (6 x 64 B) + 4 B slot")
+                                         note="TF-exact sparse Adam, all four tables in one launch: m, v, w of EVERY row read and written "
+                                              "(6 x row bytes) + 4 B slot word")
     eng.close()
     del eng
     torch.cuda.empty_cache()
@@ -219,30 +220,50 @@ def hbm_microbench(pk, dev):
     eng.pool["cate_w"].normal_(0, 0.01)
     eng.pool["dense_param"].normal_(0, 0.05)
     n_look = B2 * T + B2
-    byts = n_look * ((64 + 8) + (16 + 8))                    # gradient row + sorted key / source index, per lookup and table
-    for tag, min_len, what in (("sparse_scatter_segreduce", T, "full histories (every position a real item)"),
-                               ("sparse_scatter_segreduce_padded", 1, "history lengths uniform in 1..T: half of all positions are the padding id 0")):
-        feed = synth.array_batch(77, B2, T, 50000, ni, nc, zipf_a=1.05, min_len=min_len)
-        db = eng.upload(feed)
-        for _ in range(2):
-            eng.train_step(db)
-        eng.profile(True)
-        reps = 3
-        for _ in range(reps):
-            eng.train_step(db)
-        tab = eng.profile_table()
-        eng.profile(False)
-        ms = tab["sparse_segreduce"][0] / reps               # item (16 floats) + cate (4 floats) launches of one step
-        out[tag] = dict(kernel="k_seg_reduce<16> + k_seg_reduce<4>", lookups=n_look, ms=ms, achieved=byts / ms / 1e6, peak=pk["hbm"],
-                        unit="GB/s", frac=byts / ms / 1e6 / pk["hbm"], bytes_per_lookup=96,
-                        note="inside a full train step at B=65535, T=50, Zipf(1.05) ids over 10 M items, " + what + ": 80 B of gradient "
-                             "row + 16 B of sorted key / index per lookup; the 64-B item part and the 16-B category part of a 160-B "
-                             "token row are read by separate launches, so DRAM traffic is about 2x the algorithmic bytes")
-        if min_len == T:
-            ms = tab["embed_fwd"][0] / reps
-            out["embed_fwd_in_step"] = dict(kernel="k_embed_fwd", lookups=B2 * T, ms=ms, achieved=248 * B2 * T / ms / 1e6, peak=pk["hbm"],
-                                            unit="GB/s", frac=248 * B2 * T / ms / 1e6 / pk["hbm"], note="same step; Zipf ids, so hot rows hit L2")
-        del db
+    byts = n_look * ((64 + 8) + (16 + 8))                    # gradient row + sorted rank / source index, per lookup and table
+    for mode in ("dense_exact", "lazy"):
+        if mode == "lazy":
+            eng.close()
+            del eng
+            torch.cuda.empty_cache()
+            eng = Engine(50000, ni, nc, T, B2, sparse_adam="lazy").allocate(str(dev))
+            eng.pool["item_w"].normal_(0, 0.01)
+            eng.pool["cate_w"].normal_(0, 0.01)
+            eng.pool["dense_param"].normal_(0, 0.05)
+        for tag, min_len, what in (("sparse_scatter", T, "full histories (every position a real item)"),
+                                   ("sparse_scatter_padded", 1, "history lengths uniform in 1..T: half of all positions are the padding id 0")):
+            feed = synth.array_batch(77, B2, T, 50000, ni, nc, zipf_a=1.05, min_len=min_len)
+            db = eng.upload(feed)
+            for _ in range(2):
+                eng.train_step(db)
+            eng.profile(True)
+            reps = 3
+            for _ in range(reps):
+                eng.train_step(db)
+            tab = eng.profile_table()
+            eng.profile(False)
+            ms = tab["sparse_walk"][0] / reps                    # ONE launch: item (64-byte) and category (16-byte) rows
+            uniq = eng.ws("sp.nuniq").cpu().numpy()
+            extra = 0
+            if mode == "lazy":                                   # + Adam on the touched rows inside the same kernel: w, m, v read and written
+                extra = int(uniq[0]) * 6 * 64 + int(uniq[1]) * 6 * 16
+            else:                                                # + the compact accumulator rows written for the sweep
+                extra = int(uniq[0]) * 64 + int(uniq[1]) * 16
+            key = tag + ("_fused_adam" if mode == "lazy" else "_segreduce")
+            out[key] = dict(kernel="k_sp2_walk<%s>" % ("SP2_FUSED" if mode == "lazy" else "SP2_COMPACT"), lookups=n_look,
+                            unique_rows=[int(uniq[0]), int(uniq[1])], ms=ms, achieved=(byts + extra) / ms / 1e6, peak=pk["hbm"],
+                            unit="GB/s", frac=(byts + extra) / ms / 1e6 / pk["hbm"], bytes_per_lookup=96, bytes_unique_rows=extra,
+                            plan_ms=tab["sparse_plan"][0] / reps, adam_ms=tab["sparse_adam"][0] / reps,
+                            note="inside a full train step at B=65535, T=50, Zipf(1.05) ids over 10 M items, " + what + ": 80 B of "
+                                 "gradient row + 16 B of rank / source index per lookup, plus per unique row "
+                                 + ("the Adam update applied in the same kernel (w, m, v read and written: 6 x row bytes)" if mode == "lazy"
+                                    else "its compact accumulator row (the full-table sweep follows)")
+                                 + "; plan_ms = one merged radix sort + scan on the side stream, adam_ms = what is left for the Adam launch")
+            if min_len == T and mode == "dense_exact":
+                ms = tab["embed_fwd"][0] / reps
+                out["embed_fwd_in_step"] = dict(kernel="k_embed_fwd", lookups=B2 * T, ms=ms, achieved=248 * B2 * T / ms / 1e6, peak=pk["hbm"],
+                                                unit="GB/s", frac=248 * B2 * T / ms / 1e6 / pk["hbm"], note="same step; Zipf ids, so hot rows hit L2")
+            del db
     eng.close()
     return out
 
@@ -352,8 +373,11 @@ def run_ours(args, w, rank, world):
         "config": {"workload": args.workload, "batch_per_gpu": B, "seq_len": T, "group": 5, "n_items": w["n_items"],
                    "n_cates": w["n_cates"], "n_users": w["n_users"], "sparse_adam": "dense_exact",
                    "global_batch": B * world, "tables": eng.tables,
-                   "parallelism": "single GPU" if world == 1 else f"dp{world}: groups sharded over ranks, tables row-sharded "
-                                  "(id % N) with NCCL all-to-all of rows / row gradients, sync-BN + dense all-reduce",
+                   "parallelism": "single GPU" if world == 1 else (
+                       f"dp{world}: groups sharded over ranks, " + (
+                           "tables row-sharded (id % N) with NCCL all-to-all of rows / row gradients" if eng.tables == "sharded" else
+                           "tables replicated (small vocabularies): gradient tables all-reduced with the dense gradients") +
+                       ", sync-BN through NVLink peer mailboxes inside the persistent head kernels"),
                    "l2": "flushed between timed steps (256 MiB write); per-step working set also exceeds L2",
                    "batch_note": "BASELINE batch 1024 rounded to 1025: batches must be multiples of 5",
                    "e2e_note": "PAMRECModel.train_async one step ahead (as fit_step runs): per step one pinned H2D of the feed, "

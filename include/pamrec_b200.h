@@ -48,8 +48,11 @@ enum { PAMREC_ADAM_DENSE_EXACT = 0, /* tf.train.AdamOptimizer: decay + update EV
 
 /* embedding-table placement */
 enum { PAMREC_TABLES_LOCAL = 0,     /* whole tables on this GPU, direct gather (world_size must be 1)          */
-       PAMREC_TABLES_SHARDED = 1 }; /* row r lives on rank r % world_size at local row r / world_size; rows
+       PAMREC_TABLES_SHARDED = 1,   /* row r lives on rank r % world_size at local row r / world_size; rows
                                        and row gradients travel by all-to-all (works with world_size 1 too) */
+       PAMREC_TABLES_REPLICATED = 2 }; /* every rank holds whole tables (small vocabularies): direct gather, the merged row
+                                       gradients and the looked-up-row marks are all-reduced with the dense gradients
+                                       and every rank applies the same update (world_size 1: same as LOCAL)     */
 
 /* hparams.loss */
 enum { PAMREC_LOSS_XENT = 0,        /* "cross_entropy_loss" (config/mmoe.yaml)                                  */
@@ -70,7 +73,7 @@ typedef struct PamrecConfig {
    * reference is single-device).  Each rank passes its share of one GLOBAL batch; batch-norm
    * statistics, clip norms, loss means and dense gradients are all-reduced inside the step,
    * so the result equals the single-GPU step on the concatenated batch.  world_size > 1
-   * needs pamrec_comm_init and table_mode = PAMREC_TABLES_SHARDED.                        */
+   * needs pamrec_comm_init and table_mode = PAMREC_TABLES_SHARDED or _REPLICATED.         */
   int32_t world_size, rank;
   int32_t table_mode;                /* PAMREC_TABLES_*                                                 */
   /* hparams.loss (base_model.py:195-242, pamrec.py:81-106): PAMREC_LOSS_XENT = "cross_entropy_loss" (mean sigmoid cross
@@ -103,7 +106,7 @@ typedef struct PamrecBatch {
 typedef struct PamrecBuffers {
   float* dense_param; float* dense_grad; float* dense_m; float* dense_v; /* [dense_numel] each      */
   float* bn_moving;                                                      /* [bn_numel] mean|var sets */
-  /* tables: [rows,width] with rows = vocabulary size (PAMREC_TABLES_LOCAL) or pamrec_shard_rows (SHARDED) */
+  /* tables: [rows,width] with rows = vocabulary size (PAMREC_TABLES_LOCAL / _REPLICATED) or pamrec_shard_rows (SHARDED) */
   float* item_w; float* item_m; float* item_v;                           /* [rows(n_items),16]      */
   float* cate_w; float* cate_m; float* cate_v;                           /* [rows(n_cates),4]       */
   float* ulong_w; float* ulong_m; float* ulong_v;                        /* [rows(n_users),20]      */

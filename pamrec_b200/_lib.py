@@ -10,7 +10,7 @@ POOL_DENSE, POOL_BN, POOL_WORKSPACE = 0, 1, 2
 F32, I32, F64, U8 = 0, 1, 2, 3
 SEG_L2, SEG_POS, SEG_DEAD = 1, 2, 4
 ADAM_DENSE_EXACT, ADAM_LAZY = 0, 1
-TABLES_LOCAL, TABLES_SHARDED = 0, 1
+TABLES_LOCAL, TABLES_SHARDED, TABLES_REPLICATED = 0, 1, 2
 LOSS_XENT, LOSS_SOFTMAX = 0, 1
 COMM_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64

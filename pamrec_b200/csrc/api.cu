@@ -36,6 +36,7 @@ struct PamrecHandle_ {
   Xchg xc[3];                   // item, cate, user
   bool xc_users = false;        // the current exchange carried user ids (training)
   bool sharded() const { return cfg.table_mode == PAMREC_TABLES_SHARDED; }
+  bool replicated() const { return cfg.table_mode == PAMREC_TABLES_REPLICATED && cfg.world_size > 1; }
   // Internal side stream: work that is off the critical path of a step (the id sort of the sparse plan, the weight-gradient
   // GEMMs of the head) is forked from the caller's stream with events and joined back before anything consumes it.
   cudaStream_t side = nullptr;
@@ -143,8 +144,9 @@ int pamrec_create(const PamrecConfig* cfg, PamrecHandle* out) {
   if (cfg->max_batch < 1) return -4;
   const int world = cfg->world_size < 1 ? 1 : cfg->world_size;
   if (world > 64 || cfg->rank < 0 || cfg->rank >= world) return -5;
-  if (cfg->table_mode != PAMREC_TABLES_LOCAL && cfg->table_mode != PAMREC_TABLES_SHARDED) return -6;
-  if (world > 1 && cfg->table_mode != PAMREC_TABLES_SHARDED) return -6;      // multi-GPU = row-sharded tables
+  if (cfg->table_mode != PAMREC_TABLES_LOCAL && cfg->table_mode != PAMREC_TABLES_SHARDED && cfg->table_mode != PAMREC_TABLES_REPLICATED) return -6;
+  if (world > 1 && cfg->table_mode == PAMREC_TABLES_LOCAL) return -6;        // multi-GPU = row-sharded or replicated tables
+  if (cfg->table_mode != PAMREC_TABLES_SHARDED && (int64_t)cfg->n_items + cfg->n_cates + cfg->n_users >= ((int64_t)1 << 31)) return -7;
   if (cfg->loss_kind != PAMREC_LOSS_XENT && cfg->loss_kind != PAMREC_LOSS_SOFTMAX) return -8;
   if (cfg->loss_kind == PAMREC_LOSS_SOFTMAX) {
     const int g = cfg->softmax_group < 1 ? 1 : cfg->softmax_group;
@@ -279,6 +281,18 @@ int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(h, "no CUDA device: the CUDA path is the only path"); }
   h->buf = *bufs;
+  {
+    // experiment hook: DRAM -> L2 fetch granularity (a device-wide hint, 32 / 64 / 128 bytes); unset = leave the driver's default
+    const char* fg = getenv("PAMREC_L2_FETCH");
+    if (fg != nullptr) {
+      size_t before = 0, after = 0;
+      cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+      cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg));
+      cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+      fprintf(stderr, "pamrec: L2 fetch granularity %zu -> %zu\n", before, after);
+      cudaGetLastError();
+    }
+  }
   if (init_encoder_kernels(h->cfg.max_seq_len)) return check_cuda(h, "shared-memory opt-in of the encoder kernels");
   {
     int dev = 0;
@@ -297,12 +311,17 @@ int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
   static const char* names[BN_COUNT] = {"s0", "s1", "e0", "g0", "e1", "g1", "t0", "t1"};
   for (int i = 0; i < BN_COUNT; ++i) h->bn[i] = make_bn(h, i, names[i]);
   size_t need = sparse_temp_bytes(h->L.cub_keys);
+  if (!h->sharded()) { const size_t n2 = sp2_temp_bytes(h->L.cub_keys); need = n2 > need ? n2 : need; }
   size_t have = (size_t)h->L.ws[h->L.ws_index["cub_temp"]].numel;
   if (need > have) return fail(h, "cub temp storage: need %zu have %zu", need, have);
   cudaMemsetAsync(h->buf.workspace, 0, h->L.ws_bytes, st);
-  cudaMemsetAsync(h->wi("sp.item.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_items) * 4, st);
-  cudaMemsetAsync(h->wi("sp.cate.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_cates) * 4, st);
-  cudaMemsetAsync(h->wi("sp.user.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_users) * 4, st);
+  if (h->sharded()) {
+    cudaMemsetAsync(h->wi("sp.item.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_items) * 4, st);
+    cudaMemsetAsync(h->wi("sp.cate.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_cates) * 4, st);
+    cudaMemsetAsync(h->wi("sp.user.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_users) * 4, st);
+  } else {
+    cudaMemsetAsync(h->wi("sp2.slot"), 0xFF, ((size_t)h->cfg.n_items + h->cfg.n_cates + h->cfg.n_users) * 4, st);
+  }
   if (h->sharded() && !h->h_counts &&
       cudaMallocHost(&h->h_counts, sizeof(int) * (8 * (size_t)h->cfg.world_size + 4)) != cudaSuccess)
     return fail(h, "cudaMallocHost for the exchange counts failed");
@@ -318,7 +337,7 @@ static int check_batch(PamrecHandle h, const PamrecBatch* b, bool training) {
   if (!h) return -1;
   if (!h->bound) return fail(h, "pamrec_bind has not been called");
   if (!b) return fail(h, "null batch");
-  if (b->batch == 0 && h->sharded()) return 0;          // this rank only takes part in the collectives
+  if (b->batch == 0 && (h->sharded() || h->cfg.world_size > 1)) return 0;  // this rank only takes part in the collectives
   if (b->batch < 1 || b->batch > h->cfg.max_batch) return fail(h, "batch %d outside [1, %d]", b->batch, h->cfg.max_batch);
   if (training && b->batch % PAMREC_GROUP != 0)
     return fail(h, "training batch %d is not a multiple of %d (pamrec.py:73-75)", b->batch, PAMREC_GROUP);
@@ -330,24 +349,35 @@ static int check_batch(PamrecHandle h, const PamrecBatch* b, bool training) {
   return 0;
 }
 
-static SparseTable table_of(PamrecHandle h, const char* which) {
-  SparseTable t;
-  memset(&t, 0, sizeof t);
-  std::string w = which;
-  std::string p = (w == "item" || w == "cate") ? "sp." + w + "." : "sp.user.";
-  t.keys = h->wi(p + "keys"); t.idx = h->wi(p + "idx"); t.skeys = h->wi(p + "skeys"); t.sidx = h->wi(p + "sidx");
-  t.uidx = h->wi(p + "uidx"); t.ukeys = h->wi(p + "ukeys"); t.slot = h->wi(p + "slot");
-  int* nu = h->wi("sp.nuniq");
-  double* ns = h->wd("sp_normsq");
-  if (w == "item") { t.width = kI; t.n_rows = h->cfg.n_items; t.w = h->buf.item_w; t.m = h->buf.item_m; t.v = h->buf.item_v;
-                     t.accum = h->wf("sp.item.accum"); t.nuniq = nu; t.normsq = ns; }
-  else if (w == "cate") { t.width = kC; t.n_rows = h->cfg.n_cates; t.w = h->buf.cate_w; t.m = h->buf.cate_m; t.v = h->buf.cate_v;
-                          t.accum = h->wf("sp.cate.accum"); t.nuniq = nu + 1; t.normsq = ns + 1; }
-  else if (w == "ulong") { t.width = PAMREC_USER_DIM; t.n_rows = h->cfg.n_users; t.w = h->buf.ulong_w; t.m = h->buf.ulong_m;
-                           t.v = h->buf.ulong_v; t.accum = nullptr; t.nuniq = nu + 2; t.normsq = ns + 2; }
-  else { t.width = PAMREC_USER_DIM; t.n_rows = h->cfg.n_users; t.w = h->buf.ushort_w; t.m = h->buf.ushort_m;
-         t.v = h->buf.ushort_v; t.accum = nullptr; t.nuniq = nu + 2; t.normsq = ns + 3; }
-  return t;
+// whole tables on this GPU (local or replicated): the one-sort plan / run walk of kernels_sparse2.cu
+static Sp2 make_sp2(PamrecHandle h, const PamrecBatch* b) {
+  Sp2 s;
+  memset(&s, 0, sizeof s);
+  const PamrecConfig& c = h->cfg;
+  s.item_hist = b->item_history; s.cate_hist = b->item_cate_history; s.items = b->items; s.cates = b->cates; s.users = b->users;
+  s.B = b->batch; s.N = (int64_t)b->batch * c.max_seq_len;
+  s.n_items = c.n_items; s.n_cates = c.n_cates; s.n_users = c.n_users;
+  s.keys = h->wi("sp2.keys"); s.idx = h->wi("sp2.idx"); s.skeys = h->wi("sp2.skeys"); s.sidx = h->wi("sp2.sidx"); s.uidx = h->wi("sp2.uidx");
+  s.ukeys[0] = h->wi("sp.item.ukeys"); s.ukeys[1] = h->wi("sp.cate.ukeys"); s.ukeys[2] = h->wi("sp.user.ukeys");
+  s.nuniq = h->wi("sp.nuniq"); s.meta = h->wi("sp2.meta");
+  s.accum[0] = h->wf("sp.item.accum"); s.accum[1] = h->wf("sp.cate.accum");
+  s.dflag[0] = h->wi("sp2.dflag"); s.dflag[1] = s.dflag[0] + h->L.cub_keys_table;
+  s.l2sq = h->wd("sp2.l2sq"); s.undedup = h->wd("sp_normsq");
+  s.w[0] = h->buf.item_w; s.m[0] = h->buf.item_m; s.v[0] = h->buf.item_v;
+  s.w[1] = h->buf.cate_w; s.m[1] = h->buf.cate_m; s.v[1] = h->buf.cate_v;
+  s.w[2] = h->buf.ulong_w; s.m[2] = h->buf.ulong_m; s.v[2] = h->buf.ulong_v;
+  s.w[3] = h->buf.ushort_w; s.m[3] = h->buf.ushort_m; s.v[3] = h->buf.ushort_v;
+  s.dX0 = h->wf("g_a"); s.dT = h->wf("d_tgt_total");
+  if (h->replicated()) { s.mode = SP2_DENSE; s.rep_grad = h->wf("rep.grad"); }
+  else if (c.sparse_adam_mode == PAMREC_ADAM_LAZY) s.mode = SP2_FUSED;
+  else { s.mode = SP2_COMPACT; s.slot = h->wi("sp2.slot"); }
+  return s;
+}
+static AdamP make_adam(PamrecHandle h, float lr_t) {
+  const PamrecConfig& c = h->cfg;
+  AdamP a;
+  a.lr = lr_t; a.b1 = c.beta1; a.b2 = c.beta2; a.eps = c.epsilon; a.l2 = c.embed_l2; a.clip = c.max_grad_norm; a.is_clip = c.is_clip_norm;
+  return a;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -553,16 +583,11 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
   float* x0 = h->wf("x0");
   if (int rc = embed_forward(h, b, training != 0, x0, st)) return rc;
   nl += 1;
-  if (training && !h->sharded()) {
+  if (training && !h->sharded() && B > 0) {
     // the id sort / unique pass of the sparse backward depends on the batch only: run it beside the forward pass
     int prc = 0;
     h->fork(st, [&](cudaStream_t s2) {
-      void* tmp = h->ws<char>("cub_temp");
-      const size_t tmp_bytes = (size_t)L.ws[L.ws_index.at("cub_temp")].numel;
-      SparseTable ti = table_of(h, "item"), tc = table_of(h, "cate"), tu = table_of(h, "ulong");
-      prc |= launch_sparse_plan(ti, b->item_history, b->items, N, B, 1, 0, ti.n_rows, true, tmp, tmp_bytes, s2);
-      prc |= launch_sparse_plan(tc, b->item_cate_history, b->cates, N, B, 1, 0, tc.n_rows, true, tmp, tmp_bytes, s2);
-      prc |= launch_sparse_plan(tu, b->users, nullptr, B, 0, 1, 0, tu.n_rows, true, tmp, tmp_bytes, s2);
+      prc |= launch_sp2_plan(make_sp2(h, b), h->ws<char>("cub_temp"), (size_t)L.ws[L.ws_index.at("cub_temp")].numel, s2);
       cudaEventRecord(h->ev_plan, s2);
     });
     if (prc) return fail(h, "cub sort failed");
@@ -1122,7 +1147,8 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
     nl += 3;
   }
   // dX0 is in g_a
-  launch_embed_bwd_reduce(g_a, h->wf("d_tgt"), h->wf("d_tgt_total"), h->G(L.pos), h->wd("sp_normsq") + 4, B, T, st); nl += 2;
+  launch_embed_bwd_reduce(g_a, h->wf("d_tgt"), h->wf("d_tgt_total"), h->G(L.pos), h->wd("sp_normsq") + 4,
+                          h->sharded() ? nullptr : h->wd("sp_normsq"), B, T, st); nl += 2;
   h->join(st);                    // the head's weight-gradient GEMMs (side stream) are complete from here on
   if (crc) return fail(h, "nccl: %s", h->comm.err.c_str());
   return check_cuda(h, "backward");
@@ -1195,37 +1221,37 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
       launch_slot_reset(own, nr, st);
     }
   } else {
-  const bool planned = h->plan_for == b->item_history && h->plan_rows == B;
-  h->plan_for = nullptr;
-  if (planned) cudaStreamWaitEvent(st, h->ev_plan, 0);       // plans of all three tables were sorted beside the forward pass
-  {
-    SparseTable t = table_of(h, "item");
-    if (!planned && launch_sparse_plan(t, b->item_history, b->items, N, B, 1, 0, t.n_rows, true, tmp, tmp_bytes, st)) return fail(h, "cub sort failed");
-    launch_sparse_segreduce(t, N + B, N, dX0, kD, 0, dT, kE, 0, t.normsq, st);
-    launch_sparse_l2norm(t, N + B, c.embed_l2, reg, st);
-    launch_sparse_adam(t, N + B, c.sparse_adam_mode, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm, c.is_clip_norm, st);
-    launch_slot_reset(t, N + B, st);
-    nl += 7;
-  }
-  {
-    SparseTable t = table_of(h, "cate");
-    if (!planned && launch_sparse_plan(t, b->item_cate_history, b->cates, N, B, 1, 0, t.n_rows, true, tmp, tmp_bytes, st)) return fail(h, "cub sort failed");
-    launch_sparse_segreduce(t, N + B, N, dX0, kD, kI, dT, kE, kI, t.normsq, st);
-    launch_sparse_l2norm(t, N + B, c.embed_l2, reg, st);
-    launch_sparse_adam(t, N + B, c.sparse_adam_mode, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm, c.is_clip_norm, st);
-    launch_slot_reset(t, N + B, st);
-    nl += 7;
-  }
-  {
-    SparseTable tl = table_of(h, "ulong"), ts = table_of(h, "ushort");
-    if (!planned && launch_sparse_plan(tl, b->users, nullptr, B, 0, 1, 0, tl.n_rows, true, tmp, tmp_bytes, st)) return fail(h, "cub sort failed");
-    launch_sparse_l2norm(tl, B, c.embed_l2, reg, st);
-    launch_sparse_l2norm(ts, B, c.embed_l2, reg, st);
-    launch_sparse_adam(tl, B, c.sparse_adam_mode, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm, c.is_clip_norm, st);
-    launch_sparse_adam(ts, B, c.sparse_adam_mode, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm, c.is_clip_norm, st);
-    launch_slot_reset(tl, B, st);
-    nl += 8;
-  }
+    // ---- whole tables on this GPU: one-sort plan (side stream, beside the forward pass) -> run walk -> Adam
+    const bool planned = h->plan_for == b->item_history && h->plan_rows == B;
+    h->plan_for = nullptr;
+    const Sp2 s2 = make_sp2(h, b);
+    const AdamP ap = make_adam(h, lr_t);
+    if (planned) cudaStreamWaitEvent(st, h->ev_plan, 0);
+    else if (launch_sp2_plan(s2, tmp, tmp_bytes, st)) return fail(h, "cub sort failed");
+    launch_sp2_walk(s2, ap, st);
+    nl += 10;
+    if (h->replicated()) {
+      // replicated tables: gradient tables + touch counts, dense gradients, clip norms and losses summed over the ranks
+      Comm& cm = h->comm;
+      int crc = 0;
+      {
+        PAMREC_PROF("allreduce_grads", 1, st);
+        crc |= cm.group_start();
+        crc |= cm.all_reduce(h->buf.dense_grad, L.dense_numel, COMM_F32, st);
+        crc |= cm.all_reduce(s2.rep_grad, sp2_rep_floats(c.n_items, c.n_cates, c.n_users), COMM_F32, st);
+        crc |= cm.all_reduce(h->wd("sp_normsq"), 8, COMM_F64, st);
+        crc |= cm.all_reduce(h->wd("loss_acc"), 4, COMM_F64, st);
+        crc |= cm.group_end();
+      }
+      if (crc) return fail(h, "nccl: %s", cm.err.c_str());
+      launch_sp2_rep_l2(s2, st);
+      launch_sp2_adam_sweep(s2, ap, c.sparse_adam_mode == PAMREC_ADAM_LAZY ? 1 : 0, st);
+      nl += 3;
+    } else if (s2.mode == SP2_FUSED) {
+      launch_sp2_lazy_finish(s2, ap, st); nl += 1;
+    } else {
+      launch_sp2_adam_sweep(s2, ap, 0, st); nl += 1;
+    }
   }
   const int n_seg = (int)L.dense.size();
   launch_dense_norm(h->buf.dense_param, h->buf.dense_grad, h->wi("seg_tab"), n_seg, c.layer_l2, h->wd("seg_normsq"),
@@ -1233,7 +1259,7 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
   launch_dense_adam(h->buf.dense_param, h->buf.dense_grad, h->buf.dense_m, h->buf.dense_v, h->wi("seg_id"), h->wi("seg_tab"),
                     h->wd("seg_normsq"), L.dense_numel, c.layer_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm,
                     c.is_clip_norm, st);
-  launch_finish_losses(h->wd("loss_acc"), h->wf("losses"), st);
+  launch_finish_losses(h->wd("loss_acc"), h->wf("losses"), h->sharded() ? nullptr : h->wd("sp2.l2sq"), c.embed_l2, h->wd("sp_normsq"), st);
   nl += 3;
   return check_cuda(h, "apply_gradients");
 }
@@ -1273,9 +1299,12 @@ int pamrec_bench_table_adam(PamrecHandle h, int64_t step, void* stream) {
   const PamrecConfig& c = h->cfg;
   const double b1 = c.beta1, b2 = c.beta2;
   const float lr_t = (float)((double)c.learning_rate * std::sqrt(1.0 - std::pow(b2, (double)step)) / (1.0 - std::pow(b1, (double)step)));
-  SparseTable t = table_of(h, "item");
-  launch_sparse_adam(t, 0, PAMREC_ADAM_DENSE_EXACT, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm, c.is_clip_norm,
-                     (cudaStream_t)stream);
+  if (h->sharded()) return fail(h, "bench_table_adam runs on whole tables");
+  PamrecBatch nb;
+  memset(&nb, 0, sizeof nb);
+  Sp2 s2 = make_sp2(h, &nb);                              // no lookups: every row decays, none is touched
+  s2.mode = SP2_COMPACT; s2.slot = h->wi("sp2.slot");
+  launch_sp2_adam_sweep(s2, make_adam(h, lr_t), 0, (cudaStream_t)stream);
   return check_cuda(h, "bench_table_adam");
 }
 

@@ -91,8 +91,9 @@ struct SparseTable {
   int* nuniq;                 // device scalar
   double* normsq;             // device scalar: sum of squares of every un-deduplicated gradient row
 };
+// undedup (nullable): [0] += sum of squares of every item gradient row (history and target lookups), [1] likewise category rows
 void launch_embed_bwd_reduce(const float* dX0, const float* dTgtHead, float* dTgtTotal, float* dPos, double* pos_normsq,
-                             int B, int T, cudaStream_t st);
+                             double* undedup, int B, int T, cudaStream_t st);
 size_t sparse_temp_bytes(int64_t n_keys);
 // builds keys (history ids then target ids), sorts, finds unique rows, reduces duplicate rows into accum
 int launch_sparse_reduce(const SparseTable& t, const int* hist_ids, const int* tgt_ids, int64_t n_hist, int64_t n_tgt,
@@ -113,7 +114,38 @@ void launch_dense_norm(const float* P, const float* G, const int* seg_tab, int n
 void launch_dense_adam(float* P, const float* G, float* M, float* V, const int* seg_id, const int* seg_tab,
                        const double* seg_normsq, int64_t n, float layer_l2, float lr_t, float b1, float b2, float eps,
                        float clip, int is_clip, cudaStream_t st);
-void launch_finish_losses(const double* loss_acc, float* losses, cudaStream_t st);
+// l2sq (nullable): |w|^2 of the unique looked-up rows per table (kernels_sparse2.cu) - their share of the regularisation loss
+// and of the clip norms (added to sp_normsq[0..3] here, after every consumer has run, so that sp_normsq reads as the full norm)
+void launch_finish_losses(const double* loss_acc, float* losses, const double* l2sq, float embed_l2, double* sp_normsq, cudaStream_t st);
+
+// ---- kernels_sparse2.cu (one-sort plan, run walk with fused Adam; local and replicated tables)
+enum { SP2_COMPACT = 0,   // DENSE_EXACT on local tables: run sums -> compact accumulator, row -> unique index map, full sweep
+       SP2_FUSED = 1,     // LAZY on local tables: Adam applied to the row inside the walk
+       SP2_DENSE = 2 };   // replicated tables (data parallel): run sums -> dense gradient table + touch counts, all-reduced, sweep
+struct AdamP { float lr, b1, b2, eps, l2, clip; int is_clip; };
+struct Sp2 {
+  const int* item_hist; const int* cate_hist; const int* items; const int* cates; const int* users;
+  int64_t N; int B;                                  // history positions (B * T), rows
+  int n_items, n_cates, n_users;
+  int* keys; int* idx; int* skeys; int* sidx; int* uidx;   // [2 (N + B) + B]: item lookups | category lookups | users
+  int* ukeys[3]; int* nuniq;                         // per table: sorted unique ids, their count (nuniq[0..2])
+  int* meta;                                         // [0..2] global unique index of the first run of table t, [3] total
+  int* slot;                                         // COMPACT: [n_items + n_cates + n_users] row -> unique index of its table, or -1
+  float* accum[2]; int* dflag[2];                    // compact run sums [unique][width]; FUSED: rows left to k_sp2_lazy_finish
+  double* l2sq;                                      // [4] item cate user_long user_short: |w|^2 over the unique rows
+  const double* undedup;                             // [4] squared norm of the un-deduplicated gradient rows (sp_normsq)
+  float* w[4]; float* m[4]; float* v[4];             // item cate user_long user_short
+  const float* dX0; const float* dT;                 // [N,40] token gradients (item 0:16, cate 16:20); [B,20] target-row gradients
+  float* rep_grad;                                   // DENSE: G_item [n_items,16] | G_cate [n_cates,4] | touch [n_items+n_cates+n_users]
+  int mode;
+};
+inline int64_t sp2_rep_floats(int64_t n_items, int64_t n_cates, int64_t n_users) { return n_items * 17 + n_cates * 5 + n_users; }
+size_t sp2_temp_bytes(int64_t n_keys);
+int launch_sp2_plan(const Sp2& s, void* cub_temp, size_t cub_bytes, cudaStream_t st);
+void launch_sp2_walk(const Sp2& s, const AdamP& a, cudaStream_t st);
+void launch_sp2_lazy_finish(const Sp2& s, const AdamP& a, cudaStream_t st);
+void launch_sp2_adam_sweep(const Sp2& s, const AdamP& a, int lazy, cudaStream_t st);
+void launch_sp2_rep_l2(const Sp2& s, cudaStream_t st);
 
 // ---- kernels_p2p.cu (small all-reduces through NVLink peer mailboxes)
 constexpr int kP2PMaxDoubles = 2048;     // payload capacity of one mailbox slot (expert + gate layer-0 sums: 1256)

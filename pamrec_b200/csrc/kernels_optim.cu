@@ -20,21 +20,32 @@ namespace pamrec {
 // d_tgt_total[b,:] = d_tgt_head[b,:] + sum_t dX0[b,t,20:40];  pos_normsq += |dX0|^2;
 // dPos[t,:] += sum_b dX0[b,t,:]
 __global__ void __launch_bounds__(128) k_dtgt_total(const float* __restrict__ dX0, const float* __restrict__ dTgtHead,
-                                                    float* __restrict__ dTgtTotal, double* __restrict__ pos_normsq, int T) {
-  __shared__ double sh[4];
+                                                    float* __restrict__ dTgtTotal, double* __restrict__ pos_normsq,
+                                                    double* __restrict__ undedup, int T) {
+  __shared__ double sh[3][4];
   const int b = blockIdx.x, tid = threadIdx.x;
   const float* base = dX0 + (int64_t)b * T * kD;
-  double sq = 0.0;
-  for (int i = tid; i < T * kD; i += 128) { float v = base[i]; sq += (double)v * (double)v; }
-  sq = warp_sum_d(sq);
-  if ((tid & 31) == 0) sh[tid >> 5] = sq;
-  __syncthreads();
-  if (tid == 0) atomicAdd(pos_normsq, sh[0] + sh[1] + sh[2] + sh[3]);
+  // squared norms of the rows this sample contributes to the three IndexedSlices gradients: position rows (all 40 columns),
+  // item history rows (columns 0:16), category history rows (16:20); the target rows follow below
+  double sq = 0.0, sq_i = 0.0, sq_c = 0.0;
+  for (int i = tid; i < T * kD; i += 128) {
+    const float v = base[i];
+    const double q = (double)v * (double)v;
+    const int col = i % kD;
+    sq += q;
+    if (col < kI) sq_i += q; else if (col < kE) sq_c += q;
+  }
   if (tid < kE) {
     float s = dTgtHead[(int64_t)b * kE + tid];
     for (int t = 0; t < T; ++t) s += base[t * kD + kE + tid];
     dTgtTotal[(int64_t)b * kE + tid] = s;
+    if (tid < kI) sq_i += (double)s * (double)s; else sq_c += (double)s * (double)s;
   }
+  sq = warp_sum_d(sq); sq_i = warp_sum_d(sq_i); sq_c = warp_sum_d(sq_c);
+  if ((tid & 31) == 0) { sh[0][tid >> 5] = sq; sh[1][tid >> 5] = sq_i; sh[2][tid >> 5] = sq_c; }
+  __syncthreads();
+  if (tid == 0) atomicAdd(pos_normsq, sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3]);
+  if (undedup != nullptr && (tid == 1 || tid == 2)) atomicAdd(undedup + (tid - 1), sh[tid][0] + sh[tid][1] + sh[tid][2] + sh[tid][3]);
 }
 constexpr int kPosRows = 64;
 __global__ void k_pos_grad(const float* __restrict__ dX0, float* __restrict__ dPos, int B, int T) {
@@ -46,9 +57,9 @@ __global__ void k_pos_grad(const float* __restrict__ dX0, float* __restrict__ dP
   atomicAdd(dPos + e, s);
 }
 void launch_embed_bwd_reduce(const float* dX0, const float* dTgtHead, float* dTgtTotal, float* dPos, double* pos_normsq,
-                             int B, int T, cudaStream_t st) { PAMREC_PROF("embed_bwd_reduce", 2, st);
+                             double* undedup, int B, int T, cudaStream_t st) { PAMREC_PROF("embed_bwd_reduce", 2, st);
   if (B == 0) return;
-  k_dtgt_total<<<B, 128, 0, st>>>(dX0, dTgtHead, dTgtTotal, pos_normsq, T);
+  k_dtgt_total<<<B, 128, 0, st>>>(dX0, dTgtHead, dTgtTotal, pos_normsq, undedup, T);
   dim3 grid((T * kD + 127) / 128, (B + kPosRows - 1) / kPosRows);
   k_pos_grad<<<grid, 128, 0, st>>>(dX0, dPos, B, T);
 }
@@ -413,14 +424,23 @@ void launch_dense_adam(float* P, const float* G, float* M, float* V, const int* 
                                                            eps, clip, is_clip);
 }
 
-__global__ void k_finish_losses(const double* __restrict__ acc, float* __restrict__ losses) {
+__global__ void k_finish_losses(const double* __restrict__ acc, float* __restrict__ losses, const double* __restrict__ l2sq,
+                                float embed_l2, double* __restrict__ sp_normsq) {
   // pamrec.py:444-448 order: loss, data_loss, regular_loss, auxiliary_data_loss, order_loss
-  losses[0] = (float)(acc[0] + acc[3] + acc[1] + acc[2]);
+  double reg = acc[3];
+  if (l2sq != nullptr) {
+    reg += 0.5 * (double)embed_l2 * (l2sq[0] + l2sq[1] + l2sq[2] + l2sq[3]);
+    for (int t = 0; t < 4; ++t) sp_normsq[t] += (double)embed_l2 * (double)embed_l2 * l2sq[t];
+  }
+  losses[0] = (float)(acc[0] + reg + acc[1] + acc[2]);
   losses[1] = (float)acc[0];
-  losses[2] = (float)acc[3];
+  losses[2] = (float)reg;
   losses[3] = (float)acc[1];
   losses[4] = (float)acc[2];
 }
-void launch_finish_losses(const double* loss_acc, float* losses, cudaStream_t st) { PAMREC_PROF("finish_losses", 1, st); k_finish_losses<<<1, 1, 0, st>>>(loss_acc, losses); }
+void launch_finish_losses(const double* loss_acc, float* losses, const double* l2sq, float embed_l2, double* sp_normsq, cudaStream_t st) {
+  PAMREC_PROF("finish_losses", 1, st);
+  k_finish_losses<<<1, 1, 0, st>>>(loss_acc, losses, l2sq, embed_l2, sp_normsq);
+}
 
 }  // namespace pamrec

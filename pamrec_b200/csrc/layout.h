@@ -35,6 +35,7 @@ struct Layout {
   int world = 1, table_mode = 0;
   ShardDim sh_item, sh_cate, sh_user;
   int64_t cub_keys = 0;                         // largest key count handed to cub
+  int64_t cub_keys_table = 0;                   // lookups of one table per batch (N + B)
   int64_t rows_of(int64_t vocab) const { return table_mode == PAMREC_TABLES_SHARDED ? (vocab + world - 1) / world : vocab; }
   std::vector<TensorDesc> dense, bn, ws;
   int64_t dense_numel = 0, bn_numel = 0;
@@ -222,27 +223,45 @@ struct Layout {
     // sparse path: keys = history ids then target ids.  "sp.*" is the plan of THIS rank's lookups; the slot map
     // (table row -> unique index) always covers the rows this rank owns.
     const int64_t NK = N + B;
+    const bool sharded = table_mode == PAMREC_TABLES_SHARDED;
+    cub_keys_table = NK;
     for (const char* t : {"item", "cate"}) {
       std::string p = std::string("sp.") + t + ".";
-      add_ws(p + "keys", PAMREC_I32, {NK});
-      add_ws(p + "idx", PAMREC_I32, {NK});
-      add_ws(p + "skeys", PAMREC_I32, {NK});
-      add_ws(p + "sidx", PAMREC_I32, {NK});
-      add_ws(p + "uidx", PAMREC_I32, {NK});
+      if (sharded) {
+        add_ws(p + "keys", PAMREC_I32, {NK});
+        add_ws(p + "idx", PAMREC_I32, {NK});
+        add_ws(p + "skeys", PAMREC_I32, {NK});
+        add_ws(p + "sidx", PAMREC_I32, {NK});
+        add_ws(p + "uidx", PAMREC_I32, {NK});
+        add_ws(p + "slot", PAMREC_I32, {rows_of(t[0] == 'i' ? n_items : n_cates)});
+      }
       add_ws(p + "ukeys", PAMREC_I32, {NK});
       add_ws(p + "accum", PAMREC_F32, {NK, t[0] == 'i' ? kI : kC});
-      add_ws(p + "slot", PAMREC_I32, {rows_of(t[0] == 'i' ? n_items : n_cates)});
     }
-    add_ws("sp.user.keys", PAMREC_I32, {B});
-    add_ws("sp.user.idx", PAMREC_I32, {B});
-    add_ws("sp.user.skeys", PAMREC_I32, {B});
-    add_ws("sp.user.sidx", PAMREC_I32, {B});
-    add_ws("sp.user.uidx", PAMREC_I32, {B});
+    if (sharded) {
+      add_ws("sp.user.keys", PAMREC_I32, {B});
+      add_ws("sp.user.idx", PAMREC_I32, {B});
+      add_ws("sp.user.skeys", PAMREC_I32, {B});
+      add_ws("sp.user.sidx", PAMREC_I32, {B});
+      add_ws("sp.user.uidx", PAMREC_I32, {B});
+      add_ws("sp.user.slot", PAMREC_I32, {rows_of(n_users)});
+    }
     add_ws("sp.user.ukeys", PAMREC_I32, {B});
-    add_ws("sp.user.slot", PAMREC_I32, {rows_of(n_users)});
     add_ws("sp.nuniq", PAMREC_I32, {8});           // 0 item 1 cate 2 user ; 4 5 6 = owner-side plans (sharded tables)
     add_ws("dp.scalars", PAMREC_F64, {8});         // [0] listwise groups with a non-zero label sum over all ranks
     cub_keys = NK;
+    if (!sharded) {
+      // whole tables on this GPU (kernels_sparse2.cu): ONE plan over the lookups of the three id spaces
+      const int64_t NKA = 2 * NK + B;
+      for (const char* n : {"keys", "idx", "skeys", "sidx", "uidx"}) add_ws(std::string("sp2.") + n, PAMREC_I32, {NKA});
+      add_ws("sp2.meta", PAMREC_I32, {16});
+      add_ws("sp2.slot", PAMREC_I32, {(int64_t)n_items + n_cates + n_users});
+      add_ws("sp2.dflag", PAMREC_I32, {2 * NK});
+      add_ws("sp2.l2sq", PAMREC_F64, {4});
+      if (table_mode == PAMREC_TABLES_REPLICATED && world > 1)
+        add_ws("rep.grad", PAMREC_F32, {(int64_t)n_items * 17 + (int64_t)n_cates * 5 + n_users});
+      cub_keys = NKA;
+    }
     if (table_mode == PAMREC_TABLES_SHARDED) {
       // exchange buffers ("sh.*") and the owner-side plan of the rows other ranks asked this rank for ("so.*")
       auto dim = [&](int64_t vocab, int64_t nk, int width) {

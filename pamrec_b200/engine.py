@@ -30,6 +30,10 @@ DEFAULT_HP = dict(learning_rate=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8, embe
                   max_grad_norm=2.0, is_clip_norm=1, fuzhu_weight=0.5, discrepancy_loss_weight=0.1,
                   loss="cross_entropy_loss", softmax_group=1)      # hparams.loss / train_num_ngs + 1 (base_model.py:195-242)
 
+# tables="auto" on several GPUs: replicate the tables when they are this small (the all-reduce of their gradient tables costs
+# less than the id / row / gradient exchange of the sharded layout; 64 MiB of tables = 16 MiB of item gradients per step)
+REPLICATE_BYTES = 64 * 2 ** 20
+
 BATCH_FIELDS = (  # name, dtype, per-row shape suffix, needed for scoring
     ("item_history", np.int32, True), ("item_cate_history", np.int32, True), ("item_loop_times_history", np.float32, True),
     ("mask", np.int32, True), ("users", np.int32, False), ("items", np.int32, False), ("cates", np.int32, False),
@@ -87,14 +91,22 @@ class PendingHost:
 class Engine:
     def __init__(self, n_users, n_items, n_cates, max_seq_len, max_batch, hp=None, sparse_adam="dense_exact",
                  world_size=1, rank=0, tables=None):
-        """tables: "local" (whole tables on this GPU) or "sharded" (row r on rank r % world_size, rows and row gradients
-        exchanged by all-to-all; required for world_size > 1, also runs on one GPU)."""
+        """tables: "local" (whole tables on this GPU, world_size 1), "replicated" (every rank holds whole tables; the merged
+        row gradients are all-reduced with the dense gradients and every rank applies the same update), "sharded" (row r on
+        rank r % world_size, rows and row gradients exchanged by all-to-all; also runs on one GPU) or "auto" / None: local on one
+        GPU; on several, replicated while the four tables together stay below REPLICATE_BYTES (PAMREC_REPLICATE_MB), else sharded."""
         self.lib = L.load()
         self.world, self.rank = int(world_size), int(rank)
-        if tables is None:
-            tables = "sharded" if self.world > 1 else "local"
-        if self.world > 1 and tables != "sharded":
-            raise PamrecError("world_size > 1 needs tables='sharded'")
+        if tables in (None, "auto"):
+            table_bytes = 4 * (int(n_items) * 16 + int(n_cates) * 4 + 2 * int(n_users) * 20)
+            limit = float(os.environ.get("PAMREC_REPLICATE_MB", REPLICATE_BYTES / 2 ** 20)) * 2 ** 20
+            tables = "local" if self.world == 1 else ("replicated" if table_bytes <= limit else "sharded")
+        if tables == "replicated" and self.world == 1:
+            tables = "local"
+        if tables not in ("local", "replicated", "sharded"):
+            raise PamrecError(f"unknown table placement {tables!r}")
+        if self.world > 1 and tables == "local":
+            raise PamrecError("world_size > 1 needs tables='replicated' or 'sharded'")
         self.tables = tables
         h = dict(DEFAULT_HP)
         if hp:
@@ -108,7 +120,7 @@ class Engine:
             embed_l2=h["embed_l2"], layer_l2=h["layer_l2"], max_grad_norm=h["max_grad_norm"],
             is_clip_norm=int(h["is_clip_norm"]), fuzhu_weight=h["fuzhu_weight"],
             order_weight=h["discrepancy_loss_weight"], sparse_adam_mode=mode, world_size=world_size, rank=rank,
-            table_mode=L.TABLES_SHARDED if tables == "sharded" else L.TABLES_LOCAL,
+            table_mode={"local": L.TABLES_LOCAL, "sharded": L.TABLES_SHARDED, "replicated": L.TABLES_REPLICATED}[tables],
             loss_kind={"cross_entropy_loss": L.LOSS_XENT, "softmax": L.LOSS_SOFTMAX}[h["loss"]], softmax_group=int(h["softmax_group"]))
         self.handle = C.c_void_p()
         rc = self.lib.pamrec_create(C.byref(self.cfg), C.byref(self.handle))

@@ -42,7 +42,8 @@ def attempt(k, rank, world, local):
     om = O.OracleModel(nu, ni, nc, T, seed=3 + k)
     O.perturb_params(om.params, om.bn_state, seed=4 + k)
     cap = -(-(Bg // 5) // world) * 5
-    eng = Engine(nu, ni, nc, T, max(cap, 40), world_size=world, rank=rank).allocate(f"cuda:{local}")
+    tables = os.environ.get("PAMREC_TEST_TABLES", "sharded")       # "sharded" | "replicated"
+    eng = Engine(nu, ni, nc, T, max(cap, 40), world_size=world, rank=rank, tables=tables).allocate(f"cuda:{local}")
     eng.init_comm()
     eng.set_variables({n: t.numpy() for n, t in om.params.items()})
     eng.set_variables({n: t.numpy() for n, t in om.bn_state.items()})
@@ -50,7 +51,7 @@ def attempt(k, rank, world, local):
     worst = {}
     solo = None
     if rank == 0:                                    # the same model on ONE GPU, fed the whole global batch
-        solo = Engine(nu, ni, nc, T, Bg, tables="sharded").allocate(f"cuda:{local}")
+        solo = Engine(nu, ni, nc, T, Bg, tables="sharded" if tables == "sharded" else "local").allocate(f"cuda:{local}")
         solo.set_variables({n: t.numpy() for n, t in om.params.items()})
         solo.set_variables({n: t.numpy() for n, t in om.bn_state.items()})
 

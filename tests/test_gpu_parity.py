@@ -265,6 +265,36 @@ def test_lazy_mode_touches_only_looked_up_rows():
     eng.close()
 
 
+@pytest.mark.parametrize("shape", [(100, 4000, 30, 20, 25), (300, 900, 7, 50, 400)])
+def test_lazy_fused_adam_equals_dense_exact_on_the_first_step(shape):
+    """LAZY applies Adam inside the run walk (kernels_sparse2.cu: complete runs directly, runs that cross a warp block through the
+    compact accumulator + k_sp2_lazy_finish).  From zero Adam slots one step of DENSE_EXACT leaves untouched rows alone, so after
+    the first step both modes must agree on every row of every table and slot (the second shape has few items and long histories:
+    hot rows whose runs span many warp blocks, and 7 categories with runs of thousands of positions)."""
+    nu, ni, nc, T, B = shape
+    om, lazy = _setup(nu, ni, nc, T, B, seed=5, sparse_adam="lazy")
+    om2, exact = _setup(nu, ni, nc, T, B, seed=5, sparse_adam="dense_exact")
+    batch = O.make_batch(1, B, T, nu, ni, nc)
+    la = lazy.train_step(lazy.upload(batch)).cpu().numpy()
+    ex = exact.train_step(exact.upload(batch)).cpu().numpy()
+    assert np.allclose(la, ex, rtol=1e-6, atol=1e-8), (la, ex)
+    for tab in ("item", "cate", "ulong", "ushort"):
+        for sfx in ("w", "m", "v"):
+            a, b = lazy.pool[f"{tab}_{sfx}"].cpu().numpy(), exact.pool[f"{tab}_{sfx}"].cpu().numpy()
+            # summation order of a run that crosses warp blocks is not fixed (atomics): agreement to fp32 rounding of the sum
+            assert np.allclose(a, b, rtol=2e-5, atol=1e-9), (tab, sfx, float(np.abs(a - b).max()))
+    # second step: rows looked up in both steps keep agreeing only where the first step touched them too; check the lazy rule
+    batch2 = O.make_batch(2, B, T, nu, ni, nc)
+    m0 = lazy.pool["item_m"].clone()
+    lazy.train_step(lazy.upload(batch2))
+    torch.cuda.synchronize()
+    touched = np.zeros(ni, bool)
+    touched[np.unique(np.concatenate([batch2["item_history"].reshape(-1), batch2["items"]]))] = True
+    same = (lazy.pool["item_m"] == m0).all(1).cpu().numpy()
+    assert same[~touched].all(), "LAZY moved the first moment of a row that was not looked up"
+    lazy.close(); exact.close()
+
+
 def test_error_paths():
     from pamrec_b200.engine import PamrecError
     nu, ni, nc, T, B = 50, 300, 20, 12, 20

@@ -79,13 +79,15 @@ def test_sharded_empty_share_is_refused_without_peers_but_not_fatal():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("tables", ["sharded", "replicated"])
 @pytest.mark.parametrize("small_allreduce", ["mailbox", "nccl"])
-def test_two_rank_step_matches_oracle(small_allreduce):
-    """small_allreduce: batch-norm sums through the NVLink peer mailboxes (fused with finalize) or through NCCL."""
+def test_two_rank_step_matches_oracle(small_allreduce, tables):
+    """small_allreduce: batch-norm sums through the NVLink peer mailboxes (inside the persistent head kernels) or through NCCL.
+    tables: rows sharded over the ranks (id / row / gradient exchange) or whole tables on every rank (gradient tables all-reduced)."""
     n = min(torch.cuda.device_count(), int(os.environ.get("PAMREC_TEST_RANKS", "2")))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-           "--master-port", "29611" if small_allreduce == "mailbox" else "29613", os.path.join(ROOT, "tests", "dist_worker.py")]
-    env = dict(os.environ, PAMREC_NO_MAILBOX="0" if small_allreduce == "mailbox" else "1")
+           "--master-port", str(29611 + 2 * (small_allreduce == "nccl") + 4 * (tables == "replicated")), os.path.join(ROOT, "tests", "dist_worker.py")]
+    env = dict(os.environ, PAMREC_NO_MAILBOX="0" if small_allreduce == "mailbox" else "1", PAMREC_TEST_TABLES=tables)
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     fails = [ln for ln in r.stdout.splitlines() if "DIST_PARITY_FAIL" in ln]
     print("\n".join(fails) or r.stdout[-3000:])
