@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "comm.h"
+#include "head2.h"
 #include "headcoop.h"
 #include "kernels.h"
 #include "layout.h"
@@ -60,6 +61,11 @@ struct PamrecHandle_ {
   int attn_tc = 0;                  // 1: attention forward on tcgen05 (kernels_attn_tc.cu) where the sequence length allows it
   uint32_t coop_epoch = 0;          // mailbox epoch of the cooperative kernels (one per launch, all ranks in lockstep)
   bool use_coop() const { return coop_grid > 0 && prog_fwd && (cfg.world_size == 1 || mbox_open); }
+  // row-stationary head (kernels_head2.cu): the default; PAMREC_HEAD=tiles selects the tile programs, PAMREC_HEAD_LEGACY=1 the
+  // stand-alone kernels
+  Head2 head2;
+  int head2_grid = 0;
+  bool use_head2() const { return head2_grid > 0 && (cfg.world_size == 1 || mbox_open); }
   double* mbox_slots(int p) const { return static_cast<double*>(mbox_peer[p]); }
   uint32_t* mbox_flags(int p) const {
     return reinterpret_cast<uint32_t*>(static_cast<char*>(mbox_peer[p]) + (size_t)kP2PSlots * cfg.world_size * kP2PMaxDoubles * sizeof(double));
@@ -621,6 +627,13 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
   }
   const float* H = xin;
   BnSet* bn = h->bn;
+  if (h->use_head2()) {
+    // the whole head as ONE persistent cooperative kernel, row-stationary (kernels_head2.cu)
+    HeadDyn d = head_dyn(h, b, training != 0, 0);
+    d.pred = pred_out;
+    if (launch_head2_fwd(h->head2, d, h->head2_grid, training ? "head_fwd" : "head_score", st)) return check_cuda(h, "cooperative head launch");
+    return check_cuda(h, "forward");
+  }
   if (h->use_coop()) {
     // the whole head as ONE persistent cooperative kernel (kernels_headcoop.cu)
     HeadDyn d = head_dyn(h, b, training != 0, 0);
@@ -740,8 +753,48 @@ static HeadDyn head_dyn(PamrecHandle h, const PamrecBatch* b, bool training, int
 // down (which stays as the PAMREC_HEAD_LEGACY=1 path), grouped into barrier-separated phases.
 static int build_head_programs(PamrecHandle h, cudaStream_t st) {
   static_assert(BN_S1 == BN_S1_ && BN_E1 == BN_E1_ && BN_G1 == BN_G1_ && BN_COUNT == BN_COUNT_, "headcoop.h mirrors layout.h:BnId");
+  h->head2_grid = 0;
   if (getenv("PAMREC_HEAD_LEGACY") != nullptr) { h->coop_grid = 0; return 0; }
   if (h->cfg.world_size > kP2PMaxWorld) { h->coop_grid = 0; return 0; }
+  {
+    const char* hs = getenv("PAMREC_HEAD");
+    if (hs == nullptr || std::string(hs) != "tiles") {
+      const Layout& L = h->L;
+      Head2& H = h->head2;
+      memset(&H, 0, sizeof H);
+      H.H = h->wf("blk1.out"); H.tgt = h->wf("tgt");
+      H.s_w0 = h->P(L.score.w0); H.s_b0 = h->P(L.score.b0); H.s_w1 = h->P(L.score.w1); H.s_b1 = h->P(L.score.b1);
+      H.e_w0 = h->P(L.expert.w0); H.e_b0 = h->P(L.expert.b0); H.e_w1 = h->P(L.expert.w1); H.e_b1 = h->P(L.expert.b1);
+      H.g_w0 = h->P(L.gate.w0); H.g_b0 = h->P(L.gate.b0); H.g_w1 = h->P(L.gate.w1); H.g_b1 = h->P(L.gate.b1);
+      H.t_w0 = h->P(L.tower.w0); H.t_b0 = h->P(L.tower.b0); H.t_w1 = h->P(L.tower.w1); H.t_b1 = h->P(L.tower.b1);
+      H.t_wo = h->P(L.tower.wout); H.t_bo = h->P(L.tower.bout);
+      H.ds_w0 = h->G(L.score.w0); H.ds_b0 = h->G(L.score.b0); H.ds_w1 = h->G(L.score.w1); H.ds_b1 = h->G(L.score.b1);
+      H.de_w0 = h->G(L.expert.w0); H.de_b0 = h->G(L.expert.b0); H.de_w1 = h->G(L.expert.w1); H.de_b1 = h->G(L.expert.b1);
+      H.dg_w0 = h->G(L.gate.w0); H.dg_b0 = h->G(L.gate.b0); H.dg_w1 = h->G(L.gate.w1); H.dg_b1 = h->G(L.gate.b1);
+      H.dt_w0 = h->G(L.tower.w0); H.dt_b0 = h->G(L.tower.b0); H.dt_w1 = h->G(L.tower.w1); H.dt_b1 = h->G(L.tower.b1);
+      H.dt_wo = h->G(L.tower.wout); H.dt_bo = h->G(L.tower.bout);
+      H.wT = h->wf("head.wT");
+      for (int i = 0; i < BN_COUNT; ++i) H.bn[i] = h->bn[i];
+      H.z1 = h->wf("z1"); H.z2 = h->wf("z2"); H.aw = h->wf("pool.aw"); H.new_long = h->wf("new_long");
+      H.ze0 = h->wf("ze0"); H.zg0 = h->wf("zg0"); H.ze1 = h->wf("ze1"); H.zg1 = h->wf("zg1"); H.u = h->wf("u");
+      H.zt0 = h->wf("zt0"); H.zt1 = h->wf("zt1"); H.logits = h->wf("logits");
+      H.d_logits = h->wf("d_logits"); H.d_t1 = h->wf("d_t1"); H.d_t0 = h->wf("d_t0"); H.d_e1 = h->wf("d_e1"); H.d_g1 = h->wf("d_g1");
+      H.d_e0 = h->wf("d_e0"); H.d_g0 = h->wf("d_g0"); H.d_new_long = h->wf("d_new_long"); H.d_tgt = h->wf("d_tgt");
+      H.d_z2 = h->wf("d_z2"); H.g_a = h->wf("g_a");
+      H.loss_acc = h->wd("loss_acc"); H.dp_scalars = h->wd("dp.scalars");
+      const int g2 = head2_grid();
+      if (g2 > 0) {
+        if (!h->head_bar) {
+          if (cudaMalloc(&h->head_bar, 256 + 2 * 32 * 8) != cudaSuccess) return check_cuda(h, "head barrier alloc");
+          cudaMemsetAsync(h->head_bar, 0, 256 + 2 * 32 * 8, st);
+        }
+        h->head2_grid = g2;
+        h->coop_grid = 0;
+        return check_cuda(h, "head2");
+      }
+      cudaGetLastError();
+    }
+  }
   int per_sm = 0;
   const int grid = head_program_grid(&per_sm);
   if (grid <= 0) { cudaGetLastError(); h->coop_grid = 0; return 0; }   // no cooperative launch on this device: stand-alone kernels
@@ -969,7 +1022,8 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   cudaMemsetAsync(h->buf.dense_grad, 0, (size_t)L.dense_numel * 4, st);
   cudaMemsetAsync(h->wd("loss_acc"), 0, 8 * sizeof(double), st);
   cudaMemsetAsync(h->wd("sp_normsq"), 0, 8 * sizeof(double), st);
-  const bool coop = h->use_coop();
+  const bool rows = h->use_head2();
+  const bool coop = rows || h->use_coop();
   if (!coop) {
   launch_loss(h->wf("logits"), b->labels_satisfied, b->labels_play, b->plays, h->wf("d_logits"), h->wd("loss_acc"), B, Bg,
               W > 1 ? h->wd("dp.scalars") : nullptr, h->cfg.fuzhu_weight, h->cfg.order_weight,
@@ -979,7 +1033,13 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   // gradient buffer also accumulates the two column sums of its layer's BN, the consumers turn dA into dz while loading.
   // Buffers produced by the mixing / pooling kernels get their sums from k_bn_bwd_stats.  Data parallel: sums over ranks.
   cudaMemsetAsync(h->wd("bn.bsums"), 0, (size_t)L.ws[L.ws_index.at("bn.bsums")].numel * sizeof(double), st);
-  if (coop) {
+  if (rows) {
+    // loss + the dX chain of the head as ONE persistent cooperative kernel; the weight gradients (no consumer before the
+    // optimiser) run on the side stream beside the encoder's backward pass
+    HeadDyn d = head_dyn(h, b, true, 12);
+    if (launch_head2_bwd(h->head2, d, h->head2_grid, st)) return check_cuda(h, "cooperative head launch");
+    h->fork(st, [&](cudaStream_t s2) { launch_head2_dw(h->head2, B, s2); });
+  } else if (coop) {
     // loss + the whole head backward (activation, weight and batch-norm gradients) as ONE persistent cooperative kernel
     HeadDyn d = head_dyn(h, b, true, 12);
     if (launch_head_program(h->prog_bwd, d, h->coop_grid, "head_bwd", st)) return check_cuda(h, "cooperative head launch");

@@ -49,6 +49,7 @@ struct HeadDyn {
   double* peer_slots[kP2PMaxWorld]; uint32_t* peer_flags[kP2PMaxWorld];
   uint32_t p2p_epoch; int p2p_slot0; uint32_t* p2p_err;
   unsigned long long* trace;                        // [32] %globaltimer of the kernel start ([31]) and of every barrier release; may be null
+  float* pred;                                      // scoring (row-stationary kernels): sigmoid(logit 0) per row, or null
 };
 
 int head_program_grid(int* ctas_per_sm_out);        // CTAs of the persistent grid on the current device, < 0 if unsupported

@@ -173,6 +173,8 @@ struct Layout {
     }
     add_ws("z1", PAMREC_F32, {B, T, 20});
     add_ws("z2", PAMREC_F32, {B, T});
+    add_ws("pool.aw", PAMREC_F32, {B, T});        // attention-pooling weights, kept for the backward pass (kernels_head2.cu)
+    add_ws("head.wT", PAMREC_F32, {3 * 6400 + 3 * 8400 + 5 * 6400 + 2 * 320 + 628 * 40});   // transposed head weights of the dX chain
     add_ws("new_long", PAMREC_F32, {B, kD});
     add_ws("ze0", PAMREC_F32, {B, 500});
     add_ws("zg0", PAMREC_F32, {B, 128});

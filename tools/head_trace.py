@@ -18,9 +18,15 @@ from pamrec_b200 import _lib as L  # noqa: E402
 from pamrec_b200 import synth  # noqa: E402
 from pamrec_b200.engine import Engine  # noqa: E402
 
-FWD = ["s0 fwd (N rows)", "s1 fwd (N rows)", "pool fwd", "e0 + g0 fwd", "e1 + g1 fwd", "combine fwd", "t0 fwd", "t1 fwd", "tout fwd (to the end of CTA 0)"]
-BWD = ["loss", "tout dx + dw", "t1 dx + dw", "t0 dx + dw", "combine bwd", "e1 / g1 dx + dw", "e0 dx, e0 / g0 dw", "g0 dx", "pool bwd",
-       "s1 dx + dw (N rows)", "s0 dx + dw (N rows, to the end of CTA 0)"]
+FWD = ["F1 score layer 0 (tokens)", "F2 score layer 1 (tokens)", "F3 pooling + experts / gates layer 0", "F4 experts / gates layer 1",
+       "F5 mixing + towers layer 0", "F6 towers layer 1", "F7 logits (to the end of CTA 0)"]
+BWD = ["K0 weight transposes + losses", "K1 dA(t1)", "K2 dz(t1) -> dA(t0)", "K3 dz(t0) -> d_u -> mixing backward", "K4 dz(e1, g1) -> dA(e0, g0)",
+       "K5 dz(e0, g0) -> d_new_long -> pooling backward", "K6 dz2 -> sums of BN_S0, score layer 1 gradients",
+       "K7 dz1 -> dH, score layer 0 gradients (to the end of CTA 0)"]
+if os.environ.get("PAMREC_HEAD") == "tiles":
+    FWD = ["s0 fwd (N rows)", "s1 fwd (N rows)", "pool fwd", "e0 + g0 fwd", "e1 + g1 fwd", "combine fwd", "t0 fwd", "t1 fwd", "tout fwd (to the end of CTA 0)"]
+    BWD = ["loss", "tout dx + dw", "t1 dx + dw", "t0 dx + dw", "combine bwd", "e1 / g1 dx + dw", "e0 dx, e0 / g0 dw", "g0 dx", "pool bwd",
+           "s1 dx + dw (N rows)", "s0 dx + dw (N rows, to the end of CTA 0)"]
 
 
 def main():
