@@ -191,6 +191,8 @@ int pamrec_bench_table_adam(PamrecHandle h, int64_t step, void* stream);
 #define PAMREC_DEBUG_HEAD_TRACE 2
 int pamrec_set_debug(PamrecHandle h, int flags);
 int pamrec_head_trace(PamrecHandle h, int backward, uint64_t out[32]);
+/* the same run, per CTA: out[barrier * 256 + cta] = %globaltimer (ns) at which CTA `cta` arrived at barrier `barrier` (16 x 256 words) */
+int pamrec_head_trace_ctas(PamrecHandle h, int backward, uint64_t* out);
 
 /* Per-launcher device timing: CUDA events recorded on the caller's stream around every launch while enabled.
  * Synchronise the stream, then read (name, accumulated ms, timed launches) per launcher. */

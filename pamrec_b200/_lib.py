@@ -93,6 +93,7 @@ EXPORTS = {
     "pamrec_bench_table_adam": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "pamrec_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "pamrec_head_trace": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
+    "pamrec_head_trace_ctas": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
     "pamrec_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "pamrec_profile_reset": (C.c_int, [C.c_void_p]),
     "pamrec_profile_count": (C.c_int, [C.c_void_p]),

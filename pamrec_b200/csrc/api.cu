@@ -56,6 +56,7 @@ struct PamrecHandle_ {
   HeadProgram* prog_bwd = nullptr;
   unsigned* head_bar = nullptr;      // 64 words of barrier state, then 2 x 32 trace stamps (forward, backward)
   bool head_trace = false;
+  unsigned long long* head_trace_cta = nullptr;   // debug: arrival stamps of every CTA at every barrier (2 kernels x 16 x 256)
   int coop_grid = 0;
   int n_sm = 148;
   int attn_tc = 0;                  // 1: attention forward on tcgen05 (kernels_attn_tc.cu) where the sequence length allows it
@@ -79,6 +80,7 @@ struct PamrecHandle_ {
     if (prog_fwd) cudaFree(prog_fwd);
     if (prog_bwd) cudaFree(prog_bwd);
     if (head_bar) cudaFree(head_bar);
+    if (head_trace_cta) cudaFree(head_trace_cta);
     for (auto e : ev_side) if (e) cudaEventDestroy(e);
     if (ev_join) cudaEventDestroy(ev_join);
     if (ev_plan) cudaEventDestroy(ev_plan);
@@ -599,7 +601,7 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     if (prc) return fail(h, "cub sort failed");
     h->plan_for = b->item_history; h->plan_rows = B;
   }
-  if (training && W > 1) {
+  if (training && W > 1 && !h->use_head2()) {             // (the row-stationary head kernel counts them itself)
     cudaMemsetAsync(h->wd("dp.scalars"), 0, 8 * sizeof(double), st);
     launch_count_valid_groups(b->plays, B, h->wd("dp.scalars"), st);
   }
@@ -742,8 +744,12 @@ static HeadDyn head_dyn(PamrecHandle h, const PamrecBatch* b, bool training, int
   d.sm_group = h->cfg.loss_kind == PAMREC_LOSS_SOFTMAX ? h->cfg.softmax_group : 0;
   d.bar = h->head_bar;
   d.trace = h->head_trace ? reinterpret_cast<unsigned long long*>(h->head_bar + 64) + (slot0 ? 32 : 0) : nullptr;
+  d.trace_cta = (h->head_trace && h->head_trace_cta) ? h->head_trace_cta + (slot0 ? 16 * 256 : 0) : nullptr;
   if (W > 1) {
-    for (int p = 0; p < W; ++p) { d.peer_slots[p] = h->mbox_slots(p); d.peer_flags[p] = h->mbox_flags(p); }
+    for (int p = 0; p < W; ++p) {
+      d.peer_slots[p] = h->mbox_slots(p); d.peer_flags[p] = h->mbox_flags(p);
+      d.peer_ll[p] = reinterpret_cast<uint4*>(static_cast<char*>(h->mbox_peer[p]) + p2p_ll_offset(W));
+    }
     d.p2p_epoch = ++h->coop_epoch; d.p2p_slot0 = slot0; d.p2p_err = h->mbox_err();
   }
   return d;
@@ -774,7 +780,13 @@ static int build_head_programs(PamrecHandle h, cudaStream_t st) {
       H.dt_w0 = h->G(L.tower.w0); H.dt_b0 = h->G(L.tower.b0); H.dt_w1 = h->G(L.tower.w1); H.dt_b1 = h->G(L.tower.b1);
       H.dt_wo = h->G(L.tower.wout); H.dt_bo = h->G(L.tower.bout);
       H.wT = h->wf("head.wT");
-      for (int i = 0; i < BN_COUNT; ++i) H.bn[i] = h->bn[i];
+      static_assert(kHead2Groups == 8, "layout.h: bn.gsums / bn.gbsums hold 8 copies");
+      for (int i = 0; i < BN_COUNT; ++i) {
+        H.bn[i] = h->bn[i];
+        // set i's copies are contiguous: [kHead2Groups][C_i][2], sets one after the other
+        H.gsums[i] = h->wd("bn.gsums") + (size_t)kHead2Groups * L.bn_bsums_off[i];
+        H.gbsums[i] = h->wd("bn.gbsums") + (size_t)kHead2Groups * L.bn_bsums_off[i];
+      }
       H.z1 = h->wf("z1"); H.z2 = h->wf("z2"); H.aw = h->wf("pool.aw"); H.new_long = h->wf("new_long");
       H.ze0 = h->wf("ze0"); H.zg0 = h->wf("zg0"); H.ze1 = h->wf("ze1"); H.zg1 = h->wf("zg1"); H.u = h->wf("u");
       H.zt0 = h->wf("zt0"); H.zt1 = h->wf("zt1"); H.logits = h->wf("logits");
@@ -1372,6 +1384,14 @@ int pamrec_set_debug(PamrecHandle h, int flags) {
   if (!h) return -1;
   h->debug = flags;
   h->head_trace = (flags & PAMREC_DEBUG_HEAD_TRACE) != 0;
+  if (h->head_trace && !h->head_trace_cta && cudaMalloc(&h->head_trace_cta, 2 * 16 * 256 * 8) == cudaSuccess)
+    cudaMemset(h->head_trace_cta, 0, 2 * 16 * 256 * 8);
+  return 0;
+}
+int pamrec_head_trace_ctas(PamrecHandle h, int backward, uint64_t* out /* [16][256] */) {
+  if (!h || !out || !h->head_trace_cta) return -1;
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(out, h->head_trace_cta + (backward ? 16 * 256 : 0), 16 * 256 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return check_cuda(h, "head trace");
   return 0;
 }
 int pamrec_head_trace(PamrecHandle h, int backward, uint64_t out[32]) {

@@ -7,6 +7,7 @@
 namespace pamrec {
 
 constexpr int kHead2Threads = 512;
+constexpr int kHead2Groups = 8;            // copies of the batch-norm sums (atomic contention: 148 CTAs / 8 per address)
 constexpr int kHead2WtFloats = 3 * 6400 + 3 * 8400 + 5 * 6400 + 2 * 320 + 628 * 40;   // transposed weights of the dX chain
 
 struct Head2 {
@@ -21,6 +22,8 @@ struct Head2 {
   float *dt_w0, *dt_b0, *dt_w1, *dt_b1, *dt_wo, *dt_bo;
   float* wT;                            // workspace [kHead2WtFloats]
   BnSet bn[BN_COUNT];
+  double* gsums[BN_COUNT];              // [kHead2Groups][C][2] copies of the forward sums, zero between steps
+  double* gbsums[BN_COUNT];             // ... of the backward sums
   // activations / gradients (workspace)
   float *z1, *z2, *aw, *new_long, *ze0, *zg0, *ze1, *zg1, *u, *zt0, *zt1, *logits;
   float *d_logits, *d_t1, *d_t0, *d_e1, *d_g1, *d_e0, *d_g0, *d_new_long, *d_tgt, *d_z2, *g_a;

@@ -160,9 +160,14 @@ struct P2PArgs {
   BnSet bn[2]; double count[2]; int nbn;                  // optional fused batch-norm finalize
 };
 void launch_p2p_allreduce(const P2PArgs& a, cudaStream_t st);
-inline size_t p2p_mailbox_bytes(int world) {
-  return (size_t)kP2PSlots * world * kP2PMaxDoubles * sizeof(double) + (size_t)kP2PSlots * world * sizeof(uint32_t) + 256;
+// payload | flags | error word (k_p2p_allreduce), then the flag-in-data region of the persistent head kernels: 16 bytes per double
+// ({low word, epoch, high word, epoch}: the arrival of the data IS the signal - one NVLink trip per exchange instead of
+// payload, system fence, flag)
+inline size_t p2p_ll_offset(int world) {
+  const size_t b = (size_t)kP2PSlots * world * kP2PMaxDoubles * sizeof(double) + (size_t)kP2PSlots * world * sizeof(uint32_t) + 256;
+  return (b + 255) / 256 * 256;
 }
+inline size_t p2p_mailbox_bytes(int world) { return p2p_ll_offset(world) + (size_t)kP2PSlots * world * kP2PMaxDoubles * 16; }
 
 // ---- kernels_shard.cu (row-sharded tables)
 void launch_shard_route(const SparseTable& req, int64_t n, int world, int64_t rps, int* off, int* counts, int slot, int* send_ids,

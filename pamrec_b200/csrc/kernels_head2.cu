@@ -28,6 +28,7 @@ namespace {
 constexpr int kT2 = kHead2Threads;          // 512 threads, one CTA per SM
 constexpr int kRC = 8;                       // rows per chunk (= accumulators per thread)
 constexpr int kXS = 640;                     // staged input columns per chunk (largest: 500 expert + 128 gate pre-activations)
+constexpr int kWBuf = 32768;                 // floats of next-phase weights held in shared memory (largest set: 32 640)
 constexpr int kSlots = 25;                   // tokens in flight per pass of the score-MLP phases: 25 x 20 columns = 500 threads
 
 // ---- memory-ordering helpers (see kernels_headcoop.cu for the measurements behind relaxed polling)
@@ -139,6 +140,10 @@ __device__ __forceinline__ void epi_bwd(const float (&acc)[kRC], float* __restri
       s1 += (double)dy; s2 += (double)dy * (double)xh;
     }
 }
+// Batch-norm sums are collected in kHead2Groups copies (CTA c adds to copy c % kHead2Groups): the L2 serialises atomics per
+// address, and 148 CTAs adding to one word cost 4 - 10 us per barrier (measured: arrival -> release); the leader adds the copies.
+__device__ __forceinline__ double* grp_fwd(const Head2& h, int set) { return h.gsums[set] + (size_t)(blockIdx.x % kHead2Groups) * 2 * h.bn[set].C; }
+__device__ __forceinline__ double* grp_bwd(const Head2& h, int set) { return h.gbsums[set] + (size_t)(blockIdx.x % kHead2Groups) * 2 * h.bn[set].C; }
 __device__ __forceinline__ void add_sums(double* dst, int col, double a, double b) {
   if (a != 0.0 || b != 0.0) { atomicAdd(dst + 2 * col, a); atomicAdd(dst + 2 * col + 1, b); }
 }
@@ -150,33 +155,40 @@ struct Leader {
   int eval_stats;
 };
 
+// All-reduce of fp64 vectors over the ranks through the peer mailboxes, flag-in-data: every double travels as ONE 16-byte store
+// {low, epoch, high, epoch} into the receiver's memory; the receiver polls the entry until both epoch words match (a torn
+// 16-byte store is harmless: each half carries its own copy).  One NVLink trip per exchange; sums in rank order, so every rank
+// gets bit-identical results.  A slot is reused one step later with a different epoch (head_dyn: one epoch per launch).
 __device__ __forceinline__ void leader_p2p(const HeadDyn& d, int slot, double* const* buf, const int* n, int nbuf) {
   const int tid = threadIdx.x;
   int total = 0;
   for (int b = 0; b < nbuf; ++b) total += n[b];
+  const uint32_t ep = d.p2p_epoch;
   for (int i = tid; i < total; i += kT2) {
     int b = 0, o = i;
     while (o >= n[b]) { o -= n[b]; ++b; }
-    const double v = buf[b][o];
-    for (int p = 0; p < d.world; ++p) d.peer_slots[p][(size_t)(slot * d.world + d.rank) * kP2PMaxDoubles + i] = v;
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (tid < d.world) st_flag_sys(d.peer_flags[tid] + slot * d.world + d.rank, d.p2p_epoch);
-  if (tid < d.world) {
-    const uint32_t* f = d.peer_flags[d.rank] + slot * d.world + tid;
-    uint32_t spins = 0;
-    while ((int32_t)(ld_flag_sys_relaxed(f) - d.p2p_epoch) < 0) {
-      if (++spins > (1u << 24)) { *d.p2p_err = 1u + (uint32_t)slot; break; }
-      __nanosleep(64);
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(buf[b][o]);
+    const uint4 v = make_uint4((uint32_t)bits, ep, (uint32_t)(bits >> 32), ep);
+    for (int p = 0; p < d.world; ++p) {
+      uint4* dst = d.peer_ll[p] + (size_t)(slot * d.world + d.rank) * kP2PMaxDoubles + i;
+      asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
     }
-    fence_acq_rel_sys();
   }
-  __syncthreads();
-  const double* mine = d.peer_slots[d.rank] + (size_t)slot * d.world * kP2PMaxDoubles;
+  const uint4* mine = d.peer_ll[d.rank] + (size_t)slot * d.world * kP2PMaxDoubles;
   for (int i = tid; i < total; i += kT2) {
     double s = 0.0;
-    for (int p = 0; p < d.world; ++p) s += __ldcg(mine + (size_t)p * kP2PMaxDoubles + i);
+    for (int p = 0; p < d.world; ++p) {
+      const uint4* src = mine + (size_t)p * kP2PMaxDoubles + i;
+      uint4 v;
+      uint32_t spins = 0;
+      for (;;) {
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
+        if (v.y == ep && v.w == ep) break;
+        if (++spins > (1u << 22)) { *d.p2p_err = 1u + (uint32_t)slot; break; }
+        __nanosleep(32);
+      }
+      s += __longlong_as_double((long long)(((unsigned long long)v.z << 32) | (unsigned long long)v.x));
+    }
     int b = 0, o = i;
     while (o >= n[b]) { o -= n[b]; ++b; }
     buf[b][o] = s;
@@ -184,14 +196,28 @@ __device__ __forceinline__ void leader_p2p(const HeadDyn& d, int slot, double* c
   __syncthreads();
 }
 
+// sum of the kHead2Groups copies of element i of a set's sums (all loads in flight at once); the copies go back to zero
+__device__ __forceinline__ double take_copies(double* g, int C, int i) {
+  double v[kHead2Groups];
+#pragma unroll
+  for (int q = 0; q < kHead2Groups; ++q) v[q] = __ldcg(g + (size_t)q * 2 * C + i);
+  double t = 0.0;
+#pragma unroll
+  for (int q = 0; q < kHead2Groups; ++q) { t += v[q]; g[(size_t)q * 2 * C + i] = 0.0; }
+  return t;
+}
+__device__ __forceinline__ void bn_finalize_col(const BnSet& s, int c, double sum, double sq, double count, float mm, float mv) {
+  // k_bn_finalize's arithmetic (kernels_head.cu)
+  const double mean = sum / count;
+  double var = sq / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  s.stat[2 * c] = (float)mean;
+  s.stat[2 * c + 1] = (float)(1.0 / sqrt(var + (double)kBnEps));
+  s.mmean[c] = mm - (mm - (float)mean) * kBnDecay;
+  s.mvar[c] = mv - (mv - (float)var) * kBnDecay;
+}
 __device__ __noinline__ void leader_work(const Head2& h, const HeadDyn& d, const Leader& L, int barrier_index) {
   const int tid = threadIdx.x;
-  if (d.world > 1 && d.training && (L.n_sync > 0 || L.scalars)) {
-    double* buf[3]; int n[3]; int nb = 0;
-    for (int k = 0; k < L.n_sync; ++k) { const BnSet& s = h.bn[L.sync[k]]; buf[nb] = L.bwd ? s.bsums : s.sums; n[nb++] = 2 * s.C; }
-    if (L.scalars) { buf[nb] = h.dp_scalars; n[nb++] = 8; }
-    leader_p2p(d, d.p2p_slot0 + barrier_index, buf, n, nb);
-  }
   if (!d.training) {
     if (L.eval_stats)
       for (int k = 0; k < BN_COUNT; ++k) {
@@ -200,24 +226,52 @@ __device__ __noinline__ void leader_work(const Head2& h, const HeadDyn& d, const
       }
     return;
   }
+  const float gs = 1.0f / (float)d.world;
+  if (d.world == 1) {
+    // one pass, one L2 round trip per thread: the copies of the column's two sums and its moving statistics are requested together
+    for (int k = 0; k < L.n_sync; ++k) {
+      const BnSet& s = h.bn[L.sync[k]];
+      double* g = L.bwd ? h.gbsums[L.sync[k]] : h.gsums[L.sync[k]];
+      const double count = L.fin_rows_n ? d.cntN : d.cntB;
+      for (int c = tid; c < s.C; c += kT2) {
+        float mm = 0.f, mv = 0.f;
+        if (!L.bwd) { mm = __ldcg(s.mmean + c); mv = __ldcg(s.mvar + c); }
+        const double a = take_copies(g, s.C, 2 * c), b = take_copies(g, s.C, 2 * c + 1);
+        if (!L.bwd) bn_finalize_col(s, c, a, b, count, mm, mv);
+        else {
+          // gamma / beta gradients of the set; consumers read S1 / S2 from the canonical array
+          s.bsums[2 * c] = a; s.bsums[2 * c + 1] = b;
+          s.dbeta[c] += (float)a * gs;
+          s.dgamma[c] += (float)b * gs;
+        }
+      }
+    }
+    return;
+  }
+  // data parallel: copies -> canonical array, all-reduce over the ranks (peer mailboxes), then finalize / parameter gradients
+  for (int k = 0; k < L.n_sync; ++k) {
+    const BnSet& s = h.bn[L.sync[k]];
+    double* g = L.bwd ? h.gbsums[L.sync[k]] : h.gsums[L.sync[k]];
+    double* dst = L.bwd ? s.bsums : s.sums;
+    for (int i = tid; i < 2 * s.C; i += kT2) dst[i] = take_copies(g, s.C, i);
+  }
+  __syncthreads();
+  if (L.n_sync > 0 || L.scalars) {
+    double* buf[3]; int n[3]; int nb = 0;
+    for (int k = 0; k < L.n_sync; ++k) { const BnSet& s = h.bn[L.sync[k]]; buf[nb] = L.bwd ? s.bsums : s.sums; n[nb++] = 2 * s.C; }
+    if (L.scalars) { buf[nb] = h.dp_scalars; n[nb++] = 8; }
+    leader_p2p(d, d.p2p_slot0 + barrier_index, buf, n, nb);
+  }
   for (int k = 0; k < L.n_sync; ++k) {
     const BnSet& s = h.bn[L.sync[k]];
     if (!L.bwd) {
       const double count = L.fin_rows_n ? d.cntN : d.cntB;
-      for (int c = tid; c < s.C; c += kT2) {                  // k_bn_finalize's arithmetic (kernels_head.cu)
-        const double mean = s.sums[2 * c] / count;
-        double var = s.sums[2 * c + 1] / count - mean * mean;
-        if (var < 0.0) var = 0.0;
-        s.stat[2 * c] = (float)mean;
-        s.stat[2 * c + 1] = (float)(1.0 / sqrt(var + (double)kBnEps));
-        s.mmean[c] -= (s.mmean[c] - (float)mean) * kBnDecay;
-        s.mvar[c] -= (s.mvar[c] - (float)var) * kBnDecay;
+      for (int c = tid; c < s.C; c += kT2) {
+        bn_finalize_col(s, c, s.sums[2 * c], s.sums[2 * c + 1], count, s.mmean[c], s.mvar[c]);
         s.sums[2 * c] = 0.0;
         s.sums[2 * c + 1] = 0.0;
       }
     } else {
-      // gamma / beta gradients of the set: the sums are global, the dense all-reduce of a data-parallel step adds W copies
-      const float gs = 1.0f / (float)d.world;
       for (int c = tid; c < s.C; c += kT2) {
         s.dbeta[c] += (float)s.bsums[2 * c] * gs;
         s.dgamma[c] += (float)s.bsums[2 * c + 1] * gs;
@@ -226,17 +280,44 @@ __device__ __noinline__ void leader_work(const Head2& h, const HeadDyn& d, const
   }
 }
 
-__device__ __forceinline__ void grid_barrier(const Head2& h, const HeadDyn& d, unsigned& epoch, const Leader& L, int& n_barrier) {
+// Weights of the NEXT phase, copied into shared memory by the threads that only wait at a barrier (thread 0 arrives / polls):
+// the column kernel then reads its weights with conflict-free LDS instead of a chain of L2 round trips (the phases were bound
+// by exactly that latency: 13 batches of 8 loads for a 100-long contraction).
+struct Prefetch { const float* s0; int n0; const float* s1; int n1; };
+__device__ __forceinline__ Prefetch no_prefetch() { return Prefetch{nullptr, 0, nullptr, 0}; }
+__device__ __forceinline__ void copy_weights(float* __restrict__ wbuf, const Prefetch& pf, int t, int nt) {
+  // t in [0, nt): this thread's index among the copying threads
+#pragma unroll 1
+  for (int part = 0; part < 2; ++part) {
+    const float* __restrict__ src = part ? pf.s1 : pf.s0;
+    const int n = part ? pf.n1 : pf.n0;
+    float* dst = wbuf + (part ? pf.n0 : 0);
+    for (int i0 = t; i0 < n; i0 += 16 * nt) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = i0 + u * nt < n ? __ldg(src + i0 + u * nt) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) if (i0 + u * nt < n) dst[i0 + u * nt] = v[u];
+    }
+  }
+}
+
+__device__ __forceinline__ void grid_barrier(const Head2& h, const HeadDyn& d, unsigned& epoch, const Leader& L, int& n_barrier,
+                                             float* wbuf, const Prefetch& pf) {
   unsigned* bar = d.bar;
   __syncthreads();
+  if (d.trace_cta != nullptr && threadIdx.x == 0 && n_barrier < 16 && blockIdx.x < 256) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); d.trace_cta[n_barrier * 256 + blockIdx.x] = t;
+  }
   if (blockIdx.x == 0) {
     if (threadIdx.x == 0) {
       unsigned spins = 0;
       while (ld_relaxed_u32(bar) < gridDim.x - 1) {
-        if (++spins > (1u << 24)) { bar[2] = 1u + (unsigned)n_barrier; break; }
-        __nanosleep(32);
+        if (++spins > (1u << 26)) { bar[2] = 1u + (unsigned)n_barrier; break; }
       }
       fence_acq_rel_gpu();
+    } else if (gridDim.x == 1) {
+      copy_weights(wbuf, pf, threadIdx.x - 1, kT2 - 1);
     }
     __syncthreads();
     leader_work(h, d, L, n_barrier);
@@ -257,6 +338,8 @@ __device__ __forceinline__ void grid_barrier(const Head2& h, const HeadDyn& d, u
         __nanosleep(32);
       }
       fence_acq_rel_gpu();
+    } else {
+      copy_weights(wbuf, pf, threadIdx.x - 1, kT2 - 1);
     }
     __syncthreads();
   }
@@ -316,153 +399,160 @@ __device__ __forceinline__ double block_sum_d(double v, double* sh) {
   return r;
 }
 
-// ---- L1 + L2 + L3 and their gradients (base_model.py:196-242, pamrec.py:70-106); `item` covers kT2 listwise groups.
-// ApproxNDCG restated from TensorFlow-Ranking 0.3.x (oracle/pamrec_oracle.py:approx_ndcg_loss).
+// ---- L1 + L2 + L3 and their gradients (base_model.py:196-242, pamrec.py:70-106), spread as thinly as the arithmetic allows -
+// the phase is a chain of transcendental functions per unit, so its duration is the LONGEST chain, not the sum:
+//   * cross entropy (or the softmax loss): one (row, head) pair - or one (softmax group, head) pair - per lane;
+//   * ApproxNDCG (restated from TensorFlow-Ranking 0.3.x, oracle/pamrec_oracle.py:approx_ndcg_loss): one listwise group per
+//     8 lanes, lane i < 5 owns element i: its score, its rank (4 pairwise sigmoids), its gain / discount terms; the other
+//     elements' values arrive by shuffles.
+// nval = number of listwise groups with a non-zero label sum (over all ranks): dp_scalars[0], counted by the forward kernel.
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float xent(float x, float y) { return fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x))); }
-__device__ __noinline__ void loss_item(const Head2& h, const HeadDyn& d, int item, double* sh) {
-  const int tid = threadIdx.x, B = d.B;
-  const int G = B / PAMREC_GROUP;
-  const float* logits = h.logits;
-  float* d_logits = h.d_logits;
-  double nval;
-  if (d.world > 1) {
-    nval = *h.dp_scalars;                                    // count over all ranks (all-reduced in the forward pass)
-  } else {
-    double cnt = 0.0;
-    for (int g = tid; g < G; g += kT2) {
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < PAMREC_GROUP; ++i) s += d.plays[g * PAMREC_GROUP + i];
-      cnt += (s > 0.f) ? 1.0 : 0.0;
-    }
-    nval = block_sum_d(cnt, sh);
-  }
+__device__ __forceinline__ void loss_rows_item(const Head2& h, const HeadDyn& d, int item) {
+  const int lane = threadIdx.x & 31, B = d.B;
   const float inv_b = 1.0f / (float)d.Bg;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  const int u = item * 32 + lane;
+  double a0 = 0.0, a1 = 0.0;
   if (d.sm_group == 0) {
-    for (int k = 0; k < PAMREC_GROUP; ++k) {
-      const int b = (item * kT2) * PAMREC_GROUP + k * kT2 + tid;
-      if (b < B) {
-        const float x0 = logits[3 * b], x1 = logits[3 * b + 1];
-        const float y0 = d.y_sat[b], y1 = d.y_play[b];
-        a0 += (double)xent(x0, y0);
-        a1 += (double)xent(x1, y1);
-        d_logits[3 * b] = (sigm(x0) - y0) * inv_b;
-        d_logits[3 * b + 1] = d.fuzhu_w * (sigm(x1) - y1) * inv_b;
-      }
+    const int b = u >> 1, head = u & 1;
+    if (b < B) {
+      const float x = h.logits[3 * b + head];
+      const float y = head ? d.y_play[b] : d.y_sat[b];
+      const double a = (double)xent(x, y);
+      if (head) a1 = a; else a0 = a;
+      h.d_logits[3 * b + head] = (head ? d.fuzhu_w : 1.0f) * (sigm(x) - y) * inv_b;
     }
   } else {
-    // hparams.loss == "softmax":  -group * mean(log(where(y == 1, softmax, 1))) over all B elements
+    // hparams.loss == "softmax":  -group * mean(log(where(y == 1, softmax, 1))) over all B elements; units are (group, head) pairs
     const int sm = d.sm_group;
     const float scale = (float)sm * inv_b;
-    const int u = item * kT2 + tid;
     if (u < 2 * (B / sm)) {
       const int head = u & 1, r0 = (u >> 1) * sm;
       const float* y = head ? d.y_play : d.y_sat;
       float mx = -INFINITY;
-      for (int i = 0; i < sm; ++i) mx = fmaxf(mx, logits[3 * (r0 + i) + head]);
+      for (int i = 0; i < sm; ++i) mx = fmaxf(mx, h.logits[3 * (r0 + i) + head]);
       float se = 0.f;
       int n_pos = 0;
-      for (int i = 0; i < sm; ++i) { se += expf(logits[3 * (r0 + i) + head] - mx); n_pos += y[r0 + i] == 1.0f; }
+      for (int i = 0; i < sm; ++i) { se += expf(h.logits[3 * (r0 + i) + head] - mx); n_pos += y[r0 + i] == 1.0f; }
       const float lse = mx + logf(se), wgt = head ? d.fuzhu_w : 1.0f;
       double acc = 0.0;
       for (int i = 0; i < sm; ++i) {
-        const float x = logits[3 * (r0 + i) + head];
+        const float x = h.logits[3 * (r0 + i) + head];
         const bool pos = y[r0 + i] == 1.0f;
         if (pos) acc += (double)(lse - x);
-        d_logits[3 * (r0 + i) + head] = wgt * scale * ((float)n_pos * expf(x - lse) - (pos ? 1.0f : 0.f));
+        h.d_logits[3 * (r0 + i) + head] = wgt * scale * ((float)n_pos * expf(x - lse) - (pos ? 1.0f : 0.f));
       }
-      if (head) a1 += acc * (double)sm; else a0 += acc * (double)sm;
+      if (head) a1 = acc * (double)sm; else a0 = acc * (double)sm;
     }
   }
-  const float alpha = 10.0f;
-  const int g = item * kT2 + tid;
-  if (g < G) {
-    float o[5], s[5], y[5], gain[5], rank[5], dLr[5];
-    float lsum = 0.f;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      o[i] = logits[3 * (g * 5 + i) + 2];
-      s[i] = sigm(o[i]);                          // pamrec.py:74
-      y[i] = d.plays[g * 5 + i];
-      lsum += y[i];
-    }
-    const bool valid = lsum > 0.f;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const float yy = valid ? y[i] : 1e-10f;
-      y[i] = yy;
-      gain[i] = exp2f(yy) - 1.0f;
-    }
-    float dcg = 0.f;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      float r = 0.5f;
-#pragma unroll
-      for (int j = 0; j < 5; ++j) r += sigm(alpha * (s[j] - s[i]));
-      rank[i] = r;
-      dcg += gain[i] / log1pf(r);
-    }
-    float ys[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) ys[i] = y[i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)                    // sort descending (5 elements)
-#pragma unroll
-      for (int j = 0; j < 4 - i; ++j)
-        if (ys[j] < ys[j + 1]) { const float tmp = ys[j]; ys[j] = ys[j + 1]; ys[j + 1] = tmp; }
-    float idcg = 0.f;
-#pragma unroll
-    for (int r = 0; r < 5; ++r) idcg += (exp2f(ys[r]) - 1.0f) / log1pf((float)(r + 1));
-    const float inv = idcg > 0.f ? 1.0f / idcg : 0.f;
-    const float w = valid ? 1.0f : 0.f;
-    a2 += (double)(w * -(dcg * inv));
-    const float coef = (nval > 0.0) ? d.order_w * w / (float)nval : 0.f;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const float l1p = log1pf(rank[i]);
-      dLr[i] = gain[i] * inv / (l1p * l1p * (1.0f + rank[i]));
-    }
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      float acc = 0.f;
-#pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        if (i == j) continue;
-        const float sij = sigm(alpha * (s[j] - s[i]));   // d rank_i / d s_j
-        const float sji = sigm(alpha * (s[i] - s[j]));   // d rank_j / d s_j (negative sign)
-        acc += dLr[i] * alpha * sij * (1.0f - sij) - dLr[j] * alpha * sji * (1.0f - sji);
-      }
-      d_logits[3 * (g * 5 + j) + 2] = coef * acc * s[j] * (1.0f - s[j]);
-    }
+  if (item == 0) {
+    const int G = B / PAMREC_GROUP;
+    for (int b = G * 5 + lane; b < B; b += 32) h.d_logits[3 * b + 2] = 0.f;    // rows outside a complete listwise group
   }
-  if (item == 0)
-    for (int b = G * 5 + tid; b < B; b += kT2) d_logits[3 * b + 2] = 0.f;
-  a0 = block_sum_d(a0, sh);
-  a1 = block_sum_d(a1, sh);
-  a2 = block_sum_d(a2, sh);
-  if (tid == 0) {
+  a0 = warp_sum_d(a0); a1 = warp_sum_d(a1);
+  if (lane == 0) {
     if (a0 != 0.0) atomicAdd(h.loss_acc, a0 / (double)d.Bg);
     if (a1 != 0.0) atomicAdd(h.loss_acc + 1, (double)d.fuzhu_w * a1 / (double)d.Bg);
-    if (a2 != 0.0 && nval > 0.0) atomicAdd(h.loss_acc + 2, (double)d.order_w * a2 / nval);
   }
 }
+__device__ __forceinline__ void loss_ndcg_item(const Head2& h, const HeadDyn& d, int item) {
+  const int lane = threadIdx.x & 31, sub = lane & 7, base = lane & ~7;
+  const int G = d.B / PAMREC_GROUP;
+  const int g = item * 4 + (lane >> 3);
+  const bool on = g < G && sub < 5;
+  const double nval = *h.dp_scalars;
+  const float alpha = 10.0f;
+  const int row = on ? g * 5 + sub : 0;
+  const float s = on ? sigm(h.logits[3 * row + 2]) : 0.f;              // pamrec.py:74
+  float y = on ? d.plays[row] : 0.f;
+  float sj[5], yj[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) { sj[j] = __shfl_sync(0xffffffffu, s, base + j); yj[j] = __shfl_sync(0xffffffffu, y, base + j); }
+  const bool valid = (yj[0] + yj[1] + yj[2] + yj[3] + yj[4]) > 0.f;
+  if (!valid) {
+    y = 1e-10f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) yj[j] = 1e-10f;
+  }
+  const float gain = exp2f(y) - 1.0f;
+  float rank = 1.0f, pq[5];                                           // 0.5 + sigmoid(0) of the pair (i, i)
+  int pos = 0;                                                        // place of y in the descending order (ties: by index)
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    pq[j] = 0.f;
+    if (j != sub) {
+      const float p = sigm(alpha * (sj[j] - s));
+      rank += p;
+      pq[j] = p * (1.0f - p);
+      pos += (yj[j] > y) || (yj[j] == y && j < sub);
+    }
+  }
+  const float l1p = log1pf(rank);
+  float dcg = on ? gain / l1p : 0.f, idcg = on ? gain / log1pf((float)(pos + 1)) : 0.f;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) { dcg += __shfl_xor_sync(0xffffffffu, dcg, o); idcg += __shfl_xor_sync(0xffffffffu, idcg, o); }
+  const float inv = idcg > 0.f ? 1.0f / idcg : 0.f;
+  const float w = valid ? 1.0f : 0.f;
+  const float coef = (nval > 0.0) ? d.order_w * w / (float)nval : 0.f;
+  const float dLr = gain * inv / (l1p * l1p * (1.0f + rank));
+  float acc = 0.f;                                                    // d loss / d s_i = alpha sum_{j != i} (dLr_j - dLr_i) p_ij (1 - p_ij)
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const float dj = __shfl_sync(0xffffffffu, dLr, base + j);
+    acc += alpha * pq[j] * (dj - dLr);
+  }
+  if (on) h.d_logits[3 * row + 2] = coef * acc * s * (1.0f - s);
+  double a2 = (on && sub == 0) ? (double)(w * -(dcg * inv)) : 0.0;
+  a2 = warp_sum_d(a2);
+  if (lane == 0 && a2 != 0.0 && nval > 0.0) atomicAdd(h.loss_acc + 2, (double)d.order_w * a2 / nval);
+}
 
-struct Rows { int b0, b1; };                                 // samples of this CTA
+// samples of this CTA.  CTA 0 is the coordinator of the grid barriers (batch-norm finalize, data-parallel exchange): it owns no
+// rows, so that the other CTAs never wait for its share of a phase on top of its leader work.
+struct Rows { int b0, b1; };
 __device__ __forceinline__ Rows my_rows(int B) {
-  const int per = (B + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int workers = max((int)gridDim.x - 1, 1);
+  const int me = gridDim.x > 1 ? (int)blockIdx.x - 1 : 0;
+  const int per = (B + workers - 1) / workers;
   Rows r;
-  r.b0 = min(B, (int)blockIdx.x * per);
-  r.b1 = min(B, r.b0 + per);
+  r.b0 = me < 0 ? B : min(B, me * per);
+  r.b1 = me < 0 ? B : min(B, r.b0 + per);
   return r;
 }
 
 }  // namespace
 
+// transposed weights in the workspace (written at the tail of the forward kernel): offsets in floats
+constexpr int kWT_t1 = 0;                      // towers layer 1:  [3][64][100]   (n, k)
+constexpr int kWT_t0 = kWT_t1 + 3 * 6400;      // towers layer 0:  [3][100][84]
+constexpr int kWT_e1 = kWT_t0 + 3 * 8400;      // experts layer 1: [5][64][100]
+constexpr int kWT_g1 = kWT_e1 + 5 * 6400;      // gates layer 1:   [2][5][64]
+constexpr int kWT_x0 = kWT_g1 + 2 * 320;       // experts then gates layer 0 as ONE [628][40] matrix: rows g*100+n (expert g), 500+g*64+n (gate g)
+constexpr int kWT_total = kWT_x0 + 628 * 40;
+static_assert(kWT_total == kHead2WtFloats, "head2.h: workspace size of the transposed weights");
+__device__ __forceinline__ void head2_transpose_weights(const Head2& h) {
+  float* wT = h.wT;
+  const int64_t gtid = (int64_t)blockIdx.x * kT2 + threadIdx.x, gsz = (int64_t)gridDim.x * kT2;
+  for (int64_t i = gtid; i < kWT_total; i += gsz) {
+    float v;
+    if (i < kWT_t0) { const int j = (int)i, g = j / 6400, r = j % 6400, n = r / 100, k = r % 100; v = h.t_w1[g * 6400 + k * 64 + n]; }
+    else if (i < kWT_e1) { const int j = (int)i - kWT_t0, g = j / 8400, r = j % 8400, n = r / 84, k = r % 84; v = h.t_w0[g * 8400 + k * 100 + n]; }
+    else if (i < kWT_g1) { const int j = (int)i - kWT_e1, g = j / 6400, r = j % 6400, n = r / 100, k = r % 100; v = h.e_w1[g * 6400 + k * 64 + n]; }
+    else if (i < kWT_x0) { const int j = (int)i - kWT_g1, g = j / 320, r = j % 320, n = r / 64, k = r % 64; v = h.g_w1[g * 320 + k * 5 + n]; }
+    else {
+      const int j = (int)i - kWT_x0, row = j / 40, k = j % 40;
+      if (row < 500) { const int g = row / 100, n = row % 100; v = h.e_w0[g * 4000 + k * 100 + n]; }
+      else { const int rr = row - 500, g = rr / 64, n = rr % 64; v = h.g_w0[g * 2560 + k * 64 + n]; }
+    }
+    wT[i] = v;
+  }
+}
+
 // ================================================================================================ forward
 __global__ void __launch_bounds__(kT2, 1) k_head2_fwd(const __grid_constant__ Head2 h, const __grid_constant__ HeadDyn d) {
-  __shared__ __align__(16) float xs[kXS * kRC];               // staged inputs of the current chunk, [column][row]
+  extern __shared__ __align__(16) float dsm[];
+  float* wbuf = dsm;                                          // weights of the current / next phase
+  float* xs = dsm + kWBuf;                                    // staged inputs of the current chunk, [column][row]
   __shared__ __align__(16) float w0s[kD * 20 + 64];           // score layer 0 weights [40][20], b0[20], w1[20], b1
   __shared__ double shd[64];
   __shared__ unsigned s_epoch;
@@ -479,8 +569,28 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_fwd(const __grid_constant__ He
   const int T = d.T;
   const Rows R = my_rows(d.B);
   const int64_t tok0 = (int64_t)R.b0 * T, tok1 = (int64_t)R.b1 * T;
-  if (!train) { Leader L = leader_of(-1, -1, 0, 0); L.eval_stats = 1; grid_barrier(h, d, epoch, L, n_barrier); }
+  // training: grid barrier (the waiting threads copy the next phase's weights); scoring: batch-norm statistics are constants, the
+  // CTAs never meet again after the first barrier and every CTA copies its weights itself
+  auto sync_point = [&](const Leader& L, const Prefetch& pf) {
+    if (train) grid_barrier(h, d, epoch, L, n_barrier, wbuf, pf);
+    else { __syncthreads(); copy_weights(wbuf, pf, tid, kT2); __syncthreads(); }
+  };
+  if (!train) { Leader L = leader_of(-1, -1, 0, 0); L.eval_stats = 1; grid_barrier(h, d, epoch, L, n_barrier, wbuf, no_prefetch()); }
 
+  // ---- the coordinator counts the listwise groups with a non-zero label sum (ApproxNDCG weight, pamrec.py:76): dp_scalars[0];
+  //      data parallel: summed over the ranks with the sums of the first barrier
+  if (train && blockIdx.x == 0) {
+    const int G = d.B / PAMREC_GROUP;
+    double cnt = 0.0;
+    for (int g = tid; g < G; g += kT2) {
+      float sg = 0.f;
+#pragma unroll
+      for (int i = 0; i < PAMREC_GROUP; ++i) sg += d.plays[g * PAMREC_GROUP + i];
+      cnt += (sg > 0.f) ? 1.0 : 0.0;
+    }
+    cnt = block_sum_d(cnt, shd);
+    if (tid == 0) h.dp_scalars[0] = cnt;
+  }
   // ---- F1: z1 = H W0 + b0 over the CTA's tokens; thread (slot, j) owns column j for the tokens slot, slot + 25, ...
   {
     const int slot = tid / 20, j = tid % 20;
@@ -511,10 +621,10 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_fwd(const __grid_constant__ He
         const int which = tid / 20, c = tid % 20;
         double t = 0.0;
         for (int k = 0; k < kSlots; ++k) t += red[which * 500 + k * 20 + c];
-        if (t != 0.0) atomicAdd(h.bn[BN_S0].sums + 2 * c + which, t);
+        if (t != 0.0) atomicAdd(grp_fwd(h, BN_S0) + 2 * c + which, t);
       }
     }
-    if (train) grid_barrier(h, d, epoch, leader_of(BN_S0, -1, 0, 1, 1), n_barrier);
+    sync_point(leader_of(BN_S0, -1, 0, 1, 1), Prefetch{h.e_w0, 5 * 4000, h.g_w0, 2 * 2560});
   }
   // ---- F2: z2 = relu(bn(z1)) w1 + b1, one thread per token
   __syncthreads();
@@ -537,9 +647,9 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_fwd(const __grid_constant__ He
     }
     if (train) {
       s = block_sum_d(s, shd); q = block_sum_d(q, shd);
-      if (tid == 0 && (s != 0.0 || q != 0.0)) { atomicAdd(h.bn[BN_S1].sums, s); atomicAdd(h.bn[BN_S1].sums + 1, q); }
+      if (tid == 0 && (s != 0.0 || q != 0.0)) { atomicAdd(grp_fwd(h, BN_S1), s); atomicAdd(grp_fwd(h, BN_S1) + 1, q); }
     }
-    if (train) grid_barrier(h, d, epoch, leader_of(BN_S1, -1, 0, 1), n_barrier);
+    sync_point(leader_of(BN_S1, -1, 0, 1), no_prefetch());
   }
   // ---- F3: pooling (warp per sample) -> new_long, then experts / gates layer 0 on the CTA's rows
   __syncthreads();
@@ -580,12 +690,12 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_fwd(const __grid_constant__ He
         if (col < 500) {
           const int g = col / 100, n = col % 100;
           acc_set(acc, h.e_b0[g * 100 + n]);
-          col_gemm(xs, 0, kD, h.e_w0 + g * 4000 + n, 100, acc);
+          col_gemm(xs, 0, kD, wbuf + g * 4000 + n, 100, acc);
           epi_fwd(acc, h.ze0, 500, col, row0, nr, s[pass], q[pass]);
         } else {
           const int cg = col - 500, g = cg / 64, n = cg % 64;
           acc_set(acc, h.g_b0[g * 64 + n]);
-          col_gemm(xs, 0, kD, h.g_w0 + g * 2560 + n, 64, acc);
+          col_gemm(xs, 0, kD, wbuf + 20000 + g * 2560 + n, 64, acc);
           epi_fwd(acc, h.zg0, 128, cg, row0, nr, s[pass], q[pass]);
         }
       }
@@ -594,11 +704,11 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_fwd(const __grid_constant__ He
 #pragma unroll
       for (int pass = 0; pass < 2; ++pass) {
         const int col = tid + pass * kT2;
-        if (col < 500) add_sums(h.bn[BN_E0].sums, col, s[pass], q[pass]);
-        else if (col < 628) add_sums(h.bn[BN_G0].sums, col - 500, s[pass], q[pass]);
+        if (col < 500) add_sums(grp_fwd(h, BN_E0), col, s[pass], q[pass]);
+        else if (col < 628) add_sums(grp_fwd(h, BN_G0), col - 500, s[pass], q[pass]);
       }
     }
-    if (train) grid_barrier(h, d, epoch, leader_of(BN_E0, BN_G0, 0, 0), n_barrier);
+    sync_point(leader_of(BN_E0, BN_G0, 0, 0), Prefetch{h.e_w1, 5 * 6400, h.g_w1, 2 * 320});
   }
   // ---- F4: experts / gates layer 1
   {
@@ -614,20 +724,20 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_fwd(const __grid_constant__ He
       if (col < 320) {
         const int g = col / 64, n = col % 64;
         acc_set(acc, h.e_b1[g * 64 + n]);
-        col_gemm(xs, g * 100, 100, h.e_w1 + g * 6400 + n, 64, acc);
+        col_gemm(xs, g * 100, 100, wbuf + g * 6400 + n, 64, acc);
         epi_fwd(acc, h.ze1, 320, col, row0, nr, s, q);
       } else if (col < 330) {
         const int cg = col - 320, g = cg / 5, n = cg % 5;
         acc_set(acc, h.g_b1[g * 5 + n]);
-        col_gemm(xs, 500 + g * 64, 64, h.g_w1 + g * 320 + n, 5, acc);
+        col_gemm(xs, 500 + g * 64, 64, wbuf + 32000 + g * 320 + n, 5, acc);
         epi_fwd(acc, h.zg1, 10, cg, row0, nr, s, q);
       }
     }
     if (train) {
-      if (tid < 320) add_sums(h.bn[BN_E1].sums, tid, s, q);
-      else if (tid < 330) add_sums(h.bn[BN_G1].sums, tid - 320, s, q);
+      if (tid < 320) add_sums(grp_fwd(h, BN_E1), tid, s, q);
+      else if (tid < 330) add_sums(grp_fwd(h, BN_G1), tid - 320, s, q);
     }
-    if (train) grid_barrier(h, d, epoch, leader_of(BN_E1, BN_G1, 0, 0), n_barrier);
+    sync_point(leader_of(BN_E1, BN_G1, 0, 0), Prefetch{h.t_w0, 3 * 8400, nullptr, 0});
   }
   // ---- F5: MMoE mixing (pamrec.py:46-50, 315-316) -> u = [main | tgt | sub | tgt]; towers layer 0
   {
@@ -668,12 +778,12 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_fwd(const __grid_constant__ He
         const int g = tid / 100, n = tid % 100;
         float acc[kRC];
         acc_set(acc, h.t_b0[g * 100 + n]);
-        col_gemm(xs, g == 1 ? 84 : 0, 84, h.t_w0 + g * 8400 + n, 100, acc);
+        col_gemm(xs, g == 1 ? 84 : 0, 84, wbuf + g * 8400 + n, 100, acc);
         epi_fwd(acc, h.zt0, 300, tid, row0, nr, s, q);
       }
     }
-    if (train && tid < 300) add_sums(h.bn[BN_T0].sums, tid, s, q);
-    if (train) grid_barrier(h, d, epoch, leader_of(BN_T0, -1, 0, 0), n_barrier);
+    if (train && tid < 300) add_sums(grp_fwd(h, BN_T0), tid, s, q);
+    sync_point(leader_of(BN_T0, -1, 0, 0), Prefetch{h.t_w1, 3 * 6400, nullptr, 0});
   }
   // ---- F6: towers layer 1
   {
@@ -687,12 +797,12 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_fwd(const __grid_constant__ He
         const int g = tid / 64, n = tid % 64;
         float acc[kRC];
         acc_set(acc, h.t_b1[g * 64 + n]);
-        col_gemm(xs, g * 100, 100, h.t_w1 + g * 6400 + n, 64, acc);
+        col_gemm(xs, g * 100, 100, wbuf + g * 6400 + n, 64, acc);
         epi_fwd(acc, h.zt1, 192, tid, row0, nr, s, q);
       }
     }
-    if (train && tid < 192) add_sums(h.bn[BN_T1].sums, tid, s, q);
-    if (train) grid_barrier(h, d, epoch, leader_of(BN_T1, -1, 0, 0), n_barrier);
+    if (train && tid < 192) add_sums(grp_fwd(h, BN_T1), tid, s, q);
+    sync_point(leader_of(BN_T1, -1, 0, 0), no_prefetch());
   }
   // ---- F7: logits (pamrec.py:212-215, 71); scoring: pred = sigmoid(logit 0)
   {
@@ -713,21 +823,16 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_fwd(const __grid_constant__ He
     }
   }
   if (tid == 0 && blockIdx.x == 0 && d.trace != nullptr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); d.trace[30] = t; d.trace[29] = (unsigned long long)n_barrier; }
+  // ---- training: transposed weights for the dX chain of the backward kernel (nobody waits for this tail)
+  if (train) head2_transpose_weights(h);
 }
 
 // ================================================================================================ backward (dX chain)
-// transposed weights in the workspace (written by phase K0): offsets in floats
-constexpr int kWT_t1 = 0;                      // towers layer 1:  [3][64][100]   (n, k)
-constexpr int kWT_t0 = kWT_t1 + 3 * 6400;      // towers layer 0:  [3][100][84]
-constexpr int kWT_e1 = kWT_t0 + 3 * 8400;      // experts layer 1: [5][64][100]
-constexpr int kWT_g1 = kWT_e1 + 5 * 6400;      // gates layer 1:   [2][5][64]
-constexpr int kWT_x0 = kWT_g1 + 2 * 320;       // experts then gates layer 0 as ONE [628][40] matrix: rows g*100+n (expert g), 500+g*64+n (gate g)
-constexpr int kWT_total = kWT_x0 + 628 * 40;
-static_assert(kWT_total == kHead2WtFloats, "head2.h: workspace size of the transposed weights");
-
 __global__ void __launch_bounds__(kT2, 1) k_head2_bwd(const __grid_constant__ Head2 h, const __grid_constant__ HeadDyn d) {
-  __shared__ __align__(16) float xs[kXS * kRC];
-  __shared__ __align__(16) float aux[4096];                   // combine / pooling / score scratch
+  extern __shared__ __align__(16) float dsm[];
+  float* wbuf = dsm;                                          // transposed weights of the current / next phase
+  float* xs = dsm + kWBuf;
+  float* aux = xs + kXS * kRC;                                // [4096] combine / pooling / score scratch
   __shared__ double shd[64];
   __shared__ unsigned s_epoch;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -739,32 +844,20 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_bwd(const __grid_constant__ He
   const int T = d.T;
   const Rows R = my_rows(d.B);
   const int64_t tok0 = (int64_t)R.b0 * T, tok1 = (int64_t)R.b1 * T;
-  float* wT = h.wT;
+  const float* wT = h.wT;
 
-  // ---- K0: transposed weights for the dX chain; the losses and d_logits
+  // ---- K0: the losses and d_logits, one warp per 32 listwise groups
   {
-    const int64_t gtid = (int64_t)blockIdx.x * kT2 + tid, gsz = (int64_t)gridDim.x * kT2;
-    for (int64_t i = gtid; i < kWT_total; i += gsz) {
-      float v;
-      if (i < kWT_t0) { const int j = (int)i, g = j / 6400, r = j % 6400, n = r / 100, k = r % 100; v = h.t_w1[g * 6400 + k * 64 + n]; }
-      else if (i < kWT_e1) { const int j = (int)i - kWT_t0, g = j / 8400, r = j % 8400, n = r / 84, k = r % 84; v = h.t_w0[g * 8400 + k * 100 + n]; }
-      else if (i < kWT_g1) { const int j = (int)i - kWT_e1, g = j / 6400, r = j % 6400, n = r / 100, k = r % 100; v = h.e_w1[g * 6400 + k * 64 + n]; }
-      else if (i < kWT_x0) { const int j = (int)i - kWT_g1, g = j / 320, r = j % 320, n = r / 64, k = r % 64; v = h.g_w1[g * 320 + k * 5 + n]; }
-      else {
-        const int j = (int)i - kWT_x0, row = j / 40, k = j % 40;
-        if (row < 500) { const int g = row / 100, n = row % 100; v = h.e_w0[g * 4000 + k * 100 + n]; }
-        else { const int rr = row - 500, g = rr / 64, n = rr % 64; v = h.g_w0[g * 2560 + k * 64 + n]; }
-      }
-      wT[i] = v;
-    }
     const int G = d.B / PAMREC_GROUP;
-    int units = G;
-    if (d.sm_group > 0) { const int u2 = 2 * (d.B / d.sm_group); units = u2 > G ? u2 : G; }
-    int n_items = (units + kT2 - 1) / kT2;
-    if (n_items < 1) n_items = 1;
-    if (d.B > 0)
-      for (int i = blockIdx.x; i < n_items; i += gridDim.x) { __syncthreads(); loss_item(h, d, i, shd); }
-    grid_barrier(h, d, epoch, leader_of(-1, -1, 1, 0), n_barrier);
+    const int n_ndcg = (G + 3) / 4;
+    const int n_units = d.sm_group > 0 ? 2 * (d.B / d.sm_group) : 2 * d.B;
+    const int n_rows = max((n_units + 31) / 32, 1);
+    const int workers = max((int)gridDim.x - 1, 1), me = gridDim.x > 1 ? (int)blockIdx.x - 1 : 0;
+    if (d.B > 0 && me >= 0)
+      for (int i = me + workers * warp; i < n_ndcg + n_rows; i += workers * (kT2 / 32)) {
+        if (i < n_ndcg) loss_ndcg_item(h, d, i); else loss_rows_item(h, d, i - n_ndcg);
+      }
+    grid_barrier(h, d, epoch, leader_of(-1, -1, 1, 0), n_barrier, wbuf, Prefetch{wT + kWT_t1, 3 * 6400, nullptr, 0});
   }
   // ---- K1: dA(t1) = d_logits (x) w_out, sums of BN_T1
   {
@@ -781,9 +874,9 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_bwd(const __grid_constant__ He
         const float dy = fmaf(k.ga, xh, k.be) > 0.f ? da : 0.f;
         s1 += (double)dy; s2 += (double)dy * (double)xh;
       }
-      add_sums(h.bn[BN_T1].bsums, tid, s1, s2);
+      add_sums(grp_bwd(h, BN_T1), tid, s1, s2);
     }
-    grid_barrier(h, d, epoch, leader_of(BN_T1, -1, 1, 0), n_barrier);
+    grid_barrier(h, d, epoch, leader_of(BN_T1, -1, 1, 0), n_barrier, wbuf, no_prefetch());
   }
   // ---- K2: dz(t1) -> dA(t0) = dz(t1) W1^T, sums of BN_T0
   {
@@ -798,12 +891,12 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_bwd(const __grid_constant__ He
         const int g = tid / 100, kk = tid % 100;
         float acc[kRC];
         acc_set(acc, 0.f);
-        col_gemm(xs, g * 64, 64, wT + kWT_t1 + g * 6400 + kk, 100, acc);
+        col_gemm(xs, g * 64, 64, wbuf + g * 6400 + kk, 100, acc);
         epi_bwd(acc, h.d_t0, h.zt0, 300, tid, row0, nr, k, s1, s2);
       }
     }
-    if (tid < 300) add_sums(h.bn[BN_T0].bsums, tid, s1, s2);
-    grid_barrier(h, d, epoch, leader_of(BN_T0, -1, 1, 0), n_barrier);
+    if (tid < 300) add_sums(grp_bwd(h, BN_T0), tid, s1, s2);
+    grid_barrier(h, d, epoch, leader_of(BN_T0, -1, 1, 0), n_barrier, wbuf, Prefetch{wT + kWT_t0, 3 * 8400, nullptr, 0});
   }
   // ---- K3: dz(t0) -> d_u = dz(t0) W0^T -> mixing backward: dA(e1), dA(g1), d_tgt; sums of BN_E1 / BN_G1
   {
@@ -823,10 +916,10 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_bwd(const __grid_constant__ He
         float acc[kRC];
         acc_set(acc, 0.f);
         if (tid < 84) {
-          col_gemm(xs, 0, 100, wT + kWT_t0 + tid, 84, acc);
-          col_gemm(xs, 200, 100, wT + kWT_t0 + 2 * 8400 + tid, 84, acc);
+          col_gemm(xs, 0, 100, wbuf + tid, 84, acc);
+          col_gemm(xs, 200, 100, wbuf + 2 * 8400 + tid, 84, acc);
         } else {
-          col_gemm(xs, 100, 100, wT + kWT_t0 + 8400 + (tid - 84), 84, acc);
+          col_gemm(xs, 100, 100, wbuf + 8400 + (tid - 84), 84, acc);
         }
         st4(du + tid * kRC, make_float4(acc[0], acc[1], acc[2], acc[3]));
         st4(du + tid * kRC + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
@@ -864,9 +957,9 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_bwd(const __grid_constant__ He
         }
       }
     }
-    if (tid < 320) add_sums(h.bn[BN_E1].bsums, tid, s1, s2);
-    else if (tid < 400) add_sums(h.bn[BN_G1].bsums, (tid - 320) >> 3, s1, s2);
-    grid_barrier(h, d, epoch, leader_of(BN_E1, BN_G1, 1, 0), n_barrier);
+    if (tid < 320) add_sums(grp_bwd(h, BN_E1), tid, s1, s2);
+    else if (tid < 400) add_sums(grp_bwd(h, BN_G1), (tid - 320) >> 3, s1, s2);
+    grid_barrier(h, d, epoch, leader_of(BN_E1, BN_G1, 1, 0), n_barrier, wbuf, Prefetch{wT + kWT_e1, 5 * 6400 + 2 * 320, nullptr, 0});
   }
   // ---- K4: dz(e1), dz(g1) -> dA(e0), dA(g0); sums of BN_E0 / BN_G0
   {
@@ -891,11 +984,11 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_bwd(const __grid_constant__ He
         acc_set(acc, 0.f);
         if (col < 500) {
           const int g = col / 100, kk = col % 100;
-          col_gemm(xs, g * 64, 64, wT + kWT_e1 + g * 6400 + kk, 100, acc);
+          col_gemm(xs, g * 64, 64, wbuf + g * 6400 + kk, 100, acc);
           epi_bwd(acc, h.d_e0, h.ze0, 500, col, row0, nr, kc[pass], s1[pass], s2[pass]);
         } else {
           const int cg = col - 500, g = cg / 64, kk = cg % 64;
-          col_gemm(xs, 320 + g * 5, 5, wT + kWT_g1 + g * 320 + kk, 64, acc);
+          col_gemm(xs, 320 + g * 5, 5, wbuf + 32000 + g * 320 + kk, 64, acc);
           epi_bwd(acc, h.d_g0, h.zg0, 128, cg, row0, nr, kc[pass], s1[pass], s2[pass]);
         }
       }
@@ -903,10 +996,10 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_bwd(const __grid_constant__ He
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
       const int col = tid + pass * kT2;
-      if (col < 500) add_sums(h.bn[BN_E0].bsums, col, s1[pass], s2[pass]);
-      else if (col < 628) add_sums(h.bn[BN_G0].bsums, col - 500, s1[pass], s2[pass]);
+      if (col < 500) add_sums(grp_bwd(h, BN_E0), col, s1[pass], s2[pass]);
+      else if (col < 628) add_sums(grp_bwd(h, BN_G0), col - 500, s1[pass], s2[pass]);
     }
-    grid_barrier(h, d, epoch, leader_of(BN_E0, BN_G0, 1, 0), n_barrier);
+    grid_barrier(h, d, epoch, leader_of(BN_E0, BN_G0, 1, 0), n_barrier, wbuf, Prefetch{wT + kWT_x0, 628 * 40, nullptr, 0});
   }
   // ---- K5: dz(e0), dz(g0) -> d_new_long = [dz(e0) | dz(g0)] [W_e0 | W_g0]^T (one 628-long contraction split over 12 thread
   //          groups); pooling backward (warp per sample): dA(z2), sums of BN_S1
@@ -926,7 +1019,7 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_bwd(const __grid_constant__ He
         const int k0 = grp * 53, kn = min(53, 628 - k0);
         float acc[kRC];
         acc_set(acc, 0.f);
-        col_gemm(xs, k0, kn, wT + kWT_x0 + k0 * 40 + c, 40, acc);
+        col_gemm(xs, k0, kn, wbuf + k0 * 40 + c, 40, acc);
         float* p = part + (grp * 40 + c) * kRC;
         st4(p, make_float4(acc[0], acc[1], acc[2], acc[3]));
         st4(p + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
@@ -977,8 +1070,8 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_bwd(const __grid_constant__ He
       }
     }
     b1 = block_sum_d(b1, shd); b2 = block_sum_d(b2, shd);
-    if (tid == 0 && (b1 != 0.0 || b2 != 0.0)) { atomicAdd(h.bn[BN_S1].bsums, b1); atomicAdd(h.bn[BN_S1].bsums + 1, b2); }
-    grid_barrier(h, d, epoch, leader_of(BN_S1, -1, 1, 1), n_barrier);
+    if (tid == 0 && (b1 != 0.0 || b2 != 0.0)) { atomicAdd(grp_bwd(h, BN_S1), b1); atomicAdd(grp_bwd(h, BN_S1) + 1, b2); }
+    grid_barrier(h, d, epoch, leader_of(BN_S1, -1, 1, 1), n_barrier, wbuf, no_prefetch());
   }
   // score MLP constants in shared memory: W0 [40][20], its transpose, w1, BN coefficients
   float* w0s = aux;                                           // [800]  W0[k][j]
@@ -1016,12 +1109,12 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_bwd(const __grid_constant__ He
       double t = 0.0;
       for (int k = 0; k < kSlots; ++k) t += red[which * 500 + k * 20 + c];
       if (t != 0.0) {
-        if (which < 2) atomicAdd(h.bn[BN_S0].bsums + 2 * c + which, t);
+        if (which < 2) atomicAdd(grp_bwd(h, BN_S0) + 2 * c + which, t);
         else if (which == 2) atomicAdd(h.ds_w1 + c, (float)t);
         else if (c == 0) atomicAdd(h.ds_b1, (float)t);
       }
     }
-    grid_barrier(h, d, epoch, leader_of(BN_S0, -1, 1, 1), n_barrier);
+    grid_barrier(h, d, epoch, leader_of(BN_S0, -1, 1, 1), n_barrier, wbuf, no_prefetch());
   }
   // ---- K7: dz1 -> dH = a_t d_new_long + dz1 W0^T  (the gradient of the encoder output, g_a);  dW0 = H^T dz1, db0
   {
@@ -1165,14 +1258,18 @@ __global__ void __launch_bounds__(kDwThreads) k_head2_dw(const __grid_constant__
 }
 
 // ================================================================================================ host side
+constexpr size_t kFwdSmem = (size_t)(kWBuf + kXS * kRC) * sizeof(float);
+constexpr size_t kBwdSmem = (size_t)(kWBuf + kXS * kRC + 4096) * sizeof(float);
 int head2_grid() {
   int dev = 0, sms = 0, coop = 0, occ_f = 0, occ_b = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(k_head2_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(k_head2_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem) != cudaSuccess) return -1;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
   if (!coop) return -1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_head2_fwd, kT2, 0) != cudaSuccess || occ_f < 1) return -1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_head2_bwd, kT2, 0) != cudaSuccess || occ_b < 1) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_head2_fwd, kT2, kFwdSmem) != cudaSuccess || occ_f < 1) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_head2_bwd, kT2, kBwdSmem) != cudaSuccess || occ_b < 1) return -1;
   return sms;
 }
 
@@ -1180,13 +1277,13 @@ int launch_head2_fwd(const Head2& h, const HeadDyn& d, int grid, const char* nam
   PAMREC_PROF(name, 1, st);
   if (d.B == 0 && d.world == 1) return 0;
   void* args[2] = {(void*)&h, (void*)&d};
-  return cudaLaunchCooperativeKernel((const void*)k_head2_fwd, dim3(grid), dim3(kT2), args, 0, st) == cudaSuccess ? 0 : -1;
+  return cudaLaunchCooperativeKernel((const void*)k_head2_fwd, dim3(grid), dim3(kT2), args, kFwdSmem, st) == cudaSuccess ? 0 : -1;
 }
 int launch_head2_bwd(const Head2& h, const HeadDyn& d, int grid, cudaStream_t st) {
   PAMREC_PROF("head_bwd", 1, st);
   if (d.B == 0 && d.world == 1) return 0;
   void* args[2] = {(void*)&h, (void*)&d};
-  return cudaLaunchCooperativeKernel((const void*)k_head2_bwd, dim3(grid), dim3(kT2), args, 0, st) == cudaSuccess ? 0 : -1;
+  return cudaLaunchCooperativeKernel((const void*)k_head2_bwd, dim3(grid), dim3(kT2), args, kBwdSmem, st) == cudaSuccess ? 0 : -1;
 }
 void launch_head2_dw(const Head2& h, int B, cudaStream_t st) {
   PAMREC_PROF("head_dw", 1, st);

@@ -217,6 +217,8 @@ struct Layout {
       bn_c += bnoff[i].C;
     }
     add_ws("bn.bsums", PAMREC_F64, {bn_c, 2});   // backward sums (sum dy, sum dy*xhat) of all sets: one memset per step
+    add_ws("bn.gsums", PAMREC_F64, {8, bn_c, 2});    // row-stationary head: 8 copies of the forward sums (set-major inside a copy group)
+    add_ws("bn.gbsums", PAMREC_F64, {8, bn_c, 2});   // ... and of the backward sums
     // optimiser scratch
     add_ws("seg_id", PAMREC_I32, {dense_numel});
     add_ws("seg_tab", PAMREC_I32, {(int64_t)dense.size(), 4});   // off, numel, flags, -

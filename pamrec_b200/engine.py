@@ -470,6 +470,12 @@ class Engine:
         n, t0 = int(buf[29]), int(buf[31])
         return [int(buf[i]) - t0 for i in range(n)] + [int(buf[30]) - t0]
 
+    def head_trace_ctas(self, backward=False):
+        """[16, 256] ns at which every CTA of the last persistent head kernel arrived at every barrier (0 = unused)."""
+        buf = (C.c_uint64 * (16 * 256))()
+        self._check(self.lib.pamrec_head_trace_ctas(self.handle, int(backward), buf))
+        return np.frombuffer(buf, dtype=np.uint64).reshape(16, 256).copy()
+
     def profile(self, on=True):
         self._check(self.lib.pamrec_profile_enable(self.handle, int(on)))
         self._check(self.lib.pamrec_profile_reset(self.handle))
