@@ -9,7 +9,6 @@
 
 #include "comm.h"
 #include "head2.h"
-#include "headcoop.h"
 #include "kernels.h"
 #include "layout.h"
 
@@ -51,19 +50,15 @@ struct PamrecHandle_ {
   void* mbox_peer[kP2PMaxWorld] = {};
   bool mbox_open = false;
   uint32_t mbox_epoch[kP2PSlots] = {};
-  // persistent cooperative head kernels (kernels_headcoop.cu): device-resident programs, barrier words, grid size
-  HeadProgram* prog_fwd = nullptr;
-  HeadProgram* prog_bwd = nullptr;
+  // persistent cooperative head kernels (kernels_head2.cu): barrier words, trace stamps
   unsigned* head_bar = nullptr;      // 64 words of barrier state, then 2 x 32 trace stamps (forward, backward)
   bool head_trace = false;
   unsigned long long* head_trace_cta = nullptr;   // debug: arrival stamps of every CTA at every barrier (2 kernels x 16 x 256)
-  int coop_grid = 0;
   int n_sm = 148;
   int attn_tc = 0;                  // 1: attention forward on tcgen05 (kernels_attn_tc.cu) where the sequence length allows it
   uint32_t coop_epoch = 0;          // mailbox epoch of the cooperative kernels (one per launch, all ranks in lockstep)
-  bool use_coop() const { return coop_grid > 0 && prog_fwd && (cfg.world_size == 1 || mbox_open); }
-  // row-stationary head (kernels_head2.cu): the default; PAMREC_HEAD=tiles selects the tile programs, PAMREC_HEAD_LEGACY=1 the
-  // stand-alone kernels
+  // row-stationary persistent head kernels (kernels_head2.cu): the default; PAMREC_HEAD_LEGACY=1 (or a device without
+  // cooperative launch, or more than 8 ranks) selects the stand-alone kernels of kernels_head.cu
   Head2 head2;
   int head2_grid = 0;
   bool use_head2() const { return head2_grid > 0 && (cfg.world_size == 1 || mbox_open); }
@@ -77,8 +72,6 @@ struct PamrecHandle_ {
     for (int p = 0; p < kP2PMaxWorld; ++p)
       if (mbox_peer[p] && mbox_peer[p] != mbox) cudaIpcCloseMemHandle(mbox_peer[p]);
     if (mbox) cudaFree(mbox);
-    if (prog_fwd) cudaFree(prog_fwd);
-    if (prog_bwd) cudaFree(prog_bwd);
     if (head_bar) cudaFree(head_bar);
     if (head_trace_cta) cudaFree(head_trace_cta);
     for (auto e : ev_side) if (e) cudaEventDestroy(e);
@@ -276,7 +269,7 @@ static BnSet make_bn(PamrecHandle h, int id, const char* name) {
   return s;
 }
 
-static int build_head_programs(PamrecHandle h, cudaStream_t st);
+static int build_head(PamrecHandle h, cudaStream_t st);
 static HeadDyn head_dyn(PamrecHandle h, const PamrecBatch* b, bool training, int slot0);
 
 int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
@@ -335,7 +328,7 @@ int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
     return fail(h, "cudaMallocHost for the exchange counts failed");
   cudaMemcpyAsync(h->wi("seg_id"), h->h_seg_id.data(), h->h_seg_id.size() * 4, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(h->wi("seg_tab"), h->h_seg_tab.data(), h->h_seg_tab.size() * 4, cudaMemcpyHostToDevice, st);
-  if (int rc = build_head_programs(h, st)) return rc;
+  if (int rc = build_head(h, st)) return rc;
   cudaStreamSynchronize(st);
   h->bound = true;
   return check_cuda(h, "bind");
@@ -636,13 +629,6 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     if (launch_head2_fwd(h->head2, d, h->head2_grid, training ? "head_fwd" : "head_score", st)) return check_cuda(h, "cooperative head launch");
     return check_cuda(h, "forward");
   }
-  if (h->use_coop()) {
-    // the whole head as ONE persistent cooperative kernel (kernels_headcoop.cu)
-    HeadDyn d = head_dyn(h, b, training != 0, 0);
-    if (launch_head_program(h->prog_fwd, d, h->coop_grid, training ? "head_fwd" : "head_score", st)) return check_cuda(h, "cooperative head launch");
-    if (pred_out) launch_sigmoid_col0(h->wf("logits"), pred_out, B, st);
-    return check_cuda(h, "forward");
-  }
   if (!training) {
     for (int i = 0; i < BN_COUNT; ++i) launch_bn_eval_stat(bn[i], st);
     nl += BN_COUNT;
@@ -755,266 +741,48 @@ static HeadDyn head_dyn(PamrecHandle h, const PamrecBatch* b, bool training, int
   return d;
 }
 
-// The two programs of the persistent head kernels: the same layer descriptions as the stand-alone launch sequence further
-// down (which stays as the PAMREC_HEAD_LEGACY=1 path), grouped into barrier-separated phases.
-static int build_head_programs(PamrecHandle h, cudaStream_t st) {
-  static_assert(BN_S1 == BN_S1_ && BN_E1 == BN_E1_ && BN_G1 == BN_G1_ && BN_COUNT == BN_COUNT_, "headcoop.h mirrors layout.h:BnId");
+// Pointers of the row-stationary head kernels (kernels_head2.cu); they never change after pamrec_bind.
+static int build_head(PamrecHandle h, cudaStream_t st) {
   h->head2_grid = 0;
-  if (getenv("PAMREC_HEAD_LEGACY") != nullptr) { h->coop_grid = 0; return 0; }
-  if (h->cfg.world_size > kP2PMaxWorld) { h->coop_grid = 0; return 0; }
-  {
-    const char* hs = getenv("PAMREC_HEAD");
-    if (hs == nullptr || std::string(hs) != "tiles") {
-      const Layout& L = h->L;
-      Head2& H = h->head2;
-      memset(&H, 0, sizeof H);
-      H.H = h->wf("blk1.out"); H.tgt = h->wf("tgt");
-      H.s_w0 = h->P(L.score.w0); H.s_b0 = h->P(L.score.b0); H.s_w1 = h->P(L.score.w1); H.s_b1 = h->P(L.score.b1);
-      H.e_w0 = h->P(L.expert.w0); H.e_b0 = h->P(L.expert.b0); H.e_w1 = h->P(L.expert.w1); H.e_b1 = h->P(L.expert.b1);
-      H.g_w0 = h->P(L.gate.w0); H.g_b0 = h->P(L.gate.b0); H.g_w1 = h->P(L.gate.w1); H.g_b1 = h->P(L.gate.b1);
-      H.t_w0 = h->P(L.tower.w0); H.t_b0 = h->P(L.tower.b0); H.t_w1 = h->P(L.tower.w1); H.t_b1 = h->P(L.tower.b1);
-      H.t_wo = h->P(L.tower.wout); H.t_bo = h->P(L.tower.bout);
-      H.ds_w0 = h->G(L.score.w0); H.ds_b0 = h->G(L.score.b0); H.ds_w1 = h->G(L.score.w1); H.ds_b1 = h->G(L.score.b1);
-      H.de_w0 = h->G(L.expert.w0); H.de_b0 = h->G(L.expert.b0); H.de_w1 = h->G(L.expert.w1); H.de_b1 = h->G(L.expert.b1);
-      H.dg_w0 = h->G(L.gate.w0); H.dg_b0 = h->G(L.gate.b0); H.dg_w1 = h->G(L.gate.w1); H.dg_b1 = h->G(L.gate.b1);
-      H.dt_w0 = h->G(L.tower.w0); H.dt_b0 = h->G(L.tower.b0); H.dt_w1 = h->G(L.tower.w1); H.dt_b1 = h->G(L.tower.b1);
-      H.dt_wo = h->G(L.tower.wout); H.dt_bo = h->G(L.tower.bout);
-      H.wT = h->wf("head.wT");
-      static_assert(kHead2Groups == 8, "layout.h: bn.gsums / bn.gbsums hold 8 copies");
-      for (int i = 0; i < BN_COUNT; ++i) {
-        H.bn[i] = h->bn[i];
-        // set i's copies are contiguous: [kHead2Groups][C_i][2], sets one after the other
-        H.gsums[i] = h->wd("bn.gsums") + (size_t)kHead2Groups * L.bn_bsums_off[i];
-        H.gbsums[i] = h->wd("bn.gbsums") + (size_t)kHead2Groups * L.bn_bsums_off[i];
-      }
-      H.z1 = h->wf("z1"); H.z2 = h->wf("z2"); H.aw = h->wf("pool.aw"); H.new_long = h->wf("new_long");
-      H.ze0 = h->wf("ze0"); H.zg0 = h->wf("zg0"); H.ze1 = h->wf("ze1"); H.zg1 = h->wf("zg1"); H.u = h->wf("u");
-      H.zt0 = h->wf("zt0"); H.zt1 = h->wf("zt1"); H.logits = h->wf("logits");
-      H.d_logits = h->wf("d_logits"); H.d_t1 = h->wf("d_t1"); H.d_t0 = h->wf("d_t0"); H.d_e1 = h->wf("d_e1"); H.d_g1 = h->wf("d_g1");
-      H.d_e0 = h->wf("d_e0"); H.d_g0 = h->wf("d_g0"); H.d_new_long = h->wf("d_new_long"); H.d_tgt = h->wf("d_tgt");
-      H.d_z2 = h->wf("d_z2"); H.g_a = h->wf("g_a");
-      H.loss_acc = h->wd("loss_acc"); H.dp_scalars = h->wd("dp.scalars");
-      const int g2 = head2_grid();
-      if (g2 > 0) {
-        if (!h->head_bar) {
-          if (cudaMalloc(&h->head_bar, 256 + 2 * 32 * 8) != cudaSuccess) return check_cuda(h, "head barrier alloc");
-          cudaMemsetAsync(h->head_bar, 0, 256 + 2 * 32 * 8, st);
-        }
-        h->head2_grid = g2;
-        h->coop_grid = 0;
-        return check_cuda(h, "head2");
-      }
-      cudaGetLastError();
-    }
-  }
-  int per_sm = 0;
-  const int grid = head_program_grid(&per_sm);
-  if (grid <= 0) { cudaGetLastError(); h->coop_grid = 0; return 0; }   // no cooperative launch on this device: stand-alone kernels
+  if (getenv("PAMREC_HEAD_LEGACY") != nullptr) return 0;
+  if (h->cfg.world_size > kP2PMaxWorld) return 0;
   const Layout& L = h->L;
-  BnSet* bn = h->bn;
-  const float* Pb = h->buf.dense_param;
-  const float gs = 1.0f / (float)h->cfg.world_size;
-  std::vector<HeadPhase> F, K;
-  auto phase = [](int op, int rows_n) { HeadPhase p; memset(&p, 0, sizeof p); p.op = op; p.rows_n = rows_n; return p; };
-  auto fin = [](HeadPhase& p, std::initializer_list<int> ids, int rows_n) {
-    p.barrier = 1; p.fin_rows_n = rows_n;
-    for (int id : ids) { p.fin[p.n_fin++] = id; p.sync[p.n_sync++] = id; }
-  };
-  auto grad_of = [&](int id, const float* Z) {
-    BnGrad g; g.Z = Z; g.stat = bn[id].stat; g.gamma = bn[id].gamma; g.beta = bn[id].beta; g.bsums = bn[id].bsums; g.count = 0.0;
-    return g;
-  };
-  auto out_of = [&](int id, const float* Z) {
-    BnGradOut o; o.Z = Z; o.stat = bn[id].stat; o.gamma = bn[id].gamma; o.beta = bn[id].beta; o.bsums = bn[id].bsums;
-    return o;
-  };
-  auto dw_bn = [&](DenseDwP& w, int id, const float* Z) {
-    w.g = grad_of(id, Z); w.g_dgamma = bn[id].dgamma; w.g_dbeta = bn[id].dbeta; w.g_C = bn[id].C; w.g_scale = gs;
-  };
-  const float* H = h->wf("blk1.out");
-  // ------------------------------------------------------------------ forward
-  {
-    HeadPhase p = phase(HEAD_OP_NONE, 0); p.only = 2; p.barrier = 1; p.eval_stats = 1; F.push_back(p);
+  Head2& H = h->head2;
+  memset(&H, 0, sizeof H);
+  H.H = h->wf("blk1.out"); H.tgt = h->wf("tgt");
+  H.s_w0 = h->P(L.score.w0); H.s_b0 = h->P(L.score.b0); H.s_w1 = h->P(L.score.w1); H.s_b1 = h->P(L.score.b1);
+  H.e_w0 = h->P(L.expert.w0); H.e_b0 = h->P(L.expert.b0); H.e_w1 = h->P(L.expert.w1); H.e_b1 = h->P(L.expert.b1);
+  H.g_w0 = h->P(L.gate.w0); H.g_b0 = h->P(L.gate.b0); H.g_w1 = h->P(L.gate.w1); H.g_b1 = h->P(L.gate.b1);
+  H.t_w0 = h->P(L.tower.w0); H.t_b0 = h->P(L.tower.b0); H.t_w1 = h->P(L.tower.w1); H.t_b1 = h->P(L.tower.b1);
+  H.t_wo = h->P(L.tower.wout); H.t_bo = h->P(L.tower.bout);
+  H.ds_w0 = h->G(L.score.w0); H.ds_b0 = h->G(L.score.b0); H.ds_w1 = h->G(L.score.w1); H.ds_b1 = h->G(L.score.b1);
+  H.de_w0 = h->G(L.expert.w0); H.de_b0 = h->G(L.expert.b0); H.de_w1 = h->G(L.expert.w1); H.de_b1 = h->G(L.expert.b1);
+  H.dg_w0 = h->G(L.gate.w0); H.dg_b0 = h->G(L.gate.b0); H.dg_w1 = h->G(L.gate.w1); H.dg_b1 = h->G(L.gate.b1);
+  H.dt_w0 = h->G(L.tower.w0); H.dt_b0 = h->G(L.tower.b0); H.dt_w1 = h->G(L.tower.w1); H.dt_b1 = h->G(L.tower.b1);
+  H.dt_wo = h->G(L.tower.wout); H.dt_bo = h->G(L.tower.bout);
+  H.wT = h->wf("head.wT");
+  static_assert(kHead2Groups == 8, "layout.h: bn.gsums / bn.gbsums hold 8 copies");
+  for (int i = 0; i < BN_COUNT; ++i) {
+    H.bn[i] = h->bn[i];
+    // set i's copies are contiguous: [kHead2Groups][C_i][2], sets one after the other
+    H.gsums[i] = h->wd("bn.gsums") + (size_t)kHead2Groups * L.bn_bsums_off[i];
+    H.gbsums[i] = h->wd("bn.gbsums") + (size_t)kHead2Groups * L.bn_bsums_off[i];
   }
-  {
-    HeadPhase p = phase(HEAD_OP_DENSE_FWD, 1);
-    p.u.f = dense_p(H, kD, 0, 1, kD, 20, h->P(L.score.w0), 0, h->P(L.score.b0), 0, h->wf("z1"), 20);
-    p.u.f.out_sums = bn[BN_S0].sums;
-    fin(p, {BN_S0}, 1); p.sync_scalars = 1; F.push_back(p);
-    HeadPhase q = phase(HEAD_OP_DENSE_FWD, 1);
-    q.u.f = dense_p(h->wf("z1"), 20, 0, 1, 20, 1, h->P(L.score.w1), 0, h->P(L.score.b1), 0, h->wf("z2"), 1);
-    set_in_bn(q.u.f, bn[BN_S0]); q.u.f.out_sums = bn[BN_S1].sums;
-    fin(q, {BN_S1}, 1); F.push_back(q);
-    HeadPhase r = phase(HEAD_OP_POOL_FWD, 0);
-    r.u.pl.H = H; r.u.pl.Z2 = h->wf("z2"); r.u.pl.new_long = h->wf("new_long");
-    r.barrier = 1; F.push_back(r);
-  }
-  {
-    HeadPhase e0 = phase(HEAD_OP_DENSE_FWD, 0);
-    e0.u.f = dense_p(h->wf("new_long"), kD, 0, 5, kD, 100, h->P(L.expert.w0), 4000, h->P(L.expert.b0), 100, h->wf("ze0"), 500);
-    for (int g = 0; g < 5; ++g) { e0.u.f.x_off[g] = 0; e0.u.f.z_off[g] = g * 100; }
-    e0.u.f.out_sums = bn[BN_E0].sums; F.push_back(e0);
-    HeadPhase g0 = phase(HEAD_OP_DENSE_FWD, 0);
-    g0.u.f = dense_p(h->wf("new_long"), kD, 0, 2, kD, 64, h->P(L.gate.w0), 2560, h->P(L.gate.b0), 64, h->wf("zg0"), 128);
-    for (int g = 0; g < 2; ++g) { g0.u.f.x_off[g] = 0; g0.u.f.z_off[g] = g * 64; }
-    g0.u.f.out_sums = bn[BN_G0].sums;
-    fin(g0, {BN_E0, BN_G0}, 0); F.push_back(g0);
-    HeadPhase e1 = phase(HEAD_OP_DENSE_FWD, 0);
-    e1.u.f = dense_p(h->wf("ze0"), 500, 0, 5, 100, 64, h->P(L.expert.w1), 6400, h->P(L.expert.b1), 64, h->wf("ze1"), 320);
-    for (int g = 0; g < 5; ++g) { e1.u.f.x_off[g] = g * 100; e1.u.f.z_off[g] = g * 64; }
-    set_in_bn(e1.u.f, bn[BN_E0]); e1.u.f.out_sums = bn[BN_E1].sums; F.push_back(e1);
-    HeadPhase g1 = phase(HEAD_OP_DENSE_FWD, 0);
-    g1.u.f = dense_p(h->wf("zg0"), 128, 0, 2, 64, 5, h->P(L.gate.w1), 320, h->P(L.gate.b1), 5, h->wf("zg1"), 10);
-    for (int g = 0; g < 2; ++g) { g1.u.f.x_off[g] = g * 64; g1.u.f.z_off[g] = g * 5; }
-    set_in_bn(g1.u.f, bn[BN_G0]); g1.u.f.out_sums = bn[BN_G1].sums;
-    fin(g1, {BN_E1, BN_G1}, 0); F.push_back(g1);
-    HeadPhase c = phase(HEAD_OP_COMBINE_FWD, 0);
-    c.u.cb.ZE1 = h->wf("ze1"); c.u.cb.ZG1 = h->wf("zg1"); c.u.cb.tgt = h->wf("tgt"); c.u.cb.U = h->wf("u");
-    c.barrier = 1; F.push_back(c);
-  }
-  {
-    HeadPhase t0 = phase(HEAD_OP_DENSE_FWD, 0);
-    t0.u.f = dense_p(h->wf("u"), 168, 0, 3, 84, 100, h->P(L.tower.w0), 8400, h->P(L.tower.b0), 100, h->wf("zt0"), 300);
-    t0.u.f.x_off[0] = 0; t0.u.f.x_off[1] = 84; t0.u.f.x_off[2] = 0;
-    for (int g = 0; g < 3; ++g) t0.u.f.z_off[g] = g * 100;
-    t0.u.f.out_sums = bn[BN_T0].sums;
-    fin(t0, {BN_T0}, 0); F.push_back(t0);
-    HeadPhase t1 = phase(HEAD_OP_DENSE_FWD, 0);
-    t1.u.f = dense_p(h->wf("zt0"), 300, 0, 3, 100, 64, h->P(L.tower.w1), 6400, h->P(L.tower.b1), 64, h->wf("zt1"), 192);
-    for (int g = 0; g < 3; ++g) { t1.u.f.x_off[g] = g * 100; t1.u.f.z_off[g] = g * 64; }
-    set_in_bn(t1.u.f, bn[BN_T0]); t1.u.f.out_sums = bn[BN_T1].sums;
-    fin(t1, {BN_T1}, 0); F.push_back(t1);
-    HeadPhase to = phase(HEAD_OP_DENSE_FWD, 0);
-    to.u.f = dense_p(h->wf("zt1"), 192, 0, 3, 64, 1, h->P(L.tower.wout), 64, h->P(L.tower.bout), 1, h->wf("logits"), 3);
-    for (int g = 0; g < 3; ++g) { to.u.f.x_off[g] = g * 64; to.u.f.z_off[g] = g; }
-    set_in_bn(to.u.f, bn[BN_T1]); F.push_back(to);
-  }
-  // ------------------------------------------------------------------ backward
-  auto sync_b = [](HeadPhase& p, std::initializer_list<int> ids) {
-    p.barrier = 1; p.sync_bwd = 1;
-    for (int id : ids) p.sync[p.n_sync++] = id;
-  };
-  {
-    HeadPhase l = phase(HEAD_OP_LOSS, 0);
-    l.u.ls.logits = h->wf("logits"); l.u.ls.d_logits = h->wf("d_logits"); l.u.ls.loss_acc = h->wd("loss_acc");
-    l.u.ls.n_valid_global = h->wd("dp.scalars");
-    l.barrier = 1; K.push_back(l);
-  }
-  {  // towers
-    HeadPhase x = phase(HEAD_OP_DENSE_DX, 0);
-    x.u.x = dx_p(h->wf("d_logits"), 3, 0, 64, Pb, h->wf("d_t1"), 192, 0);
-    for (int g = 0; g < 3; ++g) dx_add(x.u.x, g, g * 64, g, L.tower.wout + g * 64, 1);
-    x.u.x.o = out_of(BN_T1, h->wf("zt1")); K.push_back(x);
-    HeadPhase w = phase(HEAD_OP_DENSE_DW, 0);
-    w.u.w = dw_p(h->wf("zt1"), 192, 0, 3, 64, 1, h->wf("d_logits"), 3, h->G(L.tower.wout), 64, h->G(L.tower.bout), 1);
-    for (int g = 0; g < 3; ++g) { w.u.w.x_off[g] = g * 64; w.u.w.z_off[g] = g; }
-    set_in_bn_dw(w.u.w, bn[BN_T1]);
-    sync_b(w, {BN_T1}); K.push_back(w);
-    HeadPhase x1 = phase(HEAD_OP_DENSE_DX, 0);
-    x1.u.x = dx_p(h->wf("d_t1"), 192, 0, 100, Pb, h->wf("d_t0"), 300, 0);
-    for (int g = 0; g < 3; ++g) dx_add(x1.u.x, g, g * 100, g * 64, L.tower.w1 + (int64_t)g * 6400, 64);
-    x1.u.x.g = grad_of(BN_T1, h->wf("zt1")); x1.u.x.o = out_of(BN_T0, h->wf("zt0")); K.push_back(x1);
-    HeadPhase w1 = phase(HEAD_OP_DENSE_DW, 0);
-    w1.u.w = dw_p(h->wf("zt0"), 300, 0, 3, 100, 64, h->wf("d_t1"), 192, h->G(L.tower.w1), 6400, h->G(L.tower.b1), 64);
-    for (int g = 0; g < 3; ++g) { w1.u.w.x_off[g] = g * 100; w1.u.w.z_off[g] = g * 64; }
-    set_in_bn_dw(w1.u.w, bn[BN_T0]); dw_bn(w1.u.w, BN_T1, h->wf("zt1"));
-    sync_b(w1, {BN_T0}); K.push_back(w1);
-    HeadPhase x0 = phase(HEAD_OP_DENSE_DX, 0);
-    x0.u.x = dx_p(h->wf("d_t0"), 300, 0, 84, Pb, h->wf("d_u"), 168, 0);
-    dx_add(x0.u.x, 0, 0, 0, L.tower.w0, 100);
-    dx_add(x0.u.x, 0, 0, 200, L.tower.w0 + 2 * 8400, 100);
-    dx_add(x0.u.x, 1, 84, 100, L.tower.w0 + 8400, 100);
-    x0.u.x.g = grad_of(BN_T0, h->wf("zt0")); K.push_back(x0);
-    HeadPhase w0 = phase(HEAD_OP_DENSE_DW, 0);
-    w0.u.w = dw_p(h->wf("u"), 168, 0, 3, 84, 100, h->wf("d_t0"), 300, h->G(L.tower.w0), 8400, h->G(L.tower.b0), 100);
-    w0.u.w.x_off[0] = 0; w0.u.w.x_off[1] = 84; w0.u.w.x_off[2] = 0;
-    for (int g = 0; g < 3; ++g) w0.u.w.z_off[g] = g * 100;
-    dw_bn(w0.u.w, BN_T0, h->wf("zt0"));
-    w0.barrier = 1; K.push_back(w0);
-  }
-  {  // mixing + MMoE
-    HeadPhase c = phase(HEAD_OP_COMBINE_BWD, 0);
-    c.u.cb.ZE1 = h->wf("ze1"); c.u.cb.ZG1 = h->wf("zg1"); c.u.cb.dU = h->wf("d_u"); c.u.cb.dE1 = h->wf("d_e1");
-    c.u.cb.dG1 = h->wf("d_g1"); c.u.cb.dTgt = h->wf("d_tgt");
-    sync_b(c, {BN_E1, BN_G1}); K.push_back(c);
-    HeadPhase xe = phase(HEAD_OP_DENSE_DX, 0);
-    xe.u.x = dx_p(h->wf("d_e1"), 320, 0, 100, Pb, h->wf("d_e0"), 500, 0);
-    for (int g = 0; g < 5; ++g) dx_add(xe.u.x, g, g * 100, g * 64, L.expert.w1 + (int64_t)g * 6400, 64);
-    xe.u.x.g = grad_of(BN_E1, h->wf("ze1")); xe.u.x.o = out_of(BN_E0, h->wf("ze0")); K.push_back(xe);
-    HeadPhase xg = phase(HEAD_OP_DENSE_DX, 0);
-    xg.u.x = dx_p(h->wf("d_g1"), 10, 0, 64, Pb, h->wf("d_g0"), 128, 0);
-    for (int g = 0; g < 2; ++g) dx_add(xg.u.x, g, g * 64, g * 5, L.gate.w1 + (int64_t)g * 320, 5);
-    xg.u.x.g = grad_of(BN_G1, h->wf("zg1")); xg.u.x.o = out_of(BN_G0, h->wf("zg0")); K.push_back(xg);
-    HeadPhase we = phase(HEAD_OP_DENSE_DW, 0);
-    we.u.w = dw_p(h->wf("ze0"), 500, 0, 5, 100, 64, h->wf("d_e1"), 320, h->G(L.expert.w1), 6400, h->G(L.expert.b1), 64);
-    for (int g = 0; g < 5; ++g) { we.u.w.x_off[g] = g * 100; we.u.w.z_off[g] = g * 64; }
-    set_in_bn_dw(we.u.w, bn[BN_E0]); dw_bn(we.u.w, BN_E1, h->wf("ze1")); K.push_back(we);
-    HeadPhase wg = phase(HEAD_OP_DENSE_DW, 0);
-    wg.u.w = dw_p(h->wf("zg0"), 128, 0, 2, 64, 5, h->wf("d_g1"), 10, h->G(L.gate.w1), 320, h->G(L.gate.b1), 5);
-    for (int g = 0; g < 2; ++g) { wg.u.w.x_off[g] = g * 64; wg.u.w.z_off[g] = g * 5; }
-    set_in_bn_dw(wg.u.w, bn[BN_G0]); dw_bn(wg.u.w, BN_G1, h->wf("zg1"));
-    sync_b(wg, {BN_E0, BN_G0}); K.push_back(wg);
-    HeadPhase xe0 = phase(HEAD_OP_DENSE_DX, 0);
-    xe0.u.x = dx_p(h->wf("d_e0"), 500, 0, kD, Pb, h->wf("d_new_long"), kD, 0);
-    for (int g = 0; g < 5; ++g) dx_add(xe0.u.x, 0, 0, g * 100, L.expert.w0 + (int64_t)g * 4000, 100);
-    xe0.u.x.g = grad_of(BN_E0, h->wf("ze0")); K.push_back(xe0);
-    HeadPhase we0 = phase(HEAD_OP_DENSE_DW, 0);
-    we0.u.w = dw_p(h->wf("new_long"), kD, 0, 5, kD, 100, h->wf("d_e0"), 500, h->G(L.expert.w0), 4000, h->G(L.expert.b0), 100);
-    for (int g = 0; g < 5; ++g) { we0.u.w.x_off[g] = 0; we0.u.w.z_off[g] = g * 100; }
-    dw_bn(we0.u.w, BN_E0, h->wf("ze0")); K.push_back(we0);
-    HeadPhase wg0 = phase(HEAD_OP_DENSE_DW, 0);
-    wg0.u.w = dw_p(h->wf("new_long"), kD, 0, 2, kD, 64, h->wf("d_g0"), 128, h->G(L.gate.w0), 2560, h->G(L.gate.b0), 64);
-    for (int g = 0; g < 2; ++g) { wg0.u.w.x_off[g] = 0; wg0.u.w.z_off[g] = g * 64; }
-    dw_bn(wg0.u.w, BN_G0, h->wf("zg0"));
-    wg0.barrier = 1; K.push_back(wg0);
-    HeadPhase xg0 = phase(HEAD_OP_DENSE_DX, 0);                  // accumulates onto the experts' part: its own barrier interval
-    xg0.u.x = dx_p(h->wf("d_g0"), 128, 0, kD, Pb, h->wf("d_new_long"), kD, 1);
-    for (int g = 0; g < 2; ++g) dx_add(xg0.u.x, 0, 0, g * 64, L.gate.w0 + (int64_t)g * 2560, 64);
-    xg0.u.x.g = grad_of(BN_G0, h->wf("zg0"));
-    xg0.barrier = 1; K.push_back(xg0);
-  }
-  {  // attention pooling
-    HeadPhase pb = phase(HEAD_OP_POOL_BWD, 0);
-    pb.u.pl.H = H; pb.u.pl.Z2 = h->wf("z2"); pb.u.pl.dNL = h->wf("d_new_long"); pb.u.pl.dA2 = h->wf("d_z2"); pb.u.pl.dH = h->wf("g_a");
-    sync_b(pb, {BN_S1}); K.push_back(pb);
-    HeadPhase x1 = phase(HEAD_OP_DENSE_DX, 1);
-    x1.u.x = dx_p(h->wf("d_z2"), 1, 0, 20, Pb, h->wf("d_a1"), 20, 0);
-    dx_add(x1.u.x, 0, 0, 0, L.score.w1, 1);
-    x1.u.x.g = grad_of(BN_S1, h->wf("z2")); x1.u.x.o = out_of(BN_S0, h->wf("z1")); K.push_back(x1);
-    HeadPhase w1 = phase(HEAD_OP_DENSE_DW, 1);
-    w1.u.w = dw_p(h->wf("z1"), 20, 0, 1, 20, 1, h->wf("d_z2"), 1, h->G(L.score.w1), 0, h->G(L.score.b1), 0);
-    set_in_bn_dw(w1.u.w, bn[BN_S0]); dw_bn(w1.u.w, BN_S1, h->wf("z2"));
-    sync_b(w1, {BN_S0}); K.push_back(w1);
-    HeadPhase x0 = phase(HEAD_OP_DENSE_DX, 1);
-    x0.u.x = dx_p(h->wf("d_a1"), 20, 0, kD, Pb, h->wf("g_a"), kD, 1);
-    dx_add(x0.u.x, 0, 0, 0, L.score.w0, 20);
-    x0.u.x.g = grad_of(BN_S0, h->wf("z1")); K.push_back(x0);
-    HeadPhase w0 = phase(HEAD_OP_DENSE_DW, 1);
-    w0.u.w = dw_p(H, kD, 0, 1, kD, 20, h->wf("d_a1"), 20, h->G(L.score.w0), 0, h->G(L.score.b0), 0);
-    dw_bn(w0.u.w, BN_S0, h->wf("z1")); K.push_back(w0);
-  }
-  if ((int)F.size() > kHeadMaxPhases || (int)K.size() > kHeadMaxPhases) return fail(h, "head program too long");
-  std::vector<HeadProgram> host(2);
-  for (int k = 0; k < 2; ++k) {
-    HeadProgram& P = host[k];
-    memset(&P, 0, sizeof P);
-    const std::vector<HeadPhase>& src = k == 0 ? F : K;
-    P.n = (int)src.size();
-    for (int i = 0; i < BN_COUNT; ++i) P.bn[i] = bn[i];
-    P.dp_scalars = h->wd("dp.scalars");
-    for (int i = 0; i < P.n; ++i) memcpy(&P.ph[i], &src[i], sizeof(HeadPhase));
-  }
-  if (!h->prog_fwd && cudaMalloc(&h->prog_fwd, sizeof(HeadProgram)) != cudaSuccess) return check_cuda(h, "head program alloc");
-  if (!h->prog_bwd && cudaMalloc(&h->prog_bwd, sizeof(HeadProgram)) != cudaSuccess) return check_cuda(h, "head program alloc");
+  H.z1 = h->wf("z1"); H.z2 = h->wf("z2"); H.aw = h->wf("pool.aw"); H.new_long = h->wf("new_long");
+  H.ze0 = h->wf("ze0"); H.zg0 = h->wf("zg0"); H.ze1 = h->wf("ze1"); H.zg1 = h->wf("zg1"); H.u = h->wf("u");
+  H.zt0 = h->wf("zt0"); H.zt1 = h->wf("zt1"); H.logits = h->wf("logits");
+  H.d_logits = h->wf("d_logits"); H.d_t1 = h->wf("d_t1"); H.d_t0 = h->wf("d_t0"); H.d_e1 = h->wf("d_e1"); H.d_g1 = h->wf("d_g1");
+  H.d_e0 = h->wf("d_e0"); H.d_g0 = h->wf("d_g0"); H.d_new_long = h->wf("d_new_long"); H.d_tgt = h->wf("d_tgt");
+  H.d_z2 = h->wf("d_z2"); H.g_a = h->wf("g_a");
+  H.loss_acc = h->wd("loss_acc"); H.dp_scalars = h->wd("dp.scalars");
+  const int g2 = head2_grid();
+  if (g2 <= 0) { cudaGetLastError(); return 0; }           // no cooperative launch on this device: stand-alone kernels
   if (!h->head_bar) {
     if (cudaMalloc(&h->head_bar, 256 + 2 * 32 * 8) != cudaSuccess) return check_cuda(h, "head barrier alloc");
     cudaMemsetAsync(h->head_bar, 0, 256 + 2 * 32 * 8, st);
   }
-  cudaMemcpyAsync(h->prog_fwd, &host[0], sizeof(HeadProgram), cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(h->prog_bwd, &host[1], sizeof(HeadProgram), cudaMemcpyHostToDevice, st);
-  cudaStreamSynchronize(st);                            // `host` goes out of scope
-  h->coop_grid = grid;
-  return check_cuda(h, "head programs");
+  h->head2_grid = g2;
+  return check_cuda(h, "head2");
 }
 
 int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
@@ -1035,7 +803,7 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   cudaMemsetAsync(h->wd("loss_acc"), 0, 8 * sizeof(double), st);
   cudaMemsetAsync(h->wd("sp_normsq"), 0, 8 * sizeof(double), st);
   const bool rows = h->use_head2();
-  const bool coop = rows || h->use_coop();
+  const bool coop = rows;
   if (!coop) {
   launch_loss(h->wf("logits"), b->labels_satisfied, b->labels_play, b->plays, h->wf("d_logits"), h->wd("loss_acc"), B, Bg,
               W > 1 ? h->wd("dp.scalars") : nullptr, h->cfg.fuzhu_weight, h->cfg.order_weight,
@@ -1051,10 +819,6 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
     HeadDyn d = head_dyn(h, b, true, 12);
     if (launch_head2_bwd(h->head2, d, h->head2_grid, st)) return check_cuda(h, "cooperative head launch");
     h->fork(st, [&](cudaStream_t s2) { launch_head2_dw(h->head2, B, s2); });
-  } else if (coop) {
-    // loss + the whole head backward (activation, weight and batch-norm gradients) as ONE persistent cooperative kernel
-    HeadDyn d = head_dyn(h, b, true, 12);
-    if (launch_head_program(h->prog_bwd, d, h->coop_grid, "head_bwd", st)) return check_cuda(h, "cooperative head launch");
   }
   int p2p_slot = 6;
   auto sync_bsums = [&](std::initializer_list<int> ids) {

@@ -1,6 +1,5 @@
-// Tile bodies of the head kernels as device functions: one "item" = what one CTA of kHT threads does.  The stand-alone
-// kernels (kernels_head.cu) call them with (blockIdx, gridDim); the persistent cooperative head kernels
-// (kernels_headcoop.cu) call them from their phase loops with item indices, separated by grid-wide barriers.
+// Tile bodies of the stand-alone head kernels (kernels_head.cu, the PAMREC_HEAD_LEGACY=1 / no-cooperative-launch path) as
+// device functions: one "item" = what one CTA of kHT threads does, called with (blockIdx, gridDim).
 #pragma once
 #include "kernels.h"
 

@@ -4,7 +4,7 @@
 //
 // Why: every layer of the head is followed by a batch norm over the whole batch (pamrec.py:366-372, base_model.py:680-686), so a
 // step has 6 + 6 points where every row must have been seen; in between the work is a few MFLOP.  The tile programs that ran
-// here before (kernels_headcoop.cu) re-distributed 32 x 32 output tiles over the grid in every phase: 31 M warp instructions for
+// here before (round 2, first half; profiles/r02_bench_coop4.json) re-distributed 32 x 32 output tiles over the grid in every phase: 31 M warp instructions for
 // 3 M warp-FMAs of arithmetic, 8 + 10 barriers, 0.57 ms.  Here
 //   * a CTA stages the (batch-normalised, rectified) inputs of its <= 8 rows in shared memory, a thread owns one OUTPUT COLUMN
 //     and keeps the 8 row accumulators in registers: per k one coalesced weight load and two broadcast LDS.128 feed 8 FFMAs,
@@ -31,7 +31,9 @@ constexpr int kXS = 640;                     // staged input columns per chunk (
 constexpr int kWBuf = 32768;                 // floats of next-phase weights held in shared memory (largest set: 32 640)
 constexpr int kSlots = 25;                   // tokens in flight per pass of the score-MLP phases: 25 x 20 columns = 500 threads
 
-// ---- memory-ordering helpers (see kernels_headcoop.cu for the measurements behind relaxed polling)
+// ---- memory-ordering helpers.  Spin loads are RELAXED: an acquire load makes the SM invalidate its whole L1 (CCTL.IVALL) after
+// every poll, which starved the warps that were still working; the acquire happens once, by a fence, after the awaited value
+// has been seen.
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   unsigned v;

@@ -395,7 +395,7 @@ __device__ __forceinline__ void sp2_sweep_table(const Sp2& s, const AdamP& a, in
 }
 struct Sp2SweepGrid { int g[4]; };                       // CTAs per table
 template <int MODE, bool LAZY>
-__global__ void __launch_bounds__(256) k_sp2_adam_sweep(const Sp2 s, const AdamP a, const Sp2SweepGrid sg) {
+__global__ void __launch_bounds__(256, 8) k_sp2_adam_sweep(const Sp2 s, const AdamP a, const Sp2SweepGrid sg) {
   int b = blockIdx.x, t = 0;
   while (t < 3 && b >= sg.g[t]) { b -= sg.g[t]; ++t; }
   const float scale = sp2_clip_scale(s, a, t);

@@ -11,7 +11,13 @@ hdr = next(r)
 ki, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
 data = [(x[ki], x[gi], x[bi], float(x[vi].replace(",", ""))) for x in r]
 idx = [i for i, d in enumerate(data) if "k_embed_fwd" in d[0]]
-if len(idx) >= 2:
+# the bench runs its timed steps first and the large-batch HBM microbench afterwards: a step of the bench workload is a window
+# between two gathers of the FIRST grid size seen (the 4th such window: past the warm-up), unless --last asks for the last one
+same = [i for i in idx if data[i][1] == data[idx[0]][1]] if idx else []
+if "--last" not in sys.argv and len(same) >= 2:
+    k = min(4, len(same) - 2)
+    s, e = same[k], same[k + 1]
+elif len(idx) >= 2:
     s, e = idx[-2], idx[-1]
 else:                                   # window holds one step start: take a full step's worth of launches around it
     fin = [i for i, d in enumerate(data) if "k_finish_losses" in d[0]]
