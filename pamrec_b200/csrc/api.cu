@@ -67,6 +67,18 @@ struct PamrecHandle_ {
     return reinterpret_cast<uint32_t*>(static_cast<char*>(mbox_peer[p]) + (size_t)kP2PSlots * cfg.world_size * kP2PMaxDoubles * sizeof(double));
   }
   uint32_t* mbox_err() const { return mbox_flags(cfg.rank) + kP2PSlots * cfg.world_size; }
+  // gradient exchange through peer memory (kernels_p2p.cu:k_xr_*): dense gradients, then the replicated tables' gradient tables
+  int64_t xr_dense() const { return (L.dense_numel + 63) / 64 * 64; }
+  int64_t xr_floats() const { return xr_dense() + (replicated() ? sp2_rep_floats(cfg.n_items, cfg.n_cates, cfg.n_users) : 0); }
+  char* xr_region(int p) const { return static_cast<char*>(mbox_peer[p]) + p2p_xr_offset(cfg.world_size); }
+  bool use_xr() const { return mbox_open && cfg.world_size > 1 && getenv("PAMREC_NCCL_GRADS") == nullptr; }
+  uint32_t xr_epoch = 0;
+  // the replicated tables' gradient tables + touch counts: inside the exchange buffers when those exist (the run walk writes
+  // the contribution in place, the Adam sweep reads the reduced copy), else a workspace tensor reduced by NCCL
+  float* rep_grad_in() const { return use_xr() ? xr_xbuf(xr_region(cfg.rank)) + xr_dense() : wf("rep.grad"); }
+  float* rep_grad_out() const {
+    return use_xr() ? xr_xbuf(xr_region(cfg.rank)) + p2p_xr_cap(cfg.world_size, xr_floats()) + xr_dense() : wf("rep.grad");
+  }
   ~PamrecHandle_() {
     if (h_counts) cudaFreeHost(h_counts);
     for (int p = 0; p < kP2PMaxWorld; ++p)
@@ -204,7 +216,7 @@ int pamrec_comm_mailbox_create(PamrecHandle h, char handle_out[PAMREC_IPC_HANDLE
   static_assert(sizeof(cudaIpcMemHandle_t) == PAMREC_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
   if (h->cfg.world_size > kP2PMaxWorld) return fail(h, "mailboxes support at most %d ranks", kP2PMaxWorld);
   if (!h->mbox) {
-    const size_t bytes = p2p_mailbox_bytes(h->cfg.world_size);
+    const size_t bytes = p2p_mailbox_bytes(h->cfg.world_size, h->xr_floats());
     if (cudaMalloc(&h->mbox, bytes) != cudaSuccess) return check_cuda(h, "mailbox alloc");
     cudaMemset(h->mbox, 0, bytes);
     cudaDeviceSynchronize();
@@ -369,7 +381,7 @@ static Sp2 make_sp2(PamrecHandle h, const PamrecBatch* b) {
   s.w[2] = h->buf.ulong_w; s.m[2] = h->buf.ulong_m; s.v[2] = h->buf.ulong_v;
   s.w[3] = h->buf.ushort_w; s.m[3] = h->buf.ushort_m; s.v[3] = h->buf.ushort_v;
   s.dX0 = h->wf("g_a"); s.dT = h->wf("d_tgt_total");
-  if (h->replicated()) { s.mode = SP2_DENSE; s.rep_grad = h->wf("rep.grad"); }
+  if (h->replicated()) { s.mode = SP2_DENSE; s.rep_grad = h->rep_grad_in(); }
   else if (c.sparse_adam_mode == PAMREC_ADAM_LAZY) s.mode = SP2_FUSED;
   else { s.mode = SP2_COMPACT; s.slot = h->wi("sp2.slot"); }
   return s;
@@ -990,6 +1002,23 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   return check_cuda(h, "backward");
 }
 
+// dense gradients (+ the replicated tables' gradient tables, already in the exchange buffer), clip norms and loss sums summed
+// over the ranks through peer memory (kernels_p2p.cu:k_xr_*)
+static void peer_allreduce_grads(PamrecHandle h, cudaStream_t st) {
+  XrArgs a;
+  memset(&a, 0, sizeof a);
+  const int W = h->cfg.world_size;
+  for (int p = 0; p < W; ++p) a.peer[p] = h->xr_region(p);
+  a.world = W; a.rank = h->cfg.rank; a.epoch = ++h->xr_epoch;
+  a.cap = p2p_xr_cap(W, h->xr_floats());
+  a.dense_grad = h->buf.dense_grad; a.n_dense = h->L.dense_numel;
+  a.scalars[0] = h->wd("sp_normsq"); a.n_scalars[0] = 8;
+  a.scalars[1] = h->wd("loss_acc"); a.n_scalars[1] = 4;
+  a.counter = reinterpret_cast<unsigned*>(h->xr_region(h->cfg.rank) + 128);
+  a.err = h->mbox_err();
+  launch_xr_allreduce(a, h->buf.dense_grad, st);
+}
+
 // ------------------------------------------------------------------------------------------
 int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, void* stream) {
   if (int rc = check_batch(h, b, true)) return rc;
@@ -1038,7 +1067,9 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
       launch_sparse_l2norm(own, nr, c.embed_l2, reg, st);
       if (t == 2) launch_sparse_l2norm(own_table(h, 2, true), nr, c.embed_l2, reg, st);
     }
-    {
+    if (h->use_xr()) {
+      peer_allreduce_grads(h, st);
+    } else {
       PAMREC_PROF("allreduce_grads", 1, st);
       crc |= cm.group_start();
       crc |= cm.all_reduce(h->buf.dense_grad, L.dense_numel, COMM_F32, st);
@@ -1068,20 +1099,26 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
     nl += 10;
     if (h->replicated()) {
       // replicated tables: gradient tables + touch counts, dense gradients, clip norms and losses summed over the ranks
-      Comm& cm = h->comm;
-      int crc = 0;
-      {
-        PAMREC_PROF("allreduce_grads", 1, st);
-        crc |= cm.group_start();
-        crc |= cm.all_reduce(h->buf.dense_grad, L.dense_numel, COMM_F32, st);
-        crc |= cm.all_reduce(s2.rep_grad, sp2_rep_floats(c.n_items, c.n_cates, c.n_users), COMM_F32, st);
-        crc |= cm.all_reduce(h->wd("sp_normsq"), 8, COMM_F64, st);
-        crc |= cm.all_reduce(h->wd("loss_acc"), 4, COMM_F64, st);
-        crc |= cm.group_end();
+      Sp2 s3 = s2;                                           // after the all-reduce: the summed gradient tables
+      if (h->use_xr()) {
+        peer_allreduce_grads(h, st);
+        s3.rep_grad = h->rep_grad_out();
+      } else {
+        Comm& cm = h->comm;
+        int crc = 0;
+        {
+          PAMREC_PROF("allreduce_grads", 1, st);
+          crc |= cm.group_start();
+          crc |= cm.all_reduce(h->buf.dense_grad, L.dense_numel, COMM_F32, st);
+          crc |= cm.all_reduce(s2.rep_grad, sp2_rep_floats(c.n_items, c.n_cates, c.n_users), COMM_F32, st);
+          crc |= cm.all_reduce(h->wd("sp_normsq"), 8, COMM_F64, st);
+          crc |= cm.all_reduce(h->wd("loss_acc"), 4, COMM_F64, st);
+          crc |= cm.group_end();
+        }
+        if (crc) return fail(h, "nccl: %s", cm.err.c_str());
       }
-      if (crc) return fail(h, "nccl: %s", cm.err.c_str());
-      launch_sp2_rep_l2(s2, st);
-      launch_sp2_adam_sweep(s2, ap, c.sparse_adam_mode == PAMREC_ADAM_LAZY ? 1 : 0, st);
+      launch_sp2_rep_l2(s3, st);
+      launch_sp2_adam_sweep(s3, ap, c.sparse_adam_mode == PAMREC_ADAM_LAZY ? 1 : 0, st);
       nl += 3;
     } else if (s2.mode == SP2_FUSED) {
       launch_sp2_lazy_finish(s2, ap, st); nl += 1;

@@ -167,7 +167,27 @@ inline size_t p2p_ll_offset(int world) {
   const size_t b = (size_t)kP2PSlots * world * kP2PMaxDoubles * sizeof(double) + (size_t)kP2PSlots * world * sizeof(uint32_t) + 256;
   return (b + 255) / 256 * 256;
 }
-inline size_t p2p_mailbox_bytes(int world) { return p2p_ll_offset(world) + (size_t)kP2PSlots * world * kP2PMaxDoubles * 16; }
+// ... then the gradient exchange region of k_xr_* (kernels_p2p.cu): flags | scalars | own contribution | reduced result
+constexpr int kXrScalars = 16;           // doubles per rank travelling with the gradients (8 clip norms + 4 loss sums)
+inline size_t p2p_xr_offset(int world) { return (p2p_ll_offset(world) + (size_t)kP2PSlots * world * kP2PMaxDoubles * 16 + 255) / 256 * 256; }
+inline int64_t p2p_xr_cap(int world, int64_t n_floats) { const int64_t q = 64 * (int64_t)world; return (n_floats + q - 1) / q * q; }
+inline size_t p2p_xr_header_bytes() { return 512 + (size_t)kP2PMaxWorld * kXrScalars * sizeof(double); }
+inline size_t p2p_mailbox_bytes(int world, int64_t xr_floats) {
+  return p2p_xr_offset(world) + p2p_xr_header_bytes() + 2 * (size_t)p2p_xr_cap(world, xr_floats) * sizeof(float);
+}
+// All-reduce (sum) of the gradient buffers of a data-parallel step through peer memory, two-shot: every rank sums ITS slice of all
+// ranks' contributions (reads over NVLink, rank order) and writes the result into every rank's result buffer.
+struct XrArgs {
+  char* peer[kP2PMaxWorld];               // every rank's exchange region (own one included)
+  int world, rank; uint32_t epoch;
+  int64_t cap;                            // floats of one contribution (multiple of 64 * world)
+  const float* dense_grad; int64_t n_dense;   // packed into the front of the contribution; the reduced values are copied back
+  double* scalars[2]; int n_scalars[2];   // fp64 scalars reduced alongside (in place)
+  unsigned* counter;                      // device words for the "last CTA" hand-off (3 words)
+  uint32_t* err;
+};
+inline float* xr_xbuf(char* region) { return reinterpret_cast<float*>(region + p2p_xr_header_bytes()); }
+void launch_xr_allreduce(const XrArgs& a, float* dense_grad_out, cudaStream_t st);
 
 // ---- kernels_shard.cu (row-sharded tables)
 void launch_shard_route(const SparseTable& req, int64_t n, int world, int64_t rps, int* off, int* counts, int slot, int* send_ids,

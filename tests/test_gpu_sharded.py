@@ -121,6 +121,12 @@ def test_driver_under_torchrun_matches_single_process(tmp_path):
                    "--master-port", "29631"], "two")
     print("single:", one, "\ntwo ranks:", two, "\nmax |pred diff|:", float(np.abs(p1 - p2).max()))
     assert set(one) == set(two)
+    # The evidence is the predictions: two fp32 trajectories that differ only in summation order (all-reduce in rank order vs
+    # one batch-wide sum) agree to ~1e-5 after the epoch.  The model is still near chance here (logloss 0.693, scores within a
+    # few 1e-3 of 0.5), so the per-user rank metrics are averages over ~400 users of AUC / MRR / NDCG on 2-5 rows each: ONE pair
+    # of scores 1e-5 apart that flips moves such an average by up to 1 / 400.  Global metrics get the tight bound, the per-user
+    # ones room for a handful of flips.
+    assert p1.shape == p2.shape and np.abs(p1 - p2).max() <= 5e-5
     for k in one:
-        assert abs(one[k] - two[k]) <= 3e-3, (k, one[k], two[k])
-    assert p1.shape == p2.shape and np.abs(p1 - p2).max() <= 5e-3
+        tol = 3e-3 if k in ("auc", "logloss") else 1.5e-2
+        assert abs(one[k] - two[k]) <= tol, (k, one[k], two[k])
