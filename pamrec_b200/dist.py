@@ -83,3 +83,43 @@ def exchange_plan(ids, world, rps):
     owners = ukeys // rps
     per_owner = [(ukeys[owners == o] - o * rps).astype(np.int32) for o in range(world)]
     return per_owner, inverse.astype(np.int32)
+
+
+# ---------------------------------------------------------------------------------------------- replicated tables
+REPLICATE_BYTES = 64 * 2 ** 20     # tables="auto" on several GPUs: replicate while the four tables together stay this small
+
+
+def choose_tables(tables, world, n_users, n_items, n_cates, limit_bytes=REPLICATE_BYTES):
+    """Table placement of an engine (Engine.__init__): "local" on one GPU; on several, "replicated" (every rank holds whole
+    tables, the merged row gradients ride the dense all-reduce) while item + category + 2 user tables fit `limit_bytes`, else
+    "sharded" (row r on rank r % world, rows / row gradients exchanged)."""
+    if tables in (None, "auto"):
+        table_bytes = 4 * (int(n_items) * 16 + int(n_cates) * 4 + 2 * int(n_users) * 20)
+        tables = "local" if world == 1 else ("replicated" if table_bytes <= limit_bytes else "sharded")
+    if tables == "replicated" and world == 1:
+        tables = "local"
+    if tables not in ("local", "replicated", "sharded"):
+        raise ValueError(f"unknown table placement {tables!r}")
+    if world > 1 and tables == "local":
+        raise ValueError("world_size > 1 needs tables='replicated' or 'sharded'")
+    return tables
+
+
+def replicated_contribution(ids, grads, vocab):
+    """numpy mirror of what the run walk leaves in a rank's exchange buffer for one replicated table (kernels_sparse2.cu, mode
+    SP2_DENSE): the rank's lookups merged into a DENSE [vocab, width] gradient table plus one touch mark per looked-up row."""
+    ids = np.asarray(ids).reshape(-1)
+    g = np.zeros((vocab, grads.shape[-1]), np.float64)
+    np.add.at(g, ids, np.asarray(grads, np.float64).reshape(ids.size, -1))
+    touch = np.zeros(vocab, np.float64)
+    touch[np.unique(ids)] = 1.0
+    return g, touch
+
+
+def two_shot_slices(n, world):
+    """[lo, hi) of the slice of an n-element contribution that rank r sums in the peer-memory all-reduce (kernels_p2p.cu:k_xr_*);
+    n is padded to a multiple of 64 * world so that every slice is a whole number of 16-byte vectors."""
+    q = 64 * world
+    cap = (n + q - 1) // q * q
+    step = cap // world
+    return cap, [(r * step, (r + 1) * step) for r in range(world)]

@@ -30,10 +30,6 @@ DEFAULT_HP = dict(learning_rate=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8, embe
                   max_grad_norm=2.0, is_clip_norm=1, fuzhu_weight=0.5, discrepancy_loss_weight=0.1,
                   loss="cross_entropy_loss", softmax_group=1)      # hparams.loss / train_num_ngs + 1 (base_model.py:195-242)
 
-# tables="auto" on several GPUs: replicate the tables when they are this small (the all-reduce of their gradient tables costs
-# less than the id / row / gradient exchange of the sharded layout; 64 MiB of tables = 16 MiB of item gradients per step)
-REPLICATE_BYTES = 64 * 2 ** 20
-
 BATCH_FIELDS = (  # name, dtype, per-row shape suffix, needed for scoring
     ("item_history", np.int32, True), ("item_cate_history", np.int32, True), ("item_loop_times_history", np.float32, True),
     ("mask", np.int32, True), ("users", np.int32, False), ("items", np.int32, False), ("cates", np.int32, False),
@@ -97,16 +93,11 @@ class Engine:
         GPU; on several, replicated while the four tables together stay below REPLICATE_BYTES (PAMREC_REPLICATE_MB), else sharded."""
         self.lib = L.load()
         self.world, self.rank = int(world_size), int(rank)
-        if tables in (None, "auto"):
-            table_bytes = 4 * (int(n_items) * 16 + int(n_cates) * 4 + 2 * int(n_users) * 20)
-            limit = float(os.environ.get("PAMREC_REPLICATE_MB", REPLICATE_BYTES / 2 ** 20)) * 2 ** 20
-            tables = "local" if self.world == 1 else ("replicated" if table_bytes <= limit else "sharded")
-        if tables == "replicated" and self.world == 1:
-            tables = "local"
-        if tables not in ("local", "replicated", "sharded"):
-            raise PamrecError(f"unknown table placement {tables!r}")
-        if self.world > 1 and tables == "local":
-            raise PamrecError("world_size > 1 needs tables='replicated' or 'sharded'")
+        try:
+            limit = float(os.environ.get("PAMREC_REPLICATE_MB", D.REPLICATE_BYTES / 2 ** 20)) * 2 ** 20
+            tables = D.choose_tables(tables, self.world, n_users, n_items, n_cates, limit)
+        except ValueError as e:
+            raise PamrecError(str(e))
         self.tables = tables
         h = dict(DEFAULT_HP)
         if hp:

@@ -69,6 +69,28 @@ def test_exchange_plan_properties():
         assert (np.diff(rows) > 0).all() and (rows < rps).all()  # sorted, in range
 
 
+def test_table_placement_rule():
+    assert D.choose_tables(None, 1, 50000, 30000, 50) == "local"
+    assert D.choose_tables("auto", 8, 50000, 30000, 50) == "replicated"            # configs[1]: 10 MB of tables
+    assert D.choose_tables("auto", 8, 50000, 10_000_000, 100_000) == "sharded"     # configs[2]: 650 MB
+    assert D.choose_tables("replicated", 1, 10, 10, 10) == "local"
+    assert D.choose_tables("sharded", 1, 10, 10, 10) == "sharded"                  # the exchange path also runs on one GPU
+    with pytest.raises(ValueError):
+        D.choose_tables("local", 2, 10, 10, 10)
+    with pytest.raises(ValueError):
+        D.choose_tables("mirrored", 2, 10, 10, 10)
+
+
+def test_two_shot_slices_cover_the_padded_contribution():
+    for n in (1, 63, 64, 1000, 252_197 + 560_250):
+        for world in (2, 3, 8):
+            cap, sl = D.two_shot_slices(n, world)
+            assert cap >= n and cap % (64 * world) == 0 and cap - n < 64 * world
+            assert sl[0][0] == 0 and sl[-1][1] == cap
+            assert all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+            assert all((hi - lo) % 4 == 0 for lo, hi in sl)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -125,7 +147,27 @@ def _worker(rank, world, port, q):
         dist.all_gather_object(box5, z.numpy())
         zz = np.concatenate(box5)
         ok_bn = np.allclose(s[0].numpy() / s[2].numpy(), zz.mean(0)) and np.allclose(s[1].numpy() / s[2].numpy(), (zz * zz).mean(0))
-        q.put((rank, bool(ok_lookup), bool(ok_grad), bool(ok_bn)))
+        # replicated tables: every rank's dense contribution (+ touch marks) summed by the two-shot scheme of k_xr_* - rank r
+        # sums slice r of all contributions in rank order, everybody receives every slice - equals the whole job's gradient,
+        # and the rows touched by ANY rank are the unique ids of the global batch (the L2 rows of tf.unique)
+        contrib, touch = D.replicated_contribution(ids, g, vocab)
+        flat = np.concatenate([contrib.reshape(-1), touch])
+        cap, slices = D.two_shot_slices(flat.size, world)
+        xbuf = np.zeros(cap)
+        xbuf[:flat.size] = flat
+        box6 = [None] * world
+        dist.all_gather_object(box6, xbuf)                                  # "peer memory": every rank can read every contribution
+        lo, hi = slices[rank]
+        mine_sum = np.zeros(hi - lo)
+        for src in range(world):
+            mine_sum += box6[src][lo:hi]
+        box7 = [None] * world
+        dist.all_gather_object(box7, mine_sum)                              # every rank stores its slice into every result buffer
+        rbuf = np.concatenate(box7)
+        ok_rep = np.allclose(rbuf[:contrib.size].reshape(vocab, width), dense, rtol=1e-12, atol=1e-12)
+        all_ids = np.unique(np.concatenate([i for i, _ in box4]))
+        ok_rep = ok_rep and np.array_equal(np.nonzero(rbuf[contrib.size:flat.size] > 0)[0], all_ids)
+        q.put((rank, bool(ok_lookup), bool(ok_grad), bool(ok_bn), bool(ok_rep)))
     finally:
         dist.destroy_process_group()
 
@@ -142,7 +184,8 @@ def test_two_rank_exchange_over_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(r[0] for r in res) == [0, 1]
-    for rank, ok_lookup, ok_grad, ok_bn in res:
+    for rank, ok_lookup, ok_grad, ok_bn, ok_rep in res:
+        assert ok_rep, f"rank {rank}: replicated-table contributions summed by the two-shot scheme differ from the job's gradient"
         assert ok_lookup, f"rank {rank}: sharded lookup differs from the full-table lookup"
         assert ok_grad, f"rank {rank}: merged row gradients differ from the dense gradient"
         assert ok_bn, f"rank {rank}: all-reduced statistics differ"
