@@ -593,27 +593,49 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_fwd(const __grid_constant__ He
     cnt = block_sum_d(cnt, shd);
     if (tid == 0) h.dp_scalars[0] = cnt;
   }
-  // ---- F1: z1 = H W0 + b0 over the CTA's tokens; thread (slot, j) owns column j for the tokens slot, slot + 25, ...
+  // ---- F1: z1 = H W0 + b0 over the CTA's tokens in chunks of 125: the chunk's rows (20 KB, contiguous) go through shared memory,
+  //          the next chunk's rows are already in flight while thread (slot, j) computes column j of tokens slot, slot + 25, ...
   {
+    constexpr int kChunk = 5 * kSlots;
     const int slot = tid / 20, j = tid % 20;
     double s = 0.0, q = 0.0;
-    if (slot < kSlots) {
-      float wc[kD];
+    float wc[kD];
 #pragma unroll
-      for (int k = 0; k < kD; ++k) wc[k] = w0s[k * 20 + j];
-      const float b = w0s[800 + j];
-      for (int64_t tok = tok0 + slot; tok < tok1; tok += kSlots) {
-        const float* hr = h.H + tok * kD;
-        float z = b;
+    for (int k = 0; k < kD; ++k) wc[k] = w0s[k * 20 + (slot < kSlots ? j : 0)];
+    const float b = w0s[800 + j];
+    float4 pre[3];
+    auto load_chunk = [&](int64_t c0) {
+      const int nq = (int)min((int64_t)kChunk, tok1 - c0) * 10;
 #pragma unroll
-        for (int i = 0; i < 10; ++i) {
-          const float4 x = ld4(hr + 4 * i);
-          z = fmaf(x.x, wc[4 * i], z); z = fmaf(x.y, wc[4 * i + 1], z); z = fmaf(x.z, wc[4 * i + 2], z); z = fmaf(x.w, wc[4 * i + 3], z);
+      for (int u = 0; u < 3; ++u) { const int i = tid + u * kT2; pre[u] = i < nq ? ld4(h.H + c0 * kD + 4 * i) : f4_zero(); }
+    };
+    if (tok0 < tok1) load_chunk(tok0);
+    for (int64_t c0 = tok0; c0 < tok1; c0 += kChunk) {
+      const int nt = (int)min((int64_t)kChunk, tok1 - c0);
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < 3; ++u) { const int i = tid + u * kT2; if (i < kChunk * 10) st4(xs + 4 * i, pre[u]); }
+      __syncthreads();
+      if (c0 + kChunk < tok1) load_chunk(c0 + kChunk);
+      if (slot < kSlots) {
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          const int tl = slot + u * kSlots;
+          if (tl < nt) {
+            const float* hr = xs + tl * kD;
+            float z = b;
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+              const float4 x = ld4(hr + 4 * i);
+              z = fmaf(x.x, wc[4 * i], z); z = fmaf(x.y, wc[4 * i + 1], z); z = fmaf(x.z, wc[4 * i + 2], z); z = fmaf(x.w, wc[4 * i + 3], z);
+            }
+            h.z1[(c0 + tl) * 20 + j] = z;
+            s += (double)z; q += (double)z * (double)z;
+          }
         }
-        h.z1[tok * 20 + j] = z;
-        s += (double)z; q += (double)z * (double)z;
       }
     }
+    __syncthreads();
     if (train) {
       // the 25 slot-threads of a column: reduce through shared memory (xs is free here)
       double* red = reinterpret_cast<double*>(xs);            // [2][25][20]
@@ -1118,67 +1140,92 @@ __global__ void __launch_bounds__(kT2, 1) k_head2_bwd(const __grid_constant__ He
     }
     grid_barrier(h, d, epoch, leader_of(BN_S0, -1, 1, 1), n_barrier, wbuf, no_prefetch());
   }
-  // ---- K7: dz1 -> dH = a_t d_new_long + dz1 W0^T  (the gradient of the encoder output, g_a);  dW0 = H^T dz1, db0
+  // ---- K7: dz1 -> dH = a_t d_new_long + dz1 W0^T  (the gradient of the encoder output, g_a);  dW0 = H^T dz1, db0.
+  //          Batches of 50 tokens; everything a batch reads from global memory is requested one batch ahead:
+  //          thread (token, k quad), tid < 500: its float4 of H, the token's pooling weight and its float4 of d_new_long;
+  //          thread (slot, j), tid < 500: d_z2, z2, z1 of tokens slot and slot + 25.
   {
+    constexpr int kTB = 2 * kSlots;
     const BnB k1 = bn_b(h.bn[BN_S1], 0, d.cntN);
     const int slot = tid / 20, j = tid % 20;
+    const int sl_h = tid / 10, kq = tid % 10;
     if (tid < 20) {
       const BnB k = bn_b(h.bn[BN_S0], tid, d.cntN);
       c0[6 * tid] = k.mean; c0[6 * tid + 1] = k.inv; c0[6 * tid + 2] = k.ga; c0[6 * tid + 3] = k.be; c0[6 * tid + 4] = k.s1n; c0[6 * tid + 5] = k.s2n;
     }
-    float* Hs = xs;                                           // [25][40] encoder outputs of the batch
-    float* dzs = xs + 1024;                                   // [25][20] dz1 of the batch
-    float gw[4] = {0.f, 0.f, 0.f, 0.f};                       // dW0[k][4 jq .. 4 jq + 3] of the thread (warps 8..15)
+    float* Hs = xs;                                           // [50][40] encoder outputs of the batch
+    float* dzs = xs + kTB * kD;                               // [50][20] dz1 of the batch
+    float gw[4] = {0.f, 0.f, 0.f, 0.f};                       // dW0[k][4 jq .. 4 jq + 3] of threads 0..199
     double gb = 0.0;
-    const int wk = (tid - 256) / 5, wjq = (tid - 256) % 5;    // tid in [256, 456): k = wk, j quad = wjq
+    const int wk = tid / 5, wjq = tid % 5;
     __syncthreads();
-    const BnB k0 = slot < kSlots ? BnB{c0[6 * j], c0[6 * j + 1], c0[6 * j + 2], c0[6 * j + 3], c0[6 * j + 4], c0[6 * j + 5]} : BnB{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const float w1j = slot < kSlots ? w1s[j] : 0.f;
-    for (int64_t tb = tok0; tb < tok1; tb += kSlots) {
-      const int nt = (int)min((int64_t)kSlots, tok1 - tb);
-      __syncthreads();
-      if (tid < 250) {                                        // 25 tokens x 160 B, contiguous
-        const int64_t e = tb * kD + 4 * tid;
-        st4(Hs + 4 * tid, tid < nt * 10 ? ld4(h.H + e) : f4_zero());
+    const bool colthr = slot < kSlots;
+    const BnB k0 = colthr ? BnB{c0[6 * j], c0[6 * j + 1], c0[6 * j + 2], c0[6 * j + 3], c0[6 * j + 4], c0[6 * j + 5]} : BnB{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float w1j = colthr ? w1s[j] : 0.f;
+    float4 pH = f4_zero(), pDn = f4_zero();
+    float pA = 0.f, pdA[2] = {0.f, 0.f}, pz2[2] = {0.f, 0.f}, pz1[2] = {0.f, 0.f};
+    auto prefetch = [&](int64_t tb) {
+      const int nt = (int)min((int64_t)kTB, tok1 - tb);
+      if (tid < kTB * 10) {
+        const bool ok = sl_h < nt;
+        const int64_t tok = tb + sl_h;
+        pH = ok ? ld4(h.H + tok * kD + 4 * kq) : f4_zero();
+        pA = ok ? h.aw[tok] : 0.f;
+        pDn = ok ? ld4(h.d_new_long + (tok / T) * kD + 4 * kq) : f4_zero();
       }
-      if (slot < kSlots) {
-        float dz1 = 0.f;
-        if (slot < nt) {
-          const int64_t tok = tb + slot;
-          const float dz2 = bn_dz(h.d_z2[tok], h.z2[tok], k1);
-          dz1 = bn_dz(dz2 * w1j, h.z1[tok * 20 + j], k0);
-          gb += (double)dz1;
-        }
-        dzs[slot * 20 + j] = dz1;
-      }
-      __syncthreads();
-      if (tid < 250) {
-        // dH[slot][4 kq .. 4 kq + 3]
-        const int sl = tid / 10, kq = tid % 10;
-        if (sl < nt) {
-          const int64_t tok = tb + sl;
-          const int b = (int)(tok / T);
-          const float a = h.aw[tok];
-          const float4 dn = ld4(h.d_new_long + (int64_t)b * kD + 4 * kq);
-          float4 o = make_float4(a * dn.x, a * dn.y, a * dn.z, a * dn.w);
+      if (colthr) {
 #pragma unroll
-          for (int jj = 0; jj < 20; ++jj) f4_fma(o, dzs[sl * 20 + jj], ld4(w0t + jj * 40 + 4 * kq));
-          st4(h.g_a + tok * kD + 4 * kq, o);
+        for (int u = 0; u < 2; ++u) {
+          const int sl = slot + u * kSlots;
+          const int64_t tok = tb + sl;
+          pdA[u] = sl < nt ? h.d_z2[tok] : 0.f; pz2[u] = sl < nt ? h.z2[tok] : 0.f; pz1[u] = sl < nt ? h.z1[tok * 20 + j] : 0.f;
         }
-      } else if (tid >= 256 && tid < 456) {
+      }
+    };
+    if (tok0 < tok1) prefetch(tok0);
+    for (int64_t tb = tok0; tb < tok1; tb += kTB) {
+      const int nt = (int)min((int64_t)kTB, tok1 - tb);
+      __syncthreads();                                        // the previous batch has been consumed
+      float4 dn = pDn;
+      const float a = pA;
+      if (tid < kTB * 10) st4(Hs + 4 * tid, pH);
+      if (colthr) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int sl = slot + u * kSlots;
+          float dz1 = 0.f;
+          if (sl < nt) {
+            const float dz2 = bn_dz(pdA[u], pz2[u], k1);
+            dz1 = bn_dz(dz2 * w1j, pz1[u], k0);
+            gb += (double)dz1;
+          }
+          dzs[sl * 20 + j] = dz1;
+        }
+      }
+      __syncthreads();
+      if (tb + kTB < tok1) prefetch(tb + kTB);
+      if (tid < kTB * 10 && sl_h < nt) {
+        // dH[token][4 kq .. 4 kq + 3]
+        float4 o = make_float4(a * dn.x, a * dn.y, a * dn.z, a * dn.w);
+#pragma unroll
+        for (int jj = 0; jj < 20; ++jj) f4_fma(o, dzs[sl_h * 20 + jj], ld4(w0t + jj * 40 + 4 * kq));
+        st4(h.g_a + (tb + sl_h) * kD + 4 * kq, o);
+      }
+      if (tid < 200) {
         // dW0[k][4 jq ..] += sum over the batch's tokens
         float4 acc = make_float4(gw[0], gw[1], gw[2], gw[3]);
+#pragma unroll 5
         for (int sl = 0; sl < nt; ++sl) f4_fma(acc, Hs[sl * 40 + wk], ld4(dzs + sl * 20 + 4 * wjq));
         gw[0] = acc.x; gw[1] = acc.y; gw[2] = acc.z; gw[3] = acc.w;
       }
     }
-    if (tid >= 256 && tid < 456) {
+    if (tid < 200) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) if (gw[i] != 0.f) atomicAdd(h.ds_w0 + wk * 20 + 4 * wjq + i, gw[i]);
     }
     double* red = reinterpret_cast<double*>(aux + 2048);      // [25][20]
     __syncthreads();
-    if (slot < kSlots) red[slot * 20 + j] = gb;
+    if (colthr) red[slot * 20 + j] = gb;
     __syncthreads();
     if (tid < 20) {
       double t = 0.0;

@@ -360,7 +360,9 @@ void launch_slot_reset(const SparseTable& t, int64_t n_keys, cudaStream_t st) { 
 }
 
 // ------------------------------------------------------------------------------------------
-// dense variables: one CTA per TF variable computes |g + l2 p|^2 and the L2 loss term
+// dense variables: |g + l2 p|^2 and the L2 loss term per TF variable; a variable is cut into kNormSplit pieces (the largest -
+// the [10, 1600] time-aware tables - would otherwise keep one CTA busy for 60 dependent iterations), partial sums by atomics
+constexpr int kNormSplit = 8;
 __global__ void __launch_bounds__(256)
 k_dense_norm(const float* __restrict__ P, const float* __restrict__ G, const int* __restrict__ seg_tab, float layer_l2,
              double* __restrict__ seg_normsq, const double* __restrict__ pos_normsq, double* __restrict__ reg_acc) {
@@ -369,8 +371,12 @@ k_dense_norm(const float* __restrict__ P, const float* __restrict__ G, const int
   const int64_t off = seg_tab[4 * s];
   const int n = seg_tab[4 * s + 1], flags = seg_tab[4 * s + 2];
   const float l2 = (flags & PAMREC_SEG_L2) ? layer_l2 : 0.f;
+  const int per = ((n + kNormSplit - 1) / kNormSplit + 3) & ~3;
+  const int i0 = blockIdx.y * per, i1 = min(n, i0 + per);
+  if (i0 >= n && blockIdx.y > 0) return;
   double a = 0.0, b = 0.0;
-  for (int i = threadIdx.x; i < n; i += 256) {
+#pragma unroll 4
+  for (int i = i0 + threadIdx.x; i < i1; i += 256) {
     float p = P[off + i];
     float g = G[off + i] + l2 * p;
     a += (double)g * (double)g;
@@ -382,13 +388,15 @@ k_dense_norm(const float* __restrict__ P, const float* __restrict__ G, const int
   if (threadIdx.x == 0) {
     double ta = 0.0, tb = 0.0;
     for (int k = 0; k < 8; ++k) { ta += sh[0][k]; tb += sh[1][k]; }
-    seg_normsq[s] = (flags & PAMREC_SEG_POS) ? *pos_normsq : ta;
-    if (l2 != 0.f) atomicAdd(reg_acc, 0.5 * (double)l2 * tb);
+    if (flags & PAMREC_SEG_POS) { if (blockIdx.y == 0) seg_normsq[s] = *pos_normsq; }      // sparse-style norm of the position table
+    else if (ta != 0.0) atomicAdd(seg_normsq + s, ta);
+    if (l2 != 0.f && tb != 0.0) atomicAdd(reg_acc, 0.5 * (double)l2 * tb);
   }
 }
 void launch_dense_norm(const float* P, const float* G, const int* seg_tab, int n_seg, float layer_l2, double* seg_normsq,
                        const double* pos_normsq, double* reg_acc, cudaStream_t st) { PAMREC_PROF("dense_norm", 1, st);
-  k_dense_norm<<<n_seg, 256, 0, st>>>(P, G, seg_tab, layer_l2, seg_normsq, pos_normsq, reg_acc);
+  cudaMemsetAsync(seg_normsq, 0, (size_t)n_seg * sizeof(double), st);
+  k_dense_norm<<<dim3(n_seg, kNormSplit), 256, 0, st>>>(P, G, seg_tab, layer_l2, seg_normsq, pos_normsq, reg_acc);
 }
 
 __global__ void __launch_bounds__(256)
