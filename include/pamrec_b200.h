@@ -54,6 +54,15 @@ enum { PAMREC_TABLES_LOCAL = 0,     /* whole tables on this GPU, direct gather (
                                        gradients and the looked-up-row marks are all-reduced with the dense gradients
                                        and every rank applies the same update (world_size 1: same as LOCAL)     */
 
+/* model family (all share the feed dict, the tables, BN / clip / Adam semantics and the C ABI below).  The sibling multi-task
+ * baselines of the reference run on one GPU with whole tables (PAMREC_TABLES_LOCAL):
+ *   PAMREC_MODEL_MMOE         MMoEModel_original   models/sequential/mmoe.py:24-82, 183-337
+ *   PAMREC_MODEL_PLE          PLEModel             models/sequential/ple.py:24-60
+ *   PAMREC_MODEL_SHAREBOTTOM  ShareBottomModel     models/sequential/sharebottom.py:160-203
+ * DIN-style attention pooling (`_attention_fcn`) of the satisfied-only and of the full history against the target item, a
+ * mixing layer (MMoE / PLE / none) and two towers; loss = data + regular + 0.5 * auxiliary. */
+enum { PAMREC_MODEL_PAMREC = 0, PAMREC_MODEL_MMOE = 1, PAMREC_MODEL_PLE = 2, PAMREC_MODEL_SHAREBOTTOM = 3 };
+
 /* hparams.loss */
 enum { PAMREC_LOSS_XENT = 0,        /* "cross_entropy_loss" (config/mmoe.yaml)                                  */
        PAMREC_LOSS_SOFTMAX = 1 };   /* "softmax" over groups of train_num_ngs + 1 rows (base_model.py:222-242)  */
@@ -83,6 +92,7 @@ typedef struct PamrecConfig {
    * world_size > 1 softmax_group must divide 5 (ranks hold whole listwise groups of 5).                                   */
   int32_t loss_kind;
   int32_t softmax_group;             /* used by PAMREC_LOSS_SOFTMAX only; 0 is read as 1                */
+  int32_t model_kind;                /* PAMREC_MODEL_*                                                  */
 } PamrecConfig;
 
 /* One batch, device pointers (layouts of io/sequential_iterator.py:1111-1135). */
@@ -100,6 +110,11 @@ typedef struct PamrecBatch {
   const float* plays;                 /* [B]  bucket index as float (train only)               */
   int32_t global_batch;               /* rows of the whole global batch over all ranks; 0 = batch * world_size.
                                          batch may be 0 on a rank that only takes part in the collectives   */
+  /* satisfied-only copy of the history, compacted to the left (io/sequential_iterator.py:1069-1103): read by the sibling
+   * models only (PAMREC_MODEL_MMOE / _PLE / _SHAREBOTTOM, mmoe.py:199-201); may be NULL for PAMREC_MODEL_PAMREC */
+  const int32_t* satisfied_item_history; /* [B,T]                                              */
+  const int32_t* satisfied_cate_history; /* [B,T]                                              */
+  const int32_t* satisfied_mask;         /* [B,T] 1 = real position                            */
 } PamrecBatch;
 
 /* Caller-owned device memory handed to the library once. */
@@ -151,7 +166,9 @@ int pamrec_gather_fwd(PamrecHandle h, const PamrecBatch* b, float* x0_out, void*
 int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pred_out, void* stream);
 /* losses + backward into dense_grad / workspace (requires pamrec_forward(training=1) on the same batch) */
 int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream);
-/* per-tensor clip + Adam on dense and sparse variables; `step` is 1-based (beta powers) */
+/* per-tensor clip + Adam on dense and sparse variables; `step` is 1-based (beta powers).  step = 0 (one GPU, whole tables):
+ * use and advance the step counter the library keeps on the device (every call with step >= 1 sets it) - the form to capture
+ * in a CUDA graph, where a host-computed step size would be frozen into the captured launch arguments */
 int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, void* stream);
 /* forward + backward + apply; losses_out (device, 5 floats): loss, data, regular, auxiliary, order (pamrec.py:444-448) */
 int pamrec_train_step(PamrecHandle h, const PamrecBatch* b, int64_t step, float* losses_out, void* stream);

@@ -108,25 +108,28 @@ def add_satisfied_fields(batch, seed=0):
     return out
 
 
-def _attention_fcn(ctx, query, hist, mask, scope):
+def _attention_fcn(ctx, query, hist, mask, scope, tag=None):
     """MM:299-337.  query [B, 20], hist [B, T, 20], mask [B, T] -> hist * softmax weights [B, T, 20]."""
     B, T, _ = hist.shape
     att_inputs = hist @ ctx.p[scope + "/attention_mat"]                                    # tensordot over the feature axis
     q = query[:, None, :].expand(B, T, query.shape[1])
     feats = torch.cat([att_inputs, q, att_inputs - q, att_inputs * q], -1)                # [B, T, 80]
-    score = O._mlp(ctx, feats, scope + "/att_fcn", ATT_SIZES, out=True).squeeze(-1)        # BN statistics over all B*T rows
+    score = O._mlp(ctx, feats, scope + "/att_fcn", ATT_SIZES, out=True, tag=tag).squeeze(-1)   # BN statistics over all B*T rows
     pad = torch.full_like(score, float(-(2 ** 32) + 1))
     w = torch.softmax(torch.where(mask == 1, score, pad), dim=-1)                          # an all-padding row: uniform weights
+    if tag:
+        ctx.t[tag + ".feat"], ctx.t[tag + ".score"], ctx.t[tag + ".w"] = feats, score, w
     return hist * w[..., None]
 
 
-def forward(model, p, bn_state, batch, training, dtype=torch.float64, rows=None, **sizes):
-    """-> ctx with ctx.t["logits"] [B, 2] = (logit of `labels` (satisfied), valid_logit of `labels_play`) and ctx.t["pred"]."""
+def forward(model, p, bn_state, batch, training, dtype=torch.float64, rows=None, relu_masks=None, **sizes):
+    """-> ctx with ctx.t["logits"] [B, 2] = (logit of `labels` (satisfied), valid_logit of `labels_play`) and ctx.t["pred"].
+    relu_masks: activation pattern to differentiate on, keyed by BN scope (pamrec_oracle._act)."""
     expert_num = sizes.get("expert_num", 5)
     share_n, indep_n = sizes.get("share_expert_num", 3), sizes.get("independent_expert_num", 2)
     expert_sizes, gate_sizes = sizes.get("expert_sizes", (100, 64)), sizes.get("gate_sizes", (64, 5))
     tower_sizes = sizes.get("tower_sizes", (100, 64))
-    ctx = O._Ctx(p, bn_state, training, dtype)
+    ctx = O._Ctx(p, bn_state, training, dtype, relu_masks=relu_masks)
     emb = "sequential/embedding/"
     idx = lambda k: torch.as_tensor(np.asarray(batch[k])).long()
     item_w, cate_w = p[emb + "item_embedding"], p[emb + "cate_embedding"]
@@ -137,23 +140,25 @@ def forward(model, p, bn_state, batch, training, dtype=torch.float64, rows=None,
     target = torch.cat([rows["tgt_item"], rows["tgt_cate"]], -1)                            # SBM:669-671
     long_in = torch.cat([rows["sat_item"], rows["sat_cate"]], -1)                           # MM:199-201
     short_in = torch.cat([rows["hist_item"], rows["hist_cate"]], -1)                        # MM:208-210
-    long = _attention_fcn(ctx, target, long_in, idx("satisfied_mask"), "sequential/clsr/long_term/attention_fcn").sum(1)
-    short = _attention_fcn(ctx, target, short_in, idx("mask"), "sequential/clsr/short_term/attention_fcn").sum(1)
+    long = _attention_fcn(ctx, target, long_in, idx("satisfied_mask"), "sequential/clsr/long_term/attention_fcn", tag="att0").sum(1)
+    short = _attention_fcn(ctx, target, short_in, idx("mask"), "sequential/clsr/short_term/attention_fcn", tag="att1").sum(1)
     x = torch.cat([long, short, target], -1)                                                # [B, 60]
     ctx.t["x"] = x
 
     # a gate is a BN + ReLU MLP like any other (no softmax, MM:43-46): [B, E] x experts [B, E, 64] -> [B, 64]
     if model == "mmoe":
         scopes = [f"sequential/clsr/expert_{j}" for j in range(expert_num)]
-        experts = torch.stack([O._mlp(ctx, x, s, expert_sizes) for s in scopes], 1)
-        main = (O._mlp(ctx, x, "sequential/clsr/gate_main", gate_sizes)[:, None, :] @ experts).squeeze(1)
-        sub = (O._mlp(ctx, x, "sequential/clsr/gate_sub", gate_sizes)[:, None, :] @ experts).squeeze(1)
+        experts = torch.stack([O._mlp(ctx, x, s, expert_sizes, tag=f"expert{j}") for j, s in enumerate(scopes)], 1)
+        main = (O._mlp(ctx, x, "sequential/clsr/gate_main", gate_sizes, tag="gate0")[:, None, :] @ experts).squeeze(1)
+        sub = (O._mlp(ctx, x, "sequential/clsr/gate_sub", gate_sizes, tag="gate1")[:, None, :] @ experts).squeeze(1)
     elif model == "ple":
-        share = [O._mlp(ctx, x, f"sequential/clsr/share_expert_{j}", expert_sizes) for j in range(share_n)]
-        own = {t: [O._mlp(ctx, x, f"sequential/clsr/{t}_expert_{j}", expert_sizes) for j in range(indep_n)] for t in ("main", "sub")}
+        # tags number the experts in the device layout's order: shared 0-2, main 3-4, sub 5-6
+        share = [O._mlp(ctx, x, f"sequential/clsr/share_expert_{j}", expert_sizes, tag=f"expert{j}") for j in range(share_n)]
+        own = {t: [O._mlp(ctx, x, f"sequential/clsr/{t}_expert_{j}", expert_sizes, tag=f"expert{share_n + k * indep_n + j}")
+                   for j in range(indep_n)] for k, t in enumerate(("main", "sub"))}
         outs = {}
-        for t in ("main", "sub"):                                                          # PLE:51-58: shared experts first
-            gate = O._mlp(ctx, x, f"sequential/clsr/gate_{t}", gate_sizes)
+        for k, t in enumerate(("main", "sub")):                                            # PLE:51-58: shared experts first
+            gate = O._mlp(ctx, x, f"sequential/clsr/gate_{t}", gate_sizes, tag=f"gate{k}")
             outs[t] = (gate[:, None, :] @ torch.stack(share + own[t], 1)).squeeze(1)
         main, sub = outs["main"], outs["sub"]
     else:
@@ -162,8 +167,10 @@ def forward(model, p, bn_state, batch, training, dtype=torch.float64, rows=None,
         model_output = valid_output = x                                                    # SB:200-201
     else:
         model_output, valid_output = torch.cat([main, target], -1), torch.cat([sub, target], -1)
-    valid_logit = O._mlp(ctx, valid_output, "sequential/valid_logit_fcn", tower_sizes, out=True)    # MM:175
-    logit = O._mlp(ctx, model_output, "sequential/logit_fcn", tower_sizes, out=True)               # MM:177
+    valid_logit = O._mlp(ctx, valid_output, "sequential/valid_logit_fcn", tower_sizes, out=True, tag="tower1")    # MM:175
+    logit = O._mlp(ctx, model_output, "sequential/logit_fcn", tower_sizes, out=True, tag="tower0")               # MM:177
+    if main is not None:
+        ctx.t["main"], ctx.t["sub"] = main, sub
     ctx.t["logits"] = torch.cat([logit, valid_logit], -1)
     ctx.t["pred"] = torch.sigmoid(logit)                                                           # BM:93-113
     return ctx
@@ -352,10 +359,10 @@ class SiblingOracleModel(O.OracleModel):
             g["pos"] = (emb + "position_embedding", torch.arange(T)[None, :].expand(B, T))
         return g, {k: p[name][i] for k, (name, i) in g.items()}
 
-    def _forward(self, p, batch, training, rows=None):
+    def _forward(self, p, batch, training, rows=None, relu_masks=None):
         if self.model == "sasrec":
             return sasrec_forward(p, self.bn_state, batch, training, self.dtype, rows=rows, **self.sizes)
-        return forward(self.model, p, self.bn_state, batch, training, self.dtype, rows=rows, **self.sizes)
+        return forward(self.model, p, self.bn_state, batch, training, self.dtype, rows=rows, relu_masks=relu_masks, **self.sizes)
 
     def _losses(self, ctx, batch, rows):
         dtype, hp = self.dtype, self.hp

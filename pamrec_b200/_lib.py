@@ -12,6 +12,7 @@ SEG_L2, SEG_POS, SEG_DEAD = 1, 2, 4
 ADAM_DENSE_EXACT, ADAM_LAZY = 0, 1
 TABLES_LOCAL, TABLES_SHARDED, TABLES_REPLICATED = 0, 1, 2
 LOSS_XENT, LOSS_SOFTMAX = 0, 1
+MODEL_PAMREC, MODEL_MMOE, MODEL_PLE, MODEL_SHAREBOTTOM = 0, 1, 2, 3
 COMM_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 GROUP = 5
@@ -27,7 +28,7 @@ class PamrecConfig(C.Structure):
         ("embed_l2", C.c_float), ("layer_l2", C.c_float), ("max_grad_norm", C.c_float), ("is_clip_norm", C.c_int32),
         ("fuzhu_weight", C.c_float), ("order_weight", C.c_float), ("sparse_adam_mode", C.c_int32),
         ("world_size", C.c_int32), ("rank", C.c_int32), ("table_mode", C.c_int32),
-        ("loss_kind", C.c_int32), ("softmax_group", C.c_int32),
+        ("loss_kind", C.c_int32), ("softmax_group", C.c_int32), ("model_kind", C.c_int32),
     ]
 
 
@@ -38,6 +39,7 @@ class PamrecBatch(C.Structure):
         ("mask", C.c_void_p), ("users", C.c_void_p), ("items", C.c_void_p), ("cates", C.c_void_p),
         ("labels_satisfied", C.c_void_p), ("labels_play", C.c_void_p), ("plays", C.c_void_p),
         ("global_batch", C.c_int32),
+        ("satisfied_item_history", C.c_void_p), ("satisfied_cate_history", C.c_void_p), ("satisfied_mask", C.c_void_p),
     ]
 
 

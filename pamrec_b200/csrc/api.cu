@@ -36,6 +36,7 @@ struct PamrecHandle_ {
   Xchg xc[3];                   // item, cate, user
   bool xc_users = false;        // the current exchange carried user ids (training)
   bool sharded() const { return cfg.table_mode == PAMREC_TABLES_SHARDED; }
+  bool sibling() const { return cfg.model_kind != PAMREC_MODEL_PAMREC; }
   bool replicated() const { return cfg.table_mode == PAMREC_TABLES_REPLICATED && cfg.world_size > 1; }
   // Internal side stream: work that is off the critical path of a step (the id sort of the sparse plan, the weight-gradient
   // GEMMs of the head) is forked from the caller's stream with events and joined back before anything consumes it.
@@ -171,6 +172,9 @@ int pamrec_create(const PamrecConfig* cfg, PamrecHandle* out) {
     if (cfg->n_cates > big) big = cfg->n_cates;
     if (((big + world - 1) / world) * world >= ((int64_t)1 << 31)) return -7;
   }
+  if (cfg->model_kind < PAMREC_MODEL_PAMREC || cfg->model_kind > PAMREC_MODEL_SHAREBOTTOM) return -9;
+  if (cfg->model_kind != PAMREC_MODEL_PAMREC && (world != 1 || cfg->table_mode != PAMREC_TABLES_LOCAL || cfg->loss_kind != PAMREC_LOSS_XENT))
+    return -9;                                                               // sibling models: one GPU, whole tables, cross entropy
   PamrecHandle h = new PamrecHandle_();
   h->cfg = *cfg;
   h->cfg.world_size = world;
@@ -328,7 +332,7 @@ int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
   size_t have = (size_t)h->L.ws[h->L.ws_index["cub_temp"]].numel;
   if (need > have) return fail(h, "cub temp storage: need %zu have %zu", need, have);
   cudaMemsetAsync(h->buf.workspace, 0, h->L.ws_bytes, st);
-  if (h->sharded()) {
+  if (h->sharded() || h->sibling()) {
     cudaMemsetAsync(h->wi("sp.item.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_items) * 4, st);
     cudaMemsetAsync(h->wi("sp.cate.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_cates) * 4, st);
     cudaMemsetAsync(h->wi("sp.user.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_users) * 4, st);
@@ -340,7 +344,8 @@ int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
     return fail(h, "cudaMallocHost for the exchange counts failed");
   cudaMemcpyAsync(h->wi("seg_id"), h->h_seg_id.data(), h->h_seg_id.size() * 4, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(h->wi("seg_tab"), h->h_seg_tab.data(), h->h_seg_tab.size() * 4, cudaMemcpyHostToDevice, st);
-  if (int rc = build_head(h, st)) return rc;
+  if (h->sibling()) h->head2_grid = 0;                     // sibling models run on the stand-alone kernels (api_sibling.inl)
+  else if (int rc = build_head(h, st)) return rc;
   cudaStreamSynchronize(st);
   h->bound = true;
   return check_cuda(h, "bind");
@@ -352,6 +357,13 @@ static int check_batch(PamrecHandle h, const PamrecBatch* b, bool training) {
   if (!b) return fail(h, "null batch");
   if (b->batch == 0 && (h->sharded() || h->cfg.world_size > 1)) return 0;  // this rank only takes part in the collectives
   if (b->batch < 1 || b->batch > h->cfg.max_batch) return fail(h, "batch %d outside [1, %d]", b->batch, h->cfg.max_batch);
+  if (h->sibling()) {
+    if (!b->satisfied_item_history || !b->satisfied_cate_history || !b->satisfied_mask || !b->item_history || !b->item_cate_history ||
+        !b->mask || !b->items || !b->cates)
+      return fail(h, "null batch field (the sibling models also read satisfied_item_history / satisfied_cate_history / satisfied_mask)");
+    if (training && (!b->users || !b->labels_satisfied || !b->labels_play)) return fail(h, "null label field");
+    return 0;
+  }
   if (training && b->batch % PAMREC_GROUP != 0)
     return fail(h, "training batch %d is not a multiple of %d (pamrec.py:73-75)", b->batch, PAMREC_GROUP);
   if (training && h->cfg.loss_kind == PAMREC_LOSS_SOFTMAX && b->batch % h->cfg.softmax_group != 0)
@@ -390,6 +402,7 @@ static AdamP make_adam(PamrecHandle h, float lr_t) {
   const PamrecConfig& c = h->cfg;
   AdamP a;
   a.lr = lr_t; a.b1 = c.beta1; a.b2 = c.beta2; a.eps = c.epsilon; a.l2 = c.embed_l2; a.clip = c.max_grad_norm; a.is_clip = c.is_clip_norm;
+  a.lr_dev = nullptr;
   return a;
 }
 
@@ -539,6 +552,7 @@ static int embed_forward(PamrecHandle h, const PamrecBatch* b, bool training, fl
 
 int pamrec_gather_fwd(PamrecHandle h, const PamrecBatch* b, float* x0_out, void* stream) {
   if (int rc = check_batch(h, b, false)) return rc;
+  if (h->sibling()) return fail(h, "pamrec_gather_fwd is PAMRec's fused gather; the sibling models gather inside pamrec_forward");
   ProfBind _pb(h);
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = embed_forward(h, b, false, x0_out ? x0_out : h->wf("x0"), st)) return rc;
@@ -556,10 +570,15 @@ static DenseP dense_p(const float* X, int ldx, int M, int groups, int K, int N, 
 static void set_in_bn(DenseP& p, const BnSet& s) { p.in_stat = s.stat; p.in_gamma = s.gamma; p.in_beta = s.beta; }
 static void set_in_bn_dw(DenseDwP& p, const BnSet& s) { p.in_stat = s.stat; p.in_gamma = s.gamma; p.in_beta = s.beta; }
 
+static int sib_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pred_out, cudaStream_t st);
+static int sib_backward(PamrecHandle h, const PamrecBatch* b, cudaStream_t st);
+static int sib_apply(PamrecHandle h, const PamrecBatch* b, int64_t step, cudaStream_t st);
+
 int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pred_out, void* stream) {
   if (int rc = check_batch(h, b, training != 0)) return rc;
   ProfBind _pb(h);
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->sibling()) return sib_forward(h, b, training, pred_out, st);
   const Layout& L = h->L;
   const int B = b->batch, T = h->cfg.max_seq_len, N = B * T;
   const int W = h->cfg.world_size;
@@ -801,6 +820,7 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   if (int rc = check_batch(h, b, true)) return rc;
   ProfBind _pb(h);
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->sibling()) return sib_backward(h, b, st);
   const Layout& L = h->L;
   const int B = b->batch, T = h->cfg.max_seq_len, N = B * T;
   const int W = h->cfg.world_size;
@@ -1023,14 +1043,25 @@ static void peer_allreduce_grads(PamrecHandle h, cudaStream_t st) {
 int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, void* stream) {
   if (int rc = check_batch(h, b, true)) return rc;
   ProfBind _pb(h);
-  if (step < 1) return fail(h, "step must be >= 1");
+  // step >= 1: the caller counts the steps; step == 0: the device counter advances by one ("adam.step", for a step replayed from
+  // a CUDA graph: a host-computed step size would be frozen into the graph).  Whole-table layouts only.
+  if (h->sibling()) return sib_apply(h, b, step, (cudaStream_t)stream);
+  if (step < 0) return fail(h, "step must be >= 1 (or 0: advance the device step counter)");
+  if (step == 0 && (h->sharded() || h->cfg.world_size > 1)) return fail(h, "the device step counter (step = 0) needs one GPU with whole tables");
   cudaStream_t st = (cudaStream_t)stream;
   const Layout& L = h->L;
   const PamrecConfig& c = h->cfg;
   const int B = b->batch, T = c.max_seq_len;
   const int64_t N = (int64_t)B * T;
   const double b1 = c.beta1, b2 = c.beta2;
-  const float lr_t = (float)((double)c.learning_rate * std::sqrt(1.0 - std::pow(b2, (double)step)) / (1.0 - std::pow(b1, (double)step)));
+  const double tstep = step > 0 ? (double)step : 1.0;
+  const float lr_t = (float)((double)c.learning_rate * std::sqrt(1.0 - std::pow(b2, tstep)) / (1.0 - std::pow(b1, tstep)));
+  const float* lr_dev = nullptr;
+  if (!h->sharded()) {
+    // whole tables: every Adam kernel of this step reads lr_t from the device
+    launch_adam_step(step, h->wd("adam.step"), c.learning_rate, c.beta1, c.beta2, h->wf("adam.lr"), st);
+    lr_dev = h->wf("adam.lr");
+  }
   double* reg = h->wd("loss_acc") + 3;
   void* tmp = h->ws<char>("cub_temp");
   size_t tmp_bytes = (size_t)L.ws[L.ws_index.at("cub_temp")].numel;
@@ -1092,7 +1123,8 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
     const bool planned = h->plan_for == b->item_history && h->plan_rows == B;
     h->plan_for = nullptr;
     const Sp2 s2 = make_sp2(h, b);
-    const AdamP ap = make_adam(h, lr_t);
+    AdamP ap = make_adam(h, lr_t);
+    ap.lr_dev = lr_dev;
     if (planned) cudaStreamWaitEvent(st, h->ev_plan, 0);
     else if (launch_sp2_plan(s2, tmp, tmp_bytes, st)) return fail(h, "cub sort failed");
     launch_sp2_walk(s2, ap, st);
@@ -1130,12 +1162,14 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
   launch_dense_norm(h->buf.dense_param, h->buf.dense_grad, h->wi("seg_tab"), n_seg, c.layer_l2, h->wd("seg_normsq"),
                     h->wd("sp_normsq") + 4, reg, st);
   launch_dense_adam(h->buf.dense_param, h->buf.dense_grad, h->buf.dense_m, h->buf.dense_v, h->wi("seg_id"), h->wi("seg_tab"),
-                    h->wd("seg_normsq"), L.dense_numel, c.layer_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm,
+                    h->wd("seg_normsq"), L.dense_numel, c.layer_l2, lr_t, lr_dev, c.beta1, c.beta2, c.epsilon, c.max_grad_norm,
                     c.is_clip_norm, st);
   launch_finish_losses(h->wd("loss_acc"), h->wf("losses"), h->sharded() ? nullptr : h->wd("sp2.l2sq"), c.embed_l2, h->wd("sp_normsq"), st);
   nl += 3;
   return check_cuda(h, "apply_gradients");
 }
+
+#include "api_sibling.inl"
 
 int pamrec_train_step(PamrecHandle h, const PamrecBatch* b, int64_t step, float* losses_out, void* stream) {
   if (!h) return -1;
@@ -1159,6 +1193,7 @@ int pamrec_comm_all_reduce(PamrecHandle h, void* dptr, int64_t count, int dtype,
 int pamrec_bench_gather(PamrecHandle h, const int32_t* item_ids, const int32_t* cate_ids, const int32_t* tgt_items,
                         const int32_t* tgt_cates, int64_t n_rows, int32_t T, float* out, void* stream) {
   if (!h || !h->bound) return fail(h, "not bound");
+  if (h->sibling()) return fail(h, "bench_gather measures PAMRec's fused gather");
   if (T < 1 || T > h->cfg.max_seq_len) return fail(h, "T outside the position table");
   ProfBind _pb(h);
   launch_embed_fwd(item_ids, cate_ids, tgt_items, tgt_cates, h->buf.item_w, h->buf.cate_w, h->P(h->L.pos), out, nullptr, n_rows,
@@ -1172,7 +1207,7 @@ int pamrec_bench_table_adam(PamrecHandle h, int64_t step, void* stream) {
   const PamrecConfig& c = h->cfg;
   const double b1 = c.beta1, b2 = c.beta2;
   const float lr_t = (float)((double)c.learning_rate * std::sqrt(1.0 - std::pow(b2, (double)step)) / (1.0 - std::pow(b1, (double)step)));
-  if (h->sharded()) return fail(h, "bench_table_adam runs on whole tables");
+  if (h->sharded() || h->sibling()) return fail(h, "bench_table_adam runs on PAMRec's whole tables");
   PamrecBatch nb;
   memset(&nb, 0, sizeof nb);
   Sp2 s2 = make_sp2(h, &nb);                              // no lookups: every row decays, none is touched

@@ -90,6 +90,8 @@ struct SparseTable {
   float* accum;               // [n_keys, width]
   int* nuniq;                 // device scalar
   double* normsq;             // device scalar: sum of squares of every un-deduplicated gradient row
+  const int* l2_has0;         // nullable device flag; when it reads 0, row 0 is looked up but carries no L2 term (sibling models: the
+                              // padding id of the satisfied-only history, kernels_sibling.cu:k_sib_has0)
 };
 // undedup (nullable): [0] += sum of squares of every item gradient row (history and target lookups), [1] likewise category rows
 void launch_embed_bwd_reduce(const float* dX0, const float* dTgtHead, float* dTgtTotal, float* dPos, double* pos_normsq,
@@ -112,8 +114,11 @@ void launch_sparse_adam(const SparseTable& t, int64_t n_keys, int mode, float l2
 void launch_dense_norm(const float* P, const float* G, const int* seg_tab, int n_seg, float layer_l2, double* seg_normsq,
                        const double* pos_normsq, double* reg_acc, cudaStream_t st);
 void launch_dense_adam(float* P, const float* G, float* M, float* V, const int* seg_id, const int* seg_tab,
-                       const double* seg_normsq, int64_t n, float layer_l2, float lr_t, float b1, float b2, float eps,
+                       const double* seg_normsq, int64_t n, float layer_l2, float lr_t, const float* lr_dev, float b1, float b2, float eps,
                        float clip, int is_clip, cudaStream_t st);
+// step > 0: *step_dev = step; step == 0: *step_dev += 1 (graph replay).  *lr_out = lr * sqrt(1 - b2^t) / (1 - b1^t) in double, as
+// the host computes it (base_model.py:270-271 + TF 2.4 AdamOptimizer._prepare)
+void launch_adam_step(int64_t step, double* step_dev, float lr, float b1, float b2, float* lr_out, cudaStream_t st);
 // l2sq (nullable): |w|^2 of the unique looked-up rows per table (kernels_sparse2.cu) - their share of the regularisation loss
 // and of the clip norms (added to sp_normsq[0..3] here, after every consumer has run, so that sp_normsq reads as the full norm)
 void launch_finish_losses(const double* loss_acc, float* losses, const double* l2sq, float embed_l2, double* sp_normsq, cudaStream_t st);
@@ -122,7 +127,9 @@ void launch_finish_losses(const double* loss_acc, float* losses, const double* l
 enum { SP2_COMPACT = 0,   // DENSE_EXACT on local tables: run sums -> compact accumulator, row -> unique index map, full sweep
        SP2_FUSED = 1,     // LAZY on local tables: Adam applied to the row inside the walk
        SP2_DENSE = 2 };   // replicated tables (data parallel): run sums -> dense gradient table + touch counts, all-reduced, sweep
-struct AdamP { float lr, b1, b2, eps, l2, clip; int is_clip; };
+// lr = lr_t of TF's Adam (learning rate with both bias corrections); lr_dev != null: read it from device memory instead (the
+// step counter lives on the device when the step is replayed from a CUDA graph, kernels_optim.cu:k_adam_step)
+struct AdamP { float lr, b1, b2, eps, l2, clip; int is_clip; const float* lr_dev; };
 struct Sp2 {
   const int* item_hist; const int* cate_hist; const int* items; const int* cates; const int* users;
   int64_t N; int B;                                  // history positions (B * T), rows
@@ -146,6 +153,28 @@ void launch_sp2_walk(const Sp2& s, const AdamP& a, cudaStream_t st);
 void launch_sp2_lazy_finish(const Sp2& s, const AdamP& a, cudaStream_t st);
 void launch_sp2_adam_sweep(const Sp2& s, const AdamP& a, int lazy, cudaStream_t st);
 void launch_sp2_rep_l2(const Sp2& s, cudaStream_t st);
+
+// ---- kernels_sibling.cu (MMoE_original / PLE / ShareBottom: DIN attention pooling, mixing, loss)
+void launch_sib_gather(const int* sat_item, const int* sat_cate, const int* hist_item, const int* hist_cate, const int* items,
+                       const int* cates, const float* item_w, const float* cate_w, float* h, float* tgt, int* ids_item,
+                       int* ids_cate, int B, int T, cudaStream_t st);
+void launch_sib_has0(const int* hist_item, const int* hist_cate, const int* items, const int* cates, int B, int T, int* has0,
+                     cudaStream_t st);
+void launch_sib_feat_fwd(float* feat, const float* tgt, int B, int T, cudaStream_t st);
+void launch_sib_feat_bwd(const float* d_feat, const float* feat, const float* tgt, float* d_att, float* dq, int B, int T,
+                         cudaStream_t st);
+void launch_sib_pool_fwd(const float* h, const float* score, const int* sat_mask, const int* mask, const float* tgt, float* aw,
+                         float* x, int B, int T, cudaStream_t st);
+void launch_sib_pool_bwd(const float* h, const float* aw, const int* sat_mask, const int* mask, const float* d_x, float* d_score,
+                         float* dh, int B, int T, cudaStream_t st);
+void launch_sib_tgt_total(const float* d_tgt, const float* d_x, const float* dq, float* out, int B, cudaStream_t st);
+void launch_sib_mix_fwd(const float* ZE1, const float* ZG1, const BnSet& e1, const BnSet& g1, const float* tgt, float* U, int n_expert,
+                        const int sel[2][5], int B, cudaStream_t st);
+void launch_sib_mix_bwd(const float* ZE1, const float* ZG1, const BnSet& e1, const BnSet& g1, const float* dU, float* dE1, float* dG1,
+                        float* dTgt, int n_expert, const int sel[2][5], int B, cudaStream_t st);
+void launch_sib_loss(const float* logits, const float* y_sat, const float* y_play, float* d_logits, double* loss_acc, int B, float aux_w,
+                     cudaStream_t st);
+void launch_sib_pred(const float* logits, float* pred, int B, cudaStream_t st);
 
 // ---- kernels_p2p.cu (small all-reduces through NVLink peer mailboxes)
 constexpr int kP2PMaxDoubles = 2048;     // payload capacity of one mailbox slot (expert + gate layer-0 sums: 1256)

@@ -236,7 +236,7 @@ int launch_sparse_reduce(const SparseTable& t, const int* hist_ids, const int* t
 template <int W>
 __global__ void __launch_bounds__(256)
 k_sparse_l2norm(const int* __restrict__ ukeys, const int* __restrict__ nuniq, const float* __restrict__ w, float l2,
-                double* __restrict__ normsq, double* __restrict__ reg_acc) {
+                double* __restrict__ normsq, double* __restrict__ reg_acc, const int* __restrict__ has0) {
   __shared__ double sh[8];
   constexpr int CH = W / 4;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -244,8 +244,9 @@ k_sparse_l2norm(const int* __restrict__ ukeys, const int* __restrict__ nuniq, co
   double s = 0.0;
   if (i < total) {
     int u = (int)(i / CH), c = (int)(i % CH);
-    float4 v = ld4(w + (int64_t)ukeys[u] * W + 4 * c);
-    s = (double)f4_dot(v, v);
+    const int key = ukeys[u];
+    float4 v = ld4(w + (int64_t)key * W + 4 * c);
+    if (!(has0 != nullptr && key == 0 && *has0 == 0)) s = (double)f4_dot(v, v);   // row 0 looked up without being an L2 row (SparseTable::l2_has0)
   }
   s = warp_sum_d(s);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
@@ -263,9 +264,9 @@ void launch_sparse_l2norm(const SparseTable& t, int64_t n_keys, float l2, double
   int64_t total = n_keys * (t.width / 4);
   if (total == 0) return;
   unsigned g = (unsigned)((total + 255) / 256);
-  if (t.width == 16) k_sparse_l2norm<16><<<g, 256, 0, st>>>(t.ukeys, t.nuniq, t.w, l2, t.normsq, reg_acc);
-  else if (t.width == 4) k_sparse_l2norm<4><<<g, 256, 0, st>>>(t.ukeys, t.nuniq, t.w, l2, t.normsq, reg_acc);
-  else k_sparse_l2norm<20><<<g, 256, 0, st>>>(t.ukeys, t.nuniq, t.w, l2, t.normsq, reg_acc);
+  if (t.width == 16) k_sparse_l2norm<16><<<g, 256, 0, st>>>(t.ukeys, t.nuniq, t.w, l2, t.normsq, reg_acc, t.l2_has0);
+  else if (t.width == 4) k_sparse_l2norm<4><<<g, 256, 0, st>>>(t.ukeys, t.nuniq, t.w, l2, t.normsq, reg_acc, t.l2_has0);
+  else k_sparse_l2norm<20><<<g, 256, 0, st>>>(t.ukeys, t.nuniq, t.w, l2, t.normsq, reg_acc, t.l2_has0);
 }
 
 __device__ __forceinline__ void adam_row4(float4& w, float4& m, float4& v, const float4& g, float lr, float b1, float b2,
@@ -289,10 +290,11 @@ template <int W>
 __global__ void __launch_bounds__(256)
 k_table_adam_dense(float* __restrict__ tw, float* __restrict__ tm, float* __restrict__ tv, const int* __restrict__ slot,
                    const float* __restrict__ accum, const double* __restrict__ normsq, int64_t n_rows, float l2, float lr,
-                   float b1, float b2, float eps, float clip, int is_clip) {
+                   float b1, float b2, float eps, float clip, int is_clip, const int* __restrict__ has0) {
   constexpr int CH = W / 4;
   const int64_t total = n_rows * CH;
   const float scale = clip_scale(normsq, clip, is_clip);
+  const bool no_l2_row0 = has0 != nullptr && *has0 == 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / CH;
     const int c = (int)(i % CH);
@@ -301,8 +303,9 @@ k_table_adam_dense(float* __restrict__ tw, float* __restrict__ tm, float* __rest
     const int u = __ldg(slot + r);
     if (u >= 0) {
       float4 a = accum ? ld4(accum + (int64_t)u * W + 4 * c) : f4_zero();
-      g.x = scale * (a.x + l2 * w.x); g.y = scale * (a.y + l2 * w.y);
-      g.z = scale * (a.z + l2 * w.z); g.w = scale * (a.w + l2 * w.w);
+      const float l2r = (no_l2_row0 && r == 0) ? 0.f : l2;
+      g.x = scale * (a.x + l2r * w.x); g.y = scale * (a.y + l2r * w.y);
+      g.z = scale * (a.z + l2r * w.z); g.w = scale * (a.w + l2r * w.w);
     }
     adam_row4(w, m, v, g, lr, b1, b2, eps);
     st4(tw + 4 * i, w); st4(tm + 4 * i, m); st4(tv + 4 * i, v);
@@ -312,13 +315,14 @@ template <int W>
 __global__ void __launch_bounds__(256)
 k_table_adam_lazy(float* __restrict__ tw, float* __restrict__ tm, float* __restrict__ tv, const int* __restrict__ ukeys,
                   const int* __restrict__ nuniq, const float* __restrict__ accum, const double* __restrict__ normsq, float l2,
-                  float lr, float b1, float b2, float eps, float clip, int is_clip) {
+                  float lr, float b1, float b2, float eps, float clip, int is_clip, const int* __restrict__ has0) {
   constexpr int CH = W / 4;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)(*nuniq) * CH) return;
   const int u = (int)(i / CH), c = (int)(i % CH);
   const int64_t o = (int64_t)ukeys[u] * W + 4 * c;
   const float scale = clip_scale(normsq, clip, is_clip);
+  if (has0 != nullptr && ukeys[u] == 0 && *has0 == 0) l2 = 0.f;
   float4 w = ld4(tw + o), m = ld4(tm + o), v = ld4(tv + o);
   float4 a = accum ? ld4(accum + (int64_t)u * W + 4 * c) : f4_zero();
   float4 g;
@@ -340,12 +344,12 @@ static void sparse_adam_w(const SparseTable& t, int64_t n_keys, int mode, float 
     int64_t blocks = (total + 255) / 256;
     const int64_t cap = 148 * 32;                                 // grid-stride above 32 CTAs per SM
     unsigned g = (unsigned)(blocks < cap ? blocks : cap);
-    k_table_adam_dense<W><<<g, 256, 0, st>>>(t.w, t.m, t.v, t.slot, t.accum, t.normsq, t.n_rows, l2, lr, b1, b2, eps, clip, is_clip);
+    k_table_adam_dense<W><<<g, 256, 0, st>>>(t.w, t.m, t.v, t.slot, t.accum, t.normsq, t.n_rows, l2, lr, b1, b2, eps, clip, is_clip, t.l2_has0);
   } else {
     int64_t total = n_keys * (W / 4);
     if (total == 0) return;
     k_table_adam_lazy<W><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t.w, t.m, t.v, t.ukeys, t.nuniq, t.accum, t.normsq, l2,
-                                                                        lr, b1, b2, eps, clip, is_clip);
+                                                                        lr, b1, b2, eps, clip, is_clip, t.l2_has0);
   }
 }
 void launch_sparse_adam(const SparseTable& t, int64_t n_keys, int mode, float l2, float lr_t, float b1, float b2, float eps,
@@ -402,9 +406,10 @@ void launch_dense_norm(const float* P, const float* G, const int* seg_tab, int n
 __global__ void __launch_bounds__(256)
 k_dense_adam(float* __restrict__ P, const float* __restrict__ G, float* __restrict__ M, float* __restrict__ V,
              const int* __restrict__ seg_id, const int* __restrict__ seg_tab, const double* __restrict__ seg_normsq, int64_t n,
-             float layer_l2, float lr, float b1, float b2, float eps, float clip, int is_clip) {
+             float layer_l2, float lr, const float* __restrict__ lr_dev, float b1, float b2, float eps, float clip, int is_clip) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (lr_dev != nullptr) lr = __ldg(lr_dev);
   const int s = seg_id[i];
   const int flags = seg_tab[4 * s + 2];
   const float l2 = (flags & PAMREC_SEG_L2) ? layer_l2 : 0.f;
@@ -426,10 +431,20 @@ k_dense_adam(float* __restrict__ P, const float* __restrict__ G, float* __restri
   P[i] = p; M[i] = m; V[i] = v;
 }
 void launch_dense_adam(float* P, const float* G, float* M, float* V, const int* seg_id, const int* seg_tab,
-                       const double* seg_normsq, int64_t n, float layer_l2, float lr_t, float b1, float b2, float eps,
+                       const double* seg_normsq, int64_t n, float layer_l2, float lr_t, const float* lr_dev, float b1, float b2, float eps,
                        float clip, int is_clip, cudaStream_t st) { PAMREC_PROF("dense_adam", 1, st);
-  k_dense_adam<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, G, M, V, seg_id, seg_tab, seg_normsq, n, layer_l2, lr_t, b1, b2,
+  k_dense_adam<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, G, M, V, seg_id, seg_tab, seg_normsq, n, layer_l2, lr_t, lr_dev, b1, b2,
                                                            eps, clip, is_clip);
+}
+
+__global__ void k_adam_step(long long step, double* __restrict__ step_dev, float lr, float b1, float b2, float* __restrict__ lr_out) {
+  const double t = step > 0 ? (double)step : *step_dev + 1.0;
+  *step_dev = t;
+  *lr_out = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+}
+void launch_adam_step(int64_t step, double* step_dev, float lr, float b1, float b2, float* lr_out, cudaStream_t st) {
+  PAMREC_PROF("adam_step", 1, st);
+  k_adam_step<<<1, 1, 0, st>>>((long long)step, step_dev, lr, b1, b2, lr_out);
 }
 
 __global__ void k_finish_losses(const double* __restrict__ acc, float* __restrict__ losses, const double* __restrict__ l2sq,

@@ -52,7 +52,7 @@ __device__ __forceinline__ float sp2_clip_scale(const Sp2& s, const AdamP& a, in
 }
 __device__ __forceinline__ void sp2_adam4(float4& w, float4& m, float4& v, const float4& g, const AdamP& a) {
   // TF _apply_sparse_shared: m = m*b1 + g*(1-b1); v = v*b2 + g*g*(1-b2); w -= lr*m/(sqrt(v)+eps)
-  const float b1 = a.b1, b2 = a.b2, lr = a.lr, eps = a.eps;
+  const float b1 = a.b1, b2 = a.b2, lr = a.lr_dev ? __ldg(a.lr_dev) : a.lr, eps = a.eps;
   m.x = m.x * b1 + g.x * (1.f - b1); m.y = m.y * b1 + g.y * (1.f - b1);
   m.z = m.z * b1 + g.z * (1.f - b1); m.w = m.w * b1 + g.w * (1.f - b1);
   v.x = v.x * b2 + (g.x * g.x) * (1.f - b2); v.y = v.y * b2 + (g.y * g.y) * (1.f - b2);

@@ -46,6 +46,14 @@ struct Layout {
   BnOff bnoff[BN_COUNT];
   int64_t bn_bsums_off[BN_COUNT];
   std::map<std::string, size_t> ws_index;
+  // sibling models (PAMREC_MODEL_MMOE / _PLE / _SHAREBOTTOM, build_sibling below): the attention MLP of the two DIN branches
+  // takes the place of the score MLP (BN_S0 / BN_S1 = its two layers, 2 x 80 and 2 x 40 channels)
+  int model_kind = PAMREC_MODEL_PAMREC;
+  int n_expert = 0;                             // 5 (MMoE), 7 (PLE: 3 shared, 2 main, 2 sub), 0 (share-bottom)
+  int gate_sel[2][5] = {{0, 1, 2, 3, 4}, {0, 1, 2, 3, 4}};   // experts mixed by gate_main / gate_sub (ple.py:51-58)
+  int tower_in = 0;                             // 84 = 64 + 20 (mixing output | target) or 60 (share-bottom: x itself)
+  MlpOff att;                                   // att_fcn of long_term, short_term (group-strided)
+  int64_t att_mat = 0;                          // attention_mat of long_term; short_term follows at + 400
 
   int64_t add_dense(const std::string& name, std::initializer_list<int64_t> shape, int flags) {
     TensorDesc t;
@@ -117,9 +125,130 @@ struct Layout {
     return o;
   }
 
+  // optimiser scratch shared by every model family
+  void add_optim_ws() {
+    add_ws("seg_id", PAMREC_I32, {dense_numel});
+    add_ws("seg_tab", PAMREC_I32, {(int64_t)dense.size(), 4});   // off, numel, flags, -
+    add_ws("seg_normsq", PAMREC_F64, {(int64_t)dense.size()});
+    add_ws("sp_normsq", PAMREC_F64, {8});          // 0 item 1 cate 2 ulong 3 ushort 4 pos
+    add_ws("adam.step", PAMREC_F64, {2});          // optimiser step on the device (graph replay advances it there)
+    add_ws("adam.lr", PAMREC_F32, {4});            // lr_t of the current step, written by k_adam_step
+  }
+  void add_bn_ws() {
+    const char* bn_names[BN_COUNT] = {"s0", "s1", "e0", "g0", "e1", "g1", "t0", "t1"};
+    int64_t bn_c = 0;
+    for (int i = 0; i < BN_COUNT; ++i) {
+      std::string p = std::string("bn.") + bn_names[i];
+      add_ws(p + ".sums", PAMREC_F64, {bnoff[i].C, 2});
+      add_ws(p + ".stat", PAMREC_F32, {bnoff[i].C, 2});
+      bn_bsums_off[i] = 2 * bn_c;
+      bn_c += bnoff[i].C;
+    }
+    add_ws("bn.bsums", PAMREC_F64, {bn_c, 2});   // backward sums (sum dy, sum dy*xhat) of all sets: one memset per step
+    add_ws("bn.gsums", PAMREC_F64, {8, bn_c, 2});    // row-stationary head: 8 copies of the forward sums (set-major inside a copy group)
+    add_ws("bn.gbsums", PAMREC_F64, {8, bn_c, 2});   // ... and of the backward sums
+  }
+
+  // MMoEModel_original / PLEModel / ShareBottomModel (oracle/siblings_oracle.py:param_spec has the same inventory, by TF name)
+  void build_sibling(const PamrecConfig& c) {
+    const int L2 = PAMREC_SEG_L2;
+    const int64_t B = Bcap, N = (int64_t)Bcap * T;
+    const std::string clsr = "sequential/clsr/";
+    // ---- dense pool
+    att_mat = add_dense(clsr + "long_term/attention_fcn/attention_mat", {kE, kE}, L2);          // mmoe.py:315-319
+    add_dense(clsr + "short_term/attention_fcn/attention_mat", {kE, kE}, L2);
+    att = add_mlp({clsr + "long_term/attention_fcn/att_fcn", clsr + "short_term/attention_fcn/att_fcn"}, {L2, L2}, 4 * kE, 80, 40, true,
+                  &bnoff[BN_S0], &bnoff[BN_S1]);                                                 // mmoe.py:327-329
+    const int x_dim = 3 * kE;
+    std::vector<std::string> ex;
+    if (model_kind == PAMREC_MODEL_MMOE) {
+      for (int j = 0; j < 5; ++j) ex.push_back(clsr + "expert_" + std::to_string(j));           // mmoe.py:38-41
+    } else if (model_kind == PAMREC_MODEL_PLE) {
+      for (int j = 0; j < 3; ++j) ex.push_back(clsr + "share_expert_" + std::to_string(j));     // ple.py:38-49
+      for (int j = 0; j < 2; ++j) ex.push_back(clsr + "main_expert_" + std::to_string(j));
+      for (int j = 0; j < 2; ++j) ex.push_back(clsr + "sub_expert_" + std::to_string(j));
+      const int ms[5] = {0, 1, 2, 3, 4}, ss[5] = {0, 1, 2, 5, 6};                              // shared experts first (ple.py:51-58)
+      for (int j = 0; j < 5; ++j) { gate_sel[0][j] = ms[j]; gate_sel[1][j] = ss[j]; }
+    }
+    n_expert = (int)ex.size();
+    if (n_expert) {
+      expert = add_mlp(ex, std::vector<int>(ex.size(), L2), x_dim, 100, 64, false, &bnoff[BN_E0], &bnoff[BN_E1]);
+      gate = add_mlp({clsr + "gate_main", clsr + "gate_sub"}, {L2, L2}, x_dim, 64, 5, false, &bnoff[BN_G0], &bnoff[BN_G1]);
+      tower_in = 64 + kE;
+    } else {
+      bnoff[BN_E0] = bnoff[BN_E1] = bnoff[BN_G0] = bnoff[BN_G1] = BnOff{0, 0, 0, 0, 0};
+      tower_in = x_dim;                                                                          // sharebottom.py:200-201
+    }
+    tower = add_mlp({"sequential/logit_fcn", "sequential/valid_logit_fcn"}, {L2, L2}, tower_in, 100, 64, true, &bnoff[BN_T0], &bnoff[BN_T1]);
+    // ---- workspace.  Branch 0 = long_term (satisfied-only history), branch 1 = short_term (full history).
+    add_ws("sib.ids_item", PAMREC_I32, {2, N});      // lookups of the item table in branch order (keys of the sparse plan)
+    add_ws("sib.ids_cate", PAMREC_I32, {2, N});
+    add_ws("sib.h", PAMREC_F32, {2, N, kE});         // gathered history tokens item | cate
+    add_ws("tgt", PAMREC_F32, {B, kE});
+    add_ws("sib.feat", PAMREC_F32, {N, 160});        // per branch: a = h A | q | a - q | a * q   (mmoe.py:320-326)
+    add_ws("z1", PAMREC_F32, {N, 160});              // att_fcn layer 0 pre-activations (both branches)
+    add_ws("z2", PAMREC_F32, {N, 80});               // layer 1
+    add_ws("sib.score", PAMREC_F32, {N, 2});         // linear output = attention logits
+    add_ws("sib.aw", PAMREC_F32, {2, N});            // softmax weights, kept for the backward pass
+    add_ws("x", PAMREC_F32, {B, 60});                // long | short | target
+    add_ws("ze0", PAMREC_F32, {B, (int64_t)n_expert * 100});
+    add_ws("zg0", PAMREC_F32, {B, n_expert ? 128 : 0});
+    add_ws("ze1", PAMREC_F32, {B, (int64_t)n_expert * 64});
+    add_ws("zg1", PAMREC_F32, {B, n_expert ? 10 : 0});
+    add_ws("u", PAMREC_F32, {B, 168});
+    add_ws("zt0", PAMREC_F32, {B, 200});
+    add_ws("zt1", PAMREC_F32, {B, 128});
+    add_ws("logits", PAMREC_F32, {B, 2});            // logit_fcn (satisfied label), valid_logit_fcn (play label)
+    add_ws("losses", PAMREC_F32, {8});
+    add_ws("loss_acc", PAMREC_F64, {8});
+    add_ws("d_logits", PAMREC_F32, {B, 2});
+    add_ws("d_t1", PAMREC_F32, {B, 128});
+    add_ws("d_t0", PAMREC_F32, {B, 200});
+    add_ws("d_u", PAMREC_F32, {B, 168});
+    add_ws("d_e1", PAMREC_F32, {B, (int64_t)n_expert * 64});
+    add_ws("d_g1", PAMREC_F32, {B, n_expert ? 10 : 0});
+    add_ws("d_e0", PAMREC_F32, {B, (int64_t)n_expert * 100});
+    add_ws("d_g0", PAMREC_F32, {B, n_expert ? 128 : 0});
+    add_ws("d_x", PAMREC_F32, {B, 60});
+    add_ws("d_tgt", PAMREC_F32, {B, kE});            // from the towers' target columns
+    add_ws("d_tgt_total", PAMREC_F32, {B, kE});
+    add_ws("sib.d_score", PAMREC_F32, {N, 2});
+    add_ws("sib.d_a1", PAMREC_F32, {N, 80});
+    add_ws("sib.d_a0", PAMREC_F32, {N, 160});
+    add_ws("sib.d_feat", PAMREC_F32, {N, 160});
+    add_ws("sib.d_att", PAMREC_F32, {2, N, kE});     // gradient of a = h A
+    add_ws("sib.dq", PAMREC_F32, {B, 2, kE});        // gradient of the query (target) through the feature rows, per branch
+    add_ws("sib.dh", PAMREC_F32, {2, N, kE});        // gradient of the gathered tokens = rows of the sparse gradient
+    add_ws("sib.zero", PAMREC_F32, {256});           // never written: the bias of the bias-free attention_mat product
+    add_ws("sib.dummy", PAMREC_F32, {256});          // sink of that product's bias gradient
+    add_ws("sib.has0", PAMREC_I32, {4});             // [0] item [1] category: id 0 occurs among the history / target ids; when it
+                                                     // does not, row 0 is looked up by the satisfied-only history's padding alone and
+                                                     // is not among the L2 rows (sequential_base_model.py:640-664)
+    add_bn_ws();
+    add_optim_ws();
+    // sparse path (kernels_optim.cu, one plan per table): keys = satisfied ids, history ids, target ids
+    const int64_t NK = 2 * N + B;
+    cub_keys_table = NK;
+    for (const char* t : {"item", "cate"}) {
+      std::string p = std::string("sp.") + t + ".";
+      for (const char* n : {"keys", "idx", "skeys", "sidx", "uidx", "ukeys"}) add_ws(p + n, PAMREC_I32, {NK});
+      add_ws(p + "slot", PAMREC_I32, {t[0] == 'i' ? n_items : n_cates});
+      add_ws(p + "accum", PAMREC_F32, {NK, t[0] == 'i' ? kI : kC});
+    }
+    for (const char* n : {"keys", "idx", "skeys", "sidx", "uidx", "ukeys"}) add_ws(std::string("sp.user.") + n, PAMREC_I32, {B});
+    add_ws("sp.user.slot", PAMREC_I32, {n_users});
+    add_ws("sp.nuniq", PAMREC_I32, {8});
+    add_ws("dp.scalars", PAMREC_F64, {8});
+    cub_keys = NK;
+    add_ws("cub_temp", PAMREC_U8, {(int64_t)(16u << 20) + 16 * cub_keys});
+    (void)c;
+  }
+
   void build(const PamrecConfig& c) {
     n_users = c.n_users; n_items = c.n_items; n_cates = c.n_cates; T = c.max_seq_len; Bcap = c.max_batch;
     world = c.world_size < 1 ? 1 : c.world_size; table_mode = c.table_mode;
+    model_kind = c.model_kind;
+    if (model_kind != PAMREC_MODEL_PAMREC) { build_sibling(c); return; }
     const int L2 = PAMREC_SEG_L2;
     // ---- dense pool: encoder first so that every float4-loaded matrix starts on a 16-byte boundary
     pos = add_dense("sequential/embedding/position_embedding", {T, kD}, PAMREC_SEG_POS);
@@ -206,24 +335,9 @@ struct Layout {
     add_ws("d_Q", PAMREC_F32, {B, T, kD});
     add_ws("d_K", PAMREC_F32, {B, T, kD});
     add_ws("d_V", PAMREC_F32, {B, T, kD});
-    // batch-norm statistics
-    const char* bn_names[BN_COUNT] = {"s0", "s1", "e0", "g0", "e1", "g1", "t0", "t1"};
-    int64_t bn_c = 0;
-    for (int i = 0; i < BN_COUNT; ++i) {
-      std::string p = std::string("bn.") + bn_names[i];
-      add_ws(p + ".sums", PAMREC_F64, {bnoff[i].C, 2});
-      add_ws(p + ".stat", PAMREC_F32, {bnoff[i].C, 2});
-      bn_bsums_off[i] = 2 * bn_c;
-      bn_c += bnoff[i].C;
-    }
-    add_ws("bn.bsums", PAMREC_F64, {bn_c, 2});   // backward sums (sum dy, sum dy*xhat) of all sets: one memset per step
-    add_ws("bn.gsums", PAMREC_F64, {8, bn_c, 2});    // row-stationary head: 8 copies of the forward sums (set-major inside a copy group)
-    add_ws("bn.gbsums", PAMREC_F64, {8, bn_c, 2});   // ... and of the backward sums
-    // optimiser scratch
-    add_ws("seg_id", PAMREC_I32, {dense_numel});
-    add_ws("seg_tab", PAMREC_I32, {(int64_t)dense.size(), 4});   // off, numel, flags, -
-    add_ws("seg_normsq", PAMREC_F64, {(int64_t)dense.size()});
-    add_ws("sp_normsq", PAMREC_F64, {8});          // 0 item 1 cate 2 ulong 3 ushort 4 pos
+    // batch-norm statistics, optimiser scratch
+    add_bn_ws();
+    add_optim_ws();
     // sparse path: keys = history ids then target ids.  "sp.*" is the plan of THIS rank's lookups; the slot map
     // (table row -> unique index) always covers the rows this rank owns.
     const int64_t NK = N + B;

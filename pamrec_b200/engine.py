@@ -35,6 +35,9 @@ BATCH_FIELDS = (  # name, dtype, per-row shape suffix, needed for scoring
     ("mask", np.int32, True), ("users", np.int32, False), ("items", np.int32, False), ("cates", np.int32, False),
     ("labels_satisfied", np.float32, False), ("labels_play", np.float32, False), ("plays", np.float32, False),
 )
+# the satisfied-only copy of the history (IT:1069-1103): read by the sibling models only (mmoe.py:199-201)
+SIBLING_FIELDS = (("satisfied_item_history", np.int32, True), ("satisfied_cate_history", np.int32, True), ("satisfied_mask", np.int32, True))
+MODELS = {"pamrec": L.MODEL_PAMREC, "mmoe": L.MODEL_MMOE, "ple": L.MODEL_PLE, "sharebottom": L.MODEL_SHAREBOTTOM}
 
 
 class PamrecError(RuntimeError):
@@ -86,13 +89,21 @@ class PendingHost:
 
 class Engine:
     def __init__(self, n_users, n_items, n_cates, max_seq_len, max_batch, hp=None, sparse_adam="dense_exact",
-                 world_size=1, rank=0, tables=None):
-        """tables: "local" (whole tables on this GPU, world_size 1), "replicated" (every rank holds whole tables; the merged
+                 world_size=1, rank=0, tables=None, model="pamrec"):
+        """model: "pamrec" (PAMRECModel) or one of the sibling multi-task baselines "mmoe" (MMoEModel_original), "ple" (PLEModel),
+        "sharebottom" (ShareBottomModel) - those run on one GPU with whole tables.
+        tables: "local" (whole tables on this GPU, world_size 1), "replicated" (every rank holds whole tables; the merged
         row gradients are all-reduced with the dense gradients and every rank applies the same update), "sharded" (row r on
         rank r % world_size, rows and row gradients exchanged by all-to-all; also runs on one GPU) or "auto" / None: local on one
         GPU; on several, replicated while the four tables together stay below REPLICATE_BYTES (PAMREC_REPLICATE_MB), else sharded."""
         self.lib = L.load()
         self.world, self.rank = int(world_size), int(rank)
+        if model not in MODELS:
+            raise PamrecError(f"unknown model {model!r}: one of {sorted(MODELS)}")
+        self.model = model
+        self.batch_fields = BATCH_FIELDS + (SIBLING_FIELDS if model != "pamrec" else ())
+        if model != "pamrec" and (self.world != 1 or tables not in (None, "auto", "local")):
+            raise PamrecError("the sibling models (mmoe / ple / sharebottom) run on one GPU with whole tables")
         try:
             limit = float(os.environ.get("PAMREC_REPLICATE_MB", D.REPLICATE_BYTES / 2 ** 20)) * 2 ** 20
             tables = D.choose_tables(tables, self.world, n_users, n_items, n_cates, limit)
@@ -112,12 +123,13 @@ class Engine:
             is_clip_norm=int(h["is_clip_norm"]), fuzhu_weight=h["fuzhu_weight"],
             order_weight=h["discrepancy_loss_weight"], sparse_adam_mode=mode, world_size=world_size, rank=rank,
             table_mode={"local": L.TABLES_LOCAL, "sharded": L.TABLES_SHARDED, "replicated": L.TABLES_REPLICATED}[tables],
-            loss_kind={"cross_entropy_loss": L.LOSS_XENT, "softmax": L.LOSS_SOFTMAX}[h["loss"]], softmax_group=int(h["softmax_group"]))
+            loss_kind={"cross_entropy_loss": L.LOSS_XENT, "softmax": L.LOSS_SOFTMAX}[h["loss"]], softmax_group=int(h["softmax_group"]),
+            model_kind=MODELS[model])
         self.handle = C.c_void_p()
         rc = self.lib.pamrec_create(C.byref(self.cfg), C.byref(self.handle))
         if rc != 0:
             raise PamrecError(f"pamrec_create failed ({rc}): check vocabulary sizes, max_seq_len <= 256, max_batch, "
-                              "world_size <= 64, rank, table mode")
+                              "world_size <= 64, rank, table mode, model (siblings: one GPU, cross_entropy_loss)")
         self.dense_numel = self.lib.pamrec_dense_numel(self.handle)
         self.bn_numel = self.lib.pamrec_bn_numel(self.handle)
         self.workspace_bytes = self.lib.pamrec_workspace_bytes(self.handle)
@@ -319,9 +331,9 @@ class Engine:
         the streaming path used by PAMRECModel.train / eval."""
         B = int(np.asarray(feed["items"]).shape[0])
         T = self.dims[3]
-        need = ("item_history", "item_cate_history", "item_loop_times_history", "mask", "items", "cates")
+        need = ("item_history", "item_cate_history", "item_loop_times_history", "mask", "items", "cates") + tuple(n for n, _, _ in SIBLING_FIELDS)
         fields = []
-        for name, dt, is_seq in BATCH_FIELDS:
+        for name, dt, is_seq in self.batch_fields:
             if name not in feed:
                 if training or name in need:
                     raise KeyError(f"feed is missing {name}")
@@ -337,7 +349,7 @@ class Engine:
             nbytes = sum(t.numel() * 4 for t in tensors.values())
         else:
             if not hasattr(self, "_stage"):
-                cap = (4 * self.dims[4] * T + 6 * self.dims[4]) * 4 + 16 * 256
+                cap = (len([f for f in self.batch_fields if f[2]]) * self.dims[4] * T + 6 * self.dims[4]) * 4 + 20 * 256
                 self._stage = [dict(host=torch.empty(cap, dtype=torch.uint8).pin_memory(),
                                     dev=torch.empty(cap, dtype=torch.uint8, device=self.device),
                                     done=torch.cuda.Event()) for _ in range(2)]
@@ -357,11 +369,11 @@ class Engine:
                     tdt = torch.int32 if dt == np.int32 else torch.float32
                     dv[name] = slot["dev"][off:off + n].view(tdt).view(shape)
                     off += (n + 255) // 256 * 256
-                for name, _, _ in BATCH_FIELDS:
+                for name, _, _ in self.batch_fields:
                     if name not in dv:
                         dv[name] = torch.empty(0, device=self.device)
                 db = DeviceBatch(dv, B, global_batch)
-                for name, _, _ in BATCH_FIELDS:
+                for name, _, _ in self.batch_fields:
                     if dv[name].numel() == 0:
                         setattr(db.struct, name, None)
                 db.h2d_bytes = off
@@ -373,12 +385,12 @@ class Engine:
             slot["done"].record(torch.cuda.current_stream(self.device))
             db.struct.global_batch = int(global_batch)
             return db
-        for name, _, _ in BATCH_FIELDS:          # scoring: unused pointers stay null
+        for name, _, _ in self.batch_fields:     # scoring: unused pointers stay null
             if name not in tensors:
                 tensors[name] = torch.empty(0, device=self.device)
         db = DeviceBatch(tensors, B, global_batch)
         db.h2d_bytes = nbytes
-        for name, _, _ in BATCH_FIELDS:
+        for name, _, _ in self.batch_fields:
             if tensors[name].numel() == 0:
                 setattr(db.struct, name, None)
         return db

@@ -64,6 +64,36 @@ def test_inventory_matches_oracle(lib_built):
     eng.close()
 
 
+@pytest.mark.parametrize("model", ["mmoe", "ple", "sharebottom"])
+def test_sibling_inventory_matches_oracle(lib_built, model):
+    """MMoEModel_original / PLEModel / ShareBottomModel: the library's variables, by TF name, are the oracle's param_spec."""
+    from oracle import siblings_oracle as S
+    from pamrec_b200 import _lib as L
+    from pamrec_b200.engine import Engine, PamrecError
+    eng = Engine(n_users=37, n_items=211, n_cates=13, max_seq_len=50, max_batch=25, model=model)
+    shapes = eng.variable_shapes()
+    spec, bn = S.param_spec(model, 37, 211, 13)
+    want = {n: tuple(s) for n, s, _, _ in spec}
+    for scope, c in bn:
+        want[scope + "/moving_mean"] = (c,)
+        want[scope + "/moving_variance"] = (c,)
+    assert set(shapes) == set(want)
+    for n in want:
+        assert tuple(shapes[n]) == want[n], n
+    assert all(d["flags"] & L.SEG_L2 for d in eng.info[L.POOL_DENSE].values())      # everything outside sequential/embedding gets L2
+    segs = sorted((d["offset"], d["numel"]) for d in eng.info[L.POOL_DENSE].values())
+    pos = 0
+    for off, n in segs:
+        assert off == pos
+        pos += n
+    assert pos == eng.dense_numel
+    eng.close()
+    with pytest.raises(PamrecError):
+        Engine(n_users=37, n_items=211, n_cates=13, max_seq_len=50, max_batch=25, model=model, world_size=2, tables="replicated")
+    with pytest.raises(PamrecError):
+        Engine(n_users=37, n_items=211, n_cates=13, max_seq_len=50, max_batch=25, model="din")
+
+
 def test_create_rejects_bad_config(lib_built):
     from pamrec_b200.engine import Engine, PamrecError
     with pytest.raises(PamrecError):
@@ -109,6 +139,9 @@ def test_config_validation_and_calls_before_bind(lib_built):
     assert create(loss_kind=L.LOSS_SOFTMAX, softmax_group=3) == 0                                   # one GPU: any group
     assert create(loss_kind=L.LOSS_SOFTMAX, softmax_group=3, world_size=2, table_mode=L.TABLES_SHARDED) == -8   # ranks hold groups of 5
     assert create(loss_kind=L.LOSS_SOFTMAX, softmax_group=5, world_size=2, table_mode=L.TABLES_SHARDED) == 0
+    assert create(model_kind=4) == -9 and create(model_kind=L.MODEL_PLE) == 0
+    assert create(model_kind=L.MODEL_MMOE, world_size=2, table_mode=L.TABLES_REPLICATED) == -9     # sibling models: one GPU
+    assert create(model_kind=L.MODEL_MMOE, loss_kind=L.LOSS_SOFTMAX, softmax_group=5) == -9
     assert lib.pamrec_create(None, None) == -1
     # a device call before pamrec_bind: error code + message, no crash
     cfg, h = L.PamrecConfig(**base), C.c_void_p()
