@@ -17,6 +17,9 @@ import tensorflow.compat.v1 as tf  # noqa: E402  (shim)
 from reco_utils.recommender.deeprec.deeprec_utils import prepare_hparams  # noqa: E402
 from reco_utils.recommender.deeprec.io.sequential_iterator import SequentialIterator  # noqa: E402
 from reco_utils.recommender.deeprec.models.sequential.pamrec import PAMRECModel  # noqa: E402
+from reco_utils.recommender.deeprec.models.sequential.mmoe import MMoEModel_original  # noqa: E402
+from reco_utils.recommender.deeprec.models.sequential.ple import PLEModel  # noqa: E402
+from reco_utils.recommender.deeprec.models.sequential.sharebottom import ShareBottomModel  # noqa: E402
 
 FLAGS = flags.FLAGS
 flags.DEFINE_string("dataset", "wechat", "Dataset name.")
@@ -26,7 +29,7 @@ flags.DEFINE_integer("test_num_ngs", 0, "negatives per positive in test_data")
 flags.DEFINE_integer("batch_size", 500, "Batch size.")
 flags.DEFINE_string("save_path", "ranking", "Save path.")
 flags.DEFINE_string("name", "try", "Experiment name.")
-flags.DEFINE_string("model", "PAMREC", "Model name.")
+flags.DEFINE_string("model", "PAMREC", "Model name: PAMREC, MMOE_ORIGINAL, PLE or SHAREBOTTOM.")
 flags.DEFINE_boolean("only_test", False, "Only test and do not train.")
 flags.DEFINE_boolean("write_prediction_to_file", False, "Whether to write prediction to file.")
 flags.DEFINE_integer("is_clip_norm", 1, "Whether to clip gradient norm.")
@@ -53,11 +56,15 @@ flags.DEFINE_string("loss", "cross_entropy_loss", "cross_entropy_loss or softmax
 
 
 def get_model(f, model_path, summary_path, user_vocab, item_vocab, cate_vocab):
-    if f.model != "PAMREC":
-        raise NotImplementedError("only --model PAMREC is implemented")
+    # model name -> (class, yaml) as in the reference driver (example/00_quick_start/sequential.py:113-296)
+    models = {"PAMREC": (PAMRECModel, "mmoe.yaml"), "MMOE_ORIGINAL": (MMoEModel_original, "mmoe.yaml"), "PLE": (PLEModel, "ple.yaml"),
+              "SHAREBOTTOM": (ShareBottomModel, "sharebottom.yaml")}
+    if f.model not in models:
+        raise NotImplementedError("--model must be one of " + ", ".join(models))
+    cls, yaml_name = models[f.model]
     weighted = {"wechat": ["wauc", "wmrr", "wndcg@2;4;6;8;10", "whit@2;4;6;8;10"],
                 "takatak": ["wauc", "wmrr", "wndcg@10", "whit@10", "wmrr@10"]}[f.dataset]
-    yaml_file = os.path.join(HERE, "..", "..", "reco_utils", "recommender", "deeprec", "config", "mmoe.yaml")
+    yaml_file = os.path.join(HERE, "..", "..", "reco_utils", "recommender", "deeprec", "config", yaml_name)
     hparams = prepare_hparams(
         yaml_file, dataset=f.dataset, bucket_num=f.bucket_num, add_feature=f.add_feature, embed_l2=f.embed_l2,
         layer_l2=f.layer_l2, discrepancy_loss_weight=f.discrepancy_loss_weight, learning_rate=f.learning_rate,
@@ -68,7 +75,7 @@ def get_model(f, model_path, summary_path, user_vocab, item_vocab, cate_vocab):
         eval_step=f.eval_step, noise_train_hist=f.noise_train_hist, noise_train_listwise=f.noise_train_listwise,
         noise_only_predict=f.noise_only_predict, sparse_adam=f.sparse_adam, checkpoint_format=f.checkpoint_format,
         save_optimizer=f.save_optimizer, loss=f.loss)
-    return PAMRECModel(hparams, SequentialIterator, seed=8)
+    return cls(hparams, SequentialIterator, seed=8)
 
 
 def main(argv):

@@ -180,8 +180,15 @@ __device__ __forceinline__ void dense_fwd_item(const DenseP& p, int M, double* o
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = bias[j];
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     tile_mma(As, Bs, p.K, ty, tx, acc);
+    // the bias joins the finished product (as tf.matmul + bias does): ONE rounding at the bias's magnitude instead of K of them.
+    // It matters where a batch norm follows: a bias of 0.1 in front of a signal of std 5e-4 (the attention MLPs of the sibling
+    // models at init) puts every partial sum on a 1.5e-8 grid, and the normalisation then amplifies that by 1 / sqrt(eps) = 100.
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += bias[j];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int r = 2 * ty + i;

@@ -89,9 +89,11 @@ class PendingHost:
 
 class Engine:
     def __init__(self, n_users, n_items, n_cates, max_seq_len, max_batch, hp=None, sparse_adam="dense_exact",
-                 world_size=1, rank=0, tables=None, model="pamrec"):
+                 world_size=1, rank=0, tables=None, model="pamrec", graph=None):
         """model: "pamrec" (PAMRECModel) or one of the sibling multi-task baselines "mmoe" (MMoEModel_original), "ple" (PLEModel),
         "sharebottom" (ShareBottomModel) - those run on one GPU with whole tables.
+        graph: replay the train step from a CUDA graph (one graph per resident / staged DeviceBatch, captured at its second use;
+        one GPU, whole tables, PAMRec only).  None reads PAMREC_GRAPH (default off).
         tables: "local" (whole tables on this GPU, world_size 1), "replicated" (every rank holds whole tables; the merged
         row gradients are all-reduced with the dense gradients and every rank applies the same update), "sharded" (row r on
         rank r % world_size, rows and row gradients exchanged by all-to-all; also runs on one GPU) or "auto" / None: local on one
@@ -136,6 +138,11 @@ class Engine:
         self.info = {p: self._query(p) for p in (L.POOL_DENSE, L.POOL_BN, L.POOL_WORKSPACE)}
         self.step = 0
         self.device = None
+        if graph is None:
+            graph = os.environ.get("PAMREC_GRAPH", "0") == "1"
+        self.graph = bool(graph)
+        self._graphs, self._profiling = {}, False
+        self._dev_step = None                        # value of the device-side step counter, when known to equal self.step
         self.frozen = {n: np.zeros(f(n_users), np.float32) for n, f in FROZEN.items()}
 
     # ------------------------------------------------------------------ inventory (host only)
@@ -301,6 +308,7 @@ class Engine:
         for key, val in st.items():
             if key == "step":
                 self.step = int(np.asarray(val).reshape(-1)[0])
+                self._dev_step = None
                 continue
             name, _, slot = key.rpartition("/")
             which = {"Adam": "m", "Adam_1": "v"}.get(slot)
@@ -412,16 +420,43 @@ class Engine:
     def apply_gradients(self, db):
         self.step += 1
         self._check(self.lib.pamrec_apply_gradients(self.handle, C.byref(db.struct), self.step, self._stream()))
+        self._dev_step = self.step
         return self.ws("losses")[:5]
 
     def train_step(self, db, losses_out=None):
         """One optimisation step; returns a device tensor [loss, data, regular, auxiliary, order] (pamrec.py:444-448)."""
+        if losses_out is None and self._dev_step == self.step and self._graph_ok():
+            return self._train_step_graph(db)
         self.step += 1
         if losses_out is None:
             losses_out = torch.empty(5, dtype=torch.float32, device=self.device)
         self._check(self.lib.pamrec_train_step(self.handle, C.byref(db.struct), self.step,
                                                C.c_void_p(losses_out.data_ptr()), self._stream()))
+        self._dev_step = self.step                   # a call with step >= 1 sets the device counter
         return losses_out
+
+    def _graph_ok(self):
+        return self.graph and self.world == 1 and self.model == "pamrec" and self.tables == "local" and not self._profiling
+
+    def _train_step_graph(self, db):
+        """The step as ONE CUDA-graph launch.  The captured launches freeze their arguments, so a graph belongs to one DeviceBatch
+        (its device pointers and row count) and the optimiser step lives on the device: pamrec_train_step(step = 0) makes every
+        Adam kernel read lr_t from memory that a one-thread kernel at the head of the step advances (kernels_optim.cu:k_adam_step).
+        The returned losses tensor is owned by the graph and overwritten by its next replay."""
+        ent = self._graphs.get(id(db))
+        if ent is None or ent["db"] is not db or ent["batch"] != db.batch:
+            losses = torch.empty(5, dtype=torch.float32, device=self.device)
+            g = torch.cuda.CUDAGraph()
+            cap = torch.cuda.Stream(self.device)
+            cap.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.graph(g, stream=cap):
+                self._check(self.lib.pamrec_train_step(self.handle, C.byref(db.struct), 0, C.c_void_p(losses.data_ptr()), self._stream()))
+            torch.cuda.current_stream(self.device).wait_stream(cap)
+            ent = self._graphs[id(db)] = dict(graph=g, losses=losses, db=db, batch=db.batch)
+        self.step += 1
+        self._dev_step = self.step
+        ent["graph"].replay()
+        return ent["losses"]
 
     def train_step_async(self, db):
         """train_step whose losses travel to pinned host memory behind the step's kernels; returns a PendingLosses.  The caller
@@ -480,6 +515,7 @@ class Engine:
         return np.frombuffer(buf, dtype=np.uint64).reshape(16, 256).copy()
 
     def profile(self, on=True):
+        self._profiling = bool(on)                   # per-launcher CUDA events: the step is launched kernel by kernel, not replayed
         self._check(self.lib.pamrec_profile_enable(self.handle, int(on)))
         self._check(self.lib.pamrec_profile_reset(self.handle))
 
@@ -498,6 +534,7 @@ class Engine:
         return int(self.lib.pamrec_last_launch_count(self.handle))
 
     def close(self):
+        self._graphs = {}
         if self.handle:
             self.lib.pamrec_destroy(self.handle)
             self.handle = C.c_void_p()

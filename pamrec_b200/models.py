@@ -24,7 +24,8 @@ from .engine import Engine
 from .prefetch import Prefetcher
 from .sequential_iterator import LocalFeed
 
-__all__ = ["PAMRECModel", "SequentialBaseModel", "BaseModel", "latest_checkpoint", "initial_variables"]
+__all__ = ["PAMRECModel", "MMoEModel_original", "PLEModel", "ShareBottomModel", "SequentialBaseModel", "BaseModel", "latest_checkpoint",
+           "initial_variables"]
 
 
 # ----------------------------------------------------------------------------- initial values
@@ -183,8 +184,8 @@ class BaseModel:
         need(hp.optimizer == "adam", "optimizer must be adam (BM:270-271)")
         need(hp.item_embedding_dim == 16 and hp.cate_embedding_dim == 4 and hp.user_embedding_dim == 20,
              "embedding dims must be 16 / 4 / 20 (config/mmoe.yaml:22-24)")
-        need(list(hp.layer_sizes) == [100, 64] and list(hp.expert_layer_sizes) == [100, 64] and
-             list(hp.gate_layer_sizes) == [64, 5] and hp.expert_num == 5, "tower / expert / gate sizes of config/mmoe.yaml")
+        need(list(hp.layer_sizes) == [100, 64], "tower sizes of config/mmoe.yaml")
+        self._check_mixing(hp, need)
         need(list(hp.activation)[:2] == ["relu", "relu"], "activation must be [relu, relu]")
         need(bool(hp.enable_BN), "enable_BN must be True")
         need(all(float(d) == 0.0 for d in hp.dropout) and float(hp.embedding_dropout) == 0.0 and not hp.user_dropout,
@@ -195,6 +196,10 @@ class BaseModel:
              float(hp.cross_l2) == 0.0, "L1 / cross regularisation must be 0")
         need(1 <= hp.max_seq_length <= 256, "max_seq_length must be in [1, 256]")
         need(hp.batch_size % 5 == 0, "batch_size must be a multiple of 5 (IT:684-685, PAM:73-75)")
+
+    def _check_mixing(self, hp, need):
+        need(list(hp.expert_layer_sizes) == [100, 64] and list(hp.gate_layer_sizes) == [64, 5] and hp.expert_num == 5,
+             "expert / gate sizes of config/mmoe.yaml")
 
     def _build_graph(self):
         raise NotImplementedError
@@ -442,6 +447,7 @@ class _PendingStep:
 class PAMRECModel(SequentialBaseModel):
     """PAM:25: the playback-duration-augmented model.  The graph (embeddings, time-aware 2-block encoder, attention
     pooling, MMoE, three towers, four-term loss, per-tensor clip + Adam) is libpamrec_b200.so."""
+    ENGINE_MODEL = "pamrec"
 
     def _build_graph(self):
         hp = self.hparams
@@ -451,7 +457,7 @@ class PAMRECModel(SequentialBaseModel):
         engine_hp = dict(
             learning_rate=float(hp.learning_rate), embed_l2=float(hp.embed_l2), layer_l2=float(hp.layer_l2),
             max_grad_norm=float(hp.max_grad_norm), is_clip_norm=int(bool(hp.is_clip_norm)),
-            fuzhu_weight=float(hp.fuzhu_weight), discrepancy_loss_weight=float(hp.discrepancy_loss_weight),
+            fuzhu_weight=float(getattr(hp, "fuzhu_weight", 0.5)), discrepancy_loss_weight=float(hp.discrepancy_loss_weight),
             loss=hp.loss, softmax_group=int(hp.train_num_ngs or 0) + 1)
         mode = getattr(hp, "sparse_adam", "dense_exact")
         # data parallel (no reference counterpart): one process per GPU under torchrun.  hparams.batch_size stays the GLOBAL
@@ -469,7 +475,7 @@ class PAMRECModel(SequentialBaseModel):
             cap = max(-(-(cap // 5) // world) * 5, -(-cap // world))
         tables = getattr(hp, "tables", None)
         self.engine = Engine(n_users, n_items, n_cates, hp.max_seq_length, cap, hp=engine_hp, sparse_adam=mode,
-                             world_size=world, rank=rank, tables=tables)
+                             world_size=world, rank=rank, tables=tables, model=self.ENGINE_MODEL)
         default_dev = "cuda:{}".format(int(os.environ.get("LOCAL_RANK", 0))) if world > 1 else "cuda:0"
         self.engine.allocate(getattr(hp, "device", default_dev))
         self.engine.init_comm()
@@ -523,3 +529,61 @@ class PAMRECModel(SequentialBaseModel):
         if pending is not None:
             epoch_loss += account(step, pending.result())
         return epoch_loss
+
+
+# ----------------------------------------------------------------------------- sibling multi-task baselines
+class _PendingStep7(_PendingStep):
+    def result(self):
+        l = self._pending.result()
+        return [None, None, float(l[0]), float(l[1]), float(l[2]), float(l[3]), None]
+
+
+class _DinMultiTask(PAMRECModel):
+    """What MMoEModel_original, PLEModel and ShareBottomModel share (models/sequential/mmoe.py, ple.py, sharebottom.py): the
+    input pipeline, DIN attention pooling of the satisfied-only and of the full history against the target (`_attention_fcn`),
+    two towers, loss = data + regular + 0.5 * auxiliary, and the host loops - which differ from PAMRec's only in the 7-tuple
+    that train() returns (no order loss, MM:341-373).  One GPU; embedding dims 16 / 4 / 20 (config/mmoe.yaml) - the kernels'
+    table widths are compile-time constants, so config/ple.yaml and config/sharebottom.yaml are shipped with those dims instead
+    of the reference files' 32 / 8 / 40."""
+
+    def _check_supported(self, hp):
+        super()._check_supported(hp)
+        if list(getattr(hp, "att_fcn_layer_sizes", [80, 40])) != [80, 40]:
+            raise ValueError("pamrec_b200: unsupported configuration: att_fcn_layer_sizes must be [80, 40]")
+        if hp.loss != "cross_entropy_loss":
+            raise ValueError("pamrec_b200: unsupported configuration: the sibling models train with cross_entropy_loss")
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            raise ValueError("pamrec_b200: the sibling models run on one GPU")
+
+    def train_async(self, sess, feed_dict):
+        return _PendingStep7(self.engine.train_step_async(self.engine.upload(feed_dict, training=True, staged=True)))
+
+    def step_train(self, step, step_result):
+        """MM:375-385."""
+        (_, _, step_loss, step_data_loss, _, step_aux, _) = step_result
+        if step % self.hparams.show_step == 0:
+            print("step {0:d} , total_loss: {1:.4f}, data_loss: {2:.4f}, auxiliary_data_loss: {3:.4f}".format(
+                step, step_loss, step_data_loss, step_aux))
+
+
+class MMoEModel_original(_DinMultiTask):
+    """MM:24: five experts, two BN + ReLU gates over all of them (MM:26-50)."""
+    ENGINE_MODEL = "mmoe"
+
+
+class PLEModel(_DinMultiTask):
+    """PLE:24: three shared experts, two per task; each task's gate mixes the shared ones and its own (PLE:25-59)."""
+    ENGINE_MODEL = "ple"
+
+    def _check_mixing(self, hp, need):
+        need(list(hp.expert_layer_sizes) == [100, 64] and list(hp.gate_layer_sizes) == [64, 5] and
+             getattr(hp, "share_expert_num", None) == 3 and getattr(hp, "independent_expert_num", None) == 2,
+             "expert / gate sizes and expert counts of config/ple.yaml (3 shared + 2 per task, gates 64 -> 5)")
+
+
+class ShareBottomModel(_DinMultiTask):
+    """SB:24: no mixing layer, both towers read concat(long, short, target) (SB:196-203)."""
+    ENGINE_MODEL = "sharebottom"
+
+    def _check_mixing(self, hp, need):
+        pass

@@ -21,7 +21,8 @@ REF_DRIVER = "/root/reference/example/00_quick_start/sequential.py"
 pytestmark = pytest.mark.skipif(not os.path.exists(REF_DRIVER), reason="reference tree not mounted")
 
 
-def test_unmodified_reference_driver_runs(tmp_path, monkeypatch, capsys, lib_built):
+@pytest.mark.parametrize("model_flag", ["PAMREC", "MMOE_ORIGINAL", "PLE", "SHAREBOTTOM"])
+def test_unmodified_reference_driver_runs(tmp_path, monkeypatch, capsys, lib_built, model_flag):
     from pamrec_b200 import models as M
     from pamrec_b200 import synth
     if not torch.cuda.is_available():
@@ -33,7 +34,7 @@ def test_unmodified_reference_driver_runs(tmp_path, monkeypatch, capsys, lib_bui
     monkeypatch.syspath_prepend(compat)
     monkeypatch.chdir(os.path.join(compat, "example", "00_quick_start"))       # the driver opens ../../reco_utils/.../config/mmoe.yaml
     argv = [REF_DRIVER, "--dataset", "wechat", "--data_path", str(data), "--save_path", str(tmp_path / "ranking"), "--epochs", "1",
-            "--batch_size", "100", "--eval_step", "5", "--show_step", "5", "--write_prediction_to_file"]
+            "--batch_size", "100", "--eval_step", "5", "--show_step", "5", "--write_prediction_to_file", "--model", model_flag]
     monkeypatch.setattr(sys, "argv", argv)
     for name in [m for m in sys.modules if m == "reco_utils" or m.startswith("reco_utils.") or m == "tensorflow" or m.startswith("tensorflow.")]:
         monkeypatch.delitem(sys.modules, name)
@@ -48,7 +49,7 @@ def test_unmodified_reference_driver_runs(tmp_path, monkeypatch, capsys, lib_bui
     res = eval(last, {"__builtins__": {}, "np": np})                           # numpy 2 prints its scalars as np.float64(...)
     for key in ("auc", "logloss", "wauc", "wmrr", "wndcg@2", "whit@10"):       # QS:100-101 metric lists for wechat
         assert key in res and np.isfinite(res[key]), (key, res)
-    ckpt_dir = tmp_path / "ranking" / "PAMREC" / "try" / "model"
+    ckpt_dir = tmp_path / "ranking" / model_flag / "try" / "model"
     assert (ckpt_dir / "checkpoint").exists(), "fit_step saved no checkpoint for tf.train.latest_checkpoint to find"
     preds = np.loadtxt(data / "wechat" / "output.txt")
     n_test = sum(1 for _ in open(data / "wechat" / "test_data"))
