@@ -93,7 +93,7 @@ class Engine:
         """model: "pamrec" (PAMRECModel) or one of the sibling multi-task baselines "mmoe" (MMoEModel_original), "ple" (PLEModel),
         "sharebottom" (ShareBottomModel) - those run on one GPU with whole tables.
         graph: replay the train step from a CUDA graph (one graph per resident / staged DeviceBatch, captured at its second use;
-        one GPU, whole tables, PAMRec only).  None reads PAMREC_GRAPH (default off).
+        one GPU, whole tables, PAMRec only).  None reads PAMREC_GRAPH (default on; PAMREC_GRAPH=0 launches kernel by kernel).
         tables: "local" (whole tables on this GPU, world_size 1), "replicated" (every rank holds whole tables; the merged
         row gradients are all-reduced with the dense gradients and every rank applies the same update), "sharded" (row r on
         rank r % world_size, rows and row gradients exchanged by all-to-all; also runs on one GPU) or "auto" / None: local on one
@@ -139,7 +139,7 @@ class Engine:
         self.step = 0
         self.device = None
         if graph is None:
-            graph = os.environ.get("PAMREC_GRAPH", "0") == "1"
+            graph = os.environ.get("PAMREC_GRAPH", "1") != "0"
         self.graph = bool(graph)
         self._graphs, self._profiling = {}, False
         self._dev_step = None                        # value of the device-side step counter, when known to equal self.step
@@ -426,7 +426,9 @@ class Engine:
     def train_step(self, db, losses_out=None):
         """One optimisation step; returns a device tensor [loss, data, regular, auxiliary, order] (pamrec.py:444-448)."""
         if losses_out is None and self._dev_step == self.step and self._graph_ok():
-            return self._train_step_graph(db)
+            db.graph_uses = getattr(db, "graph_uses", 0) + 1
+            if db.graph_uses >= 2:                   # a batch that comes back (resident, or a staging slot): worth a capture
+                return self._train_step_graph(db)
         self.step += 1
         if losses_out is None:
             losses_out = torch.empty(5, dtype=torch.float32, device=self.device)

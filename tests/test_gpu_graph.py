@@ -25,7 +25,7 @@ def test_graph_replay_matches_eager_steps():
         for k, e in enumerate(engs):
             got[k].append(e.train_step(dbs[k][step % 2]).cpu().numpy().copy())
     eager, graphed = engs
-    assert len(graphed._graphs) == 2 and not eager._graphs            # step 1 eager, then one graph per resident batch
+    assert len(graphed._graphs) == 2 and not eager._graphs            # first use of a batch eager, then one graph per resident batch
     assert graphed.step == eager.step == 7
     assert float(graphed.ws("adam.step")[0]) == 7.0
     for step in range(7):
