@@ -20,6 +20,7 @@ from reco_utils.recommender.deeprec.models.sequential.pamrec import PAMRECModel 
 from reco_utils.recommender.deeprec.models.sequential.mmoe import MMoEModel_original  # noqa: E402
 from reco_utils.recommender.deeprec.models.sequential.ple import PLEModel  # noqa: E402
 from reco_utils.recommender.deeprec.models.sequential.sharebottom import ShareBottomModel  # noqa: E402
+from reco_utils.recommender.deeprec.models.sequential.sasrec import SASRecModel  # noqa: E402
 
 FLAGS = flags.FLAGS
 flags.DEFINE_string("dataset", "wechat", "Dataset name.")
@@ -29,7 +30,7 @@ flags.DEFINE_integer("test_num_ngs", 0, "negatives per positive in test_data")
 flags.DEFINE_integer("batch_size", 500, "Batch size.")
 flags.DEFINE_string("save_path", "ranking", "Save path.")
 flags.DEFINE_string("name", "try", "Experiment name.")
-flags.DEFINE_string("model", "PAMREC", "Model name: PAMREC, MMOE_ORIGINAL, PLE or SHAREBOTTOM.")
+flags.DEFINE_string("model", "PAMREC", "Model name: PAMREC, MMOE_ORIGINAL, PLE, SHAREBOTTOM or SASREC.")
 flags.DEFINE_boolean("only_test", False, "Only test and do not train.")
 flags.DEFINE_boolean("write_prediction_to_file", False, "Whether to write prediction to file.")
 flags.DEFINE_integer("is_clip_norm", 1, "Whether to clip gradient norm.")
@@ -58,7 +59,7 @@ flags.DEFINE_string("loss", "cross_entropy_loss", "cross_entropy_loss or softmax
 def get_model(f, model_path, summary_path, user_vocab, item_vocab, cate_vocab):
     # model name -> (class, yaml) as in the reference driver (example/00_quick_start/sequential.py:113-296)
     models = {"PAMREC": (PAMRECModel, "mmoe.yaml"), "MMOE_ORIGINAL": (MMoEModel_original, "mmoe.yaml"), "PLE": (PLEModel, "ple.yaml"),
-              "SHAREBOTTOM": (ShareBottomModel, "sharebottom.yaml")}
+              "SHAREBOTTOM": (ShareBottomModel, "sharebottom.yaml"), "SASREC": (SASRecModel, "sasrec.yaml")}
     if f.model not in models:
         raise NotImplementedError("--model must be one of " + ", ".join(models))
     cls, yaml_name = models[f.model]

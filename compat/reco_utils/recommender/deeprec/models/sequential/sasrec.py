@@ -1,5 +1,1 @@
-class SASRecModel:
-    """Baseline model of the reference, outside the PAMRec hot path."""
-
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("SASRecModel is out of scope of pamrec_b200; only PAMRECModel is implemented")
+from pamrec_b200.models import SASRecModel  # noqa: F401

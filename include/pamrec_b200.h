@@ -59,9 +59,12 @@ enum { PAMREC_TABLES_LOCAL = 0,     /* whole tables on this GPU, direct gather (
  *   PAMREC_MODEL_MMOE         MMoEModel_original   models/sequential/mmoe.py:24-82, 183-337
  *   PAMREC_MODEL_PLE          PLEModel             models/sequential/ple.py:24-60
  *   PAMREC_MODEL_SHAREBOTTOM  ShareBottomModel     models/sequential/sharebottom.py:160-203
- * DIN-style attention pooling (`_attention_fcn`) of the satisfied-only and of the full history against the target item, a
- * mixing layer (MMoE / PLE / none) and two towers; loss = data + regular + 0.5 * auxiliary. */
-enum { PAMREC_MODEL_PAMREC = 0, PAMREC_MODEL_MMOE = 1, PAMREC_MODEL_PLE = 2, PAMREC_MODEL_SHAREBOTTOM = 3 };
+ *   PAMREC_MODEL_SASREC       SASRecModel          models/sequential/sasrec.py:16-96, 230-330
+ * The first three: DIN-style attention pooling (`_attention_fcn`) of the satisfied-only and of the full history against the target
+ * item, a mixing layer (MMoE / PLE / none) and two towers; loss = data + regular + 0.5 * auxiliary.  SASRec: the satisfied-only
+ * history + a position table through two 20-wide self-attention blocks with dense Q / K / V, the state at the last satisfied
+ * position | target into one tower; loss = data + regular (single task; no user tables: the ulong / ushort buffers are unused). */
+enum { PAMREC_MODEL_PAMREC = 0, PAMREC_MODEL_MMOE = 1, PAMREC_MODEL_PLE = 2, PAMREC_MODEL_SHAREBOTTOM = 3, PAMREC_MODEL_SASREC = 4 };
 
 /* hparams.loss */
 enum { PAMREC_LOSS_XENT = 0,        /* "cross_entropy_loss" (config/mmoe.yaml)                                  */
@@ -111,7 +114,7 @@ typedef struct PamrecBatch {
   int32_t global_batch;               /* rows of the whole global batch over all ranks; 0 = batch * world_size.
                                          batch may be 0 on a rank that only takes part in the collectives   */
   /* satisfied-only copy of the history, compacted to the left (io/sequential_iterator.py:1069-1103): read by the sibling
-   * models only (PAMREC_MODEL_MMOE / _PLE / _SHAREBOTTOM, mmoe.py:199-201); may be NULL for PAMREC_MODEL_PAMREC */
+   * models only (PAMREC_MODEL_MMOE / _PLE / _SHAREBOTTOM / _SASREC, mmoe.py:199-201, sasrec.py:55-64); may be NULL for PAMREC_MODEL_PAMREC */
   const int32_t* satisfied_item_history; /* [B,T]                                              */
   const int32_t* satisfied_cate_history; /* [B,T]                                              */
   const int32_t* satisfied_mask;         /* [B,T] 1 = real position                            */

@@ -266,10 +266,11 @@ def sasrec_init(spec, bn_spec, seed=8, init_value=0.01):
     return {n: params[n] for n, _, _, _ in spec}, bn_state
 
 
-def sasrec_forward(p, bn_state, batch, training, dtype=torch.float64, tower_sizes=(100, 64), rows=None):
+def sasrec_forward(p, bn_state, batch, training, dtype=torch.float64, tower_sizes=(100, 64), rows=None, relu_masks=None):
     """rows: optional pre-gathered lookups (sat_item, sat_cate, tgt_item, tgt_cate, pos [B, T, 20]) so that a caller can observe
-    their per-lookup gradients; by default they are read from the tables here."""
-    ctx = O._Ctx(p, bn_state, training, dtype)
+    their per-lookup gradients; by default they are read from the tables here.  relu_masks: see pamrec_oracle._act (keys
+    "blk{b}.ffn" for the point-wise FFN, the BN scopes of the tower)."""
+    ctx = O._Ctx(p, bn_state, training, dtype, relu_masks=relu_masks)
     emb = "sequential/embedding/"
     idx = lambda k: torch.as_tensor(np.asarray(batch[k])).long()
     mask = idx("satisfied_mask")
@@ -279,6 +280,7 @@ def sasrec_forward(p, bn_state, batch, training, dtype=torch.float64, tower_size
                 "tgt_item": p[emb + "item_embedding"][idx("items")], "tgt_cate": p[emb + "cate_embedding"][idx("cates")],
                 "pos": p[emb + "position_embedding"][None].expand(mask.shape[0], -1, -1)}   # SAS:39-44: tile(range(T)) lookup
     seq = torch.cat([rows["sat_item"], rows["sat_cate"]], -1) + rows["pos"]                # SAS:61-64
+    ctx.t["x0"] = seq
     target = torch.cat([rows["tgt_item"], rows["tgt_cate"]], -1)
     pad = float(-(2 ** 32) + 1)
     for b in range(2):
@@ -290,16 +292,17 @@ def sasrec_forward(p, bn_state, batch, training, dtype=torch.float64, tower_size
         s = torch.where(mask[:, None, :] == 0, torch.full_like(s, pad), s)                # SAS:288-293 key mask only
         y = torch.softmax(s, -1) @ V + q_in                                               # SAS:318-324 residual on the queries
         f = O._ln(y, p[pre + "ln_1/Variable"], p[pre + "ln_1/Variable_1"])
-        hid = torch.relu(f @ p[pre + "multihead_attention/conv1d/kernel"][0] + p[pre + "multihead_attention/conv1d/bias"])
+        hid = O._act(ctx, f @ p[pre + "multihead_attention/conv1d/kernel"][0] + p[pre + "multihead_attention/conv1d/bias"], f"blk{b}.ffn")
         seq = hid @ p[pre + "multihead_attention/conv1d_1/kernel"][0] + p[pre + "multihead_attention/conv1d_1/bias"] + f   # SAS:127-141
-        ctx.t[f"blk{b}.out"] = seq
+        ctx.t[f"blk{b}.qin"], ctx.t[f"blk{b}.Q"], ctx.t[f"blk{b}.K"], ctx.t[f"blk{b}.V"] = q_in, Q, K, V
+        ctx.t[f"blk{b}.y"], ctx.t[f"blk{b}.f"], ctx.t[f"blk{b}.out"] = y, f, seq
     length = mask.sum(1)
     # SAS:72-78 reads seq[b, length - 1]: index -1 for a row without any satisfied item, which tf.gather_nd rejects on CPU and
     # answers with zeros on GPU.  The iterator can produce such rows; the restatement follows the GPU behaviour.
     last = torch.clamp(length - 1, min=0)
     final = seq[torch.arange(seq.shape[0]), last] * (length > 0).to(seq.dtype)[:, None]
     ctx.t["final_state"] = final
-    logit = O._mlp(ctx, torch.cat([final, target], -1), "sequential/logit_fcn", tower_sizes, out=True)
+    logit = O._mlp(ctx, torch.cat([final, target], -1), "sequential/logit_fcn", tower_sizes, out=True, tag="tower0")
     ctx.t["logits"] = logit
     ctx.t["pred"] = torch.sigmoid(logit)
     return ctx
@@ -361,7 +364,7 @@ class SiblingOracleModel(O.OracleModel):
 
     def _forward(self, p, batch, training, rows=None, relu_masks=None):
         if self.model == "sasrec":
-            return sasrec_forward(p, self.bn_state, batch, training, self.dtype, rows=rows, **self.sizes)
+            return sasrec_forward(p, self.bn_state, batch, training, self.dtype, rows=rows, relu_masks=relu_masks, **self.sizes)
         return forward(self.model, p, self.bn_state, batch, training, self.dtype, rows=rows, relu_masks=relu_masks, **self.sizes)
 
     def _losses(self, ctx, batch, rows):

@@ -12,7 +12,7 @@ SEG_L2, SEG_POS, SEG_DEAD = 1, 2, 4
 ADAM_DENSE_EXACT, ADAM_LAZY = 0, 1
 TABLES_LOCAL, TABLES_SHARDED, TABLES_REPLICATED = 0, 1, 2
 LOSS_XENT, LOSS_SOFTMAX = 0, 1
-MODEL_PAMREC, MODEL_MMOE, MODEL_PLE, MODEL_SHAREBOTTOM = 0, 1, 2, 3
+MODEL_PAMREC, MODEL_MMOE, MODEL_PLE, MODEL_SHAREBOTTOM, MODEL_SASREC = 0, 1, 2, 3, 4
 COMM_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 GROUP = 5

@@ -172,7 +172,7 @@ int pamrec_create(const PamrecConfig* cfg, PamrecHandle* out) {
     if (cfg->n_cates > big) big = cfg->n_cates;
     if (((big + world - 1) / world) * world >= ((int64_t)1 << 31)) return -7;
   }
-  if (cfg->model_kind < PAMREC_MODEL_PAMREC || cfg->model_kind > PAMREC_MODEL_SHAREBOTTOM) return -9;
+  if (cfg->model_kind < PAMREC_MODEL_PAMREC || cfg->model_kind > PAMREC_MODEL_SASREC) return -9;
   if (cfg->model_kind != PAMREC_MODEL_PAMREC && (world != 1 || cfg->table_mode != PAMREC_TABLES_LOCAL || cfg->loss_kind != PAMREC_LOSS_XENT))
     return -9;                                                               // sibling models: one GPU, whole tables, cross entropy
   PamrecHandle h = new PamrecHandle_();
@@ -335,7 +335,8 @@ int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
   if (h->sharded() || h->sibling()) {
     cudaMemsetAsync(h->wi("sp.item.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_items) * 4, st);
     cudaMemsetAsync(h->wi("sp.cate.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_cates) * 4, st);
-    cudaMemsetAsync(h->wi("sp.user.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_users) * 4, st);
+    if (h->cfg.model_kind != PAMREC_MODEL_SASREC)
+      cudaMemsetAsync(h->wi("sp.user.slot"), 0xFF, (size_t)h->L.rows_of(h->cfg.n_users) * 4, st);
   } else {
     cudaMemsetAsync(h->wi("sp2.slot"), 0xFF, ((size_t)h->cfg.n_items + h->cfg.n_cates + h->cfg.n_users) * 4, st);
   }
@@ -361,7 +362,8 @@ static int check_batch(PamrecHandle h, const PamrecBatch* b, bool training) {
     if (!b->satisfied_item_history || !b->satisfied_cate_history || !b->satisfied_mask || !b->item_history || !b->item_cate_history ||
         !b->mask || !b->items || !b->cates)
       return fail(h, "null batch field (the sibling models also read satisfied_item_history / satisfied_cate_history / satisfied_mask)");
-    if (training && (!b->users || !b->labels_satisfied || !b->labels_play)) return fail(h, "null label field");
+    const bool sas = h->cfg.model_kind == PAMREC_MODEL_SASREC;
+    if (training && (!b->labels_satisfied || (!sas && (!b->users || !b->labels_play)))) return fail(h, "null label field");
     return 0;
   }
   if (training && b->batch % PAMREC_GROUP != 0)
@@ -573,11 +575,14 @@ static void set_in_bn_dw(DenseDwP& p, const BnSet& s) { p.in_stat = s.stat; p.in
 static int sib_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pred_out, cudaStream_t st);
 static int sib_backward(PamrecHandle h, const PamrecBatch* b, cudaStream_t st);
 static int sib_apply(PamrecHandle h, const PamrecBatch* b, int64_t step, cudaStream_t st);
+static int sas_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pred_out, cudaStream_t st);
+static int sas_backward(PamrecHandle h, const PamrecBatch* b, cudaStream_t st);
 
 int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pred_out, void* stream) {
   if (int rc = check_batch(h, b, training != 0)) return rc;
   ProfBind _pb(h);
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->cfg.model_kind == PAMREC_MODEL_SASREC) return sas_forward(h, b, training, pred_out, st);
   if (h->sibling()) return sib_forward(h, b, training, pred_out, st);
   const Layout& L = h->L;
   const int B = b->batch, T = h->cfg.max_seq_len, N = B * T;
@@ -820,6 +825,7 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
   if (int rc = check_batch(h, b, true)) return rc;
   ProfBind _pb(h);
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->cfg.model_kind == PAMREC_MODEL_SASREC) return sas_backward(h, b, st);
   if (h->sibling()) return sib_backward(h, b, st);
   const Layout& L = h->L;
   const int B = b->batch, T = h->cfg.max_seq_len, N = B * T;

@@ -9,6 +9,7 @@
 static SparseTable sib_table(PamrecHandle h, int which /* 0 item 1 cate 2 user_long 3 user_short */) {
   SparseTable t;
   memset(&t, 0, sizeof t);
+  if (which >= 2 && h->cfg.model_kind == PAMREC_MODEL_SASREC) return t;
   const std::string p = which == 0 ? "sp.item." : (which == 1 ? "sp.cate." : "sp.user.");
   t.keys = h->wi(p + "keys"); t.idx = h->wi(p + "idx"); t.skeys = h->wi(p + "skeys"); t.sidx = h->wi(p + "sidx");
   t.uidx = h->wi(p + "uidx"); t.ukeys = h->wi(p + "ukeys"); t.slot = h->wi(p + "slot");
@@ -35,7 +36,8 @@ static int sib_plans(PamrecHandle h, const PamrecBatch* b, cudaStream_t st) {
   SparseTable ti = sib_table(h, 0), tc = sib_table(h, 1), tu = sib_table(h, 2);
   rc |= launch_sparse_plan(ti, h->wi("sib.ids_item"), b->items, 2 * N, B, 1, 0, ti.n_rows, true, tmp, tmp_bytes, st);
   rc |= launch_sparse_plan(tc, h->wi("sib.ids_cate"), b->cates, 2 * N, B, 1, 0, tc.n_rows, true, tmp, tmp_bytes, st);
-  rc |= launch_sparse_plan(tu, b->users, nullptr, B, 0, 1, 0, tu.n_rows, true, tmp, tmp_bytes, st);
+  if (h->cfg.model_kind != PAMREC_MODEL_SASREC)      // SASRec has no user tables (sasrec_param_spec)
+    rc |= launch_sparse_plan(tu, b->users, nullptr, B, 0, 1, 0, tu.n_rows, true, tmp, tmp_bytes, st);
   return rc;
 }
 
@@ -137,7 +139,7 @@ static int sib_forward(PamrecHandle h, const PamrecBatch* b, int training, float
     set_in_bn(to, bn[BN_T1]);
     launch_dense_fwd(to, st);
   }
-  if (pred_out) launch_sib_pred(h->wf("logits"), pred_out, B, st);
+  if (pred_out) launch_sib_pred(h->wf("logits"), pred_out, B, 2, st);
   return check_cuda(h, "forward");
 }
 
@@ -151,7 +153,7 @@ static int sib_backward(PamrecHandle h, const PamrecBatch* b, cudaStream_t st) {
   cudaMemsetAsync(h->wd("loss_acc"), 0, 8 * sizeof(double), st);
   cudaMemsetAsync(h->wd("sp_normsq"), 0, 8 * sizeof(double), st);
   cudaMemsetAsync(h->wd("bn.bsums"), 0, (size_t)L.ws[L.ws_index.at("bn.bsums")].numel * sizeof(double), st);
-  launch_sib_loss(h->wf("logits"), b->labels_satisfied, b->labels_play, h->wf("d_logits"), h->wd("loss_acc"), B, 0.5f, st);
+  launch_sib_loss(h->wf("logits"), b->labels_satisfied, b->labels_play, h->wf("d_logits"), h->wd("loss_acc"), B, 0.5f, 2, st);
   auto grad_of = [&](int id, const float* Z, double cnt) {
     BnGrad g; g.Z = Z; g.stat = bn[id].stat; g.gamma = bn[id].gamma; g.beta = bn[id].beta; g.bsums = bn[id].bsums; g.count = cnt;
     return g;
@@ -320,7 +322,7 @@ static int sib_apply(PamrecHandle h, const PamrecBatch* b, int64_t step, cudaStr
     launch_sparse_adam(tab, 2 * N + B, c.sparse_adam_mode, c.embed_l2, lr_t, c.beta1, c.beta2, c.epsilon, c.max_grad_norm, c.is_clip_norm, st);
     launch_slot_reset(tab, 2 * N + B, st);
   }
-  {
+  if (c.model_kind != PAMREC_MODEL_SASREC) {
     SparseTable tl = sib_table(h, 2), ts = sib_table(h, 3);
     launch_sparse_l2norm(tl, B, c.embed_l2, reg, st);
     launch_sparse_l2norm(ts, B, c.embed_l2, reg, st);
@@ -336,4 +338,141 @@ static int sib_apply(PamrecHandle h, const PamrecBatch* b, int64_t step, cudaStr
                     c.is_clip_norm, st);
   launch_finish_losses(h->wd("loss_acc"), h->wf("losses"), nullptr, c.embed_l2, h->wd("sp_normsq"), st);
   return check_cuda(h, "apply_gradients");
+}
+
+// ================================================================================================ SASRecModel
+// models/sequential/sasrec.py:16-96 (_build_sasrec), :230-330 (multihead_attention with dense Q / K / V), :100-141 (feedforward);
+// kernels_sasrec.cu.  The sparse backward is the siblings': keys = satisfied-only ids (the lookups), full-history ids (zero gradient
+// rows: they only make the row an L2 row, sequential_base_model.py:640-664), target ids.
+static int sas_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pred_out, cudaStream_t st) {
+  const Layout& L = h->L;
+  const int B = b->batch, T = h->cfg.max_seq_len;
+  const int64_t N = (int64_t)B * T;
+  const double cntB = (double)B;
+  BnSet* bn = h->bn;
+  float* hb = h->wf("sib.h");
+  launch_sib_gather(b->satisfied_item_history, b->satisfied_cate_history, b->item_history, b->item_cate_history, b->items, b->cates,
+                    h->buf.item_w, h->buf.cate_w, hb, h->wf("tgt"), training ? h->wi("sib.ids_item") : nullptr,
+                    training ? h->wi("sib.ids_cate") : nullptr, B, T, st);
+  if (training) {
+    launch_sib_has0(b->item_history, b->item_cate_history, b->items, b->cates, B, T, h->wi("sib.has0"), st);
+    int prc = 0;
+    h->fork(st, [&](cudaStream_t s2) {
+      prc = sib_plans(h, b, s2);
+      cudaEventRecord(h->ev_plan, s2);
+    });
+    if (prc) return fail(h, "cub sort failed");
+    h->plan_for = b->item_history; h->plan_rows = B;
+  } else {
+    launch_bn_eval_stat(bn[BN_T0], st);
+    launch_bn_eval_stat(bn[BN_T1], st);
+  }
+  launch_sas_embed(hb, h->P(L.pos), h->wf("x0"), B, T, st);
+  const float* xin = h->wf("x0");
+  for (int k = 0; k < 2; ++k) {
+    const Layout::SasBlock& o = L.sas[k];
+    const std::string p = "blk" + std::to_string(k) + ".";
+    launch_sas_proj_fwd(xin, h->P(o.wqkv), h->P(o.bqkv), h->P(o.ln_a_beta), h->P(o.ln_a_gamma), h->wf(p + "xq"), h->wf(p + "qkv"), N, st);
+    launch_sas_attn_fwd(h->wf(p + "qkv"), h->wf(p + "xq"), b->satisfied_mask, h->wf(p + "y"), h->wf(p + "ml"), B, T, st);
+    launch_sas_ffn_fwd(h->wf(p + "y"), h->P(o.w1), h->P(o.b1), h->P(o.w2), h->P(o.b2), h->P(o.ln_b_beta), h->P(o.ln_b_gamma), h->wf(p + "f"),
+                       h->wf(p + "hpre"), h->wf(p + "out"), N, st);
+    xin = h->wf(p + "out");
+  }
+  launch_sas_final_fwd(xin, b->satisfied_mask, h->wf("tgt"), h->wf("u"), B, T, st);
+  {
+    DenseP t0 = dense_p(h->wf("u"), 40, B, 1, 40, 100, h->P(L.tower.w0), 0, h->P(L.tower.b0), 0, h->wf("zt0"), 100);
+    t0.out_sums = training ? bn[BN_T0].sums : nullptr;
+    launch_dense_fwd(t0, st);
+    if (training) launch_bn_finalize(bn[BN_T0], cntB, st);
+    DenseP t1 = dense_p(h->wf("zt0"), 100, B, 1, 100, 64, h->P(L.tower.w1), 0, h->P(L.tower.b1), 0, h->wf("zt1"), 64);
+    set_in_bn(t1, bn[BN_T0]);
+    t1.out_sums = training ? bn[BN_T1].sums : nullptr;
+    launch_dense_fwd(t1, st);
+    if (training) launch_bn_finalize(bn[BN_T1], cntB, st);
+    DenseP to = dense_p(h->wf("zt1"), 64, B, 1, 64, 1, h->P(L.tower.wout), 0, h->P(L.tower.bout), 0, h->wf("logits"), 1);
+    set_in_bn(to, bn[BN_T1]);
+    launch_dense_fwd(to, st);
+  }
+  if (pred_out) launch_sib_pred(h->wf("logits"), pred_out, B, 1, st);
+  return check_cuda(h, "forward");
+}
+
+static int sas_backward(PamrecHandle h, const PamrecBatch* b, cudaStream_t st) {
+  const Layout& L = h->L;
+  const int B = b->batch, T = h->cfg.max_seq_len;
+  const int64_t N = (int64_t)B * T;
+  const double cntB = (double)B;
+  BnSet* bn = h->bn;
+  const float* Pb = h->buf.dense_param;
+  cudaMemsetAsync(h->buf.dense_grad, 0, (size_t)L.dense_numel * 4, st);
+  cudaMemsetAsync(h->wd("loss_acc"), 0, 8 * sizeof(double), st);
+  cudaMemsetAsync(h->wd("sp_normsq"), 0, 8 * sizeof(double), st);
+  cudaMemsetAsync(h->wd("bn.bsums"), 0, (size_t)L.ws[L.ws_index.at("bn.bsums")].numel * sizeof(double), st);
+  launch_sib_loss(h->wf("logits"), b->labels_satisfied, nullptr, h->wf("d_logits"), h->wd("loss_acc"), B, 0.f, 1, st);
+  auto grad_of = [&](int id, const float* Z, double cnt) {
+    BnGrad g; g.Z = Z; g.stat = bn[id].stat; g.gamma = bn[id].gamma; g.beta = bn[id].beta; g.bsums = bn[id].bsums; g.count = cnt;
+    return g;
+  };
+  auto out_of = [&](int id, const float* Z) {
+    BnGradOut o; o.Z = Z; o.stat = bn[id].stat; o.gamma = bn[id].gamma; o.beta = bn[id].beta; o.bsums = bn[id].bsums;
+    return o;
+  };
+  auto dw_bn = [&](DenseDwP& w, int id, const float* Z, double cnt) {
+    w.g = grad_of(id, Z, cnt); w.g_dgamma = bn[id].dgamma; w.g_dbeta = bn[id].dbeta; w.g_C = bn[id].C; w.g_scale = 1.0f;
+  };
+  auto side_dw = [&](const DenseDwP& w) { h->fork(st, [&](cudaStream_t s2) { launch_dense_dw(w, s2); }); };
+  // ---- tower (sequential_base_model.py:76-79 -> _fcn_net)
+  {
+    DenseDwP w = dw_p(h->wf("zt1"), 64, B, 1, 64, 1, h->wf("d_logits"), 1, h->G(L.tower.wout), 0, h->G(L.tower.bout), 0);
+    set_in_bn_dw(w, bn[BN_T1]);
+    side_dw(w);
+    DenseDxP dx = dx_p(h->wf("d_logits"), 1, B, 64, Pb, h->wf("d_t1"), 64, 0);
+    dx_add(dx, 0, 0, 0, L.tower.wout, 1);
+    dx.o = out_of(BN_T1, h->wf("zt1"));
+    launch_dense_dx(dx, st);
+    DenseDwP w1 = dw_p(h->wf("zt0"), 100, B, 1, 100, 64, h->wf("d_t1"), 64, h->G(L.tower.w1), 0, h->G(L.tower.b1), 0);
+    set_in_bn_dw(w1, bn[BN_T0]);
+    dw_bn(w1, BN_T1, h->wf("zt1"), cntB);
+    side_dw(w1);
+    DenseDxP x1 = dx_p(h->wf("d_t1"), 64, B, 100, Pb, h->wf("d_t0"), 100, 0);
+    dx_add(x1, 0, 0, 0, L.tower.w1, 64);
+    x1.g = grad_of(BN_T1, h->wf("zt1"), cntB);
+    x1.o = out_of(BN_T0, h->wf("zt0"));
+    launch_dense_dx(x1, st);
+    DenseDwP w0 = dw_p(h->wf("u"), 40, B, 1, 40, 100, h->wf("d_t0"), 100, h->G(L.tower.w0), 0, h->G(L.tower.b0), 0);
+    dw_bn(w0, BN_T0, h->wf("zt0"), cntB);
+    side_dw(w0);
+    DenseDxP x0 = dx_p(h->wf("d_t0"), 100, B, 40, Pb, h->wf("d_u"), 40, 0);
+    dx_add(x0, 0, 0, 0, L.tower.w0, 100);
+    x0.g = grad_of(BN_T0, h->wf("zt0"), cntB);
+    launch_dense_dx(x0, st);
+  }
+  float* g_a = h->wf("sas.g_a");
+  float* g_b = h->wf("sas.g_b");
+  float* dh = h->wf("sib.dh");
+  launch_sas_final_bwd(h->wf("d_u"), b->satisfied_mask, g_a, h->wf("d_tgt_total"), B, T, st);
+  // ---- encoder blocks (gradient of block 1's output is in g_a)
+  for (int k = 1; k >= 0; --k) {
+    const Layout::SasBlock& o = L.sas[k];
+    const std::string p = "blk" + std::to_string(k) + ".";
+    const float* gout = k == 1 ? g_a : g_b;
+    float* gin = k == 1 ? g_b : dh;                          // block 0's input gradient = rows of the satisfied lookups (+ position rows)
+    launch_sas_ffn_bwd(h->wf(p + "y"), h->wf(p + "hpre"), gout, h->P(o.w1), h->P(o.w2), h->P(o.ln_b_gamma), h->wf("sas.hid"),
+                       h->wf("sas.d_hpre"), h->wf("sas.d_y"), h->G(o.ln_b_gamma), h->G(o.ln_b_beta), N, st);
+    // weight gradients on the main stream: sas.hid / sas.d_hpre / sas.d_qkv are reused by the next block
+    launch_dense_dw(dw_p(h->wf("sas.hid"), kE, (int)N, 1, kE, kE, gout, kE, h->G(o.w2), 0, h->G(o.b2), 0), st);
+    launch_dense_dw(dw_p(h->wf(p + "f"), kE, (int)N, 1, kE, kE, h->wf("sas.d_hpre"), kE, h->G(o.w1), 0, h->G(o.b1), 0), st);
+    launch_sas_attn_bwd(h->wf(p + "qkv"), h->wf(p + "xq"), h->wf(p + "y"), h->wf("sas.d_y"), h->wf(p + "ml"), b->satisfied_mask,
+                        h->wf("sas.d_qkv"), h->wf("sas.dq"), B, T, st);
+    launch_sas_proj_bwd(h->wf(p + "xq"), h->wf("sas.d_qkv"), h->wf("sas.d_y"), h->P(o.wqkv), h->P(o.ln_a_gamma), gin, h->G(o.ln_a_gamma),
+                        h->G(o.ln_a_beta), N, st);
+    DenseDwP wq = dw_p(h->wf(p + "xq"), 2 * kE, (int)N, 3, kE, kE, h->wf("sas.d_qkv"), 3 * kE, h->G(o.wqkv), kE * kE, h->G(o.bqkv), kE);
+    wq.x_off[0] = 0; wq.x_off[1] = kE; wq.x_off[2] = kE;
+    for (int g = 0; g < 3; ++g) wq.z_off[g] = g * kE;
+    launch_dense_dw(wq, st);
+  }
+  launch_sas_pos_bwd(dh, h->G(L.pos), h->wd("sp_normsq") + 4, B, T, st);
+  cudaMemsetAsync(dh + N * kE, 0, (size_t)N * kE * sizeof(float), st);      // the full-history "lookups" carry no gradient
+  h->join(st);
+  return check_cuda(h, "backward");
 }

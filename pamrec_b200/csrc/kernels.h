@@ -172,9 +172,27 @@ void launch_sib_mix_fwd(const float* ZE1, const float* ZG1, const BnSet& e1, con
                         const int sel[2][5], int B, cudaStream_t st);
 void launch_sib_mix_bwd(const float* ZE1, const float* ZG1, const BnSet& e1, const BnSet& g1, const float* dU, float* dE1, float* dG1,
                         float* dTgt, int n_expert, const int sel[2][5], int B, cudaStream_t st);
+// heads = 2: logits [B,2] (satisfied label, play label x aux_w); heads = 1: logits [B,1], data loss only (SASRec)
 void launch_sib_loss(const float* logits, const float* y_sat, const float* y_play, float* d_logits, double* loss_acc, int B, float aux_w,
-                     cudaStream_t st);
-void launch_sib_pred(const float* logits, float* pred, int B, cudaStream_t st);
+                     int heads, cudaStream_t st);
+void launch_sib_pred(const float* logits, float* pred, int B, int heads, cudaStream_t st);
+
+// ---- kernels_sasrec.cu (SASRecModel: two 20-wide self-attention blocks with dense Q / K / V)
+void launch_sas_embed(const float* h, const float* pos, float* x0, int B, int T, cudaStream_t st);
+void launch_sas_proj_fwd(const float* X, const float* W, const float* bias, const float* ln_beta, const float* ln_gamma, float* XQ,
+                         float* QKV, int64_t N, cudaStream_t st);
+void launch_sas_proj_bwd(const float* XQ, const float* dQKV, const float* dY, const float* W, const float* ln_gamma, float* dX,
+                         float* g_gamma, float* g_beta, int64_t N, cudaStream_t st);
+void launch_sas_attn_fwd(const float* QKV, const float* XQ, const int* mask, float* Y, float* ML, int B, int T, cudaStream_t st);
+void launch_sas_attn_bwd(const float* QKV, const float* XQ, const float* Y, const float* dY, const float* ML, const int* mask, float* dQKV,
+                         float* Dq, int B, int T, cudaStream_t st);
+void launch_sas_ffn_fwd(const float* Y, const float* W1, const float* b1, const float* W2, const float* b2, const float* ln_beta,
+                        const float* ln_gamma, float* F, float* HPRE, float* OUT, int64_t N, cudaStream_t st);
+void launch_sas_ffn_bwd(const float* Y, const float* HPRE, const float* dOUT, const float* W1, const float* W2, const float* ln_gamma,
+                        float* HID, float* DHPRE, float* dY, float* g_gamma, float* g_beta, int64_t N, cudaStream_t st);
+void launch_sas_final_fwd(const float* SEQ, const int* mask, const float* tgt, float* U, int B, int T, cudaStream_t st);
+void launch_sas_final_bwd(const float* dU, const int* mask, float* dSEQ, float* dTgt, int B, int T, cudaStream_t st);
+void launch_sas_pos_bwd(const float* dX0, float* dPos, double* normsq, int B, int T, cudaStream_t st);
 
 // ---- kernels_p2p.cu (small all-reduces through NVLink peer mailboxes)
 constexpr int kP2PMaxDoubles = 2048;     // payload capacity of one mailbox slot (expert + gate layer-0 sums: 1256)

@@ -328,18 +328,20 @@ __device__ __forceinline__ float sib_sigmoid(float x) { return 1.0f / (1.0f + ex
 __device__ __forceinline__ float sib_xent(float x, float y) { return fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x))); }
 __global__ void __launch_bounds__(1024)
 k_sib_loss(const float* __restrict__ logits, const float* __restrict__ y_sat, const float* __restrict__ y_play,
-           float* __restrict__ d_logits, double* __restrict__ loss_acc, int B, float aux_w) {
+           float* __restrict__ d_logits, double* __restrict__ loss_acc, int B, float aux_w, int heads) {
   __shared__ double sh[2][32];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const float inv_b = 1.0f / (float)B;
   double a0 = 0.0, a1 = 0.0;
   for (int b = tid; b < B; b += blockDim.x) {
-    const float x0 = logits[2 * b], x1 = logits[2 * b + 1];
-    const float y0 = y_sat[b], y1 = y_play[b];
+    const float x0 = logits[heads * b], y0 = y_sat[b];
     a0 += (double)sib_xent(x0, y0);
-    a1 += (double)sib_xent(x1, y1);
-    d_logits[2 * b] = (sib_sigmoid(x0) - y0) * inv_b;
-    d_logits[2 * b + 1] = aux_w * (sib_sigmoid(x1) - y1) * inv_b;
+    d_logits[heads * b] = (sib_sigmoid(x0) - y0) * inv_b;
+    if (heads == 2) {
+      const float x1 = logits[2 * b + 1], y1 = y_play[b];
+      a1 += (double)sib_xent(x1, y1);
+      d_logits[2 * b + 1] = aux_w * (sib_sigmoid(x1) - y1) * inv_b;
+    }
   }
   a0 = warp_sum_d(a0); a1 = warp_sum_d(a1);
   if (lane == 0) { sh[0][w] = a0; sh[1][w] = a1; }
@@ -353,17 +355,17 @@ k_sib_loss(const float* __restrict__ logits, const float* __restrict__ y_sat, co
   }
 }
 void launch_sib_loss(const float* logits, const float* y_sat, const float* y_play, float* d_logits, double* loss_acc, int B, float aux_w,
-                     cudaStream_t st) { PAMREC_PROF("sib_loss", 1, st);
-  k_sib_loss<<<1, 1024, 0, st>>>(logits, y_sat, y_play, d_logits, loss_acc, B, aux_w);
+                     int heads, cudaStream_t st) { PAMREC_PROF("sib_loss", 1, st);
+  k_sib_loss<<<1, 1024, 0, st>>>(logits, y_sat, y_play, d_logits, loss_acc, B, aux_w, heads);
 }
 
-__global__ void k_sib_pred(const float* __restrict__ logits, float* __restrict__ pred, int B) {
+__global__ void k_sib_pred(const float* __restrict__ logits, float* __restrict__ pred, int B, int heads) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) pred[b] = sib_sigmoid(logits[2 * b]);
+  if (b < B) pred[b] = sib_sigmoid(logits[heads * b]);
 }
-void launch_sib_pred(const float* logits, float* pred, int B, cudaStream_t st) { PAMREC_PROF("sigmoid", 1, st);
+void launch_sib_pred(const float* logits, float* pred, int B, int heads, cudaStream_t st) { PAMREC_PROF("sigmoid", 1, st);
   if (B == 0) return;
-  k_sib_pred<<<(B + 255) / 256, 256, 0, st>>>(logits, pred, B);
+  k_sib_pred<<<(B + 255) / 256, 256, 0, st>>>(logits, pred, B, heads);
 }
 
 }  // namespace pamrec

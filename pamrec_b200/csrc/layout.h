@@ -244,10 +244,93 @@ struct Layout {
     (void)c;
   }
 
+  // SASRecModel (oracle/siblings_oracle.py:sasrec_param_spec has the same inventory, by TF name)
+  struct SasBlock { int64_t ln_a_beta, ln_a_gamma, wqkv, bqkv, ln_b_beta, ln_b_gamma, w1, b1, w2, b2; };
+  SasBlock sas[2];
+  void build_sasrec(const PamrecConfig& c) {
+    const int L2 = PAMREC_SEG_L2;
+    const int64_t B = Bcap, N = (int64_t)Bcap * T;
+    pos = add_dense("sequential/embedding/position_embedding", {T, kE}, PAMREC_SEG_POS);       // sasrec.py:29-34
+    for (int b = 0; b < 2; ++b) {
+      const std::string p = "sequential/sasrec/num_blocks_" + std::to_string(b) + "/";
+      SasBlock& o = sas[b];
+      // Q, K, V kernels adjacent (one grouped weight-gradient GEMM), then their biases
+      o.wqkv = add_dense(p + "self_attention/dense/kernel", {kE, kE}, L2);
+      add_dense(p + "self_attention/dense_1/kernel", {kE, kE}, L2);
+      add_dense(p + "self_attention/dense_2/kernel", {kE, kE}, L2);
+      o.bqkv = add_dense(p + "self_attention/dense/bias", {kE}, L2);
+      add_dense(p + "self_attention/dense_1/bias", {kE}, L2);
+      add_dense(p + "self_attention/dense_2/bias", {kE}, L2);
+      o.ln_a_beta = add_dense(p + "ln/Variable", {kE}, L2);
+      o.ln_a_gamma = add_dense(p + "ln/Variable_1", {kE}, L2);
+      o.w1 = add_dense(p + "multihead_attention/conv1d/kernel", {1, kE, kE}, L2);
+      o.w2 = add_dense(p + "multihead_attention/conv1d_1/kernel", {1, kE, kE}, L2);
+      o.b1 = add_dense(p + "multihead_attention/conv1d/bias", {kE}, L2);
+      o.b2 = add_dense(p + "multihead_attention/conv1d_1/bias", {kE}, L2);
+      o.ln_b_beta = add_dense(p + "ln_1/Variable", {kE}, L2);
+      o.ln_b_gamma = add_dense(p + "ln_1/Variable_1", {kE}, L2);
+    }
+    for (int i = 0; i < BN_COUNT; ++i) bnoff[i] = BnOff{0, 0, 0, 0, 0};
+    tower_in = 2 * kE;
+    tower = add_mlp({"sequential/logit_fcn"}, {L2}, tower_in, 100, 64, true, &bnoff[BN_T0], &bnoff[BN_T1]);   // sequential_base_model.py:76-79
+    // ---- workspace
+    add_ws("sib.ids_item", PAMREC_I32, {2, N});      // satisfied-only ids (looked up), then the full-history ids (L2 rows only)
+    add_ws("sib.ids_cate", PAMREC_I32, {2, N});
+    add_ws("sib.h", PAMREC_F32, {2, N, kE});
+    add_ws("tgt", PAMREC_F32, {B, kE});
+    add_ws("x0", PAMREC_F32, {N, kE});               // history token + position row
+    for (int b = 0; b < 2; ++b) {
+      const std::string p = "blk" + std::to_string(b) + ".";
+      add_ws(p + "xq", PAMREC_F32, {N, 2 * kE});     // LN(x) | x
+      add_ws(p + "qkv", PAMREC_F32, {N, 3 * kE});
+      add_ws(p + "ml", PAMREC_F32, {N, 2});
+      add_ws(p + "y", PAMREC_F32, {N, kE});
+      add_ws(p + "f", PAMREC_F32, {N, kE});          // LN_1(y)
+      add_ws(p + "hpre", PAMREC_F32, {N, kE});       // f W1 + b1 (the ReLU pattern of the point-wise FFN)
+      add_ws(p + "out", PAMREC_F32, {N, kE});
+    }
+    add_ws("u", PAMREC_F32, {B, 2 * kE});            // final state | target
+    add_ws("zt0", PAMREC_F32, {B, 100});
+    add_ws("zt1", PAMREC_F32, {B, 64});
+    add_ws("logits", PAMREC_F32, {B, 1});
+    add_ws("losses", PAMREC_F32, {8});
+    add_ws("loss_acc", PAMREC_F64, {8});
+    add_ws("d_logits", PAMREC_F32, {B, 1});
+    add_ws("d_t1", PAMREC_F32, {B, 64});
+    add_ws("d_t0", PAMREC_F32, {B, 100});
+    add_ws("d_u", PAMREC_F32, {B, 2 * kE});
+    add_ws("d_tgt_total", PAMREC_F32, {B, kE});
+    add_ws("sas.g_a", PAMREC_F32, {N, kE});          // gradient of a block's output (ping)
+    add_ws("sas.g_b", PAMREC_F32, {N, kE});          // ... (pong)
+    add_ws("sas.hid", PAMREC_F32, {N, kE});
+    add_ws("sas.d_hpre", PAMREC_F32, {N, kE});
+    add_ws("sas.d_y", PAMREC_F32, {N, kE});
+    add_ws("sas.d_qkv", PAMREC_F32, {N, 3 * kE});
+    add_ws("sas.dq", PAMREC_F32, {N});
+    add_ws("sib.dh", PAMREC_F32, {2, N, kE});        // [0] = gradient of x0 = rows of the satisfied lookups; [1] = 0 (L2 rows only)
+    add_ws("sib.has0", PAMREC_I32, {4});
+    add_bn_ws();
+    add_optim_ws();
+    const int64_t NK = 2 * N + B;
+    cub_keys_table = NK;
+    for (const char* t : {"item", "cate"}) {
+      std::string p = std::string("sp.") + t + ".";
+      for (const char* n : {"keys", "idx", "skeys", "sidx", "uidx", "ukeys"}) add_ws(p + n, PAMREC_I32, {NK});
+      add_ws(p + "slot", PAMREC_I32, {t[0] == 'i' ? n_items : n_cates});
+      add_ws(p + "accum", PAMREC_F32, {NK, t[0] == 'i' ? kI : kC});
+    }
+    add_ws("sp.nuniq", PAMREC_I32, {8});
+    add_ws("dp.scalars", PAMREC_F64, {8});
+    cub_keys = NK;
+    add_ws("cub_temp", PAMREC_U8, {(int64_t)(16u << 20) + 16 * cub_keys});
+    (void)c;
+  }
+
   void build(const PamrecConfig& c) {
     n_users = c.n_users; n_items = c.n_items; n_cates = c.n_cates; T = c.max_seq_len; Bcap = c.max_batch;
     world = c.world_size < 1 ? 1 : c.world_size; table_mode = c.table_mode;
     model_kind = c.model_kind;
+    if (model_kind == PAMREC_MODEL_SASREC) { build_sasrec(c); return; }
     if (model_kind != PAMREC_MODEL_PAMREC) { build_sibling(c); return; }
     const int L2 = PAMREC_SEG_L2;
     // ---- dense pool: encoder first so that every float4-loaded matrix starts on a 16-byte boundary

@@ -37,7 +37,7 @@ BATCH_FIELDS = (  # name, dtype, per-row shape suffix, needed for scoring
 )
 # the satisfied-only copy of the history (IT:1069-1103): read by the sibling models only (mmoe.py:199-201)
 SIBLING_FIELDS = (("satisfied_item_history", np.int32, True), ("satisfied_cate_history", np.int32, True), ("satisfied_mask", np.int32, True))
-MODELS = {"pamrec": L.MODEL_PAMREC, "mmoe": L.MODEL_MMOE, "ple": L.MODEL_PLE, "sharebottom": L.MODEL_SHAREBOTTOM}
+MODELS = {"pamrec": L.MODEL_PAMREC, "mmoe": L.MODEL_MMOE, "ple": L.MODEL_PLE, "sharebottom": L.MODEL_SHAREBOTTOM, "sasrec": L.MODEL_SASREC}
 
 
 class PamrecError(RuntimeError):
@@ -90,8 +90,8 @@ class PendingHost:
 class Engine:
     def __init__(self, n_users, n_items, n_cates, max_seq_len, max_batch, hp=None, sparse_adam="dense_exact",
                  world_size=1, rank=0, tables=None, model="pamrec", graph=None):
-        """model: "pamrec" (PAMRECModel) or one of the sibling multi-task baselines "mmoe" (MMoEModel_original), "ple" (PLEModel),
-        "sharebottom" (ShareBottomModel) - those run on one GPU with whole tables.
+        """model: "pamrec" (PAMRECModel) or one of the sibling baselines "mmoe" (MMoEModel_original), "ple" (PLEModel),
+        "sharebottom" (ShareBottomModel), "sasrec" (SASRecModel) - those run on one GPU with whole tables.
         graph: replay the train step from a CUDA graph (one graph per resident / staged DeviceBatch, captured at its second use;
         one GPU, whole tables, PAMRec only).  None reads PAMREC_GRAPH (default on; PAMREC_GRAPH=0 launches kernel by kernel).
         tables: "local" (whole tables on this GPU, world_size 1), "replicated" (every rank holds whole tables; the merged
@@ -105,7 +105,9 @@ class Engine:
         self.model = model
         self.batch_fields = BATCH_FIELDS + (SIBLING_FIELDS if model != "pamrec" else ())
         if model != "pamrec" and (self.world != 1 or tables not in (None, "auto", "local")):
-            raise PamrecError("the sibling models (mmoe / ple / sharebottom) run on one GPU with whole tables")
+            raise PamrecError("the sibling models (mmoe / ple / sharebottom / sasrec) run on one GPU with whole tables")
+        # SASRecModel has neither the user_long / user_short tables nor play_lookup (sasrec.py:20-34 on top of SBM:562-593)
+        self.tables_by_name = {n: v for n, v in TABLES.items() if model != "sasrec" or v[0] in ("item", "cate")}
         try:
             limit = float(os.environ.get("PAMREC_REPLICATE_MB", D.REPLICATE_BYTES / 2 ** 20)) * 2 ** 20
             tables = D.choose_tables(tables, self.world, n_users, n_items, n_cates, limit)
@@ -143,7 +145,7 @@ class Engine:
         self.graph = bool(graph)
         self._graphs, self._profiling = {}, False
         self._dev_step = None                        # value of the device-side step counter, when known to equal self.step
-        self.frozen = {n: np.zeros(f(n_users), np.float32) for n, f in FROZEN.items()}
+        self.frozen = {n: np.zeros(f(n_users), np.float32) for n, f in FROZEN.items() if model != "sasrec" or not n.endswith("play_lookup")}
 
     # ------------------------------------------------------------------ inventory (host only)
     def _query(self, pool):
@@ -159,8 +161,8 @@ class Engine:
         """TF variable name -> shape for every variable of the reference graph."""
         nu, ni, nc, T, _ = self.dims
         shapes = {n: d["shape"] for n, d in self.info[L.POOL_DENSE].items()}
-        shapes.update({EMB + "item_embedding": (ni, 16), EMB + "cate_embedding": (nc, 4),
-                       EMB + "user_long_embedding": (nu, 20), EMB + "user_short_embedding": (nu, 20)})
+        rows = {"item": ni, "cate": nc, "ulong": nu, "ushort": nu}
+        shapes.update({n: (rows[pre], w) for n, (pre, w) in self.tables_by_name.items()})
         shapes.update({n: a.shape for n, a in self.frozen.items()})
         shapes.update({n: d["shape"] for n, d in self.info[L.POOL_BN].items()})
         return shapes
@@ -266,7 +268,7 @@ class Engine:
         """variables: TF name -> array.  Unknown names raise; missing names keep their current value."""
         for name, val in variables.items():
             t = torch.as_tensor(np.asarray(val, dtype=np.float32))
-            if name in TABLES:
+            if name in self.tables_by_name:
                 if self.tables == "sharded":
                     t = torch.from_numpy(D.shard_table(t.numpy(), self.world, self.rank))
                 self.pool[TABLES[name][0] + "_w"].copy_(t.to(self.device))
@@ -284,7 +286,7 @@ class Engine:
         if "var" in pools:
             for name in self.info[L.POOL_DENSE]:
                 out[name] = self.dense(name).detach().cpu().numpy().copy()
-            for name, (pre, _) in TABLES.items():
+            for name, (pre, _) in self.tables_by_name.items():
                 out[name] = self._gather_table(self.pool[pre + "_w"], self._vocab(pre))
             out.update({n: a.copy() for n, a in self.frozen.items()})
         if "bn" in pools:
@@ -297,7 +299,7 @@ class Engine:
         for name in self.info[L.POOL_DENSE]:
             st[name + "/Adam"] = self.dense(name, "dense_m").detach().cpu().numpy().copy()
             st[name + "/Adam_1"] = self.dense(name, "dense_v").detach().cpu().numpy().copy()
-        for name, (pre, _) in TABLES.items():
+        for name, (pre, _) in self.tables_by_name.items():
             st[name + "/Adam"] = self._gather_table(self.pool[pre + "_m"], self._vocab(pre))
             st[name + "/Adam_1"] = self._gather_table(self.pool[pre + "_v"], self._vocab(pre))
         return st
@@ -315,7 +317,7 @@ class Engine:
             if which is None:
                 raise KeyError(f"unknown optimizer slot {key}")
             t = torch.as_tensor(np.asarray(val, dtype=np.float32))
-            if name in TABLES:
+            if name in self.tables_by_name:
                 if self.tables == "sharded":
                     t = torch.from_numpy(D.shard_table(t.numpy(), self.world, self.rank))
                 self.pool[f"{TABLES[name][0]}_{which}"].copy_(t.to(self.device))

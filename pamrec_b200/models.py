@@ -24,7 +24,7 @@ from .engine import Engine
 from .prefetch import Prefetcher
 from .sequential_iterator import LocalFeed
 
-__all__ = ["PAMRECModel", "MMoEModel_original", "PLEModel", "ShareBottomModel", "SequentialBaseModel", "BaseModel", "latest_checkpoint",
+__all__ = ["PAMRECModel", "MMoEModel_original", "PLEModel", "ShareBottomModel", "SASRecModel", "SequentialBaseModel", "BaseModel", "latest_checkpoint",
            "initial_variables"]
 
 
@@ -587,3 +587,42 @@ class ShareBottomModel(_DinMultiTask):
 
     def _check_mixing(self, hp, need):
         pass
+
+
+class _PendingStep5(_PendingStep):
+    def result(self):
+        l = self._pending.result()
+        return [None, None, float(l[0]), float(l[1]), None]
+
+
+class SASRecModel(_DinMultiTask):
+    """models/sequential/sasrec.py:16: the satisfied-only history + a position table through two 20-wide self-attention blocks with
+    dense Q / K / V, read out at the last satisfied position, one tower; loss = data + regular.  train() returns the base class's
+    5-tuple (update, extra_update_ops, loss, data_loss, summary) (BM:350-372)."""
+    ENGINE_MODEL = "sasrec"
+
+    def _check_mixing(self, hp, need):
+        pass
+
+    def train_async(self, sess, feed_dict):
+        return _PendingStep5(self.engine.train_step_async(self.engine.upload(feed_dict, training=True, staged=True)))
+
+    def step_train(self, step, step_result):
+        """SBM:227-236."""
+        (_, _, step_loss, step_data_loss, _) = step_result
+        if step % self.hparams.show_step == 0:
+            print("step {0:d} , total_loss: {1:.4f}, data_loss: {2:.4f}".format(step, step_loss, step_data_loss))
+
+    def batch_train(self, file_iterator, train_sess):
+        """SBM:87-125."""
+        step, epoch_loss, pending = 0, 0.0, None
+        for feed in file_iterator:
+            if feed:
+                queued = self.train_async(train_sess, feed)
+                if pending is not None:
+                    epoch_loss += pending.result()[2]
+                pending = queued
+                step += 1
+        if pending is not None:
+            epoch_loss += pending.result()[2]
+        return epoch_loss

@@ -64,7 +64,7 @@ def test_inventory_matches_oracle(lib_built):
     eng.close()
 
 
-@pytest.mark.parametrize("model", ["mmoe", "ple", "sharebottom"])
+@pytest.mark.parametrize("model", ["mmoe", "ple", "sharebottom", "sasrec"])
 def test_sibling_inventory_matches_oracle(lib_built, model):
     """MMoEModel_original / PLEModel / ShareBottomModel: the library's variables, by TF name, are the oracle's param_spec."""
     from oracle import siblings_oracle as S
@@ -72,7 +72,7 @@ def test_sibling_inventory_matches_oracle(lib_built, model):
     from pamrec_b200.engine import Engine, PamrecError
     eng = Engine(n_users=37, n_items=211, n_cates=13, max_seq_len=50, max_batch=25, model=model)
     shapes = eng.variable_shapes()
-    spec, bn = S.param_spec(model, 37, 211, 13)
+    spec, bn = S.sasrec_param_spec(37, 211, 13, 50) if model == "sasrec" else S.param_spec(model, 37, 211, 13)
     want = {n: tuple(s) for n, s, _, _ in spec}
     for scope, c in bn:
         want[scope + "/moving_mean"] = (c,)
@@ -80,7 +80,8 @@ def test_sibling_inventory_matches_oracle(lib_built, model):
     assert set(shapes) == set(want)
     for n in want:
         assert tuple(shapes[n]) == want[n], n
-    assert all(d["flags"] & L.SEG_L2 for d in eng.info[L.POOL_DENSE].values())      # everything outside sequential/embedding gets L2
+    for n, d in eng.info[L.POOL_DENSE].items():                                      # everything outside sequential/embedding gets L2
+        assert bool(d["flags"] & L.SEG_L2) == (not n.startswith("sequential/embedding/")), n
     segs = sorted((d["offset"], d["numel"]) for d in eng.info[L.POOL_DENSE].values())
     pos = 0
     for off, n in segs:
@@ -139,7 +140,7 @@ def test_config_validation_and_calls_before_bind(lib_built):
     assert create(loss_kind=L.LOSS_SOFTMAX, softmax_group=3) == 0                                   # one GPU: any group
     assert create(loss_kind=L.LOSS_SOFTMAX, softmax_group=3, world_size=2, table_mode=L.TABLES_SHARDED) == -8   # ranks hold groups of 5
     assert create(loss_kind=L.LOSS_SOFTMAX, softmax_group=5, world_size=2, table_mode=L.TABLES_SHARDED) == 0
-    assert create(model_kind=4) == -9 and create(model_kind=L.MODEL_PLE) == 0
+    assert create(model_kind=5) == -9 and create(model_kind=L.MODEL_PLE) == 0 and create(model_kind=L.MODEL_SASREC) == 0
     assert create(model_kind=L.MODEL_MMOE, world_size=2, table_mode=L.TABLES_REPLICATED) == -9     # sibling models: one GPU
     assert create(model_kind=L.MODEL_MMOE, loss_kind=L.LOSS_SOFTMAX, softmax_group=5) == -9
     assert lib.pamrec_create(None, None) == -1

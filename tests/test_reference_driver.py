@@ -21,7 +21,7 @@ REF_DRIVER = "/root/reference/example/00_quick_start/sequential.py"
 pytestmark = pytest.mark.skipif(not os.path.exists(REF_DRIVER), reason="reference tree not mounted")
 
 
-@pytest.mark.parametrize("model_flag", ["PAMREC", "MMOE_ORIGINAL", "PLE", "SHAREBOTTOM"])
+@pytest.mark.parametrize("model_flag", ["PAMREC", "MMOE_ORIGINAL", "PLE", "SHAREBOTTOM", "SASREC"])
 def test_unmodified_reference_driver_runs(tmp_path, monkeypatch, capsys, lib_built, model_flag):
     from pamrec_b200 import models as M
     from pamrec_b200 import synth

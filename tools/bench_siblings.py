@@ -1,4 +1,4 @@
-"""Train-step throughput of the sibling multi-task baselines (MMoEModel_original / PLEModel / ShareBottomModel) on the takatak bench
+"""Train-step throughput of the sibling baselines (MMoEModel_original / PLEModel / ShareBottomModel / SASRecModel) on the takatak bench
 shape (B = 1025, T = 50): one JSON line per model with the device-timed samples/s (8 resident batches, L2 flushed between steps),
 the end-to-end number through Model.train_async with host feeds (one step ahead, as fit_step runs) and the per-launcher table.
 
@@ -18,7 +18,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 W = dict(dataset="takatak", n_users=50000, n_items=30000, n_cates=50, T=50, B=1025)
-MODELS = (("MMoEModel_original", "mmoe.yaml"), ("PLEModel", "ple.yaml"), ("ShareBottomModel", "sharebottom.yaml"))
+MODELS = (("MMoEModel_original", "mmoe.yaml"), ("PLEModel", "ple.yaml"), ("ShareBottomModel", "sharebottom.yaml"), ("SASRecModel", "sasrec.yaml"))
 
 
 def satisfied_fields(feed, seed):
