@@ -42,7 +42,7 @@ struct PamrecHandle_ {
   // GEMMs of the head) is forked from the caller's stream with events and joined back before anything consumes it.
   cudaStream_t side = nullptr;
   cudaEvent_t ev_side[12] = {};
-  cudaEvent_t ev_join = nullptr, ev_plan = nullptr;
+  cudaEvent_t ev_join = nullptr, ev_plan = nullptr, ev_bucket = nullptr;
   int ev_next = 0;
   const void* plan_for = nullptr;   // batch whose sparse plan is in flight / ready on the side stream (local tables)
   int plan_rows = -1;
@@ -90,6 +90,7 @@ struct PamrecHandle_ {
     for (auto e : ev_side) if (e) cudaEventDestroy(e);
     if (ev_join) cudaEventDestroy(ev_join);
     if (ev_plan) cudaEventDestroy(ev_plan);
+    if (ev_bucket) cudaEventDestroy(ev_bucket);
     if (side) cudaStreamDestroy(side);
   }
   // run fn(side) after everything enqueued on `main` so far
@@ -324,6 +325,7 @@ int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
     for (auto& e : h->ev_side) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_plan, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_bucket, cudaEventDisableTiming);
   }
   static const char* names[BN_COUNT] = {"s0", "s1", "e0", "g0", "e1", "g1", "t0", "t1"};
   for (int i = 0; i < BN_COUNT; ++i) h->bn[i] = make_bn(h, i, names[i]);
@@ -618,6 +620,17 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     for (int id : ids) { launch_bn_finalize(h->bn[id], cnt, st); nl += 1; }
   };
   float* x0 = h->wf("x0");
+  int* ctl = h->wi("bucket_ctl");
+  // The bucket sort of the tokens depends on the play-ratio buckets of the batch only: on the side stream beside the gather
+  // (whole tables; the sharded exchange synchronises with the host and keeps everything on one stream)
+  const bool bucket_aside = !h->sharded() && getenv("PAMREC_NO_SIDE_STREAM") == nullptr;
+  if (bucket_aside) {
+    h->fork(st, [&](cudaStream_t s2) {
+      launch_bucket_plan(b->item_loop_times_history, N, h->wi("bucket"), h->wi("perm"), ctl, h->wi("tile_bucket"), h->wi("tile_begin"),
+                         h->wi("tile_count"), s2);
+      cudaEventRecord(h->ev_bucket, s2);
+    });
+  }
   if (int rc = embed_forward(h, b, training != 0, x0, st)) return rc;
   nl += 1;
   if (training && !h->sharded() && B > 0) {
@@ -634,9 +647,10 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     cudaMemsetAsync(h->wd("dp.scalars"), 0, 8 * sizeof(double), st);
     launch_count_valid_groups(b->plays, B, h->wd("dp.scalars"), st);
   }
-  int* ctl = h->wi("bucket_ctl");
-  launch_bucket_plan(b->item_loop_times_history, N, h->wi("bucket"), h->wi("perm"), ctl, h->wi("tile_bucket"),
-                     h->wi("tile_begin"), h->wi("tile_count"), st); nl += 3;
+  if (bucket_aside) cudaStreamWaitEvent(st, h->ev_bucket, 0);
+  else launch_bucket_plan(b->item_loop_times_history, N, h->wi("bucket"), h->wi("perm"), ctl, h->wi("tile_bucket"),
+                          h->wi("tile_begin"), h->wi("tile_count"), st);
+  nl += 3;
   const int max_tiles = N / kTokTile + kNB + 1;
   const float* xin = x0;
   for (int k = 0; k < 2; ++k) {
@@ -1072,6 +1086,7 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
   void* tmp = h->ws<char>("cub_temp");
   size_t tmp_bytes = (size_t)L.ws[L.ws_index.at("cub_temp")].numel;
   int64_t nl = 0;
+  bool dense_aside = false;
   const float* dX0 = h->wf("g_a");
   const float* dT = h->wf("d_tgt_total");
   if (h->sharded()) {
@@ -1126,6 +1141,17 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
     }
   } else {
     // ---- whole tables on this GPU: one-sort plan (side stream, beside the forward pass) -> run walk -> Adam
+    if (c.world_size == 1 && getenv("PAMREC_NO_SIDE_STREAM") == nullptr) {
+      // one GPU: the dense variables' clip norms + Adam share nothing with the tables' walk + sweep: side stream, joined before the losses
+      dense_aside = true;
+      h->fork(st, [&](cudaStream_t s2) {
+        launch_dense_norm(h->buf.dense_param, h->buf.dense_grad, h->wi("seg_tab"), (int)L.dense.size(), c.layer_l2, h->wd("seg_normsq"),
+                          h->wd("sp_normsq") + 4, reg, s2);
+        launch_dense_adam(h->buf.dense_param, h->buf.dense_grad, h->buf.dense_m, h->buf.dense_v, h->wi("seg_id"), h->wi("seg_tab"),
+                          h->wd("seg_normsq"), L.dense_numel, c.layer_l2, lr_t, lr_dev, c.beta1, c.beta2, c.epsilon, c.max_grad_norm,
+                          c.is_clip_norm, s2);
+      });
+    }
     const bool planned = h->plan_for == b->item_history && h->plan_rows == B;
     h->plan_for = nullptr;
     const Sp2 s2 = make_sp2(h, b);
@@ -1165,11 +1191,15 @@ int pamrec_apply_gradients(PamrecHandle h, const PamrecBatch* b, int64_t step, v
     }
   }
   const int n_seg = (int)L.dense.size();
-  launch_dense_norm(h->buf.dense_param, h->buf.dense_grad, h->wi("seg_tab"), n_seg, c.layer_l2, h->wd("seg_normsq"),
-                    h->wd("sp_normsq") + 4, reg, st);
-  launch_dense_adam(h->buf.dense_param, h->buf.dense_grad, h->buf.dense_m, h->buf.dense_v, h->wi("seg_id"), h->wi("seg_tab"),
-                    h->wd("seg_normsq"), L.dense_numel, c.layer_l2, lr_t, lr_dev, c.beta1, c.beta2, c.epsilon, c.max_grad_norm,
-                    c.is_clip_norm, st);
+  if (dense_aside) {
+    h->join(st);
+  } else {
+    launch_dense_norm(h->buf.dense_param, h->buf.dense_grad, h->wi("seg_tab"), n_seg, c.layer_l2, h->wd("seg_normsq"),
+                      h->wd("sp_normsq") + 4, reg, st);
+    launch_dense_adam(h->buf.dense_param, h->buf.dense_grad, h->buf.dense_m, h->buf.dense_v, h->wi("seg_id"), h->wi("seg_tab"),
+                      h->wd("seg_normsq"), L.dense_numel, c.layer_l2, lr_t, lr_dev, c.beta1, c.beta2, c.epsilon, c.max_grad_norm,
+                      c.is_clip_norm, st);
+  }
   launch_finish_losses(h->wd("loss_acc"), h->wf("losses"), h->sharded() ? nullptr : h->wd("sp2.l2sq"), c.embed_l2, h->wd("sp_normsq"), st);
   nl += 3;
   return check_cuda(h, "apply_gradients");

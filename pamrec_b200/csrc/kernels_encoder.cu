@@ -235,7 +235,22 @@ void launch_proj_fwd(const float* X, const int* perm, const int* ctl, const int*
 constexpr int kAttnCh = 8;
 __host__ __device__ inline int attn_nw(int T) { return (T + 31) / 32; }
 __host__ __device__ inline int attn_spb(int T) { int nw = attn_nw(T); return nw >= 4 ? 1 : 4 / nw; }
-__host__ __device__ inline int attn_fwd_per(int T) { return 2 * T * kAttnStride + ((T + 3) & ~3); }   // floats per sample, 16-byte multiple
+// floats per sample (16-byte multiple): K | V | mask [T4] | indices of the live keys [T4] | their count [4]
+__host__ __device__ inline int attn_fwd_per(int T) { return 2 * T * kAttnStride + 2 * ((T + 3) & ~3) + 4; }
+// The keys a query attends to are the sample's live ones: a masked key's weight is exp(-(2^32) - m) = 0 exactly whenever the sample
+// has any live key, so both attention kernels walk a compacted index list (built once per sample by one warp) instead of testing
+// the mask per key - half of the score / PV work at the bench's uniform history lengths.  lv / nl: list and count in shared memory.
+__device__ __forceinline__ void attn_live_list(const int* __restrict__ mk, int T, int lane, int* __restrict__ lv, int* __restrict__ nl) {
+  int base = 0;
+  for (int c = 0; c < T; c += 32) {
+    const int j = c + lane;
+    const bool live = j < T && mk[j] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, live);
+    if (live) lv[base + __popc(bal & ((1u << lane) - 1u))] = j;
+    base += __popc(bal);
+  }
+  if (lane == 0) *nl = base;
+}
 inline size_t attn_fwd_smem(int T) { return (size_t)attn_spb(T) * attn_fwd_per(T) * 4; }
 
 // 40-wide dot product as four independent FMA chains of ten (a single chain of 40 would serialise on FMA latency)
@@ -273,27 +288,31 @@ k_attn_fwd(const float* __restrict__ Q, const float* __restrict__ K, const float
   }
   __syncthreads();
   const int sl = tid / tps, t = tid % tps;
+  const int T4 = (T + 3) & ~3;
+  if (sl < ns && t < 32) {                                   // the first warp of every sample (tps is a multiple of 32)
+    int* mki = reinterpret_cast<int*>(sm + sl * per + 2 * T * kAttnStride);
+    attn_live_list(mki, T, t, mki + T4, mki + 2 * T4);
+  }
+  __syncthreads();
   if (sl >= ns || t >= T) return;
   const float* Ks = sm + sl * per;
   const float* Vs = Ks + T * kAttnStride;
-  const int* mk = reinterpret_cast<const int*>(Vs + T * kAttnStride);
+  const int* lv = reinterpret_cast<const int*>(Vs + T * kAttnStride) + T4;
+  const int nl = lv[T4];
   const int64_t row = ((int64_t)(b0 + sl) * T + t) * kD;
   float4 q[10], o[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) { q[i] = ld4(Q + row + 4 * i); o[i] = f4_zero(); }
   const float rscale = 1.0f / sqrtf((float)kD);
   float m = -INFINITY, l = 0.f;
-  for (int j0 = 0; j0 < T; j0 += kAttnCh) {
+  for (int k0 = 0; k0 < nl; k0 += kAttnCh) {
     float sc[kAttnCh];
     float cm = -INFINITY;
 #pragma unroll
     for (int jj = 0; jj < kAttnCh; ++jj) {
-      const int j = j0 + jj;
+      const int k = k0 + jj;
       float val = -INFINITY;
-      if (j < T) {
-        const float d = dot40(q, Ks + j * kAttnStride);
-        val = mk[j] ? d * rscale : kMaskNeg;
-      }
+      if (k < nl) val = dot40(q, Ks + lv[k] * kAttnStride) * rscale;
       sc[jj] = val;
       cm = fmaxf(cm, val);
     }
@@ -304,16 +323,23 @@ k_attn_fwd(const float* __restrict__ Q, const float* __restrict__ K, const float
     for (int i = 0; i < 10; ++i) { o[i].x *= corr; o[i].y *= corr; o[i].z *= corr; o[i].w *= corr; }
 #pragma unroll
     for (int jj = 0; jj < kAttnCh; ++jj) {
-      const int j = j0 + jj;
-      if (j < T) {
+      const int k = k0 + jj;
+      if (k < nl) {
         const float pj = expf(sc[jj] - mn);
         l += pj;
-        const float* vr = Vs + j * kAttnStride;
+        const float* vr = Vs + lv[k] * kAttnStride;
 #pragma unroll
         for (int i = 0; i < 10; ++i) f4_fma(o[i], pj, ld4(vr + 4 * i));
       }
     }
     m = mn;
+  }
+  if (nl == 0) {                                           // no live key at all: every score is the padding constant, uniform weights
+    m = kMaskNeg; l = (float)T;
+    for (int j = 0; j < T; ++j) {
+#pragma unroll
+      for (int i = 0; i < 10; ++i) f4_fma(o[i], 1.0f, ld4(Vs + j * kAttnStride + 4 * i));
+    }
   }
   const float inv = 1.0f / l;
 #pragma unroll
@@ -721,7 +747,8 @@ void launch_ffn_bwd(const float* Y, const float* dOUT, const float* W1, const fl
 // up front, pass A (thread == query row t) forms dQ_t in one sweep over the keys and pass B (thread == key j) forms
 // dK_j and dV_j in one sweep over the queries; both recompute p = exp(s - m_t) / l_t from the saved statistics, all
 // shared-memory reads are warp-wide broadcasts.
-inline size_t attn_bwd_smem(int T) { return (size_t)attn_spb(T) * ((size_t)4 * T * kAttnStride + 4 * T) * 4; }
+__host__ __device__ inline int attn_bwd_per(int T) { return 4 * T * kAttnStride + ((5 * T + 4 + 3) & ~3); }   // K | V | Q | dY | m | 1/l | D | mask | live list | count
+inline size_t attn_bwd_smem(int T) { return (size_t)attn_spb(T) * attn_bwd_per(T) * 4; }
 
 __global__ void __launch_bounds__(256)
 k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
@@ -731,7 +758,7 @@ k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float
   extern __shared__ __align__(16) float sm[];
   const int nw = attn_nw(T), spb = attn_spb(T), tps = nw * 32;
   const int TS = T * kAttnStride;
-  const int per = 4 * TS + 4 * T;                           // K | V | Q | dY | m | l | D | mask
+  const int per = attn_bwd_per(T);
   const int tid = threadIdx.x;
   const int b0 = blockIdx.x * spb;
   const int ns = min(spb, B - b0);
@@ -761,6 +788,11 @@ k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float
     reinterpret_cast<int*>(S + 4 * TS + 3 * T)[t] = mask[tok];
   }
   __syncthreads();
+  if (sl < ns && t < 32) {
+    int* mki = reinterpret_cast<int*>(S + 4 * TS + 3 * T);
+    attn_live_list(mki, T, t, mki + T, mki + 2 * T);
+  }
+  __syncthreads();
   if (!active) return;
   const float* Ks = S;
   const float* Vs = S + TS;
@@ -770,6 +802,8 @@ k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float
   const float* ril = rm + T;                               // 1 / row sum
   const float* rD = ril + T;
   const int* mk = reinterpret_cast<const int*>(rD + T);
+  const int* lv = mk + T;
+  const int nl = lv[T];
   const float rscale = 1.0f / sqrtf((float)kD);
   const int64_t row = ((int64_t)(b0 + sl) * T + t) * kD;
   // ---- pass A: dQ_t
@@ -779,16 +813,15 @@ k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float
     for (int i = 0; i < 10; ++i) { q[i] = ld4(Qs + t * kAttnStride + 4 * i); g[i] = ld4(Gs + t * kAttnStride + 4 * i); acc[i] = f4_zero(); }
     const float mt = rm[t], il = ril[t], Dt = rD[t];
 #pragma unroll 2
-    for (int j = 0; j < T; ++j) {
-      if (mk[j]) {                                         // masked keys: p > 0 but dS = 0 (constant score)
-        const float* kr = Ks + j * kAttnStride;
-        const float sv = dot40(q, kr) * rscale;
-        const float p = expf(sv - mt) * il;
-        const float dp = dot40(g, Vs + j * kAttnStride);
-        const float ds = p * (dp - Dt) * rscale;
+    for (int k = 0; k < nl; ++k) {                         // live keys only: a masked key's score is a constant (dS = 0)
+      const int j = lv[k];
+      const float* kr = Ks + j * kAttnStride;
+      const float sv = dot40(q, kr) * rscale;
+      const float p = expf(sv - mt) * il;
+      const float dp = dot40(g, Vs + j * kAttnStride);
+      const float ds = p * (dp - Dt) * rscale;
 #pragma unroll
-        for (int i = 0; i < 10; ++i) f4_fma(acc[i], ds, ld4(kr + 4 * i));
-      }
+      for (int i = 0; i < 10; ++i) f4_fma(acc[i], ds, ld4(kr + 4 * i));
     }
 #pragma unroll
     for (int i = 0; i < 10; ++i) st4(dQ + row + 4 * i, acc[i]);
@@ -800,7 +833,10 @@ k_attn_bwd(const float* __restrict__ Q, const float* __restrict__ K, const float
 #pragma unroll
     for (int i = 0; i < 10; ++i) { kj[i] = ld4(Ks + j * kAttnStride + 4 * i); vj[i] = ld4(Vs + j * kAttnStride + 4 * i); ak[i] = f4_zero(); av[i] = f4_zero(); }
     const int mkj = mk[j];
-    for (int tt = 0; tt < T; ++tt) {
+    // a masked key of a sample that has live keys: p = exp(-(2^32) - m_t) = 0 for every query, nothing to accumulate (a warp whose
+    // keys are all padding leaves here)
+    const int tq_end = (mkj || nl == 0) ? T : 0;
+    for (int tt = 0; tt < tq_end; ++tt) {
       const float* qr = Qs + tt * kAttnStride;
       const float* gr = Gs + tt * kAttnStride;
       const float sv = mkj ? dot40(kj, qr) * rscale : kMaskNeg;
