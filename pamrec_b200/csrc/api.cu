@@ -57,6 +57,7 @@ struct PamrecHandle_ {
   unsigned long long* head_trace_cta = nullptr;   // debug: arrival stamps of every CTA at every barrier (2 kernels x 16 x 256)
   int n_sm = 148;
   int attn_tc = 0;                  // 1: attention forward on tcgen05 (kernels_attn_tc.cu) where the sequence length allows it
+  int attn_mma = 1;                 // attention on warp-level tensor-core MMAs (kernels_attn_mma.cu); PAMREC_ATTN=ffma: the FFMA kernels
   uint32_t coop_epoch = 0;          // mailbox epoch of the cooperative kernels (one per launch, all ranks in lockstep)
   // row-stationary persistent head kernels (kernels_head2.cu): the default; PAMREC_HEAD_LEGACY=1 (or a device without
   // cooperative launch, or more than 8 ranks) selects the stand-alone kernels of kernels_head.cu
@@ -318,6 +319,8 @@ int pamrec_bind(PamrecHandle h, const PamrecBuffers* bufs, void* stream) {
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dev);
     const char* a = getenv("PAMREC_ATTN");
     h->attn_tc = (a != nullptr && std::string(a) == "tc") ? 1 : 0;
+    h->attn_mma = (a == nullptr || std::string(a) == "mma") ? 1 : 0;
+    if (init_attn_mma_kernels(h->cfg.max_seq_len)) return check_cuda(h, "shared-memory opt-in of the MMA attention kernels");
     if (h->attn_tc && init_attn_tc_kernels(h->cfg.max_seq_len)) return check_cuda(h, "shared-memory opt-in of the tcgen05 attention kernel");
   }
   if (!h->side) {
@@ -659,7 +662,9 @@ int pamrec_forward(PamrecHandle h, const PamrecBatch* b, int training, float* pr
     launch_proj_fwd(xin, h->wi("perm"), ctl, h->wi("tile_bucket"), h->wi("tile_begin"), h->wi("tile_count"), max_tiles,
                     h->P(o.wq), h->P(o.wk), h->P(o.wv), h->P(o.ln_a_beta), h->P(o.ln_a_gamma), h->wf(p + "qin"), h->wf(p + "Q"),
                     h->wf(p + "K"), h->wf(p + "V"), st);
-    if (h->attn_tc && attn_tc_supported(T))
+    if (h->attn_mma)
+      launch_attn_fwd_mma(h->wf(p + "Q"), h->wf(p + "K"), h->wf(p + "V"), h->wf(p + "qin"), b->mask, h->wf(p + "y"), h->wf(p + "ml"), B, T, st);
+    else if (h->attn_tc && attn_tc_supported(T))
       launch_attn_fwd_tc(h->wf(p + "Q"), h->wf(p + "K"), h->wf(p + "V"), h->wf(p + "qin"), b->mask, h->wf(p + "y"), h->wf(p + "ml"), B, T,
                          h->n_sm, reinterpret_cast<int*>(h->head_bar + 3), st);
     else
@@ -1027,8 +1032,12 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
     float* gin = k == 1 ? g_b : g_a;
     launch_ffn_bwd(h->wf(p + "y"), gout, h->P(o.w1), h->P(o.b1), h->P(o.w2), h->P(o.ln_b_beta), h->P(o.ln_b_gamma), h->wf("d_y"),
                    h->G(o.w1), h->G(o.b1), h->G(o.w2), h->G(o.b2), h->G(o.ln_b_beta), h->G(o.ln_b_gamma), N, st);
-    launch_attn_bwd(h->wf(p + "Q"), h->wf(p + "K"), h->wf(p + "V"), h->wf("d_y"), h->wf(p + "y"), h->wf(p + "qin"), h->wf(p + "ml"),
-                    b->mask, h->wf("d_Q"), h->wf("d_K"), h->wf("d_V"), B, T, st);
+    if (h->attn_mma && getenv("PAMREC_ATTN_BWD_FFMA") == nullptr)
+      launch_attn_bwd_mma(h->wf(p + "Q"), h->wf(p + "K"), h->wf(p + "V"), h->wf("d_y"), h->wf(p + "y"), h->wf(p + "qin"), h->wf(p + "ml"),
+                          b->mask, h->wf("d_Q"), h->wf("d_K"), h->wf("d_V"), B, T, st);
+    else
+      launch_attn_bwd(h->wf(p + "Q"), h->wf(p + "K"), h->wf(p + "V"), h->wf("d_y"), h->wf(p + "y"), h->wf(p + "qin"), h->wf(p + "ml"),
+                      b->mask, h->wf("d_Q"), h->wf("d_K"), h->wf("d_V"), B, T, st);
     launch_proj_bwd(xin, h->wf("d_y"), h->wf("d_Q"), h->wf("d_K"), h->wf("d_V"), h->wi("perm"), ctl, h->wi("tile_bucket"),
                     h->wi("tile_begin"), h->wi("tile_count"), max_tiles, h->P(o.wq), h->P(o.wk), h->P(o.wv), h->P(o.ln_a_beta),
                     h->P(o.ln_a_gamma), gin, h->G(o.wq), h->G(o.wk), h->G(o.wv), h->G(o.ln_a_beta), h->G(o.ln_a_gamma), st);

@@ -60,6 +60,13 @@ int init_attn_tc_kernels(int max_T);
 void launch_attn_fwd_tc(const float* Q, const float* K, const float* V, const float* QIN, const int* mask, float* Y, float* ML, int B, int T,
                         int n_sm, int* err, cudaStream_t st);
 
+// ---- kernels_attn_mma.cu (attention forward + backward on warp-level tensor-core MMAs, 3xTF32; the default)
+int init_attn_mma_kernels(int max_T);
+void launch_attn_fwd_mma(const float* Q, const float* K, const float* V, const float* QIN, const int* mask, float* Y, float* ML, int B, int T,
+                         cudaStream_t st);
+void launch_attn_bwd_mma(const float* Q, const float* K, const float* V, const float* dY, const float* Y, const float* QIN, const float* ML,
+                         const int* mask, float* dQ, float* dK, float* dV, int B, int T, cudaStream_t st);
+
 // ---- kernels_head.cu
 void launch_dense_fwd(const DenseP& p, cudaStream_t st);
 void launch_dense_dx(const DenseDxP& p, cudaStream_t st);
