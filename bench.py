@@ -41,6 +41,7 @@ WORKLOADS = {
 METRIC = "train samples/sec"
 METRIC_SCORE = "scored samples/sec"
 N_POOL = 8            # distinct resident batches cycled through the timed steps
+ATTN_PIPE = "fp32" if os.environ.get("PAMREC_ATTN", "mma") == "ffma" else "tensor"
 
 
 def peaks():
@@ -126,8 +127,10 @@ def flops_bytes(w):
     tower = 2 * 3 * (84 * 100 + 100 * 64 + 64) * B
     head_act = 4 * (N * 21 + B * (500 + 320 + 128 + 10 + 168 + 300 + 192 + 3))            # pre-activations written once
     return {
-        "attn_fwd": dict(flop=2 * (2 * T * T * 40) * B * 2, byte=2 * 5 * t, pipe="fp32"),      # Q K^T, P V ; Q K V qin -> y  (x 2 blocks)
-        "attn_bwd": dict(flop=2 * (5 * T * T * 40) * B * 2, byte=2 * 9 * t, pipe="fp32"),      # S, dP, dV, dQ, dK
+        # attention: warp-level 3xTF32 MMAs (kernels_attn_mma.cu) unless PAMREC_ATTN=ffma; the T x T count is the reference's (every
+        # key, padded or not); the kernels only visit the live keys of a sample
+        "attn_fwd": dict(flop=2 * (2 * T * T * 40) * B * 2, byte=2 * 5 * t, pipe=ATTN_PIPE),   # Q K^T, P V ; Q K V qin -> y  (x 2 blocks)
+        "attn_bwd": dict(flop=2 * (5 * T * T * 40) * B * 2, byte=2 * 9 * t, pipe=ATTN_PIPE),   # S, dP, dV, dQ, dK
         "proj_fwd": dict(flop=2 * (3 * 1600) * N * 2, byte=2 * 5 * t, pipe="tensor"),
         "proj_bwd": dict(flop=2 * (6 * 1600) * N * 2, byte=2 * 6 * t, pipe="tensor"),
         "ffn_fwd": dict(flop=2 * (2 * 1600) * N * 2, byte=2 * 2 * t, pipe="tensor"),
@@ -156,7 +159,7 @@ def step_work(w):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the `ncu --set full` capture of this workload
 # (profiles/r01e_ncu_encoder_full.csv, takatak_b1025_t50); null for kernels / workloads without a capture
-NCU_TRAFFIC = {"takatak_b1025_t50": {"attn_bwd": 49.85e6 + 1.04e6, "proj_bwd": 41.67e6 + 0.08e6, "ffn_bwd": 16.51e6 + 0.0}}
+NCU_TRAFFIC = {"takatak_b1025_t50": {"proj_bwd": 41.67e6 + 0.08e6, "ffn_bwd": 16.51e6 + 0.0}}
 
 
 def hbm_microbench(pk, dev):

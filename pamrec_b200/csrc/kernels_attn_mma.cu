@@ -16,6 +16,8 @@
 // Backward = two passes like the FFMA kernel: pass A (warp = 16 queries) recomputes S, forms dP, dS and dQ; pass B (warp = 16
 // keys) recomputes S^T = K Q^T against ALL queries, forms P^T and dS^T from the saved row statistics and accumulates dV = P^T dY,
 // dK = dS^T Q.  Everything is warp-local: no atomics, sums in a fixed order.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "mma.cuh"
 
@@ -197,8 +199,8 @@ __host__ __device__ inline size_t bwd_smem(int T) {
   return ((size_t)2 * Tp16 * kSt + 2 * Tp8 * kSt + 3 * Tp8 + 2 * T4 + 4) * 4;
 }
 
-template <int NTM>
-__global__ void __launch_bounds__(kThreads)
+template <int MINB>                      // resident CTAs per SM the register allocation must allow (3: no spills; 4: 128 registers)
+__global__ void __launch_bounds__(kThreads, MINB)
 k_attn_bwd_mma(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, const float* __restrict__ dY,
                const float* __restrict__ Y, const float* __restrict__ QIN, const float* __restrict__ ML, const int* __restrict__ mask,
                float* __restrict__ dQ, float* __restrict__ dK, float* __restrict__ dV, int T) {
@@ -380,7 +382,8 @@ int init_attn_mma_kernels(int max_T) {
   set((const void*)amma::k_attn_fwd_mma<13>, f);
   set((const void*)amma::k_attn_fwd_mma<25>, f);
   set((const void*)amma::k_attn_fwd_mma<32>, f);
-  set((const void*)amma::k_attn_bwd_mma<1>, b);
+  set((const void*)amma::k_attn_bwd_mma<3>, b);
+  set((const void*)amma::k_attn_bwd_mma<4>, b);
   return e == cudaSuccess ? 0 : -1;
 }
 
@@ -398,7 +401,10 @@ void launch_attn_bwd_mma(const float* Q, const float* K, const float* V, const f
                          const int* mask, float* dQ, float* dK, float* dV, int B, int T, cudaStream_t st) {
   PAMREC_PROF("attn_bwd", 1, st);
   if (B == 0) return;
-  amma::k_attn_bwd_mma<1><<<dim3(B, (T + 63) / 64), amma::kThreads, amma::bwd_smem(T), st>>>(Q, K, V, dY, Y, QIN, ML, mask, dQ, dK, dV, T);
+  static const bool occ4 = getenv("PAMREC_ATTN_BWD_OCC4") != nullptr;      // experiment switch: 4 CTAs / SM at the price of spills
+  const dim3 grid(B, (T + 63) / 64);
+  if (occ4) amma::k_attn_bwd_mma<4><<<grid, amma::kThreads, amma::bwd_smem(T), st>>>(Q, K, V, dY, Y, QIN, ML, mask, dQ, dK, dV, T);
+  else amma::k_attn_bwd_mma<3><<<grid, amma::kThreads, amma::bwd_smem(T), st>>>(Q, K, V, dY, Y, QIN, ML, mask, dQ, dK, dV, T);
 }
 
 }  // namespace pamrec

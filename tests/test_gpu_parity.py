@@ -308,3 +308,35 @@ def test_error_paths():
     with pytest.raises(PamrecError):          # larger than max_batch
         eng.forward(eng.upload(big), training=False)
     eng.close()
+
+
+@pytest.mark.parametrize("T,B", [(12, 20), (50, 130), (100, 35), (200, 10), (256, 5)])
+def test_attention_mma_and_ffma_paths_agree(T, B, monkeypatch):
+    """The default attention kernels (warp-level 3xTF32 MMAs over the live keys, kernels_attn_mma.cu) against the FFMA kernels
+    (PAMREC_ATTN=ffma, kernels_encoder.cu) on the same batch - including a sample without any live key (uniform weights) and
+    arbitrary, non-prefix masks: outputs, saved row statistics and all three gradients."""
+    nu, ni, nc = 200, 2000, 40
+    batch = O.make_batch(21, B, T, nu, ni, nc)
+    rng = np.random.default_rng(3)
+    batch["mask"][5:10] = 0                                             # one listwise group without history
+    batch["mask"][10:15] = (rng.random((1, T)) < 0.5).astype(np.int32)  # holes in the middle of a history
+    got = {}
+    for mode in ("ffma", "mma"):
+        monkeypatch.setenv("PAMREC_ATTN", mode)
+        om, eng = _setup(nu, ni, nc, T, B, seed=11)
+        db = eng.upload(batch)
+        eng.forward(db, training=True, want_pred=False)
+        eng.backward(db)
+        torch.cuda.synchronize()
+        got[mode] = {k: eng.ws(k, B).cpu().numpy().copy() for k in ("blk0.y", "blk1.y", "blk0.ml", "blk1.ml", "d_Q", "d_K", "d_V", "g_a")}
+        got[mode]["logits"] = eng.ws("logits", B).cpu().numpy().copy()
+        eng.close()
+    for k in got["mma"]:
+        a, b = got["ffma"][k].astype(np.float64), got["mma"][k].astype(np.float64)
+        if k.endswith(".ml"):
+            # row maximum and row sum: the sum is relative to the maximum, which the two kernels round differently
+            assert np.allclose(a[..., 0], b[..., 0], rtol=1e-5, atol=1e-5), k
+            assert np.allclose(a[..., 1], b[..., 1], rtol=1e-4), k
+            continue
+        scale = max(np.abs(a).max(), 1e-30)
+        assert np.abs(a - b).max() <= 1e-5 * scale, (k, float(np.abs(a - b).max() / scale))

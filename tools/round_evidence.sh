@@ -10,7 +10,9 @@ for w in long_b4095_t200 wechat_b500_t100 eval_1p99 sharded_10m_b1025_t50; do
   timeout 300 python bench.py --workload $w --no-cpu-baseline > gpurun_out/${T}_bench_$w.json 2> gpurun_out/${T}_bench_$w.err; echo "bench $w rc=$?"
 done
 timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err; echo "reference rc=$?"
+timeout 200 python tools/bench_siblings.py > gpurun_out/${T}_bench_siblings.jsonl 2> gpurun_out/${T}_bench_siblings.err; echo "siblings rc=$?"
 timeout 60 python tools/file_e2e.py > gpurun_out/${T}_file_e2e.json 2> gpurun_out/${T}_file_e2e.err; echo "file_e2e rc=$?"
+export PAMREC_GRAPH=0   # the profiler sees the step kernel by kernel (graph replay launches the same kernels)
 timeout 120 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_bench_plain.json 2> gpurun_out/${T}_bench_plain.err || exit 1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${T}_ncu_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu_bench.log 2>&1; echo "ncu launches rc=$?"
