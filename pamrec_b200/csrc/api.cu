@@ -1032,7 +1032,9 @@ int pamrec_backward(PamrecHandle h, const PamrecBatch* b, void* stream) {
     float* gin = k == 1 ? g_b : g_a;
     launch_ffn_bwd(h->wf(p + "y"), gout, h->P(o.w1), h->P(o.b1), h->P(o.w2), h->P(o.ln_b_beta), h->P(o.ln_b_gamma), h->wf("d_y"),
                    h->G(o.w1), h->G(o.b1), h->G(o.w2), h->G(o.b2), h->G(o.ln_b_beta), h->G(o.ln_b_gamma), N, st);
-    if (h->attn_mma && getenv("PAMREC_ATTN_BWD_FFMA") == nullptr)
+    // backward: the MMA kernel keeps K, V, Q and dY of a sample in shared memory (141 KB at T = 200: one CTA per SM), measured slower
+    // than the FFMA kernel there (8.5 vs 6.4 ms per step on long_b4095_t200) and faster below (T = 100: 230 vs 292 us, T = 50: 152 vs 196 us)
+    if (h->attn_mma && (T <= 128 || getenv("PAMREC_ATTN_BWD_MMA") != nullptr) && getenv("PAMREC_ATTN_BWD_FFMA") == nullptr)
       launch_attn_bwd_mma(h->wf(p + "Q"), h->wf(p + "K"), h->wf(p + "V"), h->wf("d_y"), h->wf(p + "y"), h->wf(p + "qin"), h->wf(p + "ml"),
                           b->mask, h->wf("d_Q"), h->wf("d_K"), h->wf("d_V"), B, T, st);
     else

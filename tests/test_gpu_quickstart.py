@@ -199,4 +199,8 @@ def test_train_async_one_step_ahead_equals_blocking_train(data_root):
         assert np.allclose(r0[2:7], r1[2:7], rtol=2e-6, atol=1e-7), (r0, r1)
     va, vb = a.engine.get_variables(), b.engine.get_variables()
     worst, where = _worst_difference(va, vb)
-    assert worst <= 5e-5, (worst, where)
+    # The two runs launch the same kernels; what differs is the order of the fp32 atomics in the weight-gradient sums (~1e-7 of the
+    # gradient).  Adam divides by sqrt(v): on entries whose gradient is itself that small the noise decides the direction of a step of
+    # size lr, so nine steps can open a gap of a few percent of lr = 1e-3 on single entries (observed 2e-5 .. 9e-5 over the runs of this
+    # round); anything systematic - a step applied twice, a stale batch, a missed update - shows up at >= lr.
+    assert worst <= 0.2 * 1e-3, (worst, where)

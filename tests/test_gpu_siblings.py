@@ -253,7 +253,10 @@ def test_sibling_multi_step_and_eval(model):
         # opposite directions in fp32 and fp64 (2 * lr per step); the bulk of the table must agree far better than that
         assert d.max() <= 2 * lr * 5 * 1.01 and d.mean() <= 0.05 * lr, (name, float(d.max()), float(d.mean()))
     for name, tval in om.bn_state.items():
-        assert np.allclose(got_vars[name], tval.numpy(), rtol=2e-4, atol=2e-4), name
+        # A moving mean tracks the batch mean of h W + b, and b - a bias in front of a batch norm, exact gradient 0 - random-walks by
+        # +-lr per step on rounding noise that Adam normalises: means to 5 steps of that walk, variances tightly
+        tol = 5 * lr * 0.25 if name.endswith("moving_mean") else 2e-4
+        assert np.allclose(got_vars[name], tval.numpy(), rtol=2e-4, atol=tol), name
     ev = _batch(999, 77, T, nu, ni, nc, grouped=False)
     pred = eng.forward(eng.upload(ev, training=False), training=False).cpu().numpy()
     want = om.eval_forward(ev).t["pred"].numpy().reshape(-1)
