@@ -159,7 +159,8 @@ def step_work(w):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the `ncu --set full` capture of this workload
 # (profiles/r01e_ncu_encoder_full.csv, takatak_b1025_t50); null for kernels / workloads without a capture
-NCU_TRAFFIC = {"takatak_b1025_t50": {"proj_bwd": 41.67e6 + 0.08e6, "ffn_bwd": 16.51e6 + 0.0}}
+# (profiles/r02z_ncu_step_full.csv)
+NCU_TRAFFIC = {"takatak_b1025_t50": {"attn_bwd": 41.67e6 + 0.96e6, "attn_fwd": 24.87e6 + 0.0, "proj_bwd": 41.66e6 + 0.33e6, "ffn_bwd": 16.49e6 + 0.0}}
 
 
 def hbm_microbench(pk, dev):
