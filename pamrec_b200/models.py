@@ -405,15 +405,19 @@ class SequentialBaseModel(BaseModel):
         for feed, step_pred in self._scored(filename, min_seq_length=self.min_seq_length):
             step_labels, step_user = self._labels_users(feed)
             step_labels = np.asarray(step_labels, np.float32).reshape(-1, 1)
-            users.extend(np.reshape(np.asarray(step_user).astype(np.int32), -1))
-            preds.extend(np.reshape(step_pred, -1))
-            labels.extend(np.reshape(step_labels, -1))
+            users.append(np.reshape(np.asarray(step_user).astype(np.int32), -1))    # the reference extends Python lists row by row
+            preds.append(np.reshape(step_pred, -1))                                   # (SBM:449-455); arrays per batch, joined once
+            labels.append(np.reshape(step_labels, -1))
             gp = np.reshape(step_pred, (-1, group))
             gl = np.reshape(step_labels, (-1, group))
             keep = gl.sum(axis=1) != 0                           # SBM:456-460: groups without a positive are dropped
-            group_preds.extend(gp[keep])
-            group_labels.extend(gl[keep])
-        users, preds, labels = filter_single_class_users(users, preds, labels)
+            group_preds.append(gp[keep])
+            group_labels.append(gl[keep])
+        cat = lambda parts, dt: np.concatenate(parts) if parts else np.zeros(0, dt)
+        users, preds, labels = cat(users, np.int32), cat(preds, np.float32), cat(labels, np.float32)
+        group_preds = np.concatenate(group_preds) if group_preds else []
+        group_labels = np.concatenate(group_labels) if group_labels else []
+        users, preds, labels = filter_single_class_users(users, preds, labels, as_arrays=True)
         res = cal_metric(labels, preds, self.hparams.metrics)
         res.update(cal_metric(group_labels, group_preds, self.hparams.pairwise_metrics))
         res.update(cal_weighted_metric(users, preds, labels, self.hparams.weighted_metrics))

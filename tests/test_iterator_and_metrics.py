@@ -300,3 +300,37 @@ def test_memoised_group_auc_is_sklearn_bit_for_bit():
     assert DU.cal_weighted_metric(users, preds, labels, ["wauc"])["wauc"] == round(direct, 4)
     groups_l, groups_p = list(labels.reshape(-1, 3)), list(preds.reshape(-1, 3))
     assert DU.cal_metric(groups_l, groups_p, ["group_auc"])["group_auc"] == round(np.mean([roc_auc_score(l, p) for l, p in zip(groups_l, groups_p)]), 4)
+
+
+def test_pairwise_metrics_over_all_groups_equal_the_per_group_functions():
+    """cal_metric's fast path for rectangular groups (every impression has num_ngs + 1 rows): mrr / ndcg@k / hit@k evaluated on the
+    rows of one 2-D array are bit-identical to the reference's per-group functions (DU:665-747), ties and k > group included, and
+    cal_metric returns the same dict whether the groups come as a list of arrays, a list of lists or one array."""
+    from pamrec_b200 import deeprec_utils as D
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        G, n = int(rng.integers(1, 30)), int(rng.integers(1, 110))
+        P = rng.random((G, n)).astype(np.float32)
+        if trial % 3 == 0:
+            P = np.round(P, 1)                                   # many ties
+        L = (rng.random((G, n)) < 0.1).astype(np.float32)
+        L[np.arange(G), rng.integers(0, n, G)] = 1
+        for k in (1, 2, 10, 200):
+            assert np.array_equal([D.ndcg_score(l, p, k) for l, p in zip(L, P)], D._dcg_rows(L, P, k) / D._dcg_rows(L, L, k))
+            assert np.array_equal([D.hit_score(l, p, k) for l, p in zip(L, P)], D._hit_rows(L, P, k))
+        assert np.array_equal([D.mrr_score(l, p) for l, p in zip(L, P)], D._mrr_rows(L, P))
+        metrics = ["mean_mrr", "ndcg@2;10", "hit@1;10", "group_auc"] if (L.sum(1) < n).all() else ["mean_mrr", "ndcg@2;10", "hit@1;10"]
+        a = D.cal_metric(L, P, metrics)
+        b = D.cal_metric([l for l in L], [p for p in P], metrics)
+        c = D.cal_metric([l.tolist() for l in L], [p.tolist() for p in P], metrics)
+        assert a == b, (a, b)
+        for key in a:                                            # python floats instead of float32 rows: same to the 4 decimals reported
+            assert abs(a[key] - c[key]) <= 1.001e-4, (key, a[key], c[key])
+    # ragged groups take the per-group path
+    r = D.cal_metric([np.array([1., 0.]), np.array([0., 1., 0.])], [np.array([.3, .2]), np.array([.1, .5, .4])], ["mean_mrr", "hit@1"])
+    assert r == {"mean_mrr": 1.0, "hit@1": 1.0}
+    # log loss: the clipping list comprehension of DU:769 as np.clip
+    y, p = np.array([1., 0., 1., 0.]), np.array([1.0, 0.0, 0.7, 0.2], np.float32)
+    from sklearn.metrics import log_loss
+    want = round(log_loss(y, np.asarray([max(min(v, 1.0 - 10e-12), 10e-12) for v in p])), 4)
+    assert D.cal_metric(y, p, ["logloss"])["logloss"] == want
