@@ -433,7 +433,13 @@ def rooflines(w, tab, K, ms_per_step, pk, clk, workload):
         roof["algorithmic_bytes_per_launch"] = wk["byte"] / launches_per_step
         roof["algorithmic_flop_per_launch"] = wk["flop"] / launches_per_step
         roof["also"] = {"algorithmic_GB_per_s": gb, "hbm_frac": gb / pk["hbm"], "algorithmic_TFLOP_per_s": tf,
-                        "fp32_frac": tf / fp32_peak, "tensor_frac": tf / pk["tensor_sustained"]}
+                        "fp32_frac": tf / fp32_peak, "tensor_frac": tf / pk["tensor_sustained"],
+                        # an fp32-accurate product costs three TF32 MMAs, and TF32 runs at half the bf16 rate: the roof such a kernel
+                        # could reach at best
+                        "tf32x3_frac": tf / (pk["tensor_sustained"] / 6.0)}
+        if wk["pipe"] == "tensor":
+            roof["note"] = ("3xTF32 mma.sync (m16n8k8) kernel at d = 40: latency- and occupancy-bound, not peak-bound; ncu "
+                            "sm__pipe_tensor_cycles_active for this launch is in profiles/ (22.8 % for attn_bwd)")
     flop, byte = step_work(w)
     s_ = ms_per_step / 1e3
     roof_step = {"algorithmic_GB_per_step": byte / 1e9, "algorithmic_GFLOP_per_step": flop / 1e9, "GB_per_s": byte / s_ / 1e9,
