@@ -7,6 +7,7 @@ One "step" = one optimisation step (forward + losses + backward + per-tensor cli
 synthetic MX-TakaTak-shaped input.  Prints ONE JSON line (rank 0).  Keys: see DESIGN.md "Measurement".
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -304,26 +305,33 @@ def run_ours(args, w, rank, world):
     for i in range(max(W, 2 * N_POOL)):
         eng.train_step(resident[i % N_POOL])
     barrier()
-    for _ in range(400):                                            # at least one clock sample before the timed region;
-        have = torch.tensor([1 if clocks.rows else 0], device=dev)  # every rank takes the same number of extra warm-up steps
+    # A few clock samples before the timed region (every rank takes the same number of extra warm-up steps).  Not just one: the
+    # device stalls for several ms once while nvidia-smi attaches (seen as one 4 - 8 ms step right after its first line of output,
+    # never later: tools/step_jitter.py), which a 20-step timed region would carry as + 25 %.
+    for _ in range(3000):
+        have = torch.tensor([1 if len(clocks.rows) >= 3 else 0], device=dev)
         if world > 1:
             torch.distributed.all_reduce(have, op=torch.distributed.ReduceOp.MIN)
         if int(have.item()):
             break
         eng.train_step(resident[0])
         torch.cuda.synchronize()
+    # the events exist before the timed region and the collector is off inside it: a host pause between the record of a step's start
+    # and its launch would be charged to the device (the stream only runs ahead of the host after the first few steps)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    gc.collect()
+    gc.disable()
     barrier()
-    evs = []
     t_wall0 = time.perf_counter()
     for i in range(K):
         flush.fill_(i & 0xFF)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a, b = evs[i]
         a.record()
         eng.train_step(resident[i % N_POOL])
         b.record()
-        evs.append((a, b))
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    gc.enable()
     step_ms = [a.elapsed_time(b) for a, b in evs]
     step_sorted = sorted(step_ms)
     launches = eng.launches()
