@@ -273,6 +273,18 @@ def hbm_microbench(pk, dev):
     return out
 
 
+def settle_sampler(clocks, dev, world, step):
+    """Extra un-timed steps until the clock sampler has delivered three samples (the same number of steps on every rank)."""
+    for _ in range(3000):
+        have = torch.tensor([1 if len(clocks.rows) >= 3 else 0], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(have, op=torch.distributed.ReduceOp.MIN)
+        if int(have.item()):
+            break
+        step()
+        torch.cuda.synchronize()
+
+
 def run_ours(args, w, rank, world):
     from pamrec_b200 import synth
     pk = peaks()
@@ -308,14 +320,7 @@ def run_ours(args, w, rank, world):
     # A few clock samples before the timed region (every rank takes the same number of extra warm-up steps).  Not just one: the
     # device stalls for several ms once while nvidia-smi attaches (seen as one 4 - 8 ms step right after its first line of output,
     # never later: tools/step_jitter.py), which a 20-step timed region would carry as + 25 %.
-    for _ in range(3000):
-        have = torch.tensor([1 if len(clocks.rows) >= 3 else 0], device=dev)
-        if world > 1:
-            torch.distributed.all_reduce(have, op=torch.distributed.ReduceOp.MIN)
-        if int(have.item()):
-            break
-        eng.train_step(resident[0])
-        torch.cuda.synchronize()
+    settle_sampler(clocks, dev, world, lambda: eng.train_step(resident[0]))
     # the events exist before the timed region and the collector is off inside it: a host pause between the record of a step's start
     # and its launch would be charged to the device (the stream only runs ahead of the host after the first few steps)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -501,14 +506,15 @@ def run_score(args, w, rank, world):
     for i in range(W):
         eng.forward(resident[i % N_POOL], training=False)
     barrier()
-    evs = []
+    settle_sampler(clocks, dev, world, lambda: eng.forward(resident[0], training=False))
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
     for i in range(K):
         flush.fill_(i & 0xFF)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a, b = evs[i]
         a.record()
         eng.forward(resident[i % N_POOL], training=False)
         b.record()
-        evs.append((a, b))
     barrier()
     launches = eng.launches()
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
