@@ -8,7 +8,9 @@
 // per-user warm-up lengths, so the RNG call sequence of the reference (IT:545, IT:622) is untouched.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../include/pamrec_b200.h"
@@ -41,6 +43,8 @@ struct PamrecBatcher_ {
   int64_t eval_line = 0;
   int min_seq = 1;
   bool training = false, active = false;
+  std::vector<int64_t> eval_jobs;
+  int n_threads = 1;                          // threads that fill the history arrays of an evaluation batch (PAMREC_BATCHER_THREADS)
 
   // io/sequential_iterator.py:43-53 with numpy.searchsorted(side="right") semantics (NaN sorts last)
   int lisan(double x) const {
@@ -150,6 +154,11 @@ int pamrec_batcher_create(const PamrecLines* lines, const double* borders, int n
   b->L = *lines;
   b->borders.assign(borders, borders + n_borders);
   b->T = max_seq_len;
+  {
+    const char* e = getenv("PAMREC_BATCHER_THREADS");
+    int nt = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+    b->n_threads = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
+  }
   *out = b;
   return 0;
 }
@@ -248,6 +257,10 @@ int next_impl(PamrecBatcher b, int batch_size, int world, int rank, void* const*
       }
     }
   } else {
+    // The lines of an evaluation pass are independent (no history state, IT:375-474): the per-line scalars are written here, the
+    // T-long history arrays of the batch's rows - the expensive part - by a few threads over disjoint rows afterwards.
+    std::vector<int64_t>& jobs = b->eval_jobs;                 // line of the k-th row written by this call
+    jobs.clear();
     while (rows < batch_size && b->eval_line < L.n_lines) {
       const int64_t ln = b->eval_line++;
       const int64_t lo = L.offsets[ln], hi = L.offsets[ln + 1];
@@ -262,10 +275,26 @@ int next_impl(PamrecBatcher b, int batch_size, int world, int rank, void* const*
       o.users[r] = (float)L.user_ids[ln];
       o.items[r] = L.tgt_item[ln]; o.cates[r] = L.tgt_cate[ln];
       o.durations[r] = (float)L.tgt_dur[ln];
-      write_history(*b, o, r, 1, hi - lo, [&](int64_t k) { return L.items[lo + k]; }, [&](int64_t k) { return L.cates[lo + k]; },
-                    [&](int which, int64_t k) { return which == 0 ? L.durs[lo + k] : (which == 1 ? L.sats[lo + k] : L.plays[lo + k]); });
+      jobs.push_back(ln);
       rows += 1;
       local += 1;
+    }
+    auto run = [&](int64_t r0, int64_t r1) {
+      for (int64_t r = r0; r < r1; ++r) {
+        const int64_t lo = L.offsets[jobs[(size_t)r]], hi = L.offsets[jobs[(size_t)r] + 1];
+        write_history(*b, o, r, 1, hi - lo, [&](int64_t k) { return L.items[lo + k]; }, [&](int64_t k) { return L.cates[lo + k]; },
+                      [&](int which, int64_t k) { return which == 0 ? L.durs[lo + k] : (which == 1 ? L.sats[lo + k] : L.plays[lo + k]); });
+      }
+    };
+    const int64_t n = (int64_t)jobs.size();
+    int nt = b->n_threads;
+    if (n < 512) nt = 1;                                       // not worth the thread start-up
+    if (nt <= 1) run(0, n);
+    else {
+      std::vector<std::thread> pool;
+      for (int i = 1; i < nt; ++i) pool.emplace_back(run, n * i / nt, n * (i + 1) / nt);
+      run(0, n / nt);
+      for (auto& th : pool) th.join();
     }
   }
   if (rows == 0) b->active = false;

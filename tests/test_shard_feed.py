@@ -154,3 +154,31 @@ def test_two_ranks_run_the_model_loops_on_their_share(tmp_path, lib_built):
         for (gb, items, hist), (_, items1, hist1) in zip(seen, seen1):
             rows = D.group_rows(len(items1), world, rank)
             assert gb == len(items1) and np.array_equal(items, items1[rows]) and np.array_equal(hist, hist1[rows])
+
+
+@pytest.mark.parametrize("shard", [None, (3, 1)])
+def test_eval_batches_are_the_same_with_one_or_several_batcher_threads(shard, monkeypatch, lib_built):
+    """The native batcher fills the history arrays of a large evaluation batch with several threads over disjoint rows
+    (csrc/batcher.cu, PAMREC_BATCHER_THREADS): every one of the 19 arrays is identical to the single-threaded result."""
+    from pamrec_b200 import synth
+    case = list(G.CASES)[0]
+    with tempfile.TemporaryDirectory() as tmp:
+        data_dir = G.synth_case(case, tmp)
+        hp = G.hparams_for(case, data_dir)
+        hp.batch_size = 1500                                                       # above the 512-row threshold of the threaded path
+        path = os.path.join(tmp, "big_eval")
+        T = hp.max_seq_length
+        n_users, n_items, n_cates = (len(IT.load_dict(p)) for p in (hp.user_vocab, hp.item_vocab, hp.cate_vocab))
+        synth.write_eval_file(path, 40, 99, T, n_users, n_items, n_cates, seed=3)   # 4 000 lines: 2 full batches + a tail
+
+        def run(threads):
+            monkeypatch.setenv("PAMREC_BATCHER_THREADS", str(threads))
+            it = IT.SequentialIterator(hp, None)
+            it.shard = shard
+            return list(it.load_data_from_file(path, min_seq_length=1))
+        one, four = run(1), run(4)
+        assert len(one) == len(four) == 3
+        for a, b in zip(one, four):
+            assert list(a) == list(b)
+            for k in a:
+                assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k], equal_nan=True), k
