@@ -45,6 +45,7 @@ struct PamrecBatcher_ {
   bool training = false, active = false;
   std::vector<int64_t> eval_jobs;
   int n_threads = 1;                          // threads that fill the history arrays of an evaluation batch (PAMREC_BATCHER_THREADS)
+  int n_cores = 1;
 
   // io/sequential_iterator.py:43-53 with numpy.searchsorted(side="right") semantics (NaN sorts last)
   int lisan(double x) const {
@@ -156,8 +157,10 @@ int pamrec_batcher_create(const PamrecLines* lines, const double* borders, int n
   b->T = max_seq_len;
   {
     const char* e = getenv("PAMREC_BATCHER_THREADS");
-    int nt = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+    const int hw = (int)std::thread::hardware_concurrency();
+    int nt = e ? atoi(e) : hw;
     b->n_threads = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
+    b->n_cores = e ? 1 << 20 : (hw < 1 ? 1 : hw);             // an explicit thread count is taken as given
   }
   *out = b;
   return 0;
@@ -288,7 +291,8 @@ int next_impl(PamrecBatcher b, int batch_size, int world, int rank, void* const*
     };
     const int64_t n = (int64_t)jobs.size();
     int nt = b->n_threads;
-    if (n < 512) nt = 1;                                       // not worth the thread start-up
+    if (world > 1 && b->n_cores / world < nt) nt = b->n_cores / world;   // one process per GPU: the ranks share the host's cores
+    if (n < 512 || nt < 1) nt = 1;                             // not worth the thread start-up
     if (nt <= 1) run(0, n);
     else {
       std::vector<std::thread> pool;
